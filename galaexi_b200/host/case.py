@@ -1,0 +1,74 @@
+"""Assemble everything the Fortran host hands to the hot path at init time.
+
+In the reference this is the sequence InitInterpolation -> InitMesh -> InitEquation -> InitDG ->
+InitLifting -> InitTimeDisc (src/flexilib.f90:188-214); the result is the set of module-global arrays
+that `DGTimeDerivative_weakForm` reads. Here the same arrays are collected in a
+`Case` whose buffers are in the reference's memory layout, ready to be passed through the C ABI
+(include/dgx.h) by the Python driver that stands in for the Fortran host.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import basis as bs
+from . import equation as eq
+from . import mappings as mp
+from . import mesh as ms
+from . import metrics as mt
+from . import timedisc as td
+
+SPLIT_IDS = {None: -1, "NONE": -1, "SD": 0, "MO": 1, "DU": 2, "KG": 3, "PI": 4}      # SPLIT_DG
+RIEMANN_IDS = {"LF": 0, "ROE": 1, "ROEL2": 2, "ROEENTROPYFIX": 3, "HLL": 4, "HLLC": 5, "HLLE": 6, "HLLEM": 7}
+
+
+@dataclass
+class Case:
+    N: int
+    node_type: str
+    basis: bs.DGBasis
+    mesh: ms.Mesh
+    geo: dict
+    maps: dict
+    eos: eq.Eos
+    RefStatePrim: np.ndarray
+    BCSides: np.ndarray
+    timedisc: td.TimeDisc
+    split: int
+    riemann: int
+    parabolic: bool
+    hopr: dict = field(repr=False, default=None)
+
+    @property
+    def n(self):
+        return self.N + 1
+
+    @property
+    def nDOF(self):
+        return self.mesh.nElems * self.n ** 3
+
+
+def build_case(hopr: dict, N: int, node_type: str = bs.NODETYPE_GL, split: str | None = "PI",
+               riemann: str = "RoeEntropyFix", parabolic: bool = True, eos: eq.Eos | None = None,
+               refstates=((1.0, 1.0, 0.0, 0.0, 17194.8345650329),), user_bcs: dict | None = None,
+               nProcs: int = 1, myRank: int = 0, timedisc: str = "carpenterrk4-5", CFLScale: float = 0.9,
+               DFLScale: float = 0.9, useCurveds: bool = True, crossProductMetrics: bool = False) -> Case:
+    eos = eos or eq.Eos()
+    node_type = node_type.upper()
+    split_id = SPLIT_IDS[split.upper() if isinstance(split, str) else split]
+    riem_id = RIEMANN_IDS[riemann.upper()]
+    if split_id >= 0 and node_type != bs.NODETYPE_GL:
+        # splitflux.f90:116-119
+        raise ValueError("Wrong Pointset: Gauss-Lobatto-Points are mandatory for using SplitDG !")
+    if split_id >= 0 and riem_id in (4, 5, 6, 7):
+        # src/CMakeLists.txt:108-127
+        raise ValueError("HLL-type Riemann solvers are not available with SplitDG")
+    basis = bs.init_dg_basis(N, node_type)
+    mesh = ms.prepare_mesh(hopr, nProcs=nProcs, myRank=myRank, useCurveds=useCurveds, user_bcs=user_bcs)
+    geo = mt.calc_metrics(mesh, N, node_type, crossProductMetrics=crossProductMetrics, hopr=hopr)
+    maps = mp.build_mappings(N)
+    refprim = eq.refstate_prim(refstates, eos)
+    bcs = eq.bc_sides(mesh)
+    tdisc = td.set_timedisc(timedisc, N, node_type, CFLScale, DFLScale)
+    return Case(N, node_type, basis, mesh, geo, maps, eos, refprim, bcs, tdisc, split_id, riem_id, bool(parabolic), hopr)

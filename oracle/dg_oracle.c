@@ -1,0 +1,975 @@
+/*
+ * dg_oracle.c -- CPU restatement of GALAEXI's DGSEM right-hand side + low-storage RK stage.
+ *
+ * TEST INFRASTRUCTURE ONLY. This file is the parity oracle for the CUDA library in galaexi_b200/csrc.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may build,
+ * load or call it. The product path never routes through it.
+ *
+ * The reference (flexi-framework/galaexi @1119a65, CUDA Fortran) cannot be compiled in this
+ * environment (needs nvfortran + HDF5 + MPI), so this is a plain-C restatement of its arithmetic in the
+ * reference's own array layout (variable index fastest, U(nVar,i,j,k,iElem)) and operation order.
+ * Every routine cites the reference file:line it follows (paths relative to /root/reference/src).
+ *
+ * Pinned against (tests/test_oracle_goldens.py): unitTests/ProlongToFace_{G,GL}3D.bin,
+ * unitTests/SurfInt_{G,GL}3D.bin (100 eps), regressioncheck tgv/split CSV rows 1-2 (IC gradients,
+ * first dt, kinetic energy after one RK step), parabolic/cavity_3D reference state.
+ *
+ * Scope of the restatement: 3D, conforming meshes, PP_nVar=5, PP_nVarPrim=6, PP_nVarLifting=5
+ * (PP_OPTLIFT=0), BR1 lifting in strong non-conservative form (the GALAEXI defaults, lifting.f90:81-85),
+ * node types Gauss / Gauss-Lobatto, weak form or split form (SD, KG, PI), Riemann solvers LF, Roe,
+ * RoeEntropyFix, HLLC, constant or Sutherland viscosity, BC types 2, 3, 4, 9.
+ *
+ * OpenMP over elements / sides is only used to time the CPU baseline on all host cores; results do not
+ * depend on the thread count (every loop iteration owns its outputs, as in the reference's gather kernels).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+
+#define NV 5   /* PP_nVar        */
+#define NP 6   /* PP_nVarPrim    */
+#define NL 5   /* PP_nVarLifting */
+
+/* eos.h index macros, 0-based */
+enum { DENS = 0, MOM1, MOM2, MOM3, ENER };
+enum { VEL1 = 1, VEL2, VEL3, PRES, TEMP };
+static const int PRIM_LIFT[NL] = {0, 1, 2, 3, 5}; /* eos.h:143 */
+enum { LIFT_DENS = 0, LIFT_VEL1, LIFT_VEL2, LIFT_VEL3, LIFT_TEMP };
+/* extended state U_LL/U_RR (eos.h:116-131): cons 0..4, then sRho, vel1..3, pres, temp */
+enum { E_DENS = 0, E_MOM1, E_MOM2, E_MOM3, E_ENER, E_SRHO, E_VEL1, E_VEL2, E_VEL3, E_PRES, E_TEMP, NEXT };
+enum { EOS_KAPPA = 0, EOS_R, EOS_PR, EOS_MU0, EOS_TS, EOS_TREF, EOS_EXPOSUTH, EOS_CSUTH };
+
+/* local sides, flexi.h:97-102 */
+enum { ZETA_MINUS = 1, ETA_MINUS = 2, XI_PLUS = 3, ETA_PLUS = 4, XI_MINUS = 5, ZETA_PLUS = 6 };
+
+typedef struct {
+    int N, nElems, nSides;
+    int nBCSides, firstInnerSide, lastInnerSide;
+    int firstMPISide_MINE, lastMPISide_MINE, firstMPISide_YOUR, lastMPISide_YOUR;
+    int nodeType;  /* 1 Gauss, 2 Gauss-Lobatto (PP_NodeType) */
+    int splitDG;   /* -1 off; 0 SD, 3 KG, 4 PI (SPLIT_DG) */
+    int riemann;   /* 0 LF, 1 Roe, 3 RoeEntropyFix, 5 HLLC (RIEMANN) */
+    int parabolic; /* PARABOLIC */
+    int viscLaw;   /* PP_VISC: 0 constant, 1 Sutherland */
+    int nRefState;
+    double EOS[8];
+    /* operators, Fortran column-major (0:N,0:N): M(a,b) at [a + n*b] */
+    const double *D_T, *D_Hat_T, *DVolSurf, *L_Minus, *L_Plus, *L_HatMinus, *L_HatPlus;
+    /* mesh tables (Fortran memory) */
+    const int *ElemToSide;  /* (3,6,nElems) */
+    const int *S2V2;        /* (2,0:N,0:N,0:4,1:6) */
+    const int *S2V2_inv;
+    const int *BCSides;     /* (2,nBCSides): BC_TYPE, BC_STATE */
+    const double *Metrics_fTilde, *Metrics_gTilde, *Metrics_hTilde; /* (3,n,n,n,nElems) */
+    const double *sJ;       /* (n,n,n,nElems) */
+    const double *NormVec, *TangVec1, *TangVec2; /* (3,n,n,nSides) */
+    const double *SurfElem; /* (n,n,nSides) */
+    const double *RefStatePrim; /* (6,nRefState) */
+} dgo_config;
+
+typedef struct {
+    dgo_config c;
+    int n, n2, n3;
+    size_t nDOF, nFace;
+    double *U, *Ut, *UPrim, *Ut_tmp;
+    double *U_master, *U_slave, *UPrim_master, *UPrim_slave, *Flux_master, *Flux_slave;
+    double *gradUx, *gradUy, *gradUz;
+    double *gradUx_master, *gradUy_master, *gradUz_master, *gradUx_slave, *gradUy_slave, *gradUz_slave;
+    double *f, *g, *h;
+    double *MetricsAdv, *MetricsVisc;
+} dgo;
+
+#define IDX_VOL(s, nv, v, i, j, k, e) ((size_t)(v) + (size_t)(nv) * ((size_t)(i) + (s)->n * ((size_t)(j) + (s)->n * ((size_t)(k) + (size_t)(s)->n * (size_t)(e)))))
+#define IDX_FACE(s, nv, v, p, q, sd) ((size_t)(v) + (size_t)(nv) * ((size_t)(p) + (s)->n * ((size_t)(q) + (size_t)(s)->n * (size_t)(sd))))
+
+static inline int s2v2(const int *tab, int n, int c, int p, int q, int flip, int loc)
+{ /* S2V2(c,p,q,flip,loc) with c in 1..2, loc in 1..6 */
+    return tab[(c - 1) + 2 * (p + n * (q + n * (flip + 5 * (loc - 1))))];
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* equations/navierstokes/idealgas/eos.f90:212-239 ConsToPrim */
+static inline void cons_to_prim(double *prim, const double *cons, double kappa, double R)
+{
+    double sRho = 1. / cons[DENS];
+    prim[DENS] = cons[DENS];
+    prim[VEL1] = cons[MOM1] * sRho;
+    prim[VEL2] = cons[MOM2] * sRho;
+    prim[VEL3] = cons[MOM3] * sRho;
+    prim[PRES] = (kappa - 1.) * (cons[ENER] - 0.5 * (cons[MOM1] * prim[VEL1] + cons[MOM2] * prim[VEL2] + cons[MOM3] * prim[VEL3]));
+    prim[TEMP] = prim[PRES] * sRho / R;
+}
+/* eos.f90:467-489 PrimToCons */
+static inline void prim_to_cons(const double *prim, double *cons, double kappa)
+{
+    cons[DENS] = prim[DENS];
+    cons[MOM1] = prim[VEL1] * prim[DENS];
+    cons[MOM2] = prim[VEL2] * prim[DENS];
+    cons[MOM3] = prim[VEL3] * prim[DENS];
+    cons[ENER] = prim[PRES] / (kappa - 1.) + 0.5 * (cons[MOM1] * prim[VEL1] + cons[MOM2] * prim[VEL2] + cons[MOM3] * prim[VEL3]);
+}
+/* idealgas/viscosity.f90 muSuth + eos.h:89-110 VISCOSITY_PRIM_EOS / THERMAL_CONDUCTIVITY_EOS */
+static inline double viscosity(const dgo_config *c, const double *prim)
+{
+    if (c->viscLaw == 0) return c->EOS[EOS_MU0];
+    /* viscosity.f90:105: TnoDim=T*Tref; IF(TnoDim >= Ts) mu0*TnoDim**ExpoSuth*(1+Ts)/(TnoDim+Ts) ELSE mu0*TnoDim*cSuth */
+    double Tn = prim[TEMP] * c->EOS[EOS_TREF];
+    double Ts = c->EOS[EOS_TS];
+    if (Tn >= Ts) return c->EOS[EOS_MU0] * pow(Tn, c->EOS[EOS_EXPOSUTH]) * (1. + Ts) / (Tn + Ts);
+    return c->EOS[EOS_MU0] * Tn * c->EOS[EOS_CSUTH];
+}
+static inline double conductivity(const dgo_config *c, double mu)
+{
+    return mu * c->EOS[EOS_R] * c->EOS[EOS_KAPPA] / ((c->EOS[EOS_KAPPA] - 1.) * c->EOS[EOS_PR]);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* interpolation/prolongtoface.t90:168-344 EvalElemFaceG_Device / EvalElemFaceGL_Device
+ * (one thread per (elem, locSide, p, q); routes to master (flip==0) or slave) */
+static void prolong_to_face(const dgo *s, int nVar, const double *Uvol, double *Um, double *Us)
+{
+    const dgo_config *c = &s->c;
+    const int n = s->n, N = c->N;
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < c->nElems; e++)
+        for (int loc = 1; loc <= 6; loc++) {
+            int SideID = c->ElemToSide[0 + 3 * ((loc - 1) + 6 * e)];
+            int flip = c->ElemToSide[1 + 3 * ((loc - 1) + 6 * e)];
+            double *dst = (flip == 0) ? Um : Us;
+            for (int q = 0; q < n; q++)
+                for (int p = 0; p < n; p++) {
+                    int i = s2v2(c->S2V2, n, 1, p, q, flip, loc);
+                    int j = s2v2(c->S2V2, n, 2, p, q, flip, loc);
+                    double Uface[8];
+                    if (c->nodeType == 2) {
+                        for (int v = 0; v < nVar; v++) {
+                            switch (loc) {
+                            case XI_MINUS:   Uface[v] = Uvol[IDX_VOL(s, nVar, v, 0, i, j, e)]; break;
+                            case ETA_MINUS:  Uface[v] = Uvol[IDX_VOL(s, nVar, v, i, 0, j, e)]; break;
+                            case ZETA_MINUS: Uface[v] = Uvol[IDX_VOL(s, nVar, v, i, j, 0, e)]; break;
+                            case XI_PLUS:    Uface[v] = Uvol[IDX_VOL(s, nVar, v, N, i, j, e)]; break;
+                            case ETA_PLUS:   Uface[v] = Uvol[IDX_VOL(s, nVar, v, i, N, j, e)]; break;
+                            default:         Uface[v] = Uvol[IDX_VOL(s, nVar, v, i, j, N, e)]; break;
+                            }
+                        }
+                    } else {
+                        const double *L = (loc == XI_MINUS || loc == ETA_MINUS || loc == ZETA_MINUS) ? c->L_Minus : c->L_Plus;
+                        for (int v = 0; v < nVar; v++) {
+                            double a = 0.;
+                            for (int l = 0; l < n; l++) {
+                                double u;
+                                switch (loc) {
+                                case XI_MINUS: case XI_PLUS:   u = Uvol[IDX_VOL(s, nVar, v, l, i, j, e)]; break;
+                                case ETA_MINUS: case ETA_PLUS: u = Uvol[IDX_VOL(s, nVar, v, i, l, j, e)]; break;
+                                default:                       u = Uvol[IDX_VOL(s, nVar, v, i, j, l, e)]; break;
+                                }
+                                a = (l == 0) ? u * L[0] : a + u * L[l];
+                            }
+                            Uface[v] = a;
+                        }
+                    }
+                    for (int v = 0; v < nVar; v++) dst[IDX_FACE(s, nVar, v, p, q, SideID - 1)] = Uface[v];
+                }
+        }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* dg/surfint.t90:352-586 SurfInt_Device (two fluxes, slave gets -Flux_slave) and :591-725
+ * SurfInt_Device_Single_Flux (lifting; strong form: sig=+1, weak: sig = 2*isMaster-1), incl. optional sJ */
+static void surf_int(const dgo *s, int nVar, const double *Fm, const double *Fs, double *Ut, int single, int weak, int applyJac)
+{
+    const dgo_config *c = &s->c;
+    const int n = s->n, N = c->N;
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < c->nElems; e++)
+        for (int k = 0; k < n; k++) for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) {
+            double loc_[8];
+            for (int v = 0; v < nVar; v++) loc_[v] = 0.;
+            for (int loc = 1; loc <= 6; loc++) {
+                int SideID = c->ElemToSide[0 + 3 * ((loc - 1) + 6 * e)];
+                int flip = c->ElemToSide[1 + 3 * ((loc - 1) + 6 * e)];
+                int isM = c->ElemToSide[2 + 3 * ((loc - 1) + 6 * e)];
+                int a, b, l; double Lh; int minus;
+                switch (loc) {
+                case XI_MINUS:   a = j; b = k; l = i; minus = 1; break;
+                case ETA_MINUS:  a = i; b = k; l = j; minus = 1; break;
+                case ZETA_MINUS: a = i; b = j; l = k; minus = 1; break;
+                case XI_PLUS:    a = j; b = k; l = i; minus = 0; break;
+                case ETA_PLUS:   a = i; b = k; l = j; minus = 0; break;
+                default:         a = i; b = j; l = k; minus = 0; break;
+                }
+                if (c->nodeType == 2) { /* collocation: only the boundary layer contributes */
+                    if (minus ? (l != 0) : (l != N)) continue;
+                    Lh = minus ? c->L_HatMinus[0] : c->L_HatPlus[N];
+                } else {
+                    Lh = minus ? c->L_HatMinus[l] : c->L_HatPlus[l];
+                }
+                int p = s2v2(c->S2V2_inv, n, 1, a, b, flip, loc);
+                int q = s2v2(c->S2V2_inv, n, 2, a, b, flip, loc);
+                if (single) {
+                    double sig = weak ? (2. * (double)isM - 1.) : 1.;
+                    for (int v = 0; v < nVar; v++) loc_[v] = loc_[v] + sig * Fm[IDX_FACE(s, nVar, v, p, q, SideID - 1)] * Lh;
+                } else if (flip == 0) {
+                    for (int v = 0; v < nVar; v++) loc_[v] = loc_[v] + Fm[IDX_FACE(s, nVar, v, p, q, SideID - 1)] * Lh;
+                } else {
+                    for (int v = 0; v < nVar; v++) loc_[v] = loc_[v] - Fs[IDX_FACE(s, nVar, v, p, q, SideID - 1)] * Lh;
+                }
+            }
+            for (int v = 0; v < nVar; v++) {
+                size_t id = IDX_VOL(s, nVar, v, i, j, k, e);
+                if (applyJac) Ut[id] = c->sJ[i + n * (j + n * (k + (size_t)n * e))] * (Ut[id] + loc_[v]);
+                else Ut[id] = Ut[id] + loc_[v];
+            }
+        }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* BCs: idealgas/eos.f90:605-628 PRESSURE_RIEMANN_PURE */
+static double pressure_riemann(const double *P, double kappa)
+{
+    double P_RP;
+    if (P[VEL1] <= 0.) {
+        double kf = 2. * kappa / (kappa - 1.);
+        P_RP = P[PRES] * pow(fmax(0.0001, (1. + 0.5 * (kappa - 1.) * P[VEL1] / sqrt(kappa * P[PRES] / P[DENS]))), kf);
+    } else {
+        double ar = 2. / ((kappa + 1.) * P[DENS]);
+        double br = (kappa - 1.) / (kappa + 1.) * P[PRES];
+        P_RP = P[PRES] + P[VEL1] / ar * 0.5 * (P[VEL1] + sqrt(P[VEL1] * P[VEL1] + 4. * ar * (P[PRES] + br)));
+    }
+    return P_RP;
+}
+/* idealgas/getboundaryflux.f90:262-487 GetBoundaryState, BC types 2,3,4,9 */
+static int get_boundary_state(const dgo_config *c, int BCType, double *out, const double *Pm, const double *Ref,
+                              const double *nv, const double *t1, const double *t2)
+{
+    double kappa = c->EOS[EOS_KAPPA], R = c->EOS[EOS_R];
+    if (BCType == 2) { for (int v = 0; v < NP; v++) out[v] = Ref[v]; return 0; }
+    if (BCType == 3 || BCType == 4 || BCType == 9) {
+        double b[NP];
+        b[DENS] = Pm[DENS];
+        b[VEL1] = Pm[VEL1] * nv[0] + Pm[VEL2] * nv[1] + Pm[VEL3] * nv[2];
+        b[VEL2] = Pm[VEL1] * t1[0] + Pm[VEL2] * t1[1] + Pm[VEL3] * t1[2];
+        b[VEL3] = Pm[VEL1] * t2[0] + Pm[VEL2] * t2[1] + Pm[VEL3] * t2[2];
+        b[PRES] = Pm[PRES];
+        b[TEMP] = Pm[TEMP];
+        if (BCType == 3) {
+            b[PRES] = pressure_riemann(b, kappa);
+            b[VEL1] = b[VEL2] = b[VEL3] = 0.;
+            b[TEMP] = Pm[TEMP];
+            b[DENS] = b[PRES] / (b[TEMP] * R);
+        } else if (BCType == 4) {
+            b[PRES] = pressure_riemann(b, kappa);
+            b[VEL1] = b[VEL2] = b[VEL3] = 0.;
+            b[TEMP] = Ref[TEMP];
+            b[DENS] = b[PRES] / (b[TEMP] * R);
+        } else {
+            b[PRES] = pressure_riemann(b, kappa);
+            b[VEL1] = 0.;
+            b[DENS] = Pm[DENS];
+            b[TEMP] = b[PRES] / (b[DENS] * R);
+        }
+        out[DENS] = b[DENS];
+        for (int d = 0; d < 3; d++) out[VEL1 + d] = b[VEL1] * nv[d] + b[VEL2] * t1[d] + b[VEL3] * t2[d];
+        out[PRES] = b[PRES];
+        out[TEMP] = b[TEMP];
+        return 0;
+    }
+    return 1;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* equations/navierstokes/splitflux.f90: surface fluxes :315 (SD) :627 (KG) :735 (PI) */
+static void split_surface_flux(int variant, const double *L, const double *R, double *F)
+{
+    if (variant == 0) {
+        F[DENS] = 0.5 * (L[E_MOM1] + R[E_MOM1]);
+        F[MOM1] = 0.5 * (L[E_MOM1] * L[E_VEL1] + L[E_PRES] + R[E_MOM1] * R[E_VEL1] + R[E_PRES]);
+        F[MOM2] = 0.5 * (L[E_MOM1] * L[E_VEL2] + R[E_MOM1] * R[E_VEL2]);
+        F[MOM3] = 0.5 * (L[E_MOM1] * L[E_VEL3] + R[E_MOM1] * R[E_VEL3]);
+        F[ENER] = 0.5 * ((L[E_ENER] + L[E_PRES]) * L[E_VEL1] + (R[E_ENER] + R[E_PRES]) * R[E_VEL1]);
+    } else if (variant == 3) {
+        double E_LL = L[E_ENER] / L[E_DENS], E_RR = R[E_ENER] / R[E_DENS];
+        F[DENS] = 0.25 * (L[E_DENS] + R[E_DENS]) * (L[E_VEL1] + R[E_VEL1]);
+        F[MOM1] = 0.125 * (L[E_DENS] + R[E_DENS]) * ((L[E_VEL1] + R[E_VEL1]) * (L[E_VEL1] + R[E_VEL1])) + 0.5 * (L[E_PRES] + R[E_PRES]);
+        F[MOM2] = 0.125 * (L[E_DENS] + R[E_DENS]) * (L[E_VEL1] + R[E_VEL1]) * (L[E_VEL2] + R[E_VEL2]);
+        F[MOM3] = 0.125 * (L[E_DENS] + R[E_DENS]) * (L[E_VEL1] + R[E_VEL1]) * (L[E_VEL3] + R[E_VEL3]);
+        F[ENER] = 0.125 * (L[E_DENS] + R[E_DENS]) * (E_LL + E_RR) * (L[E_VEL1] + R[E_VEL1]) +
+                  0.25 * (L[E_PRES] + R[E_PRES]) * (L[E_VEL1] + R[E_VEL1]);
+    } else { /* PI */
+        double H_LL = (L[E_ENER] + L[E_PRES]) / L[E_DENS], H_RR = (R[E_ENER] + R[E_PRES]) / R[E_DENS];
+        F[DENS] = 0.25 * (L[E_DENS] + R[E_DENS]) * (L[E_VEL1] + R[E_VEL1]);
+        F[MOM1] = 0.125 * (L[E_DENS] + R[E_DENS]) * ((L[E_VEL1] + R[E_VEL1]) * (L[E_VEL1] + R[E_VEL1])) + 0.5 * (L[E_PRES] + R[E_PRES]);
+        F[MOM2] = 0.125 * (L[E_DENS] + R[E_DENS]) * (L[E_VEL1] + R[E_VEL1]) * (L[E_VEL2] + R[E_VEL2]);
+        F[MOM3] = 0.125 * (L[E_DENS] + R[E_DENS]) * (L[E_VEL1] + R[E_VEL1]) * (L[E_VEL3] + R[E_VEL3]);
+        F[ENER] = 0.125 * (L[E_DENS] + R[E_DENS]) * (H_LL + H_RR) * (L[E_VEL1] + R[E_VEL1]);
+    }
+}
+
+/* splitflux.f90: volume two-point fluxes :145 (SD) :437 (KG) :669 (PI) */
+static void split_volume_flux(int variant, const double *URef, const double *PRef, const double *U, const double *P,
+                              const double *MRef, const double *M, double *Flux)
+{
+    double f[NV], g[NV], h[NV];
+    if (variant == 0) {
+        double rhoEpRef = URef[ENER] + PRef[PRES], rhoEp = U[ENER] + P[PRES];
+        f[DENS] = (URef[MOM1] + U[MOM1]);
+        f[MOM1] = (URef[MOM1] * PRef[VEL1] + PRef[PRES] + U[MOM1] * P[VEL1] + P[PRES]);
+        f[MOM2] = (URef[MOM1] * PRef[VEL2] + U[MOM1] * P[VEL2]);
+        f[MOM3] = (URef[MOM1] * PRef[VEL3] + U[MOM1] * P[VEL3]);
+        f[ENER] = (rhoEpRef * PRef[VEL1] + rhoEp * P[VEL1]);
+        g[DENS] = (URef[MOM2] + U[MOM2]);
+        g[MOM1] = (URef[MOM1] * PRef[VEL2] + U[MOM1] * P[VEL2]);
+        g[MOM2] = (URef[MOM2] * PRef[VEL2] + PRef[PRES] + U[MOM2] * P[VEL2] + P[PRES]);
+        g[MOM3] = (URef[MOM2] * PRef[VEL3] + U[MOM2] * P[VEL3]);
+        g[ENER] = (rhoEpRef * PRef[VEL2] + rhoEp * P[VEL2]);
+        h[DENS] = (URef[MOM3] + U[MOM3]);
+        h[MOM1] = (URef[MOM1] * PRef[VEL3] + U[MOM1] * P[VEL3]);
+        h[MOM2] = (URef[MOM2] * PRef[VEL3] + U[MOM2] * P[VEL3]);
+        h[MOM3] = (URef[MOM3] * PRef[VEL3] + PRef[PRES] + U[MOM3] * P[VEL3] + P[PRES]);
+        h[ENER] = (rhoEpRef * PRef[VEL3] + rhoEp * P[VEL3]);
+    } else {
+        double rs = URef[DENS] + U[DENS];
+        double us = PRef[VEL1] + P[VEL1], vs = PRef[VEL2] + P[VEL2], ws = PRef[VEL3] + P[VEL3];
+        double ps = PRef[PRES] + P[PRES];
+        f[DENS] = 0.5 * rs * us;
+        f[MOM1] = 0.25 * rs * (us * us) + ps;
+        f[MOM2] = 0.25 * rs * us * vs;
+        f[MOM3] = 0.25 * rs * us * ws;
+        g[DENS] = 0.5 * rs * vs;
+        g[MOM1] = f[MOM2];
+        g[MOM2] = 0.25 * rs * (vs * vs) + ps;
+        g[MOM3] = 0.25 * rs * vs * ws;
+        h[DENS] = 0.5 * rs * ws;
+        h[MOM1] = f[MOM3];
+        h[MOM2] = g[MOM3];
+        h[MOM3] = 0.25 * rs * (ws * ws) + ps;
+        if (variant == 3) { /* KG: {rho}{E}{u} + {p}{u} */
+            double eRef = URef[ENER] / URef[DENS], e = U[ENER] / U[DENS];
+            f[ENER] = 0.25 * rs * us * (eRef + e) + 0.5 * ps * us;
+            g[ENER] = 0.25 * rs * vs * (eRef + e) + 0.5 * ps * vs;
+            h[ENER] = 0.25 * rs * ws * (eRef + e) + 0.5 * ps * ws;
+        } else { /* PI: {rho}{H}{u} */
+            double HRef = (URef[ENER] + PRef[PRES]) / URef[DENS], H = (U[ENER] + P[PRES]) / U[DENS];
+            f[ENER] = 0.25 * rs * us * (HRef + H);
+            g[ENER] = 0.25 * rs * vs * (HRef + H);
+            h[ENER] = 0.25 * rs * ws * (HRef + H);
+        }
+    }
+    for (int v = 0; v < NV; v++)
+        Flux[v] = 0.5 * (MRef[0] + M[0]) * f[v] + 0.5 * (MRef[2] + M[2]) * h[v] + 0.5 * (MRef[1] + M[1]) * g[v];
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* riemann.f90: solvers :707 LF, :738 HLLC, :809 Roe, :885 RoeEntropyFix */
+static void roe_averages(const double *L, const double *R, double kappa, double *RoeVel, double *RoeH, double *Roec, double *absVel)
+{
+    double H_L = (L[E_ENER] + L[E_PRES]) * L[E_SRHO];
+    double H_R = (R[E_ENER] + R[E_PRES]) * R[E_SRHO];
+    double sl = sqrt(L[E_DENS]), sr = sqrt(R[E_DENS]);
+    double ss = 1. / (sl + sr);
+    for (int d = 0; d < 3; d++) RoeVel[d] = (sr * R[E_VEL1 + d] + sl * L[E_VEL1 + d]) * ss;
+    *RoeH = (sr * H_R + sl * H_L) * ss;
+    *absVel = RoeVel[0] * RoeVel[0] + RoeVel[1] * RoeVel[1] + RoeVel[2] * RoeVel[2];
+    *Roec = sqrt((kappa - 1.) * (*RoeH - 0.5 * (*absVel)));
+}
+
+static void riemann_solver(const dgo_config *c, double *F, const double *F_L, const double *F_R, const double *L, const double *R)
+{
+    const double kappa = c->EOS[EOS_KAPPA];
+    const int split = c->splitDG >= 0;
+    if (c->riemann == 0) { /* LF */
+        double cL = sqrt(kappa * L[E_PRES] * L[E_SRHO]), cR = sqrt(kappa * R[E_PRES] * R[E_SRHO]);
+        double LambdaMax = fmax(fabs(R[E_VEL1]), fabs(L[E_VEL1])) + fmax(cL, cR);
+        if (!split) {
+            for (int v = 0; v < NV; v++) F[v] = 0.5 * ((F_L[v] + F_R[v]) - LambdaMax * (R[v] - L[v]));
+        } else {
+            split_surface_flux(c->splitDG, L, R, F);
+            for (int v = 0; v < NV; v++) F[v] = F[v] - 0.5 * LambdaMax * (R[v] - L[v]);
+        }
+        return;
+    }
+    if (c->riemann == 5) { /* HLLC (non-split builds only, CMakeLists.txt:113-117) */
+        double RoeVel[3], RoeH, Roec, absVel;
+        roe_averages(L, R, kappa, RoeVel, &RoeH, &Roec, &absVel);
+        double Ssl = RoeVel[0] - Roec, Ssr = RoeVel[0] + Roec;
+        if (Ssl >= 0.) { for (int v = 0; v < NV; v++) F[v] = F_L[v]; }
+        else if (Ssr <= 0.) { for (int v = 0; v < NV; v++) F[v] = F_R[v]; }
+        else {
+            double sMu_L = Ssl - L[E_VEL1], sMu_R = Ssr - R[E_VEL1];
+            double SStar = (R[E_PRES] - L[E_PRES] + L[E_MOM1] * sMu_L - R[E_MOM1] * sMu_R) / (L[E_DENS] * sMu_L - R[E_DENS] * sMu_R);
+            double Us[NV];
+            if (Ssl <= 0. && SStar >= 0.) {
+                double EStar = L[E_ENER] * L[E_SRHO] + (SStar - L[E_VEL1]) * (SStar + L[E_PRES] * L[E_SRHO] / sMu_L);
+                double fac = L[E_DENS] * sMu_L / (Ssl - SStar);
+                Us[0] = fac * 1.; Us[1] = fac * SStar; Us[2] = fac * L[E_VEL2]; Us[3] = fac * L[E_VEL3]; Us[4] = fac * EStar;
+                for (int v = 0; v < NV; v++) F[v] = F_L[v] + Ssl * (Us[v] - L[v]);
+            } else {
+                double EStar = R[E_ENER] * R[E_SRHO] + (SStar - R[E_VEL1]) * (SStar + R[E_PRES] * R[E_SRHO] / sMu_R);
+                double fac = R[E_DENS] * sMu_R / (Ssr - SStar);
+                Us[0] = fac * 1.; Us[1] = fac * SStar; Us[2] = fac * R[E_VEL2]; Us[3] = fac * R[E_VEL3]; Us[4] = fac * EStar;
+                for (int v = 0; v < NV; v++) F[v] = F_R[v] + Ssr * (Us[v] - R[v]);
+            }
+        }
+        return;
+    }
+    /* Roe family */
+    double RoeVel[3], RoeH, Roec, absVel;
+    roe_averages(L, R, kappa, RoeVel, &RoeH, &Roec, &absVel);
+    double a[5] = {RoeVel[0] - Roec, RoeVel[0], RoeVel[0], RoeVel[0], RoeVel[0] + Roec};
+    double r1[5] = {1., a[0], RoeVel[1], RoeVel[2], RoeH - RoeVel[0] * Roec};
+    double r2[5] = {1., RoeVel[0], RoeVel[1], RoeVel[2], 0.5 * absVel};
+    double r3[5] = {0., 0., 1., 0., RoeVel[1]};
+    double r4[5] = {0., 0., 0., 1., RoeVel[2]};
+    double r5[5] = {1., a[4], RoeVel[1], RoeVel[2], RoeH + RoeVel[0] * Roec};
+    double Alpha[5];
+    if (c->riemann == 1) { /* Roe :809-877 */
+        double dU[6];
+        for (int v = 0; v < NV; v++) dU[v] = R[v] - L[v];
+        dU[5] = dU[4] - (dU[2] - RoeVel[1] * dU[0]) * RoeVel[1] - (dU[3] - RoeVel[2] * dU[0]) * RoeVel[2];
+        Alpha[2] = dU[2] - RoeVel[1] * dU[0];
+        Alpha[3] = dU[3] - RoeVel[2] * dU[0];
+        Alpha[1] = (kappa - 1.) / (Roec * Roec) * (dU[0] * (RoeH - RoeVel[0] * RoeVel[0]) - dU[5] + RoeVel[0] * dU[1]);
+        Alpha[0] = 0.5 / Roec * (dU[0] * (RoeVel[0] + Roec) - dU[1] - Roec * Alpha[1]);
+        Alpha[4] = dU[0] - Alpha[0] - Alpha[1];
+        for (int i = 0; i < 5; i++) a[i] = fabs(a[i]);
+    } else { /* RoeEntropyFix :885-986 */
+        double c_L = sqrt(kappa * L[E_PRES] * L[E_SRHO]), c_R = sqrt(kappa * R[E_PRES] * R[E_SRHO]);
+        double RoeDens = sqrt(L[E_DENS] * R[E_DENS]);
+        double dU[5];
+        dU[0] = R[E_DENS] - L[E_DENS];
+        dU[1] = R[E_VEL1] - L[E_VEL1]; dU[2] = R[E_VEL2] - L[E_VEL2]; dU[3] = R[E_VEL3] - L[E_VEL3];
+        dU[4] = R[E_PRES] - L[E_PRES];
+        double tmp = 0.5 / (Roec * Roec);
+        Alpha[0] = tmp * (dU[4] - RoeDens * Roec * dU[1]);
+        Alpha[1] = dU[0] - dU[4] * 2. * tmp;
+        Alpha[2] = RoeDens * dU[2];
+        Alpha[3] = RoeDens * dU[3];
+        Alpha[4] = tmp * (dU[4] + RoeDens * Roec * dU[1]);
+        double al[5] = {L[E_VEL1] - c_L, L[E_VEL1], L[E_VEL1], L[E_VEL1], L[E_VEL1] + c_L};
+        double ar[5] = {R[E_VEL1] - c_R, R[E_VEL1], R[E_VEL1], R[E_VEL1], R[E_VEL1] + c_R};
+        for (int i = 0; i < 5; i++) {
+            double da = fmax(0., fmax(a[i] - al[i], ar[i] - a[i]));
+            if (fabs(a[i]) < da) a[i] = 0.5 * (a[i] * a[i] / da + da);
+            else a[i] = fabs(a[i]);
+        }
+    }
+    if (!split) {
+        for (int v = 0; v < NV; v++)
+            F[v] = 0.5 * ((F_L[v] + F_R[v]) - Alpha[0] * a[0] * r1[v] - Alpha[1] * a[1] * r2[v] - Alpha[2] * a[2] * r3[v]
+                          - Alpha[3] * a[3] * r4[v] - Alpha[4] * a[4] * r5[v]);
+    } else {
+        split_surface_flux(c->splitDG, L, R, F);
+        for (int v = 0; v < NV; v++)
+            F[v] = F[v] - 0.5 * (Alpha[0] * a[0] * r1[v] + Alpha[1] * a[1] * r2[v] + Alpha[2] * a[2] * r3[v]
+                                 + Alpha[3] * a[3] * r4[v] + Alpha[4] * a[4] * r5[v]);
+    }
+}
+
+/* riemann.f90:216-289 Riemann (rotate, solve, rotate back); flux.f90:1123 EvalEulerFlux1D_fast */
+static void riemann(const dgo_config *c, double *FOut, const double *U_L, const double *U_R, const double *P_L, const double *P_R,
+                    const double *nv, const double *t1, const double *t2)
+{
+    double LL[NEXT], RR[NEXT], F_L[NV], F_R[NV], F[NV];
+    LL[E_DENS] = U_L[DENS]; LL[E_SRHO] = 1. / LL[E_DENS]; LL[E_ENER] = U_L[ENER]; LL[E_PRES] = P_L[PRES];
+    LL[E_VEL1] = P_L[VEL1] * nv[0] + P_L[VEL2] * nv[1] + P_L[VEL3] * nv[2];
+    LL[E_VEL2] = P_L[VEL1] * t1[0] + P_L[VEL2] * t1[1] + P_L[VEL3] * t1[2];
+    LL[E_MOM1] = LL[E_DENS] * LL[E_VEL1]; LL[E_MOM2] = LL[E_DENS] * LL[E_VEL2];
+    LL[E_VEL3] = P_L[VEL1] * t2[0] + P_L[VEL2] * t2[1] + P_L[VEL3] * t2[2];
+    LL[E_MOM3] = LL[E_DENS] * LL[E_VEL3]; LL[E_TEMP] = 0.;
+    RR[E_DENS] = U_R[DENS]; RR[E_SRHO] = 1. / RR[E_DENS]; RR[E_ENER] = U_R[ENER]; RR[E_PRES] = P_R[PRES];
+    RR[E_VEL1] = P_R[VEL1] * nv[0] + P_R[VEL2] * nv[1] + P_R[VEL3] * nv[2];
+    RR[E_VEL2] = P_R[VEL1] * t1[0] + P_R[VEL2] * t1[1] + P_R[VEL3] * t1[2];
+    RR[E_MOM1] = RR[E_DENS] * RR[E_VEL1]; RR[E_MOM2] = RR[E_DENS] * RR[E_VEL2];
+    RR[E_VEL3] = P_R[VEL1] * t2[0] + P_R[VEL2] * t2[1] + P_R[VEL3] * t2[2];
+    RR[E_MOM3] = RR[E_DENS] * RR[E_VEL3]; RR[E_TEMP] = 0.;
+    if (c->splitDG < 0) {
+        F_L[DENS] = LL[E_MOM1]; F_L[MOM1] = LL[E_MOM1] * LL[E_VEL1] + LL[E_PRES]; F_L[MOM2] = LL[E_MOM1] * LL[E_VEL2];
+        F_L[MOM3] = LL[E_MOM1] * LL[E_VEL3]; F_L[ENER] = (LL[E_ENER] + LL[E_PRES]) * LL[E_VEL1];
+        F_R[DENS] = RR[E_MOM1]; F_R[MOM1] = RR[E_MOM1] * RR[E_VEL1] + RR[E_PRES]; F_R[MOM2] = RR[E_MOM1] * RR[E_VEL2];
+        F_R[MOM3] = RR[E_MOM1] * RR[E_VEL3]; F_R[ENER] = (RR[E_ENER] + RR[E_PRES]) * RR[E_VEL1];
+    } else {
+        for (int v = 0; v < NV; v++) F_L[v] = F_R[v] = 0.;
+    }
+    riemann_solver(c, F, F_L, F_R, LL, RR);
+    FOut[DENS] = F[DENS];
+    for (int d = 0; d < 3; d++) FOut[MOM1 + d] = nv[d] * F[MOM1] + t1[d] * F[MOM2] + t2[d] * F[MOM3];
+    FOut[ENER] = F[ENER];
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* flux.f90:700-745 EvalDiffFlux3D (3 Cartesian viscous fluxes) */
+static void eval_diff_flux3d(const double *P, const double *gx, const double *gy, const double *gz, double *f, double *g, double *h,
+                             double mu, double lambda)
+{
+    const double s23 = 2. / 3., s43 = 4. / 3.;
+    double tau_xx = mu * (s43 * gx[LIFT_VEL1] - s23 * gy[LIFT_VEL2] - s23 * gz[LIFT_VEL3]);
+    double tau_yy = mu * (-s23 * gx[LIFT_VEL1] + s43 * gy[LIFT_VEL2] - s23 * gz[LIFT_VEL3]);
+    double tau_zz = mu * (-s23 * gx[LIFT_VEL1] - s23 * gy[LIFT_VEL2] + s43 * gz[LIFT_VEL3]);
+    double tau_xy = mu * (gy[LIFT_VEL1] + gx[LIFT_VEL2]);
+    double tau_xz = mu * (gz[LIFT_VEL1] + gx[LIFT_VEL3]);
+    double tau_yz = mu * (gz[LIFT_VEL2] + gy[LIFT_VEL3]);
+    f[DENS] = 0.; f[MOM1] = -tau_xx; f[MOM2] = -tau_xy; f[MOM3] = -tau_xz;
+    f[ENER] = -tau_xx * P[VEL1] - tau_xy * P[VEL2] - tau_xz * P[VEL3] - lambda * gx[LIFT_TEMP];
+    g[DENS] = 0.; g[MOM1] = -tau_xy; g[MOM2] = -tau_yy; g[MOM3] = -tau_yz;
+    g[ENER] = -tau_xy * P[VEL1] - tau_yy * P[VEL2] - tau_yz * P[VEL3] - lambda * gy[LIFT_TEMP];
+    h[DENS] = 0.; h[MOM1] = -tau_xz; h[MOM2] = -tau_yz; h[MOM3] = -tau_zz;
+    h[ENER] = -tau_xz * P[VEL1] - tau_yz * P[VEL2] - tau_zz * P[VEL3] - lambda * gz[LIFT_TEMP];
+}
+/* flux.f90:779-822 EvalNormalDiffFlux3D */
+static void eval_normal_diff_flux3d(const double *P, const double *gx, const double *gy, const double *gz, double *f, const double *nv,
+                                    double mu, double lambda)
+{
+    const double s23 = 2. / 3., s43 = 4. / 3.;
+    double tau_xx = mu * (s43 * gx[LIFT_VEL1] - s23 * gy[LIFT_VEL2] - s23 * gz[LIFT_VEL3]);
+    double tau_yy = mu * (-s23 * gx[LIFT_VEL1] + s43 * gy[LIFT_VEL2] - s23 * gz[LIFT_VEL3]);
+    double tau_zz = mu * (-s23 * gx[LIFT_VEL1] - s23 * gy[LIFT_VEL2] + s43 * gz[LIFT_VEL3]);
+    double tau_xy = mu * (gy[LIFT_VEL1] + gx[LIFT_VEL2]);
+    double tau_xz = mu * (gz[LIFT_VEL1] + gx[LIFT_VEL3]);
+    double tau_yz = mu * (gz[LIFT_VEL2] + gy[LIFT_VEL3]);
+    f[DENS] = 0.;
+    f[MOM1] = -nv[0] * tau_xx - nv[1] * tau_xy - nv[2] * tau_xz;
+    f[MOM2] = -nv[0] * tau_xy - nv[1] * tau_yy - nv[2] * tau_yz;
+    f[MOM3] = -nv[0] * tau_xz - nv[1] * tau_yz - nv[2] * tau_zz;
+    f[ENER] = -nv[0] * (tau_xx * P[VEL1] + tau_xy * P[VEL2] + tau_xz * P[VEL3] + lambda * gx[LIFT_TEMP])
+              - nv[1] * (tau_xy * P[VEL1] + tau_yy * P[VEL2] + tau_yz * P[VEL3] + lambda * gy[LIFT_TEMP])
+              - nv[2] * (tau_xz * P[VEL1] + tau_yz * P[VEL2] + tau_zz * P[VEL3] + lambda * gz[LIFT_TEMP]);
+}
+
+/* flux.f90:137-186 (Euler, _fast), :509-614 (Euler+diff), :619-697 (diff only): transformed fluxes at one node */
+static void eval_transformed_flux(int euler, int visc, const double *U, const double *P, const double *gx, const double *gy, const double *gz,
+                                  double *f, double *g, double *h, const double *Mf, const double *Mg, const double *Mh,
+                                  double mu, double lambda)
+{
+    double tau_xx = 0, tau_yy = 0, tau_zz = 0, tau_xy = 0, tau_xz = 0, tau_yz = 0, tX = 0, tY = 0, tZ = 0;
+    if (visc) {
+        const double s23 = 2. / 3., s43 = 4. / 3.;
+        tau_xx = mu * (s43 * gx[LIFT_VEL1] - s23 * gy[LIFT_VEL2] - s23 * gz[LIFT_VEL3]);
+        tau_yy = mu * (-s23 * gx[LIFT_VEL1] + s43 * gy[LIFT_VEL2] - s23 * gz[LIFT_VEL3]);
+        tau_zz = mu * (-s23 * gx[LIFT_VEL1] - s23 * gy[LIFT_VEL2] + s43 * gz[LIFT_VEL3]);
+        tau_xy = mu * (gy[LIFT_VEL1] + gx[LIFT_VEL2]);
+        tau_xz = mu * (gz[LIFT_VEL1] + gx[LIFT_VEL3]);
+        tau_yz = mu * (gz[LIFT_VEL2] + gy[LIFT_VEL3]);
+        tX = tau_xx * P[VEL1] + tau_xy * P[VEL2] + tau_xz * P[VEL3] + lambda * gx[LIFT_TEMP];
+        tY = tau_xy * P[VEL1] + tau_yy * P[VEL2] + tau_yz * P[VEL3] + lambda * gy[LIFT_TEMP];
+        tZ = tau_xz * P[VEL1] + tau_yz * P[VEL2] + tau_zz * P[VEL3] + lambda * gz[LIFT_TEMP];
+    }
+    const double *Ms[3] = {Mf, Mg, Mh};
+    double *Fs[3] = {f, g, h};
+    double Ep = euler ? (U[ENER] + P[PRES]) / U[DENS] : 0.;
+    for (int d = 0; d < 3; d++) {
+        const double *M = Ms[d];
+        double *F = Fs[d];
+        if (euler && visc) {
+            double Mmom = M[0] * U[MOM1] + M[1] * U[MOM2] + M[2] * U[MOM3];
+            F[DENS] = Mmom;
+            F[MOM1] = Mmom * P[VEL1] + M[0] * P[PRES] - M[0] * tau_xx - M[1] * tau_xy - M[2] * tau_xz;
+            F[MOM2] = Mmom * P[VEL2] + M[1] * P[PRES] - M[0] * tau_xy - M[1] * tau_yy - M[2] * tau_yz;
+            F[MOM3] = Mmom * P[VEL3] + M[2] * P[PRES] - M[0] * tau_xz - M[1] * tau_yz - M[2] * tau_zz;
+            F[ENER] = Mmom * Ep - M[0] * tX - M[1] * tY - M[2] * tZ;
+        } else if (euler) {
+            double Mmom = M[0] * U[MOM1] + M[1] * U[MOM2] + M[2] * U[MOM3];
+            F[DENS] = Mmom;
+            F[MOM1] = Mmom * P[VEL1] + M[0] * P[PRES];
+            F[MOM2] = Mmom * P[VEL2] + M[1] * P[PRES];
+            F[MOM3] = Mmom * P[VEL3] + M[2] * P[PRES];
+            F[ENER] = Mmom * Ep;
+        } else {
+            F[DENS] = 0.;
+            F[MOM1] = -M[0] * tau_xx - M[1] * tau_xy - M[2] * tau_xz;
+            F[MOM2] = -M[0] * tau_xy - M[1] * tau_yy - M[2] * tau_yz;
+            F[MOM3] = -M[0] * tau_xz - M[1] * tau_yz - M[2] * tau_zz;
+            F[ENER] = -M[0] * tX - M[1] * tY - M[2] * tZ;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* lifting: dg/lifting/lifting_br1.t90:47-167 (strong form, non-conservative volume integral) */
+static void lifting_br1(dgo *s)
+{
+    const dgo_config *c = &s->c;
+    const int n = s->n;
+    double *Flux = s->gradUz_slave; /* the reference reuses this buffer for the untransformed flux, lifting_br1.t90:76-80 */
+    /* lifting_fillflux.t90:109-140 + getboundaryflux.f90:945-1019 Lifting_GetBoundaryFlux_Kernel (strong form) */
+#pragma omp parallel for schedule(static)
+    for (int sd = 0; sd < c->nBCSides; sd++)
+        for (int q = 0; q < n; q++) for (int p = 0; p < n; p++) {
+            int bct = c->BCSides[0 + 2 * sd], bcs = c->BCSides[1 + 2 * sd];
+            const double *Pm = &s->UPrim_master[IDX_FACE(s, NP, 0, p, q, sd)];
+            const double *nv = &c->NormVec[IDX_FACE(s, 3, 0, p, q, sd)];
+            const double *t1 = &c->TangVec1[IDX_FACE(s, 3, 0, p, q, sd)];
+            const double *t2 = &c->TangVec2[IDX_FACE(s, 3, 0, p, q, sd)];
+            double Pb[NP], Fl[NL];
+            get_boundary_state(c, bct, Pb, Pm, &c->RefStatePrim[NP * (bcs > 0 ? bcs - 1 : 0)], nv, t1, t2);
+            if (bct == 2) {
+                for (int v = 0; v < NL; v++) Fl[v] = 0.5 * (Pm[PRIM_LIFT[v]] + Pb[PRIM_LIFT[v]]);
+            } else if (bct == 3 || bct == 4) {
+                Fl[LIFT_DENS] = Pb[DENS]; Fl[LIFT_VEL1] = Fl[LIFT_VEL2] = Fl[LIFT_VEL3] = 0.; Fl[LIFT_TEMP] = Pb[TEMP];
+            } else {
+                Fl[LIFT_DENS] = Pm[DENS]; Fl[LIFT_VEL1] = Pb[VEL1]; Fl[LIFT_VEL2] = Pb[VEL2]; Fl[LIFT_VEL3] = Pb[VEL3]; Fl[LIFT_TEMP] = Pm[TEMP];
+            }
+            for (int v = 0; v < NL; v++) Fl[v] = Fl[v] - Pm[PRIM_LIFT[v]];
+            double se = c->SurfElem[p + n * (q + (size_t)n * sd)];
+            for (int v = 0; v < NL; v++) Flux[IDX_FACE(s, NL, v, p, q, sd)] = Fl[v] * se;
+        }
+    /* lifting_fillflux.t90:39-93 Lifting_FillFlux: inner + MPI MINE sides, sig=-1 (strong) */
+#pragma omp parallel for schedule(static)
+    for (int sd = c->firstInnerSide - 1; sd < c->lastMPISide_MINE; sd++)
+        for (int q = 0; q < n; q++) for (int p = 0; p < n; p++) {
+            double se = c->SurfElem[p + n * (q + (size_t)n * sd)];
+            for (int v = 0; v < NL; v++)
+                Flux[IDX_FACE(s, NL, v, p, q, sd)] = 0.5 * se * (-1. * s->UPrim_master[IDX_FACE(s, NP, PRIM_LIFT[v], p, q, sd)]
+                                                                 + s->UPrim_slave[IDX_FACE(s, NP, PRIM_LIFT[v], p, q, sd)]);
+        }
+    /* (MPI) flux on YOUR sides arrives from the master rank: single-rank oracle has none. */
+    /* lifting_fillflux.t90:212-256 Lifting_FillFlux_NormVec */
+#pragma omp parallel for schedule(static)
+    for (int sd = 0; sd < c->nSides; sd++)
+        for (int q = 0; q < n; q++) for (int p = 0; p < n; p++) {
+            const double *nv = &c->NormVec[IDX_FACE(s, 3, 0, p, q, sd)];
+            for (int v = 0; v < NL; v++) {
+                double fl = Flux[IDX_FACE(s, NL, v, p, q, sd)];
+                s->gradUx_master[IDX_FACE(s, NL, v, p, q, sd)] = fl * nv[0];
+                s->gradUy_master[IDX_FACE(s, NL, v, p, q, sd)] = fl * nv[1];
+                s->gradUz_master[IDX_FACE(s, NL, v, p, q, sd)] = fl * nv[2];
+            }
+        }
+    /* lifting_volint.t90:262-328 Lifting_VolInt_Nonconservative_GPU_Kernel */
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < c->nElems; e++)
+        for (int k = 0; k < n; k++) for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) {
+            double gxi[NL], get[NL], gze[NL];
+            for (int v = 0; v < NL; v++) gxi[v] = get[v] = gze[v] = 0.;
+            for (int l = 0; l < n; l++)
+                for (int v = 0; v < NL; v++) {
+                    gxi[v] = gxi[v] + c->D_T[l + n * i] * s->UPrim[IDX_VOL(s, NP, PRIM_LIFT[v], l, j, k, e)];
+                    get[v] = get[v] + c->D_T[l + n * j] * s->UPrim[IDX_VOL(s, NP, PRIM_LIFT[v], i, l, k, e)];
+                    gze[v] = gze[v] + c->D_T[l + n * k] * s->UPrim[IDX_VOL(s, NP, PRIM_LIFT[v], i, j, l, e)];
+                }
+            const double *Mf = &c->Metrics_fTilde[IDX_VOL(s, 3, 0, i, j, k, e)];
+            const double *Mg = &c->Metrics_gTilde[IDX_VOL(s, 3, 0, i, j, k, e)];
+            const double *Mh = &c->Metrics_hTilde[IDX_VOL(s, 3, 0, i, j, k, e)];
+            for (int v = 0; v < NL; v++) {
+                s->gradUx[IDX_VOL(s, NL, v, i, j, k, e)] = Mf[0] * gxi[v] + Mg[0] * get[v] + Mh[0] * gze[v];
+                s->gradUy[IDX_VOL(s, NL, v, i, j, k, e)] = Mf[1] * gxi[v] + Mg[1] * get[v] + Mh[1] * gze[v];
+                s->gradUz[IDX_VOL(s, NL, v, i, j, k, e)] = Mf[2] * gxi[v] + Mg[2] * get[v] + Mh[2] * gze[v];
+            }
+        }
+    /* lifting_br1.t90:118-124 SurfIntLifting x3 (single flux, strong, with sJ) */
+    surf_int(s, NL, s->gradUx_master, NULL, s->gradUx, 1, 0, 1);
+    surf_int(s, NL, s->gradUy_master, NULL, s->gradUy, 1, 0, 1);
+    surf_int(s, NL, s->gradUz_master, NULL, s->gradUz, 1, 0, 1);
+    /* lifting_br1.t90:152-156 ProlongToFaceLifting x3 */
+    prolong_to_face(s, NL, s->gradUx, s->gradUx_master, s->gradUx_slave);
+    prolong_to_face(s, NL, s->gradUy, s->gradUy_master, s->gradUy_slave);
+    prolong_to_face(s, NL, s->gradUz, s->gradUz_master, s->gradUz_slave);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* dg/applydmatrix.t90:19-75 ApplyDMatrix_Kernel */
+static void apply_dmatrix(const dgo *s, double *Ut, int overwrite)
+{
+    const dgo_config *c = &s->c;
+    const int n = s->n;
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < c->nElems; e++)
+        for (int k = 0; k < n; k++) for (int j = 0; j < n; j++) for (int i = 0; i < n; i++)
+            for (int v = 0; v < NV; v++) {
+                double a = 0.;
+                for (int l = 0; l < n; l++)
+                    a = a + c->D_Hat_T[l + n * i] * s->f[IDX_VOL(s, NV, v, l, j, k, e)]
+                          + c->D_Hat_T[l + n * k] * s->h[IDX_VOL(s, NV, v, i, j, l, e)]
+                          + c->D_Hat_T[l + n * j] * s->g[IDX_VOL(s, NV, v, i, l, k, e)];
+                size_t id = IDX_VOL(s, NV, v, i, j, k, e);
+                Ut[id] = overwrite ? a : Ut[id] + a;
+            }
+}
+
+/* dg/volint.f90:60-119 (visc), :129-188 (weak), :211-353 (split) */
+static void vol_int(dgo *s)
+{
+    const dgo_config *c = &s->c;
+    const int n = s->n;
+    const int split = c->splitDG >= 0;
+    if (!split || c->parabolic) {
+#pragma omp parallel for schedule(static)
+        for (size_t d = 0; d < s->nDOF; d++) {
+            const double *P = &s->UPrim[NP * d];
+            double mu = 0., lambda = 0.;
+            if (c->parabolic) { mu = viscosity(c, P); lambda = conductivity(c, mu); }
+            eval_transformed_flux(!split, c->parabolic, &s->U[NV * d], P,
+                                  c->parabolic ? &s->gradUx[NL * d] : NULL, c->parabolic ? &s->gradUy[NL * d] : NULL,
+                                  c->parabolic ? &s->gradUz[NL * d] : NULL, &s->f[NV * d], &s->g[NV * d], &s->h[NV * d],
+                                  &c->Metrics_fTilde[3 * d], &c->Metrics_gTilde[3 * d], &c->Metrics_hTilde[3 * d], mu, lambda);
+        }
+        apply_dmatrix(s, s->Ut, 1);
+    }
+    if (split) { /* volint.f90:265-353 VolInt_splitForm_Kernel */
+#pragma omp parallel for schedule(static)
+        for (int e = 0; e < c->nElems; e++)
+            for (int k = 0; k < n; k++) for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) {
+                double acc[NV], Fl[NV];
+                for (int v = 0; v < NV; v++) acc[v] = 0.;
+                size_t d0 = IDX_VOL(s, 1, 0, i, j, k, e);
+                for (int l = 0; l < n; l++) {
+                    size_t d1 = IDX_VOL(s, 1, 0, l, j, k, e);
+                    split_volume_flux(c->splitDG, &s->U[NV * d0], &s->UPrim[NP * d0], &s->U[NV * d1], &s->UPrim[NP * d1],
+                                      &c->Metrics_fTilde[3 * d0], &c->Metrics_fTilde[3 * d1], Fl);
+                    for (int v = 0; v < NV; v++) acc[v] = acc[v] + c->DVolSurf[l + n * i] * Fl[v];
+                }
+                for (int l = 0; l < n; l++) {
+                    size_t d1 = IDX_VOL(s, 1, 0, i, l, k, e);
+                    split_volume_flux(c->splitDG, &s->U[NV * d0], &s->UPrim[NP * d0], &s->U[NV * d1], &s->UPrim[NP * d1],
+                                      &c->Metrics_gTilde[3 * d0], &c->Metrics_gTilde[3 * d1], Fl);
+                    for (int v = 0; v < NV; v++) acc[v] = acc[v] + c->DVolSurf[l + n * j] * Fl[v];
+                }
+                for (int l = 0; l < n; l++) {
+                    size_t d1 = IDX_VOL(s, 1, 0, i, j, l, e);
+                    split_volume_flux(c->splitDG, &s->U[NV * d0], &s->UPrim[NP * d0], &s->U[NV * d1], &s->UPrim[NP * d1],
+                                      &c->Metrics_hTilde[3 * d0], &c->Metrics_hTilde[3 * d1], Fl);
+                    for (int v = 0; v < NV; v++) acc[v] = acc[v] + c->DVolSurf[l + n * k] * Fl[v];
+                }
+                for (int v = 0; v < NV; v++) {
+                    if (c->parabolic) s->Ut[NV * d0 + v] = s->Ut[NV * d0 + v] + acc[v];
+                    else s->Ut[NV * d0 + v] = acc[v];
+                }
+            }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* dg/fillflux.f90:45-172 FillFlux (BC sides, inner + MPI-MINE sides), getboundaryflux.f90:542-838 */
+static int fill_flux(dgo *s)
+{
+    const dgo_config *c = &s->c;
+    const int n = s->n;
+    const double kappa = c->EOS[EOS_KAPPA];
+    int err = 0;
+#pragma omp parallel for schedule(static) reduction(|:err)
+    for (int sd = 0; sd < c->lastMPISide_MINE; sd++)
+        for (int q = 0; q < n; q++) for (int p = 0; p < n; p++) {
+            const double *nv = &c->NormVec[IDX_FACE(s, 3, 0, p, q, sd)];
+            const double *t1 = &c->TangVec1[IDX_FACE(s, 3, 0, p, q, sd)];
+            const double *t2 = &c->TangVec2[IDX_FACE(s, 3, 0, p, q, sd)];
+            const double *Pm = &s->UPrim_master[IDX_FACE(s, NP, 0, p, q, sd)];
+            double *F = &s->Flux_master[IDX_FACE(s, NV, 0, p, q, sd)];
+            const double *gxm = &s->gradUx_master[IDX_FACE(s, NL, 0, p, q, sd)];
+            const double *gym = &s->gradUy_master[IDX_FACE(s, NL, 0, p, q, sd)];
+            const double *gzm = &s->gradUz_master[IDX_FACE(s, NL, 0, p, q, sd)];
+            if (sd < c->nBCSides) {
+                int bct = c->BCSides[0 + 2 * sd], bcs = c->BCSides[1 + 2 * sd];
+                double Pb[NP];
+                err |= get_boundary_state(c, bct, Pb, Pm, &c->RefStatePrim[NP * (bcs > 0 ? bcs - 1 : 0)], nv, t1, t2);
+                if (bct == 2) {
+                    double Um[NV], Ub[NV];
+                    prim_to_cons(Pm, Um, kappa);
+                    prim_to_cons(Pb, Ub, kappa);
+                    riemann(c, F, Um, Ub, Pm, Pb, nv, t1, t2);
+                    if (c->parabolic) { /* riemann.f90:485-528 ViscousFlux (point), master gradients on both sides */
+                        double fL[NV], gL[NV], hL[NV], fR[NV], gR[NV], hR[NV];
+                        double mu = viscosity(c, Pm), la = conductivity(c, mu);
+                        eval_diff_flux3d(Pm, gxm, gym, gzm, fL, gL, hL, mu, la);
+                        mu = viscosity(c, Pb); la = conductivity(c, mu);
+                        eval_diff_flux3d(Pb, gxm, gym, gzm, fR, gR, hR, mu, la);
+                        for (int v = 0; v < NV; v++)
+                            F[v] = F[v] + 0.5 * (nv[0] * (fL[v] + fR[v]) + nv[1] * (gL[v] + gR[v]) + nv[2] * (hL[v] + hR[v]));
+                    }
+                } else if (bct == 3 || bct == 4 || bct == 9) {
+                    F[DENS] = 0.;
+                    for (int d = 0; d < 3; d++) F[MOM1 + d] = Pb[PRES] * nv[d];
+                    F[ENER] = 0.;
+                    if (c->parabolic) {
+                        double mu = viscosity(c, Pb), la = conductivity(c, mu);
+                        double fd[NV], gd[NV], hd[NV];
+                        if (bct == 9) {
+                            double B[3][3], gxf[NL], gyf[NL], gzf[NL];
+                            B[0][0] = 1. - nv[0] * nv[0]; B[1][1] = 1. - nv[1] * nv[1]; B[2][2] = 1. - nv[2] * nv[2];
+                            B[0][1] = -nv[0] * nv[1]; B[0][2] = -nv[0] * nv[2]; B[2][1] = -nv[2] * nv[1];
+                            B[1][0] = B[0][1]; B[2][0] = B[0][2]; B[1][2] = B[2][1];
+                            for (int v = 0; v < NL; v++) {
+                                gxf[v] = B[0][0] * gxm[v] + B[0][1] * gym[v] + B[0][2] * gzm[v];
+                                gyf[v] = B[1][0] * gxm[v] + B[1][1] * gym[v] + B[1][2] * gzm[v];
+                                gzf[v] = B[2][0] * gxm[v] + B[2][1] * gym[v] + B[2][2] * gzm[v];
+                            }
+                            eval_diff_flux3d(Pb, gxf, gyf, gzf, fd, gd, hd, mu, la);
+                        } else {
+                            eval_diff_flux3d(Pb, gxm, gym, gzm, fd, gd, hd, mu, la);
+                            if (bct == 3) fd[ENER] = gd[ENER] = hd[ENER] = 0.;
+                        }
+                        for (int v = 0; v < NV; v++) F[v] = F[v] + nv[0] * fd[v] + nv[1] * gd[v] + nv[2] * hd[v];
+                    }
+                } else err |= 1;
+            } else {
+                const double *Ps = &s->UPrim_slave[IDX_FACE(s, NP, 0, p, q, sd)];
+                riemann(c, F, &s->U_master[IDX_FACE(s, NV, 0, p, q, sd)], &s->U_slave[IDX_FACE(s, NV, 0, p, q, sd)], Pm, Ps, nv, t1, t2);
+                if (c->parabolic) { /* riemann.f90:638-700 ViscousFlux_Kernel_CUDA */
+                    double nd[NV];
+                    double mu = viscosity(c, Pm), la = conductivity(c, mu);
+                    eval_normal_diff_flux3d(Pm, gxm, gym, gzm, nd, nv, mu, la);
+                    for (int v = 0; v < NV; v++) F[v] = F[v] + 0.5 * nd[v];
+                    mu = viscosity(c, Ps); la = conductivity(c, mu);
+                    eval_normal_diff_flux3d(Ps, &s->gradUx_slave[IDX_FACE(s, NL, 0, p, q, sd)], &s->gradUy_slave[IDX_FACE(s, NL, 0, p, q, sd)],
+                                            &s->gradUz_slave[IDX_FACE(s, NL, 0, p, q, sd)], nd, nv, mu, la);
+                    for (int v = 0; v < NV; v++) F[v] = F[v] + 0.5 * nd[v];
+                }
+            }
+            double se = c->SurfElem[p + n * (q + (size_t)n * sd)];
+            for (int v = 0; v < NV; v++) {
+                F[v] = F[v] * se;
+                s->Flux_slave[IDX_FACE(s, NV, v, p, q, sd)] = F[v];
+            }
+        }
+    return err;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* dg/dg.f90:255-425 DGTimeDerivative_weakForm (single rank: no halo phases) */
+int dgo_time_derivative(dgo *s, double t)
+{
+    (void)t;
+    const dgo_config *c = &s->c;
+    const double kappa = c->EOS[EOS_KAPPA], R = c->EOS[EOS_R];
+    /* 2. */ prolong_to_face(s, NV, s->U, s->U_master, s->U_slave);
+    /* 3. eos.f90:328 ConsToPrim volume */
+#pragma omp parallel for schedule(static)
+    for (size_t d = 0; d < s->nDOF; d++) cons_to_prim(&s->UPrim[NP * d], &s->U[NV * d], kappa, R);
+    /* 5. equation.f90:198-261 GetPrimitiveStateSurface */
+#pragma omp parallel for schedule(static)
+    for (size_t d = 0; d < s->nFace; d++) {
+        cons_to_prim(&s->UPrim_master[NP * d], &s->U_master[NV * d], kappa, R);
+        cons_to_prim(&s->UPrim_slave[NP * d], &s->U_slave[NV * d], kappa, R);
+    }
+    /* 6. */ if (c->parabolic) lifting_br1(s);
+    /* 8. */ vol_int(s);
+    /* 11. */ int err = fill_flux(s);
+    /* 11.5 */ surf_int(s, NV, s->Flux_master, s->Flux_slave, s->Ut, 0, 0, 0);
+    /* 12. vector.f90:210 VAX_GPU(-1), 14. applyjacobian.t90:196 */
+#pragma omp parallel for schedule(static)
+    for (size_t d = 0; d < s->nDOF; d++) {
+        for (int v = 0; v < NV; v++) s->Ut[NV * d + v] = s->Ut[NV * d + v] * (-1.);
+        for (int v = 0; v < NV; v++) s->Ut[NV * d + v] = s->Ut[NV * d + v] * c->sJ[d];
+    }
+    return err;
+}
+
+/* timedisc/timestep.f90:49-120 one stage of TimeStepByLSERKW2 + globals/vector.f90:163-183 VAXPB_OUT_VAXPB_IN */
+int dgo_rk_stage(dgo *s, double tStage, double mRKA, double b_dt)
+{
+    int err = dgo_time_derivative(s, tStage);
+    size_t nTot = NV * s->nDOF;
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < nTot; i++) {
+        s->Ut_tmp[i] = s->Ut_tmp[i] * mRKA + s->Ut[i];
+        s->U[i] = s->U[i] + s->Ut_tmp[i] * b_dt;
+    }
+    return err;
+}
+
+int dgo_rk_step(dgo *s, double t, double dt, int nStages, const double *RKA, const double *RKb, const double *RKc)
+{
+    int err = 0;
+    for (int st = 0; st < nStages; st++) {
+        double tStage = (st == 0) ? t : t + RKc[st] * dt;
+        double mRKA = (st == 0) ? 0. : -1. * RKA[st];
+        err |= dgo_rk_stage(s, tStage, mRKA, RKb[st] * dt);
+    }
+    return err;
+}
+
+/* calctimestep.f90:47-90 InitCalctimestep, :98-296 CalcTimeStep / CalcMaxEigenvalue.
+ * The min over elements is taken as min_e(CFL*2/lambda_e): the value the reference's CUF reduction produces
+ * when every thread owns one element (calctimestep.f90:157 has a misplaced parenthesis otherwise). */
+double dgo_calc_timestep(dgo *s, double CFLScale, double DFLScale, double *dt_conv, double *dt_visc)
+{
+    const dgo_config *c = &s->c;
+    const int n = s->n;
+    const double kappa = c->EOS[EOS_KAPPA], R = c->EOS[EOS_R];
+    double tc = HUGE_VAL, tv = HUGE_VAL;
+    double KappasPr_max = fmax(4. / 3., kappa / c->EOS[EOS_PR]);
+#pragma omp parallel for schedule(static) reduction(min:tc) reduction(min:tv)
+    for (int e = 0; e < c->nElems; e++) {
+        double mx[6] = {0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < n; k++) for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) {
+            size_t d = IDX_VOL(s, 1, 0, i, j, k, e);
+            const double *U = &s->U[NV * d];
+            double sJ = c->sJ[d];
+            const double *Mf = &c->Metrics_fTilde[3 * d], *Mg = &c->Metrics_gTilde[3 * d], *Mh = &c->Metrics_hTilde[3 * d];
+            double sRho = 1. / U[DENS];
+            double vel[3] = {U[MOM1] * sRho, U[MOM2] * sRho, U[MOM3] * sRho};
+            double pres = (kappa - 1.) * (U[ENER] - 0.5 * (vel[0] * U[MOM1] + vel[1] * U[MOM2] + vel[2] * U[MOM3]));
+            double prim[NP] = {U[DENS], vel[0], vel[1], vel[2], pres, pres * sRho / R};
+            double cs = sqrt(kappa * pres * sRho);
+            double vsJ[3] = {vel[0] * sJ, vel[1] * sJ, vel[2] * sJ};
+            double adv[3] = {sJ * sqrt(Mf[0] * Mf[0] + Mf[1] * Mf[1] + Mf[2] * Mf[2]),
+                             sJ * sqrt(Mg[0] * Mg[0] + Mg[1] * Mg[1] + Mg[2] * Mg[2]),
+                             sJ * sqrt(Mh[0] * Mh[0] + Mh[1] * Mh[1] + Mh[2] * Mh[2])};
+            mx[0] = fmax(mx[0], fabs(Mf[0] * vsJ[0] + Mf[1] * vsJ[1] + Mf[2] * vsJ[2]) + cs * adv[0]);
+            mx[1] = fmax(mx[1], fabs(Mg[0] * vsJ[0] + Mg[1] * vsJ[1] + Mg[2] * vsJ[2]) + cs * adv[1]);
+            mx[2] = fmax(mx[2], fabs(Mh[0] * vsJ[0] + Mh[1] * vsJ[1] + Mh[2] * vsJ[2]) + cs * adv[2]);
+            if (c->parabolic) {
+                double mu = viscosity(c, prim);
+                double vis[3] = {KappasPr_max * ((Mf[0] * sJ) * (Mf[0] * sJ) + (Mf[1] * sJ) * (Mf[1] * sJ) + (Mf[2] * sJ) * (Mf[2] * sJ)),
+                                 KappasPr_max * ((Mg[0] * sJ) * (Mg[0] * sJ) + (Mg[1] * sJ) * (Mg[1] * sJ) + (Mg[2] * sJ) * (Mg[2] * sJ)),
+                                 KappasPr_max * ((Mh[0] * sJ) * (Mh[0] * sJ) + (Mh[1] * sJ) * (Mh[1] * sJ) + (Mh[2] * sJ) * (Mh[2] * sJ))};
+                for (int d3 = 0; d3 < 3; d3++) mx[3 + d3] = fmax(mx[3 + d3], mu * sRho * vis[d3]);
+            }
+        }
+        double lc = mx[0] + mx[1] + mx[2];
+        tc = fmin(tc, CFLScale * 2. / lc);
+        if (c->parabolic) { double lv = mx[3] + mx[4] + mx[5]; tv = fmin(tv, DFLScale * 4. / lv); }
+    }
+    if (dt_conv) *dt_conv = tc;
+    if (dt_visc) *dt_visc = tv;
+    return fmin(tc, tv);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+dgo *dgo_create(const dgo_config *cfg)
+{
+    dgo *s = (dgo *)calloc(1, sizeof(dgo));
+    s->c = *cfg;
+    s->n = cfg->N + 1; s->n2 = s->n * s->n; s->n3 = s->n2 * s->n;
+    s->nDOF = (size_t)s->n3 * cfg->nElems;
+    s->nFace = (size_t)s->n2 * cfg->nSides;
+#define AL(x, cnt) s->x = (double *)calloc((size_t)(cnt) + 1, sizeof(double))
+    AL(U, NV * s->nDOF); AL(Ut, NV * s->nDOF); AL(UPrim, NP * s->nDOF); AL(Ut_tmp, NV * s->nDOF);
+    AL(U_master, NV * s->nFace); AL(U_slave, NV * s->nFace); AL(UPrim_master, NP * s->nFace); AL(UPrim_slave, NP * s->nFace);
+    AL(Flux_master, NV * s->nFace); AL(Flux_slave, NV * s->nFace);
+    AL(gradUx, NL * s->nDOF); AL(gradUy, NL * s->nDOF); AL(gradUz, NL * s->nDOF);
+    AL(gradUx_master, NL * s->nFace); AL(gradUy_master, NL * s->nFace); AL(gradUz_master, NL * s->nFace);
+    AL(gradUx_slave, NL * s->nFace); AL(gradUy_slave, NL * s->nFace); AL(gradUz_slave, NL * s->nFace);
+    AL(f, NV * s->nDOF); AL(g, NV * s->nDOF); AL(h, NV * s->nDOF);
+#undef AL
+    /* the reference initialises U_slave/UPrim_slave of BC sides to 0 and never touches them; prim of a zero
+     * state would divide by zero, so the slave arrays of sides without a slave element get a benign state. */
+    for (size_t d = 0; d < s->nFace; d++) { s->U_slave[NV * d] = 1.; s->U_slave[NV * d + 4] = 1.; s->U_master[NV * d] = 1.; s->U_master[NV * d + 4] = 1.; }
+    return s;
+}
+
+void dgo_destroy(dgo *s)
+{
+    if (!s) return;
+    double *p[] = {s->U, s->Ut, s->UPrim, s->Ut_tmp, s->U_master, s->U_slave, s->UPrim_master, s->UPrim_slave, s->Flux_master,
+                   s->Flux_slave, s->gradUx, s->gradUy, s->gradUz, s->gradUx_master, s->gradUy_master, s->gradUz_master,
+                   s->gradUx_slave, s->gradUy_slave, s->gradUz_slave, s->f, s->g, s->h};
+    for (size_t i = 0; i < sizeof(p) / sizeof(p[0]); i++) free(p[i]);
+    free(s);
+}
+
+/* array access for the tests: name -> pointer */
+double *dgo_array(dgo *s, const char *name)
+{
+#define R(x) if (!strcmp(name, #x)) return s->x
+    R(U); R(Ut); R(UPrim); R(Ut_tmp); R(U_master); R(U_slave); R(UPrim_master); R(UPrim_slave); R(Flux_master); R(Flux_slave);
+    R(gradUx); R(gradUy); R(gradUz); R(gradUx_master); R(gradUy_master); R(gradUz_master);
+    R(gradUx_slave); R(gradUy_slave); R(gradUz_slave);
+#undef R
+    return NULL;
+}
+
+/* stand-alone entry points used by the golden tests (unitTests/ProlongToFace.f90, unitTests/SurfInt.f90) */
+void dgo_prolong_to_face(dgo *s, int nVar, const double *Uvol, double *Um, double *Us) { prolong_to_face(s, nVar, Uvol, Um, Us); }
+void dgo_surf_int(dgo *s, int nVar, const double *Fm, const double *Fs, double *Ut) { surf_int(s, nVar, Fm, Fs, Ut, 0, 0, 0); }
+void dgo_lifting(dgo *s) { lifting_br1(s); }
+size_t dgo_sizeof_config(void) { return sizeof(dgo_config); }

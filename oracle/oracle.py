@@ -1,0 +1,159 @@
+"""ctypes loader for the CPU parity oracle (oracle/dg_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs. The product package (galaexi_b200) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libdgoracle.so")
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class _Config(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("N", "nElems", "nSides", "nBCSides", "firstInnerSide", "lastInnerSide",
+                                       "firstMPISide_MINE", "lastMPISide_MINE", "firstMPISide_YOUR", "lastMPISide_YOUR",
+                                       "nodeType", "splitDG", "riemann", "parabolic", "viscLaw", "nRefState")] + \
+               [("EOS", C.c_double * 8)] + \
+               [(k, _dp) for k in ("D_T", "D_Hat_T", "DVolSurf", "L_Minus", "L_Plus", "L_HatMinus", "L_HatPlus")] + \
+               [(k, _ip) for k in ("ElemToSide", "S2V2", "S2V2_inv", "BCSides")] + \
+               [(k, _dp) for k in ("Metrics_fTilde", "Metrics_gTilde", "Metrics_hTilde", "sJ", "NormVec", "TangVec1",
+                                   "TangVec2", "SurfElem", "RefStatePrim")]
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "dg_oracle.c")
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "libdgoracle.so"])
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.dgo_create.restype = C.c_void_p
+        _lib.dgo_create.argtypes = [C.POINTER(_Config)]
+        _lib.dgo_destroy.argtypes = [C.c_void_p]
+        _lib.dgo_array.restype = _dp
+        _lib.dgo_array.argtypes = [C.c_void_p, C.c_char_p]
+        _lib.dgo_time_derivative.argtypes = [C.c_void_p, C.c_double]
+        _lib.dgo_rk_stage.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        _lib.dgo_rk_step.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, _dp, _dp, _dp]
+        _lib.dgo_calc_timestep.restype = C.c_double
+        _lib.dgo_calc_timestep.argtypes = [C.c_void_p, C.c_double, C.c_double, _dp, _dp]
+        _lib.dgo_prolong_to_face.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
+        _lib.dgo_surf_int.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
+        _lib.dgo_lifting.argtypes = [C.c_void_p]
+        _lib.dgo_sizeof_config.restype = C.c_size_t
+        assert _lib.dgo_sizeof_config() == C.sizeof(_Config)
+    return _lib
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+class Oracle:
+    """One single-rank DG operator instance built from a galaexi_b200.host.case.Case."""
+
+    def __init__(self, case):
+        L = lib()
+        m, b, g = case.mesh, case.basis, case.geo
+        self.case = case
+        self.n = case.N + 1
+        # keep references: the C side stores raw pointers
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        # operator matrices: Fortran M(a,b) at [a + n*b] == C array M.T
+        self._keep = dict(
+            D_T=f64(b.D_T.T), D_Hat_T=f64(b.D_Hat_T.T), DVolSurf=f64(b.DVolSurf.T), L_Minus=f64(b.L_Minus), L_Plus=f64(b.L_Plus),
+            L_HatMinus=f64(b.L_HatMinus), L_HatPlus=f64(b.L_HatPlus),
+            ElemToSide=i32(m.ElemToSide), S2V2=i32(case.maps["S2V2"]), S2V2_inv=i32(case.maps["S2V2_inv"]),
+            BCSides=i32(case.BCSides if case.BCSides.size else np.zeros((1, 2))),
+            Metrics_fTilde=f64(g["Metrics_fTilde"]), Metrics_gTilde=f64(g["Metrics_gTilde"]), Metrics_hTilde=f64(g["Metrics_hTilde"]),
+            sJ=f64(g["sJ"]), NormVec=f64(g["NormVec"]), TangVec1=f64(g["TangVec1"]), TangVec2=f64(g["TangVec2"]),
+            SurfElem=f64(g["SurfElem"]), RefStatePrim=f64(case.RefStatePrim))
+        c = _Config()
+        c.N, c.nElems, c.nSides = case.N, m.nElems, m.nSides
+        c.nBCSides, c.firstInnerSide, c.lastInnerSide = m.nBCSides, m.firstInnerSide, m.lastInnerSide
+        c.firstMPISide_MINE, c.lastMPISide_MINE = m.firstMPISide_MINE, m.lastMPISide_MINE
+        c.firstMPISide_YOUR, c.lastMPISide_YOUR = m.firstMPISide_YOUR, m.lastMPISide_YOUR
+        c.nodeType = 2 if case.node_type == "GAUSS-LOBATTO" else 1
+        c.splitDG, c.riemann, c.parabolic = case.split, case.riemann, int(case.parabolic)
+        c.viscLaw, c.nRefState = case.eos.visc_law, case.RefStatePrim.shape[0]
+        for k, v in enumerate(case.eos.eos_vars()):
+            c.EOS[k] = v
+        for k in ("D_T", "D_Hat_T", "DVolSurf", "L_Minus", "L_Plus", "L_HatMinus", "L_HatPlus", "Metrics_fTilde",
+                  "Metrics_gTilde", "Metrics_hTilde", "sJ", "NormVec", "TangVec1", "TangVec2", "SurfElem", "RefStatePrim"):
+            setattr(c, k, _d(self._keep[k]))
+        for k in ("ElemToSide", "S2V2", "S2V2_inv", "BCSides"):
+            setattr(c, k, _i(self._keep[k]))
+        self._cfg = c
+        self.h = L.dgo_create(C.byref(c))
+        n, nE, nS = self.n, m.nElems, m.nSides
+        self._shapes = {}
+        for nm in ("U", "Ut", "Ut_tmp"):
+            self._shapes[nm] = (nE, n, n, n, 5)
+        self._shapes["UPrim"] = (nE, n, n, n, 6)
+        for nm in ("gradUx", "gradUy", "gradUz"):
+            self._shapes[nm] = (nE, n, n, n, 5)
+        for nm in ("U_master", "U_slave", "Flux_master", "Flux_slave", "gradUx_master", "gradUy_master", "gradUz_master",
+                   "gradUx_slave", "gradUy_slave", "gradUz_slave"):
+            self._shapes[nm] = (nS, n, n, 5)
+        for nm in ("UPrim_master", "UPrim_slave"):
+            self._shapes[nm] = (nS, n, n, 6)
+
+    def array(self, name: str) -> np.ndarray:
+        """Writable numpy view (reference memory layout, C-order reversed index list) of an oracle array."""
+        p = lib().dgo_array(self.h, name.encode())
+        shp = self._shapes[name]
+        return np.ctypeslib.as_array(p, shape=(int(np.prod(shp)),)).reshape(shp)
+
+    def set_state(self, U: np.ndarray):
+        self.array("U")[...] = U
+        self.array("Ut_tmp")[...] = 0.0
+
+    def time_derivative(self, t: float = 0.0) -> np.ndarray:
+        err = lib().dgo_time_derivative(self.h, float(t))
+        if err:
+            raise RuntimeError("oracle: unsupported boundary condition type")
+        return self.array("Ut")
+
+    def rk_step(self, t: float, dt: float):
+        td = self.case.timedisc
+        A, b, c = (np.ascontiguousarray(x, dtype=np.float64) for x in (td.RKA, td.RKb, td.RKc))
+        err = lib().dgo_rk_step(self.h, float(t), float(dt), td.nRKStages, _d(A), _d(b), _d(c))
+        if err:
+            raise RuntimeError("oracle: unsupported boundary condition type")
+
+    def calc_timestep(self):
+        tc, tv = C.c_double(), C.c_double()
+        td = self.case.timedisc
+        dt = lib().dgo_calc_timestep(self.h, td.CFLScale, td.DFLScale, C.byref(tc), C.byref(tv))
+        return dt, tc.value, tv.value
+
+    def close(self):
+        if self.h:
+            lib().dgo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

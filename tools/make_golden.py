@@ -1,0 +1,84 @@
+#!/usr/bin/env python
+"""Extracts the reference's own golden vectors into small fixtures under tests/golden/.
+
+Run in the build container (needs /root/reference, which does not exist on the GPU box):
+    python tools/make_golden.py
+Sources (all from flexi-framework/galaexi, read-only):
+  unitTests/*.bin                                   Fortran sequential unformatted records (4-byte markers)
+  regressioncheck/checks/tgv/split/*.csv + mesh     TGV N=7 GL split-form regression (first rows)
+  regressioncheck/checks/parabolic/cavity_3D/*      cavity N=2 Gauss NS+BR1 reference state + mesh
+  regressioncheck/checks/naca/3D mesh               curved NGeo=2 mesh (for metric checks)
+Only data files are converted (to .npz); no reference source code is copied.
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+from galaexi_b200.host import h5lite  # noqa: E402
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(__file__), "..", "tests", "golden")
+
+
+def fort_records(path):
+    b = open(path, "rb").read()
+    o, recs = 0, []
+    while o < len(b):
+        n = int(np.frombuffer(b, "<i4", 1, o)[0])
+        recs.append(b[o + 4:o + 4 + n])
+        assert int(np.frombuffer(b, "<i4", 1, o + 4 + n)[0]) == n
+        o += 8 + n
+    return recs
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    U = os.path.join(REF, "unitTests")
+    g = {}
+    r = fort_records(os.path.join(U, "NodesAndWeights.bin"))[0]
+    g["nodes_xi_w_wbary"] = np.frombuffer(r, "<f8").reshape(3, 4, 10, 11)     # [xi|w|wBary][G,GL,CL,VISU][N-1][0:10]
+    r = fort_records(os.path.join(U, "DerivativeMatrix.bin"))[0]
+    g["D"] = np.frombuffer(r, "<f8").reshape(40, 11, 11)                      # [10*(type-1)+N-1][col][row]
+    r = fort_records(os.path.join(U, "UnittestElementData3D.bin"))[0]
+    o = 0
+    g["ued_nElems"] = np.frombuffer(r, "<i4", 1, o); o += 4
+    g["ued_SideToElem"] = np.frombuffer(r, "<i4", 30, o).reshape(6, 5); o += 120
+    g["ued_ranges"] = np.frombuffer(r, "<i4", 3, o); o += 12
+    g["ued_S2V2"] = np.frombuffer(r, "<i4", 6000, o).reshape(6, 5, 10, 10, 2); o += 24000
+    for nm in ("L_Minus", "L_Plus", "L_HatPlus", "L_HatMinus"):
+        g["ued_" + nm] = np.frombuffer(r, "<f8", 10, o); o += 80
+    g["ued_sJ"] = np.frombuffer(r, "<f8", 2000, o).reshape(2, 10, 10, 10); o += 16000
+    assert o == len(r)
+    g["p2f_Uvol"] = np.frombuffer(fort_records(os.path.join(U, "ProlongToFaceUvol.bin"))[0], "<f8").reshape(10, 10, 10)
+    for nt in ("G", "GL"):
+        rr = fort_records(os.path.join(U, f"ProlongToFace_{nt}3D.bin"))
+        g[f"p2f_{nt}"] = np.frombuffer(rr[0], "<f8").reshape(6, 10, 10)       # [side][q][p]
+    g["si_Flux"] = np.frombuffer(fort_records(os.path.join(U, "SurfIntFlux.bin"))[0], "<f8").reshape(6, 10, 10)
+    for nt in ("G", "GL"):
+        rr = fort_records(os.path.join(U, f"SurfInt_{nt}3D.bin"))
+        g[f"si_{nt}"] = np.frombuffer(rr[0], "<f8").reshape(10, 10, 10)       # [k][j][i]
+    rr = fort_records(os.path.join(U, "Vandermonde.bin"))
+    g["vdm_raw"] = np.frombuffer(b"".join(rr), "<f8")
+    np.savez_compressed(os.path.join(OUT, "unit_goldens.npz"), **g)
+
+    # regression meshes + references
+    def mesh_npz(src, dst):
+        m = h5lite.read_hopr_mesh(os.path.join(REF, src))
+        np.savez_compressed(os.path.join(OUT, dst), NGeo=m["NGeo"], ElemInfo=m["ElemInfo"], SideInfo=m["SideInfo"],
+                            NodeCoords=m["NodeCoords"], BCNames=np.array(m["BCNames"]), BCType=m["BCType"])
+    mesh_npz("regressioncheck/checks/tgv/split/CART_HEX_PERIODIC_008_mesh.h5", "tgv_split_mesh.npz")
+    mesh_npz("regressioncheck/checks/parabolic/cavity_3D/cavity4x4x4_mesh.h5", "cavity3d_mesh.npz")
+    mesh_npz("regressioncheck/checks/naca/3D/NACA0012_652_Ng2_mesh.h5", "naca_mesh.npz")
+    mesh_npz("tutorials/convtest/CART_HEX_PERIODIC_002_mesh.h5", "cart_periodic_002_mesh.npz")
+    csv = np.loadtxt(os.path.join(REF, "regressioncheck/checks/tgv/split/TGV_Re1600_Split_TGVAnalysis_Reference.csv"),
+                     delimiter=",", skiprows=1, converters=lambda s: float(s.replace("E+0", "E+").replace("E-0", "E-")))
+    np.savez_compressed(os.path.join(OUT, "tgv_split_csv.npz"), rows=csv[:40])
+    st = h5lite.read_state(os.path.join(REF, "regressioncheck/checks/parabolic/cavity_3D/reggie_cavity_Re100_State_0000001.000000000.h5"))
+    np.savez_compressed(os.path.join(OUT, "cavity3d_state.npz"), DG_Solution=st["DG_Solution"], Time=st["attrs"]["Time"])
+    print("wrote", sorted(os.listdir(OUT)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,559 @@
+// Host side of the C ABI (include/dgx.h): device memory ownership, layout conversion at the boundary,
+// the RHS / Runge-Kutta orchestration on CUDA streams and the NCCL face-halo exchange.
+//
+// Orchestration replaces DGTimeDerivative_weakForm (dg/dg.f90:255-425) + TimeStepByLSERKW2
+// (timedisc/timestep.f90:49-120) of the reference. Differences by design:
+//   * 3 fused kernels per stage (k_lifting, k_sideflux, k_volsurf) instead of ~20, no device-wide syncs;
+//   * face states are double buffered: the RK epilogue of stage s writes the faces stage s+1 reads;
+//   * 2 halo phases per Navier-Stokes stage instead of 4: both sides of an MPI face exchange their face
+//     state / face gradients, then lifting flux and numerical flux are evaluated redundantly (bit-identical)
+//     on both ranks, which removes the lifting-flux and flux messages (mpi/mpi.f90:277-387, SURVEY 2.3 rows 2,4).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dgx.h"
+#include "dgx_launch.h"
+
+using namespace dgx;
+
+namespace dgx {
+const KernelTable* kernel_table(int N, int nodeType) {
+    switch (N) {
+#define DGX_CASE(NN) case NN: return kernel_table_N##NN(nodeType);
+#ifdef DGX_HAVE_N1
+        DGX_CASE(1)
+#endif
+#ifdef DGX_HAVE_N2
+        DGX_CASE(2)
+#endif
+#ifdef DGX_HAVE_N3
+        DGX_CASE(3)
+#endif
+#ifdef DGX_HAVE_N4
+        DGX_CASE(4)
+#endif
+#ifdef DGX_HAVE_N5
+        DGX_CASE(5)
+#endif
+#ifdef DGX_HAVE_N6
+        DGX_CASE(6)
+#endif
+#ifdef DGX_HAVE_N7
+        DGX_CASE(7)
+#endif
+#ifdef DGX_HAVE_N8
+        DGX_CASE(8)
+#endif
+#ifdef DGX_HAVE_N9
+        DGX_CASE(9)
+#endif
+        default: return nullptr;
+    }
+}
+}  // namespace dgx
+
+// ------------------------------------------------------------------------------------------------------
+// NCCL through dlopen: single-GPU use must not depend on libnccl being present
+// ------------------------------------------------------------------------------------------------------
+namespace {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat64 = 8, ncclMin = 3 };
+struct Nccl {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string& err) {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) { err = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
+#define SYM(f) *(void**)(&f) = dlsym(lib, "nccl" #f); if (!f) { err = "missing symbol nccl" #f; return false; }
+        SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(Send) SYM(Recv) SYM(AllReduce) SYM(GroupStart) SYM(GroupEnd) SYM(GetErrorString)
+#undef SYM
+        return true;
+    }
+};
+Nccl g_nccl;
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------
+struct dgx_handle {
+    dgx_config cfg;  // scalar copies only; pointers are not retained
+    int n, n2, n3;
+    const KernelTable* kt = nullptr;
+    KParams P;
+    std::string err;
+    long long launches = 0;
+    cudaStream_t s = nullptr, cs = nullptr;
+    cudaEvent_t evFaces = nullptr, evUhalo = nullptr, evGrad = nullptr, evGhalo = nullptr, evT0 = nullptr, evT1 = nullptr;
+    // device memory
+    std::vector<void*> allocs;
+    double *U = nullptr, *Ut = nullptr, *Ut_tmp = nullptr, *gradU = nullptr, *metrics = nullptr, *sJ = nullptr, *geo = nullptr;
+    double *Uf[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [buffer][master/slave]
+    double *gm = nullptr, *gs = nullptr, *Flux = nullptr;
+    double *stage = nullptr;  // staging for layout conversion, 5*nDOF doubles
+    double *dtOut = nullptr;  // [3] device
+    double *hPinned = nullptr;  // [4] pinned host scalars
+    int *errFlag = nullptr;
+    int cur = 0;
+    // element / side lists for overlap
+    int *innerList = nullptr, *bndList = nullptr;
+    int nInner = 0, nBnd = 0;
+    // RK
+    std::vector<double> RKA, RKb, RKc;
+    // MPI-like neighbour tables
+    std::vector<int> NbProc, nMine, nYour, offMine, offYour;
+    ncclComm_t comm = nullptr;
+    size_t nDOF() const { return (size_t)cfg.nElems * n3; }
+    size_t nFace() const { return (size_t)cfg.nSides * n2; }
+};
+
+namespace {
+
+int fail(dgx_handle* h, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    return 1;
+}
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return fail(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define NK(call)                                                                                       \
+    do {                                                                                               \
+        ncclResult_t r_ = (call);                                                                      \
+        if (r_ != 0) return fail(h, "%s failed: %s (%s:%d)", #call, g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T>
+int dalloc(dgx_handle* h, T** p, size_t count) {
+    void* q = nullptr;
+    CK(cudaMalloc(&q, (count ? count : 1) * sizeof(T)));
+    CK(cudaMemsetAsync(q, 0, (count ? count : 1) * sizeof(T), h->s));
+    h->allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+template <class T>
+int upload(dgx_handle* h, T** p, const T* host, size_t count) {
+    if (dalloc(h, p, count)) return 1;
+    if (count) CK(cudaMemcpyAsync(*p, host, count * sizeof(T), cudaMemcpyHostToDevice, h->s));
+    return 0;
+}
+
+inline unsigned blocks_for(size_t total, int bs) { return (unsigned)((total + bs - 1) / bs); }
+
+int check_launch(dgx_handle* h, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, "kernel launch %s failed: %s", what, cudaGetErrorString(e));
+    h->launches++;
+    return 0;
+}
+
+// ---- halo exchange: both directions for every MPI side range -----------------------------------------
+int exchange(dgx_handle* h, double* am, double* as, int nvar) {
+    const size_t per = (size_t)nvar * h->n2;
+    NK(g_nccl.GroupStart());
+    for (size_t ib = 0; ib < h->NbProc.size(); ib++) {
+        const int peer = h->NbProc[ib];
+        const size_t m0 = (size_t)h->offMine[ib] * per, mc = (size_t)h->nMine[ib] * per;
+        const size_t y0 = (size_t)h->offYour[ib] * per, yc = (size_t)h->nYour[ib] * per;
+        if (mc) {  // I am master: send my master data, receive the neighbour's slave data
+            NK(g_nccl.Send(am + m0, mc, ncclFloat64, peer, h->comm, h->cs));
+            NK(g_nccl.Recv(as + m0, mc, ncclFloat64, peer, h->comm, h->cs));
+        }
+        if (yc) {  // I am slave: send my slave data, receive the neighbour's master data
+            NK(g_nccl.Send(as + y0, yc, ncclFloat64, peer, h->comm, h->cs));
+            NK(g_nccl.Recv(am + y0, yc, ncclFloat64, peer, h->comm, h->cs));
+        }
+    }
+    NK(g_nccl.GroupEnd());
+    return 0;
+}
+
+// ---- one RHS evaluation (mode 0: store Ut) or RK stage (mode 1) ---------------------------------------
+struct StageTimes {
+    cudaEvent_t ev[8];
+    int nev = 0;
+};
+
+int rhs(dgx_handle* h, int mode, double mRKA, double b_dt, StageTimes* st = nullptr) {
+    const dgx_config& c = h->cfg;
+    const KernelTable* kt = h->kt;
+    KParams P = h->P;
+    P.Um = h->Uf[h->cur][0];
+    P.Us = h->Uf[h->cur][1];
+    P.UmNext = h->Uf[h->cur ^ 1][0];
+    P.UsNext = h->Uf[h->cur ^ 1][1];
+    const bool multi = c.nRanks > 1 && !h->NbProc.empty();
+    auto mark = [&](void) { if (st) cudaEventRecord(st->ev[st->nev++], h->s); };
+    mark();
+    if (multi) {
+        CK(cudaEventRecord(h->evFaces, h->s));
+        CK(cudaStreamWaitEvent(h->cs, h->evFaces, 0));
+        if (exchange(h, P.Um, P.Us, 5)) return 1;
+        CK(cudaEventRecord(h->evUhalo, h->cs));
+    }
+    KParams Pi = P, Pb = P;
+    if (multi) {
+        Pi.elemList = h->innerList; Pi.nList = h->nInner;
+        Pb.elemList = h->bndList; Pb.nList = h->nBnd;
+    }
+    if (c.parabolic) {
+        kt->lifting(multi ? Pi : P, multi ? h->nInner : c.nElems, h->s);
+        if (check_launch(h, "k_lifting")) return 1;
+        if (multi) {
+            CK(cudaStreamWaitEvent(h->s, h->evUhalo, 0));
+            if (h->nBnd) { kt->lifting(Pb, h->nBnd, h->s); if (check_launch(h, "k_lifting(bnd)")) return 1; }
+            CK(cudaEventRecord(h->evGrad, h->s));
+            CK(cudaStreamWaitEvent(h->cs, h->evGrad, 0));
+            if (exchange(h, P.gm, P.gs, 12)) return 1;
+            CK(cudaEventRecord(h->evGhalo, h->cs));
+        }
+    } else if (multi) {
+        CK(cudaStreamWaitEvent(h->s, h->evUhalo, 0));
+    }
+    mark();
+    // BC + inner sides
+    kt->sideflux(P, 0, c.lastInnerSide, h->s);
+    if (c.lastInnerSide > 0 && check_launch(h, "k_sideflux")) return 1;
+    mark();
+    if (!multi) {
+        kt->volsurf(P, mode, mRKA, b_dt, c.nElems, h->s);
+        if (check_launch(h, "k_volsurf")) return 1;
+    } else {
+        if (h->nInner) { kt->volsurf(Pi, mode, mRKA, b_dt, h->nInner, h->s); if (check_launch(h, "k_volsurf(inner)")) return 1; }
+        if (c.parabolic) CK(cudaStreamWaitEvent(h->s, h->evGhalo, 0));
+        const int nMPI = c.lastMPISide_YOUR - c.firstMPISide_MINE + 1;
+        if (nMPI > 0) { kt->sideflux(P, c.firstMPISide_MINE - 1, nMPI, h->s); if (check_launch(h, "k_sideflux(mpi)")) return 1; }
+        if (h->nBnd) { kt->volsurf(Pb, mode, mRKA, b_dt, h->nBnd, h->s); if (check_launch(h, "k_volsurf(bnd)")) return 1; }
+    }
+    mark();
+    if (mode == 1) h->cur ^= 1;
+    return 0;
+}
+
+int prolong_current(dgx_handle* h) {
+    KParams P = h->P;
+    P.Um = h->Uf[h->cur][0];
+    P.Us = h->Uf[h->cur][1];
+    h->kt->prolong(P, h->cfg.nElems, h->s);
+    return check_launch(h, "k_prolong");
+}
+
+int check_err_flag(dgx_handle* h, const char* where) {
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, h->errFlag, sizeof(int), cudaMemcpyDeviceToHost, h->s));
+    CK(cudaStreamSynchronize(h->s));
+    if (flag & 1) return fail(h, "%s: unsupported boundary condition type (supported: 2,3,4,9)", where);
+    return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* dgx_last_error(const dgx_handle* h) { return h ? h->err.c_str() : "null handle"; }
+long long dgx_launch_count(const dgx_handle* h) { return h ? h->launches : 0; }
+
+int dgx_nccl_unique_id(char* out128) {
+    std::string err;
+    if (!g_nccl.load(err)) return 1;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != 0) return 2;
+    memcpy(out128, id.internal, 128);
+    return 0;
+}
+
+void dgx_destroy(dgx_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->s) cudaStreamSynchronize(h->s);
+    if (h->cs) cudaStreamSynchronize(h->cs);
+    if (h->comm) g_nccl.CommDestroy(h->comm);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->hPinned) cudaFreeHost(h->hPinned);
+    cudaEvent_t evs[] = {h->evFaces, h->evUhalo, h->evGrad, h->evGhalo, h->evT0, h->evT1};
+    for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+    if (h->s) cudaStreamDestroy(h->s);
+    if (h->cs) cudaStreamDestroy(h->cs);
+    delete h;
+}
+
+int dgx_create(dgx_handle** out, const dgx_config* cfg) {
+    if (!out || !cfg) return 1;
+    dgx_handle* h = new dgx_handle();
+    *out = h;  // returned even on failure so that dgx_last_error can be queried; caller destroys it
+    h->cfg = *cfg;
+    const dgx_config& c = h->cfg;
+    if (c.N < 1 || c.N > 9) return fail(h, "polynomial degree N=%d not supported (1..9)", c.N);
+    h->n = c.N + 1; h->n2 = h->n * h->n; h->n3 = h->n2 * h->n;
+    h->kt = kernel_table(c.N, c.nodeType);
+    if (!h->kt) return fail(h, "no kernels compiled for N=%d (rebuild with this degree enabled)", c.N);
+    if (c.nodeType != 1 && c.nodeType != 2) return fail(h, "nodeType must be 1 (Gauss) or 2 (Gauss-Lobatto)");
+    if (c.splitDG >= 0 && c.nodeType != 2) return fail(h, "Wrong Pointset: Gauss-Lobatto-Points are mandatory for using SplitDG !");
+    if (c.splitDG != -1 && c.splitDG != 0 && c.splitDG != 3 && c.splitDG != 4) return fail(h, "SplitDG variant %d not available (SD=0, KG=3, PI=4)", c.splitDG);
+    if (c.riemann != 0 && c.riemann != 1 && c.riemann != 3 && c.riemann != 5) return fail(h, "Riemann solver %d not available (LF=0, Roe=1, RoeEntropyFix=3, HLLC=5)", c.riemann);
+    if (c.splitDG >= 0 && c.riemann == 5) return fail(h, "HLLC is not available with SplitDG (as in the reference, src/CMakeLists.txt:113-117)");
+    if (c.nRKStages < 1) return fail(h, "nRKStages < 1");
+    CK(cudaSetDevice(c.device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, c.device));
+    if (prop.major < 10) return fail(h, "device %s is sm_%d%d; this library is built for sm_100a (B200) only", prop.name, prop.major, prop.minor);
+    int lo, hi;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&h->s, cudaStreamNonBlocking, lo));
+    CK(cudaStreamCreateWithPriority(&h->cs, cudaStreamNonBlocking, hi));
+    cudaEvent_t* evs[] = {&h->evFaces, &h->evUhalo, &h->evGrad, &h->evGhalo};
+    for (cudaEvent_t* e : evs) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    CK(cudaEventCreate(&h->evT0));
+    CK(cudaEventCreate(&h->evT1));
+    { int r = h->kt->setup(); if (r) return fail(h, "cudaFuncSetAttribute failed: %s", cudaGetErrorString((cudaError_t)r)); }
+
+    const int n = h->n, n2 = h->n2, n3 = h->n3;
+    const size_t nDOF = h->nDOF(), nFace = h->nFace();
+    // ---- device arrays
+    if (dalloc(h, &h->U, 5 * nDOF) || dalloc(h, &h->Ut, 5 * nDOF) || dalloc(h, &h->Ut_tmp, 5 * nDOF)) return 1;
+    if (dalloc(h, &h->gradU, c.parabolic ? 12 * nDOF : 1)) return 1;
+    if (dalloc(h, &h->metrics, 9 * nDOF) || dalloc(h, &h->sJ, nDOF) || dalloc(h, &h->geo, 10 * nFace)) return 1;
+    for (int b = 0; b < 2; b++) for (int m = 0; m < 2; m++) if (dalloc(h, &h->Uf[b][m], 5 * nFace)) return 1;
+    if (dalloc(h, &h->gm, c.parabolic ? 12 * nFace : 1) || dalloc(h, &h->gs, c.parabolic ? 12 * nFace : 1)) return 1;
+    if (dalloc(h, &h->Flux, 5 * nFace)) return 1;
+    if (dalloc(h, &h->stage, 5 * nDOF > 12 * nFace ? 5 * nDOF : 12 * nFace)) return 1;
+    if (dalloc(h, &h->dtOut, 4) || dalloc(h, &h->errFlag, 1)) return 1;
+    CK(cudaMallocHost((void**)&h->hPinned, 8 * sizeof(double)));
+    // ---- geometry: upload in reference layout, repack on the device
+    {
+        double *mf, *mg, *mh, *nv, *t1, *t2, *se;
+        if (upload(h, &mf, c.Metrics_fTilde, 3 * nDOF) || upload(h, &mg, c.Metrics_gTilde, 3 * nDOF) || upload(h, &mh, c.Metrics_hTilde, 3 * nDOF)) return 1;
+        k_pack_metrics<<<blocks_for(9 * nDOF, 256), 256, 0, h->s>>>(mf, mg, mh, h->metrics, n3, 9 * nDOF);
+        if (check_launch(h, "k_pack_metrics")) return 1;
+        CK(cudaMemcpyAsync(h->sJ, c.sJ, nDOF * sizeof(double), cudaMemcpyHostToDevice, h->s));
+        if (upload(h, &nv, c.NormVec, 3 * nFace) || upload(h, &t1, c.TangVec1, 3 * nFace) || upload(h, &t2, c.TangVec2, 3 * nFace) || upload(h, &se, c.SurfElem, nFace)) return 1;
+        if (nFace) { k_pack_geo<<<blocks_for(10 * nFace, 256), 256, 0, h->s>>>(nv, t1, t2, se, h->geo, n2, 10 * nFace); if (check_launch(h, "k_pack_geo")) return 1; }
+        CK(cudaStreamSynchronize(h->s));
+        // free the temporaries (last 7 allocations)
+        for (int x = 0; x < 7; x++) { cudaFree(h->allocs.back()); h->allocs.pop_back(); }
+    }
+    // ---- kernel parameter block
+    KParams& P = h->P;
+    memset(&P, 0, sizeof P);
+    P.nElems = c.nElems; P.nSides = c.nSides; P.nBCSides = c.nBCSides;
+    P.firstInner = c.firstInnerSide; P.lastInner = c.lastInnerSide;
+    P.firstMINE = c.firstMPISide_MINE; P.lastMINE = c.lastMPISide_MINE; P.firstYOUR = c.firstMPISide_YOUR; P.lastYOUR = c.lastMPISide_YOUR;
+    P.splitDG = c.splitDG; P.riemann = c.riemann; P.parabolic = c.parabolic;
+    P.eos.kappa = c.EOS_Vars[0]; P.eos.R = c.EOS_Vars[1]; P.eos.Pr = c.EOS_Vars[2]; P.eos.mu0 = c.EOS_Vars[3];
+    P.eos.Ts = c.EOS_Vars[4]; P.eos.Tref = c.EOS_Vars[5]; P.eos.ExpoSuth = c.EOS_Vars[6]; P.eos.cSuth = c.EOS_Vars[7];
+    P.eos.viscLaw = c.viscLaw;
+    for (int x = 0; x < n * n; x++) { P.D_T[x] = c.D_T[x]; P.D_Hat_T[x] = c.D_Hat_T[x]; P.DVolSurf[x] = c.DVolSurf ? c.DVolSurf[x] : 0.0; }
+    for (int x = 0; x < n; x++) { P.L_Minus[x] = c.L_Minus[x]; P.L_Plus[x] = c.L_Plus[x]; P.L_HatMinus[x] = c.L_HatMinus[x]; P.L_HatPlus[x] = c.L_HatPlus[x]; }
+    {
+        int *e2s, *s2v2, *s2v2i, *bcs;
+        double* ref;
+        if (upload(h, &e2s, c.ElemToSide, (size_t)18 * c.nElems)) return 1;
+        if (upload(h, &s2v2, c.S2V2, (size_t)2 * n2 * 30) || upload(h, &s2v2i, c.S2V2_inv, (size_t)2 * n2 * 30)) return 1;
+        if (upload(h, &bcs, c.BCSides, (size_t)2 * c.nBCSides)) return 1;
+        if (upload(h, &ref, c.RefStatePrim, (size_t)6 * (c.nRefState > 0 ? c.nRefState : 0))) return 1;
+        P.E2S = e2s; P.S2V2 = s2v2; P.S2V2inv = s2v2i; P.BCSides = bcs; P.RefPrim = ref;
+    }
+    P.metrics = h->metrics; P.sJ = h->sJ; P.geo = h->geo;
+    P.U = h->U; P.Ut = h->Ut; P.Ut_tmp = h->Ut_tmp; P.gradU = h->gradU;
+    P.gm = h->gm; P.gs = h->gs; P.Flux = h->Flux; P.errFlag = h->errFlag;
+    P.elemList = nullptr; P.nList = 0;
+    // benign state on faces that are never written (slave side of BC sides), cf. dg.f90:118-121
+    {
+        std::vector<double> init(5 * nFace, 0.0);
+        for (size_t s = 0; s < (size_t)c.nSides; s++)
+            for (int pq = 0; pq < n2; pq++) { init[s * 5 * n2 + 0 * n2 + pq] = 1.0; init[s * 5 * n2 + 4 * n2 + pq] = 1.0; }
+        for (int b = 0; b < 2; b++) for (int m = 0; m < 2; m++)
+            if (nFace) CK(cudaMemcpyAsync(h->Uf[b][m], init.data(), 5 * nFace * sizeof(double), cudaMemcpyHostToDevice, h->s));
+        CK(cudaStreamSynchronize(h->s));
+    }
+    h->RKA.assign(c.RKA, c.RKA + c.nRKStages);
+    h->RKb.assign(c.RKb, c.RKb + c.nRKStages);
+    h->RKc.assign(c.RKc, c.RKc + c.nRKStages);
+    // ---- domain decomposition
+    if (c.nRanks > 1) {
+        for (int ib = 0; ib < c.nNbProcs; ib++) {
+            h->NbProc.push_back(c.NbProc[ib]);
+            h->nMine.push_back(c.nMPISides_MINE_Proc[ib]);
+            h->nYour.push_back(c.nMPISides_YOUR_Proc[ib]);
+            h->offMine.push_back(c.offsetMPISides_MINE[ib]);
+            h->offYour.push_back(c.offsetMPISides_YOUR[ib]);
+        }
+        // element lists: elements touching an MPI side vs the rest
+        std::vector<int> inner, bnd;
+        for (int e = 0; e < c.nElems; e++) {
+            bool mpi = false;
+            for (int l = 0; l < 6; l++) if (c.ElemToSide[0 + 3 * (l + 6 * e)] >= c.firstMPISide_MINE) mpi = true;
+            (mpi ? bnd : inner).push_back(e);
+        }
+        h->nInner = (int)inner.size(); h->nBnd = (int)bnd.size();
+        if (upload(h, &h->innerList, inner.data(), inner.size()) || upload(h, &h->bndList, bnd.data(), bnd.size())) return 1;
+        if (!c.ncclUniqueId) return fail(h, "nRanks>1 requires ncclUniqueId");
+        if (!g_nccl.load(h->err)) return 1;
+        ncclUniqueId id;
+        memcpy(id.internal, c.ncclUniqueId, 128);
+        NK(g_nccl.CommInitRank(&h->comm, c.nRanks, id, c.myRank));
+    }
+    CK(cudaStreamSynchronize(h->s));
+    h->cfg.RefStatePrim = nullptr;  // pointers are not retained
+    return 0;
+}
+
+int dgx_sync(dgx_handle* h) {
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->s));
+    CK(cudaStreamSynchronize(h->cs));
+    return 0;
+}
+
+int dgx_set_state(dgx_handle* h, const double* U) {
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t tot = 5 * h->nDOF();
+    if (tot) {
+        CK(cudaMemcpyAsync(h->stage, U, tot * sizeof(double), cudaMemcpyHostToDevice, h->s));
+        k_aos_to_soa<5><<<blocks_for(tot, 256), 256, 0, h->s>>>(h->stage, h->U, h->n3, tot);
+        if (check_launch(h, "k_aos_to_soa")) return 1;
+        CK(cudaMemsetAsync(h->Ut_tmp, 0, tot * sizeof(double), h->s));
+        if (prolong_current(h)) return 1;
+    }
+    CK(cudaStreamSynchronize(h->s));
+    return 0;
+}
+
+static int get_vol(dgx_handle* h, const double* soa, double* host, int soaStride, int soaOffset, int nvar) {
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t tot = (size_t)nvar * h->nDOF();
+    if (!tot) return 0;
+    if (nvar == 5) k_soa_to_aos<5><<<blocks_for(tot, 256), 256, 0, h->s>>>(soa, h->stage, h->n3, tot, soaStride, soaOffset);
+    else k_soa_to_aos<4><<<blocks_for(tot, 256), 256, 0, h->s>>>(soa, h->stage, h->n3, tot, soaStride, soaOffset);
+    if (check_launch(h, "k_soa_to_aos")) return 1;
+    CK(cudaMemcpyAsync(host, h->stage, tot * sizeof(double), cudaMemcpyDeviceToHost, h->s));
+    CK(cudaStreamSynchronize(h->s));
+    return 0;
+}
+int dgx_get_state(dgx_handle* h, double* U) { return get_vol(h, h->U, U, 5, 0, 5); }
+int dgx_get_ut(dgx_handle* h, double* Ut) { return get_vol(h, h->Ut, Ut, 5, 0, 5); }
+int dgx_get_gradients(dgx_handle* h, double* gx, double* gy, double* gz) {
+    if (!h->cfg.parabolic) return fail(h, "gradients are only available for PARABOLIC runs");
+    if (get_vol(h, h->gradU, gx, 12, 0, 4)) return 1;
+    if (get_vol(h, h->gradU, gy, 12, 4, 4)) return 1;
+    return get_vol(h, h->gradU, gz, 12, 8, 4);
+}
+
+int dgx_time_derivative(dgx_handle* h, double t) {
+    (void)t;
+    CK(cudaSetDevice(h->cfg.device));
+    if (rhs(h, 0, 0.0, 0.0)) return 1;
+    return check_err_flag(h, "dgx_time_derivative");
+}
+
+int dgx_rk_stage(dgx_handle* h, int iStage, double t, double dt) {
+    (void)t;
+    CK(cudaSetDevice(h->cfg.device));
+    if (iStage < 1 || iStage > h->cfg.nRKStages) return fail(h, "iStage out of range");
+    const double mRKA = (iStage == 1) ? 0.0 : -1.0 * h->RKA[iStage - 1];
+    return rhs(h, 1, mRKA, h->RKb[iStage - 1] * dt);
+}
+
+int dgx_rk_step(dgx_handle* h, double t, double dt) {
+    for (int st = 1; st <= h->cfg.nRKStages; st++)
+        if (dgx_rk_stage(h, st, st == 1 ? t : t + h->RKc[st - 1] * dt, dt)) return 1;
+    return 0;
+}
+
+int dgx_calc_timestep(dgx_handle* h, double* dt, int* errType) {
+    CK(cudaSetDevice(h->cfg.device));
+    const double big = 1.7976931348623157e308;
+    h->hPinned[0] = big; h->hPinned[1] = big; h->hPinned[2] = 0.0;
+    CK(cudaMemcpyAsync(h->dtOut, h->hPinned, 3 * sizeof(double), cudaMemcpyHostToDevice, h->s));
+    CK(cudaMemsetAsync(h->errFlag, 0, sizeof(int), h->s));
+    h->kt->timestep(h->P, h->cfg.CFLScale, h->cfg.DFLScale, h->dtOut, h->s);
+    if (h->cfg.nElems && check_launch(h, "k_timestep")) return 1;
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, h->errFlag, sizeof(int), cudaMemcpyDeviceToHost, h->s));
+    if (h->comm) {
+        CK(cudaStreamSynchronize(h->s));
+        h->hPinned[4] = -(double)(flag != 0);
+        CK(cudaMemcpyAsync(h->dtOut + 2, h->hPinned + 4, sizeof(double), cudaMemcpyHostToDevice, h->s));
+        NK(g_nccl.AllReduce(h->dtOut, h->dtOut, 3, ncclFloat64, ncclMin, h->comm, h->s));  // calctimestep.f90:181
+    }
+    CK(cudaMemcpyAsync(h->hPinned, h->dtOut, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->s));
+    CK(cudaStreamSynchronize(h->s));
+    if (h->comm) flag = (h->hPinned[2] < 0.0) ? 2 : 0;
+    if (errType) *errType = flag ? 2 : 0;
+    if (dt) *dt = h->hPinned[0] < h->hPinned[1] ? h->hPinned[0] : h->hPinned[1];
+    return 0;
+}
+
+int dgx_run_steps(dgx_handle* h, int nSteps, double t, double dt, int adaptive_dt, float* ms, long long* launches) {
+    CK(cudaSetDevice(h->cfg.device));
+    const long long l0 = h->launches;
+    CK(cudaStreamSynchronize(h->s));
+    CK(cudaEventRecord(h->evT0, h->s));
+    for (int it = 0; it < nSteps; it++) {
+        if (adaptive_dt) { int et = 0; if (dgx_calc_timestep(h, &dt, &et)) return 1; if (et) return fail(h, "timestep is NaN / state not admissible at t=%g", t); }
+        if (dgx_rk_step(h, t, dt)) return 1;
+        t += dt;
+    }
+    CK(cudaEventRecord(h->evT1, h->s));
+    CK(cudaEventSynchronize(h->evT1));
+    CK(cudaStreamSynchronize(h->cs));
+    float m = 0.f;
+    CK(cudaEventElapsedTime(&m, h->evT0, h->evT1));
+    if (ms) *ms = m;
+    if (launches) *launches = h->launches - l0;
+    return check_err_flag(h, "dgx_run_steps");
+}
+
+int dgx_profile_stage(dgx_handle* h, double t, double dt, int cap, const char** names, float* ms, int* count) {
+    (void)t;
+    if (count) *count = 0;
+    CK(cudaSetDevice(h->cfg.device));
+    StageTimes st;
+    for (int i = 0; i < 8; i++) CK(cudaEventCreate(&st.ev[i]));
+    const int stage = h->cfg.nRKStages > 1 ? 2 : 1;
+    const double mRKA = (stage == 1) ? 0.0 : -1.0 * h->RKA[stage - 1];
+    if (rhs(h, 1, mRKA, h->RKb[stage - 1] * dt, &st)) return 1;
+    CK(cudaStreamSynchronize(h->s));
+    static const char* nm[] = {"halo+lifting", "sideflux", "volsurf_rk"};
+    int cnt = 0;
+    for (int i = 0; i + 1 < st.nev && cnt < cap && i < 3; i++) {
+        float m = 0.f;
+        cudaEventElapsedTime(&m, st.ev[i], st.ev[i + 1]);
+        names[cnt] = nm[i];
+        ms[cnt] = m;
+        cnt++;
+    }
+    for (int i = 0; i < 8; i++) cudaEventDestroy(st.ev[i]);
+    if (count) *count = cnt;
+    return 0;
+}
+
+}  // extern "C"

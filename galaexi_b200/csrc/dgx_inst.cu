@@ -1,0 +1,49 @@
+// Kernel instantiations for one polynomial degree (compile with -DDGX_N=<N>); see dgx_kernels.cuh.
+#include "dgx_launch.h"
+#ifndef DGX_N
+#error "compile with -DDGX_N=<polynomial degree>"
+#endif
+namespace dgx {
+namespace {
+constexpr int n = DGX_N + 1;
+constexpr int n3 = n * n * n;
+
+template <int NT>
+struct L {
+    static int setup() {
+        cudaError_t e;
+        e = cudaFuncSetAttribute(k_lifting<n, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lifting_smem_bytes<n>());
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(k_volsurf<n, NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)volsurf_smem_bytes<n>());
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(k_volsurf<n, NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)volsurf_smem_bytes<n>());
+        return (int)e;
+    }
+    static void prolong(const KParams& P, int nb, cudaStream_t s) {
+        if (nb > 0) k_prolong<n, NT><<<nb, n3, 0, s>>>(P);
+    }
+    static void lifting(const KParams& P, int nb, cudaStream_t s) {
+        if (nb > 0) k_lifting<n, NT><<<nb, n3, lifting_smem_bytes<n>(), s>>>(P);
+    }
+    static void sideflux(const KParams& P, int side0, int nS, cudaStream_t s) {
+        if (nS <= 0) return;
+        const long long tot = (long long)nS * n * n;
+        k_sideflux<n><<<(unsigned)((tot + 127) / 128), 128, 0, s>>>(P, side0, nS);
+    }
+    static void volsurf(const KParams& P, int mode, double mRKA, double b_dt, int nb, cudaStream_t s) {
+        if (nb <= 0) return;
+        if (mode == 0) k_volsurf<n, NT, 0><<<nb, n3, volsurf_smem_bytes<n>(), s>>>(P, mRKA, b_dt);
+        else k_volsurf<n, NT, 1><<<nb, n3, volsurf_smem_bytes<n>(), s>>>(P, mRKA, b_dt);
+    }
+    static void timestep(const KParams& P, double CFL, double DFL, double* out, cudaStream_t s) {
+        if (P.nElems > 0) k_timestep<n><<<P.nElems, timestep_threads<n>(), 0, s>>>(P, CFL, DFL, out);
+    }
+};
+const KernelTable tabG = {L<1>::setup, L<1>::prolong, L<1>::lifting, L<1>::sideflux, L<1>::volsurf, L<1>::timestep};
+const KernelTable tabGL = {L<2>::setup, L<2>::prolong, L<2>::lifting, L<2>::sideflux, L<2>::volsurf, L<2>::timestep};
+}  // namespace
+
+#define DGX_CAT2(a, b) a##b
+#define DGX_CAT(a, b) DGX_CAT2(a, b)
+const KernelTable* DGX_CAT(kernel_table_N, DGX_N)(int nodeType) { return nodeType == 2 ? &tabGL : &tabG; }
+}  // namespace dgx

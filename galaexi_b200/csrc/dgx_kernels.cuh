@@ -1,0 +1,689 @@
+// Element- and side-centric CUDA kernels of the DGSEM operator for sm_100a (FP64 CUDA cores, HBM-bound).
+//
+// Data layout in HBM (all FP64, per-variable contiguous tiles so every warp access is a coalesced 8-byte
+// stream; the reference's AoS layout U(nVar,i,j,k,iElem) is only used at the C ABI):
+//   volume   U, Ut, Ut_tmp : [elem][5][n^3]        gradU : [elem][3*4][n^3] (d*4+v; d=x,y,z; v=u,v,w,T)
+//            metrics       : [elem][9][n^3]        (f1 f2 f3 g1 g2 g3 h1 h2 h3)   sJ : [elem][n^3]
+//   sides    Um, Us, Flux  : [side][5][n^2]        gm, gs : [side][12][n^2]       geo: [side][10][n^2]
+//            geo = nv(3), t1(3), t2(3), SurfElem   (side-local (p,q) index, p fastest)
+// One CTA works on one element (n^3 threads); its tile is staged in shared memory, the three 1-D
+// tensor-product sweeps read lines from shared memory, face data are staged through shared memory in the
+// element's own face-node order so that the surface integral is a conflict-free gather.
+//
+// Reference kernels replaced per launch (paths relative to /root/reference/src):
+//   k_prolong   interpolation/prolongtoface.t90:168-344
+//   k_lifting   equations/.../eos.f90:328 (ConsToPrim), dg/lifting/lifting_fillflux.t90:39-256,
+//               idealgas/getboundaryflux.f90:945-1019, dg/lifting/lifting_volint.t90:262-328,
+//               dg/surfint.t90:591-725 (x3, with sJ), interpolation/prolongtoface.t90 (x3 lifting)
+//   k_sideflux  dg/fillflux.f90:45-172, equations/navierstokes/riemann.f90:401,638, getboundaryflux.f90:542-838
+//   k_volsurf   eos.f90:328, flux.f90:304-384, dg/applydmatrix.t90:19-75, dg/volint.f90:265-353,
+//               dg/surfint.t90:352-586, globals/vector.f90:210-226 (x -1), interpolation/applyjacobian.t90:196,
+//               globals/vector.f90:163-183 (RK 2N update) and prolongtoface of the next stage
+//   k_timestep  equations/navierstokes/calctimestep.f90:192-296
+#pragma once
+#include "dgx_physics.cuh"
+
+namespace dgx {
+
+constexpr int MAXN1 = 10;  // n = N+1 <= 10
+
+struct KParams {
+    int nElems, nSides, nBCSides;
+    int firstInner, lastInner, firstMINE, lastMINE, firstYOUR, lastYOUR;  // 1-based inclusive
+    int splitDG, riemann, parabolic;
+    Eos eos;
+    // small operator tables (copied to shared memory by the kernels), Fortran (a,b) at [a + n*b]
+    double D_T[MAXN1 * MAXN1], D_Hat_T[MAXN1 * MAXN1], DVolSurf[MAXN1 * MAXN1];
+    double L_Minus[MAXN1], L_Plus[MAXN1], L_HatMinus[MAXN1], L_HatPlus[MAXN1];
+    const int* E2S;      // (3,6,nElems)
+    const int* S2V2;     // (2,n,n,5,6)
+    const int* S2V2inv;
+    const int* BCSides;  // (2,nBCSides)
+    const double* RefPrim;
+    const double* metrics;
+    const double* sJ;
+    const double* geo;
+    double* U;
+    double* Ut;
+    double* Ut_tmp;
+    double* gradU;
+    double* Um;  // face states read by this stage
+    double* Us;
+    double* UmNext;  // face states written by the RK epilogue (double buffered)
+    double* UsNext;
+    double* gm;
+    double* gs;
+    double* Flux;
+    const int* elemList;  // optional indirection (MPI-boundary / inner element lists), or nullptr
+    int nList;
+    int* errFlag;
+};
+
+enum { ZETA_MINUS = 1, ETA_MINUS = 2, XI_PLUS = 3, ETA_PLUS = 4, XI_MINUS = 5, ZETA_PLUS = 6 };
+
+template <int n>
+__device__ __forceinline__ int s2v2(const int* __restrict__ tab, int c, int p, int q, int flip, int loc) {
+    return __ldg(&tab[c + 2 * (p + n * (q + n * (flip + 5 * (loc - 1))))]);
+}
+
+// volume index of face node (a,b) at depth l for local side loc
+template <int n>
+__device__ __forceinline__ int face_vol_index(int loc, int a, int b, int l) {
+    switch (loc) {
+        case XI_MINUS:
+        case XI_PLUS: return l + n * (a + n * b);
+        case ETA_MINUS:
+        case ETA_PLUS: return a + n * (l + n * b);
+        default: return a + n * (b + n * l);
+    }
+}
+__device__ __forceinline__ bool is_minus(int loc) { return loc == XI_MINUS || loc == ETA_MINUS || loc == ZETA_MINUS; }
+
+// Extract the 6 faces of a shared-memory element tile [NVAR][n^3] into the side arrays (master if flip==0,
+// else slave), in side-local orientation. GL: copy of the boundary layer; Gauss: contraction with L_Minus/L_Plus.
+template <int n, int NT, int NVAR>
+__device__ __forceinline__ void extract_faces(const double* __restrict__ tile, double* __restrict__ dstM, double* __restrict__ dstS,
+                                              const int* __restrict__ e2s, const int* __restrict__ S2V2, const double* __restrict__ sLm,
+                                              const double* __restrict__ sLp) {
+    constexpr int n2 = n * n, n3 = n2 * n;
+    for (int f = threadIdx.x; f < 6 * n2; f += blockDim.x) {
+        const int loc = f / n2 + 1;
+        const int pq = f - (loc - 1) * n2;
+        const int q = pq / n, p = pq - q * n;
+        const int side = __ldg(&e2s[0 + 3 * (loc - 1)]) - 1;
+        const int flip = __ldg(&e2s[1 + 3 * (loc - 1)]);
+        const int a = s2v2<n>(S2V2, 0, p, q, flip, loc);
+        const int b = s2v2<n>(S2V2, 1, p, q, flip, loc);
+        double* dst = (flip == 0 ? dstM : dstS) + (size_t)side * NVAR * n2 + pq;
+        if (NT == 2) {
+            const int node = face_vol_index<n>(loc, a, b, is_minus(loc) ? 0 : n - 1);
+#pragma unroll
+            for (int v = 0; v < NVAR; v++) dst[v * n2] = tile[v * n3 + node];
+        } else {
+            const double* L = is_minus(loc) ? sLm : sLp;
+            const int base = face_vol_index<n>(loc, a, b, 0);
+            const int stride = face_vol_index<n>(loc, a, b, 1) - base;
+#pragma unroll
+            for (int v = 0; v < NVAR; v++) {
+                double acc = tile[v * n3 + base] * L[0];
+#pragma unroll
+                for (int l = 1; l < n; l++) acc += tile[v * n3 + base + l * stride] * L[l];
+                dst[v * n2] = acc;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+template <int n, int NT>
+__global__ void __launch_bounds__(n* n* n) k_prolong(const KParams P) {
+    constexpr int n2 = n * n, n3 = n2 * n;
+    __shared__ double tile[5 * n3];
+    __shared__ double sLm[n], sLp[n];
+    const int e = P.elemList ? P.elemList[blockIdx.x] : blockIdx.x;
+    const int t = threadIdx.x;
+    if (t < n) { sLm[t] = P.L_Minus[t]; sLp[t] = P.L_Plus[t]; }
+    const double* U = P.U + (size_t)e * 5 * n3;
+#pragma unroll
+    for (int v = 0; v < 5; v++) tile[v * n3 + t] = U[v * n3 + t];
+    __syncthreads();
+    extract_faces<n, NT, 5>(tile, P.Um, P.Us, P.E2S + 18 * e, P.S2V2, sLm, sLp);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// BR1 lifting (strong form, non-conservative volume integral): gradU = sJ * ( M . D U + sum_faces F n Lhat )
+template <int n, int NT>
+__global__ void __launch_bounds__(n* n* n) k_lifting(const KParams P) {
+    constexpr int n2 = n * n, n3 = n2 * n;
+    extern __shared__ double smem[];
+    double* sT = smem;                 // [4][n3] lifting variables; later aliased by the gradient tile [12][n3]
+    double* sG = smem;                 // alias (used after the sweeps are done)
+    double* sF = smem + 12 * n3;       // [6][7][n2] face lifting flux (4) + normal (3), element face order
+    double* sD = sF + 6 * 7 * n2;      // D_T [n*n]
+    double* sLhm = sD + n * n;
+    double* sLhp = sLhm + n;
+    double* sLm = sLhp + n;
+    double* sLp = sLm + n;
+    const int e = P.elemList ? P.elemList[blockIdx.x] : blockIdx.x;
+    const int t = threadIdx.x;
+    for (int x = t; x < n * n; x += n3) sD[x] = P.D_T[x];
+    if (t < n) { sLhm[t] = P.L_HatMinus[t]; sLhp[t] = P.L_HatPlus[t]; sLm[t] = P.L_Minus[t]; sLp[t] = P.L_Plus[t]; }
+    const Eos eos = P.eos;
+    const int* e2s = P.E2S + 18 * e;
+
+    // 1. node: primitive lifting variables into the tile
+    {
+        const double* U = P.U + (size_t)e * 5 * n3;
+        double Uc[5], Pr[6];
+#pragma unroll
+        for (int v = 0; v < 5; v++) Uc[v] = U[v * n3 + t];
+        cons_to_prim(Pr, Uc, eos);
+        sT[0 * n3 + t] = Pr[VEL1];
+        sT[1 * n3 + t] = Pr[VEL2];
+        sT[2 * n3 + t] = Pr[VEL3];
+        sT[3 * n3 + t] = Pr[TEMP];
+    }
+    // 2. faces: lifting flux F = 1/2 (U_s - U_m) SurfElem in side orientation -> stored in element face order
+    for (int f = t; f < 6 * n2; f += n3) {
+        const int loc = f / n2 + 1;
+        const int pq = f - (loc - 1) * n2;
+        const int q = pq / n, p = pq - q * n;
+        const int side = __ldg(&e2s[0 + 3 * (loc - 1)]) - 1;
+        const int flip = __ldg(&e2s[1 + 3 * (loc - 1)]);
+        const int a = s2v2<n>(P.S2V2, 0, p, q, flip, loc);
+        const int b = s2v2<n>(P.S2V2, 1, p, q, flip, loc);
+        const double* g = P.geo + (size_t)side * 10 * n2 + pq;
+        const double nv[3] = {g[0 * n2], g[1 * n2], g[2 * n2]};
+        const double se = g[9 * n2];
+        double Um[5], Pm[6], Fl[4];
+#pragma unroll
+        for (int v = 0; v < 5; v++) Um[v] = P.Um[(size_t)side * 5 * n2 + v * n2 + pq];
+        cons_to_prim(Pm, Um, eos);
+        if (side < P.nBCSides) {
+            const int bct = __ldg(&P.BCSides[2 * side]), bcs = __ldg(&P.BCSides[2 * side + 1]);
+            const double t1[3] = {g[3 * n2], g[4 * n2], g[5 * n2]};
+            const double t2[3] = {g[6 * n2], g[7 * n2], g[8 * n2]};
+            double Pb[6];
+            if (boundary_state(bct, eos, Pb, Pm, P.RefPrim + 6 * (bcs > 0 ? bcs - 1 : 0), nv, t1, t2)) atomicOr(P.errFlag, 1);
+            if (bct == 2) {
+                Fl[0] = 0.5 * (Pm[VEL1] + Pb[VEL1]); Fl[1] = 0.5 * (Pm[VEL2] + Pb[VEL2]);
+                Fl[2] = 0.5 * (Pm[VEL3] + Pb[VEL3]); Fl[3] = 0.5 * (Pm[TEMP] + Pb[TEMP]);
+            } else if (bct == 3 || bct == 4) {
+                Fl[0] = Fl[1] = Fl[2] = 0.0; Fl[3] = Pb[TEMP];
+            } else {
+                Fl[0] = Pb[VEL1]; Fl[1] = Pb[VEL2]; Fl[2] = Pb[VEL3]; Fl[3] = Pm[TEMP];
+            }
+            Fl[0] = (Fl[0] - Pm[VEL1]) * se; Fl[1] = (Fl[1] - Pm[VEL2]) * se;
+            Fl[2] = (Fl[2] - Pm[VEL3]) * se; Fl[3] = (Fl[3] - Pm[TEMP]) * se;
+        } else {
+            double Us[5], Ps[6];
+#pragma unroll
+            for (int v = 0; v < 5; v++) Us[v] = P.Us[(size_t)side * 5 * n2 + v * n2 + pq];
+            cons_to_prim(Ps, Us, eos);
+            Fl[0] = 0.5 * se * (-Pm[VEL1] + Ps[VEL1]); Fl[1] = 0.5 * se * (-Pm[VEL2] + Ps[VEL2]);
+            Fl[2] = 0.5 * se * (-Pm[VEL3] + Ps[VEL3]); Fl[3] = 0.5 * se * (-Pm[TEMP] + Ps[TEMP]);
+        }
+        double* d = sF + (loc - 1) * 7 * n2 + (b * n + a);
+        d[0 * n2] = Fl[0]; d[1 * n2] = Fl[1]; d[2 * n2] = Fl[2]; d[3 * n2] = Fl[3];
+        d[4 * n2] = nv[0]; d[5 * n2] = nv[1]; d[6 * n2] = nv[2];
+    }
+    __syncthreads();
+    // 3. node: volume derivative + surface lifting, Jacobian
+    const int k = t / n2, j = (t - k * n2) / n, i = t - k * n2 - j * n;
+    double G[12];
+    {
+        double gxi[4] = {0, 0, 0, 0}, get[4] = {0, 0, 0, 0}, gze[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int l = 0; l < n; l++) {
+            const double dx = sD[l + n * i], dy = sD[l + n * j], dz = sD[l + n * k];
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                gxi[v] += dx * sT[v * n3 + l + n * (j + n * k)];
+                get[v] += dy * sT[v * n3 + i + n * (l + n * k)];
+                gze[v] += dz * sT[v * n3 + i + n * (j + n * l)];
+            }
+        }
+        const double* M = P.metrics + (size_t)e * 9 * n3 + t;
+        double S[12];
+#pragma unroll
+        for (int x = 0; x < 12; x++) S[x] = 0.0;
+        // surface contributions in local-side order 1..6 (surfint.t90:624-716)
+#pragma unroll
+        for (int loc = 1; loc <= 6; loc++) {
+            int a, b, l;
+            if (loc == XI_MINUS || loc == XI_PLUS) { a = j; b = k; l = i; }
+            else if (loc == ETA_MINUS || loc == ETA_PLUS) { a = i; b = k; l = j; }
+            else { a = i; b = j; l = k; }
+            const bool minus = is_minus(loc);
+            double Lh;
+            if (NT == 2) {
+                if (minus ? (l != 0) : (l != n - 1)) continue;
+                Lh = minus ? sLhm[0] : sLhp[n - 1];
+            } else {
+                Lh = minus ? sLhm[l] : sLhp[l];
+            }
+            const double* s = sF + (loc - 1) * 7 * n2 + (b * n + a);
+            const double nx = s[4 * n2], ny = s[5 * n2], nz = s[6 * n2];
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const double F = s[v * n2];
+                S[0 * 4 + v] += (F * nx) * Lh;
+                S[1 * 4 + v] += (F * ny) * Lh;
+                S[2 * 4 + v] += (F * nz) * Lh;
+            }
+        }
+        const double sJ = P.sJ[(size_t)e * n3 + t];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const double mf = M[(0 + d) * n3], mg = M[(3 + d) * n3], mh = M[(6 + d) * n3];
+#pragma unroll
+            for (int v = 0; v < 4; v++) G[d * 4 + v] = sJ * ((mf * gxi[v] + mg * get[v] + mh * gze[v]) + S[d * 4 + v]);
+        }
+    }
+    __syncthreads();  // all reads of sT done before it is overwritten by the gradient tile
+    double* gU = P.gradU + (size_t)e * 12 * n3 + t;
+#pragma unroll
+    for (int x = 0; x < 12; x++) { gU[x * n3] = G[x]; sG[x * n3 + t] = G[x]; }
+    __syncthreads();
+    // 4. gradients on the faces (ProlongToFaceLifting)
+    extract_faces<n, NT, 12>(sG, P.gm, P.gs, e2s, P.S2V2, sLm, sLp);
+}
+
+template <int n>
+constexpr size_t lifting_smem_bytes() { return sizeof(double) * (12 * n * n * n + 6 * 7 * n * n + n * n + 4 * n); }
+
+// ---------------------------------------------------------------------------------------------------------
+// Numerical flux on a range of sides [side0, side0+nS): BC flux or Riemann + 1/2(Fv_L+Fv_R).n, times SurfElem
+template <int n>
+__global__ void __launch_bounds__(128) k_sideflux(const KParams P, int side0, int nS) {
+    constexpr int n2 = n * n;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nS * n2) return;
+    const int side = side0 + gid / n2;
+    const int pq = gid % n2;
+    const Eos eos = P.eos;
+    const double* g = P.geo + (size_t)side * 10 * n2 + pq;
+    const double nv[3] = {g[0 * n2], g[1 * n2], g[2 * n2]};
+    const double t1[3] = {g[3 * n2], g[4 * n2], g[5 * n2]};
+    const double t2[3] = {g[6 * n2], g[7 * n2], g[8 * n2]};
+    const double se = g[9 * n2];
+    double Um[5], Pm[6], F[5];
+#pragma unroll
+    for (int v = 0; v < 5; v++) Um[v] = P.Um[(size_t)side * 5 * n2 + v * n2 + pq];
+    cons_to_prim(Pm, Um, eos);
+    double gm[12];
+    if (P.parabolic) {
+#pragma unroll
+        for (int x = 0; x < 12; x++) gm[x] = P.gm[(size_t)side * 12 * n2 + x * n2 + pq];
+    }
+    if (side < P.nBCSides) {
+        const int bct = __ldg(&P.BCSides[2 * side]), bcs = __ldg(&P.BCSides[2 * side + 1]);
+        double Pb[6];
+        if (boundary_state(bct, eos, Pb, Pm, P.RefPrim + 6 * (bcs > 0 ? bcs - 1 : 0), nv, t1, t2)) atomicOr(P.errFlag, 1);
+        if (bct == 2) {
+            double Umc[5], Ubc[5];
+            prim_to_cons(Pm, Umc, eos);
+            prim_to_cons(Pb, Ubc, eos);
+            riemann(P.riemann, P.splitDG, eos.kappa, F, Umc, Ubc, Pm, Pb, nv, t1, t2);
+            if (P.parabolic) {
+                Tau tL, tR;
+                double mu = viscosity(eos, Pm[TEMP]);
+                stress(tL, Pm, gm, mu, conductivity(eos, mu));
+                mu = viscosity(eos, Pb[TEMP]);
+                stress(tR, Pb, gm, mu, conductivity(eos, mu));
+                double fL[4], fR[4];
+                visc_flux_dir(tL, nv, fL);
+                visc_flux_dir(tR, nv, fR);
+#pragma unroll
+                for (int v = 0; v < 4; v++) F[1 + v] += 0.5 * (fL[v] + fR[v]);
+            }
+        } else {
+            F[DENS] = 0.0;
+            F[MOM1] = Pb[PRES] * nv[0]; F[MOM2] = Pb[PRES] * nv[1]; F[MOM3] = Pb[PRES] * nv[2];
+            F[ENER] = 0.0;
+            if (P.parabolic) {
+                const double mu = viscosity(eos, Pb[TEMP]);
+                const double la = conductivity(eos, mu);
+                Tau tb;
+                double fd[4];
+                if (bct == 9) {
+                    double gf[12];
+                    const double B[3][3] = {{1.0 - nv[0] * nv[0], -nv[0] * nv[1], -nv[0] * nv[2]},
+                                            {-nv[0] * nv[1], 1.0 - nv[1] * nv[1], -nv[2] * nv[1]},
+                                            {-nv[0] * nv[2], -nv[2] * nv[1], 1.0 - nv[2] * nv[2]}};
+#pragma unroll
+                    for (int d = 0; d < 3; d++)
+#pragma unroll
+                        for (int v = 0; v < 4; v++) gf[d * 4 + v] = B[d][0] * gm[0 * 4 + v] + B[d][1] * gm[1 * 4 + v] + B[d][2] * gm[2 * 4 + v];
+                    stress(tb, Pb, gf, mu, la);
+                } else {
+                    stress(tb, Pb, gm, mu, la);
+                }
+                visc_flux_dir(tb, nv, fd);
+                if (bct == 3) {  // adiabatic wall: no energy flux (getboundaryflux.f90:664-668)
+                    fd[3] = 0.0;
+                }
+#pragma unroll
+                for (int v = 0; v < 4; v++) F[1 + v] += fd[v];
+            }
+        }
+    } else {
+        double Us[5], Ps[6];
+#pragma unroll
+        for (int v = 0; v < 5; v++) Us[v] = P.Us[(size_t)side * 5 * n2 + v * n2 + pq];
+        cons_to_prim(Ps, Us, eos);
+        riemann(P.riemann, P.splitDG, eos.kappa, F, Um, Us, Pm, Ps, nv, t1, t2);
+        if (P.parabolic) {
+            double gs[12];
+#pragma unroll
+            for (int x = 0; x < 12; x++) gs[x] = P.gs[(size_t)side * 12 * n2 + x * n2 + pq];
+            Tau tL, tR;
+            double mu = viscosity(eos, Pm[TEMP]);
+            stress(tL, Pm, gm, mu, conductivity(eos, mu));
+            mu = viscosity(eos, Ps[TEMP]);
+            stress(tR, Ps, gs, mu, conductivity(eos, mu));
+            double fL[4], fR[4];
+            visc_flux_dir(tL, nv, fL);
+            visc_flux_dir(tR, nv, fR);
+#pragma unroll
+            for (int v = 0; v < 4; v++) { F[1 + v] += 0.5 * fL[v]; F[1 + v] += 0.5 * fR[v]; }
+        }
+    }
+    double* out = P.Flux + (size_t)side * 5 * n2 + pq;
+#pragma unroll
+    for (int v = 0; v < 5; v++) out[v * n2] = F[v] * se;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Volume integral (weak or split form, + viscous weak form), surface integral, sign, Jacobian,
+// optional RK 2N update and prolongation of the updated state to the faces.
+//   MODE 0: store Ut only (DGTimeDerivative_weakForm);  MODE 1: RK stage update (+ face extraction)
+template <int n, int NT, int MODE>
+__global__ void __launch_bounds__(n* n* n) k_volsurf(const KParams P, double mRKA, double b_dt) {
+    constexpr int n2 = n * n, n3 = n2 * n;
+    extern __shared__ double smem[];
+    double* sA = smem;               // [15][n3] multipurpose: fluxes f,g,h (15) | node record (6) + metrics (9) | U tile (5)
+    double* sFl = smem + 15 * n3;    // [6][5][n2] signed face fluxes in element face order
+    double* sDh = sFl + 30 * n2;     // D_Hat_T
+    double* sDv = sDh + n * n;       // DVolSurf
+    double* sLhm = sDv + n * n;
+    double* sLhp = sLhm + n;
+    double* sLm = sLhp + n;
+    double* sLp = sLm + n;
+    const int e = P.elemList ? P.elemList[blockIdx.x] : blockIdx.x;
+    const int t = threadIdx.x;
+    for (int x = t; x < n * n; x += n3) { sDh[x] = P.D_Hat_T[x]; sDv[x] = P.DVolSurf[x]; }
+    if (t < n) { sLhm[t] = P.L_HatMinus[t]; sLhp[t] = P.L_HatPlus[t]; sLm[t] = P.L_Minus[t]; sLp[t] = P.L_Plus[t]; }
+    const Eos eos = P.eos;
+    const int* e2s = P.E2S + 18 * e;
+    const int k = t / n2, j = (t - k * n2) / n, i = t - k * n2 - j * n;
+    const bool split = P.splitDG >= 0;
+
+    // face fluxes -> shared memory (element face order, sign: +master / -slave)
+    for (int f = t; f < 6 * n2; f += n3) {
+        const int loc = f / n2 + 1;
+        const int pq = f - (loc - 1) * n2;
+        const int q = pq / n, p = pq - q * n;
+        const int side = __ldg(&e2s[0 + 3 * (loc - 1)]) - 1;
+        const int flip = __ldg(&e2s[1 + 3 * (loc - 1)]);
+        const int a = s2v2<n>(P.S2V2, 0, p, q, flip, loc);
+        const int b = s2v2<n>(P.S2V2, 1, p, q, flip, loc);
+        const double sg = (flip == 0) ? 1.0 : -1.0;
+        const double* F = P.Flux + (size_t)side * 5 * n2 + pq;
+        double* d = sFl + (loc - 1) * 5 * n2 + (b * n + a);
+#pragma unroll
+        for (int v = 0; v < 5; v++) d[v * n2] = sg * F[v * n2];
+    }
+
+    // node state
+    double Uc[5], Pr[6], M[9];
+    {
+        const double* U = P.U + (size_t)e * 5 * n3 + t;
+#pragma unroll
+        for (int v = 0; v < 5; v++) Uc[v] = U[v * n3];
+        const double* Mg = P.metrics + (size_t)e * 9 * n3 + t;
+#pragma unroll
+        for (int x = 0; x < 9; x++) M[x] = Mg[x * n3];
+    }
+    cons_to_prim(Pr, Uc, eos);
+    double Ut[5] = {0, 0, 0, 0, 0};
+
+    // ---- weak-form part: Euler(+viscous) fluxes (non-split) or viscous fluxes only (split + parabolic)
+    if (!split || P.parabolic) {
+        double f[5], g[5], h[5];
+        if (!split) {
+            const double Ep = (Uc[ENER] + Pr[PRES]) / Uc[DENS];
+            double* Fs[3] = {f, g, h};
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                const double* Md = M + 3 * d;
+                const double Mmom = Md[0] * Uc[MOM1] + Md[1] * Uc[MOM2] + Md[2] * Uc[MOM3];
+                Fs[d][DENS] = Mmom;
+                Fs[d][MOM1] = Mmom * Pr[VEL1] + Md[0] * Pr[PRES];
+                Fs[d][MOM2] = Mmom * Pr[VEL2] + Md[1] * Pr[PRES];
+                Fs[d][MOM3] = Mmom * Pr[VEL3] + Md[2] * Pr[PRES];
+                Fs[d][ENER] = Mmom * Ep;
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < 5; v++) f[v] = g[v] = h[v] = 0.0;
+        }
+        if (P.parabolic) {
+            double gr[12];
+            const double* gU = P.gradU + (size_t)e * 12 * n3 + t;
+#pragma unroll
+            for (int x = 0; x < 12; x++) gr[x] = gU[x * n3];
+            const double mu = viscosity(eos, Pr[TEMP]);
+            Tau ta;
+            stress(ta, Pr, gr, mu, conductivity(eos, mu));
+            double v4[4];
+            visc_flux_dir(ta, M + 0, v4);
+#pragma unroll
+            for (int v = 0; v < 4; v++) f[1 + v] += v4[v];
+            visc_flux_dir(ta, M + 3, v4);
+#pragma unroll
+            for (int v = 0; v < 4; v++) g[1 + v] += v4[v];
+            visc_flux_dir(ta, M + 6, v4);
+#pragma unroll
+            for (int v = 0; v < 4; v++) h[1 + v] += v4[v];
+        }
+#pragma unroll
+        for (int v = 0; v < 5; v++) { sA[v * n3 + t] = f[v]; sA[(5 + v) * n3 + t] = g[v]; sA[(10 + v) * n3 + t] = h[v]; }
+        __syncthreads();
+        // D_Hat sweep (applydmatrix.t90:60-67); the DENS row is skipped when only viscous fluxes are present
+        const int v0 = split ? 1 : 0;
+#pragma unroll
+        for (int l = 0; l < n; l++) {
+            const double dx = sDh[l + n * i], dy = sDh[l + n * j], dz = sDh[l + n * k];
+#pragma unroll
+            for (int v = 0; v < 5; v++) {
+                if (v < v0) continue;
+                Ut[v] += dx * sA[v * n3 + l + n * (j + n * k)] + dz * sA[(10 + v) * n3 + i + n * (j + n * l)] +
+                         dy * sA[(5 + v) * n3 + i + n * (l + n * k)];
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- split-form flux differencing (volint.f90:306-347)
+    if (split) {
+        const int var = P.splitDG;
+        double me[6] = {Pr[DENS], Pr[VEL1], Pr[VEL2], Pr[VEL3], Pr[PRES], split_sixth(var, Uc, Pr)};
+#pragma unroll
+        for (int v = 0; v < 6; v++) sA[v * n3 + t] = me[v];
+#pragma unroll
+        for (int x = 0; x < 9; x++) sA[(6 + x) * n3 + t] = M[x];
+        __syncthreads();
+        double acc[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const int idx = (d == 0) ? i : (d == 1 ? j : k);
+            const int stride = (d == 0) ? 1 : (d == 1 ? n : n2);
+            const int base = t - idx * stride;
+#pragma unroll
+            for (int l = 0; l < n; l++) {
+                const int o = base + l * stride;
+                double ot[6], Ms[3], F[5];
+#pragma unroll
+                for (int v = 0; v < 6; v++) ot[v] = sA[v * n3 + o];
+#pragma unroll
+                for (int c = 0; c < 3; c++) Ms[c] = M[3 * d + c] + sA[(6 + 3 * d + c) * n3 + o];
+                split_volume_flux(var, me, ot, Ms, F);
+                const double w = sDv[l + n * idx];
+#pragma unroll
+                for (int v = 0; v < 5; v++) acc[v] += w * F[v];
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < 5; v++) Ut[v] += acc[v];
+    }
+    __syncthreads();  // sFl complete (written before the first barrier in any path), sA free for reuse
+
+    // ---- surface integral (surfint.t90:463-584), local sides in order 1..6
+    {
+        double S[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+        for (int loc = 1; loc <= 6; loc++) {
+            int a, b, l;
+            if (loc == XI_MINUS || loc == XI_PLUS) { a = j; b = k; l = i; }
+            else if (loc == ETA_MINUS || loc == ETA_PLUS) { a = i; b = k; l = j; }
+            else { a = i; b = j; l = k; }
+            const bool minus = is_minus(loc);
+            double Lh;
+            if (NT == 2) {
+                if (minus ? (l != 0) : (l != n - 1)) continue;
+                Lh = minus ? sLhm[0] : sLhp[n - 1];
+            } else {
+                Lh = minus ? sLhm[l] : sLhp[l];
+            }
+            const double* s = sFl + (loc - 1) * 5 * n2 + (b * n + a);
+#pragma unroll
+            for (int v = 0; v < 5; v++) S[v] += s[v * n2] * Lh;
+        }
+#pragma unroll
+        for (int v = 0; v < 5; v++) Ut[v] += S[v];
+    }
+    // ---- sign and Jacobian (dg.f90:413,423)
+    const double msJ = -P.sJ[(size_t)e * n3 + t];
+#pragma unroll
+    for (int v = 0; v < 5; v++) Ut[v] *= msJ;
+
+    if (MODE == 0) {
+        double* o = P.Ut + (size_t)e * 5 * n3 + t;
+#pragma unroll
+        for (int v = 0; v < 5; v++) o[v * n3] = Ut[v];
+    } else {
+        // Williamson 2N update (vector.f90:163-183): Ut_tmp = Ut_tmp*mRKA + Ut ; U = U + Ut_tmp*b_dt
+        double* ot = P.Ut_tmp + (size_t)e * 5 * n3 + t;
+        double* ou = P.U + (size_t)e * 5 * n3 + t;
+#pragma unroll
+        for (int v = 0; v < 5; v++) {
+            const double r = (mRKA == 0.0) ? Ut[v] : ot[v * n3] * mRKA + Ut[v];
+            ot[v * n3] = r;
+            const double un = Uc[v] + r * b_dt;
+            ou[v * n3] = un;
+            sA[v * n3 + t] = un;
+        }
+        __syncthreads();
+        extract_faces<n, NT, 5>(sA, P.UmNext, P.UsNext, e2s, P.S2V2, sLm, sLp);
+    }
+}
+
+template <int n>
+constexpr size_t volsurf_smem_bytes() { return sizeof(double) * (15 * n * n * n + 30 * n * n + 2 * n * n + 4 * n); }
+
+// ---------------------------------------------------------------------------------------------------------
+// positive doubles order like their bit patterns
+__device__ __forceinline__ void atomic_min_pos(double* addr, double v) {
+    atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// per element max eigenvalues -> global min of CFL*2/lam_c and DFL*4/lam_v  (calctimestep.f90:98-296)
+template <int n>
+constexpr int timestep_threads() { return ((n * n * n + 31) / 32) * 32; }
+
+template <int n>
+__global__ void __launch_bounds__(timestep_threads<n>()) k_timestep(const KParams P, double CFL, double DFL, double* out /*[2]*/) {
+    constexpr int n3 = n * n * n;
+    __shared__ double red[6][32];
+    const int e = blockIdx.x, t = threadIdx.x;
+    const bool active = t < n3;  // block is padded to full warps so the shuffles below are well defined
+    const Eos eos = P.eos;
+    double lam[6] = {0, 0, 0, 0, 0, 0};
+    bool bad = false;
+    if (active) {
+        double Uc[5], Pr[6], M[9];
+        const double* U = P.U + (size_t)e * 5 * n3 + t;
+#pragma unroll
+        for (int v = 0; v < 5; v++) Uc[v] = U[v * n3];
+        const double* Mg = P.metrics + (size_t)e * 9 * n3 + t;
+#pragma unroll
+        for (int x = 0; x < 9; x++) M[x] = Mg[x * n3];
+        const double sJ = P.sJ[(size_t)e * n3 + t];
+        cons_to_prim(Pr, Uc, eos);
+        const double c = sqrt(eos.kappa * Pr[PRES] / Uc[DENS]);
+        bad = !(Uc[DENS] > 0.0) || !(Pr[PRES] > 0.0) || !isfinite(Uc[ENER]);
+        const double kmax = fmax(4.0 / 3.0, eos.kappa / eos.Pr);
+        const double mu = P.parabolic ? viscosity(eos, Pr[TEMP]) : 0.0;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const double* Md = M + 3 * d;
+            const double nrm2 = Md[0] * Md[0] + Md[1] * Md[1] + Md[2] * Md[2];
+            lam[d] = fabs(Md[0] * (Pr[VEL1] * sJ) + Md[1] * (Pr[VEL2] * sJ) + Md[2] * (Pr[VEL3] * sJ)) + c * (sJ * sqrt(nrm2));
+            lam[3 + d] = mu / Uc[DENS] * (kmax * (nrm2 * sJ * sJ));
+        }
+    }
+#pragma unroll
+    for (int x = 0; x < 6; x++) {
+        double v = lam[x];
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if ((t & 31) == 0) red[x][t >> 5] = v;
+    }
+    const int anyBad = __syncthreads_or(bad ? 1 : 0);
+    if (t == 0) {
+        constexpr int nw = timestep_threads<n>() / 32;
+        double mx[6];
+        for (int x = 0; x < 6; x++) {
+            double v = red[x][0];
+            for (int w = 1; w < nw; w++) v = fmax(v, red[x][w]);
+            mx[x] = v;
+        }
+        const double lc = mx[0] + mx[1] + mx[2];
+        const double dtc = CFL * 2.0 / lc;
+        if (anyBad || !(dtc > 0.0) || !isfinite(dtc)) atomicOr(P.errFlag, 2);
+        else atomic_min_pos(&out[0], dtc);
+        if (P.parabolic) {
+            const double lv = mx[3] + mx[4] + mx[5];
+            const double dtv = DFL * 4.0 / lv;
+            if (dtv > 0.0 && isfinite(dtv)) atomic_min_pos(&out[1], dtv);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// layout conversion at the C ABI: reference AoS (nv, n^3, nElems) <-> SoA tiles [elem][nv][n^3]
+template <int NVAR>
+__global__ void k_aos_to_soa(const double* __restrict__ aos, double* __restrict__ soa, int n3, size_t total) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over elem*n3*NVAR in SoA order
+    if (gid >= total) return;
+    const size_t e = gid / ((size_t)NVAR * n3);
+    const int r = (int)(gid - e * NVAR * n3);
+    const int v = r / n3, node = r - v * n3;
+    soa[gid] = aos[(e * n3 + node) * NVAR + v];
+}
+template <int NVAR>
+__global__ void k_soa_to_aos(const double* __restrict__ soa, double* __restrict__ aos, int n3, size_t total, int soaStride, int soaOffset) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over elem*n3*NVAR in AoS order
+    if (gid >= total) return;
+    const size_t dof = gid / NVAR;
+    const int v = (int)(gid - dof * NVAR);
+    const size_t e = dof / n3;
+    const int node = (int)(dof - e * n3);
+    aos[gid] = soa[(e * soaStride + soaOffset + v) * n3 + node];
+}
+// side geometry (3,n,n,S)x3 + (n,n,S) -> [side][10][n2]
+static __global__ void k_pack_geo(const double* nv, const double* t1, const double* t2, const double* se, double* geo, int n2, size_t total) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const size_t s = gid / (10 * n2);
+    const int r = (int)(gid - s * 10 * n2);
+    const int c = r / n2, pq = r - c * n2;
+    double v;
+    if (c < 3) v = nv[(s * n2 + pq) * 3 + c];
+    else if (c < 6) v = t1[(s * n2 + pq) * 3 + c - 3];
+    else if (c < 9) v = t2[(s * n2 + pq) * 3 + c - 6];
+    else v = se[s * n2 + pq];
+    geo[gid] = v;
+}
+// metrics (3,n3,E)x3 -> [e][9][n3]
+static __global__ void k_pack_metrics(const double* mf, const double* mg, const double* mh, double* out, int n3, size_t total) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const size_t e = gid / (9 * (size_t)n3);
+    const int r = (int)(gid - e * 9 * n3);
+    const int c = r / n3, node = r - c * n3;
+    const double* src = c < 3 ? mf : (c < 6 ? mg : mh);
+    out[gid] = src[(e * n3 + node) * 3 + (c % 3)];
+}
+
+}  // namespace dgx

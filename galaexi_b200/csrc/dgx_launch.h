@@ -1,0 +1,20 @@
+// Launch table: one entry per (N, node type), instantiated in dgx_inst.cu (compiled once per N with -DDGX_N=<N>).
+#pragma once
+#include <cuda_runtime.h>
+#include "dgx_kernels.cuh"
+
+namespace dgx {
+struct KernelTable {
+    int (*setup)();  // opt-in to large dynamic shared memory; returns cudaError_t
+    void (*prolong)(const KParams&, int nBlocks, cudaStream_t);
+    void (*lifting)(const KParams&, int nBlocks, cudaStream_t);
+    void (*sideflux)(const KParams&, int side0, int nS, cudaStream_t);
+    void (*volsurf)(const KParams&, int mode, double mRKA, double b_dt, int nBlocks, cudaStream_t);
+    void (*timestep)(const KParams&, double CFL, double DFL, double* out, cudaStream_t);
+};
+const KernelTable* kernel_table(int N, int nodeType);  // nullptr if this N was not compiled in
+}  // namespace dgx
+
+#define DGX_DECLARE_TABLE(NN) namespace dgx { const KernelTable* kernel_table_N##NN(int nodeType); }
+DGX_DECLARE_TABLE(1) DGX_DECLARE_TABLE(2) DGX_DECLARE_TABLE(3) DGX_DECLARE_TABLE(4) DGX_DECLARE_TABLE(5)
+DGX_DECLARE_TABLE(6) DGX_DECLARE_TABLE(7) DGX_DECLARE_TABLE(8) DGX_DECLARE_TABLE(9)

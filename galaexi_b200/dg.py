@@ -1,0 +1,240 @@
+"""Host-side mirror of the reference's DG module interface over the C ABI (include/dgx.h).
+
+The reference toolchain (nvfortran) is absent here, so this Python driver plays the role of the
+Fortran host: it feeds the arrays built by ``galaexi_b200.host`` (the stand-in for InitMesh /
+InitInterpolation / InitEquation) through ``dgx_create`` and calls the same procedures, with the same
+names and argument meaning, that ``src/timedisc`` calls in the reference:
+
+    InitDG()                         dg/dg.f90:67          -> DGSolver(case)
+    DGTimeDerivative_weakForm(t)     dg/dg.f90:255         -> DGSolver.DGTimeDerivative_weakForm(t)
+    TimeStepByLSERKW2(t)             timedisc/timestep.f90:49 -> DGSolver.TimeStepByLSERKW2(t, dt)
+    CalcTimeStep(errType)            calctimestep.f90:98   -> DGSolver.CalcTimeStep()
+    FinalizeDG()                     dg/dg.f90:464         -> DGSolver.FinalizeDG()
+
+There is no CPU fallback: if ``libdgx.so`` (hand-written sm_100a kernels) is missing or no B200 is
+visible, construction fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libdgx.so")
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+EXPORTS = ("dgx_create", "dgx_destroy", "dgx_last_error", "dgx_set_state", "dgx_get_state", "dgx_get_ut",
+           "dgx_get_gradients", "dgx_time_derivative", "dgx_rk_stage", "dgx_rk_step", "dgx_calc_timestep",
+           "dgx_sync", "dgx_run_steps", "dgx_profile_stage", "dgx_nccl_unique_id", "dgx_launch_count")
+
+
+class DgxConfig(C.Structure):
+    """Mirror of ``struct dgx_config`` (include/dgx.h)."""
+    _fields_ = (
+        [(k, C.c_int) for k in ("N", "nodeType", "splitDG", "riemann", "parabolic", "viscLaw", "nElems", "nSides",
+                                "nBCSides", "firstInnerSide", "lastInnerSide", "firstMPISide_MINE", "lastMPISide_MINE",
+                                "firstMPISide_YOUR", "lastMPISide_YOUR")]
+        + [("EOS_Vars", C.c_double * 8), ("nRefState", C.c_int), ("RefStatePrim", _dp), ("BCSides", _ip)]
+        + [(k, _dp) for k in ("D_T", "D_Hat_T", "DVolSurf", "L_Minus", "L_Plus", "L_HatMinus", "L_HatPlus")]
+        + [(k, _ip) for k in ("ElemToSide", "S2V2", "S2V2_inv")]
+        + [(k, _dp) for k in ("Metrics_fTilde", "Metrics_gTilde", "Metrics_hTilde", "sJ", "NormVec", "TangVec1",
+                              "TangVec2", "SurfElem")]
+        + [("nRKStages", C.c_int), ("RKA", _dp), ("RKb", _dp), ("RKc", _dp), ("CFLScale", C.c_double),
+           ("DFLScale", C.c_double), ("myRank", C.c_int), ("nRanks", C.c_int), ("nNbProcs", C.c_int)]
+        + [(k, _ip) for k in ("NbProc", "nMPISides_MINE_Proc", "nMPISides_YOUR_Proc", "offsetMPISides_MINE",
+                              "offsetMPISides_YOUR")]
+        + [("ncclUniqueId", C.c_char_p), ("device", C.c_int)]
+    )
+
+
+_lib = None
+
+
+def load_library():
+    """Load libdgx.so; raises (no fallback) when the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: build the CUDA extension first "
+                           f"(python -c 'import __graft_entry__ as g; g.build()' or make -C galaexi_b200/csrc)")
+    lib = C.CDLL(LIB_PATH)
+    h = C.c_void_p
+    lib.dgx_create.argtypes = [C.POINTER(h), C.POINTER(DgxConfig)]
+    lib.dgx_destroy.argtypes = [h]
+    lib.dgx_destroy.restype = None
+    lib.dgx_last_error.argtypes = [h]
+    lib.dgx_last_error.restype = C.c_char_p
+    for nm in ("dgx_set_state", "dgx_get_state", "dgx_get_ut"):
+        getattr(lib, nm).argtypes = [h, _dp]
+    lib.dgx_get_gradients.argtypes = [h, _dp, _dp, _dp]
+    lib.dgx_time_derivative.argtypes = [h, C.c_double]
+    lib.dgx_rk_stage.argtypes = [h, C.c_int, C.c_double, C.c_double]
+    lib.dgx_rk_step.argtypes = [h, C.c_double, C.c_double]
+    lib.dgx_calc_timestep.argtypes = [h, _dp, _ip]
+    lib.dgx_sync.argtypes = [h]
+    lib.dgx_run_steps.argtypes = [h, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]
+    lib.dgx_profile_stage.argtypes = [h, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), _ip]
+    lib.dgx_nccl_unique_id.argtypes = [C.c_char_p]
+    lib.dgx_launch_count.argtypes = [h]
+    lib.dgx_launch_count.restype = C.c_longlong
+    _lib = lib
+    return lib
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    if load_library().dgx_nccl_unique_id(buf):
+        raise RuntimeError("ncclGetUniqueId failed (libnccl not loadable?)")
+    return buf.raw
+
+
+class DGError(RuntimeError):
+    """Raised where the reference would CALL Abort(__STAMP__, ...)."""
+
+
+class DGSolver:
+    """One rank's DG operator + LSERK time integrator on one B200 (see module docstring)."""
+
+    def __init__(self, case, device: int = 0, nccl_id: bytes | None = None):
+        self.lib = load_library()
+        self.case = case
+        m, b, g = case.mesh, case.basis, case.geo
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        td = case.timedisc
+        k = dict(
+            D_T=f64(b.D_T.T), D_Hat_T=f64(b.D_Hat_T.T), DVolSurf=f64(b.DVolSurf.T), L_Minus=f64(b.L_Minus),
+            L_Plus=f64(b.L_Plus), L_HatMinus=f64(b.L_HatMinus), L_HatPlus=f64(b.L_HatPlus),
+            ElemToSide=i32(m.ElemToSide), S2V2=i32(case.maps["S2V2"]), S2V2_inv=i32(case.maps["S2V2_inv"]),
+            BCSides=i32(case.BCSides if case.BCSides.size else np.zeros((1, 2))),
+            Metrics_fTilde=f64(g["Metrics_fTilde"]), Metrics_gTilde=f64(g["Metrics_gTilde"]),
+            Metrics_hTilde=f64(g["Metrics_hTilde"]), sJ=f64(g["sJ"]), NormVec=f64(g["NormVec"]),
+            TangVec1=f64(g["TangVec1"]), TangVec2=f64(g["TangVec2"]), SurfElem=f64(g["SurfElem"]),
+            RefStatePrim=f64(case.RefStatePrim), RKA=f64(td.RKA), RKb=f64(td.RKb), RKc=f64(td.RKc),
+            NbProc=i32(m.NbProc if m.nNbProcs else np.zeros(1)),
+            nMPISides_MINE_Proc=i32(m.nMPISides_MINE_Proc if m.nNbProcs else np.zeros(1)),
+            nMPISides_YOUR_Proc=i32(m.nMPISides_YOUR_Proc if m.nNbProcs else np.zeros(1)),
+            offsetMPISides_MINE=i32(m.offsetMPISides_MINE if m.nNbProcs else np.zeros(2)),
+            offsetMPISides_YOUR=i32(m.offsetMPISides_YOUR if m.nNbProcs else np.zeros(2)),
+        )
+        self._keep = k
+        c = DgxConfig()
+        c.N = case.N
+        c.nodeType = 2 if case.node_type == "GAUSS-LOBATTO" else 1
+        c.splitDG, c.riemann, c.parabolic, c.viscLaw = case.split, case.riemann, int(case.parabolic), case.eos.visc_law
+        c.nElems, c.nSides, c.nBCSides = m.nElems, m.nSides, m.nBCSides
+        c.firstInnerSide, c.lastInnerSide = m.firstInnerSide, m.lastInnerSide
+        c.firstMPISide_MINE, c.lastMPISide_MINE = m.firstMPISide_MINE, m.lastMPISide_MINE
+        c.firstMPISide_YOUR, c.lastMPISide_YOUR = m.firstMPISide_YOUR, m.lastMPISide_YOUR
+        for i, v in enumerate(case.eos.eos_vars()):
+            c.EOS_Vars[i] = v
+        c.nRefState = case.RefStatePrim.shape[0]
+        for nm in ("RefStatePrim", "D_T", "D_Hat_T", "DVolSurf", "L_Minus", "L_Plus", "L_HatMinus", "L_HatPlus",
+                   "Metrics_fTilde", "Metrics_gTilde", "Metrics_hTilde", "sJ", "NormVec", "TangVec1", "TangVec2",
+                   "SurfElem", "RKA", "RKb", "RKc"):
+            setattr(c, nm, k[nm].ctypes.data_as(_dp))
+        for nm in ("BCSides", "ElemToSide", "S2V2", "S2V2_inv", "NbProc", "nMPISides_MINE_Proc",
+                   "nMPISides_YOUR_Proc", "offsetMPISides_MINE", "offsetMPISides_YOUR"):
+            setattr(c, nm, k[nm].ctypes.data_as(_ip))
+        c.nRKStages, c.CFLScale, c.DFLScale = td.nRKStages, td.CFLScale, td.DFLScale
+        c.myRank, c.nRanks, c.nNbProcs = m.myRank, m.nProcs, m.nNbProcs
+        self._id = nccl_id
+        c.ncclUniqueId = nccl_id if (m.nProcs > 1 and nccl_id is not None) else None
+        c.device = device
+        self._cfg = c
+        self.h = C.c_void_p()
+        rc = self.lib.dgx_create(C.byref(self.h), C.byref(c))
+        if rc:
+            msg = self.lib.dgx_last_error(self.h).decode() if self.h else "dgx_create failed"
+            if self.h:
+                self.lib.dgx_destroy(self.h)
+                self.h = None
+            raise DGError(msg)
+        n = case.N + 1
+        self.shape_U = (m.nElems, n, n, n, 5)
+        self.shape_grad = (m.nElems, n, n, n, 4)
+
+    # ---- error mapping: non-zero return -> Abort ---------------------------------------------------------
+    def _ck(self, rc):
+        if rc:
+            raise DGError(self.lib.dgx_last_error(self.h).decode())
+
+    # ---- state transfer (reference layout U(nVar,i,j,k,iElem) == numpy [e,k,j,i,v]) -----------------------
+    def set_state(self, U: np.ndarray):
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        assert U.shape == self.shape_U, (U.shape, self.shape_U)
+        self._ck(self.lib.dgx_set_state(self.h, U.ctypes.data_as(_dp)))
+
+    def get_state(self, out: np.ndarray | None = None) -> np.ndarray:
+        U = out if out is not None else np.empty(self.shape_U)
+        self._ck(self.lib.dgx_get_state(self.h, U.ctypes.data_as(_dp)))
+        return U
+
+    def get_ut(self) -> np.ndarray:
+        Ut = np.empty(self.shape_U)
+        self._ck(self.lib.dgx_get_ut(self.h, Ut.ctypes.data_as(_dp)))
+        return Ut
+
+    def get_gradients(self):
+        g = [np.empty(self.shape_grad) for _ in range(3)]
+        self._ck(self.lib.dgx_get_gradients(self.h, *[x.ctypes.data_as(_dp) for x in g]))
+        return g
+
+    # ---- the reference's procedures ------------------------------------------------------------------------
+    def DGTimeDerivative_weakForm(self, t: float = 0.0):
+        self._ck(self.lib.dgx_time_derivative(self.h, float(t)))
+
+    def TimeStepByLSERKW2(self, t: float, dt: float):
+        self._ck(self.lib.dgx_rk_step(self.h, float(t), float(dt)))
+
+    def rk_stage(self, iStage: int, t: float, dt: float):
+        self._ck(self.lib.dgx_rk_stage(self.h, int(iStage), float(t), float(dt)))
+
+    def CalcTimeStep(self):
+        dt, err = C.c_double(), C.c_int()
+        self._ck(self.lib.dgx_calc_timestep(self.h, C.byref(dt), C.byref(err)))
+        return dt.value, err.value
+
+    def FinalizeDG(self):
+        if getattr(self, "h", None):
+            self.lib.dgx_destroy(self.h)
+            self.h = None
+
+    # ---- adapters used by host.timeloop.advance ---------------------------------------------------------------
+    def calc_timestep(self):
+        dt, err = self.CalcTimeStep()
+        if err:
+            raise DGError("Error: (1) density, (2) convective / (3) viscous timestep is NaN.")
+        return dt, None, None
+
+    def rk_step(self, t, dt):
+        self.TimeStepByLSERKW2(t, dt)
+
+    # ---- measurement ---------------------------------------------------------------------------------------------
+    def sync(self):
+        self._ck(self.lib.dgx_sync(self.h))
+
+    def run_steps(self, nSteps: int, t: float, dt: float, adaptive: bool = False):
+        ms, ln = C.c_float(), C.c_longlong()
+        self._ck(self.lib.dgx_run_steps(self.h, nSteps, float(t), float(dt), int(adaptive), C.byref(ms), C.byref(ln)))
+        return ms.value, ln.value
+
+    def profile_stage(self, t: float, dt: float):
+        names = (C.c_char_p * 8)()
+        ms = (C.c_float * 8)()
+        cnt = C.c_int()
+        self._ck(self.lib.dgx_profile_stage(self.h, float(t), float(dt), 8, names, ms, C.byref(cnt)))
+        return {names[i].decode(): ms[i] for i in range(cnt.value)}
+
+    def launch_count(self) -> int:
+        return int(self.lib.dgx_launch_count(self.h))
+
+    def __del__(self):
+        try:
+            self.FinalizeDG()
+        except Exception:
+            pass

@@ -1,0 +1,113 @@
+/*
+ * dgx.h -- C ABI of the B200-native DGSEM right-hand side + low-storage Runge-Kutta stage.
+ *
+ * Drop-in boundary for GALAEXI's hot path. The reference has no FFI layer: the boundary is a set of
+ * Fortran module procedures operating on module-global device arrays. Each entry point
+ * below replaces one of them; the Fortran ISO_C_BINDING interface a maintainer would add is in
+ * INTEGRATION.md. All array arguments are HOST pointers in the reference's own memory layout
+ * (Fortran column-major, variable index fastest), caller-owned, copied during the call; the library
+ * owns all device memory. Every function returns 0 on success, non-zero on error
+ * (dgx_last_error gives the message; the Fortran shim maps it to CALL Abort(__STAMP__,...)).
+ * Calls are collective across ranks and not thread-safe per handle.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference/src):
+ *   dgx_create            InitDG dg/dg.f90:67-171, InitLifting dg/lifting/lifting.f90:114,
+ *                         InitTimeDisc timedisc/timedisc_func.f90:94 (RK tables), InitMPIvars mpi/mpi.f90:156,
+ *                         + the H2D copies of mesh/metrics (mesh/mesh.f90:244-245,339-348,403-406,446-451)
+ *   dgx_destroy           FinalizeDG dg/dg.f90:464-495, FinalizeLifting lifting.f90:212
+ *   dgx_set_state         "d_U = U" timedisc/timedisc.f90:108, dg/dg.f90:168
+ *   dgx_get_state         "U = d_U" at analyze steps, timedisc/timedisc_func.f90:347-350
+ *   dgx_get_ut            Ut = d_Ut (diagnostics)
+ *   dgx_get_gradients     gradUx/y/z = d_gradUx/y/z, testcase/taylorgreenvortex/testcase.f90:361-364
+ *   dgx_time_derivative   DGTimeDerivative_weakForm(t) dg/dg.f90:255-425
+ *   dgx_rk_stage          one iteration of the stage loop of TimeStepByLSERKW2 timedisc/timestep.f90:86-105
+ *   dgx_rk_step           TimeStepByLSERKW2(t) timedisc/timestep.f90:49-120
+ *   dgx_calc_timestep     CalcTimeStep(errType) equations/navierstokes/calctimestep.f90:98-186
+ *   halo exchange         StartReceive/StartSend/FinishExchangeMPIData mpi/mpi.f90:277,348,494 are internal
+ *                         (NCCL send/recv on a dedicated stream); the caller only supplies the neighbour tables.
+ */
+#ifndef DGX_H
+#define DGX_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGX_NVAR      5 /* PP_nVar */
+#define DGX_NVARPRIM  6 /* PP_nVarPrim */
+#define DGX_NVARLIFT  4 /* PP_nVarLifting with PP_OPTLIFT=1: (u,v,w,T), equations/navierstokes/idealgas/eos.h:145-153 */
+
+typedef struct dgx_handle dgx_handle;
+
+typedef struct dgx_config {
+    /* discretisation (compile-time options of the reference become run-time here) */
+    int N;              /* polynomial degree PP_N */
+    int nodeType;       /* PP_NodeType: 1 Gauss, 2 Gauss-Lobatto */
+    int splitDG;        /* SPLIT_DG: -1 off (weak form), 0 SD, 3 KG, 4 PI */
+    int riemann;        /* RIEMANN: 0 LF, 1 Roe, 3 RoeEntropyFix, 5 HLLC (non-split only) */
+    int parabolic;      /* PARABOLIC: 0 Euler, 1 Navier-Stokes with BR1 lifting */
+    int viscLaw;        /* PP_VISC: 0 constant, 1 Sutherland */
+    /* mesh sizes and side ranges (1-based inclusive, mesh/mesh.f90:259-283) */
+    int nElems, nSides, nBCSides;
+    int firstInnerSide, lastInnerSide;
+    int firstMPISide_MINE, lastMPISide_MINE, firstMPISide_YOUR, lastMPISide_YOUR;
+    /* equation of state: EOS_Vars(1:8) = kappa,R,Pr,mu0,Ts,Tref,ExpoSuth,cSuth (eos.h:44-62) */
+    double EOS_Vars[8];
+    int nRefState;
+    const double *RefStatePrim;   /* (6,nRefState) */
+    const int *BCSides;           /* (2,nBCSides): BC_TYPE, BC_STATE (getboundaryflux.f90:244-252) */
+    /* operators (0:N,0:N) / (0:N), dg/dg.f90:181-242 */
+    const double *D_T, *D_Hat_T, *DVolSurf, *L_Minus, *L_Plus, *L_HatMinus, *L_HatPlus;
+    /* connectivity: ElemToSide(3,6,nElems), S2V2/S2V2_inv(2,0:N,0:N,0:4,1:6) */
+    const int *ElemToSide, *S2V2, *S2V2_inv;
+    /* geometry: Metrics_{f,g,h}Tilde(3,0:N,0:N,0:N,nElems), sJ(0:N,0:N,0:N,nElems),
+     * NormVec/TangVec1/TangVec2(3,0:N,0:N,nSides), SurfElem(0:N,0:N,nSides) */
+    const double *Metrics_fTilde, *Metrics_gTilde, *Metrics_hTilde, *sJ;
+    const double *NormVec, *TangVec1, *TangVec2, *SurfElem;
+    /* time integration: Williamson 2N tables with RKA[0]=RKc[0]=0 (timedisc_vars.f90:122-470) and the
+     * already scaled CFL/DFL numbers (timedisc_func.f90:480-550) */
+    int nRKStages;
+    const double *RKA, *RKb, *RKc;
+    double CFLScale, DFLScale;
+    /* domain decomposition (mpi/mpi_vars.f90, mesh/prepare_mesh.f90:196-320); nRanks==1: all unused */
+    int myRank, nRanks, nNbProcs;
+    const int *NbProc;               /* (nNbProcs) neighbour ranks, ascending */
+    const int *nMPISides_MINE_Proc;  /* (nNbProcs) */
+    const int *nMPISides_YOUR_Proc;  /* (nNbProcs) */
+    const int *offsetMPISides_MINE;  /* (0:nNbProcs) */
+    const int *offsetMPISides_YOUR;  /* (0:nNbProcs) */
+    const char *ncclUniqueId;        /* 128 bytes from ncclGetUniqueId on rank 0 (broadcast by the host), or NULL */
+    int device;                      /* CUDA device ordinal for this rank */
+} dgx_config;
+
+int dgx_create(dgx_handle **h, const dgx_config *cfg);
+void dgx_destroy(dgx_handle *h);
+const char *dgx_last_error(const dgx_handle *h);
+
+/* U / Ut in the reference layout U(PP_nVar,0:N,0:N,0:N,nElems); gradients (DGX_NVARLIFT,0:N,0:N,0:N,nElems).
+ * host pointers; pinned memory makes the copies asynchronous-capable but is not required */
+int dgx_set_state(dgx_handle *h, const double *U);
+int dgx_get_state(dgx_handle *h, double *U);
+int dgx_get_ut(dgx_handle *h, double *Ut);
+int dgx_get_gradients(dgx_handle *h, double *gradUx, double *gradUy, double *gradUz);
+
+int dgx_time_derivative(dgx_handle *h, double t);
+int dgx_rk_stage(dgx_handle *h, int iStage /* 1-based */, double t, double dt);
+int dgx_rk_step(dgx_handle *h, double t, double dt);
+/* dt = min(convective, viscous) over all ranks; errType != 0 if the state is not finite */
+int dgx_calc_timestep(dgx_handle *h, double *dt, int *errType);
+
+/* measurement helpers (not part of the reference interface) */
+int dgx_sync(dgx_handle *h);
+/* nSteps RK steps with fixed dt, state resident in HBM; returns device-timed milliseconds (CUDA events on
+ * the launching stream) and the number of kernels launched */
+int dgx_run_steps(dgx_handle *h, int nSteps, double t, double dt, int adaptive_dt, float *ms, long long *launches);
+/* per-kernel CUDA-event timing of one RK stage: names[i] -> ms[i], *count entries (<= cap) */
+int dgx_profile_stage(dgx_handle *h, double t, double dt, int cap, const char **names, float *ms, int *count);
+int dgx_nccl_unique_id(char *out128);
+long long dgx_launch_count(const dgx_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGX_H */

@@ -1,0 +1,117 @@
+"""Shared test cases: the reference's regression configurations + synthetic meshes (seeded, smooth fields)."""
+import os
+
+import numpy as np
+
+from galaexi_b200.host import basis as bs
+from galaexi_b200.host import case as cs
+from galaexi_b200.host import equation as eq
+from galaexi_b200.host import mesh as ms
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_mesh(name):
+    m = np.load(os.path.join(GOLD, name))
+    return dict(NGeo=int(m["NGeo"]), ElemInfo=m["ElemInfo"], SideInfo=m["SideInfo"], NodeCoords=m["NodeCoords"],
+                BCNames=[str(s) for s in m["BCNames"]], BCType=m["BCType"])
+
+
+TGV_EOS = dict(kappa=1.4, R=71.42857, Pr=0.72, mu0=6.25e-4)
+TGV_REF = ((1.0, 1.0, 0.0, 0.0, 17194.8345650329),)
+
+
+def tgv_split_case(nProcs=1, myRank=0, hopr=None, N=7, **kw):
+    """regressioncheck/checks/tgv/split: N=7 GL, PI split form, RoeEntropyFix, BR1, 8^3 periodic."""
+    h = hopr or load_mesh("tgv_split_mesh.npz")
+    eos = eq.Eos(**TGV_EOS)
+    args = dict(split="PI", riemann="RoeEntropyFix", parabolic=True, eos=eos, refstates=TGV_REF, CFLScale=0.8,
+                DFLScale=0.8, useCurveds=False, nProcs=nProcs, myRank=myRank)
+    args.update(kw)
+    c = cs.build_case(h, N, bs.NODETYPE_GL, **args)
+    U0 = eq.ini_tgv(c.geo["Elem_xGP"], eos, mach=0.1, ini_const_dens=True)
+    return c, U0
+
+
+def tgv_box_case(E=4, N=5, NGeo=1, deform=0.0, nProcs=1, myRank=0, perturb=0.0, **kw):
+    """Synthetic TGV box [0,2pi]^3, optionally curved."""
+    h = ms.make_box_mesh((E, E, E), x0=(0.0, 0.0, 0.0), x1=(2 * np.pi,) * 3, NGeo=NGeo, deform=deform)
+    eos = eq.Eos(**TGV_EOS)
+    args = dict(split="PI", riemann="RoeEntropyFix", parabolic=True, eos=eos, refstates=TGV_REF, nProcs=nProcs,
+                myRank=myRank)
+    args.update(kw)
+    nt = args.pop("node_type", bs.NODETYPE_GL)
+    c = cs.build_case(h, N, nt, **args)
+    U0 = eq.ini_tgv(c.geo["Elem_xGP"], eos)
+    if perturb:
+        U0 = eq.perturb(U0, perturb, seed=12345 + myRank)
+    return c, U0
+
+
+def cavity_case(nProcs=1, myRank=0, riemann="RoeEntropyFix"):
+    """regressioncheck/checks/parabolic/cavity_3D: N=2 Gauss, weak form, BR1, walls (4) + Dirichlet lid (2)."""
+    h = load_mesh("cavity3d_mesh.npz")
+    eos = eq.Eos(kappa=1.4, R=1.0, Pr=0.72, mu0=0.01)
+    c = cs.build_case(h, 2, bs.NODETYPE_G, split=None, riemann=riemann, parabolic=True, eos=eos,
+                      refstates=((1.0, 1.0, 0.0, 0.0, 71.4285714286), (1.0, 0.0, 0.0, 0.0, 71.4285714286)),
+                      user_bcs={"BC_wall_left": (4, 1), "BC_wall_right": (4, 1), "BC_free": (2, 1)}, CFLScale=0.99,
+                      DFLScale=0.4, useCurveds=False, nProcs=nProcs, myRank=myRank)
+    U0 = eq.ini_refstate(c.geo["Elem_xGP"], c.RefStatePrim[1], eos)
+    return c, U0
+
+
+def shu_vortex_case(E=8, N=3, nProcs=1, myRank=0, **kw):
+    """BASELINE config #1: Shu vortex, Euler, N=3, 8^3 periodic Cartesian box (ini/shuVortex)."""
+    h = ms.make_box_mesh((E, E, E), x0=(-1.0, -1.0, -1.0), x1=(1.0, 1.0, 1.0))
+    eos = eq.Eos(kappa=1.4, R=287.058)
+    args = dict(split=None, riemann="LF", parabolic=False, eos=eos, refstates=((1.0, 1.0, 0.0, 0.0, 2.85714),),
+                nProcs=nProcs, myRank=myRank)
+    args.update(kw)
+    nt = args.pop("node_type", bs.NODETYPE_G)
+    c = cs.build_case(h, N, nt, **args)
+    U0 = eq.ini_shu_vortex(c.geo["Elem_xGP"], c.RefStatePrim[0], eos, amplitude=0.2, halfwidth=0.5)
+    return c, U0
+
+
+def naca_case(N=3, nProcs=1, myRank=0, **kw):
+    """regressioncheck/checks/naca/3D mesh: curved NGeo=2, BC 2 (refstate) + 3 (adiabatic wall) + periodic z."""
+    h = load_mesh("naca_mesh.npz")
+    eos = eq.Eos(kappa=1.4, R=287.058, Pr=0.72, mu0=0.0002)
+    args = dict(split=None, riemann="RoeEntropyFix", parabolic=True, eos=eos,
+                refstates=((1.0, 0.990268069, 0.139173101, 0.0, 4.4642857),), nProcs=nProcs, myRank=myRank)
+    args.update(kw)
+    nt = args.pop("node_type", bs.NODETYPE_G)
+    c = cs.build_case(h, N, nt, **args)
+    x = c.geo["Elem_xGP"]
+    U0 = eq.ini_refstate(x, c.RefStatePrim[0], eos)
+    # smooth deterministic perturbation so that every term of the operator is exercised
+    s = 1.0 + 0.02 * np.sin(3.0 * x[..., 0]) * np.cos(2.0 * x[..., 1]) * np.cos(5.0 * x[..., 2] + 0.3)
+    U0 = U0 * s[..., None]
+    return c, U0
+
+
+def channel_case(E=4, N=5, nProcs=1, myRank=0, **kw):
+    """BASELINE config #4-like: plane channel, isothermal walls (4) at y+-, periodic x,z, Roe flux, y-stretched."""
+    def stretch(d, s):
+        if d != 1:
+            return s
+        return 0.5 * (1.0 + np.tanh(1.5 * (2.0 * s - 1.0)) / np.tanh(1.5))
+    h = ms.make_box_mesh((E, E, E), x0=(0.0, -1.0, -np.pi / 2), x1=(2 * np.pi, 1.0, np.pi / 2),
+                         bctype=["periodic", (4, 1), "periodic", (4, 1), "periodic", "periodic"], stretch=stretch)
+    eos = eq.Eos(kappa=1.4, R=287.058, Pr=0.71, mu0=5.0e-4)
+    args = dict(split="PI", riemann="Roe", parabolic=True, eos=eos, refstates=((1.0, 1.0, 0.0, 0.0, 71.4285714),),
+                nProcs=nProcs, myRank=myRank)
+    args.update(kw)
+    nt = args.pop("node_type", bs.NODETYPE_GL)
+    c = cs.build_case(h, N, nt, **args)
+    x = c.geo["Elem_xGP"]
+    prim = np.broadcast_to(c.RefStatePrim[0], x.shape[:-1] + (6,)).copy()
+    prim[..., 1] = 1.5 * (1.0 - x[..., 1] ** 2) * (1.0 + 0.1 * np.sin(2 * x[..., 0]) * np.cos(2 * x[..., 2]))
+    prim[..., 2] = 0.05 * np.sin(x[..., 0]) * (1.0 - x[..., 1] ** 2)
+    prim[..., 3] = 0.05 * np.cos(2 * x[..., 2]) * (1.0 - x[..., 1] ** 2)
+    U0 = eq.prim_to_cons(prim, eos.kappa)
+    return c, U0
+
+
+def rel_l2(a, b):
+    return float(np.sqrt(np.sum((a - b) ** 2)) / max(np.sqrt(np.sum(b ** 2)), 1e-300))

@@ -19,13 +19,23 @@
  * node types Gauss / Gauss-Lobatto, weak form or split form (SD, KG, PI), Riemann solvers LF, Roe,
  * RoeEntropyFix, HLLC, constant or Sutherland viscosity, BC types 2, 3, 4, 9.
  *
+ * Two builds of this one source (oracle/Makefile): libdgoracle.so (FP64, no FMA contraction: the reference's
+ * arithmetic) and libdgoracle_ld.so (-DDGO_EXTENDED: the same formulas and the same FP64 constants
+ * evaluated in 80-bit extended precision). The second one measures how far FP64 round-off moves a result, so
+ * that ill-conditioned comparisons (e.g. the low-Mach TGV initial residual, dominated by cancellation) can be
+ * judged against the exact value of the reference's formulas instead of against one particular rounding order.
+ *
  * OpenMP over elements / sides is only used to time the CPU baseline on all host cores; results do not
  * depend on the thread count (every loop iteration owns its outputs, as in the reference's gather kernels).
  */
-#include <math.h>
+#include <tgmath.h> /* type-generic sqrt/pow/fabs/fmax: the same source also builds the extended-precision variant */
 #include <stdlib.h>
 #include <string.h>
 #include <stdio.h>
+
+#ifdef DGO_EXTENDED
+#define double long double /* after the system headers: every FP64 quantity below becomes 80-bit extended */
+#endif
 
 #define NV 5   /* PP_nVar        */
 #define NP 6   /* PP_nVarPrim    */

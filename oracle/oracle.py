@@ -12,56 +12,80 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "libdgoracle.so")
-_dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 
 
-class _Config(C.Structure):
-    _fields_ = [(k, C.c_int) for k in ("N", "nElems", "nSides", "nBCSides", "firstInnerSide", "lastInnerSide",
-                                       "firstMPISide_MINE", "lastMPISide_MINE", "firstMPISide_YOUR", "lastMPISide_YOUR",
-                                       "nodeType", "splitDG", "riemann", "parabolic", "viscLaw", "nRefState")] + \
-               [("EOS", C.c_double * 8)] + \
-               [(k, _dp) for k in ("D_T", "D_Hat_T", "DVolSurf", "L_Minus", "L_Plus", "L_HatMinus", "L_HatPlus")] + \
-               [(k, _ip) for k in ("ElemToSide", "S2V2", "S2V2_inv", "BCSides")] + \
-               [(k, _dp) for k in ("Metrics_fTilde", "Metrics_gTilde", "Metrics_hTilde", "sJ", "NormVec", "TangVec1",
-                                   "TangVec2", "SurfElem", "RefStatePrim")]
+class _Prec:
+    """One build of dg_oracle.c: FP64 ("double") or 80-bit extended ("extended", -DDGO_EXTENDED)."""
+
+    def __init__(self, name):
+        self.name = name
+        ext = name == "extended"
+        self.real = C.c_longdouble if ext else C.c_double
+        self.np = np.longdouble if ext else np.float64
+        self.rp = C.POINTER(self.real)
+        self.libname = "libdgoracle_ld.so" if ext else "libdgoracle.so"
+        rp = self.rp
+
+        class Config(C.Structure):
+            _fields_ = [(k, C.c_int) for k in ("N", "nElems", "nSides", "nBCSides", "firstInnerSide", "lastInnerSide",
+                                               "firstMPISide_MINE", "lastMPISide_MINE", "firstMPISide_YOUR",
+                                               "lastMPISide_YOUR", "nodeType", "splitDG", "riemann", "parabolic",
+                                               "viscLaw", "nRefState")] + \
+                       [("EOS", self.real * 8)] + \
+                       [(k, rp) for k in ("D_T", "D_Hat_T", "DVolSurf", "L_Minus", "L_Plus", "L_HatMinus", "L_HatPlus")] + \
+                       [(k, _ip) for k in ("ElemToSide", "S2V2", "S2V2_inv", "BCSides")] + \
+                       [(k, rp) for k in ("Metrics_fTilde", "Metrics_gTilde", "Metrics_hTilde", "sJ", "NormVec",
+                                          "TangVec1", "TangVec2", "SurfElem", "RefStatePrim")]
+        self.Config = Config
+        self._lib = None
+
+    def lib(self):
+        if self._lib is None:
+            path = os.path.join(_HERE, self.libname)
+            src = os.path.join(_HERE, "dg_oracle.c")
+            if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+                subprocess.check_call(["make", "-s", "-C", _HERE, self.libname])
+            L = C.CDLL(path)
+            r, rp = self.real, self.rp
+            L.dgo_create.restype = C.c_void_p
+            L.dgo_create.argtypes = [C.POINTER(self.Config)]
+            L.dgo_destroy.argtypes = [C.c_void_p]
+            L.dgo_array.restype = rp
+            L.dgo_array.argtypes = [C.c_void_p, C.c_char_p]
+            L.dgo_time_derivative.argtypes = [C.c_void_p, r]
+            L.dgo_rk_stage.argtypes = [C.c_void_p, r, r, r]
+            L.dgo_rk_step.argtypes = [C.c_void_p, r, r, C.c_int, rp, rp, rp]
+            L.dgo_calc_timestep.restype = r
+            L.dgo_calc_timestep.argtypes = [C.c_void_p, r, r, rp, rp]
+            L.dgo_prolong_to_face.argtypes = [C.c_void_p, C.c_int, rp, rp, rp]
+            L.dgo_surf_int.argtypes = [C.c_void_p, C.c_int, rp, rp, rp]
+            L.dgo_lifting.argtypes = [C.c_void_p]
+            L.dgo_sizeof_config.restype = C.c_size_t
+            assert L.dgo_sizeof_config() == C.sizeof(self.Config)
+            self._lib = L
+        return self._lib
+
+    def d(self, a):
+        return a.ctypes.data_as(self.rp)
+
+
+_PREC = {"double": _Prec("double"), "extended": _Prec("extended")}
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "dg_oracle.c")
-    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-s", "-C", _HERE, "libdgoracle.so"])
-    return _LIB
-
-
-_lib = None
+    if force:
+        subprocess.check_call(["make", "-s", "-B", "-C", _HERE])
+    _PREC["double"].lib()
+    return os.path.join(_HERE, "libdgoracle.so")
 
 
 def lib():
-    global _lib
-    if _lib is None:
-        _lib = C.CDLL(build())
-        _lib.dgo_create.restype = C.c_void_p
-        _lib.dgo_create.argtypes = [C.POINTER(_Config)]
-        _lib.dgo_destroy.argtypes = [C.c_void_p]
-        _lib.dgo_array.restype = _dp
-        _lib.dgo_array.argtypes = [C.c_void_p, C.c_char_p]
-        _lib.dgo_time_derivative.argtypes = [C.c_void_p, C.c_double]
-        _lib.dgo_rk_stage.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
-        _lib.dgo_rk_step.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, _dp, _dp, _dp]
-        _lib.dgo_calc_timestep.restype = C.c_double
-        _lib.dgo_calc_timestep.argtypes = [C.c_void_p, C.c_double, C.c_double, _dp, _dp]
-        _lib.dgo_prolong_to_face.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
-        _lib.dgo_surf_int.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
-        _lib.dgo_lifting.argtypes = [C.c_void_p]
-        _lib.dgo_sizeof_config.restype = C.c_size_t
-        assert _lib.dgo_sizeof_config() == C.sizeof(_Config)
-    return _lib
+    return _PREC["double"].lib()
 
 
 def _d(a):
-    return a.ctypes.data_as(_dp)
+    return _PREC["double"].d(a)
 
 
 def _i(a):
@@ -71,13 +95,15 @@ def _i(a):
 class Oracle:
     """One single-rank DG operator instance built from a galaexi_b200.host.case.Case."""
 
-    def __init__(self, case):
-        L = lib()
+    def __init__(self, case, precision: str = "double"):
+        self.prec = _PREC[precision]
+        L = self.prec.lib()
+        _d = self.prec.d
         m, b, g = case.mesh, case.basis, case.geo
         self.case = case
         self.n = case.N + 1
         # keep references: the C side stores raw pointers
-        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        f64 = lambda a: np.ascontiguousarray(a, dtype=self.prec.np)
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
         # operator matrices: Fortran M(a,b) at [a + n*b] == C array M.T
         self._keep = dict(
@@ -88,7 +114,7 @@ class Oracle:
             Metrics_fTilde=f64(g["Metrics_fTilde"]), Metrics_gTilde=f64(g["Metrics_gTilde"]), Metrics_hTilde=f64(g["Metrics_hTilde"]),
             sJ=f64(g["sJ"]), NormVec=f64(g["NormVec"]), TangVec1=f64(g["TangVec1"]), TangVec2=f64(g["TangVec2"]),
             SurfElem=f64(g["SurfElem"]), RefStatePrim=f64(case.RefStatePrim))
-        c = _Config()
+        c = self.prec.Config()
         c.N, c.nElems, c.nSides = case.N, m.nElems, m.nSides
         c.nBCSides, c.firstInnerSide, c.lastInnerSide = m.nBCSides, m.firstInnerSide, m.lastInnerSide
         c.firstMPISide_MINE, c.lastMPISide_MINE = m.firstMPISide_MINE, m.lastMPISide_MINE
@@ -120,36 +146,39 @@ class Oracle:
 
     def array(self, name: str) -> np.ndarray:
         """Writable numpy view (reference memory layout, C-order reversed index list) of an oracle array."""
-        p = lib().dgo_array(self.h, name.encode())
+        p = self.prec.lib().dgo_array(self.h, name.encode())
         shp = self._shapes[name]
-        return np.ctypeslib.as_array(p, shape=(int(np.prod(shp)),)).reshape(shp)
+        cnt = int(np.prod(shp))
+        buf = (self.prec.real * cnt).from_address(C.addressof(p.contents))
+        return np.frombuffer(buf, dtype=self.prec.np, count=cnt).reshape(shp)
 
     def set_state(self, U: np.ndarray):
         self.array("U")[...] = U
         self.array("Ut_tmp")[...] = 0.0
 
     def time_derivative(self, t: float = 0.0) -> np.ndarray:
-        err = lib().dgo_time_derivative(self.h, float(t))
+        err = self.prec.lib().dgo_time_derivative(self.h, float(t))
         if err:
             raise RuntimeError("oracle: unsupported boundary condition type")
         return self.array("Ut")
 
     def rk_step(self, t: float, dt: float):
         td = self.case.timedisc
-        A, b, c = (np.ascontiguousarray(x, dtype=np.float64) for x in (td.RKA, td.RKb, td.RKc))
-        err = lib().dgo_rk_step(self.h, float(t), float(dt), td.nRKStages, _d(A), _d(b), _d(c))
+        _d = self.prec.d
+        A, b, c = (np.ascontiguousarray(x, dtype=self.prec.np) for x in (td.RKA, td.RKb, td.RKc))
+        err = self.prec.lib().dgo_rk_step(self.h, float(t), float(dt), td.nRKStages, _d(A), _d(b), _d(c))
         if err:
             raise RuntimeError("oracle: unsupported boundary condition type")
 
     def calc_timestep(self):
-        tc, tv = C.c_double(), C.c_double()
+        tc, tv = self.prec.real(), self.prec.real()
         td = self.case.timedisc
-        dt = lib().dgo_calc_timestep(self.h, td.CFLScale, td.DFLScale, C.byref(tc), C.byref(tv))
-        return dt, tc.value, tv.value
+        dt = self.prec.lib().dgo_calc_timestep(self.h, td.CFLScale, td.DFLScale, C.byref(tc), C.byref(tv))
+        return float(dt), float(tc.value), float(tv.value)
 
     def close(self):
         if self.h:
-            lib().dgo_destroy(self.h)
+            self.prec.lib().dgo_destroy(self.h)
             self.h = None
 
     def __del__(self):

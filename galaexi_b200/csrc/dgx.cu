@@ -280,6 +280,7 @@ extern "C" {
 
 const char* dgx_last_error(const dgx_handle* h) { return h ? h->err.c_str() : "null handle"; }
 long long dgx_launch_count(const dgx_handle* h) { return h ? h->launches : 0; }
+unsigned long dgx_sizeof_config(void) { return (unsigned long)sizeof(dgx_config); }
 
 int dgx_nccl_unique_id(char* out128) {
     std::string err;

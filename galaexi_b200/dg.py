@@ -28,7 +28,7 @@ _ip = C.POINTER(C.c_int)
 
 EXPORTS = ("dgx_create", "dgx_destroy", "dgx_last_error", "dgx_set_state", "dgx_get_state", "dgx_get_ut",
            "dgx_get_gradients", "dgx_time_derivative", "dgx_rk_stage", "dgx_rk_step", "dgx_calc_timestep",
-           "dgx_sync", "dgx_run_steps", "dgx_profile_stage", "dgx_nccl_unique_id", "dgx_launch_count")
+           "dgx_sync", "dgx_run_steps", "dgx_profile_stage", "dgx_nccl_unique_id", "dgx_launch_count", "dgx_sizeof_config")
 
 
 class DgxConfig(C.Structure):
@@ -81,6 +81,9 @@ def load_library():
     lib.dgx_nccl_unique_id.argtypes = [C.c_char_p]
     lib.dgx_launch_count.argtypes = [h]
     lib.dgx_launch_count.restype = C.c_longlong
+    lib.dgx_sizeof_config.restype = C.c_ulong
+    if lib.dgx_sizeof_config() != C.sizeof(DgxConfig):
+        raise RuntimeError(f"struct dgx_config mismatch: library {lib.dgx_sizeof_config()} B, binding {C.sizeof(DgxConfig)} B")
     _lib = lib
     return lib
 

@@ -106,6 +106,8 @@ int dgx_run_steps(dgx_handle *h, int nSteps, double t, double dt, int adaptive_d
 int dgx_profile_stage(dgx_handle *h, double t, double dt, int cap, const char **names, float *ms, int *count);
 int dgx_nccl_unique_id(char *out128);
 long long dgx_launch_count(const dgx_handle *h);
+/* sizeof(dgx_config) as compiled: lets a foreign-language binding verify its struct mirror */
+unsigned long dgx_sizeof_config(void);
 
 #ifdef __cplusplus
 }

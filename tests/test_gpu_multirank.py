@@ -1,0 +1,29 @@
+"""N>1 on real GPUs: SFC partition + NCCL face halos reproduce the single-rank result (skipped on 1-GPU boxes)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpus():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("case", ["tgv", "cavity", "channel", "shu"])
+def test_two_ranks_match_single_rank(case):
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    port = 29500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tools", "mr_check.py"), case]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    lines = [l for l in p.stdout.splitlines() if l.startswith("MRCHECK ")]
+    assert p.returncode == 0 and lines, p.stdout[-2000:] + p.stderr[-4000:]
+    r = json.loads(lines[-1][8:])
+    assert r["u_rel_l2"] <= 1e-10 and r["dt_rel"] <= 1e-13

@@ -212,5 +212,6 @@ def test_freestream_and_conservation_full_size():
     U1 = s.get_state()
     d = np.sum(W * (U1 - U0), axis=(0, 1, 2, 3))
     ref = np.sum(W * np.abs(U0), axis=(0, 1, 2, 3))
+    ref[1:4] = ref[1:4].max()  # the TGV has no z-momentum at t=0: one common momentum scale
     assert np.all(np.abs(d) <= 1e-11 * ref)
     s.FinalizeDG()

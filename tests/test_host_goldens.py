@@ -1,0 +1,203 @@
+"""Host init mirror (galaexi_b200.host) against the reference's own unit-test golden files (unitTests/*.bin,
+converted by tools/make_golden.py into tests/golden/unit_goldens.npz). CPU only.
+
+Criterion of the reference's unit tests: ALMOSTEQUALABSORREL(x, ref, 100*PP_RealTolerance) with
+PP_RealTolerance = EPSILON(1.0D0) (src/flexi.h:66-68): |x-ref| <= tol  or  |x-ref| <= tol*max(|x|,|ref|).
+Integer tables are compared bit-exactly.
+"""
+import numpy as np
+import pytest
+
+from galaexi_b200.host import basis as bs
+from galaexi_b200.host import mappings as mp
+from galaexi_b200.host import mesh as ms
+
+TOL = 100.0 * np.finfo(np.float64).eps
+TYPES = ("GAUSS", "GAUSS-LOBATTO", "CHEBYSHEV-GAUSS-LOBATTO", "VISU")
+
+
+def almost_equal_abs_or_rel(x, ref, tol=TOL):
+    x, ref = np.asarray(x, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    d = np.abs(x - ref)
+    return bool(np.all((d <= tol) | (d <= tol * np.maximum(np.abs(x), np.abs(ref)))))
+
+
+@pytest.mark.parametrize("it,node_type", list(enumerate(TYPES)))
+def test_nodes_and_weights(goldens, it, node_type):
+    """unitTests/NodesAndWeights.f90: xGP, wGP, wBary for N=1..10, four node types."""
+    ref = goldens["nodes_xi_w_wbary"]
+    for N in range(1, 11):
+        x, w, wb = bs.get_nodes_and_weights(N, node_type)
+        assert almost_equal_abs_or_rel(x, ref[0, it, N - 1, : N + 1]), (node_type, N, "x")
+        assert almost_equal_abs_or_rel(w, ref[1, it, N - 1, : N + 1]), (node_type, N, "w")
+        assert almost_equal_abs_or_rel(wb, ref[2, it, N - 1, : N + 1]), (node_type, N, "wBary")
+
+
+@pytest.mark.parametrize("it,node_type", list(enumerate(TYPES)))
+def test_derivative_matrix(goldens, it, node_type):
+    """unitTests/DerivativeMatrix.f90: D(0:N,0:N) for N=1..10."""
+    ref = goldens["D"]
+    for N in range(1, 11):
+        x, _, _ = bs.get_nodes_and_weights(N, node_type)
+        D = bs.polynomial_derivative_matrix(x)
+        r = ref[10 * it + N - 1, : N + 1, : N + 1].T  # stored [col][row]
+        assert almost_equal_abs_or_rel(D, r), (node_type, N)
+
+
+def test_vandermonde(goldens):
+    """unitTests/Vandermonde.f90: 512 nodal and modal Vandermonde pairs, N_in=2..5, N_out=3..6."""
+    raw = goldens["vdm_raw"]
+    nrec = 512
+    out_in = raw[: 6 * 7 * nrec].reshape(nrec, 7, 6)        # Vdm_Out_In(0:5,0:6,k)  -> [k][iOut][iIn]
+    in_out = raw[6 * 7 * nrec:].reshape(nrec, 6, 7)         # Vdm_In_Out(0:6,0:5,k)  -> [k][iIn][iOut]
+    k = 0
+    for n_in in range(2, 6):
+        for n_out in range(3, 7):
+            for t_in in TYPES:
+                for t_out in TYPES:
+                    for modal in (False, True):
+                        V = bs.get_vandermonde(n_in, t_in, n_out, t_out, modal=modal)       # (0:n_out, 0:n_in)
+                        Vb = bs.get_vandermonde(n_out, t_out, n_in, t_in, modal=modal)      # (0:n_in, 0:n_out)
+                        assert almost_equal_abs_or_rel(V, in_out[k, : n_in + 1, : n_out + 1].T), (n_in, t_in, n_out, t_out, modal)
+                        assert almost_equal_abs_or_rel(Vb, out_in[k, : n_out + 1, : n_in + 1].T), (n_in, t_in, n_out, t_out, modal, "back")
+                        k += 1
+    assert k == nrec
+
+
+def test_s2v2_bit_exact(goldens):
+    """UnittestElementData3D.bin: S2V2(2,0:9,0:9,0:4,1:6) of the reference (mappings.f90:150-178), bit-exact."""
+    maps = mp.build_mappings(9)
+    assert maps["S2V2"].dtype == np.int32
+    assert np.array_equal(maps["S2V2"], goldens["ued_S2V2"])
+
+
+def test_s2v2_inverse_and_flip_maps():
+    """S2V2_inv o S2V2 == identity for all N, flips and sides; FS2M is an involution pair with flip_m2s."""
+    for N in (1, 2, 3, 4, 7):
+        m = mp.build_mappings(N)
+        n = N + 1
+        for s in range(6):
+            for f in range(5):
+                for q in range(n):
+                    for p in range(n):
+                        a, b = m["S2V2"][s, f, q, p]
+                        assert tuple(m["S2V2_inv"][s, f, b, a]) == (p, q)
+
+
+@pytest.mark.parametrize("node_type", ["GAUSS", "GAUSS-LOBATTO"])
+def test_face_operators(node_type):
+    """Defining identities of L_Minus/L_Plus/L_Hat*/D/D_Hat (dg.f90:181-242) for both node types."""
+    b = bs.init_dg_basis(9, node_type)
+    # interpolation to the boundary reproduces constants and the boundary value of the nodal polynomial
+    assert abs(b.L_Minus.sum() - 1.0) < 1e-13 and abs(b.L_Plus.sum() - 1.0) < 1e-13
+    assert abs(b.L_Minus @ b.xGP + 1.0) < 1e-13 and abs(b.L_Plus @ b.xGP - 1.0) < 1e-13
+    assert np.allclose(b.L_HatMinus, b.L_Minus / b.wGP, rtol=0, atol=1e-12)
+    # D differentiates polynomials up to degree N exactly; SBP property of D_Hat: M D_Hat = -D^T M
+    for d in range(1, 6):
+        assert np.allclose(b.D @ b.xGP ** d, d * b.xGP ** (d - 1), atol=1e-11)
+    assert np.allclose(np.diag(b.wGP) @ b.D_Hat, -(b.D.T @ np.diag(b.wGP)), atol=1e-12)
+
+
+def test_unit_element_file_nodetype(goldens):
+    """Exactly one of the two node types reproduces the face operators stored in UnittestElementData3D.bin."""
+    hits = []
+    for nt in ("GAUSS", "GAUSS-LOBATTO"):
+        b = bs.init_dg_basis(9, nt)
+        hits.append(all(almost_equal_abs_or_rel(getattr(b, nm), goldens["ued_" + nm]) for nm in ("L_Minus", "L_Plus", "L_HatMinus", "L_HatPlus")))
+    assert sum(hits) == 1, hits
+
+
+def test_split_form_dvolsurf():
+    """DVolSurf = D_T with the two surface corrections (dg.f90:225-237); rows of D_T sum to zero (free stream)."""
+    for N in (2, 5, 7):
+        b = bs.init_dg_basis(N, "GAUSS-LOBATTO")
+        d = b.DVolSurf - b.D_T
+        assert d[0, 0] == 1.0 / (2.0 * b.wGP[0]) and d[N, N] == -1.0 / (2.0 * b.wGP[N])
+        d[0, 0] = d[N, N] = 0.0
+        assert not d.any()
+        assert np.abs(b.D.sum(axis=1)).max() < 1e-12
+
+
+# ---- mesh connectivity: integer tables are deterministic and self-consistent ------------------------------------
+def _check_side_tables(m, n_expected_sides=None):
+    E2S = m.ElemToSide
+    assert E2S.dtype == np.int32
+    nS = m.nSides
+    cnt_master = np.zeros(nS + 1, int)
+    cnt_slave = np.zeros(nS + 1, int)
+    for e in range(m.nElems):
+        for l in range(6):
+            sid, flip, ism = E2S[e, l]
+            assert 1 <= sid <= nS
+            assert (flip == 0) == bool(ism)
+            (cnt_master if flip == 0 else cnt_slave)[sid] += 1
+    assert cnt_master.max() <= 1 and cnt_slave.max() <= 1
+    # every BC / inner / MINE side has a master element on this rank; inner sides have both
+    for sid in range(1, nS + 1):
+        if sid <= m.nBCSides:
+            assert cnt_master[sid] == 1 and cnt_slave[sid] == 0
+        elif m.firstInnerSide <= sid <= m.lastInnerSide:
+            assert cnt_master[sid] == 1 and cnt_slave[sid] == 1
+        elif m.firstMPISide_MINE <= sid <= m.lastMPISide_MINE:
+            assert cnt_master[sid] == 1 and cnt_slave[sid] == 0
+        elif m.firstMPISide_YOUR <= sid <= m.lastMPISide_YOUR:
+            assert cnt_master[sid] == 0 and cnt_slave[sid] == 1
+
+
+def test_periodic_box_side_numbering():
+    """Periodic single-rank cube: S = 3E, all inner, nBCSides = 0 (mesh_readin.f90:642); first-touch numbering."""
+    h = ms.make_box_mesh((4, 4, 4))
+    m = ms.prepare_mesh(h)
+    assert m.nElems == 64 and m.nSides == 192 and m.nBCSides == 0
+    assert (m.firstInnerSide, m.lastInnerSide) == (1, 192)
+    _check_side_tables(m)
+    # setLocalSideIDs (prepare_mesh.f90:293-350): element-major, locSide 1..6, first touch gets the next id
+    seen = 0
+    for e in range(m.nElems):
+        for l in range(6):
+            sid = m.ElemToSide[e, l, 0]
+            if sid > seen:
+                assert sid == seen + 1
+                seen = sid
+    assert seen == m.nSides
+
+
+@pytest.mark.parametrize("nProcs", [2, 3, 4, 8])
+def test_partition_side_ranges(nProcs):
+    """Domain decomposition (mesh_readin.f90:766-778, prepare_mesh.f90:196-350): contiguous element ranges,
+    [BC, inner, MPI_MINE, MPI_YOUR] side order, MINE/YOUR counts mirrored between neighbours."""
+    h = ms.make_box_mesh((4, 4, 4))
+    meshes = [ms.prepare_mesh(h, nProcs=nProcs, myRank=r) for r in range(nProcs)]
+    off = ms.build_partition(64, nProcs)
+    assert off[0] == 0 and off[-1] == 64
+    assert sum(m.nElems for m in meshes) == 64
+    sizes = np.diff(off)
+    assert sizes.max() - sizes.min() <= 1 and np.all(np.diff(sizes) <= 0)  # first (nGlobal mod nProcs) ranks get +1
+    for r, m in enumerate(meshes):
+        _check_side_tables(m)
+        assert m.lastInnerSide + 1 == m.firstMPISide_MINE
+        assert m.lastMPISide_MINE + 1 == m.firstMPISide_YOUR
+        assert m.lastMPISide_YOUR == m.nSides
+        for ib, nb in enumerate(m.NbProc):
+            o = meshes[nb]
+            jb = list(o.NbProc).index(r)
+            assert m.nMPISides_MINE_Proc[ib] == o.nMPISides_YOUR_Proc[jb]
+            assert m.nMPISides_YOUR_Proc[ib] == o.nMPISides_MINE_Proc[jb]
+            k = m.nMPISides_MINE_Proc[ib] + m.nMPISides_YOUR_Proc[ib]
+            # lower rank is master for the first floor(k/2) sides (prepare_mesh.f90:255-262)
+            lo = m if r < nb else o
+            ilo = ib if r < nb else jb
+            assert lo.nMPISides_MINE_Proc[ilo] == k // 2
+    # unique sides across ranks: inner + BC + MINE of every rank == 3*64 for the periodic cube
+    tot = sum(m.lastMPISide_MINE for m in meshes)
+    assert tot == 192
+
+
+def test_hilbert_curve_is_a_space_filling_curve():
+    """Consecutive elements of the generated mesh are face neighbours (Hilbert ordering)."""
+    ijk = np.stack(np.meshgrid(np.arange(8), np.arange(8), np.arange(8), indexing="ij"), -1).reshape(-1, 3)
+    key = ms.hilbert_index_3d(ijk, 3)
+    assert len(np.unique(key)) == 512
+    order = np.argsort(key)
+    steps = np.abs(np.diff(ijk[order], axis=0)).sum(axis=1)
+    assert np.all(steps == 1)

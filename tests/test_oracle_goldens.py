@@ -1,0 +1,173 @@
+"""Pins the CPU oracle (oracle/dg_oracle.c) to the reference's own golden vectors. CPU only.
+
+  unitTests/ProlongToFace_{G,GL}3D.bin, unitTests/SurfInt_{G,GL}3D.bin     100*eps (abs-or-rel), src/flexi.h:66-68
+  regressioncheck/checks/parabolic/cavity_3D reference state (t=1)         abs 1e-12 (analyze.ini h5diff)
+  regressioncheck/checks/tgv/split CSV (rows 1-3)                          rel 1e-4 (analyze.ini); we hold 1e-12
+
+The golden files are fixtures under tests/golden/ made from /root/reference by tools/make_golden.py.
+"""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+import cases
+from galaexi_b200.host import basis as bs
+from galaexi_b200.host import equation as eq
+from galaexi_b200.host import mappings as mp
+from galaexi_b200.host import timedisc as td
+from galaexi_b200.host import timeloop
+from oracle.oracle import Oracle
+from test_host_goldens import almost_equal_abs_or_rel
+
+
+def unit_element_case(goldens, node_type):
+    """The single N=9 element of unitTests/unittest.f90 (ReadInReferenceElementData): 6 sides, all master, flip 0,
+    face operators taken from UnittestElementData3D.bin exactly as the reference's unit tests do."""
+    N, n = 9, 10
+    b = bs.init_dg_basis(N, node_type)
+    for nm in ("L_Minus", "L_Plus", "L_HatMinus", "L_HatPlus"):
+        setattr(b, nm, np.array(goldens["ued_" + nm], dtype=np.float64))
+    s2e = goldens["ued_SideToElem"]
+    E2S = np.zeros((1, 6, 3), dtype=np.int32)
+    for sid in range(6):
+        assert s2e[sid, 0] == 1 and s2e[sid, 1] == -1        # S2E_ELEM_ID=1, no neighbour
+        E2S[0, s2e[sid, 2] - 1] = (sid + 1, 0, 1)            # S2E_LOC_SIDE_ID -> (SideID, flip 0, master)
+    mesh = SimpleNamespace(nElems=1, nSides=6, nBCSides=0, firstInnerSide=1, lastInnerSide=6, firstMPISide_MINE=7,
+                           lastMPISide_MINE=6, firstMPISide_YOUR=7, lastMPISide_YOUR=6, ElemToSide=E2S)
+    maps = mp.build_mappings(N)
+    assert np.array_equal(maps["S2V2"], goldens["ued_S2V2"])
+    geo = dict(Metrics_fTilde=np.zeros((1, n, n, n, 3)), Metrics_gTilde=np.zeros((1, n, n, n, 3)),
+               Metrics_hTilde=np.zeros((1, n, n, n, 3)), sJ=np.ones((1, n, n, n)), NormVec=np.zeros((6, n, n, 3)),
+               TangVec1=np.zeros((6, n, n, 3)), TangVec2=np.zeros((6, n, n, 3)), SurfElem=np.ones((6, n, n)))
+    return SimpleNamespace(N=N, node_type=node_type, basis=b, mesh=mesh, geo=geo, maps=maps, eos=eq.Eos(),
+                           RefStatePrim=np.zeros((1, 6)), BCSides=np.zeros((0, 2), dtype=np.int32), split=-1, riemann=0,
+                           parabolic=False, timedisc=td.set_timedisc("carpenterrk4-5", N, node_type, 0.9, 0.9))
+
+
+@pytest.mark.parametrize("node_type,key", [("GAUSS", "p2f_G"), ("GAUSS-LOBATTO", "p2f_GL")])
+def test_prolong_to_face_unit_golden(goldens, node_type, key):
+    """unitTests/ProlongToFace.f90: random Uvol(0:9,0:9,0:9) replicated on PP_nVar -> Uface_master(1,:,:,1:6)."""
+    c = unit_element_case(goldens, node_type)
+    o = Oracle(c)
+    Uvol = np.repeat(goldens["p2f_Uvol"][None, ..., None], 5, axis=-1).copy()       # [e,k,j,i,v]
+    Um = np.zeros((6, 10, 10, 5))
+    Us = np.zeros((6, 10, 10, 5))
+    d = o.prec.d
+    o.prec.lib().dgo_prolong_to_face(o.h, 5, d(Uvol), d(Um), d(Us))
+    for v in range(5):
+        assert almost_equal_abs_or_rel(Um[..., v], goldens[key]), (node_type, v)
+    assert not Us.any()
+    o.close()
+
+
+@pytest.mark.parametrize("node_type,key", [("GAUSS", "si_G"), ("GAUSS-LOBATTO", "si_GL")])
+def test_surf_int_unit_golden(goldens, node_type, key):
+    """unitTests/SurfInt.f90: random Flux(0:9,0:9,1:6) as master and slave flux, Ut=0 before -> Ut(1,:,:,:,1)."""
+    c = unit_element_case(goldens, node_type)
+    o = Oracle(c)
+    F = np.repeat(goldens["si_Flux"][..., None], 5, axis=-1).copy()                 # [side,q,p,v]
+    Ut = np.zeros((1, 10, 10, 10, 5))
+    d = o.prec.d
+    o.prec.lib().dgo_surf_int(o.h, 5, d(F), d(F), d(Ut))
+    for v in range(5):
+        assert almost_equal_abs_or_rel(Ut[0, ..., v], goldens[key]), (node_type, v)
+    o.close()
+
+
+def test_cavity_reference_state_oracle():
+    """parabolic/cavity_3D: N=2 Gauss, NS + BR1, isothermal walls (4) + Dirichlet lid (2), 64 elements, t_end=1.
+    The restatement reproduces the reference's DG_Solution (FLEXI/GALAEXI binary output) to abs 1e-12."""
+    c, U0 = cases.cavity_case()
+    o = Oracle(c)
+    o.set_state(U0)
+    t, it = timeloop.advance(_Stepper(o), 0.0, 1.0)
+    ref = np.load(os.path.join(cases.GOLD, "cavity3d_state.npz"))["DG_Solution"]
+    assert it > 300
+    assert np.abs(o.array("U") - ref).max() <= 1.0e-12
+    o.close()
+
+
+class _Stepper:
+    """Adapter: oracle -> the (calc_timestep, rk_step) protocol of host.timeloop.advance."""
+
+    def __init__(self, o):
+        self.o = o
+
+    def calc_timestep(self):
+        return self.o.calc_timestep()
+
+    def rk_step(self, t, dt):
+        self.o.rk_step(t, dt)
+
+
+def test_tgv_split_csv_oracle():
+    """tgv/split: N=7 GL, PI split form, RoeEntropyFix, BR1, 8^3 elements. Row 1 (t=0) pins IC + lifted gradients +
+    quadrature (kinetic energy 0.125, dissipation rates); rows 2-3 pin dt (CalcTimeStep) and ten/twenty RK steps."""
+    c, U0 = cases.tgv_split_case()
+    rows = np.load(os.path.join(cases.GOLD, "tgv_split_csv.npz"))["rows"]
+    o = Oracle(c)
+    o.set_state(U0)
+    w = c.basis.wGP
+    W = w[:, None, None] * w[None, :, None] * w[None, None, :]
+    J = 1.0 / c.geo["sJ"]
+    vol = np.sum(W[None] * J)
+
+    def ekin():
+        U = o.array("U")
+        return np.sum(W[None] * J * 0.5 * (U[..., 1] ** 2 + U[..., 2] ** 2 + U[..., 3] ** 2) / U[..., 0]) / vol
+
+    assert abs(rows[0][0]) == 0.0
+    assert abs(ekin() - rows[0][4]) <= 1e-12 * rows[0][4]
+    # dissipation rate from the lifted gradients at t=0: eps = 2 mu/rho0 * <S:S> (testcase.f90:283-515, column 2: DR_S)
+    o.time_derivative(0.0)
+    gx, gy, gz = (o.array(nm) for nm in ("gradUx", "gradUy", "gradUz"))
+    G = np.stack([gx[..., 1:4], gy[..., 1:4], gz[..., 1:4]], axis=-1)               # G[..., i, j] = d u_i / d x_j
+    S = 0.5 * (G + np.swapaxes(G, -1, -2))
+    mu0, rho0 = c.eos.mu0, 1.0
+    dr_s = np.sum(W[None] * J * 2.0 * mu0 / rho0 * np.sum(S * S, axis=(-1, -2))) / vol
+    cols = [r for r in rows[0][1:8]]
+    assert min(abs(dr_s - x) / abs(x) for x in cols if x != 0.0) <= 1e-10, (dr_s, cols)
+    t = 0.0
+    for it in range(20):
+        dt = o.calc_timestep()[0]
+        o.rk_step(t, dt)
+        t += dt
+        if it in (9, 19):
+            r = rows[1 if it == 9 else 2]
+            assert abs(t - r[0]) <= 1e-12 * r[0]
+            assert abs(ekin() - r[4]) <= 1e-12 * r[4]
+    o.close()
+
+
+def test_oracle_freestream_and_conservation():
+    """Size-independent properties on a curved periodic mesh: constant state -> Ut = 0; sum_w J Ut = 0."""
+    c, U0 = cases.tgv_box_case(E=3, N=4, NGeo=2, deform=0.05, perturb=1e-3)
+    o = Oracle(c)
+    const = eq.ini_refstate(c.geo["Elem_xGP"], c.RefStatePrim[0], c.eos)
+    o.set_state(const)
+    Ut = o.time_derivative(0.0)
+    assert np.abs(Ut).max() <= 1e-9 * np.abs(const).max()
+    o.set_state(U0)
+    Ut = o.time_derivative(0.0).copy()
+    w = c.basis.wGP
+    W = (w[:, None, None] * w[None, :, None] * w[None, None, :])[None, ..., None] / c.geo["sJ"][..., None]
+    tot = np.sum(W * Ut, axis=(0, 1, 2, 3))
+    scale = np.sum(W * np.abs(Ut), axis=(0, 1, 2, 3)).max()
+    assert np.all(np.abs(tot) <= 1e-11 * scale)
+    o.close()
+
+
+def test_oracle_extended_precision_build_agrees():
+    """The 80-bit build of the same source differs from the FP64 build only by round-off."""
+    c, U0 = cases.tgv_box_case(E=2, N=3, NGeo=2, deform=0.05, perturb=1e-3)
+    o = Oracle(c)
+    x = Oracle(c, "extended")
+    o.set_state(U0)
+    x.set_state(U0)
+    a = o.time_derivative(0.0)
+    b = np.asarray(x.time_derivative(0.0), dtype=np.float64)
+    assert cases.rel_l2(a, b) <= 1e-10
+    o.close()
+    x.close()

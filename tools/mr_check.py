@@ -1,0 +1,96 @@
+#!/usr/bin/env python
+"""Multi-rank parity check (run under torchrun, one rank per GPU):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/mr_check.py [case]
+
+Every rank builds its slice of the SFC-partitioned mesh (the reference's decomposition), runs the RHS and two
+RK steps through the C ABI with NCCL face halos; rank 0 gathers the slices and compares with the single-rank CPU
+oracle on the whole mesh (criterion: Ut rel-L2 <= 1e-12, U after the steps rel-L2 <= 1e-10 -- the reference's own
+MPI=1 vs MPI=2 invariance, regressioncheck parabolic/cavity_3D) and with the bit pattern of a 1-rank GPU run."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    import cases
+    from galaexi_b200 import dg
+    name = sys.argv[1] if len(sys.argv) > 1 else "tgv"
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ids = [dg.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+
+    def build(nProcs, myRank):
+        if name == "tgv":
+            return cases.tgv_box_case(E=4, N=5, NGeo=2, deform=0.05, perturb=0.0, nProcs=nProcs, myRank=myRank)
+        if name == "cavity":
+            return cases.cavity_case(nProcs=nProcs, myRank=myRank)
+        if name == "channel":
+            return cases.channel_case(E=4, N=4, nProcs=nProcs, myRank=myRank)
+        if name == "shu":
+            return cases.shu_vortex_case(E=4, N=3, nProcs=nProcs, myRank=myRank)
+        if name == "naca":
+            return cases.naca_case(N=3, nProcs=nProcs, myRank=myRank)
+        raise SystemExit(f"unknown case {name}")
+
+    c, U0 = build(world, rank)
+    s = dg.DGSolver(c, device=local, nccl_id=ids[0])
+    s.set_state(U0)
+    s.DGTimeDerivative_weakForm(0.0)
+    Ut = s.get_ut()
+    dt, err = s.CalcTimeStep()
+    assert err == 0
+    t = 0.0
+    for _ in range(2):
+        s.TimeStepByLSERKW2(t, dt)
+        t += dt
+    U = s.get_state()
+    s.sync()
+    outs = [None] * world
+    dist.gather_object((c.mesh.offsetElem, Ut, U, dt), outs if rank == 0 else None, dst=0)
+    res = None
+    if rank == 0:
+        outs.sort(key=lambda x: x[0])
+        Ut_all = np.concatenate([o[1] for o in outs])
+        U_all = np.concatenate([o[2] for o in outs])
+        assert all(o[3] == outs[0][3] for o in outs), "dt differs between ranks"
+        from oracle.oracle import Oracle
+        c1, U01 = build(1, 0)
+        o = Oracle(c1)
+        o.set_state(U01)
+        Ut_ref = o.time_derivative(0.0).copy()
+        dt_ref = o.calc_timestep()[0]
+        t = 0.0
+        for _ in range(2):
+            o.rk_step(t, dt_ref)
+            t += dt_ref
+        U_ref = o.array("U")
+        # single-rank GPU run for the bitwise comparison
+        s1 = dg.DGSolver(c1, device=local)
+        s1.set_state(U01)
+        s1.DGTimeDerivative_weakForm(0.0)
+        Ut1 = s1.get_ut()
+        res = dict(case=name, world=world, ut_rel_l2=cases.rel_l2(Ut_all, Ut_ref), u_rel_l2=cases.rel_l2(U_all, U_ref),
+                   dt_rel=abs(outs[0][3] - dt_ref) / dt_ref, ut_vs_1gpu_maxabs=float(np.abs(Ut_all - Ut1).max()),
+                   ut_scale=float(np.abs(Ut_ref).max()))
+        s1.FinalizeDG()
+        print("MRCHECK " + json.dumps(res), flush=True)
+    s.FinalizeDG()
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        ok = res["u_rel_l2"] <= 1e-10 and res["dt_rel"] <= 1e-13 and res["ut_vs_1gpu_maxabs"] <= 1e-11 * res["ut_scale"]
+        sys.exit(0 if ok else 3)
+
+
+if __name__ == "__main__":
+    main()

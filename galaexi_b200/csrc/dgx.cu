@@ -95,6 +95,7 @@ Nccl g_nccl;
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------
+struct HaloMsg { int peer, isSend, slaveArray, side0, nSides; };
 struct dgx_handle {
     dgx_config cfg;  // scalar copies only; pointers are not retained
     int n, n2, n3;
@@ -121,6 +122,7 @@ struct dgx_handle {
     std::vector<double> RKA, RKb, RKc;
     // MPI-like neighbour tables
     std::vector<int> NbProc, nMine, nYour, offMine, offYour;
+    std::vector<HaloMsg> plan;
     ncclComm_t comm = nullptr;
     size_t nDOF() const { return (size_t)cfg.nElems * n3; }
     size_t nFace() const { return (size_t)cfg.nSides * n2; }
@@ -175,21 +177,29 @@ int check_launch(dgx_handle* h, const char* what) {
 }
 
 // ---- halo exchange: both directions for every MPI side range -----------------------------------------
+// The message plan is a pure function of the neighbour tables so that it can be executed (and tested) with any
+// point-to-point layer that, like NCCL, matches the messages between one pair of ranks in issue order.
+void halo_plan(const std::vector<int>& NbProc, const std::vector<int>& nMine, const std::vector<int>& nYour,
+               const std::vector<int>& offMine, const std::vector<int>& offYour, std::vector<HaloMsg>& plan) {
+    plan.clear();
+    for (size_t ib = 0; ib < NbProc.size(); ib++) {
+        const int peer = NbProc[ib];
+        // Both ranks send their MINE range first and their YOUR range second, so the first message arriving from
+        // the peer is ITS MINE range (= my YOUR range, master data), the second its YOUR range (= my MINE range).
+        if (nMine[ib]) plan.push_back({peer, 1, 0, offMine[ib], nMine[ib]});  // I am master: my master data
+        if (nYour[ib]) plan.push_back({peer, 1, 1, offYour[ib], nYour[ib]});  // I am slave: my slave data
+        if (nYour[ib]) plan.push_back({peer, 0, 0, offYour[ib], nYour[ib]});  // the neighbour's master data
+        if (nMine[ib]) plan.push_back({peer, 0, 1, offMine[ib], nMine[ib]});  // the neighbour's slave data
+    }
+}
+
 int exchange(dgx_handle* h, double* am, double* as, int nvar) {
     const size_t per = (size_t)nvar * h->n2;
     NK(g_nccl.GroupStart());
-    for (size_t ib = 0; ib < h->NbProc.size(); ib++) {
-        const int peer = h->NbProc[ib];
-        const size_t m0 = (size_t)h->offMine[ib] * per, mc = (size_t)h->nMine[ib] * per;
-        const size_t y0 = (size_t)h->offYour[ib] * per, yc = (size_t)h->nYour[ib] * per;
-        if (mc) {  // I am master: send my master data, receive the neighbour's slave data
-            NK(g_nccl.Send(am + m0, mc, ncclFloat64, peer, h->comm, h->cs));
-            NK(g_nccl.Recv(as + m0, mc, ncclFloat64, peer, h->comm, h->cs));
-        }
-        if (yc) {  // I am slave: send my slave data, receive the neighbour's master data
-            NK(g_nccl.Send(as + y0, yc, ncclFloat64, peer, h->comm, h->cs));
-            NK(g_nccl.Recv(am + y0, yc, ncclFloat64, peer, h->comm, h->cs));
-        }
+    for (const HaloMsg& m : h->plan) {
+        double* p = (m.slaveArray ? as : am) + (size_t)m.side0 * per;
+        if (m.isSend) NK(g_nccl.Send(p, (size_t)m.nSides * per, ncclFloat64, m.peer, h->comm, h->cs));
+        else NK(g_nccl.Recv(p, (size_t)m.nSides * per, ncclFloat64, m.peer, h->comm, h->cs));
     }
     NK(g_nccl.GroupEnd());
     return 0;
@@ -281,6 +291,19 @@ extern "C" {
 const char* dgx_last_error(const dgx_handle* h) { return h ? h->err.c_str() : "null handle"; }
 long long dgx_launch_count(const dgx_handle* h) { return h ? h->launches : 0; }
 unsigned long dgx_sizeof_config(void) { return (unsigned long)sizeof(dgx_config); }
+
+int dgx_halo_plan(int nNbProcs, const int* NbProc, const int* nMine, const int* nYour, const int* offMine, const int* offYour,
+                  int cap, int* out) {
+    std::vector<int> nb(NbProc, NbProc + nNbProcs), m(nMine, nMine + nNbProcs), y(nYour, nYour + nNbProcs), om(offMine, offMine + nNbProcs),
+        oy(offYour, offYour + nNbProcs);
+    std::vector<HaloMsg> plan;
+    halo_plan(nb, m, y, om, oy, plan);
+    for (size_t i = 0; i < plan.size() && (int)i < cap; i++) {
+        out[5 * i + 0] = plan[i].peer; out[5 * i + 1] = plan[i].isSend; out[5 * i + 2] = plan[i].slaveArray;
+        out[5 * i + 3] = plan[i].side0; out[5 * i + 4] = plan[i].nSides;
+    }
+    return (int)plan.size();
+}
 
 int dgx_nccl_unique_id(char* out128) {
     std::string err;
@@ -407,6 +430,7 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
             h->offMine.push_back(c.offsetMPISides_MINE[ib]);
             h->offYour.push_back(c.offsetMPISides_YOUR[ib]);
         }
+        halo_plan(h->NbProc, h->nMine, h->nYour, h->offMine, h->offYour, h->plan);
         // element lists: elements touching an MPI side vs the rest
         std::vector<int> inner, bnd;
         for (int e = 0; e < c.nElems; e++) {

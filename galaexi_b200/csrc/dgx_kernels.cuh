@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(n* n* n) k_prolong(const KParams P) {
 // ---------------------------------------------------------------------------------------------------------
 // BR1 lifting (strong form, non-conservative volume integral): gradU = sJ * ( M . D U + sum_faces F n Lhat )
 template <int n, int NT>
-__global__ void __launch_bounds__(n* n* n) k_lifting(const KParams P) {
+__global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting(const KParams P) {
     constexpr int n2 = n * n, n3 = n2 * n;
     extern __shared__ double smem[];
     double* sT = smem;                 // [4][n3] lifting variables; later aliased by the gradient tile [12][n3]

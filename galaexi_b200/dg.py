@@ -28,7 +28,7 @@ _ip = C.POINTER(C.c_int)
 
 EXPORTS = ("dgx_create", "dgx_destroy", "dgx_last_error", "dgx_set_state", "dgx_get_state", "dgx_get_ut",
            "dgx_get_gradients", "dgx_time_derivative", "dgx_rk_stage", "dgx_rk_step", "dgx_calc_timestep",
-           "dgx_sync", "dgx_run_steps", "dgx_profile_stage", "dgx_nccl_unique_id", "dgx_launch_count", "dgx_sizeof_config")
+           "dgx_sync", "dgx_run_steps", "dgx_profile_stage", "dgx_nccl_unique_id", "dgx_launch_count", "dgx_sizeof_config", "dgx_halo_plan")
 
 
 class DgxConfig(C.Structure):
@@ -86,6 +86,21 @@ def load_library():
         raise RuntimeError(f"struct dgx_config mismatch: library {lib.dgx_sizeof_config()} B, binding {C.sizeof(DgxConfig)} B")
     _lib = lib
     return lib
+
+
+def halo_plan(mesh):
+    """The message plan one exchange phase executes (list of (peer, isSend, slaveArray, firstSide0, nSides))."""
+    lib = load_library()
+    if not mesh.nNbProcs:
+        return []
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    tabs = [i32(mesh.NbProc), i32(mesh.nMPISides_MINE_Proc), i32(mesh.nMPISides_YOUR_Proc), i32(mesh.offsetMPISides_MINE),
+            i32(mesh.offsetMPISides_YOUR)]
+    cap = 4 * mesh.nNbProcs
+    out = np.zeros((cap, 5), dtype=np.int32)
+    lib.dgx_halo_plan.argtypes = [C.c_int] + [_ip] * 5 + [C.c_int, _ip]
+    cnt = lib.dgx_halo_plan(mesh.nNbProcs, *[t.ctypes.data_as(_ip) for t in tabs], cap, out.ctypes.data_as(_ip))
+    return [tuple(int(x) for x in r) for r in out[:cnt]]
 
 
 def nccl_unique_id() -> bytes:

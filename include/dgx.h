@@ -105,6 +105,11 @@ int dgx_run_steps(dgx_handle *h, int nSteps, double t, double dt, int adaptive_d
 /* per-kernel CUDA-event timing of one RK stage: names[i] -> ms[i], *count entries (<= cap) */
 int dgx_profile_stage(dgx_handle *h, double t, double dt, int cap, const char **names, float *ms, int *count);
 int dgx_nccl_unique_id(char *out128);
+/* The face-halo message plan the library executes with NCCL for one exchange phase (no GPU needed): writes up to
+ * cap records {peer, isSend, slaveArray, firstSide (0-based), nSides} in issue order, returns the number of messages.
+ * Replaces the loop bodies of StartReceiveMPIData/StartSendMPIData (mpi/mpi.f90:277-387). */
+int dgx_halo_plan(int nNbProcs, const int *NbProc, const int *nMPISides_MINE_Proc, const int *nMPISides_YOUR_Proc,
+                  const int *offsetMPISides_MINE, const int *offsetMPISides_YOUR, int cap, int *out);
 long long dgx_launch_count(const dgx_handle *h);
 /* sizeof(dgx_config) as compiled: lets a foreign-language binding verify its struct mirror */
 unsigned long dgx_sizeof_config(void);

@@ -596,7 +596,7 @@ static void eval_transformed_flux(int euler, int visc, const double *U, const do
 
 /* ------------------------------------------------------------------------------------------------ */
 /* lifting: dg/lifting/lifting_br1.t90:47-167 (strong form, non-conservative volume integral) */
-static void lifting_br1(dgo *s)
+static void lifting_br1_fillflux(dgo *s)
 {
     const dgo_config *c = &s->c;
     const int n = s->n;
@@ -632,7 +632,14 @@ static void lifting_br1(dgo *s)
                 Flux[IDX_FACE(s, NL, v, p, q, sd)] = 0.5 * se * (-1. * s->UPrim_master[IDX_FACE(s, NP, PRIM_LIFT[v], p, q, sd)]
                                                                  + s->UPrim_slave[IDX_FACE(s, NP, PRIM_LIFT[v], p, q, sd)]);
         }
-    /* (MPI) flux on YOUR sides arrives from the master rank: single-rank oracle has none. */
+}
+
+/* (MPI) between the two parts the lifting flux on YOUR sides arrives from the master rank, lifting_br1.t90:93-112 */
+static void lifting_br1_finish(dgo *s)
+{
+    const dgo_config *c = &s->c;
+    const int n = s->n;
+    double *Flux = s->gradUz_slave;
     /* lifting_fillflux.t90:212-256 Lifting_FillFlux_NormVec */
 #pragma omp parallel for schedule(static)
     for (int sd = 0; sd < c->nSides; sd++)
@@ -675,6 +682,8 @@ static void lifting_br1(dgo *s)
     prolong_to_face(s, NL, s->gradUy, s->gradUy_master, s->gradUy_slave);
     prolong_to_face(s, NL, s->gradUz, s->gradUz_master, s->gradUz_slave);
 }
+
+static void lifting_br1(dgo *s) { lifting_br1_fillflux(s); lifting_br1_finish(s); }
 
 /* ------------------------------------------------------------------------------------------------ */
 /* dg/applydmatrix.t90:19-75 ApplyDMatrix_Kernel */
@@ -861,6 +870,60 @@ int dgo_time_derivative(dgo *s, double t)
         for (int v = 0; v < NV; v++) s->Ut[NV * d + v] = s->Ut[NV * d + v] * c->sJ[d];
     }
     return err;
+}
+
+/* The same routine cut at the reference's four halo phases (dg.f90:290-300 U_slave YOUR->MINE; lifting_br1.t90:93-112
+ * lifting flux MINE->YOUR; lifting_br1.t90:158-165 / dg.f90:352-366 gradU*_slave YOUR->MINE; dg.f90:392-401 Flux_slave
+ * MINE->YOUR). A multi-rank test driver calls phase 0..4 and performs the exchange named after each phase with any
+ * message layer; calling the five phases back to back on one rank equals dgo_time_derivative. */
+int dgo_rhs_phase(dgo *s, int phase)
+{
+    const dgo_config *c = &s->c;
+    const double kappa = c->EOS[EOS_KAPPA], R = c->EOS[EOS_R];
+    int err = 0;
+    switch (phase) {
+    case 0:
+        prolong_to_face(s, NV, s->U, s->U_master, s->U_slave);
+#pragma omp parallel for schedule(static)
+        for (size_t d = 0; d < s->nDOF; d++) cons_to_prim(&s->UPrim[NP * d], &s->U[NV * d], kappa, R);
+        break; /* -> exchange U_slave, YOUR -> MINE */
+    case 1:
+#pragma omp parallel for schedule(static)
+        for (size_t d = 0; d < s->nFace; d++) {
+            cons_to_prim(&s->UPrim_master[NP * d], &s->U_master[NV * d], kappa, R);
+            cons_to_prim(&s->UPrim_slave[NP * d], &s->U_slave[NV * d], kappa, R);
+        }
+        if (c->parabolic) lifting_br1_fillflux(s);
+        break; /* -> exchange lifting flux (buffer gradUz_slave), MINE -> YOUR */
+    case 2:
+        if (c->parabolic) lifting_br1_finish(s);
+        break; /* -> exchange gradUx/y/z_slave, YOUR -> MINE */
+    case 3:
+        vol_int(s);
+        err = fill_flux(s);
+        break; /* -> exchange Flux_slave, MINE -> YOUR */
+    case 4:
+        surf_int(s, NV, s->Flux_master, s->Flux_slave, s->Ut, 0, 0, 0);
+#pragma omp parallel for schedule(static)
+        for (size_t d = 0; d < s->nDOF; d++) {
+            for (int v = 0; v < NV; v++) s->Ut[NV * d + v] = s->Ut[NV * d + v] * (-1.);
+            for (int v = 0; v < NV; v++) s->Ut[NV * d + v] = s->Ut[NV * d + v] * c->sJ[d];
+        }
+        break;
+    default: err = 4;
+    }
+    return err;
+}
+
+/* vector.f90:163-183 VAXPB_OUT_VAXPB_IN alone (the stage update after an externally driven RHS) */
+void dgo_rk_update(dgo *s, double mRKA, double b_dt)
+{
+    size_t nTot = NV * s->nDOF;
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < nTot; i++) {
+        s->Ut_tmp[i] = s->Ut_tmp[i] * mRKA + s->Ut[i];
+        s->U[i] = s->U[i] + s->Ut_tmp[i] * b_dt;
+    }
 }
 
 /* timedisc/timestep.f90:49-120 one stage of TimeStepByLSERKW2 + globals/vector.f90:163-183 VAXPB_OUT_VAXPB_IN */

@@ -61,6 +61,8 @@ class _Prec:
             L.dgo_prolong_to_face.argtypes = [C.c_void_p, C.c_int, rp, rp, rp]
             L.dgo_surf_int.argtypes = [C.c_void_p, C.c_int, rp, rp, rp]
             L.dgo_lifting.argtypes = [C.c_void_p]
+            L.dgo_rhs_phase.argtypes = [C.c_void_p, C.c_int]
+            L.dgo_rk_update.argtypes = [C.c_void_p, r, r]
             L.dgo_sizeof_config.restype = C.c_size_t
             assert L.dgo_sizeof_config() == C.sizeof(self.Config)
             self._lib = L
@@ -161,6 +163,14 @@ class Oracle:
         if err:
             raise RuntimeError("oracle: unsupported boundary condition type")
         return self.array("Ut")
+
+    def rhs_phase(self, phase: int):
+        """One of the five pieces of DGTimeDerivative_weakForm between the reference's halo exchanges."""
+        if self.prec.lib().dgo_rhs_phase(self.h, int(phase)):
+            raise RuntimeError("oracle: unsupported boundary condition type")
+
+    def rk_update(self, mRKA: float, b_dt: float):
+        self.prec.lib().dgo_rk_update(self.h, float(mRKA), float(b_dt))
 
     def rk_step(self, t: float, dt: float):
         td = self.case.timedisc

@@ -33,7 +33,9 @@ def main():
         if name == "tgv":
             return cases.tgv_box_case(E=4, N=5, NGeo=2, deform=0.05, perturb=0.0, nProcs=nProcs, myRank=myRank)
         if name == "cavity":
-            return cases.cavity_case(nProcs=nProcs, myRank=myRank)
+            c, U0 = cases.cavity_case(nProcs=nProcs, myRank=myRank)
+            x = c.geo["Elem_xGP"]  # the reference IC is a constant state: perturb it (same function on every rank)
+            return c, U0 * (1.0 + 0.01 * np.sin(5.0 * x[..., 0] + 1.0) * np.cos(3.0 * x[..., 1]) * np.sin(4.0 * x[..., 2] + 0.5))[..., None]
         if name == "channel":
             return cases.channel_case(E=4, N=4, nProcs=nProcs, myRank=myRank)
         if name == "shu":

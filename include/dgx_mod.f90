@@ -1,0 +1,99 @@
+!==================================================================================================================================
+! ISO_C_BINDING interface to libdgx.so (include/dgx.h): the module a GALAEXI maintainer adds under src/dg/ to route the hot path
+! (DGTimeDerivative_weakForm + TimeStepByLSERKW2 + CalcTimeStep) through the B200-native library.
+! Shipped as source: it cannot be compiled in the build container (no Fortran compiler); field order and kinds mirror
+! `struct dgx_config` one to one (tests/test_abi.py checks the C side against the ctypes mirror with dgx_sizeof_config()).
+!==================================================================================================================================
+MODULE MOD_DGX
+USE ISO_C_BINDING
+IMPLICIT NONE
+PRIVATE
+
+TYPE, BIND(C), PUBLIC :: dgx_config
+  INTEGER(C_INT) :: N, nodeType, splitDG, riemann, parabolic, viscLaw
+  INTEGER(C_INT) :: nElems, nSides, nBCSides
+  INTEGER(C_INT) :: firstInnerSide, lastInnerSide
+  INTEGER(C_INT) :: firstMPISide_MINE, lastMPISide_MINE, firstMPISide_YOUR, lastMPISide_YOUR
+  REAL(C_DOUBLE) :: EOS_Vars(8)
+  INTEGER(C_INT) :: nRefState
+  TYPE(C_PTR)    :: RefStatePrim, BCSides
+  TYPE(C_PTR)    :: D_T, D_Hat_T, DVolSurf, L_Minus, L_Plus, L_HatMinus, L_HatPlus
+  TYPE(C_PTR)    :: ElemToSide, S2V2, S2V2_inv
+  TYPE(C_PTR)    :: Metrics_fTilde, Metrics_gTilde, Metrics_hTilde, sJ
+  TYPE(C_PTR)    :: NormVec, TangVec1, TangVec2, SurfElem
+  INTEGER(C_INT) :: nRKStages
+  TYPE(C_PTR)    :: RKA, RKb, RKc
+  REAL(C_DOUBLE) :: CFLScale, DFLScale
+  INTEGER(C_INT) :: myRank, nRanks, nNbProcs
+  TYPE(C_PTR)    :: NbProc, nMPISides_MINE_Proc, nMPISides_YOUR_Proc, offsetMPISides_MINE, offsetMPISides_YOUR
+  TYPE(C_PTR)    :: ncclUniqueId
+  INTEGER(C_INT) :: device
+END TYPE dgx_config
+
+TYPE(C_PTR), PUBLIC, SAVE :: dgx = C_NULL_PTR   !< the library handle (one per rank)
+
+INTERFACE
+  INTEGER(C_INT) FUNCTION dgx_create(h,cfg) BIND(C,NAME='dgx_create')
+    IMPORT; TYPE(C_PTR),INTENT(OUT) :: h; TYPE(dgx_config),INTENT(IN) :: cfg
+  END FUNCTION
+  SUBROUTINE dgx_destroy(h) BIND(C,NAME='dgx_destroy')
+    IMPORT; TYPE(C_PTR),VALUE :: h
+  END SUBROUTINE
+  TYPE(C_PTR) FUNCTION dgx_last_error(h) BIND(C,NAME='dgx_last_error')
+    IMPORT; TYPE(C_PTR),VALUE :: h
+  END FUNCTION
+  INTEGER(C_INT) FUNCTION dgx_set_state(h,U) BIND(C,NAME='dgx_set_state')
+    IMPORT; TYPE(C_PTR),VALUE :: h; REAL(C_DOUBLE),INTENT(IN) :: U(*)
+  END FUNCTION
+  INTEGER(C_INT) FUNCTION dgx_get_state(h,U) BIND(C,NAME='dgx_get_state')
+    IMPORT; TYPE(C_PTR),VALUE :: h; REAL(C_DOUBLE),INTENT(OUT) :: U(*)
+  END FUNCTION
+  INTEGER(C_INT) FUNCTION dgx_get_ut(h,Ut) BIND(C,NAME='dgx_get_ut')
+    IMPORT; TYPE(C_PTR),VALUE :: h; REAL(C_DOUBLE),INTENT(OUT) :: Ut(*)
+  END FUNCTION
+  INTEGER(C_INT) FUNCTION dgx_get_gradients(h,gx,gy,gz) BIND(C,NAME='dgx_get_gradients')
+    IMPORT; TYPE(C_PTR),VALUE :: h; REAL(C_DOUBLE),INTENT(OUT) :: gx(*),gy(*),gz(*)
+  END FUNCTION
+  INTEGER(C_INT) FUNCTION dgx_time_derivative(h,t) BIND(C,NAME='dgx_time_derivative')
+    IMPORT; TYPE(C_PTR),VALUE :: h; REAL(C_DOUBLE),VALUE :: t
+  END FUNCTION
+  INTEGER(C_INT) FUNCTION dgx_rk_stage(h,iStage,t,dt) BIND(C,NAME='dgx_rk_stage')
+    IMPORT; TYPE(C_PTR),VALUE :: h; INTEGER(C_INT),VALUE :: iStage; REAL(C_DOUBLE),VALUE :: t,dt
+  END FUNCTION
+  INTEGER(C_INT) FUNCTION dgx_rk_step(h,t,dt) BIND(C,NAME='dgx_rk_step')
+    IMPORT; TYPE(C_PTR),VALUE :: h; REAL(C_DOUBLE),VALUE :: t,dt
+  END FUNCTION
+  INTEGER(C_INT) FUNCTION dgx_calc_timestep(h,dt,errType) BIND(C,NAME='dgx_calc_timestep')
+    IMPORT; TYPE(C_PTR),VALUE :: h; REAL(C_DOUBLE),INTENT(OUT) :: dt; INTEGER(C_INT),INTENT(OUT) :: errType
+  END FUNCTION
+  INTEGER(C_INT) FUNCTION dgx_nccl_unique_id(id) BIND(C,NAME='dgx_nccl_unique_id')
+    IMPORT; CHARACTER(KIND=C_CHAR),INTENT(OUT) :: id(128)
+  END FUNCTION
+END INTERFACE
+
+PUBLIC :: dgx_create,dgx_destroy,dgx_last_error,dgx_set_state,dgx_get_state,dgx_get_ut,dgx_get_gradients
+PUBLIC :: dgx_time_derivative,dgx_rk_stage,dgx_rk_step,dgx_calc_timestep,dgx_nccl_unique_id
+PUBLIC :: DGX_Check
+
+CONTAINS
+
+!> non-zero return code -> CALL Abort(__STAMP__,message), the reference's error path (globals/globals.f90:175-221)
+SUBROUTINE DGX_Check(rc,stamp_file,stamp_line)
+USE MOD_Globals, ONLY: Abort
+INTEGER(C_INT),INTENT(IN)   :: rc
+CHARACTER(LEN=*),INTENT(IN) :: stamp_file
+INTEGER,INTENT(IN)          :: stamp_line
+CHARACTER(KIND=C_CHAR),POINTER :: msg(:)
+CHARACTER(LEN=512)          :: text
+INTEGER                     :: i
+IF(rc.EQ.0) RETURN
+CALL C_F_POINTER(dgx_last_error(dgx),msg,[512])
+text=''
+DO i=1,512
+  IF(msg(i).EQ.C_NULL_CHAR) EXIT
+  text(i:i)=msg(i)
+END DO
+CALL Abort(stamp_file,stamp_line,'',TRIM(text))
+END SUBROUTINE DGX_Check
+
+END MODULE MOD_DGX

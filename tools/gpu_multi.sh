@@ -7,5 +7,6 @@ for c in tgv cavity channel shu naca; do
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/mr_check.py $c > $OUT/mr_${c}_$TAG.log 2>&1
   echo "$c exit $?"; grep MRCHECK $OUT/mr_${c}_$TAG.log || tail -15 $OUT/mr_${c}_$TAG.log
 done
+timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $OUT/bench_n1_$TAG.json 2> $OUT/bench_n1_$TAG.err; cat $OUT/bench_n1_$TAG.json
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 20 --warmup 3 > $OUT/bench_n${N}_$TAG.json 2> $OUT/bench_n${N}_$TAG.err
 echo "bench exit $?"; cat $OUT/bench_n${N}_$TAG.json; tail -5 $OUT/bench_n${N}_$TAG.err

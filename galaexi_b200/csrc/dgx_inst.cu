@@ -1,5 +1,7 @@
 // Kernel instantiations for one polynomial degree (compile with -DDGX_N=<N>); see dgx_kernels.cuh.
 #include "dgx_launch.h"
+#include "dgx_volsurf2.cuh"
+#include <stdlib.h>
 #ifndef DGX_N
 #error "compile with -DDGX_N=<polynomial degree>"
 #endif
@@ -17,13 +19,32 @@ struct L {
         e = cudaFuncSetAttribute(k_volsurf<n, NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)volsurf_smem_bytes<n>());
         if (e != cudaSuccess) return (int)e;
         e = cudaFuncSetAttribute(k_volsurf<n, NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)volsurf_smem_bytes<n>());
+        if (e != cudaSuccess) return (int)e;
+        if (NT == 2) {
+            e = cudaFuncSetAttribute(k_volsurf2<n, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vs2_smem_bytes<n>());
+            if (e != cudaSuccess) return (int)e;
+            e = cudaFuncSetAttribute(k_volsurf2<n, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vs2_smem_bytes<n>());
+            if (e != cudaSuccess) return (int)e;
+            e = cudaFuncSetAttribute(k_volsurf2<n, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            if (e != cudaSuccess) return (int)e;
+            e = cudaFuncSetAttribute(k_volsurf2<n, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        }
         return (int)e;
     }
     static void prolong(const KParams& P, int nb, cudaStream_t s) {
         if (nb > 0) k_prolong<n, NT><<<nb, n3, 0, s>>>(P);
     }
     static void lifting(const KParams& P, int nb, cudaStream_t s) {
-        if (nb > 0) k_lifting<n, NT><<<nb, n3, lifting_smem_bytes<n>(), s>>>(P);
+        if (nb <= 0) return;
+        static int resident = 0;
+        if (!resident) {
+            int dev = 0, sms = 148, per = 1;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_lifting<n, NT>, n3, lifting_smem_bytes<n>());
+            resident = sms * (per > 0 ? per : 1);
+        }
+        k_lifting<n, NT><<<nb, n3, lifting_smem_bytes<n>(), s>>>(P, resident);
     }
     static void sideflux(const KParams& P, int side0, int nS, cudaStream_t s) {
         if (nS <= 0) return;
@@ -32,6 +53,14 @@ struct L {
     }
     static void volsurf(const KParams& P, int mode, double mRKA, double b_dt, int nb, cudaStream_t s) {
         if (nb <= 0) return;
+        // split form on Gauss-Lobatto nodes: register-blocked kernel (DGX_VOLSURF=1 selects the thread-per-node one)
+        static const bool v1 = getenv("DGX_VOLSURF") && atoi(getenv("DGX_VOLSURF")) == 1;
+        if (NT == 2 && P.splitDG >= 0 && !v1) {
+            const int grid = (nb + vs2_epb<n>() - 1) / vs2_epb<n>();
+            if (mode == 0) k_volsurf2<n, 0><<<grid, vs2_threads<n>(), vs2_smem_bytes<n>(), s>>>(P, nb, mRKA, b_dt);
+            else k_volsurf2<n, 1><<<grid, vs2_threads<n>(), vs2_smem_bytes<n>(), s>>>(P, nb, mRKA, b_dt);
+            return;
+        }
         if (mode == 0) k_volsurf<n, NT, 0><<<nb, n3, volsurf_smem_bytes<n>(), s>>>(P, mRKA, b_dt);
         else k_volsurf<n, NT, 1><<<nb, n3, volsurf_smem_bytes<n>(), s>>>(P, mRKA, b_dt);
     }

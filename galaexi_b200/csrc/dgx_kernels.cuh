@@ -61,6 +61,13 @@ struct KParams {
 
 enum { ZETA_MINUS = 1, ETA_MINUS = 2, XI_PLUS = 3, ETA_PLUS = 4, XI_MINUS = 5, ZETA_PLUS = 6 };
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// prefetch `bytes` contiguous bytes (128-byte lines) cooperatively with `nthr` threads
+__device__ __forceinline__ void prefetch_block(const void* base, size_t bytes, int tid, int nthr) {
+    const char* p = reinterpret_cast<const char*>(base);
+    for (size_t off = (size_t)tid * 128; off < bytes; off += (size_t)nthr * 128) prefetch_l2(p + off);
+}
+
 template <int n>
 __device__ __forceinline__ int s2v2(const int* __restrict__ tab, int c, int p, int q, int flip, int loc) {
     return __ldg(&tab[c + 2 * (p + n * (q + n * (flip + 5 * (loc - 1))))]);
@@ -133,7 +140,7 @@ __global__ void __launch_bounds__(n* n* n) k_prolong(const KParams P) {
 // ---------------------------------------------------------------------------------------------------------
 // BR1 lifting (strong form, non-conservative volume integral): gradU = sJ * ( M . D U + sum_faces F n Lhat )
 template <int n, int NT>
-__global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting(const KParams P) {
+__global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting(const KParams P, int lookahead) {
     constexpr int n2 = n * n, n3 = n2 * n;
     extern __shared__ double smem[];
     double* sT = smem;                 // [4][n3] lifting variables; later aliased by the gradient tile [12][n3]
@@ -150,7 +157,6 @@ __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting
     if (t < n) { sLhm[t] = P.L_HatMinus[t]; sLhp[t] = P.L_HatPlus[t]; sLm[t] = P.L_Minus[t]; sLp[t] = P.L_Plus[t]; }
     const Eos eos = P.eos;
     const int* e2s = P.E2S + 18 * e;
-
     // 1. node: primitive lifting variables into the tile
     {
         const double* U = P.U + (size_t)e * 5 * n3;

@@ -1,0 +1,372 @@
+// k_volsurf2: split-form (Gauss-Lobatto) volume + surface integral + Jacobian + RK stage, register-blocked.
+//
+// Same operator as k_volsurf (dgx_kernels.cuh; reference: dg/volint.f90:60-119 + :211-353, dg/surfint.t90:352-586,
+// globals/vector.f90:163-226, interpolation/applyjacobian.t90:196, interpolation/prolongtoface.t90:168-344), different
+// work decomposition, chosen from the ncu profile of k_volsurf (profiles/r01a_volsurf_full.md: shared-memory
+// wavefronts and a single 512-thread CTA per SM were the limiters):
+//   * 2*n^2 threads per element instead of n^3. In the three flux-differencing sweeps a thread owns HALF A LINE
+//     (SEG = ceil(n/2) output nodes, held in registers with their accumulators): pairs inside the own segment are
+//     evaluated once (the two-point flux is symmetric), the other half of the line streams through registers.
+//     Shared-memory loads per node drop from 24*9 to about 2*9 per direction.
+//   * In the point-wise phases the same thread owns the nodes (i,j,k in its half of the zeta column), so global
+//     accesses stay coalesced and the zeta sweep accumulates directly into the registers of the epilogue.
+//   * 15 tile slots of shared memory per element (12 viscous fluxes + M_xi, later Ut partials + node record + one
+//     metric triple) -> 3 CTAs per SM at N=7, which overlaps the load / sweep / store phases of different elements.
+//   * Shared-memory tile layout for n=8: (i xor k) + 8 j + 72 k, conflict-free for 64-bit accesses of all three
+//     line directions with the lane mappings used below.
+//   * Gauss-Lobatto only (split DG requires it, splitflux.f90:116-119): surface integral and next-stage face
+//     extraction touch only the boundary layer of nodes and go directly to global memory.
+#pragma once
+#include "dgx_kernels.cuh"
+
+namespace dgx {
+
+template <int n>
+struct Tile {
+    static constexpr bool swz = (n == 8);
+    static constexpr int RS = n;
+    static constexpr int PS = swz ? 72 : n * n;
+    static constexpr int SLOT = swz ? 576 : n * n * n;
+    __device__ __forceinline__ static int idx(int i, int j, int k) { return swz ? ((i ^ k) + RS * j + PS * k) : (i + RS * j + PS * k); }
+};
+
+template <int n>
+constexpr int vs2_epb() { return (128 + n * n) / (2 * n * n) > 0 ? (128 + n * n) / (2 * n * n) : 1; }
+template <int n>
+constexpr int vs2_threads() { return vs2_epb<n>() * 2 * n * n; }
+constexpr int VS2_SLOTS = 15;
+template <int n>
+constexpr size_t vs2_smem_bytes() { return sizeof(double) * (size_t)vs2_epb<n>() * VS2_SLOTS * Tile<n>::SLOT; }
+
+// tile index of position l on the line (c1,c2) of direction d (0 xi: (j,k), 1 eta: (i,k), 2 zeta: (i,j)); d is a run-time
+// value on purpose: one copy of the sweep code serves the three directions (the fully unrolled variant was
+// instruction-cache bound, profiles/r01e_volsurf2_full.md)
+template <int n>
+__device__ __forceinline__ int line_idx(int d, int l, int c1, int c2) {
+    const int i = (d == 0) ? l : c1;
+    const int j = (d == 0) ? c1 : ((d == 1) ? l : c2);
+    const int k = (d == 2) ? l : c2;
+    return Tile<n>::idx(i, j, k);
+}
+
+// One flux-differencing sweep of direction d for the half line (c1,c2,h): acc[m][v] = sum_l DVolSurf(l,a_m) F#(a_m,l)
+template <int n>
+__device__ __forceinline__ void vs2_sweep(const double* __restrict__ R, const double* __restrict__ Mx, const double* __restrict__ Dv, int d,
+                                          int c1, int c2, int h, int var, double (&acc)[(n + 1) / 2][5]) {
+    constexpr int SEG = (n + 1) / 2, SL = Tile<n>::SLOT;
+    const int a0 = h * SEG, cnt = h ? n - SEG : SEG;
+    const int f0 = h ? 0 : SEG, fcnt = n - cnt;
+    double own[SEG][9];
+#pragma unroll
+    for (int m = 0; m < SEG; m++) {
+        const int id = line_idx<n>(d, m < cnt ? a0 + m : a0, c1, c2);
+#pragma unroll
+        for (int v = 0; v < 6; v++) own[m][v] = R[v * SL + id];
+#pragma unroll
+        for (int c = 0; c < 3; c++) own[m][6 + c] = Mx[c * SL + id];
+#pragma unroll
+        for (int v = 0; v < 5; v++) acc[m][v] = 0.0;
+    }
+    // pairs inside the own segment: evaluated once, used for both end points
+#pragma unroll
+    for (int m = 0; m < SEG; m++) {
+        if (m < cnt) {
+            double Ms[3], F[5];
+#pragma unroll
+            for (int c = 0; c < 3; c++) Ms[c] = own[m][6 + c] + own[m][6 + c];
+            split_volume_flux(var, own[m], own[m], Ms, F);
+            const double w = Dv[(a0 + m) + n * (a0 + m)];
+#pragma unroll
+            for (int v = 0; v < 5; v++) acc[m][v] += w * F[v];
+#pragma unroll
+            for (int m2 = m + 1; m2 < SEG; m2++) {
+                if (m2 < cnt) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) Ms[c] = own[m][6 + c] + own[m2][6 + c];
+                    split_volume_flux(var, own[m], own[m2], Ms, F);
+                    const double w1 = Dv[(a0 + m2) + n * (a0 + m)], w2 = Dv[(a0 + m) + n * (a0 + m2)];
+#pragma unroll
+                    for (int v = 0; v < 5; v++) { acc[m][v] += w1 * F[v]; acc[m2][v] += w2 * F[v]; }
+                }
+            }
+        }
+    }
+    // pairs with the other half of the line (rolled loop: code size)
+#pragma unroll 1
+    for (int mf = 0; mf < fcnt; mf++) {
+        const int b = f0 + mf;
+        const int id = line_idx<n>(d, b, c1, c2);
+        double ot[9];
+#pragma unroll
+        for (int v = 0; v < 6; v++) ot[v] = R[v * SL + id];
+#pragma unroll
+        for (int c = 0; c < 3; c++) ot[6 + c] = Mx[c * SL + id];
+#pragma unroll
+        for (int m = 0; m < SEG; m++) {
+            if (m < cnt) {
+                double Ms[3], F[5];
+#pragma unroll
+                for (int c = 0; c < 3; c++) Ms[c] = own[m][6 + c] + ot[6 + c];
+                split_volume_flux(var, own[m], ot, Ms, F);
+                const double w = Dv[b + n * (a0 + m)];
+#pragma unroll
+                for (int v = 0; v < 5; v++) acc[m][v] += w * F[v];
+            }
+        }
+    }
+}
+
+template <int n, int MODE>
+__global__ void __launch_bounds__(vs2_threads<n>(), (n >= 8 ? 3 : 2)) k_volsurf2(const __grid_constant__ KParams P, int nWork, double mRKA, double b_dt) {
+    constexpr int n2 = n * n, n3 = n2 * n, SEG = (n + 1) / 2, SL = Tile<n>::SLOT, T = 2 * n2, EPB = vs2_epb<n>();
+    extern __shared__ double smem[];
+    const int le = threadIdx.x / T, tid = threadIdx.x - le * T;
+    const int we = blockIdx.x * EPB + le;
+    const bool live = we < nWork;
+    const int e = live ? (P.elemList ? P.elemList[we] : we) : 0;
+    double* S = smem + (size_t)le * VS2_SLOTS * SL;
+    const int h = tid / n2, q = tid - h * n2;
+    const int c1 = q % n, c2 = q / n;          // point-wise phases: (i,j) = (c1,c2), k in the own half of the zeta column
+    const int a0 = h * SEG, cnt = h ? n - SEG : SEG;
+    const Eos eos = P.eos;
+    const bool par = P.parabolic != 0;
+    const int var = P.splitDG;
+    const double* __restrict__ Dh = P.D_Hat_T;
+    const double* __restrict__ Dv = P.DVolSurf;
+    const double* __restrict__ gU_e = P.U + (size_t)e * 5 * n3;
+    const double* __restrict__ gM_e = P.metrics + (size_t)e * 9 * n3;
+
+    // ---- P0: point-wise. All global reads of the phase are issued before the first use (one DRAM round trip per CTA
+    // instead of one per node): lifted gradients by 8-byte cp.async straight into slots 0..11 at the thread's own nodes
+    // (no registers held), state and metrics into registers. The viscous fluxes then overwrite the gradients in place.
+    double Rec[SEG][6];
+    if (live) {
+        if (par) {
+            const double* gU = P.gradU + (size_t)e * 12 * n3;
+#pragma unroll
+            for (int m = 0; m < SEG; m++) {
+                if (m < cnt) {
+                    const int node = c1 + n * c2 + n2 * (a0 + m);
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(S + Tile<n>::idx(c1, c2, a0 + m));
+#pragma unroll
+                    for (int x = 0; x < 12; x++)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (unsigned)(x * SL * 8)), "l"(gU + x * n3 + node) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        double Uc[SEG][5], M[SEG][9];
+#pragma unroll
+        for (int m = 0; m < SEG; m++) {
+            const int node = c1 + n * c2 + n2 * (m < cnt ? a0 + m : a0);
+#pragma unroll
+            for (int v = 0; v < 5; v++) Uc[m][v] = gU_e[v * n3 + node];
+            if (par) {
+#pragma unroll
+                for (int x = 0; x < 9; x++) M[m][x] = gM_e[x * n3 + node];
+            }
+        }
+        if (par) asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+        for (int m = 0; m < SEG; m++) {
+            if (m < cnt) {
+                const int id = Tile<n>::idx(c1, c2, a0 + m);
+                double Pr[6];
+                cons_to_prim(Pr, Uc[m], eos);
+                Rec[m][0] = Pr[DENS]; Rec[m][1] = Pr[VEL1]; Rec[m][2] = Pr[VEL2]; Rec[m][3] = Pr[VEL3]; Rec[m][4] = Pr[PRES];
+                Rec[m][5] = split_sixth(var, Uc[m], Pr);
+                if (par) {
+                    double gr[12];
+#pragma unroll
+                    for (int x = 0; x < 12; x++) gr[x] = S[x * SL + id];
+                    const double mu = viscosity(eos, Pr[TEMP]);
+                    Tau ta;
+                    stress(ta, Pr, gr, mu, conductivity(eos, mu));
+                    double v4[4];
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        visc_flux_dir(ta, M[m] + 3 * d, v4);
+#pragma unroll
+                        for (int v = 0; v < 4; v++) S[(4 * d + v) * SL + id] = v4[v];
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- P1: D_Hat sweep of the viscous fluxes (applydmatrix.t90:60-67), zeta column register-blocked
+    double UtV[SEG][4];
+#pragma unroll
+    for (int m = 0; m < SEG; m++)
+#pragma unroll
+        for (int v = 0; v < 4; v++) UtV[m][v] = 0.0;
+    if (par && live) {
+#pragma unroll 2
+        for (int l = 0; l < n; l++) {
+            const int idz = Tile<n>::idx(c1, c2, l);
+            double hz[4];
+#pragma unroll
+            for (int v = 0; v < 4; v++) hz[v] = S[(8 + v) * SL + idz];
+            const double dx = Dh[l + n * c1], dy = Dh[l + n * c2];
+#pragma unroll
+            for (int m = 0; m < SEG; m++) {
+                if (m < cnt) {
+                    const int k = a0 + m;
+                    const double dz = Dh[l + n * k];
+                    const int idx_ = Tile<n>::idx(l, c2, k), idy = Tile<n>::idx(c1, l, k);
+#pragma unroll
+                    for (int v = 0; v < 4; v++) UtV[m][v] += dx * S[v * SL + idx_] + dz * hz[v] + dy * S[(4 + v) * SL + idy];
+                }
+            }
+        }
+    }
+    __syncthreads();  // viscous fluxes consumed: slots 0..11 are free
+    // ---- P2: Ut partials -> slots 0..3 (momentum, energy) and 10 (density); node record -> slots 4..9
+    if (live) {
+#pragma unroll
+        for (int m = 0; m < SEG; m++) {
+            if (m < cnt) {
+                const int id = Tile<n>::idx(c1, c2, a0 + m);
+#pragma unroll
+                for (int v = 0; v < 4; v++) S[v * SL + id] = UtV[m][v];
+                S[10 * SL + id] = 0.0;
+#pragma unroll
+                for (int v = 0; v < 6; v++) S[(4 + v) * SL + id] = Rec[m][v];
+            }
+        }
+    }
+    // ---- P3: the three flux-differencing sweeps (volint.f90:306-347)
+#pragma unroll 1
+    for (int d = 0; d < 3; d++) {
+        __syncthreads();  // d=0: node record complete; d>0: previous metric triple consumed, previous partials stored
+        if (live) {
+#pragma unroll
+            for (int m = 0; m < SEG; m++) {
+                if (m < cnt) {
+                    const int k = a0 + m;
+                    const double* Mg = gM_e + (c1 + n * c2 + n2 * k) + (size_t)(3 * d) * n3;
+                    const int id = Tile<n>::idx(c1, c2, k);
+#pragma unroll
+                    for (int c = 0; c < 3; c++) S[(12 + c) * SL + id] = Mg[c * n3];
+                }
+            }
+        }
+        __syncthreads();
+        if (live) {
+            // lane -> line mapping: xi lines take (j,k) = (q/n, q%n), eta (i,k) and zeta (i,j) = (q%n, q/n): conflict-free
+            const int l1 = (d == 0) ? c2 : c1, l2 = (d == 0) ? c1 : c2;
+            double acc[SEG][5];
+            vs2_sweep<n>(S + 4 * SL, S + 12 * SL, Dv, d, l1, l2, h, var, acc);
+#pragma unroll
+            for (int m = 0; m < SEG; m++) {
+                if (m < cnt) {
+                    const int id = line_idx<n>(d, a0 + m, l1, l2);
+                    S[10 * SL + id] += acc[m][0];
+#pragma unroll
+                    for (int v = 0; v < 4; v++) S[v * SL + id] += acc[m][1 + v];
+                }
+            }
+        }
+    }
+    // ---- P4: surface integral (surfint.t90:519-573; GL: only the boundary layer). One face node per thread and round;
+    // the two faces of a round (-/+ side of one axis) touch disjoint nodes. All global reads of P4 and P5 (face fluxes,
+    // sJ, Ut_tmp, U) are issued here, before the first barrier of the rounds: one DRAM round trip for the rest of the CTA.
+    const int* e2s = P.E2S + 18 * e;
+    double Ff[3][5], wf[3];
+    int idf[3];
+    double sJv[SEG], Uo[SEG][5], Uto[SEG][5];
+    if (live) {
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const int loc = (r == 0) ? (h ? XI_PLUS : XI_MINUS) : ((r == 1) ? (h ? ETA_PLUS : ETA_MINUS) : (h ? ZETA_PLUS : ZETA_MINUS));
+            const int qq = q / n, p = q - qq * n;
+            const int side = __ldg(&e2s[0 + 3 * (loc - 1)]) - 1;
+            const int flip = __ldg(&e2s[1 + 3 * (loc - 1)]);
+            const int a = s2v2<n>(P.S2V2, 0, p, qq, flip, loc);
+            const int b = s2v2<n>(P.S2V2, 1, p, qq, flip, loc);
+            const int l = h ? n - 1 : 0;
+            idf[r] = (r == 0) ? Tile<n>::idx(l, a, b) : ((r == 1) ? Tile<n>::idx(a, l, b) : Tile<n>::idx(a, b, l));
+            wf[r] = ((flip == 0) ? 1.0 : -1.0) * (h ? P.L_HatPlus[n - 1] : P.L_HatMinus[0]);
+            const double* F = P.Flux + (size_t)side * 5 * n2 + q;
+#pragma unroll
+            for (int v = 0; v < 5; v++) Ff[r][v] = F[v * n2];
+        }
+#pragma unroll
+        for (int m = 0; m < SEG; m++) {
+            const int node = c1 + n * c2 + n2 * (m < cnt ? a0 + m : a0);
+            sJv[m] = P.sJ[(size_t)e * n3 + node];
+            if (MODE == 1) {
+#pragma unroll
+                for (int v = 0; v < 5; v++) { Uo[m][v] = gU_e[v * n3 + node]; Uto[m][v] = P.Ut_tmp[(size_t)e * 5 * n3 + v * n3 + node]; }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        __syncthreads();
+        if (live) {
+            S[10 * SL + idf[r]] += Ff[r][0] * wf[r];
+#pragma unroll
+            for (int v = 0; v < 4; v++) S[v * SL + idf[r]] += Ff[r][1 + v] * wf[r];
+        }
+    }
+    __syncthreads();  // Ut complete in slots 10, 0..3; node record consumed: slots 4..8 take the updated state
+    // ---- P5: -sJ (dg.f90:413,423) and the Williamson 2N update (vector.f90:163-183)
+    if (live) {
+#pragma unroll
+        for (int m = 0; m < SEG; m++) {
+            if (m < cnt) {
+                const int k = a0 + m;
+                const int node = c1 + n * c2 + n2 * k;
+                const int id = Tile<n>::idx(c1, c2, k);
+                const double msJ = -sJv[m];
+                double Ut[5];
+                Ut[0] = S[10 * SL + id] * msJ;
+#pragma unroll
+                for (int v = 0; v < 4; v++) Ut[1 + v] = S[v * SL + id] * msJ;
+                if (MODE == 0) {
+                    double* o = P.Ut + (size_t)e * 5 * n3 + node;
+#pragma unroll
+                    for (int v = 0; v < 5; v++) o[v * n3] = Ut[v];
+                } else {
+                    double* ot = P.Ut_tmp + (size_t)e * 5 * n3 + node;
+                    double* ou = P.U + (size_t)e * 5 * n3 + node;
+#pragma unroll
+                    for (int v = 0; v < 5; v++) {
+                        const double r = (mRKA == 0.0) ? Ut[v] : Uto[m][v] * mRKA + Ut[v];
+                        ot[v * n3] = r;
+                        const double un = Uo[m][v] + r * b_dt;
+                        ou[v * n3] = un;
+                        S[(4 + v) * SL + id] = un;
+                    }
+                }
+            }
+        }
+    }
+    if (MODE == 1) {
+        __syncthreads();
+        // next-stage face states (GL: copy of the boundary layer), side-local orientation, coalesced in (p,q)
+        if (live) {
+#pragma unroll 1
+            for (int f = tid; f < 6 * n2; f += T) {
+                const int loc = f / n2 + 1;
+                const int pq = f - (loc - 1) * n2;
+                const int qq = pq / n, p = pq - qq * n;
+                const int side = __ldg(&e2s[0 + 3 * (loc - 1)]) - 1;
+                const int flip = __ldg(&e2s[1 + 3 * (loc - 1)]);
+                const int a = s2v2<n>(P.S2V2, 0, p, qq, flip, loc);
+                const int b = s2v2<n>(P.S2V2, 1, p, qq, flip, loc);
+                const int l = is_minus(loc) ? 0 : n - 1;
+                int id;
+                if (loc == XI_MINUS || loc == XI_PLUS) id = Tile<n>::idx(l, a, b);
+                else if (loc == ETA_MINUS || loc == ETA_PLUS) id = Tile<n>::idx(a, l, b);
+                else id = Tile<n>::idx(a, b, l);
+                double* dst = (flip == 0 ? P.UmNext : P.UsNext) + (size_t)side * 5 * n2 + pq;
+#pragma unroll
+                for (int v = 0; v < 5; v++) dst[v * n2] = S[(4 + v) * SL + id];
+            }
+        }
+    }
+}
+
+}  // namespace dgx

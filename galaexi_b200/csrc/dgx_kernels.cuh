@@ -281,7 +281,7 @@ constexpr size_t lifting_smem_bytes() { return sizeof(double) * (12 * n * n * n 
 // ---------------------------------------------------------------------------------------------------------
 // Numerical flux on a range of sides [side0, side0+nS): BC flux or Riemann + 1/2(Fv_L+Fv_R).n, times SurfElem
 template <int n>
-__global__ void __launch_bounds__(128) k_sideflux(const KParams P, int side0, int nS) {
+__global__ void __launch_bounds__(128, 4) k_sideflux(const KParams P, int side0, int nS) {
     constexpr int n2 = n * n;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= nS * n2) return;

@@ -23,18 +23,22 @@ namespace dgx {
 
 template <int n>
 struct Tile {
+    // n == 8: bank-conflict-free 64-bit accesses for lines of all three directions WITHOUT padding. Position inside a
+    // 16-double row pair = (i + 8 (j&1)) xor (k + 8 (k&1)); 8-byte bank (of 16 per half warp) = (i^k) + 8 ((j^k)&1).
+    // Lane mappings that make a half warp hit 16 distinct banks: point-wise / zeta / eta lines: first coordinate fast;
+    // xi lines: k fast, two adjacent j.
     static constexpr bool swz = (n == 8);
-    static constexpr int RS = n;
-    static constexpr int PS = swz ? 72 : n * n;
-    static constexpr int SLOT = swz ? 576 : n * n * n;
-    __device__ __forceinline__ static int idx(int i, int j, int k) { return swz ? ((i ^ k) + RS * j + PS * k) : (i + RS * j + PS * k); }
+    static constexpr int SLOT = n * n * n;
+    __device__ __forceinline__ static int idx(int i, int j, int k) {
+        return swz ? (((i + 8 * (j & 1)) ^ (k + 8 * (k & 1))) + 16 * (j >> 1) + 64 * k) : (i + n * j + n * n * k);
+    }
 };
 
 template <int n>
 constexpr int vs2_epb() { return (128 + n * n) / (2 * n * n) > 0 ? (128 + n * n) / (2 * n * n) : 1; }
 template <int n>
 constexpr int vs2_threads() { return vs2_epb<n>() * 2 * n * n; }
-constexpr int VS2_SLOTS = 15;
+constexpr int VS2_SLOTS = 18;
 template <int n>
 constexpr size_t vs2_smem_bytes() { return sizeof(double) * (size_t)vs2_epb<n>() * VS2_SLOTS * Tile<n>::SLOT; }
 
@@ -116,6 +120,17 @@ __device__ __forceinline__ void vs2_sweep(const double* __restrict__ R, const do
     }
 }
 
+// Side-local node (p,q) handled by lane x of a face: the assignment is transposed when needed so that the tile
+// coordinate that must vary fastest over the lanes (b for xi faces, a otherwise) does -- conflict-free tile access.
+template <int n>
+__device__ __forceinline__ void face_lane(const int* __restrict__ S2V2, int x, int flip, int loc, int& p, int& qq) {
+    const bool a_on_p = s2v2<n>(S2V2, 0, 1, 0, flip, loc) != s2v2<n>(S2V2, 0, 0, 0, flip, loc);
+    const bool want_b_fast = (loc == XI_MINUS || loc == XI_PLUS);
+    const bool tr = (a_on_p == want_b_fast);
+    p = tr ? x / n : x % n;
+    qq = tr ? x % n : x / n;
+}
+
 template <int n, int MODE>
 __global__ void __launch_bounds__(vs2_threads<n>(), (n >= 8 ? 3 : 2)) k_volsurf2(const __grid_constant__ KParams P, int nWork, double mRKA, double b_dt) {
     constexpr int n2 = n * n, n3 = n2 * n, SEG = (n + 1) / 2, SL = Tile<n>::SLOT, T = 2 * n2, EPB = vs2_epb<n>();
@@ -161,10 +176,8 @@ __global__ void __launch_bounds__(vs2_threads<n>(), (n >= 8 ? 3 : 2)) k_volsurf2
             const int node = c1 + n * c2 + n2 * (m < cnt ? a0 + m : a0);
 #pragma unroll
             for (int v = 0; v < 5; v++) Uc[m][v] = gU_e[v * n3 + node];
-            if (par) {
 #pragma unroll
-                for (int x = 0; x < 9; x++) M[m][x] = gM_e[x * n3 + node];
-            }
+            for (int x = 0; x < 9; x++) M[m][x] = gM_e[x * n3 + node];
         }
         if (par) asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
@@ -175,6 +188,8 @@ __global__ void __launch_bounds__(vs2_threads<n>(), (n >= 8 ? 3 : 2)) k_volsurf2
                 cons_to_prim(Pr, Uc[m], eos);
                 Rec[m][0] = Pr[DENS]; Rec[m][1] = Pr[VEL1]; Rec[m][2] = Pr[VEL2]; Rec[m][3] = Pr[VEL3]; Rec[m][4] = Pr[PRES];
                 Rec[m][5] = split_sixth(var, Uc[m], Pr);
+#pragma unroll
+                for (int c = 0; c < 6; c++) S[(12 + c) * SL + id] = M[m][c];  // M_xi -> slots 12..14, M_eta -> 15..17
                 if (par) {
                     double gr[12];
 #pragma unroll
@@ -235,28 +250,30 @@ __global__ void __launch_bounds__(vs2_threads<n>(), (n >= 8 ? 3 : 2)) k_volsurf2
             }
         }
     }
-    // ---- P3: the three flux-differencing sweeps (volint.f90:306-347)
+    // ---- P3: the three flux-differencing sweeps (volint.f90:306-347). Metric triples: xi in slots 12..14 and eta in
+    // 15..17 (from P0); zeta is copied by cp.async into 12..14 while the eta sweep runs.
 #pragma unroll 1
     for (int d = 0; d < 3; d++) {
-        __syncthreads();  // d=0: node record complete; d>0: previous metric triple consumed, previous partials stored
+        if (d == 2) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();  // node record / previous partials / metric triple visible, previous triple consumed
         if (live) {
+            if (d == 1) {
 #pragma unroll
-            for (int m = 0; m < SEG; m++) {
-                if (m < cnt) {
-                    const int k = a0 + m;
-                    const double* Mg = gM_e + (c1 + n * c2 + n2 * k) + (size_t)(3 * d) * n3;
-                    const int id = Tile<n>::idx(c1, c2, k);
+                for (int m = 0; m < SEG; m++) {
+                    if (m < cnt) {
+                        const double* Mg = gM_e + (c1 + n * c2 + n2 * (a0 + m)) + (size_t)6 * n3;
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(S + 12 * SL + Tile<n>::idx(c1, c2, a0 + m));
 #pragma unroll
-                    for (int c = 0; c < 3; c++) S[(12 + c) * SL + id] = Mg[c * n3];
+                        for (int c = 0; c < 3; c++)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (unsigned)(c * SL * 8)), "l"(Mg + c * n3) : "memory");
+                    }
                 }
+                asm volatile("cp.async.commit_group;" ::: "memory");
             }
-        }
-        __syncthreads();
-        if (live) {
             // lane -> line mapping: xi lines take (j,k) = (q/n, q%n), eta (i,k) and zeta (i,j) = (q%n, q/n): conflict-free
             const int l1 = (d == 0) ? c2 : c1, l2 = (d == 0) ? c1 : c2;
             double acc[SEG][5];
-            vs2_sweep<n>(S + 4 * SL, S + 12 * SL, Dv, d, l1, l2, h, var, acc);
+            vs2_sweep<n>(S + 4 * SL, S + (d == 1 ? 15 : 12) * SL, Dv, d, l1, l2, h, var, acc);
 #pragma unroll
             for (int m = 0; m < SEG; m++) {
                 if (m < cnt) {
@@ -279,15 +296,16 @@ __global__ void __launch_bounds__(vs2_threads<n>(), (n >= 8 ? 3 : 2)) k_volsurf2
 #pragma unroll
         for (int r = 0; r < 3; r++) {
             const int loc = (r == 0) ? (h ? XI_PLUS : XI_MINUS) : ((r == 1) ? (h ? ETA_PLUS : ETA_MINUS) : (h ? ZETA_PLUS : ZETA_MINUS));
-            const int qq = q / n, p = q - qq * n;
             const int side = __ldg(&e2s[0 + 3 * (loc - 1)]) - 1;
             const int flip = __ldg(&e2s[1 + 3 * (loc - 1)]);
+            int p, qq;
+            face_lane<n>(P.S2V2, q, flip, loc, p, qq);
             const int a = s2v2<n>(P.S2V2, 0, p, qq, flip, loc);
             const int b = s2v2<n>(P.S2V2, 1, p, qq, flip, loc);
             const int l = h ? n - 1 : 0;
             idf[r] = (r == 0) ? Tile<n>::idx(l, a, b) : ((r == 1) ? Tile<n>::idx(a, l, b) : Tile<n>::idx(a, b, l));
             wf[r] = ((flip == 0) ? 1.0 : -1.0) * (h ? P.L_HatPlus[n - 1] : P.L_HatMinus[0]);
-            const double* F = P.Flux + (size_t)side * 5 * n2 + q;
+            const double* F = P.Flux + (size_t)side * 5 * n2 + (p + n * qq);
 #pragma unroll
             for (int v = 0; v < 5; v++) Ff[r][v] = F[v * n2];
         }
@@ -350,10 +368,11 @@ __global__ void __launch_bounds__(vs2_threads<n>(), (n >= 8 ? 3 : 2)) k_volsurf2
 #pragma unroll 1
             for (int f = tid; f < 6 * n2; f += T) {
                 const int loc = f / n2 + 1;
-                const int pq = f - (loc - 1) * n2;
-                const int qq = pq / n, p = pq - qq * n;
                 const int side = __ldg(&e2s[0 + 3 * (loc - 1)]) - 1;
                 const int flip = __ldg(&e2s[1 + 3 * (loc - 1)]);
+                int p, qq;
+                face_lane<n>(P.S2V2, f - (loc - 1) * n2, flip, loc, p, qq);
+                const int pq = p + n * qq;
                 const int a = s2v2<n>(P.S2V2, 0, p, qq, flip, loc);
                 const int b = s2v2<n>(P.S2V2, 1, p, qq, flip, loc);
                 const int l = is_minus(loc) ? 0 : n - 1;

@@ -277,7 +277,7 @@ def main():
     n = N_POLY + 1
     vs_ms = prof.get("volsurf_rk", float("nan"))
     ach = b_alg_volsurf(n) * ndof_local / (vs_ms * 1e-3) / 1e9
-    roofline = dict(bound="hbm", kernel="k_volsurf<8,GL,RK>", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak,
+    roofline = dict(bound="hbm", kernel="k_volsurf2<8,RK>", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak,
                     traffic=None, peak_source=peak_src, algorithmic_bytes_per_dof=b_alg_volsurf(n), ms_per_launch=vs_ms,
                     kernel_ms_per_stage=prof,
                     stage=dict(algorithmic_bytes_per_dof=b_alg_stage(n), achieved=b_alg_stage(n) / pid / 1e9,

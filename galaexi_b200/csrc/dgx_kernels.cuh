@@ -121,6 +121,67 @@ __device__ __forceinline__ void extract_faces(const double* __restrict__ tile, d
     }
 }
 
+// Shared-memory element tile layout [slot][n^3].
+template <int n>
+struct Tile {
+    // n == 8: bank-conflict-free 64-bit accesses for lines of all three directions WITHOUT padding. Position inside a
+    // 16-double row pair = (i + 8 (j&1)) xor (k + 8 (k&1)); 8-byte bank (of 16 per half warp) = (i^k) + 8 ((j^k)&1).
+    // Lane mappings that make a half warp hit 16 distinct banks: point-wise / zeta / eta lines: first coordinate fast;
+    // xi lines: k fast, two adjacent j.
+    static constexpr bool swz = (n == 8);
+    static constexpr int SLOT = n * n * n;
+    __device__ __forceinline__ static int idx(int i, int j, int k) {
+        return swz ? (((i + 8 * (j & 1)) ^ (k + 8 * (k & 1))) + 16 * (j >> 1) + 64 * k) : (i + n * j + n * n * k);
+    }
+};
+
+// Side-local node (p,q) handled by lane x of a face: the assignment is transposed when needed so that the wanted tile
+// coordinate (b if b_fast, else a; (a,b) = S2V2(p,q)) varies fastest over the lanes -- conflict-free tile access.
+template <int n>
+__device__ __forceinline__ void face_lane(const int* __restrict__ S2V2, int x, int flip, int loc, bool b_fast, int& p, int& qq) {
+    const bool a_on_p = s2v2<n>(S2V2, 0, 1, 0, flip, loc) != s2v2<n>(S2V2, 0, 0, 0, flip, loc);
+    const bool tr = (a_on_p == b_fast);
+    p = tr ? x / n : x % n;
+    qq = tr ? x % n : x / n;
+}
+
+// extract_faces for a tile in Tile<n> layout, with conflict-free lane assignment (see face_lane)
+template <int n, int NT, int NVAR>
+__device__ __forceinline__ void extract_faces_tile(const double* __restrict__ tile, double* __restrict__ dstM, double* __restrict__ dstS,
+                                                   const int* __restrict__ e2s, const int* __restrict__ S2V2, const double* __restrict__ sLm,
+                                                   const double* __restrict__ sLp) {
+    constexpr int n2 = n * n, SL = Tile<n>::SLOT;
+    for (int f = threadIdx.x; f < 6 * n2; f += blockDim.x) {
+        const int loc = f / n2 + 1;
+        const int side = __ldg(&e2s[0 + 3 * (loc - 1)]) - 1;
+        const int flip = __ldg(&e2s[1 + 3 * (loc - 1)]);
+        const bool xi = (loc == XI_MINUS || loc == XI_PLUS), eta = (loc == ETA_MINUS || loc == ETA_PLUS);
+        int p, q;
+        face_lane<n>(S2V2, f - (loc - 1) * n2, flip, loc, xi, p, q);
+        const int a = s2v2<n>(S2V2, 0, p, q, flip, loc);
+        const int b = s2v2<n>(S2V2, 1, p, q, flip, loc);
+        double* dst = (flip == 0 ? dstM : dstS) + (size_t)side * NVAR * n2 + (p + n * q);
+        if (NT == 2) {
+            const int l = is_minus(loc) ? 0 : n - 1;
+            const int id = xi ? Tile<n>::idx(l, a, b) : (eta ? Tile<n>::idx(a, l, b) : Tile<n>::idx(a, b, l));
+#pragma unroll
+            for (int v = 0; v < NVAR; v++) dst[v * n2] = tile[v * SL + id];
+        } else {
+            const double* L = is_minus(loc) ? sLm : sLp;
+#pragma unroll
+            for (int v = 0; v < NVAR; v++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int l = 0; l < n; l++) {
+                    const int id = xi ? Tile<n>::idx(l, a, b) : (eta ? Tile<n>::idx(a, l, b) : Tile<n>::idx(a, b, l));
+                    acc = (l == 0) ? tile[v * SL + id] * L[0] : acc + tile[v * SL + id] * L[l];
+                }
+                dst[v * n2] = acc;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 template <int n, int NT>
 __global__ void __launch_bounds__(n* n* n) k_prolong(const KParams P) {
@@ -147,16 +208,20 @@ __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting
     double* sG = smem;                 // alias (used after the sweeps are done)
     double* sF = smem + 12 * n3;       // [6][7][n2] face lifting flux (4) + normal (3), element face order
     double* sD = sF + 6 * 7 * n2;      // D_T [n*n]
-    double* sLhm = sD + n * n;
+    double* sDx = sD + n * n;          // D_T transposed
+    double* sLhm = sDx + n * n;
     double* sLhp = sLhm + n;
     double* sLm = sLhp + n;
     double* sLp = sLm + n;
     const int e = P.elemList ? P.elemList[blockIdx.x] : blockIdx.x;
     const int t = threadIdx.x;
-    for (int x = t; x < n * n; x += n3) sD[x] = P.D_T[x];
+    for (int x = t; x < n * n; x += n3) { sD[x] = P.D_T[x]; sDx[(x / n) + n * (x % n)] = P.D_T[x]; }
     if (t < n) { sLhm[t] = P.L_HatMinus[t]; sLhp[t] = P.L_HatPlus[t]; sLm[t] = P.L_Minus[t]; sLp[t] = P.L_Plus[t]; }
     const Eos eos = P.eos;
     const int* e2s = P.E2S + 18 * e;
+    const int k = t / n2, j = (t - k * n2) / n, i = t - k * n2 - j * n;
+    const int tid_ = Tile<n>::idx(i, j, k);
+    (void)lookahead;
     // 1. node: primitive lifting variables into the tile
     {
         const double* U = P.U + (size_t)e * 5 * n3;
@@ -164,18 +229,19 @@ __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting
 #pragma unroll
         for (int v = 0; v < 5; v++) Uc[v] = U[v * n3 + t];
         cons_to_prim(Pr, Uc, eos);
-        sT[0 * n3 + t] = Pr[VEL1];
-        sT[1 * n3 + t] = Pr[VEL2];
-        sT[2 * n3 + t] = Pr[VEL3];
-        sT[3 * n3 + t] = Pr[TEMP];
+        sT[0 * n3 + tid_] = Pr[VEL1];
+        sT[1 * n3 + tid_] = Pr[VEL2];
+        sT[2 * n3 + tid_] = Pr[VEL3];
+        sT[3 * n3 + tid_] = Pr[TEMP];
     }
     // 2. faces: lifting flux F = 1/2 (U_s - U_m) SurfElem in side orientation -> stored in element face order
     for (int f = t; f < 6 * n2; f += n3) {
         const int loc = f / n2 + 1;
-        const int pq = f - (loc - 1) * n2;
-        const int q = pq / n, p = pq - q * n;
         const int side = __ldg(&e2s[0 + 3 * (loc - 1)]) - 1;
         const int flip = __ldg(&e2s[1 + 3 * (loc - 1)]);
+        int p, q;
+        face_lane<n>(P.S2V2, f - (loc - 1) * n2, flip, loc, false, p, q);  // a fastest: contiguous writes to sF
+        const int pq = p + n * q;
         const int a = s2v2<n>(P.S2V2, 0, p, q, flip, loc);
         const int b = s2v2<n>(P.S2V2, 1, p, q, flip, loc);
         const double* g = P.geo + (size_t)side * 10 * n2 + pq;
@@ -215,18 +281,18 @@ __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting
     }
     __syncthreads();
     // 3. node: volume derivative + surface lifting, Jacobian
-    const int k = t / n2, j = (t - k * n2) / n, i = t - k * n2 - j * n;
     double G[12];
     {
         double gxi[4] = {0, 0, 0, 0}, get[4] = {0, 0, 0, 0}, gze[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int l = 0; l < n; l++) {
-            const double dx = sD[l + n * i], dy = sD[l + n * j], dz = sD[l + n * k];
+            const double dx = sDx[i + n * l], dy = sD[l + n * j], dz = sD[l + n * k];  // sDx: transposed copy, conflict-free over i
+            const int ix = Tile<n>::idx(l, j, k), iy = Tile<n>::idx(i, l, k), iz = Tile<n>::idx(i, j, l);
 #pragma unroll
             for (int v = 0; v < 4; v++) {
-                gxi[v] += dx * sT[v * n3 + l + n * (j + n * k)];
-                get[v] += dy * sT[v * n3 + i + n * (l + n * k)];
-                gze[v] += dz * sT[v * n3 + i + n * (j + n * l)];
+                gxi[v] += dx * sT[v * n3 + ix];
+                get[v] += dy * sT[v * n3 + iy];
+                gze[v] += dz * sT[v * n3 + iz];
             }
         }
         const double* M = P.metrics + (size_t)e * 9 * n3 + t;
@@ -269,14 +335,14 @@ __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting
     __syncthreads();  // all reads of sT done before it is overwritten by the gradient tile
     double* gU = P.gradU + (size_t)e * 12 * n3 + t;
 #pragma unroll
-    for (int x = 0; x < 12; x++) { gU[x * n3] = G[x]; sG[x * n3 + t] = G[x]; }
+    for (int x = 0; x < 12; x++) { gU[x * n3] = G[x]; sG[x * n3 + tid_] = G[x]; }
     __syncthreads();
     // 4. gradients on the faces (ProlongToFaceLifting)
-    extract_faces<n, NT, 12>(sG, P.gm, P.gs, e2s, P.S2V2, sLm, sLp);
+    extract_faces_tile<n, NT, 12>(sG, P.gm, P.gs, e2s, P.S2V2, sLm, sLp);
 }
 
 template <int n>
-constexpr size_t lifting_smem_bytes() { return sizeof(double) * (12 * n * n * n + 6 * 7 * n * n + n * n + 4 * n); }
+constexpr size_t lifting_smem_bytes() { return sizeof(double) * (12 * n * n * n + 6 * 7 * n * n + 2 * n * n + 4 * n); }
 
 // ---------------------------------------------------------------------------------------------------------
 // Numerical flux on a range of sides [side0, side0+nS): BC flux or Riemann + 1/2(Fv_L+Fv_R).n, times SurfElem

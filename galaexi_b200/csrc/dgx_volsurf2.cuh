@@ -22,25 +22,12 @@
 namespace dgx {
 
 template <int n>
-struct Tile {
-    // n == 8: bank-conflict-free 64-bit accesses for lines of all three directions WITHOUT padding. Position inside a
-    // 16-double row pair = (i + 8 (j&1)) xor (k + 8 (k&1)); 8-byte bank (of 16 per half warp) = (i^k) + 8 ((j^k)&1).
-    // Lane mappings that make a half warp hit 16 distinct banks: point-wise / zeta / eta lines: first coordinate fast;
-    // xi lines: k fast, two adjacent j.
-    static constexpr bool swz = (n == 8);
-    static constexpr int SLOT = n * n * n;
-    __device__ __forceinline__ static int idx(int i, int j, int k) {
-        return swz ? (((i + 8 * (j & 1)) ^ (k + 8 * (k & 1))) + 16 * (j >> 1) + 64 * k) : (i + n * j + n * n * k);
-    }
-};
-
-template <int n>
 constexpr int vs2_epb() { return (128 + n * n) / (2 * n * n) > 0 ? (128 + n * n) / (2 * n * n) : 1; }
 template <int n>
 constexpr int vs2_threads() { return vs2_epb<n>() * 2 * n * n; }
 constexpr int VS2_SLOTS = 18;
 template <int n>
-constexpr size_t vs2_smem_bytes() { return sizeof(double) * (size_t)vs2_epb<n>() * VS2_SLOTS * Tile<n>::SLOT; }
+constexpr size_t vs2_smem_bytes() { return sizeof(double) * ((size_t)vs2_epb<n>() * VS2_SLOTS * Tile<n>::SLOT + 2 * n * n); }
 
 // tile index of position l on the line (c1,c2) of direction d (0 xi: (j,k), 1 eta: (i,k), 2 zeta: (i,j)); d is a run-time
 // value on purpose: one copy of the sweep code serves the three directions (the fully unrolled variant was
@@ -120,17 +107,6 @@ __device__ __forceinline__ void vs2_sweep(const double* __restrict__ R, const do
     }
 }
 
-// Side-local node (p,q) handled by lane x of a face: the assignment is transposed when needed so that the tile
-// coordinate that must vary fastest over the lanes (b for xi faces, a otherwise) does -- conflict-free tile access.
-template <int n>
-__device__ __forceinline__ void face_lane(const int* __restrict__ S2V2, int x, int flip, int loc, int& p, int& qq) {
-    const bool a_on_p = s2v2<n>(S2V2, 0, 1, 0, flip, loc) != s2v2<n>(S2V2, 0, 0, 0, flip, loc);
-    const bool want_b_fast = (loc == XI_MINUS || loc == XI_PLUS);
-    const bool tr = (a_on_p == want_b_fast);
-    p = tr ? x / n : x % n;
-    qq = tr ? x % n : x / n;
-}
-
 template <int n, int MODE>
 __global__ void __launch_bounds__(vs2_threads<n>(), (n >= 8 ? 3 : 2)) k_volsurf2(const __grid_constant__ KParams P, int nWork, double mRKA, double b_dt) {
     constexpr int n2 = n * n, n3 = n2 * n, SEG = (n + 1) / 2, SL = Tile<n>::SLOT, T = 2 * n2, EPB = vs2_epb<n>();
@@ -140,13 +116,16 @@ __global__ void __launch_bounds__(vs2_threads<n>(), (n >= 8 ? 3 : 2)) k_volsurf2
     const bool live = we < nWork;
     const int e = live ? (P.elemList ? P.elemList[we] : we) : 0;
     double* S = smem + (size_t)le * VS2_SLOTS * SL;
+    double* sDh = smem + (size_t)EPB * VS2_SLOTS * SL;  // D_Hat_T [l + n a] and its transpose [a + n l] (lane-varying index)
+    double* sDhx = sDh + n2;
+    for (int x = threadIdx.x; x < n2; x += EPB * T) { sDh[x] = P.D_Hat_T[x]; sDhx[(x / n) + n * (x % n)] = P.D_Hat_T[x]; }
     const int h = tid / n2, q = tid - h * n2;
     const int c1 = q % n, c2 = q / n;          // point-wise phases: (i,j) = (c1,c2), k in the own half of the zeta column
     const int a0 = h * SEG, cnt = h ? n - SEG : SEG;
     const Eos eos = P.eos;
     const bool par = P.parabolic != 0;
     const int var = P.splitDG;
-    const double* __restrict__ Dh = P.D_Hat_T;
+    const double* __restrict__ Dh = P.D_Hat_T;  // uniform index only (constant bank)
     const double* __restrict__ Dv = P.DVolSurf;
     const double* __restrict__ gU_e = P.U + (size_t)e * 5 * n3;
     const double* __restrict__ gM_e = P.metrics + (size_t)e * 9 * n3;
@@ -222,7 +201,7 @@ __global__ void __launch_bounds__(vs2_threads<n>(), (n >= 8 ? 3 : 2)) k_volsurf2
             double hz[4];
 #pragma unroll
             for (int v = 0; v < 4; v++) hz[v] = S[(8 + v) * SL + idz];
-            const double dx = Dh[l + n * c1], dy = Dh[l + n * c2];
+            const double dx = sDhx[c1 + n * l], dy = sDh[l + n * c2];
 #pragma unroll
             for (int m = 0; m < SEG; m++) {
                 if (m < cnt) {
@@ -299,7 +278,7 @@ __global__ void __launch_bounds__(vs2_threads<n>(), (n >= 8 ? 3 : 2)) k_volsurf2
             const int side = __ldg(&e2s[0 + 3 * (loc - 1)]) - 1;
             const int flip = __ldg(&e2s[1 + 3 * (loc - 1)]);
             int p, qq;
-            face_lane<n>(P.S2V2, q, flip, loc, p, qq);
+            face_lane<n>(P.S2V2, q, flip, loc, (loc == XI_MINUS || loc == XI_PLUS), p, qq);
             const int a = s2v2<n>(P.S2V2, 0, p, qq, flip, loc);
             const int b = s2v2<n>(P.S2V2, 1, p, qq, flip, loc);
             const int l = h ? n - 1 : 0;
@@ -371,7 +350,7 @@ __global__ void __launch_bounds__(vs2_threads<n>(), (n >= 8 ? 3 : 2)) k_volsurf2
                 const int side = __ldg(&e2s[0 + 3 * (loc - 1)]) - 1;
                 const int flip = __ldg(&e2s[1 + 3 * (loc - 1)]);
                 int p, qq;
-                face_lane<n>(P.S2V2, f - (loc - 1) * n2, flip, loc, p, qq);
+                face_lane<n>(P.S2V2, f - (loc - 1) * n2, flip, loc, (loc == XI_MINUS || loc == XI_PLUS), p, qq);
                 const int pq = p + n * qq;
                 const int a = s2v2<n>(P.S2V2, 0, p, qq, flip, loc);
                 const int b = s2v2<n>(P.S2V2, 1, p, qq, flip, loc);

@@ -279,7 +279,7 @@ int check_err_flag(dgx_handle* h, const char* where) {
     int flag = 0;
     CK(cudaMemcpyAsync(&flag, h->errFlag, sizeof(int), cudaMemcpyDeviceToHost, h->s));
     CK(cudaStreamSynchronize(h->s));
-    if (flag & 1) return fail(h, "%s: unsupported boundary condition type (supported: 2,3,4,9)", where);
+    if (flag & 1) return fail(h, "%s: unsupported boundary condition type (supported: 2,3,4,9,91,23,24,25,27)", where);
     return 0;
 }
 
@@ -341,9 +341,10 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
     if (!h->kt) return fail(h, "no kernels compiled for N=%d (rebuild with this degree enabled)", c.N);
     if (c.nodeType != 1 && c.nodeType != 2) return fail(h, "nodeType must be 1 (Gauss) or 2 (Gauss-Lobatto)");
     if (c.splitDG >= 0 && c.nodeType != 2) return fail(h, "Wrong Pointset: Gauss-Lobatto-Points are mandatory for using SplitDG !");
-    if (c.splitDG != -1 && c.splitDG != 0 && c.splitDG != 3 && c.splitDG != 4) return fail(h, "SplitDG variant %d not available (SD=0, KG=3, PI=4)", c.splitDG);
-    if (c.riemann != 0 && c.riemann != 1 && c.riemann != 3 && c.riemann != 5) return fail(h, "Riemann solver %d not available (LF=0, Roe=1, RoeEntropyFix=3, HLLC=5)", c.riemann);
-    if (c.splitDG >= 0 && c.riemann == 5) return fail(h, "HLLC is not available with SplitDG (as in the reference, src/CMakeLists.txt:113-117)");
+    if (c.splitDG < -1 || c.splitDG > 4) return fail(h, "SplitDG variant %d not available (SD=0, MO=1, DU=2, KG=3, PI=4; CH is not implemented for GPU, splitflux.f90:133-135)", c.splitDG);
+    if (c.riemann < 0 || (c.riemann > 7 && c.riemann != 9)) return fail(h, "Riemann solver %d not available (LF=0, Roe=1, RoeL2=2, RoeEntropyFix=3, HLL=4, HLLC=5, HLLE=6, HLLEM=7, FluxAverage=9)", c.riemann);
+    if (c.splitDG >= 0 && c.riemann >= 4 && c.riemann <= 7) return fail(h, "HLL-type Riemann solvers are not supported for SPLIT_DG=ON (as in the reference, src/CMakeLists.txt:108-127)");
+    if (c.splitDG < 0 && c.riemann == 9) return fail(h, "the flux-average Riemann solver requires SplitDG (riemann.f90:1236-1252)");
     if (c.nRKStages < 1) return fail(h, "nRKStages < 1");
     CK(cudaSetDevice(c.device));
     cudaDeviceProp prop;

@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting
             const double t2[3] = {g[6 * n2], g[7 * n2], g[8 * n2]};
             double Pb[6];
             if (boundary_state(bct, eos, Pb, Pm, P.RefPrim + 6 * (bcs > 0 ? bcs - 1 : 0), nv, t1, t2)) atomicOr(P.errFlag, 1);
-            if (bct == 2) {
+            if (is_riemann_bc(bct)) {
                 Fl[0] = 0.5 * (Pm[VEL1] + Pb[VEL1]); Fl[1] = 0.5 * (Pm[VEL2] + Pb[VEL2]);
                 Fl[2] = 0.5 * (Pm[VEL3] + Pb[VEL3]); Fl[3] = 0.5 * (Pm[TEMP] + Pb[TEMP]);
             } else if (bct == 3 || bct == 4) {
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(128, 4) k_sideflux(const KParams P, int side0,
         const int bct = __ldg(&P.BCSides[2 * side]), bcs = __ldg(&P.BCSides[2 * side + 1]);
         double Pb[6];
         if (boundary_state(bct, eos, Pb, Pm, P.RefPrim + 6 * (bcs > 0 ? bcs - 1 : 0), nv, t1, t2)) atomicOr(P.errFlag, 1);
-        if (bct == 2) {
+        if (is_riemann_bc(bct)) {
             double Umc[5], Ubc[5];
             prim_to_cons(Pm, Umc, eos);
             prim_to_cons(Pb, Ubc, eos);
@@ -407,6 +407,10 @@ __global__ void __launch_bounds__(128, 4) k_sideflux(const KParams P, int side0,
                     for (int d = 0; d < 3; d++)
 #pragma unroll
                         for (int v = 0; v < 4; v++) gf[d * 4 + v] = B[d][0] * gm[0 * 4 + v] + B[d][1] * gm[1 * 4 + v] + B[d][2] * gm[2 * 4 + v];
+                    stress(tb, Pb, gf, mu, la);
+                } else if (bct == 91) {
+                    double gf[12];
+                    slip_wall_gradients_91(gm, nv, t1, t2, gf);
                     stress(tb, Pb, gf, mu, la);
                 } else {
                     stress(tb, Pb, gm, mu, la);

@@ -3,9 +3,10 @@
 // Hand-written for sm_100a FP64 CUDA cores. Formulas follow the reference (paths relative to
 // /root/reference/src/equations/navierstokes): idealgas/eos.f90:212-239 (ConsToPrim), :467-489 (PrimToCons),
 // :605-628 (PRESSURE_RIEMANN), idealgas/viscosity.f90 (muSuth), eos.h:110 (thermal conductivity),
-// riemann.f90:216-289 (rotation), :707 LF, :738 HLLC, :809 Roe, :885 RoeEntropyFix,
-// splitflux.f90:145/315 SD, :437/627 KG, :669/735 PI, flux.f90:619-697/700-745/779-822 viscous fluxes,
-// idealgas/getboundaryflux.f90:262-487 boundary states (types 2,3,4,9).
+// riemann.f90:216-289 (rotation), :707 LF, :738 HLLC, :809 Roe, :885 RoeEntropyFix, :994 RoeL2, :1075 HLL, :1126 HLLE,
+// :1175 HLLEM, :1239 FluxAverage; splitflux.f90 volume/surface: :145/315 SD, :543/627 MO, :346/407 DU, :437/506 KG,
+// :669/735 PI; flux.f90:619-697/700-745/779-822 viscous fluxes,
+// idealgas/getboundaryflux.f90:262-487 boundary states (types 2,3,4,9,91,23,24,25,27).
 #pragma once
 #include <math.h>
 
@@ -49,7 +50,7 @@ __device__ __forceinline__ double conductivity(const Eos& e, double mu) { return
 
 // ---------------------------------------------------------------------------------------------------------
 // split fluxes
-// node record used by the two-point volume fluxes: rho,u,v,w,p,X with X = H (PI), e=E/rho (KG), rhoE (SD)
+// node record used by the two-point volume fluxes: rho,u,v,w,p,X with X = H (PI), e=E/rho (KG), rhoE (SD, MO, DU)
 __device__ __forceinline__ double split_sixth(int variant, const double* U, const double* P) {
     if (variant == 4) return (U[ENER] + P[PRES]) / U[DENS];
     if (variant == 3) return U[ENER] / U[DENS];
@@ -69,6 +70,34 @@ __device__ __forceinline__ void split_volume_flux(int variant, const double* a, 
         F[MOM2] = h1 * (m1a * a[2] + m1b * b[2]) + h3 * (m2a * a[3] + m2b * b[3]) + h2 * (m2a * a[2] + m2b * b[2] + ps);
         F[MOM3] = h1 * (m1a * a[3] + m1b * b[3]) + h3 * (m3a * a[3] + m3b * b[3] + ps) + h2 * (m2a * a[3] + m2b * b[3]);
         F[ENER] = h1 * (Epa * a[1] + Epb * b[1]) + h3 * (Epa * a[3] + Epb * b[3]) + h2 * (Epa * a[2] + Epb * b[2]);
+        return;
+    }
+    if (variant == 1) {  // MO (splitflux.f90:543-622): {rho u}, {rho u}{u}+{p}, advective energy; contracted with 1/2 Ms first
+        const double h1 = 0.5 * Ms[0], h2 = 0.5 * Ms[1], h3 = 0.5 * Ms[2];
+        const double una = h1 * a[1] + h2 * a[2] + h3 * a[3], unb = h1 * b[1] + h2 * b[2] + h3 * b[3];  // contravariant velocities
+        const double mna = a[0] * una, mnb = b[0] * unb;
+        const double qa = a[1] * a[1] + a[2] * a[2] + a[3] * a[3], qb = b[1] * b[1] + b[2] * b[2] + b[3] * b[3];
+        const double rhoepa = a[5] - 0.5 * a[0] * qa + a[4], rhoepb = b[5] - 0.5 * b[0] * qb + b[4];
+        const double ms = mna + mnb, ps = a[4] + b[4];
+        const double us = a[1] + b[1], vs = a[2] + b[2], ws = a[3] + b[3];
+        F[DENS] = ms;
+        F[MOM1] = 0.5 * ms * us + h1 * ps;
+        F[MOM2] = 0.5 * ms * vs + h2 * ps;
+        F[MOM3] = 0.5 * ms * ws + h3 * ps;
+        F[ENER] = (rhoepa * una + rhoepb * unb) +
+                  0.5 * ((mna * a[1] + mnb * b[1]) * us + (mna * a[2] + mnb * b[2]) * vs + (mna * a[3] + mnb * b[3]) * ws) -
+                  0.5 * (mna * qa + mnb * qb);
+        return;
+    }
+    if (variant == 2) {  // DU (splitflux.f90:346-402): {rho}{u}, {rho u}{u}+{p}, ({rho E}+{p}){u}
+        const double h1 = 0.5 * Ms[0], h2 = 0.5 * Ms[1], h3 = 0.5 * Ms[2];
+        const double vn = 0.5 * (h1 * (a[1] + b[1]) + h2 * (a[2] + b[2]) + h3 * (a[3] + b[3]));  // 1/2 of the contravariant velocity sum
+        const double ps = a[4] + b[4];
+        F[DENS] = (a[0] + b[0]) * vn;
+        F[MOM1] = (a[0] * a[1] + b[0] * b[1]) * vn + h1 * ps;
+        F[MOM2] = (a[0] * a[2] + b[0] * b[2]) * vn + h2 * ps;
+        F[MOM3] = (a[0] * a[3] + b[0] * b[3]) * vn + h3 * ps;
+        F[ENER] = (a[5] + b[5] + ps) * vn;
         return;
     }
     const double rs = a[0] + b[0];
@@ -92,6 +121,29 @@ struct Ext {
 };
 
 __device__ __forceinline__ void split_surface_flux(int variant, const Ext& L, const Ext& R, double* F) {
+    if (variant == 1) {  // MO
+        const double qL = L.v1 * L.v1 + L.v2 * L.v2 + L.v3 * L.v3, qR = R.v1 * R.v1 + R.v2 * R.v2 + R.v3 * R.v3;
+        const double rhoepL = L.ener - 0.5 * L.rho * qL + L.pres, rhoepR = R.ener - 0.5 * R.rho * qR + R.pres;
+        const double ms = L.m1 + R.m1;
+        F[DENS] = 0.5 * ms;
+        F[MOM1] = 0.25 * ms * (L.v1 + R.v1) + 0.5 * (L.pres + R.pres);
+        F[MOM2] = 0.25 * ms * (L.v2 + R.v2);
+        F[MOM3] = 0.25 * ms * (L.v3 + R.v3);
+        F[ENER] = 0.5 * (rhoepL * L.v1 + rhoepR * R.v1) + 0.25 * (L.m1 * L.v1 + R.m1 * R.v1) * (L.v1 + R.v1) +
+                  0.25 * (L.m1 * L.v2 + R.m1 * R.v2) * (L.v2 + R.v2) + 0.25 * (L.m1 * L.v3 + R.m1 * R.v3) * (L.v3 + R.v3) -
+                  0.25 * (L.m1 * L.v1 * L.v1 + R.m1 * R.v1 * R.v1) - 0.25 * (L.m1 * L.v2 * L.v2 + R.m1 * R.v2 * R.v2) -
+                  0.25 * (L.m1 * L.v3 * L.v3 + R.m1 * R.v3 * R.v3);
+        return;
+    }
+    if (variant == 2) {  // DU
+        const double us = L.v1 + R.v1;
+        F[DENS] = 0.25 * (L.rho + R.rho) * us;
+        F[MOM1] = 0.25 * (L.m1 + R.m1) * us + 0.5 * (L.pres + R.pres);
+        F[MOM2] = 0.25 * (L.m2 + R.m2) * us;
+        F[MOM3] = 0.25 * (L.m3 + R.m3) * us;
+        F[ENER] = 0.25 * (L.ener + R.ener + L.pres + R.pres) * us;
+        return;
+    }
     if (variant == 0) {
         F[DENS] = 0.5 * (L.m1 + R.m1);
         F[MOM1] = 0.5 * (L.m1 * L.v1 + L.pres + R.m1 * R.v1 + R.pres);
@@ -155,6 +207,10 @@ __device__ __forceinline__ void riemann_solver(int riem, int split, double kappa
         }
         return;
     }
+    if (riem == 9) {  // Riemann_FluxAverage (SPLIT_DG only; dgx_create enforces it)
+        split_surface_flux(split, L, R, F);
+        return;
+    }
     // Roe averages
     const double HL = (L.ener + L.pres) * L.sRho, HR = (R.ener + R.pres) * R.sRho;
     const double sl = sqrt(L.rho), sr = sqrt(R.rho);
@@ -163,6 +219,38 @@ __device__ __forceinline__ void riemann_solver(int riem, int split, double kappa
     const double RoeH = (sr * HR + sl * HL) * ss;
     const double absVel = rv1 * rv1 + rv2 * rv2 + rv3 * rv3;
     const double Roec = sqrt((kappa - 1.0) * (RoeH - 0.5 * absVel));
+    if (riem == 4 || riem == 6 || riem == 7) {  // HLL, HLLE, HLLEM (non-split builds only)
+        double Ssl, Ssr;
+        if (riem == 4) { Ssl = rv1 - Roec; Ssr = rv1 + Roec; }
+        else {
+            const double beta = sqrt(0.5 * (kappa - 1.0) / kappa);
+            const double cL = sqrt(kappa * L.pres * L.sRho), cR = sqrt(kappa * R.pres * R.sRho);
+            Ssl = fmin(fmin(rv1 - Roec, L.v1 - beta * cL), 0.0);
+            Ssr = fmax(fmax(rv1 + Roec, R.v1 + beta * cR), 0.0);
+        }
+        if (Ssl >= 0.0) {
+#pragma unroll
+            for (int v = 0; v < 5; v++) F[v] = FL[v];
+        } else if (Ssr <= 0.0) {
+#pragma unroll
+            for (int v = 0; v < 5; v++) F[v] = FR[v];
+        } else if (riem != 7) {
+#pragma unroll
+            for (int v = 0; v < 5; v++) F[v] = (Ssr * FL[v] - Ssl * FR[v] + Ssl * Ssr * (UR[v] - UL[v])) / (Ssr - Ssl);
+        } else {
+            const double RoeDens = sqrt(L.rho * R.rho);
+            const double delta = Roec / (Roec + fabs(0.5 * (Ssl + Ssr)));
+            const double A2 = (R.rho - L.rho) - (R.pres - L.pres) / (Roec * Roec);
+            const double A3 = RoeDens * (R.v2 - L.v2), A4 = RoeDens * (R.v3 - L.v3);
+            const double q2[5] = {1.0, rv1, rv2, rv3, 0.5 * absVel};
+            const double q3[5] = {0.0, 0.0, 1.0, 0.0, rv2};
+            const double q4[5] = {0.0, 0.0, 0.0, 1.0, rv3};
+#pragma unroll
+            for (int v = 0; v < 5; v++)
+                F[v] = (Ssr * FL[v] - Ssl * FR[v] + Ssl * Ssr * (UR[v] - UL[v] - delta * (q2[v] * A2 + q3[v] * A3 + q4[v] * A4))) / (Ssr - Ssl);
+        }
+        return;
+    }
     if (riem == 5) {  // HLLC
         const double Ssl = rv1 - Roec, Ssr = rv1 + Roec;
         if (Ssl >= 0.0) {
@@ -197,11 +285,15 @@ __device__ __forceinline__ void riemann_solver(int riem, int split, double kappa
     const double r4[5] = {0.0, 0.0, 0.0, 1.0, rv3};
     const double r5[5] = {1.0, a[4], rv2, rv3, RoeH + rv1 * Roec};
     double Al[5];
-    if (riem == 1) {  // Roe
+    if (riem == 1 || riem == 2) {  // Roe, RoeL2
         double dU[6];
 #pragma unroll
         for (int v = 0; v < 5; v++) dU[v] = UR[v] - UL[v];
         dU[5] = dU[4] - (dU[2] - rv2 * dU[0]) * rv2 - (dU[3] - rv3 * dU[0]) * rv3;
+        if (riem == 2) {  // low Mach number fix (riemann.f90:1044-1046)
+            const double Ma = sqrt(absVel) / (Roec * sqrt(kappa));
+            dU[1] *= Ma; dU[2] *= Ma; dU[3] *= Ma;
+        }
         Al[2] = dU[2] - rv2 * dU[0];
         Al[3] = dU[3] - rv3 * dU[0];
         Al[1] = (kappa - 1.0) / (Roec * Roec) * (dU[0] * (RoeH - rv1 * rv1) - dU[5] + rv1 * dU[1]);
@@ -295,6 +387,9 @@ __device__ __forceinline__ double pressure_riemann(const double* P, double kappa
     return P[PRES] + P[VEL1] / ar * 0.5 * (P[VEL1] + sqrt(P[VEL1] * P[VEL1] + 4.0 * ar * (P[PRES] + br)));
 }
 
+__device__ __forceinline__ bool is_riemann_bc(int t) { return t == 2 || t == 23 || t == 24 || t == 25 || t == 27; }
+__device__ __forceinline__ bool is_wall_bc(int t) { return t == 3 || t == 4 || t == 9 || t == 91; }
+
 // returns 0 if the BC type is supported
 __device__ __forceinline__ int boundary_state(int bct, const Eos& e, double* out, const double* Pm, const double* Ref, const double* nv,
                                               const double* t1, const double* t2) {
@@ -303,36 +398,115 @@ __device__ __forceinline__ int boundary_state(int bct, const Eos& e, double* out
         for (int v = 0; v < 6; v++) out[v] = Ref[v];
         return 0;
     }
-    if (bct == 3 || bct == 4 || bct == 9) {
-        double b[6];
-        b[DENS] = Pm[DENS];
-        b[VEL1] = Pm[VEL1] * nv[0] + Pm[VEL2] * nv[1] + Pm[VEL3] * nv[2];
-        b[VEL2] = Pm[VEL1] * t1[0] + Pm[VEL2] * t1[1] + Pm[VEL3] * t1[2];
-        b[VEL3] = Pm[VEL1] * t2[0] + Pm[VEL2] * t2[1] + Pm[VEL3] * t2[2];
-        b[PRES] = Pm[PRES];
-        b[TEMP] = Pm[TEMP];
-        b[PRES] = pressure_riemann(b, e.kappa);
+    if (!is_wall_bc(bct) && !is_riemann_bc(bct)) return 1;
+    const double kappa = e.kappa, R = e.R;
+    double b[6];
+    b[DENS] = Pm[DENS];
+    b[VEL1] = Pm[VEL1] * nv[0] + Pm[VEL2] * nv[1] + Pm[VEL3] * nv[2];
+    b[VEL2] = Pm[VEL1] * t1[0] + Pm[VEL2] * t1[1] + Pm[VEL3] * t1[2];
+    b[VEL3] = Pm[VEL1] * t2[0] + Pm[VEL2] * t2[1] + Pm[VEL3] * t2[2];
+    b[PRES] = Pm[PRES];
+    b[TEMP] = Pm[TEMP];
+    if (is_wall_bc(bct)) {
+        b[PRES] = pressure_riemann(b, kappa);
         if (bct == 3) {
             b[VEL1] = b[VEL2] = b[VEL3] = 0.0;
             b[TEMP] = Pm[TEMP];
-            b[DENS] = b[PRES] / (b[TEMP] * e.R);
+            b[DENS] = b[PRES] / (b[TEMP] * R);
         } else if (bct == 4) {
             b[VEL1] = b[VEL2] = b[VEL3] = 0.0;
             b[TEMP] = Ref[TEMP];
-            b[DENS] = b[PRES] / (b[TEMP] * e.R);
-        } else {
+            b[DENS] = b[PRES] / (b[TEMP] * R);
+        } else {  // 9, 91
             b[VEL1] = 0.0;
             b[DENS] = Pm[DENS];
-            b[TEMP] = b[PRES] / (b[DENS] * e.R);
+            b[TEMP] = b[PRES] / (b[DENS] * R);
         }
-        out[DENS] = b[DENS];
-#pragma unroll
-        for (int d = 0; d < 3; d++) out[VEL1 + d] = b[VEL1] * nv[d] + b[VEL2] * t1[d] + b[VEL3] * t2[d];
-        out[PRES] = b[PRES];
-        out[TEMP] = b[TEMP];
-        return 0;
+    } else if (bct == 27) {  // subsonic inflow; Ref = (Tt, a1, a2, a3, pt) with the unit direction a set up by the host
+        const double Tt = Ref[0], pt = Ref[4];
+        const double an = Ref[1] * nv[0] + Ref[2] * nv[1] + Ref[3] * nv[2];
+        const double A = -1.0 * an;
+        const double c = sqrt(kappa * b[PRES] / b[DENS]);
+        const double Rplus = -b[VEL1] - 2.0 * c / (kappa - 1.0);
+        const double tmp1 = A * A + 2.0 / (kappa - 1.0);
+        const double tmp2 = 2.0 * Rplus;
+        const double tmp3 = (kappa - 1.0) / 2.0 * (Rplus * Rplus) - kappa * R * Tt * (A * A);
+        const double disc = sqrt(tmp2 * tmp2 - 4.0 * tmp1 * tmp3);
+        const double cb = fmax((-tmp2 + disc) / (2.0 * tmp1), (-tmp2 - disc) / (2.0 * tmp1));
+        const double Tb = cb * cb / (kappa * R);
+        const double Ma = sqrt(2.0 / (kappa - 1.0) * (Tt / Tb - 1.0));
+        const double pb = pt * pow(1.0 + 0.5 * (kappa - 1.0) * (Ma * Ma), -kappa / (kappa - 1.0));
+        const double Um = Ma * sqrt(kappa * R * Tb);
+        b[DENS] = pb / (R * Tb);
+        b[VEL1] = Um * an;
+        b[VEL2] = Um * (Ref[1] * t1[0] + Ref[2] * t1[1] + Ref[3] * t1[2]);
+        b[VEL3] = Um * (Ref[1] * t2[0] + Ref[2] * t2[1] + Ref[3] * t2[2]);
+        b[PRES] = pb;
+        b[TEMP] = Tb;
+    } else {  // 23, 24, 25: outflows (Carlson, NASA/TM-2011-217181)
+        const double c = sqrt(kappa * b[PRES] / b[DENS]);
+        const double Ma = b[VEL1] / c;
+        const double ptot = b[PRES] + 0.5 * b[DENS] * (b[VEL1] * b[VEL1] + b[VEL2] * b[VEL2] + b[VEL3] * b[VEL3]);
+        if (bct == 23) {
+            const double MaOut = Ref[1];
+            double pb;
+            if (Ma < 1.0) {
+                const double pt = b[PRES] * pow(1.0 + 0.5 * (kappa - 1.0) * Ma * Ma, kappa / (kappa - 1.0));
+                pb = pt * pow(1.0 + 0.5 * (kappa - 1.0) * MaOut * MaOut, -kappa / (kappa - 1.0));
+            } else pb = ptot;
+            b[DENS] = kappa * pb / (c * c);
+            b[PRES] = pb;
+            b[TEMP] = b[PRES] / (R * b[DENS]);
+        } else if (bct == 24) {
+            if (Ma < 1.0) {
+                const double pb = Ref[4];
+                b[DENS] = kappa * pb / (c * c);
+                b[PRES] = pb;
+                b[TEMP] = b[PRES] / (R * b[DENS]);
+            }
+        } else {
+            const double pb = (Ma < 1.0) ? Ref[4] : ptot;
+            if (b[VEL1] < 0.0) { b[VEL1] = fabs(b[VEL1]); b[VEL2] = 0.0; b[VEL3] = 0.0; }
+            b[DENS] = kappa * pb / (c * c);
+            b[PRES] = Ref[4];
+            b[TEMP] = b[PRES] / (R * b[DENS]);
+        }
     }
-    return 1;
+    out[DENS] = b[DENS];
+#pragma unroll
+    for (int d = 0; d < 3; d++) out[VEL1 + d] = b[VEL1] * nv[d] + b[VEL2] * t1[d] + b[VEL3] * t2[d];
+    out[PRES] = b[PRES];
+    out[TEMP] = b[TEMP];
+    return 0;
+}
+
+// slip wall, version 2 (BC 91, getboundaryflux.f90:716-781): wall-normal derivative of the tangential velocities and
+// wall-tangential derivatives of the normal velocity set to zero; temperature gradient loses its normal component.
+__device__ __forceinline__ void slip_wall_gradients_91(const double* gm, const double* nv, const double* t1, const double* t2, double* gf) {
+    const double* tv[3] = {nv, t1, t2};
+    const double B[3][3] = {{1.0 - nv[0] * nv[0], -nv[0] * nv[1], -nv[0] * nv[2]},
+                            {-nv[0] * nv[1], 1.0 - nv[1] * nv[1], -nv[2] * nv[1]},
+                            {-nv[0] * nv[2], -nv[2] * nv[1], 1.0 - nv[2] * nv[2]}};
+#pragma unroll
+    for (int d = 0; d < 3; d++) gf[d * 4 + LT] = B[d][0] * gm[0 * 4 + LT] + B[d][1] * gm[1 * 4 + LT] + B[d][2] * gm[2 * 4 + LT];
+    double gw[3][3], ga[3][3];
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+#pragma unroll
+        for (int w = 0; w < 3; w++) gw[d][w] = tv[w][0] * gm[d * 4 + LV1] + tv[w][1] * gm[d * 4 + LV2] + tv[w][2] * gm[d * 4 + LV3];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int w = 0; w < 3; w++) ga[a][w] = tv[a][0] * gw[0][w] + tv[a][1] * gw[1][w] + tv[a][2] * gw[2][w];
+    ga[0][1] = 0.0; ga[0][2] = 0.0; ga[1][0] = 0.0; ga[2][0] = 0.0;
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+#pragma unroll
+        for (int w = 0; w < 3; w++) gw[d][w] = nv[d] * ga[0][w] + t1[d] * ga[1][w] + t2[d] * ga[2][w];
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+#pragma unroll
+        for (int x = 0; x < 3; x++) gf[d * 4 + LV1 + x] = nv[x] * gw[d][0] + t1[x] * gw[d][1] + t2[x] * gw[d][2];
 }
 
 }  // namespace dgx

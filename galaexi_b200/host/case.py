@@ -20,7 +20,8 @@ from . import metrics as mt
 from . import timedisc as td
 
 SPLIT_IDS = {None: -1, "NONE": -1, "SD": 0, "MO": 1, "DU": 2, "KG": 3, "PI": 4}      # SPLIT_DG
-RIEMANN_IDS = {"LF": 0, "ROE": 1, "ROEL2": 2, "ROEENTROPYFIX": 3, "HLL": 4, "HLLC": 5, "HLLE": 6, "HLLEM": 7}
+RIEMANN_IDS = {"LF": 0, "ROE": 1, "ROEL2": 2, "ROEENTROPYFIX": 3, "HLL": 4, "HLLC": 5, "HLLE": 6, "HLLEM": 7,
+               "FLUXAVERAGE": 9, "AVG": 9, "CENTRAL": 9}   # RIEMANN (src/CMakeLists.txt:97-130); 9: Riemann_FluxAverage riemann.f90:1239
 
 
 @dataclass
@@ -64,11 +65,14 @@ def build_case(hopr: dict, N: int, node_type: str = bs.NODETYPE_GL, split: str |
     if split_id >= 0 and riem_id in (4, 5, 6, 7):
         # src/CMakeLists.txt:108-127
         raise ValueError("HLL-type Riemann solvers are not available with SplitDG")
+    if split_id < 0 and riem_id == 9:
+        # riemann.f90:1236-1252: Riemann_FluxAverage only exists inside #ifdef SPLIT_DG
+        raise ValueError("The flux-average Riemann solver is only available with SplitDG")
     basis = bs.init_dg_basis(N, node_type)
     mesh = ms.prepare_mesh(hopr, nProcs=nProcs, myRank=myRank, useCurveds=useCurveds, user_bcs=user_bcs)
     geo = mt.calc_metrics(mesh, N, node_type, crossProductMetrics=crossProductMetrics, hopr=hopr)
     maps = mp.build_mappings(N)
-    refprim = eq.refstate_prim(refstates, eos)
+    refprim = eq.init_bc_refstates(eq.refstate_prim(refstates, eos), mesh.BoundaryType)
     bcs = eq.bc_sides(mesh)
     tdisc = td.set_timedisc(timedisc, N, node_type, CFLScale, DFLScale)
     return Case(N, node_type, basis, mesh, geo, maps, eos, refprim, bcs, tdisc, split_id, riem_id, bool(parabolic), hopr)

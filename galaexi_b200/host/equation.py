@@ -77,6 +77,32 @@ def refstate_prim(refstates, eos: Eos) -> np.ndarray:
     return out
 
 
+def init_bc_refstates(refprim: np.ndarray, BoundaryType: np.ndarray) -> np.ndarray:
+    """InitBC (getboundaryflux.f90:194-212): for every boundary of type 27 (subsonic inflow) the refstate
+    (Tt, alpha, beta, <empty>, pt) is rewritten in place to (Tt, a1, a2, a3, pt) with the unit direction vector a.
+    Also the refstate sanity checks of :121-165 (Abort -> ValueError)."""
+    ref = np.array(refprim, dtype=np.float64, copy=True)
+    need_state = {2: "No refstate (rho,velx,vely,velz,p) defined for BC_TYPE",
+                  4: "No refstate (rho,x,x,x,p) defined to compute temperature from density and pressure for BC_TYPE",
+                  23: "No outflow Mach number in refstate (x,Ma,x,x,x) defined for BC_TYPE",
+                  24: "No outflow pressure in refstate (x,x,x,x,p) defined for BC_TYPE",
+                  25: "No outflow pressure in refstate (x,x,x,x,p) defined for BC_TYPE",
+                  27: "No inflow refstate (Tt,alpha,beta,<empty>,pT) in refstate defined for BC_TYPE"}
+    for i in range(BoundaryType.shape[0]):
+        t, st = int(BoundaryType[i, 0]), int(BoundaryType[i, 1])
+        if t in need_state and st < 1:
+            raise ValueError(f"{need_state[t]} {t}")
+        if t in need_state and st > ref.shape[0]:
+            raise ValueError(f"ERROR: Boundary RefState not defined! (MaxBCState,nRefState): {st} {ref.shape[0]}")
+        if t == 27:
+            talpha = math.tan(PI / 180.0 * ref[st - 1, 1])
+            tbeta = math.tan(PI / 180.0 * ref[st - 1, 2])
+            ref[st - 1, 1] = 1.0 / math.sqrt((1.0 + talpha ** 2 + tbeta ** 2))
+            ref[st - 1, 2] = talpha / math.sqrt((1.0 + talpha ** 2 + tbeta ** 2))
+            ref[st - 1, 3] = tbeta / math.sqrt((1.0 + talpha ** 2 + tbeta ** 2))
+    return ref
+
+
 def bc_sides(mesh) -> np.ndarray:
     """BCSides(2,nBCSides) as C array [nBCSides,2] (getboundaryflux.f90:244-252)."""
     out = np.zeros((mesh.nBCSides, 2), dtype=np.int32)

@@ -43,8 +43,9 @@ typedef struct dgx_config {
     /* discretisation (compile-time options of the reference become run-time here) */
     int N;              /* polynomial degree PP_N */
     int nodeType;       /* PP_NodeType: 1 Gauss, 2 Gauss-Lobatto */
-    int splitDG;        /* SPLIT_DG: -1 off (weak form), 0 SD, 3 KG, 4 PI */
-    int riemann;        /* RIEMANN: 0 LF, 1 Roe, 3 RoeEntropyFix, 5 HLLC (non-split only) */
+    int splitDG;        /* SPLIT_DG: -1 off (weak form), 0 SD, 1 MO, 2 DU, 3 KG, 4 PI (src/CMakeLists.txt:73-92) */
+    int riemann;        /* RIEMANN: 0 LF, 1 Roe, 2 RoeL2, 3 RoeEntropyFix, 4 HLL, 5 HLLC, 6 HLLE, 7 HLLEM (4-7: non-split
+                         * only, src/CMakeLists.txt:97-130); 9 FluxAverage (split only, riemann.f90:1239) */
     int parabolic;      /* PARABOLIC: 0 Euler, 1 Navier-Stokes with BR1 lifting */
     int viscLaw;        /* PP_VISC: 0 constant, 1 Sutherland */
     /* mesh sizes and side ranges (1-based inclusive, mesh/mesh.f90:259-283) */
@@ -54,8 +55,8 @@ typedef struct dgx_config {
     /* equation of state: EOS_Vars(1:8) = kappa,R,Pr,mu0,Ts,Tref,ExpoSuth,cSuth (eos.h:44-62) */
     double EOS_Vars[8];
     int nRefState;
-    const double *RefStatePrim;   /* (6,nRefState) */
-    const int *BCSides;           /* (2,nBCSides): BC_TYPE, BC_STATE (getboundaryflux.f90:244-252) */
+    const double *RefStatePrim;   /* (6,nRefState), after InitBC (getboundaryflux.f90:194-212: type 27 direction vector) */
+    const int *BCSides;           /* (2,nBCSides): BC_TYPE, BC_STATE (getboundaryflux.f90:244-252); types 2,3,4,9,91,23,24,25,27 */
     /* operators (0:N,0:N) / (0:N), dg/dg.f90:181-242 */
     const double *D_T, *D_Hat_T, *DVolSurf, *L_Minus, *L_Plus, *L_HatMinus, *L_HatPlus;
     /* connectivity: ElemToSide(3,6,nElems), S2V2/S2V2_inv(2,0:N,0:N,0:4,1:6) */

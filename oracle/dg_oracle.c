@@ -16,8 +16,9 @@
  *
  * Scope of the restatement: 3D, conforming meshes, PP_nVar=5, PP_nVarPrim=6, PP_nVarLifting=5
  * (PP_OPTLIFT=0), BR1 lifting in strong non-conservative form (the GALAEXI defaults, lifting.f90:81-85),
- * node types Gauss / Gauss-Lobatto, weak form or split form (SD, KG, PI), Riemann solvers LF, Roe,
- * RoeEntropyFix, HLLC, constant or Sutherland viscosity, BC types 2, 3, 4, 9.
+ * node types Gauss / Gauss-Lobatto, weak form or split form (SD, MO, DU, KG, PI), Riemann solvers LF, Roe, RoeL2,
+ * RoeEntropyFix, HLL, HLLC, HLLE, HLLEM, FluxAverage, constant or Sutherland viscosity, BC types 2, 3, 4, 9, 91,
+ * 23, 24, 25, 27.
  *
  * Two builds of this one source (oracle/Makefile): libdgoracle.so (FP64, no FMA contraction: the reference's
  * arithmetic) and libdgoracle_ld.so (-DDGO_EXTENDED: the same formulas and the same FP64 constants
@@ -58,8 +59,8 @@ typedef struct {
     int nBCSides, firstInnerSide, lastInnerSide;
     int firstMPISide_MINE, lastMPISide_MINE, firstMPISide_YOUR, lastMPISide_YOUR;
     int nodeType;  /* 1 Gauss, 2 Gauss-Lobatto (PP_NodeType) */
-    int splitDG;   /* -1 off; 0 SD, 3 KG, 4 PI (SPLIT_DG) */
-    int riemann;   /* 0 LF, 1 Roe, 3 RoeEntropyFix, 5 HLLC (RIEMANN) */
+    int splitDG;   /* -1 off; 0 SD, 1 MO, 2 DU, 3 KG, 4 PI (SPLIT_DG) */
+    int riemann;   /* 0 LF, 1 Roe, 2 RoeL2, 3 RoeEntropyFix, 4 HLL, 5 HLLC, 6 HLLE, 7 HLLEM (RIEMANN); 9 FluxAverage */
     int parabolic; /* PARABOLIC */
     int viscLaw;   /* PP_VISC: 0 constant, 1 Sutherland */
     int nRefState;
@@ -249,13 +250,15 @@ static double pressure_riemann(const double *P, double kappa)
     }
     return P_RP;
 }
-/* idealgas/getboundaryflux.f90:262-487 GetBoundaryState, BC types 2,3,4,9 */
+/* idealgas/getboundaryflux.f90:262-487 GetBoundaryState, BC types 2,3,4,9,91,23,24,25,27 */
+static int is_riemann_bc(int t) { return t == 2 || t == 23 || t == 24 || t == 25 || t == 27; }
+static int is_wall_bc(int t) { return t == 3 || t == 4 || t == 9 || t == 91; }
 static int get_boundary_state(const dgo_config *c, int BCType, double *out, const double *Pm, const double *Ref,
                               const double *nv, const double *t1, const double *t2)
 {
     double kappa = c->EOS[EOS_KAPPA], R = c->EOS[EOS_R];
     if (BCType == 2) { for (int v = 0; v < NP; v++) out[v] = Ref[v]; return 0; }
-    if (BCType == 3 || BCType == 4 || BCType == 9) {
+    if (is_wall_bc(BCType) || (is_riemann_bc(BCType) && BCType != 2)) {
         double b[NP];
         b[DENS] = Pm[DENS];
         b[VEL1] = Pm[VEL1] * nv[0] + Pm[VEL2] * nv[1] + Pm[VEL3] * nv[2];
@@ -273,11 +276,62 @@ static int get_boundary_state(const dgo_config *c, int BCType, double *out, cons
             b[VEL1] = b[VEL2] = b[VEL3] = 0.;
             b[TEMP] = Ref[TEMP];
             b[DENS] = b[PRES] / (b[TEMP] * R);
-        } else {
+        } else if (BCType == 9 || BCType == 91) {
             b[PRES] = pressure_riemann(b, kappa);
             b[VEL1] = 0.;
             b[DENS] = Pm[DENS];
             b[TEMP] = b[PRES] / (b[DENS] * R);
+        } else if (BCType == 23) { /* :361-383 outflow Mach number, RefState = (x,MaOut,x,x,x) */
+            double MaOut = Ref[1];
+            double cs = sqrt(kappa * b[PRES] / b[DENS]);
+            double Ma = b[VEL1] / cs, pb;
+            if (Ma < 1) {
+                double pt = b[PRES] * pow(1 + 0.5 * (kappa - 1) * Ma * Ma, kappa / (kappa - 1.));
+                pb = pt * pow(1 + 0.5 * (kappa - 1) * MaOut * MaOut, -kappa / (kappa - 1.));
+            } else {
+                pb = b[PRES] + 0.5 * b[DENS] * (b[VEL1] * b[VEL1] + b[VEL2] * b[VEL2] + b[VEL3] * b[VEL3]);
+            }
+            b[DENS] = kappa * pb / (cs * cs);
+            b[PRES] = pb;
+            b[TEMP] = b[PRES] / (R * b[DENS]);
+        } else if (BCType == 24) { /* :385-401 pressure outflow, RefState = (x,x,x,x,p) */
+            double cs = sqrt(kappa * b[PRES] / b[DENS]);
+            double Ma = b[VEL1] / cs;
+            if (Ma < 1) {
+                double pb = Ref[4];
+                b[DENS] = kappa * pb / (cs * cs);
+                b[PRES] = pb;
+                b[TEMP] = b[PRES] / (R * b[DENS]);
+            }
+        } else if (BCType == 25) { /* :403-426 subsonic outflow */
+            double cs = sqrt(kappa * b[PRES] / b[DENS]);
+            double Ma = b[VEL1] / cs, pb;
+            if (Ma < 1) pb = Ref[4];
+            else pb = b[PRES] + 0.5 * b[DENS] * (b[VEL1] * b[VEL1] + b[VEL2] * b[VEL2] + b[VEL3] * b[VEL3]);
+            if (b[VEL1] < 0.) { b[VEL1] = fabs(b[VEL1]); b[VEL2] = 0.; b[VEL3] = 0.; }
+            b[DENS] = kappa * pb / (cs * cs);
+            b[PRES] = Ref[4];
+            b[TEMP] = b[PRES] / (R * b[DENS]);
+        } else { /* 27, :428-474 subsonic inflow; RefState = (Tt, a(1:3) precomputed at init :201-210, pt) */
+            double Tt = Ref[0], pt = Ref[4];
+            const double *a = &Ref[1];
+            double A = -1. * (a[0] * nv[0] + a[1] * nv[1] + a[2] * nv[2]);
+            double cs = sqrt(kappa * b[PRES] / b[DENS]);
+            double Rplus = -b[VEL1] - 2. * cs / (kappa - 1.);
+            double tmp1 = A * A + 2. / (kappa - 1.);
+            double tmp2 = 2 * Rplus;
+            double tmp3 = (kappa - 1.) / 2. * (Rplus * Rplus) - kappa * R * Tt * (A * A);
+            double cb = fmax((-tmp2 + sqrt(tmp2 * tmp2 - 4 * tmp1 * tmp3)) / (2 * tmp1), (-tmp2 - sqrt(tmp2 * tmp2 - 4 * tmp1 * tmp3)) / (2 * tmp1));
+            double Tb = cb * cb / (kappa * R);
+            double Ma = sqrt(2. / (kappa - 1.) * (Tt / Tb - 1.));
+            double pb = pt * pow(1. + 0.5 * (kappa - 1.) * (Ma * Ma), -kappa / (kappa - 1.));
+            double Um = Ma * sqrt(kappa * R * Tb);
+            b[DENS] = pb / (R * Tb);
+            b[VEL1] = Um * (a[0] * nv[0] + a[1] * nv[1] + a[2] * nv[2]);
+            b[VEL2] = Um * (a[0] * t1[0] + a[1] * t1[1] + a[2] * t1[2]);
+            b[VEL3] = Um * (a[0] * t2[0] + a[1] * t2[1] + a[2] * t2[2]);
+            b[PRES] = pb;
+            b[TEMP] = Tb;
         }
         out[DENS] = b[DENS];
         for (int d = 0; d < 3; d++) out[VEL1 + d] = b[VEL1] * nv[d] + b[VEL2] * t1[d] + b[VEL3] * t2[d];
@@ -289,10 +343,30 @@ static int get_boundary_state(const dgo_config *c, int BCType, double *out, cons
 }
 
 /* ------------------------------------------------------------------------------------------------ */
-/* equations/navierstokes/splitflux.f90: surface fluxes :315 (SD) :627 (KG) :735 (PI) */
+/* equations/navierstokes/splitflux.f90: surface fluxes :315 (SD) :627 (MO) :407 (DU) :506 (KG) :735 (PI) */
 static void split_surface_flux(int variant, const double *L, const double *R, double *F)
 {
-    if (variant == 0) {
+    if (variant == 1) { /* MO :627-660 */
+        double rhoep_LL = L[E_ENER] - 0.5 * L[E_DENS] * (L[E_VEL1] * L[E_VEL1] + L[E_VEL2] * L[E_VEL2] + L[E_VEL3] * L[E_VEL3]) + L[E_PRES];
+        double rhoep_RR = R[E_ENER] - 0.5 * R[E_DENS] * (R[E_VEL1] * R[E_VEL1] + R[E_VEL2] * R[E_VEL2] + R[E_VEL3] * R[E_VEL3]) + R[E_PRES];
+        F[DENS] = 0.5 * (L[E_MOM1] + R[E_MOM1]);
+        F[MOM1] = 0.25 * (L[E_MOM1] + R[E_MOM1]) * (L[E_VEL1] + R[E_VEL1]) + 0.5 * (L[E_PRES] + R[E_PRES]);
+        F[MOM2] = 0.25 * (L[E_MOM1] + R[E_MOM1]) * (L[E_VEL2] + R[E_VEL2]);
+        F[MOM3] = 0.25 * (L[E_MOM1] + R[E_MOM1]) * (L[E_VEL3] + R[E_VEL3]);
+        F[ENER] = 0.5 * (rhoep_LL * L[E_VEL1] + rhoep_RR * R[E_VEL1]) +
+                  0.25 * (L[E_MOM1] * L[E_VEL1] + R[E_MOM1] * R[E_VEL1]) * (L[E_VEL1] + R[E_VEL1]) +
+                  0.25 * (L[E_MOM1] * L[E_VEL2] + R[E_MOM1] * R[E_VEL2]) * (L[E_VEL2] + R[E_VEL2]) +
+                  0.25 * (L[E_MOM1] * L[E_VEL3] + R[E_MOM1] * R[E_VEL3]) * (L[E_VEL3] + R[E_VEL3]) -
+                  0.25 * (L[E_MOM1] * L[E_VEL1] * L[E_VEL1] + R[E_MOM1] * R[E_VEL1] * R[E_VEL1]) -
+                  0.25 * (L[E_MOM1] * L[E_VEL2] * L[E_VEL2] + R[E_MOM1] * R[E_VEL2] * R[E_VEL2]) -
+                  0.25 * (L[E_MOM1] * L[E_VEL3] * L[E_VEL3] + R[E_MOM1] * R[E_VEL3] * R[E_VEL3]);
+    } else if (variant == 2) { /* DU :407-428 */
+        F[DENS] = 0.25 * (L[E_DENS] + R[E_DENS]) * (L[E_VEL1] + R[E_VEL1]);
+        F[MOM1] = 0.25 * (L[E_MOM1] + R[E_MOM1]) * (L[E_VEL1] + R[E_VEL1]) + 0.5 * (L[E_PRES] + R[E_PRES]);
+        F[MOM2] = 0.25 * (L[E_MOM2] + R[E_MOM2]) * (L[E_VEL1] + R[E_VEL1]);
+        F[MOM3] = 0.25 * (L[E_MOM3] + R[E_MOM3]) * (L[E_VEL1] + R[E_VEL1]);
+        F[ENER] = 0.25 * (L[E_ENER] + R[E_ENER] + L[E_PRES] + R[E_PRES]) * (L[E_VEL1] + R[E_VEL1]);
+    } else if (variant == 0) {
         F[DENS] = 0.5 * (L[E_MOM1] + R[E_MOM1]);
         F[MOM1] = 0.5 * (L[E_MOM1] * L[E_VEL1] + L[E_PRES] + R[E_MOM1] * R[E_VEL1] + R[E_PRES]);
         F[MOM2] = 0.5 * (L[E_MOM1] * L[E_VEL2] + R[E_MOM1] * R[E_VEL2]);
@@ -316,12 +390,44 @@ static void split_surface_flux(int variant, const double *L, const double *R, do
     }
 }
 
-/* splitflux.f90: volume two-point fluxes :145 (SD) :437 (KG) :669 (PI) */
+/* splitflux.f90: volume two-point fluxes :145 (SD) :543 (MO) :346 (DU) :437 (KG) :669 (PI) */
 static void split_volume_flux(int variant, const double *URef, const double *PRef, const double *U, const double *P,
                               const double *MRef, const double *M, double *Flux)
 {
     double f[NV], g[NV], h[NV];
-    if (variant == 0) {
+    if (variant == 1) { /* MO :543-622 */
+        double rhoepRef = URef[ENER] - 0.5 * URef[DENS] * (PRef[VEL1] * PRef[VEL1] + PRef[VEL2] * PRef[VEL2] + PRef[VEL3] * PRef[VEL3]) + PRef[PRES];
+        double rhoep = U[ENER] - 0.5 * U[DENS] * (P[VEL1] * P[VEL1] + P[VEL2] * P[VEL2] + P[VEL3] * P[VEL3]) + P[PRES];
+        double *F3[3] = {f, g, h};
+        for (int d = 0; d < 3; d++) {
+            double *F = F3[d];
+            double mR = URef[MOM1 + d], m = U[MOM1 + d];
+            F[DENS] = (mR + m);
+            F[MOM1] = 0.5 * (mR + m) * (PRef[VEL1] + P[VEL1]);
+            F[MOM2] = 0.5 * (mR + m) * (PRef[VEL2] + P[VEL2]);
+            F[MOM3] = 0.5 * (mR + m) * (PRef[VEL3] + P[VEL3]);
+            F[MOM1 + d] = F[MOM1 + d] + (PRef[PRES] + P[PRES]);
+            F[ENER] = (rhoepRef * PRef[VEL1 + d] + rhoep * P[VEL1 + d]) +
+                      0.5 * (mR * PRef[VEL1] + m * P[VEL1]) * (PRef[VEL1] + P[VEL1]) +
+                      0.5 * (mR * PRef[VEL2] + m * P[VEL2]) * (PRef[VEL2] + P[VEL2]) +
+                      0.5 * (mR * PRef[VEL3] + m * P[VEL3]) * (PRef[VEL3] + P[VEL3]) -
+                      0.5 * (mR * PRef[VEL1] * PRef[VEL1] + m * P[VEL1] * P[VEL1]) -
+                      0.5 * (mR * PRef[VEL2] * PRef[VEL2] + m * P[VEL2] * P[VEL2]) -
+                      0.5 * (mR * PRef[VEL3] * PRef[VEL3] + m * P[VEL3] * P[VEL3]);
+        }
+    } else if (variant == 2) { /* DU :346-402 */
+        double *F3[3] = {f, g, h};
+        for (int d = 0; d < 3; d++) {
+            double *F = F3[d];
+            double vs = PRef[VEL1 + d] + P[VEL1 + d];
+            F[DENS] = 0.5 * (URef[DENS] + U[DENS]) * vs;
+            F[MOM1] = 0.5 * (URef[MOM1] + U[MOM1]) * vs;
+            F[MOM2] = 0.5 * (URef[MOM2] + U[MOM2]) * vs;
+            F[MOM3] = 0.5 * (URef[MOM3] + U[MOM3]) * vs;
+            F[MOM1 + d] = F[MOM1 + d] + (PRef[PRES] + P[PRES]);
+            F[ENER] = 0.5 * (URef[ENER] + U[ENER] + PRef[PRES] + P[PRES]) * vs;
+        }
+    } else if (variant == 0) {
         double rhoEpRef = URef[ENER] + PRef[PRES], rhoEp = U[ENER] + P[PRES];
         f[DENS] = (URef[MOM1] + U[MOM1]);
         f[MOM1] = (URef[MOM1] * PRef[VEL1] + PRef[PRES] + U[MOM1] * P[VEL1] + P[PRES]);
@@ -371,7 +477,7 @@ static void split_volume_flux(int variant, const double *URef, const double *PRe
 }
 
 /* ------------------------------------------------------------------------------------------------ */
-/* riemann.f90: solvers :707 LF, :738 HLLC, :809 Roe, :885 RoeEntropyFix */
+/* riemann.f90: solvers :707 LF, :738 HLLC, :809 Roe, :885 RoeEntropyFix, :994 RoeL2, :1075 HLL, :1126 HLLE, :1175 HLLEM, :1239 FluxAverage */
 static void roe_averages(const double *L, const double *R, double kappa, double *RoeVel, double *RoeH, double *Roec, double *absVel)
 {
     double H_L = (L[E_ENER] + L[E_PRES]) * L[E_SRHO];
@@ -396,6 +502,38 @@ static void riemann_solver(const dgo_config *c, double *F, const double *F_L, co
         } else {
             split_surface_flux(c->splitDG, L, R, F);
             for (int v = 0; v < NV; v++) F[v] = F[v] - 0.5 * LambdaMax * (R[v] - L[v]);
+        }
+        return;
+    }
+    if (c->riemann == 9) { /* Riemann_FluxAverage :1239 (SPLIT_DG only) */
+        split_surface_flux(c->splitDG, L, R, F);
+        return;
+    }
+    if (c->riemann == 4 || c->riemann == 6 || c->riemann == 7) { /* HLL :1075, HLLE :1126, HLLEM :1175 (non-split builds only) */
+        double RoeVel[3], RoeH, Roec, absVel;
+        roe_averages(L, R, kappa, RoeVel, &RoeH, &Roec, &absVel);
+        double Ssl, Ssr;
+        if (c->riemann == 4) { Ssl = RoeVel[0] - Roec; Ssr = RoeVel[0] + Roec; }
+        else {
+            double beta = sqrt(0.5 * (kappa - 1.) / kappa);
+            double cL = sqrt(kappa * L[E_PRES] * L[E_SRHO]), cR = sqrt(kappa * R[E_PRES] * R[E_SRHO]);
+            Ssl = fmin(fmin(RoeVel[0] - Roec, L[E_VEL1] - beta * cL), 0.);
+            Ssr = fmax(fmax(RoeVel[0] + Roec, R[E_VEL1] + beta * cR), 0.);
+        }
+        if (Ssl >= 0.) { for (int v = 0; v < NV; v++) F[v] = F_L[v]; }
+        else if (Ssr <= 0.) { for (int v = 0; v < NV; v++) F[v] = F_R[v]; }
+        else if (c->riemann != 7) {
+            for (int v = 0; v < NV; v++) F[v] = (Ssr * F_L[v] - Ssl * F_R[v] + Ssl * Ssr * (R[v] - L[v])) / (Ssr - Ssl);
+        } else {
+            double RoeDens = sqrt(L[E_DENS] * R[E_DENS]);
+            double delta = Roec / (Roec + fabs(0.5 * (Ssl + Ssr)));
+            double A2 = (R[E_DENS] - L[E_DENS]) - (R[E_PRES] - L[E_PRES]) / (Roec * Roec);
+            double A3 = RoeDens * (R[E_VEL2] - L[E_VEL2]), A4 = RoeDens * (R[E_VEL3] - L[E_VEL3]);
+            double r2[5] = {1., RoeVel[0], RoeVel[1], RoeVel[2], 0.5 * absVel};
+            double r3[5] = {0., 0., 1., 0., RoeVel[1]};
+            double r4[5] = {0., 0., 0., 1., RoeVel[2]};
+            for (int v = 0; v < NV; v++)
+                F[v] = (Ssr * F_L[v] - Ssl * F_R[v] + Ssl * Ssr * (R[v] - L[v] - delta * (r2[v] * A2 + r3[v] * A3 + r4[v] * A4))) / (Ssr - Ssl);
         }
         return;
     }
@@ -433,10 +571,14 @@ static void riemann_solver(const dgo_config *c, double *F, const double *F_L, co
     double r4[5] = {0., 0., 0., 1., RoeVel[2]};
     double r5[5] = {1., a[4], RoeVel[1], RoeVel[2], RoeH + RoeVel[0] * Roec};
     double Alpha[5];
-    if (c->riemann == 1) { /* Roe :809-877 */
+    if (c->riemann == 1 || c->riemann == 2) { /* Roe :809-877, RoeL2 :994-1070 */
         double dU[6];
         for (int v = 0; v < NV; v++) dU[v] = R[v] - L[v];
         dU[5] = dU[4] - (dU[2] - RoeVel[1] * dU[0]) * RoeVel[1] - (dU[3] - RoeVel[2] * dU[0]) * RoeVel[2];
+        if (c->riemann == 2) { /* low Mach number fix :1044-1046 */
+            double Ma_loc = sqrt(absVel) / (Roec * sqrt(kappa));
+            dU[1] = dU[1] * Ma_loc; dU[2] = dU[2] * Ma_loc; dU[3] = dU[3] * Ma_loc;
+        }
         Alpha[2] = dU[2] - RoeVel[1] * dU[0];
         Alpha[3] = dU[3] - RoeVel[2] * dU[0];
         Alpha[1] = (kappa - 1.) / (Roec * Roec) * (dU[0] * (RoeH - RoeVel[0] * RoeVel[0]) - dU[5] + RoeVel[0] * dU[1]);
@@ -612,7 +754,7 @@ static void lifting_br1_fillflux(dgo *s)
             const double *t2 = &c->TangVec2[IDX_FACE(s, 3, 0, p, q, sd)];
             double Pb[NP], Fl[NL];
             get_boundary_state(c, bct, Pb, Pm, &c->RefStatePrim[NP * (bcs > 0 ? bcs - 1 : 0)], nv, t1, t2);
-            if (bct == 2) {
+            if (is_riemann_bc(bct)) {
                 for (int v = 0; v < NL; v++) Fl[v] = 0.5 * (Pm[PRIM_LIFT[v]] + Pb[PRIM_LIFT[v]]);
             } else if (bct == 3 || bct == 4) {
                 Fl[LIFT_DENS] = Pb[DENS]; Fl[LIFT_VEL1] = Fl[LIFT_VEL2] = Fl[LIFT_VEL3] = 0.; Fl[LIFT_TEMP] = Pb[TEMP];
@@ -780,7 +922,7 @@ static int fill_flux(dgo *s)
                 int bct = c->BCSides[0 + 2 * sd], bcs = c->BCSides[1 + 2 * sd];
                 double Pb[NP];
                 err |= get_boundary_state(c, bct, Pb, Pm, &c->RefStatePrim[NP * (bcs > 0 ? bcs - 1 : 0)], nv, t1, t2);
-                if (bct == 2) {
+                if (is_riemann_bc(bct)) {
                     double Um[NV], Ub[NV];
                     prim_to_cons(Pm, Um, kappa);
                     prim_to_cons(Pb, Ub, kappa);
@@ -794,7 +936,7 @@ static int fill_flux(dgo *s)
                         for (int v = 0; v < NV; v++)
                             F[v] = F[v] + 0.5 * (nv[0] * (fL[v] + fR[v]) + nv[1] * (gL[v] + gR[v]) + nv[2] * (hL[v] + hR[v]));
                     }
-                } else if (bct == 3 || bct == 4 || bct == 9) {
+                } else if (is_wall_bc(bct)) {
                     F[DENS] = 0.;
                     for (int d = 0; d < 3; d++) F[MOM1 + d] = Pb[PRES] * nv[d];
                     F[ENER] = 0.;
@@ -812,6 +954,37 @@ static int fill_flux(dgo *s)
                                 gzf[v] = B[2][0] * gxm[v] + B[2][1] * gym[v] + B[2][2] * gzm[v];
                             }
                             eval_diff_flux3d(Pb, gxf, gyf, gzf, fd, gd, hd, mu, la);
+                        } else if (bct == 91) { /* :716-781 slip wall, version 2 */
+                            double B[3][3], gf[3][NL];
+                            const double *gm_[3] = {gxm, gym, gzm};
+                            const double *tv[3] = {nv, t1, t2};
+                            B[0][0] = 1. - nv[0] * nv[0]; B[1][1] = 1. - nv[1] * nv[1]; B[2][2] = 1. - nv[2] * nv[2];
+                            B[0][1] = -nv[0] * nv[1]; B[0][2] = -nv[0] * nv[2]; B[2][1] = -nv[2] * nv[1];
+                            B[1][0] = B[0][1]; B[2][0] = B[0][2]; B[1][2] = B[2][1];
+                            for (int d = 0; d < 3; d++) {
+                                gf[d][LIFT_DENS] = 0.; /* not set by the reference; unused by the viscous flux */
+                                gf[d][LIFT_TEMP] = B[d][0] * gxm[LIFT_TEMP] + B[d][1] * gym[LIFT_TEMP] + B[d][2] * gzm[LIFT_TEMP];
+                            }
+                            /* first: gradients (x,y,z) of the wall-aligned velocities w = (normal, tang1, tang2) */
+                            double gw[3][3]; /* [dir x,y,z][w] */
+                            for (int d = 0; d < 3; d++)
+                                for (int w = 0; w < 3; w++)
+                                    gw[d][w] = tv[w][0] * gm_[d][LIFT_VEL1] + tv[w][1] * gm_[d][LIFT_VEL2] + tv[w][2] * gm_[d][LIFT_VEL3];
+                            /* second: derivatives along the wall-aligned directions a = (n,t1,t2); boundary conditions */
+                            double ga[3][3]; /* [a][w] */
+                            for (int a = 0; a < 3; a++)
+                                for (int w = 0; w < 3; w++)
+                                    ga[a][w] = tv[a][0] * gw[0][w] + tv[a][1] * gw[1][w] + tv[a][2] * gw[2][w];
+                            ga[0][1] = 0.; ga[0][2] = 0.; ga[1][0] = 0.; ga[2][0] = 0.;
+                            /* third: back to x/y/z derivatives */
+                            for (int d = 0; d < 3; d++)
+                                for (int w = 0; w < 3; w++)
+                                    gw[d][w] = nv[d] * ga[0][w] + t1[d] * ga[1][w] + t2[d] * ga[2][w];
+                            /* fourth: back to the Cartesian velocity components */
+                            for (int d = 0; d < 3; d++)
+                                for (int x = 0; x < 3; x++)
+                                    gf[d][LIFT_VEL1 + x] = nv[x] * gw[d][0] + t1[x] * gw[d][1] + t2[x] * gw[d][2];
+                            eval_diff_flux3d(Pb, gf[0], gf[1], gf[2], fd, gd, hd, mu, la);
                         } else {
                             eval_diff_flux3d(Pb, gxm, gym, gzm, fd, gd, hd, mu, la);
                             if (bct == 3) fd[ENER] = gd[ENER] = hd[ENER] = 0.;

@@ -113,5 +113,37 @@ def channel_case(E=4, N=5, nProcs=1, myRank=0, **kw):
     return c, U0
 
 
+# uniform subsonic duct flow and the matching total conditions (BC types 23/24/25/27)
+DUCT_KAPPA, DUCT_R = 1.4, 287.058
+DUCT_RHO, DUCT_U, DUCT_P = 1.2, 60.0, 1.0e5
+DUCT_MACH = DUCT_U / np.sqrt(DUCT_KAPPA * DUCT_P / DUCT_RHO)
+DUCT_T = DUCT_P / (DUCT_RHO * DUCT_R)
+DUCT_TT = DUCT_T * (1.0 + 0.5 * (DUCT_KAPPA - 1.0) * DUCT_MACH ** 2)
+DUCT_PT = DUCT_P * (1.0 + 0.5 * (DUCT_KAPPA - 1.0) * DUCT_MACH ** 2) ** (DUCT_KAPPA / (DUCT_KAPPA - 1.0))
+DUCT_REFS = ((DUCT_RHO, DUCT_U, 0.0, 0.0, DUCT_P),   # 1: the uniform flow itself (Dirichlet state / outflow pressure)
+             (1.0, DUCT_MACH, 0.0, 0.0, 1.0),        # 2: type 23, outflow Mach number in the second slot
+             (DUCT_TT, 0.0, 0.0, 0.0, DUCT_PT))      # 3: type 27 (Tt, alpha, beta, -, pt)
+
+
+def duct_case(inflow, outflow, wall, N=3, parabolic=True, node_type=bs.NODETYPE_G, split=None, riemann="Roe",
+              nelems=(3, 2, 2), deform=0.0, nProcs=1, myRank=0):
+    """Duct along x: x- inflow, x+ outflow, y+- walls, z periodic (local-side order z-, y-, x+, y+, x-, z+).
+    Returns the case, the uniform state and a sheared, perturbed state."""
+    h = ms.make_box_mesh(nelems, bctype=["periodic", wall, outflow, wall, inflow, "periodic"], NGeo=2, deform=deform)
+    eos = eq.Eos(kappa=DUCT_KAPPA, R=DUCT_R, Pr=0.72, mu0=1e-3 if parabolic else 0.0)
+    c = cs.build_case(h, N, node_type, split=split, riemann=riemann, parabolic=parabolic, eos=eos, refstates=DUCT_REFS,
+                      nProcs=nProcs, myRank=myRank)
+    x = c.geo["Elem_xGP"]
+    base = np.array([DUCT_RHO, DUCT_U, 0.0, 0.0, DUCT_P, DUCT_T])
+    U_uniform = eq.ini_refstate(x, base, eos)
+    prim = np.broadcast_to(base, x.shape[:-1] + (6,)).copy()
+    prim[..., 0] *= 1.0 + 0.03 * np.sin(2.0 * x[..., 0]) * np.cos(x[..., 2] * np.pi)
+    prim[..., 1] *= 1.0 + 0.2 * np.sin(2.0 * x[..., 1]) * np.cos(x[..., 0])
+    prim[..., 2] = 5.0 * np.sin(x[..., 0] + x[..., 1])
+    prim[..., 3] = 3.0 * np.cos(np.pi * x[..., 2]) * np.sin(x[..., 0])
+    prim[..., 4] *= 1.0 + 0.02 * np.cos(x[..., 0]) * np.cos(x[..., 1])
+    return c, U_uniform, eq.prim_to_cons(prim, eos.kappa)
+
+
 def rel_l2(a, b):
     return float(np.sqrt(np.sum((a - b) ** 2)) / max(np.sqrt(np.sum(b ** 2)), 1e-300))

@@ -89,7 +89,8 @@ def test_tgv_curved_split_pi(N):
     _compare_rhs_and_steps(c, U0)
 
 
-@pytest.mark.parametrize("split,riemann", [("SD", "LF"), ("KG", "Roe"), ("PI", "LF"), ("PI", "Roe")])
+@pytest.mark.parametrize("split,riemann", [("SD", "LF"), ("KG", "Roe"), ("PI", "LF"), ("PI", "Roe"), ("MO", "LF"), ("DU", "RoeL2"),
+                                           ("PI", "FluxAverage"), ("SD", "RoeEntropyFix"), ("MO", "RoeL2"), ("DU", "FluxAverage")])
 def test_split_variants(split, riemann):
     c, U0 = cases.tgv_box_case(E=3, N=4, NGeo=2, deform=0.05, perturb=1e-3, split=split, riemann=riemann)
     _compare_rhs_and_steps(c, U0)
@@ -100,7 +101,7 @@ def test_split_euler():
     _compare_rhs_and_steps(c, U0)
 
 
-@pytest.mark.parametrize("riemann", ["LF", "Roe", "RoeEntropyFix", "HLLC"])
+@pytest.mark.parametrize("riemann", ["LF", "Roe", "RoeL2", "RoeEntropyFix", "HLL", "HLLC", "HLLE", "HLLEM"])
 def test_shu_vortex_euler_gauss(riemann):
     c, U0 = cases.shu_vortex_case(E=4, N=3, riemann=riemann)
     _compare_rhs_and_steps(c, U0)
@@ -115,6 +116,31 @@ def test_shu_vortex_config1():
 def test_weak_form_navier_stokes(node_type):
     c, U0 = cases.tgv_box_case(E=3, N=4, NGeo=2, deform=0.05, perturb=1e-3, split=None, riemann="Roe", node_type=node_type)
     _compare_rhs_and_steps(c, U0)
+
+
+@pytest.mark.parametrize("riemann", ["HLL", "HLLE", "HLLEM", "HLLC"])
+def test_hll_family_supersonic(riemann):
+    """Mach 2.5 stream: exercises the one-sided (Ssl >= 0) branches of the HLL-type solvers."""
+    from galaexi_b200.host import basis as bs, case as cs, equation as eq, mesh as ms
+    h = ms.make_box_mesh((3, 2, 2), NGeo=2, deform=0.03)
+    c = cs.build_case(h, 3, bs.NODETYPE_G, split=None, riemann=riemann, parabolic=False, eos=eq.Eos(kappa=1.4, R=1.0),
+                      refstates=((1.0, 3.0, 0.0, 0.0, 1.0),))
+    x = c.geo["Elem_xGP"]
+    prim = np.broadcast_to(c.RefStatePrim[0], x.shape[:-1] + (6,)).copy()
+    prim[..., 0] *= 1.0 + 0.05 * np.sin(np.pi * x[..., 0]) * np.cos(np.pi * x[..., 1])
+    prim[..., 2] = 0.8 * np.sin(np.pi * x[..., 1]) * np.cos(np.pi * x[..., 2])
+    prim[..., 4] *= 1.0 + 0.05 * np.cos(np.pi * x[..., 0]) * np.cos(np.pi * x[..., 2])
+    _compare_rhs_and_steps(c, eq.prim_to_cons(prim, 1.4))
+
+
+@pytest.mark.parametrize("inflow,outflow,wall", [((2, 1), (24, 1), (9, 0)), ((2, 1), (25, 1), (91, 0)), ((2, 1), (23, 2), (9, 0)),
+                                                   ((27, 3), (24, 1), (91, 0))])
+@pytest.mark.parametrize("form", ["weak", "split"])
+def test_inflow_outflow_slip_bcs(inflow, outflow, wall, form):
+    """BC types 23/24/25/27 (getboundaryflux.f90:361-474) and both slip walls 9/91 on a curved duct, Navier-Stokes."""
+    kw = dict(node_type="GAUSS-LOBATTO", split="PI", riemann="RoeEntropyFix") if form == "split" else dict(riemann="Roe")
+    c, _, U1 = cases.duct_case(inflow, outflow, wall, N=4, deform=0.04, **kw)
+    _compare_rhs_and_steps(c, U1)
 
 
 def test_sutherland_viscosity():

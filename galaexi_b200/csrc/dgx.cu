@@ -12,6 +12,7 @@
 #include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -21,6 +22,10 @@
 #include "dgx_launch.h"
 
 using namespace dgx;
+
+#ifndef DGX_DEFAULT_FLAGS
+#define DGX_DEFAULT_FLAGS 0  // see KParams::flags; chosen from the sweep in profiles/
+#endif
 
 namespace dgx {
 const KernelTable* kernel_table(int N, int nodeType) {
@@ -410,6 +415,7 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
     P.U = h->U; P.Ut = h->Ut; P.Ut_tmp = h->Ut_tmp; P.gradU = h->gradU;
     P.gm = h->gm; P.gs = h->gs; P.Flux = h->Flux; P.errFlag = h->errFlag;
     P.elemList = nullptr; P.nList = 0;
+    P.flags = getenv("DGX_FLAGS") ? atoi(getenv("DGX_FLAGS")) : DGX_DEFAULT_FLAGS;
     // benign state on faces that are never written (slave side of BC sides), cf. dg.f90:118-121
     {
         std::vector<double> init(5 * nFace, 0.0);

@@ -10,6 +10,43 @@ namespace {
 constexpr int n = DGX_N + 1;
 constexpr int n3 = n * n * n;
 
+// k_volsurf2 is instantiated per split variant (SPLIT_DG 0..4), like the reference compiles one variant in
+template <int VAR>
+cudaError_t setup_vs2_one() {
+    cudaError_t e;
+    e = cudaFuncSetAttribute(k_volsurf2<n, 0, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vs2_smem_bytes<n>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_volsurf2<n, 1, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vs2_smem_bytes<n>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_volsurf2<n, 0, VAR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_volsurf2<n, 1, VAR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+}
+template <int VAR>
+cudaError_t setup_vs2() {
+    cudaError_t e = setup_vs2_one<VAR>();
+    if (e != cudaSuccess) return e;
+    if constexpr (VAR < 4) return setup_vs2<VAR + 1>();
+    return e;
+}
+template <int MODE, int VAR>
+void launch_vs2(const KParams& P, double mRKA, double b_dt, int nb, cudaStream_t s) {
+    if (P.splitDG == VAR) {
+        static int resident = 0;  // CTAs of one resident wave (prefetch distance)
+        if (!resident) {
+            int dev = 0, sms = 148, per = 1;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_volsurf2<n, MODE, VAR>, vs2_threads<n>(), vs2_smem_bytes<n>());
+            resident = sms * (per > 0 ? per : 1);
+        }
+        const int grid = (nb + vs2_epb<n>() - 1) / vs2_epb<n>();
+        k_volsurf2<n, MODE, VAR><<<grid, vs2_threads<n>(), vs2_smem_bytes<n>(), s>>>(P, nb, mRKA, b_dt, resident);
+        return;
+    }
+    if constexpr (VAR < 4) launch_vs2<MODE, VAR + 1>(P, mRKA, b_dt, nb, s);
+}
+
 template <int NT>
 struct L {
     static int setup() {
@@ -20,15 +57,7 @@ struct L {
         if (e != cudaSuccess) return (int)e;
         e = cudaFuncSetAttribute(k_volsurf<n, NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)volsurf_smem_bytes<n>());
         if (e != cudaSuccess) return (int)e;
-        if (NT == 2) {
-            e = cudaFuncSetAttribute(k_volsurf2<n, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vs2_smem_bytes<n>());
-            if (e != cudaSuccess) return (int)e;
-            e = cudaFuncSetAttribute(k_volsurf2<n, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vs2_smem_bytes<n>());
-            if (e != cudaSuccess) return (int)e;
-            e = cudaFuncSetAttribute(k_volsurf2<n, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            if (e != cudaSuccess) return (int)e;
-            e = cudaFuncSetAttribute(k_volsurf2<n, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        }
+        if (NT == 2) e = setup_vs2<0>();
         return (int)e;
     }
     static void prolong(const KParams& P, int nb, cudaStream_t s) {
@@ -56,9 +85,8 @@ struct L {
         // split form on Gauss-Lobatto nodes: register-blocked kernel (DGX_VOLSURF=1 selects the thread-per-node one)
         static const bool v1 = getenv("DGX_VOLSURF") && atoi(getenv("DGX_VOLSURF")) == 1;
         if (NT == 2 && P.splitDG >= 0 && !v1) {
-            const int grid = (nb + vs2_epb<n>() - 1) / vs2_epb<n>();
-            if (mode == 0) k_volsurf2<n, 0><<<grid, vs2_threads<n>(), vs2_smem_bytes<n>(), s>>>(P, nb, mRKA, b_dt);
-            else k_volsurf2<n, 1><<<grid, vs2_threads<n>(), vs2_smem_bytes<n>(), s>>>(P, nb, mRKA, b_dt);
+            if (mode == 0) launch_vs2<0, 0>(P, mRKA, b_dt, nb, s);
+            else launch_vs2<1, 0>(P, mRKA, b_dt, nb, s);
             return;
         }
         if (mode == 0) k_volsurf<n, NT, 0><<<nb, n3, volsurf_smem_bytes<n>(), s>>>(P, mRKA, b_dt);

@@ -57,6 +57,8 @@ struct KParams {
     const int* elemList;  // optional indirection (MPI-boundary / inner element lists), or nullptr
     int nList;
     int* errFlag;
+    int flags;  // tuning switches (DGX_FLAGS): 1 lifting: L2 prefetch of own later-phase data; 2 lifting: L2 prefetch of the element
+                // a resident wave ahead; 4 / 8: the same two for k_volsurf2
 };
 
 enum { ZETA_MINUS = 1, ETA_MINUS = 2, XI_PLUS = 3, ETA_PLUS = 4, XI_MINUS = 5, ZETA_PLUS = 6 };
@@ -221,7 +223,18 @@ __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting
     const int* e2s = P.E2S + 18 * e;
     const int k = t / n2, j = (t - k * n2) / n, i = t - k * n2 - j * n;
     const int tid_ = Tile<n>::idx(i, j, k);
-    (void)lookahead;
+    // L2 prefetches (fire and forget, no registers): the metrics / Jacobian this CTA reads two barriers from now, and the
+    // volume data of the element that takes this CTA's place once it retires (one resident wave ahead in the grid)
+    if (P.flags & 1) {
+        prefetch_block(P.metrics + (size_t)e * 9 * n3, sizeof(double) * 9 * n3, t, n3);
+        prefetch_block(P.sJ + (size_t)e * n3, sizeof(double) * n3, t, n3);
+    }
+    if ((P.flags & 2) && (int)blockIdx.x + lookahead < (P.elemList ? P.nList : P.nElems)) {
+        const int en = P.elemList ? P.elemList[blockIdx.x + lookahead] : (int)blockIdx.x + lookahead;
+        prefetch_block(P.U + (size_t)en * 5 * n3, sizeof(double) * 5 * n3, t, n3);
+        prefetch_block(P.metrics + (size_t)en * 9 * n3, sizeof(double) * 9 * n3, t, n3);
+        prefetch_block(P.sJ + (size_t)en * n3, sizeof(double) * n3, t, n3);
+    }
     // 1. node: primitive lifting variables into the tile
     {
         const double* U = P.U + (size_t)e * 5 * n3;

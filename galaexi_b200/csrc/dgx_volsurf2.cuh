@@ -40,10 +40,68 @@ __device__ __forceinline__ int line_idx(int d, int l, int c1, int c2) {
     return Tile<n>::idx(i, j, k);
 }
 
+// Two-point flux of one node pair for split variant VAR (compile-time: no variant branches in the sweeps, and the dead
+// variants stay out of the instruction cache). a, b: node record (6) followed by the metric triple of the direction (3).
+// Record layouts (vs2_record): PI/KG: {rho/8, u, v, w, p/2, H or e}  -- the constant factors of splitflux.f90:437-501 /
+// :669-730 folded into the operands (exact: powers of two); SD/MO/DU: {rho, u, v, w, p, rhoE}.
+template <int VAR>
+__device__ __forceinline__ void vs2_record(double* rec, const double* Uc, const double* Pr) {
+    if (VAR >= 3) {
+        rec[0] = 0.125 * Pr[DENS]; rec[1] = Pr[VEL1]; rec[2] = Pr[VEL2]; rec[3] = Pr[VEL3]; rec[4] = 0.5 * Pr[PRES];
+        rec[5] = split_sixth(VAR, Uc, Pr);
+    } else {
+        rec[0] = Pr[DENS]; rec[1] = Pr[VEL1]; rec[2] = Pr[VEL2]; rec[3] = Pr[VEL3]; rec[4] = Pr[PRES]; rec[5] = Uc[ENER];
+    }
+}
+template <int VAR>
+__device__ __forceinline__ void vs2_pair_flux(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ F) {
+    double Ms[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) Ms[c] = a[6 + c] + b[6 + c];
+    if (VAR >= 3) {
+        const double us = a[1] + b[1], vs = a[2] + b[2], ws = a[3] + b[3];
+        const double dot = Ms[0] * us + Ms[1] * vs + Ms[2] * ws;  // 2 x contravariant velocity sum
+        const double q = (a[0] + b[0]) * dot;                    // 1/4 {rho}_s * 1/2 dot
+        const double ph = a[4] + b[4];                            // 1/2 p_s
+        F[DENS] = q + q;
+        F[MOM1] = q * us + Ms[0] * ph;
+        F[MOM2] = q * vs + Ms[1] * ph;
+        F[MOM3] = q * ws + Ms[2] * ph;
+        if (VAR == 3) F[ENER] = q * (a[5] + b[5]) + ph * (0.5 * dot);
+        else F[ENER] = q * (a[5] + b[5]);
+    } else {
+        split_volume_flux(VAR, a, b, Ms, F);
+    }
+}
+// acc += w * F#(a,b) for a pair used by one end point only (the other end lives in another thread)
+template <int VAR>
+__device__ __forceinline__ void vs2_pair_acc(const double* __restrict__ a, const double* __restrict__ b, double w, double* __restrict__ acc) {
+    if (VAR >= 3) {
+        double Ms[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) Ms[c] = a[6 + c] + b[6 + c];
+        const double us = a[1] + b[1], vs = a[2] + b[2], ws = a[3] + b[3];
+        const double dot = Ms[0] * us + Ms[1] * vs + Ms[2] * ws;
+        const double wq = w * ((a[0] + b[0]) * dot);
+        const double wp = w * (a[4] + b[4]);
+        acc[DENS] = fma(wq, 2.0, acc[DENS]);
+        acc[MOM1] = fma(wp, Ms[0], fma(wq, us, acc[MOM1]));
+        acc[MOM2] = fma(wp, Ms[1], fma(wq, vs, acc[MOM2]));
+        acc[MOM3] = fma(wp, Ms[2], fma(wq, ws, acc[MOM3]));
+        acc[ENER] = fma(wq, a[5] + b[5], acc[ENER]);
+        if (VAR == 3) acc[ENER] = fma(wp, 0.5 * dot, acc[ENER]);
+    } else {
+        double F[5];
+        vs2_pair_flux<VAR>(a, b, F);
+#pragma unroll
+        for (int v = 0; v < 5; v++) acc[v] += w * F[v];
+    }
+}
+
 // One flux-differencing sweep of direction d for the half line (c1,c2,h): acc[m][v] = sum_l DVolSurf(l,a_m) F#(a_m,l)
-template <int n>
+template <int n, int VAR>
 __device__ __forceinline__ void vs2_sweep(const double* __restrict__ R, const double* __restrict__ Mx, const double* __restrict__ Dv, int d,
-                                          int c1, int c2, int h, int var, double (&acc)[(n + 1) / 2][5]) {
+                                          int c1, int c2, int h, double (&acc)[(n + 1) / 2][5]) {
     constexpr int SEG = (n + 1) / 2, SL = Tile<n>::SLOT;
     const int a0 = h * SEG, cnt = h ? n - SEG : SEG;
     const int f0 = h ? 0 : SEG, fcnt = n - cnt;
@@ -62,19 +120,12 @@ __device__ __forceinline__ void vs2_sweep(const double* __restrict__ R, const do
 #pragma unroll
     for (int m = 0; m < SEG; m++) {
         if (m < cnt) {
-            double Ms[3], F[5];
-#pragma unroll
-            for (int c = 0; c < 3; c++) Ms[c] = own[m][6 + c] + own[m][6 + c];
-            split_volume_flux(var, own[m], own[m], Ms, F);
-            const double w = Dv[(a0 + m) + n * (a0 + m)];
-#pragma unroll
-            for (int v = 0; v < 5; v++) acc[m][v] += w * F[v];
+            vs2_pair_acc<VAR>(own[m], own[m], Dv[(a0 + m) + n * (a0 + m)], acc[m]);
 #pragma unroll
             for (int m2 = m + 1; m2 < SEG; m2++) {
                 if (m2 < cnt) {
-#pragma unroll
-                    for (int c = 0; c < 3; c++) Ms[c] = own[m][6 + c] + own[m2][6 + c];
-                    split_volume_flux(var, own[m], own[m2], Ms, F);
+                    double F[5];
+                    vs2_pair_flux<VAR>(own[m], own[m2], F);
                     const double w1 = Dv[(a0 + m2) + n * (a0 + m)], w2 = Dv[(a0 + m) + n * (a0 + m2)];
 #pragma unroll
                     for (int v = 0; v < 5; v++) { acc[m][v] += w1 * F[v]; acc[m2][v] += w2 * F[v]; }
@@ -93,22 +144,13 @@ __device__ __forceinline__ void vs2_sweep(const double* __restrict__ R, const do
 #pragma unroll
         for (int c = 0; c < 3; c++) ot[6 + c] = Mx[c * SL + id];
 #pragma unroll
-        for (int m = 0; m < SEG; m++) {
-            if (m < cnt) {
-                double Ms[3], F[5];
-#pragma unroll
-                for (int c = 0; c < 3; c++) Ms[c] = own[m][6 + c] + ot[6 + c];
-                split_volume_flux(var, own[m], ot, Ms, F);
-                const double w = Dv[b + n * (a0 + m)];
-#pragma unroll
-                for (int v = 0; v < 5; v++) acc[m][v] += w * F[v];
-            }
-        }
+        for (int m = 0; m < SEG; m++)
+            if (m < cnt) vs2_pair_acc<VAR>(own[m], ot, Dv[b + n * (a0 + m)], acc[m]);
     }
 }
 
-template <int n, int MODE>
-__global__ void __launch_bounds__(vs2_threads<n>(), (n >= 8 ? 3 : 2)) k_volsurf2(const __grid_constant__ KParams P, int nWork, double mRKA, double b_dt) {
+template <int n, int MODE, int VAR>
+__global__ void __launch_bounds__(vs2_threads<n>(), (n >= 8 ? 3 : 2)) k_volsurf2(const __grid_constant__ KParams P, int nWork, double mRKA, double b_dt, int lookahead) {
     constexpr int n2 = n * n, n3 = n2 * n, SEG = (n + 1) / 2, SL = Tile<n>::SLOT, T = 2 * n2, EPB = vs2_epb<n>();
     extern __shared__ double smem[];
     const int le = threadIdx.x / T, tid = threadIdx.x - le * T;
@@ -124,12 +166,29 @@ __global__ void __launch_bounds__(vs2_threads<n>(), (n >= 8 ? 3 : 2)) k_volsurf2
     const int a0 = h * SEG, cnt = h ? n - SEG : SEG;
     const Eos eos = P.eos;
     const bool par = P.parabolic != 0;
-    const int var = P.splitDG;
     const double* __restrict__ Dh = P.D_Hat_T;  // uniform index only (constant bank)
     const double* __restrict__ Dv = P.DVolSurf;
     const double* __restrict__ gU_e = P.U + (size_t)e * 5 * n3;
     const double* __restrict__ gM_e = P.metrics + (size_t)e * 9 * n3;
 
+    // L2 prefetches (no registers): data this CTA reads several barriers from now (zeta metrics, Jacobian, Ut_tmp, face
+    // fluxes), and the P0 data of the element that replaces this CTA when it retires (one resident wave ahead)
+    if (live && (P.flags & 4)) {
+        prefetch_block(gM_e + (size_t)6 * n3, sizeof(double) * 3 * n3, tid, T);
+        prefetch_block(P.sJ + (size_t)e * n3, sizeof(double) * n3, tid, T);
+        if (MODE == 1) prefetch_block(P.Ut_tmp + (size_t)e * 5 * n3, sizeof(double) * 5 * n3, tid, T);
+        constexpr int LPS = (5 * n2 * 8 + 127) / 128;  // 128-byte lines per side of the flux array
+        if (tid < 6 * LPS) {
+            const int side = __ldg(&P.E2S[18 * e + 3 * (tid / LPS)]) - 1;
+            prefetch_l2(reinterpret_cast<const char*>(P.Flux + (size_t)side * 5 * n2) + (tid % LPS) * 128);
+        }
+    }
+    if ((P.flags & 8) && we + lookahead * EPB < nWork) {
+        const int en = P.elemList ? P.elemList[we + lookahead * EPB] : we + lookahead * EPB;
+        prefetch_block(P.U + (size_t)en * 5 * n3, sizeof(double) * 5 * n3, tid, T);
+        prefetch_block(P.metrics + (size_t)en * 9 * n3, sizeof(double) * 6 * n3, tid, T);
+        if (par) prefetch_block(P.gradU + (size_t)en * 12 * n3, sizeof(double) * 12 * n3, tid, T);
+    }
     // ---- P0: point-wise. All global reads of the phase are issued before the first use (one DRAM round trip per CTA
     // instead of one per node): lifted gradients by 8-byte cp.async straight into slots 0..11 at the thread's own nodes
     // (no registers held), state and metrics into registers. The viscous fluxes then overwrite the gradients in place.
@@ -165,8 +224,7 @@ __global__ void __launch_bounds__(vs2_threads<n>(), (n >= 8 ? 3 : 2)) k_volsurf2
                 const int id = Tile<n>::idx(c1, c2, a0 + m);
                 double Pr[6];
                 cons_to_prim(Pr, Uc[m], eos);
-                Rec[m][0] = Pr[DENS]; Rec[m][1] = Pr[VEL1]; Rec[m][2] = Pr[VEL2]; Rec[m][3] = Pr[VEL3]; Rec[m][4] = Pr[PRES];
-                Rec[m][5] = split_sixth(var, Uc[m], Pr);
+                vs2_record<VAR>(Rec[m], Uc[m], Pr);
 #pragma unroll
                 for (int c = 0; c < 6; c++) S[(12 + c) * SL + id] = M[m][c];  // M_xi -> slots 12..14, M_eta -> 15..17
                 if (par) {
@@ -209,7 +267,7 @@ __global__ void __launch_bounds__(vs2_threads<n>(), (n >= 8 ? 3 : 2)) k_volsurf2
                     const double dz = Dh[l + n * k];
                     const int idx_ = Tile<n>::idx(l, c2, k), idy = Tile<n>::idx(c1, l, k);
 #pragma unroll
-                    for (int v = 0; v < 4; v++) UtV[m][v] += dx * S[v * SL + idx_] + dz * hz[v] + dy * S[(4 + v) * SL + idy];
+                    for (int v = 0; v < 4; v++) UtV[m][v] = fma(dy, S[(4 + v) * SL + idy], fma(dz, hz[v], fma(dx, S[v * SL + idx_], UtV[m][v])));
                 }
             }
         }
@@ -252,7 +310,7 @@ __global__ void __launch_bounds__(vs2_threads<n>(), (n >= 8 ? 3 : 2)) k_volsurf2
             // lane -> line mapping: xi lines take (j,k) = (q/n, q%n), eta (i,k) and zeta (i,j) = (q%n, q/n): conflict-free
             const int l1 = (d == 0) ? c2 : c1, l2 = (d == 0) ? c1 : c2;
             double acc[SEG][5];
-            vs2_sweep<n>(S + 4 * SL, S + (d == 1 ? 15 : 12) * SL, Dv, d, l1, l2, h, var, acc);
+            vs2_sweep<n, VAR>(S + 4 * SL, S + (d == 1 ? 15 : 12) * SL, Dv, d, l1, l2, h, acc);
 #pragma unroll
             for (int m = 0; m < SEG; m++) {
                 if (m < cnt) {

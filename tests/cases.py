@@ -78,7 +78,9 @@ def naca_case(N=3, nProcs=1, myRank=0, **kw):
     h = load_mesh("naca_mesh.npz")
     eos = eq.Eos(kappa=1.4, R=287.058, Pr=0.72, mu0=0.0002)
     args = dict(split=None, riemann="RoeEntropyFix", parabolic=True, eos=eos,
-                refstates=((1.0, 0.990268069, 0.139173101, 0.0, 4.4642857),), nProcs=nProcs, myRank=myRank)
+                refstates=((1.0, 0.990268069, 0.139173101, 0.0, 4.4642857),), nProcs=nProcs, myRank=myRank,
+                # regressioncheck/checks/naca/3D/parameter.ini:50-53
+                user_bcs={"BC_inflow": (2, 1), "BC_outflow": (2, 1)})
     args.update(kw)
     nt = args.pop("node_type", bs.NODETYPE_G)
     c = cs.build_case(h, N, nt, **args)

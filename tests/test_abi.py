@@ -42,7 +42,8 @@ def test_config_struct_mirror(lib):
     ("N", 0, "polynomial degree"),
     ("N", 12, "polynomial degree"),
     ("nodeType", 3, "nodeType"),
-    ("riemann", 9, "Riemann solver"),
+    ("riemann", 8, "Riemann solver"),
+    ("riemann", 10, "Riemann solver"),
     ("splitDG", 7, "SplitDG variant"),
 ])
 def test_create_rejects_bad_config_before_touching_the_gpu(lib, field, value, msg):
@@ -60,7 +61,7 @@ def test_create_rejects_bad_config_before_touching_the_gpu(lib, field, value, ms
 def test_split_dg_needs_gauss_lobatto_and_no_hllc(lib):
     """splitflux.f90:116-119 and src/CMakeLists.txt:113-117."""
     from galaexi_b200 import dg
-    for nt, riem, msg in ((1, 3, "Gauss-Lobatto-Points are mandatory"), (2, 5, "HLLC is not available with SplitDG")):
+    for nt, riem, msg in ((1, 3, "Gauss-Lobatto-Points are mandatory"), (2, 5, "HLL-type Riemann solvers are not supported for SPLIT_DG=ON")):
         c = dg.DgxConfig()
         c.N, c.nodeType, c.splitDG, c.riemann, c.nRKStages = 3, nt, 4, riem, 5
         h = C.c_void_p()

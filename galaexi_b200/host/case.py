@@ -17,6 +17,7 @@ from . import equation as eq
 from . import mappings as mp
 from . import mesh as ms
 from . import metrics as mt
+from . import mortar as mo
 from . import timedisc as td
 
 SPLIT_IDS = {None: -1, "NONE": -1, "SD": 0, "MO": 1, "DU": 2, "KG": 3, "PI": 4}      # SPLIT_DG
@@ -40,6 +41,10 @@ class Case:
     riemann: int
     parabolic: bool
     hopr: dict = field(repr=False, default=None)
+    lifting: int = 1            # 1: BR1 (GALAEXI default, src/CMakeLists.txt:161-162), 2: BR2 (host FLEXI, lifting_br2.t90)
+    etaBR2: float = 2.0         # lifting.f90:86-91
+    etaBR2_wall: float = -1.0   # -1: use etaBR2 (lifting.f90:89-91)
+    mortar: dict = field(repr=False, default=None)   # M_0_1, M_0_2, M_1_0, M_2_0 (mortar/mortar.f90)
 
     @property
     def n(self):
@@ -54,7 +59,8 @@ def build_case(hopr: dict, N: int, node_type: str = bs.NODETYPE_GL, split: str |
                riemann: str = "RoeEntropyFix", parabolic: bool = True, eos: eq.Eos | None = None,
                refstates=((1.0, 1.0, 0.0, 0.0, 17194.8345650329),), user_bcs: dict | None = None,
                nProcs: int = 1, myRank: int = 0, timedisc: str = "carpenterrk4-5", CFLScale: float = 0.9,
-               DFLScale: float = 0.9, useCurveds: bool = True, crossProductMetrics: bool = False) -> Case:
+               DFLScale: float = 0.9, useCurveds: bool = True, crossProductMetrics: bool = False,
+               lifting: str = "br1", etaBR2: float = 2.0, etaBR2_wall: float = -1.0) -> Case:
     eos = eos or eq.Eos()
     node_type = node_type.upper()
     split_id = SPLIT_IDS[split.upper() if isinstance(split, str) else split]
@@ -75,4 +81,8 @@ def build_case(hopr: dict, N: int, node_type: str = bs.NODETYPE_GL, split: str |
     refprim = eq.init_bc_refstates(eq.refstate_prim(refstates, eos), mesh.BoundaryType)
     bcs = eq.bc_sides(mesh)
     tdisc = td.set_timedisc(timedisc, N, node_type, CFLScale, DFLScale)
-    return Case(N, node_type, basis, mesh, geo, maps, eos, refprim, bcs, tdisc, split_id, riem_id, bool(parabolic), hopr)
+    lift_id = {"br1": 1, "br2": 2}[lifting.lower()]
+    if etaBR2_wall == -1.0:
+        etaBR2_wall = etaBR2   # lifting.f90:158-159
+    return Case(N, node_type, basis, mesh, geo, maps, eos, refprim, bcs, tdisc, split_id, riem_id, bool(parabolic), hopr,
+                lift_id, float(etaBR2), float(etaBR2_wall), mo.init_mortar(N, node_type))

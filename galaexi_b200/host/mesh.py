@@ -17,7 +17,9 @@ The reference walks pointer lists element by element; here the same numbering is
 operations ("a side is numbered when the element-major, locSide-minor walk first touches it").
 ``oracle/mesh_walk.py`` holds a literal loop restatement used by the tests to pin this bit-exactly.
 
-Non-conforming (mortar) meshes are rejected, as in GALAEXI (src/mesh/mesh.f90:140-143).
+Non-conforming (mortar) meshes (rejected by GALAEXI, src/mesh/mesh.f90:140-143, but supported by the inherited host
+code) are handled by ``mesh_mortar.prepare_mesh_general``, a loop restatement that also serves as the cross-check of
+the vectorised path on conforming meshes.
 
 All 1-based reference indices (SideID, ElemID, locSide, BC index) are kept 1-based inside the integer
 tables, so they can be handed to a Fortran host unchanged; 0 / -1 keep the reference meaning.
@@ -29,6 +31,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import mappings as mp
+from . import mesh_mortar
 
 # local side -> (axis, +/-): ZETA_MINUS=1, ETA_MINUS=2, XI_PLUS=3, ETA_PLUS=4, XI_MINUS=5, ZETA_PLUS=6
 _SIDE_AXIS = {1: (2, -1), 2: (1, -1), 3: (0, +1), 4: (1, +1), 5: (0, -1), 6: (2, +1)}
@@ -304,6 +307,14 @@ class Mesh:
     offsetElemMPI: np.ndarray = None
     myRank: int = 0
     nProcs: int = 1
+    # non-conforming interfaces (mesh.f90:318-322): MortarType(2,nSides) = [type (1..3 big, -1 small, 0), index into
+    # MortarInfo]; MortarInfo(2,4,nMortarSides) = [SideID, flip] of the small sides
+    nMortarSides: int = 0
+    nMortarInnerSides: int = 0
+    nMortarMPISides: int = 0
+    MortarType: np.ndarray = None   # (nSides,2)
+    MortarInfo: np.ndarray = None   # (nMortarSides,4,2)
+    YourMaster: np.ndarray = None   # general path only: (nYOUR,5) [SideID, master elem, locSide, iMortar, mortar type]
 
 
 def _apply_user_bcs(BCNames, BCType, user_bcs):
@@ -324,11 +335,8 @@ def _apply_user_bcs(BCNames, BCType, user_bcs):
 
 
 def prepare_mesh(hopr: dict, nProcs: int = 1, myRank: int = 0, useCurveds: bool = True,
-                 user_bcs: dict | None = None) -> Mesh:
+                 user_bcs: dict | None = None, general: bool = False) -> Mesh:
     """ReadMesh + setLocalSideIDs + exchangeFlip + fillMeshInfo for one rank (see module docstring)."""
-    if hopr.get("isMortarMesh", 0):
-        raise NotImplementedError("Mortars (non-conforming elements) detected in the mesh; not supported "
-                                  "(GALAEXI aborts as well, src/mesh/mesh.f90:140-143)")
     ElemInfo = hopr["ElemInfo"]
     SideInfo = hopr["SideInfo"]
     nGlobal = ElemInfo.shape[0]
@@ -337,6 +345,9 @@ def prepare_mesh(hopr: dict, nProcs: int = 1, myRank: int = 0, useCurveds: bool 
     nElems = int(offMPI[myRank + 1] - offMPI[myRank])
     BoundaryType = _apply_user_bcs(hopr["BCNames"], hopr["BCType"], user_bcs)
     nBCs = BoundaryType.shape[0]
+    if general or mesh_mortar.has_mortars(hopr):
+        # non-conforming interfaces: host-FLEXI bookkeeping (GALAEXI aborts here, src/mesh/mesh.f90:140-143)
+        return mesh_mortar.prepare_mesh_general(hopr, nProcs, myRank, useCurveds, BoundaryType, offMPI, elem_to_proc, Mesh)
 
     ei = ElemInfo[offsetElem:offsetElem + nElems]
     if np.any(ei[:, 3] - ei[:, 2] != 6):
@@ -539,4 +550,6 @@ def prepare_mesh(hopr: dict, nProcs: int = 1, myRank: int = 0, useCurveds: bool 
     m.offsetElemMPI = offMPI
     m.myRank = myRank
     m.nProcs = nProcs
+    m.MortarType = np.zeros((nSides, 2), dtype=np.int32)
+    m.MortarInfo = -np.ones((1, 4, 2), dtype=np.int32)
     return m

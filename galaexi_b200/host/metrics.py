@@ -21,6 +21,7 @@ import numpy as np
 
 from . import basis as bs
 from . import mappings as mp
+from . import mortar as mo
 from .mesh import Mesh
 
 NormalDirs = (3, 2, 1, 2, 1, 3)       # mesh_vars.f90:112
@@ -178,7 +179,11 @@ def calc_metrics(mesh: Mesh, N: int, node_type: str, crossProductMetrics: bool =
     S2V2 = mp.build_mappings(N)["S2V2"]
     V_geo_N = ops.Vdm_CLN_N @ ops.Vdm_CLNGeo_CLN @ ops.Vdm_EQNGeo_CLNGeo
 
-    def surf(XCL_N, Ja, elem_sel, loc, side_ids):
+    has_mortar = mesh.MortarType is not None and bool(np.any(mesh.MortarType[:, 0] > 0))
+
+    def surf(XCL_N, Ja, elem_sel, loc, side_ids, iMortar=None, mtype=None):
+        """Surface metrics of the master sides `side_ids` of the elements `elem_sel` (local side loc). With iMortar /
+        mtype (arrays) the result is the iMortar-th small side of that (remote) big side instead."""
         if len(elem_sel) == 0:
             return
         xf = change_basis_surf(ops.Vdm_CLN_N, _face_slice(XCL_N[elem_sel], loc, N))
@@ -189,9 +194,27 @@ def calc_metrics(mesh: Mesh, N: int, node_type: str, crossProductMetrics: bool =
         b = S2V2[loc - 1, 0, :, :, 1]
         xf = xf[:, b, a]
         jf = jf[:, b, a]
+        if iMortar is not None:
+            # YOUR side whose master is a virtual small side of a remote big mortar side
+            for x in range(len(side_ids)):
+                if iMortar[x] > 0:
+                    mja, mx = mo.mortar_surf_metrics(int(mtype[x]), N, node_type, jf[x], xf[x])
+                    jf[x], xf[x] = mja[iMortar[x] - 1], mx[iMortar[x] - 1]
         nv, t1, t2, se = _surf_metrics_from_ja(jf, loc)
         sid = side_ids - 1
         NormVec[sid], TangVec1[sid], TangVec2[sid], SurfElem[sid], Face_xGP[sid] = nv, t1, t2, se, xf
+        if has_mortar and iMortar is None:
+            # metrics.f90:727-741 + mortar_metrics.f90: small master sides get the interpolated big-side metrics
+            for x in np.nonzero(mesh.MortarType[sid, 0] > 0)[0]:
+                big = sid[x]
+                mja, mx = mo.mortar_surf_metrics(int(mesh.MortarType[big, 0]), N, node_type, jf[x], xf[x])
+                info = mesh.MortarInfo[mesh.MortarType[big, 1] - 1]
+                for im in range(len(mja)):
+                    if info[im, 1] > 0:
+                        continue  # slave small sides (MPI YOUR) are built by their master rank
+                    s2 = int(info[im, 0]) - 1
+                    n2, u1, u2, s_e = _surf_metrics_from_ja(mja[im][None], loc)
+                    NormVec[s2], TangVec1[s2], TangVec2[s2], SurfElem[s2], Face_xGP[s2] = n2[0], u1[0], u2[0], s_e[0], mx[im]
 
     for s0 in range(0, nE, chunk):
         s1 = min(nE, s0 + chunk)
@@ -219,13 +242,18 @@ def calc_metrics(mesh: Mesh, N: int, node_type: str, crossProductMetrics: bool =
         NG0 = int(hopr["NGeo"])
         nn = (NG0 + 1) ** 3
         e2s = mesh.ElemToSide
-        your = np.argwhere(e2s[:, :, 0] >= mesh.firstMPISide_YOUR)
-        ei = hopr["ElemInfo"]
-        si = hopr["SideInfo"]
-        rows = ei[mesh.offsetElem + your[:, 0], 2].astype(np.int64) + your[:, 1]
-        nb_elem = si[rows, 2].astype(np.int64) - 1
-        nb_loc = (si[rows, 3] // 10).astype(np.int64)
-        side_ids = e2s[your[:, 0], your[:, 1], 0].astype(np.int64)
+        imort = mtyp = None
+        if mesh.YourMaster is not None:
+            ym = mesh.YourMaster
+            side_ids, nb_elem, nb_loc, imort, mtyp = ym[:, 0], ym[:, 1] - 1, ym[:, 2], ym[:, 3], ym[:, 4]
+        else:
+            your = np.argwhere((e2s[:, :, 0] >= mesh.firstMPISide_YOUR) & (e2s[:, :, 0] <= mesh.lastMPISide_YOUR))
+            ei = hopr["ElemInfo"]
+            si = hopr["SideInfo"]
+            rows = ei[mesh.offsetElem + your[:, 0], 2].astype(np.int64) + your[:, 1]
+            nb_elem = si[rows, 2].astype(np.int64) - 1
+            nb_loc = (si[rows, 3] // 10).astype(np.int64)
+            side_ids = e2s[your[:, 0], your[:, 1], 0].astype(np.int64)
         for loc in range(1, 7):
             sel = np.nonzero(nb_loc == loc)[0]
             for c0 in range(0, len(sel), chunk):
@@ -235,7 +263,8 @@ def calc_metrics(mesh: Mesh, N: int, node_type: str, crossProductMetrics: bool =
                 if NG0 != NGeo:
                     nc = nc[:, ::NG0, ::NG0, ::NG0, :]
                 XCL_N, Ja, _ = _elem_geometry(ops, np.ascontiguousarray(nc), crossProductMetrics)
-                surf(XCL_N, Ja, np.arange(len(ss)), loc, side_ids[ss])
+                surf(XCL_N, Ja, np.arange(len(ss)), loc, side_ids[ss], None if imort is None else imort[ss],
+                     None if mtyp is None else mtyp[ss])
 
     return dict(Elem_xGP=Elem_xGP, Metrics_fTilde=Mf, Metrics_gTilde=Mg, Metrics_hTilde=Mh, sJ=sJ,
                 NormVec=NormVec, TangVec1=TangVec1, TangVec2=TangVec2, SurfElem=SurfElem, Face_xGP=Face_xGP)

@@ -77,6 +77,15 @@ typedef struct {
     const double *NormVec, *TangVec1, *TangVec2; /* (3,n,n,nSides) */
     const double *SurfElem; /* (n,n,nSides) */
     const double *RefStatePrim; /* (6,nRefState) */
+    /* lifting variant: 1 BR1 (GALAEXI), 2 BR2 (host FLEXI code, dg/lifting/lifting_br2.t90); penalties lifting.f90:86-91 */
+    int lifting;
+    double etaBR2, etaBR2_wall;
+    /* non-conforming interfaces (host FLEXI code, mortar/): side ranges mesh.f90:271-283, MortarType(2,nSides),
+     * MortarInfo(2,4,nMortarSides), FS2M(2,0:N,0:N,0:4) mappings.f90:180-189, 1-D operators mortar.f90 (stored transposed) */
+    int firstMortarInnerSide, lastMortarInnerSide, firstMortarMPISide, lastMortarMPISide;
+    const int *MortarType, *MortarInfo, *FS2M;
+    const int *SideToElem; /* (5,nSides) */
+    const double *M_0_1, *M_0_2, *M_1_0, *M_2_0;
 } dgo_config;
 
 typedef struct {
@@ -89,6 +98,7 @@ typedef struct {
     double *gradUx_master, *gradUy_master, *gradUz_master, *gradUx_slave, *gradUy_slave, *gradUz_slave;
     double *f, *g, *h;
     double *MetricsAdv, *MetricsVisc;
+    double *FluxX, *FluxY, *FluxZ; /* BR2 lifting fluxes (lifting_br2.t90) */
 } dgo;
 
 #define IDX_VOL(s, nv, v, i, j, k, e) ((size_t)(v) + (size_t)(nv) * ((size_t)(i) + (s)->n * ((size_t)(j) + (s)->n * ((size_t)(k) + (size_t)(s)->n * (size_t)(e)))))
@@ -737,6 +747,128 @@ static void eval_transformed_flux(int euler, int visc, const double *U, const do
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* Non-conforming interfaces, mortar/fillmortar.t90 (host FLEXI code; GALAEXI has no GPU mortar path).
+ * 1-D operator application along the first (dir 0) or second (dir 1) side index with the reference's summation
+ * order: the l=0 term first, then l=1..N. M is stored transposed: out(p) = sum_l M(l,p) in(l). */
+static void mortar_1d(int n, int nVar, int dir, const double *M, const double *in, double *out)
+{
+    for (int q = 0; q < n; q++) for (int p = 0; p < n; p++) {
+        const int o = dir == 0 ? p : q;
+        for (int v = 0; v < nVar; v++) {
+            double a = M[0 + n * o] * in[v + nVar * (dir == 0 ? (0 + n * q) : (p + n * 0))];
+            for (int l = 1; l < n; l++) a = a + M[l + n * o] * in[v + nVar * (dir == 0 ? (l + n * q) : (p + n * l))];
+            out[v + nVar * (p + n * q)] = a;
+        }
+    }
+}
+/* the same for the sum of two operators on two inputs: out(p) = sum_l ( M1(l,p) a(l) + M2(l,p) b(l) ) */
+static void mortar_1d_pair(int n, int nVar, int dir, const double *M1, const double *M2, const double *a, const double *b, double *out)
+{
+    for (int q = 0; q < n; q++) for (int p = 0; p < n; p++) {
+        const int o = dir == 0 ? p : q;
+        for (int v = 0; v < nVar; v++) {
+            int i0 = v + nVar * (dir == 0 ? (0 + n * q) : (p + n * 0));
+            double t = M1[0 + n * o] * a[i0] + M2[0 + n * o] * b[i0];
+            for (int l = 1; l < n; l++) {
+                int il = v + nVar * (dir == 0 ? (l + n * q) : (p + n * l));
+                t = t + M1[l + n * o] * a[il] + M2[l + n * o] * b[il];
+            }
+            out[v + nVar * (p + n * q)] = t;
+        }
+    }
+}
+#define MAXFACE (8 * 10 * 10)
+/* fillmortar.t90:34-195 U_Mortar: big-side master data -> the 4 (type 1) or 2 (types 2: eta split, 3: xi split) small
+ * sides; small sides that are slave sides here (flip>0, MPI) are filled through FS2M */
+static void u_mortar(const dgo *s, int nVar, double *Um, double *Us, int firstSide, int lastSide)
+{
+    const dgo_config *c = &s->c;
+    const int n = s->n;
+    for (int sd = firstSide - 1; sd < lastSide; sd++) {
+        const double *big = &Um[IDX_FACE(s, nVar, 0, 0, 0, sd)];
+        const int type = c->MortarType[0 + 2 * sd], iSide = c->MortarType[1 + 2 * sd];
+        double tmp[4][MAXFACE], tmp2[2][MAXFACE];
+        int nMortars = 2;
+        switch (type) {
+        case 1:
+            nMortars = 4;
+            mortar_1d(n, nVar, 1, c->M_0_1, big, tmp2[0]);
+            mortar_1d(n, nVar, 1, c->M_0_2, big, tmp2[1]);
+            mortar_1d(n, nVar, 0, c->M_0_1, tmp2[0], tmp[0]);
+            mortar_1d(n, nVar, 0, c->M_0_2, tmp2[0], tmp[1]);
+            mortar_1d(n, nVar, 0, c->M_0_1, tmp2[1], tmp[2]);
+            mortar_1d(n, nVar, 0, c->M_0_2, tmp2[1], tmp[3]);
+            break;
+        case 2:
+            mortar_1d(n, nVar, 1, c->M_0_1, big, tmp[0]);
+            mortar_1d(n, nVar, 1, c->M_0_2, big, tmp[1]);
+            break;
+        default:
+            mortar_1d(n, nVar, 0, c->M_0_1, big, tmp[0]);
+            mortar_1d(n, nVar, 0, c->M_0_2, big, tmp[1]);
+        }
+        for (int im = 0; im < nMortars; im++) {
+            const int SideID = c->MortarInfo[0 + 2 * (im + 4 * (iSide - 1))], flip = c->MortarInfo[1 + 2 * (im + 4 * (iSide - 1))];
+            for (int q = 0; q < n; q++) for (int p = 0; p < n; p++) {
+                if (flip == 0) {
+                    for (int v = 0; v < nVar; v++) Um[IDX_FACE(s, nVar, v, p, q, SideID - 1)] = tmp[im][v + nVar * (p + n * q)];
+                } else {
+                    const int pm = c->FS2M[0 + 2 * (p + n * (q + n * flip))], qm = c->FS2M[1 + 2 * (p + n * (q + n * flip))];
+                    for (int v = 0; v < nVar; v++) Us[IDX_FACE(s, nVar, v, p, q, SideID - 1)] = tmp[im][v + nVar * (pm + n * qm)];
+                }
+            }
+        }
+    }
+}
+/* fillmortar.t90:215-376 Flux_Mortar: small-side fluxes -> big side with the projection operators M_1_0, M_2_0;
+ * small slave sides (MPI) enter through FS2M with the sign of the weak form */
+static void flux_mortar(const dgo *s, int nVar, double *Fm, const double *Fs, int firstSide, int lastSide, int weak)
+{
+    const dgo_config *c = &s->c;
+    const int n = s->n;
+    for (int sd = firstSide - 1; sd < lastSide; sd++) {
+        const int type = c->MortarType[0 + 2 * sd], iSide = c->MortarType[1 + 2 * sd];
+        const int nMortars = type == 1 ? 4 : 2;
+        double tmp[4][MAXFACE], tmp2[2][MAXFACE];
+        for (int im = 0; im < nMortars; im++) {
+            const int SideID = c->MortarInfo[0 + 2 * (im + 4 * (iSide - 1))], flip = c->MortarInfo[1 + 2 * (im + 4 * (iSide - 1))];
+            for (int q = 0; q < n; q++) for (int p = 0; p < n; p++) {
+                if (flip == 0) {
+                    for (int v = 0; v < nVar; v++) tmp[im][v + nVar * (p + n * q)] = Fm[IDX_FACE(s, nVar, v, p, q, SideID - 1)];
+                } else {
+                    const int pm = c->FS2M[0 + 2 * (p + n * (q + n * flip))], qm = c->FS2M[1 + 2 * (p + n * (q + n * flip))];
+                    for (int v = 0; v < nVar; v++) {
+                        double f = Fs[IDX_FACE(s, nVar, v, pm, qm, SideID - 1)];
+                        tmp[im][v + nVar * (p + n * q)] = weak ? -f : f;
+                    }
+                }
+            }
+        }
+        double *big = &Fm[IDX_FACE(s, nVar, 0, 0, 0, sd)];
+        switch (type) {
+        case 1:
+            mortar_1d_pair(n, nVar, 0, c->M_1_0, c->M_2_0, tmp[0], tmp[1], tmp2[0]);
+            mortar_1d_pair(n, nVar, 0, c->M_1_0, c->M_2_0, tmp[2], tmp[3], tmp2[1]);
+            mortar_1d_pair(n, nVar, 1, c->M_1_0, c->M_2_0, tmp2[0], tmp2[1], big);
+            break;
+        case 2: mortar_1d_pair(n, nVar, 1, c->M_1_0, c->M_2_0, tmp[0], tmp[1], big); break;
+        default: mortar_1d_pair(n, nVar, 0, c->M_1_0, c->M_2_0, tmp[0], tmp[1], big);
+        }
+    }
+}
+/* both ranges of big mortar sides (inner and MPI); on one rank the second range is empty */
+static void u_mortar_all(const dgo *s, int nVar, double *Um, double *Us)
+{
+    u_mortar(s, nVar, Um, Us, s->c.firstMortarMPISide, s->c.lastMortarMPISide);
+    u_mortar(s, nVar, Um, Us, s->c.firstMortarInnerSide, s->c.lastMortarInnerSide);
+}
+static void flux_mortar_all(const dgo *s, int nVar, double *Fm, const double *Fs, int weak)
+{
+    flux_mortar(s, nVar, Fm, Fs, s->c.firstMortarInnerSide, s->c.lastMortarInnerSide, weak);
+    flux_mortar(s, nVar, Fm, Fs, s->c.firstMortarMPISide, s->c.lastMortarMPISide, weak);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* lifting: dg/lifting/lifting_br1.t90:47-167 (strong form, non-conservative volume integral) */
 static void lifting_br1_fillflux(dgo *s)
 {
@@ -776,6 +908,7 @@ static void lifting_br1_fillflux(dgo *s)
         }
 }
 
+static void lifting_volint(dgo *s);
 /* (MPI) between the two parts the lifting flux on YOUR sides arrives from the master rank, lifting_br1.t90:93-112 */
 static void lifting_br1_finish(dgo *s)
 {
@@ -794,7 +927,31 @@ static void lifting_br1_finish(dgo *s)
                 s->gradUz_master[IDX_FACE(s, NL, v, p, q, sd)] = fl * nv[2];
             }
         }
-    /* lifting_volint.t90:262-328 Lifting_VolInt_Nonconservative_GPU_Kernel */
+    /* big mortar sides: project the small-side lifting fluxes (strong form: no sign change), as the host code does
+     * with Flux_MortarLifting on FluxX/Y/Z (lifting_br2.t90:102-106) */
+    flux_mortar_all(s, NL, s->gradUx_master, s->gradUx_master, 0);
+    flux_mortar_all(s, NL, s->gradUy_master, s->gradUy_master, 0);
+    flux_mortar_all(s, NL, s->gradUz_master, s->gradUz_master, 0);
+    lifting_volint(s);
+    /* lifting_br1.t90:118-124 SurfIntLifting x3 (single flux, strong, with sJ) */
+    surf_int(s, NL, s->gradUx_master, NULL, s->gradUx, 1, 0, 1);
+    surf_int(s, NL, s->gradUy_master, NULL, s->gradUy, 1, 0, 1);
+    surf_int(s, NL, s->gradUz_master, NULL, s->gradUz, 1, 0, 1);
+    /* lifting_br1.t90:152-156 ProlongToFaceLifting x3 */
+    prolong_to_face(s, NL, s->gradUx, s->gradUx_master, s->gradUx_slave);
+    prolong_to_face(s, NL, s->gradUy, s->gradUy_master, s->gradUy_slave);
+    prolong_to_face(s, NL, s->gradUz, s->gradUz_master, s->gradUz_slave);
+    /* gradients of the big side to its small sides (U_MortarLifting, lifting_br2.t90:175-181) */
+    u_mortar_all(s, NL, s->gradUx_master, s->gradUx_slave);
+    u_mortar_all(s, NL, s->gradUy_master, s->gradUy_slave);
+    u_mortar_all(s, NL, s->gradUz_master, s->gradUz_slave);
+}
+
+/* lifting_volint.t90:262-328 Lifting_VolInt_Nonconservative_GPU_Kernel */
+static void lifting_volint(dgo *s)
+{
+    const dgo_config *c = &s->c;
+    const int n = s->n;
 #pragma omp parallel for schedule(static)
     for (int e = 0; e < c->nElems; e++)
         for (int k = 0; k < n; k++) for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) {
@@ -815,17 +972,116 @@ static void lifting_br1_finish(dgo *s)
                 s->gradUz[IDX_VOL(s, NL, v, i, j, k, e)] = Mf[2] * gxi[v] + Mg[2] * get[v] + Mh[2] * gze[v];
             }
         }
-    /* lifting_br1.t90:118-124 SurfIntLifting x3 (single flux, strong, with sJ) */
-    surf_int(s, NL, s->gradUx_master, NULL, s->gradUx, 1, 0, 1);
-    surf_int(s, NL, s->gradUy_master, NULL, s->gradUy, 1, 0, 1);
-    surf_int(s, NL, s->gradUz_master, NULL, s->gradUz, 1, 0, 1);
-    /* lifting_br1.t90:152-156 ProlongToFaceLifting x3 */
+}
+
+/* volume index of side node (p,q) at depth l: S2V(1:3,l,p,q,flip,locSide), mappings.f90:337-377 after the flip */
+static inline void s2v3(const dgo *s, int l, int p, int q, int flip, int loc, int *ijk)
+{
+    const int n = s->n, N = s->c.N;
+    const int a = s2v2(s->c.S2V2, n, 1, p, q, flip, loc), b = s2v2(s->c.S2V2, n, 2, p, q, flip, loc);
+    switch (loc) {
+    case XI_MINUS:   ijk[0] = l;     ijk[1] = a; ijk[2] = b; break;
+    case XI_PLUS:    ijk[0] = N - l; ijk[1] = a; ijk[2] = b; break;
+    case ETA_MINUS:  ijk[0] = a; ijk[1] = l;     ijk[2] = b; break;
+    case ETA_PLUS:   ijk[0] = a; ijk[1] = N - l; ijk[2] = b; break;
+    case ZETA_MINUS: ijk[0] = a; ijk[1] = b; ijk[2] = l;     break;
+    default:         ijk[0] = a; ijk[1] = b; ijk[2] = N - l; break;
+    }
+}
+
+/* lifting_br2.t90:193-313 Lifting_SurfInt_BR2 for one gradient direction: slave sides, then master sides */
+static void lifting_surfint_br2(dgo *s, const double *Flux, double *gradU, double *gm, double *gs)
+{
+    const dgo_config *c = &s->c;
+    const int n = s->n;
+    const int lmax = (c->nodeType == 2) ? 1 : n; /* Gauss-Lobatto: only the boundary node (l=0) */
+    /* slave sides: inner sides and MPI YOUR sides */
+    const int sr[2][2] = {{c->firstInnerSide, c->lastInnerSide}, {c->firstMPISide_YOUR, c->lastMPISide_YOUR}};
+    for (int r = 0; r < 2; r++)
+        for (int sd = sr[r][0] - 1; sd < sr[r][1]; sd++) {
+            const int nbElemID = c->SideToElem[1 + 5 * sd];
+            if (nbElemID <= 0) continue;
+            const int nbloc = c->SideToElem[3 + 5 * sd], flip = c->SideToElem[4 + 5 * sd];
+            const double eta = c->etaBR2;
+            for (int q = 0; q < n; q++) for (int p = 0; p < n; p++) for (int l = 0; l < lmax; l++) {
+                int ijk[3];
+                s2v3(s, l, p, q, flip, nbloc, ijk);
+                const double sJ = c->sJ[ijk[0] + n * (ijk[1] + n * (ijk[2] + (size_t)n * (nbElemID - 1)))];
+                for (int v = 0; v < NL; v++) {
+                    double F_loc = sJ * Flux[IDX_FACE(s, NL, v, p, q, sd)] * c->L_HatMinus[l];
+                    size_t id = IDX_VOL(s, NL, v, ijk[0], ijk[1], ijk[2], nbElemID - 1);
+                    gradU[id] = gradU[id] + F_loc;
+                    gs[IDX_FACE(s, NL, v, p, q, sd)] = gs[IDX_FACE(s, NL, v, p, q, sd)] + eta * c->L_Minus[l] * F_loc;
+                }
+            }
+        }
+    /* master sides: everything but YOUR, plus the MPI mortars */
+    const int mr[2][2] = {{1, c->lastMPISide_MINE}, {c->firstMortarMPISide, c->lastMortarMPISide}};
+    for (int r = 0; r < 2; r++)
+        for (int sd = mr[r][0] - 1; sd < mr[r][1]; sd++) {
+            double eta = c->etaBR2;
+            if (sd < c->nBCSides && (c->BCSides[0 + 2 * sd] == 4 || c->BCSides[0 + 2 * sd] == 3)) eta = c->etaBR2_wall;
+            const int ElemID = c->SideToElem[0 + 5 * sd];
+            if (ElemID <= 0) continue;
+            const int loc = c->SideToElem[2 + 5 * sd];
+            for (int q = 0; q < n; q++) for (int p = 0; p < n; p++) for (int l = 0; l < lmax; l++) {
+                int ijk[3];
+                s2v3(s, l, p, q, 0, loc, ijk);
+                const double sJ = c->sJ[ijk[0] + n * (ijk[1] + n * (ijk[2] + (size_t)n * (ElemID - 1)))];
+                for (int v = 0; v < NL; v++) {
+                    double F_loc = sJ * Flux[IDX_FACE(s, NL, v, p, q, sd)] * c->L_HatMinus[l];
+                    size_t id = IDX_VOL(s, NL, v, ijk[0], ijk[1], ijk[2], ElemID - 1);
+                    gradU[id] = gradU[id] + F_loc;
+                    gm[IDX_FACE(s, NL, v, p, q, sd)] = gm[IDX_FACE(s, NL, v, p, q, sd)] + eta * c->L_Minus[l] * F_loc;
+                }
+            }
+        }
+}
+
+/* dg/lifting/lifting_br2.t90:43-184 Lifting_BR2 (host FLEXI code; non-conservative volume part). The untransformed
+ * strong-form flux 1/2 (U_s - U_m) SurfElem (BC sides: lifting_fillflux.t90:109-140) is the BR1 one; FluxX/Y/Z are
+ * that flux times the normal components. */
+static void lifting_br2_finish(dgo *s)
+{
+    const dgo_config *c = &s->c;
+    const int n = s->n;
+    const double *Flux = s->gradUz_slave;
+#pragma omp parallel for schedule(static)
+    for (int sd = 0; sd < c->nSides; sd++)
+        for (int q = 0; q < n; q++) for (int p = 0; p < n; p++) {
+            const double *nv = &c->NormVec[IDX_FACE(s, 3, 0, p, q, sd)];
+            for (int v = 0; v < NL; v++) {
+                double fl = Flux[IDX_FACE(s, NL, v, p, q, sd)];
+                s->FluxX[IDX_FACE(s, NL, v, p, q, sd)] = fl * nv[0];
+                s->FluxY[IDX_FACE(s, NL, v, p, q, sd)] = fl * nv[1];
+                s->FluxZ[IDX_FACE(s, NL, v, p, q, sd)] = fl * nv[2];
+            }
+        }
+    flux_mortar_all(s, NL, s->FluxX, s->FluxX, 0);
+    flux_mortar_all(s, NL, s->FluxY, s->FluxY, 0);
+    flux_mortar_all(s, NL, s->FluxZ, s->FluxZ, 0);
+    lifting_volint(s);
+    /* ApplyJacobianLifting(toPhysical), lifting_br2.t90:118-124 */
+#pragma omp parallel for schedule(static)
+    for (size_t d = 0; d < s->nDOF; d++)
+        for (int v = 0; v < NL; v++) {
+            s->gradUx[NL * d + v] = s->gradUx[NL * d + v] * c->sJ[d];
+            s->gradUy[NL * d + v] = s->gradUy[NL * d + v] * c->sJ[d];
+            s->gradUz[NL * d + v] = s->gradUz[NL * d + v] * c->sJ[d];
+        }
     prolong_to_face(s, NL, s->gradUx, s->gradUx_master, s->gradUx_slave);
     prolong_to_face(s, NL, s->gradUy, s->gradUy_master, s->gradUy_slave);
     prolong_to_face(s, NL, s->gradUz, s->gradUz_master, s->gradUz_slave);
+    lifting_surfint_br2(s, s->FluxX, s->gradUx, s->gradUx_master, s->gradUx_slave);
+    lifting_surfint_br2(s, s->FluxY, s->gradUy, s->gradUy_master, s->gradUy_slave);
+    lifting_surfint_br2(s, s->FluxZ, s->gradUz, s->gradUz_master, s->gradUz_slave);
+    u_mortar_all(s, NL, s->gradUx_master, s->gradUx_slave);
+    u_mortar_all(s, NL, s->gradUy_master, s->gradUy_slave);
+    u_mortar_all(s, NL, s->gradUz_master, s->gradUz_slave);
 }
 
-static void lifting_br1(dgo *s) { lifting_br1_fillflux(s); lifting_br1_finish(s); }
+static void lifting_finish(dgo *s) { if (s->c.lifting == 2) lifting_br2_finish(s); else lifting_br1_finish(s); }
+static void lifting_br1(dgo *s) { lifting_br1_fillflux(s); lifting_finish(s); }
 
 /* ------------------------------------------------------------------------------------------------ */
 /* dg/applydmatrix.t90:19-75 ApplyDMatrix_Kernel */
@@ -910,6 +1166,7 @@ static int fill_flux(dgo *s)
 #pragma omp parallel for schedule(static) reduction(|:err)
     for (int sd = 0; sd < c->lastMPISide_MINE; sd++)
         for (int q = 0; q < n; q++) for (int p = 0; p < n; p++) {
+            if (sd >= c->nBCSides && sd < c->firstInnerSide - 1) continue; /* big mortar sides: filled by Flux_Mortar */
             const double *nv = &c->NormVec[IDX_FACE(s, 3, 0, p, q, sd)];
             const double *t1 = &c->TangVec1[IDX_FACE(s, 3, 0, p, q, sd)];
             const double *t2 = &c->TangVec2[IDX_FACE(s, 3, 0, p, q, sd)];
@@ -1023,6 +1280,7 @@ int dgo_time_derivative(dgo *s, double t)
     const dgo_config *c = &s->c;
     const double kappa = c->EOS[EOS_KAPPA], R = c->EOS[EOS_R];
     /* 2. */ prolong_to_face(s, NV, s->U, s->U_master, s->U_slave);
+    /* 2b. (host FLEXI) big mortar sides -> small sides */ u_mortar_all(s, NV, s->U_master, s->U_slave);
     /* 3. eos.f90:328 ConsToPrim volume */
 #pragma omp parallel for schedule(static)
     for (size_t d = 0; d < s->nDOF; d++) cons_to_prim(&s->UPrim[NP * d], &s->U[NV * d], kappa, R);
@@ -1035,6 +1293,7 @@ int dgo_time_derivative(dgo *s, double t)
     /* 6. */ if (c->parabolic) lifting_br1(s);
     /* 8. */ vol_int(s);
     /* 11. */ int err = fill_flux(s);
+    /* 11b. (host FLEXI) small-side fluxes -> big mortar sides, weak form */ flux_mortar_all(s, NV, s->Flux_master, s->Flux_slave, 1);
     /* 11.5 */ surf_int(s, NV, s->Flux_master, s->Flux_slave, s->Ut, 0, 0, 0);
     /* 12. vector.f90:210 VAX_GPU(-1), 14. applyjacobian.t90:196 */
 #pragma omp parallel for schedule(static)
@@ -1057,6 +1316,7 @@ int dgo_rhs_phase(dgo *s, int phase)
     switch (phase) {
     case 0:
         prolong_to_face(s, NV, s->U, s->U_master, s->U_slave);
+        u_mortar_all(s, NV, s->U_master, s->U_slave);
 #pragma omp parallel for schedule(static)
         for (size_t d = 0; d < s->nDOF; d++) cons_to_prim(&s->UPrim[NP * d], &s->U[NV * d], kappa, R);
         break; /* -> exchange U_slave, YOUR -> MINE */
@@ -1069,13 +1329,14 @@ int dgo_rhs_phase(dgo *s, int phase)
         if (c->parabolic) lifting_br1_fillflux(s);
         break; /* -> exchange lifting flux (buffer gradUz_slave), MINE -> YOUR */
     case 2:
-        if (c->parabolic) lifting_br1_finish(s);
+        if (c->parabolic) lifting_finish(s);
         break; /* -> exchange gradUx/y/z_slave, YOUR -> MINE */
     case 3:
         vol_int(s);
         err = fill_flux(s);
         break; /* -> exchange Flux_slave, MINE -> YOUR */
     case 4:
+        flux_mortar_all(s, NV, s->Flux_master, s->Flux_slave, 1);
         surf_int(s, NV, s->Flux_master, s->Flux_slave, s->Ut, 0, 0, 0);
 #pragma omp parallel for schedule(static)
         for (size_t d = 0; d < s->nDOF; d++) {
@@ -1186,6 +1447,7 @@ dgo *dgo_create(const dgo_config *cfg)
     AL(gradUx_master, NL * s->nFace); AL(gradUy_master, NL * s->nFace); AL(gradUz_master, NL * s->nFace);
     AL(gradUx_slave, NL * s->nFace); AL(gradUy_slave, NL * s->nFace); AL(gradUz_slave, NL * s->nFace);
     AL(f, NV * s->nDOF); AL(g, NV * s->nDOF); AL(h, NV * s->nDOF);
+    AL(FluxX, NL * s->nFace); AL(FluxY, NL * s->nFace); AL(FluxZ, NL * s->nFace);
 #undef AL
     /* the reference initialises U_slave/UPrim_slave of BC sides to 0 and never touches them; prim of a zero
      * state would divide by zero, so the slave arrays of sides without a slave element get a benign state. */
@@ -1198,7 +1460,7 @@ void dgo_destroy(dgo *s)
     if (!s) return;
     double *p[] = {s->U, s->Ut, s->UPrim, s->Ut_tmp, s->U_master, s->U_slave, s->UPrim_master, s->UPrim_slave, s->Flux_master,
                    s->Flux_slave, s->gradUx, s->gradUy, s->gradUz, s->gradUx_master, s->gradUy_master, s->gradUz_master,
-                   s->gradUx_slave, s->gradUy_slave, s->gradUz_slave, s->f, s->g, s->h};
+                   s->gradUx_slave, s->gradUy_slave, s->gradUz_slave, s->f, s->g, s->h, s->FluxX, s->FluxY, s->FluxZ};
     for (size_t i = 0; i < sizeof(p) / sizeof(p[0]); i++) free(p[i]);
     free(s);
 }
@@ -1218,4 +1480,6 @@ double *dgo_array(dgo *s, const char *name)
 void dgo_prolong_to_face(dgo *s, int nVar, const double *Uvol, double *Um, double *Us) { prolong_to_face(s, nVar, Uvol, Um, Us); }
 void dgo_surf_int(dgo *s, int nVar, const double *Fm, const double *Fs, double *Ut) { surf_int(s, nVar, Fm, Fs, Ut, 0, 0, 0); }
 void dgo_lifting(dgo *s) { lifting_br1(s); }
+void dgo_u_mortar(dgo *s, int nVar, double *Um, double *Us) { u_mortar_all(s, nVar, Um, Us); }
+void dgo_flux_mortar(dgo *s, int nVar, double *Fm, const double *Fs, int weak) { flux_mortar_all(s, nVar, Fm, Fs, weak); }
 size_t dgo_sizeof_config(void) { return sizeof(dgo_config); }

@@ -36,7 +36,12 @@ class _Prec:
                        [(k, rp) for k in ("D_T", "D_Hat_T", "DVolSurf", "L_Minus", "L_Plus", "L_HatMinus", "L_HatPlus")] + \
                        [(k, _ip) for k in ("ElemToSide", "S2V2", "S2V2_inv", "BCSides")] + \
                        [(k, rp) for k in ("Metrics_fTilde", "Metrics_gTilde", "Metrics_hTilde", "sJ", "NormVec",
-                                          "TangVec1", "TangVec2", "SurfElem", "RefStatePrim")]
+                                          "TangVec1", "TangVec2", "SurfElem", "RefStatePrim")] + \
+                       [("lifting", C.c_int), ("etaBR2", self.real), ("etaBR2_wall", self.real)] + \
+                       [(k, C.c_int) for k in ("firstMortarInnerSide", "lastMortarInnerSide", "firstMortarMPISide",
+                                               "lastMortarMPISide")] + \
+                       [(k, _ip) for k in ("MortarType", "MortarInfo", "FS2M", "SideToElem")] + \
+                       [(k, rp) for k in ("M_0_1", "M_0_2", "M_1_0", "M_2_0")]
         self.Config = Config
         self._lib = None
 
@@ -104,6 +109,18 @@ class Oracle:
         m, b, g = case.mesh, case.basis, case.geo
         self.case = case
         self.n = case.N + 1
+        # optional pieces (hand-built single-element cases of the unit tests do not carry them)
+        nS_ = m.nSides
+        MortarType = getattr(m, "MortarType", None)
+        MortarType = np.zeros((nS_, 2)) if MortarType is None else MortarType
+        MortarInfo = getattr(m, "MortarInfo", None)
+        MortarInfo = -np.ones((1, 4, 2)) if MortarInfo is None else MortarInfo
+        SideToElem = getattr(m, "SideToElem", None)
+        SideToElem = -np.ones((nS_, 5)) if SideToElem is None else SideToElem
+        mortar = getattr(case, "mortar", None)
+        if mortar is None:
+            from galaexi_b200.host import mortar as _mo
+            mortar = _mo.init_mortar(case.N, case.node_type)
         # keep references: the C side stores raw pointers
         f64 = lambda a: np.ascontiguousarray(a, dtype=self.prec.np)
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
@@ -115,7 +132,11 @@ class Oracle:
             BCSides=i32(case.BCSides if case.BCSides.size else np.zeros((1, 2))),
             Metrics_fTilde=f64(g["Metrics_fTilde"]), Metrics_gTilde=f64(g["Metrics_gTilde"]), Metrics_hTilde=f64(g["Metrics_hTilde"]),
             sJ=f64(g["sJ"]), NormVec=f64(g["NormVec"]), TangVec1=f64(g["TangVec1"]), TangVec2=f64(g["TangVec2"]),
-            SurfElem=f64(g["SurfElem"]), RefStatePrim=f64(case.RefStatePrim))
+            SurfElem=f64(g["SurfElem"]), RefStatePrim=f64(case.RefStatePrim),
+            MortarType=i32(MortarType), MortarInfo=i32(MortarInfo), FS2M=i32(case.maps["FS2M"]), SideToElem=i32(SideToElem),
+            # mortar operators: Fortran M(l,p) at [l + n*p] == C array M.T
+            M_0_1=f64(mortar["M_0_1"].T), M_0_2=f64(mortar["M_0_2"].T), M_1_0=f64(mortar["M_1_0"].T),
+            M_2_0=f64(mortar["M_2_0"].T))
         c = self.prec.Config()
         c.N, c.nElems, c.nSides = case.N, m.nElems, m.nSides
         c.nBCSides, c.firstInnerSide, c.lastInnerSide = m.nBCSides, m.firstInnerSide, m.lastInnerSide
@@ -127,10 +148,17 @@ class Oracle:
         for k, v in enumerate(case.eos.eos_vars()):
             c.EOS[k] = v
         for k in ("D_T", "D_Hat_T", "DVolSurf", "L_Minus", "L_Plus", "L_HatMinus", "L_HatPlus", "Metrics_fTilde",
-                  "Metrics_gTilde", "Metrics_hTilde", "sJ", "NormVec", "TangVec1", "TangVec2", "SurfElem", "RefStatePrim"):
+                  "Metrics_gTilde", "Metrics_hTilde", "sJ", "NormVec", "TangVec1", "TangVec2", "SurfElem", "RefStatePrim",
+                  "M_0_1", "M_0_2", "M_1_0", "M_2_0"):
             setattr(c, k, _d(self._keep[k]))
-        for k in ("ElemToSide", "S2V2", "S2V2_inv", "BCSides"):
+        for k in ("ElemToSide", "S2V2", "S2V2_inv", "BCSides", "MortarType", "MortarInfo", "FS2M", "SideToElem"):
             setattr(c, k, _i(self._keep[k]))
+        c.lifting, c.etaBR2 = getattr(case, "lifting", 1), getattr(case, "etaBR2", 2.0)
+        c.etaBR2_wall = getattr(case, "etaBR2_wall", c.etaBR2)
+        c.firstMortarInnerSide = getattr(m, "firstMortarInnerSide", m.nBCSides + 1)
+        c.lastMortarInnerSide = getattr(m, "lastMortarInnerSide", m.nBCSides)
+        c.firstMortarMPISide = getattr(m, "firstMortarMPISide", m.nSides + 1)
+        c.lastMortarMPISide = getattr(m, "lastMortarMPISide", m.nSides)
         self._cfg = c
         self.h = L.dgo_create(C.byref(c))
         n, nE, nS = self.n, m.nElems, m.nSides

@@ -92,6 +92,32 @@ def naca_case(N=3, nProcs=1, myRank=0, **kw):
     return c, U0
 
 
+def mortar_case(mesh="002", N=3, nProcs=1, myRank=0, bc=None, **kw):
+    """tutorials/convtest/CART_HEX_PERIODIC_MORTAR_*: Cartesian box with non-conforming interfaces of all three mortar
+    types (1->4, 1->2 in eta, 1->2 in xi). bc: optional (BCType, BCState) put on all six (otherwise periodic) boundaries."""
+    h = load_mesh(f"cart_mortar_{mesh}_mesh.npz")
+    eos = eq.Eos(kappa=1.4, R=287.058, Pr=0.72, mu0=0.01)
+    args = dict(split=None, riemann="Roe", parabolic=True, eos=eos, refstates=((1.0, 0.3, 0.2, -0.1, 2.0),),
+                nProcs=nProcs, myRank=myRank)
+    if bc is not None:
+        args["user_bcs"] = {nm: bc for nm in ("BC_z-", "BC_y-", "BC_x+", "BC_y+", "BC_x-", "BC_z+")}
+    args.update(kw)
+    nt = args.pop("node_type", bs.NODETYPE_G)
+    c = cs.build_case(h, N, nt, **args)
+    x = c.geo["Elem_xGP"]
+    L = x.reshape(-1, 3).max(axis=0) - x.reshape(-1, 3).min(axis=0)
+    kx = 2.0 * np.pi / np.where(L > 0, L, 1.0) * np.array([1.0, 1.0, 1.0])
+    prim = np.broadcast_to(c.RefStatePrim[0], x.shape[:-1] + (6,)).copy()
+    ph = kx[0] * x[..., 0] + 0.3, kx[1] * x[..., 1] - 0.2, kx[2] * x[..., 2] + 0.1
+    prim[..., 0] *= 1.0 + 0.1 * np.sin(ph[0]) * np.cos(ph[1]) * np.cos(ph[2])
+    prim[..., 1] += 0.1 * np.cos(ph[0]) * np.sin(ph[1])
+    prim[..., 2] += 0.1 * np.sin(ph[1] + ph[2])
+    prim[..., 3] += 0.1 * np.cos(ph[2]) * np.sin(ph[0])
+    prim[..., 4] *= 1.0 + 0.1 * np.cos(ph[0] + ph[1]) * np.sin(ph[2])
+    U0 = eq.prim_to_cons(prim, eos.kappa)
+    return c, U0
+
+
 def channel_case(E=4, N=5, nProcs=1, myRank=0, **kw):
     """BASELINE config #4-like: plane channel, isothermal walls (4) at y+-, periodic x,z, Roe flux, y-stretched."""
     def stretch(d, s):

@@ -8,6 +8,7 @@ Sources (all from flexi-framework/galaexi, read-only):
   regressioncheck/checks/tgv/split/*.csv + mesh     TGV N=7 GL split-form regression (first rows)
   regressioncheck/checks/parabolic/cavity_3D/*      cavity N=2 Gauss NS+BR1 reference state + mesh
   regressioncheck/checks/naca/3D mesh               curved NGeo=2 mesh (for metric checks)
+  tutorials/convtest/CART_HEX_PERIODIC_MORTAR_*     non-conforming meshes (mortar types 1, 2, 3)
 Only data files are converted (to .npz); no reference source code is copied.
 """
 import os
@@ -72,6 +73,9 @@ def main():
     mesh_npz("regressioncheck/checks/parabolic/cavity_3D/cavity4x4x4_mesh.h5", "cavity3d_mesh.npz")
     mesh_npz("regressioncheck/checks/naca/3D/NACA0012_652_Ng2_mesh.h5", "naca_mesh.npz")
     mesh_npz("tutorials/convtest/CART_HEX_PERIODIC_002_mesh.h5", "cart_periodic_002_mesh.npz")
+    # non-conforming (mortar) meshes of the convergence-test tutorial: types 1 (1->4), 2 and 3 (1->2), periodic
+    for nm in ("001", "002", "004"):
+        mesh_npz(f"tutorials/convtest/CART_HEX_PERIODIC_MORTAR_{nm}_mesh.h5", f"cart_mortar_{nm}_mesh.npz")
     csv = np.loadtxt(os.path.join(REF, "regressioncheck/checks/tgv/split/TGV_Re1600_Split_TGVAnalysis_Reference.csv"),
                      delimiter=",", skiprows=1, converters=lambda s: float(s.replace("E+0", "E+").replace("E-0", "E-")))
     np.savez_compressed(os.path.join(OUT, "tgv_split_csv.npz"), rows=csv[:40])

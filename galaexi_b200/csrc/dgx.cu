@@ -129,6 +129,10 @@ struct dgx_handle {
     std::vector<int> NbProc, nMine, nYour, offMine, offYour;
     std::vector<HaloMsg> plan;
     ncclComm_t comm = nullptr;
+    // non-conforming interfaces: the two ranges of big mortar sides
+    MortarParams mp;
+    int nMortarInner = 0, nMortarMPI = 0;
+    bool hasMortar() const { return nMortarInner + nMortarMPI > 0; }
     size_t nDOF() const { return (size_t)cfg.nElems * n3; }
     size_t nFace() const { return (size_t)cfg.nSides * n2; }
 };
@@ -210,7 +214,43 @@ int exchange(dgx_handle* h, double* am, double* as, int nvar) {
     return 0;
 }
 
+// ---- non-conforming interfaces: the same operation on the inner and the MPI range of big mortar sides --------
+int mortar_u(dgx_handle* h, double* am, double* as, int nvar) {
+    MortarParams mp = h->mp;
+    mp.side0 = h->cfg.firstMortarMPISide - 1;
+    h->kt->umortar(am, as, nvar, mp, h->nMortarMPI, h->s);
+    if (h->nMortarMPI && check_launch(h, "k_umortar(mpi)")) return 1;
+    mp.side0 = h->cfg.firstMortarInnerSide - 1;
+    h->kt->umortar(am, as, nvar, mp, h->nMortarInner, h->s);
+    if (h->nMortarInner && check_launch(h, "k_umortar")) return 1;
+    return 0;
+}
+int mortar_flux(dgx_handle* h, double* F, int nvar, int weak) {
+    MortarParams mp = h->mp;
+    mp.side0 = h->cfg.firstMortarInnerSide - 1;
+    h->kt->fluxmortar(F, nvar, weak, mp, h->nMortarInner, h->s);
+    if (h->nMortarInner && check_launch(h, "k_fluxmortar")) return 1;
+    mp.side0 = h->cfg.firstMortarMPISide - 1;
+    h->kt->fluxmortar(F, nvar, weak, mp, h->nMortarMPI, h->s);
+    if (h->nMortarMPI && check_launch(h, "k_fluxmortar(mpi)")) return 1;
+    return 0;
+}
+int mortar_liftflux(dgx_handle* h, const KParams& P) {
+    MortarParams mp = h->mp;
+    mp.side0 = h->cfg.firstMortarInnerSide - 1;
+    h->kt->mortar_liftflux(P, mp, h->nMortarInner, h->s);
+    if (h->nMortarInner && check_launch(h, "k_mortar_liftflux")) return 1;
+    mp.side0 = h->cfg.firstMortarMPISide - 1;
+    h->kt->mortar_liftflux(P, mp, h->nMortarMPI, h->s);
+    if (h->nMortarMPI && check_launch(h, "k_mortar_liftflux(mpi)")) return 1;
+    return 0;
+}
+
 // ---- one RHS evaluation (mode 0: store Ut) or RK stage (mode 1) ---------------------------------------
+// Mortar meshes (host FLEXI order, dg/lifting/lifting_br2.t90:94-181 and the U_Mortar / Flux_Mortar call pattern):
+// the face states this stage reads already hold the small-side data (k_umortar runs right after every face
+// extraction); the lifting flux of big sides is projected before k_lifting, the gradient traces are interpolated to the
+// small sides after it, the numerical flux of the small sides is projected before k_volsurf.
 struct StageTimes {
     cudaEvent_t ev[8];
     int nev = 0;
@@ -238,17 +278,21 @@ int rhs(dgx_handle* h, int mode, double mRKA, double b_dt, StageTimes* st = null
         Pi.elemList = h->innerList; Pi.nList = h->nInner;
         Pb.elemList = h->bndList; Pb.nList = h->nBnd;
     }
+    const bool mortar = h->hasMortar();
     if (c.parabolic) {
+        if (mortar && !multi && mortar_liftflux(h, P)) return 1;
         kt->lifting(multi ? Pi : P, multi ? h->nInner : c.nElems, h->s);
-        if (check_launch(h, "k_lifting")) return 1;
+        if ((multi ? h->nInner : c.nElems) > 0 && check_launch(h, "k_lifting")) return 1;
         if (multi) {
             CK(cudaStreamWaitEvent(h->s, h->evUhalo, 0));
+            if (mortar && mortar_liftflux(h, P)) return 1;
             if (h->nBnd) { kt->lifting(Pb, h->nBnd, h->s); if (check_launch(h, "k_lifting(bnd)")) return 1; }
+            if (mortar && mortar_u(h, P.gm, P.gs, 12)) return 1;
             CK(cudaEventRecord(h->evGrad, h->s));
             CK(cudaStreamWaitEvent(h->cs, h->evGrad, 0));
             if (exchange(h, P.gm, P.gs, 12)) return 1;
             CK(cudaEventRecord(h->evGhalo, h->cs));
-        }
+        } else if (mortar && mortar_u(h, P.gm, P.gs, 12)) return 1;
     } else if (multi) {
         CK(cudaStreamWaitEvent(h->s, h->evUhalo, 0));
     }
@@ -258,6 +302,7 @@ int rhs(dgx_handle* h, int mode, double mRKA, double b_dt, StageTimes* st = null
     if (c.lastInnerSide > 0 && check_launch(h, "k_sideflux")) return 1;
     mark();
     if (!multi) {
+        if (mortar && mortar_flux(h, P.Flux, 5, 1)) return 1;
         kt->volsurf(P, mode, mRKA, b_dt, c.nElems, h->s);
         if (check_launch(h, "k_volsurf")) return 1;
     } else {
@@ -265,8 +310,10 @@ int rhs(dgx_handle* h, int mode, double mRKA, double b_dt, StageTimes* st = null
         if (c.parabolic) CK(cudaStreamWaitEvent(h->s, h->evGhalo, 0));
         const int nMPI = c.lastMPISide_YOUR - c.firstMPISide_MINE + 1;
         if (nMPI > 0) { kt->sideflux(P, c.firstMPISide_MINE - 1, nMPI, h->s); if (check_launch(h, "k_sideflux(mpi)")) return 1; }
+        if (mortar && mortar_flux(h, P.Flux, 5, 1)) return 1;
         if (h->nBnd) { kt->volsurf(Pb, mode, mRKA, b_dt, h->nBnd, h->s); if (check_launch(h, "k_volsurf(bnd)")) return 1; }
     }
+    if (mode == 1 && mortar && mortar_u(h, P.UmNext, P.UsNext, 5)) return 1;
     mark();
     if (mode == 1) h->cur ^= 1;
     return 0;
@@ -277,7 +324,8 @@ int prolong_current(dgx_handle* h) {
     P.Um = h->Uf[h->cur][0];
     P.Us = h->Uf[h->cur][1];
     h->kt->prolong(P, h->cfg.nElems, h->s);
-    return check_launch(h, "k_prolong");
+    if (check_launch(h, "k_prolong")) return 1;
+    return h->hasMortar() ? mortar_u(h, P.Um, P.Us, 5) : 0;
 }
 
 int check_err_flag(dgx_handle* h, const char* where) {
@@ -351,6 +399,10 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
     if (c.splitDG >= 0 && c.riemann >= 4 && c.riemann <= 7) return fail(h, "HLL-type Riemann solvers are not supported for SPLIT_DG=ON (as in the reference, src/CMakeLists.txt:108-127)");
     if (c.splitDG < 0 && c.riemann == 9) return fail(h, "the flux-average Riemann solver requires SplitDG (riemann.f90:1236-1252)");
     if (c.nRKStages < 1) return fail(h, "nRKStages < 1");
+    if (c.lifting < 0 || c.lifting > 2) return fail(h, "lifting %d not available (1: BR1, 2: BR2)", c.lifting);
+    if (c.nMortarSides < 0) return fail(h, "nMortarSides < 0");
+    if (c.nMortarSides > 0 && (!c.MortarType || !c.MortarInfo || !c.M_0_1 || !c.M_0_2 || !c.M_1_0 || !c.M_2_0))
+        return fail(h, "mortar mesh (nMortarSides=%d) needs MortarType, MortarInfo and the operators M_0_1, M_0_2, M_1_0, M_2_0", c.nMortarSides);
     CK(cudaSetDevice(c.device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, c.device));
@@ -414,6 +466,25 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
     P.metrics = h->metrics; P.sJ = h->sJ; P.geo = h->geo;
     P.U = h->U; P.Ut = h->Ut; P.Ut_tmp = h->Ut_tmp; P.gradU = h->gradU;
     P.gm = h->gm; P.gs = h->gs; P.Flux = h->Flux; P.errFlag = h->errFlag;
+    P.lifting = c.lifting == 2 ? 2 : 1; P.etaBR2 = c.etaBR2; P.etaBR2_wall = c.etaBR2_wall;
+    P.MortarType = nullptr;
+    h->mp = MortarParams{nullptr, nullptr, nullptr, 0};
+    if (c.nMortarSides > 0) {
+        h->nMortarInner = c.lastMortarInnerSide - c.firstMortarInnerSide + 1;
+        h->nMortarMPI = c.lastMortarMPISide - c.firstMortarMPISide + 1;
+        if (h->nMortarInner < 0 || h->nMortarMPI < 0 || h->nMortarInner + h->nMortarMPI != c.nMortarSides)
+            return fail(h, "mortar side ranges do not add up to nMortarSides");
+        int *mt, *mi;
+        double* M;
+        if (upload(h, &mt, c.MortarType, (size_t)2 * c.nSides) || upload(h, &mi, c.MortarInfo, (size_t)8 * c.nMortarSides)) return 1;
+        std::vector<double> Mh((size_t)4 * n * n);
+        const double* src[4] = {c.M_0_1, c.M_0_2, c.M_1_0, c.M_2_0};
+        for (int k = 0; k < 4; k++) for (int x = 0; x < n * n; x++) Mh[(size_t)k * n * n + x] = src[k][x];
+        if (upload(h, &M, Mh.data(), Mh.size())) return 1;
+        CK(cudaStreamSynchronize(h->s));
+        P.MortarType = mt;
+        h->mp = MortarParams{mt, mi, M, 0};
+    }
     P.elemList = nullptr; P.nList = 0;
     P.flags = getenv("DGX_FLAGS") ? atoi(getenv("DGX_FLAGS")) : DGX_DEFAULT_FLAGS;
     // benign state on faces that are never written (slave side of BC sides), cf. dg.f90:118-121
@@ -442,7 +513,12 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
         std::vector<int> inner, bnd;
         for (int e = 0; e < c.nElems; e++) {
             bool mpi = false;
-            for (int l = 0; l < 6; l++) if (c.ElemToSide[0 + 3 * (l + 6 * e)] >= c.firstMPISide_MINE) mpi = true;
+            for (int l = 0; l < 6; l++) {
+                const int sid = c.ElemToSide[0 + 3 * (l + 6 * e)];
+                if (sid >= c.firstMPISide_MINE) mpi = true;
+                // big mortar sides depend on small sides that may be MPI sides: keep their elements behind the halo
+                if (c.nMortarSides > 0 && c.MortarType[2 * (sid - 1)] > 0) mpi = true;
+            }
             (mpi ? bnd : inner).push_back(e);
         }
         h->nInner = (int)inner.size(); h->nBnd = (int)bnd.size();
@@ -455,6 +531,8 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
     }
     CK(cudaStreamSynchronize(h->s));
     h->cfg.RefStatePrim = nullptr;  // pointers are not retained
+    h->cfg.MortarType = h->cfg.MortarInfo = nullptr;
+    h->cfg.M_0_1 = h->cfg.M_0_2 = h->cfg.M_1_0 = h->cfg.M_2_0 = nullptr;
     return 0;
 }
 

@@ -53,6 +53,8 @@ struct L {
         cudaError_t e;
         e = cudaFuncSetAttribute(k_lifting<n, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lifting_smem_bytes<n>());
         if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(k_lifting<n, NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lifting_smem_bytes<n>());
+        if (e != cudaSuccess) return (int)e;
         e = cudaFuncSetAttribute(k_volsurf<n, NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)volsurf_smem_bytes<n>());
         if (e != cudaSuccess) return (int)e;
         e = cudaFuncSetAttribute(k_volsurf<n, NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)volsurf_smem_bytes<n>());
@@ -73,7 +75,17 @@ struct L {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_lifting<n, NT>, n3, lifting_smem_bytes<n>());
             resident = sms * (per > 0 ? per : 1);
         }
-        k_lifting<n, NT><<<nb, n3, lifting_smem_bytes<n>(), s>>>(P, resident);
+        if (P.lifting == 2 || P.MortarType) k_lifting<n, NT, 1><<<nb, n3, lifting_smem_bytes<n>(), s>>>(P, resident);
+        else k_lifting<n, NT><<<nb, n3, lifting_smem_bytes<n>(), s>>>(P, resident);
+    }
+    static void umortar(double* am, double* as, int nvar, const MortarParams& mp, int nBig, cudaStream_t s) {
+        if (nBig > 0) k_umortar<n><<<dim3(nBig, nvar), n * n, 0, s>>>(am, as, nvar, mp);
+    }
+    static void fluxmortar(double* F, int nvar, int weak, const MortarParams& mp, int nBig, cudaStream_t s) {
+        if (nBig > 0) k_fluxmortar<n><<<dim3(nBig, nvar), n * n, 0, s>>>(F, nvar, weak, mp);
+    }
+    static void mortar_liftflux(const KParams& P, const MortarParams& mp, int nBig, cudaStream_t s) {
+        if (nBig > 0) k_mortar_liftflux<n><<<dim3(nBig, 12), n * n, 0, s>>>(P, mp);
     }
     static void sideflux(const KParams& P, int side0, int nS, cudaStream_t s) {
         if (nS <= 0) return;
@@ -96,8 +108,10 @@ struct L {
         if (P.nElems > 0) k_timestep<n><<<P.nElems, timestep_threads<n>(), 0, s>>>(P, CFL, DFL, out);
     }
 };
-const KernelTable tabG = {L<1>::setup, L<1>::prolong, L<1>::lifting, L<1>::sideflux, L<1>::volsurf, L<1>::timestep};
-const KernelTable tabGL = {L<2>::setup, L<2>::prolong, L<2>::lifting, L<2>::sideflux, L<2>::volsurf, L<2>::timestep};
+const KernelTable tabG = {L<1>::setup, L<1>::prolong, L<1>::lifting, L<1>::sideflux, L<1>::volsurf, L<1>::timestep,
+                          L<1>::umortar, L<1>::fluxmortar, L<1>::mortar_liftflux};
+const KernelTable tabGL = {L<2>::setup, L<2>::prolong, L<2>::lifting, L<2>::sideflux, L<2>::volsurf, L<2>::timestep,
+                           L<2>::umortar, L<2>::fluxmortar, L<2>::mortar_liftflux};
 }  // namespace
 
 #define DGX_CAT2(a, b) a##b

@@ -57,6 +57,10 @@ struct KParams {
     const int* elemList;  // optional indirection (MPI-boundary / inner element lists), or nullptr
     int nList;
     int* errFlag;
+    // general lifting path (k_lifting<..., GEN=1>): BR2 (host FLEXI, dg/lifting/lifting_br2.t90) and/or big mortar faces
+    int lifting;               // 1 BR1, 2 BR2
+    double etaBR2, etaBR2_wall;
+    const int* MortarType;     // (2,nSides) or nullptr when the mesh has no mortars
     int flags;  // tuning switches (DGX_FLAGS): 1 lifting: L2 prefetch of own later-phase data; 2 lifting: L2 prefetch of the element
                 // a resident wave ahead; 4 / 8: the same two for k_volsurf2
 };
@@ -202,10 +206,14 @@ __global__ void __launch_bounds__(n* n* n) k_prolong(const KParams P) {
 
 // ---------------------------------------------------------------------------------------------------------
 // BR1 lifting (strong form, non-conservative volume integral): gradU = sJ * ( M . D U + sum_faces F n Lhat )
-template <int n, int NT>
+// GEN=0: BR1 on conforming meshes (the GALAEXI configuration, hot path). GEN=1: BR2 and/or elements with a big mortar
+// face, whose projected lifting flux (times normal) k_mortar_liftflux has left in gm[bigSide].
+template <int n, int NT, int GEN = 0>
 __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting(const KParams P, int lookahead) {
     constexpr int n2 = n * n, n3 = n2 * n;
     extern __shared__ double smem[];
+    __shared__ int sMort[6];  // GEN: 0-based big mortar side of local side loc, or -1
+    const bool br2 = GEN && P.lifting == 2;
     double* sT = smem;                 // [4][n3] lifting variables; later aliased by the gradient tile [12][n3]
     double* sG = smem;                 // alias (used after the sweeps are done)
     double* sF = smem + 12 * n3;       // [6][7][n2] face lifting flux (4) + normal (3), element face order
@@ -257,6 +265,11 @@ __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting
         const int pq = p + n * q;
         const int a = s2v2<n>(P.S2V2, 0, p, q, flip, loc);
         const int b = s2v2<n>(P.S2V2, 1, p, q, flip, loc);
+        if (GEN) {
+            const bool big = P.MortarType && __ldg(&P.MortarType[2 * side]) > 0;
+            if (f == (loc - 1) * n2) sMort[loc - 1] = big ? side : -1;
+            if (big) continue;  // flux comes projected from the small sides
+        }
         const double* g = P.geo + (size_t)side * 10 * n2 + pq;
         const double nv[3] = {g[0 * n2], g[1 * n2], g[2 * n2]};
         const double se = g[9 * n2];
@@ -327,14 +340,29 @@ __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting
             } else {
                 Lh = minus ? sLhm[l] : sLhp[l];
             }
+            const double sJn = GEN ? P.sJ[(size_t)e * n3 + t] : 1.0;  // BR2: F_loc = sJ * Flux * L_hat (lifting_br2.t90:252,293)
+            if (GEN && sMort[loc - 1] >= 0) {
+                // big mortar face: projected flux*normal in side-local (flip 0) node order
+                const int p = s2v2<n>(P.S2V2inv, 0, a, b, 0, loc), q = s2v2<n>(P.S2V2inv, 1, a, b, 0, loc);
+                const double* gF = P.gm + (size_t)sMort[loc - 1] * 12 * n2 + (p + n * q);
+#pragma unroll
+                for (int x = 0; x < 12; x++) S[x] += br2 ? (sJn * gF[x * n2]) * Lh : gF[x * n2] * Lh;
+                continue;
+            }
             const double* s = sF + (loc - 1) * 7 * n2 + (b * n + a);
             const double nx = s[4 * n2], ny = s[5 * n2], nz = s[6 * n2];
 #pragma unroll
             for (int v = 0; v < 4; v++) {
                 const double F = s[v * n2];
-                S[0 * 4 + v] += (F * nx) * Lh;
-                S[1 * 4 + v] += (F * ny) * Lh;
-                S[2 * 4 + v] += (F * nz) * Lh;
+                if (br2) {
+                    S[0 * 4 + v] += (sJn * (F * nx)) * Lh;
+                    S[1 * 4 + v] += (sJn * (F * ny)) * Lh;
+                    S[2 * 4 + v] += (sJn * (F * nz)) * Lh;
+                } else {
+                    S[0 * 4 + v] += (F * nx) * Lh;
+                    S[1 * 4 + v] += (F * ny) * Lh;
+                    S[2 * 4 + v] += (F * nz) * Lh;
+                }
             }
         }
         const double sJ = P.sJ[(size_t)e * n3 + t];
@@ -342,16 +370,101 @@ __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting
         for (int d = 0; d < 3; d++) {
             const double mf = M[(0 + d) * n3], mg = M[(3 + d) * n3], mh = M[(6 + d) * n3];
 #pragma unroll
-            for (int v = 0; v < 4; v++) G[d * 4 + v] = sJ * ((mf * gxi[v] + mg * get[v] + mh * gze[v]) + S[d * 4 + v]);
+            for (int v = 0; v < 4; v++) {
+                if (br2) {
+                    // volume part times sJ (ApplyJacobianLifting, lifting_br2.t90:118-124); S holds the surface part
+                    G[d * 4 + v] = (mf * gxi[v] + mg * get[v] + mh * gze[v]) * sJ;
+                } else {
+                    G[d * 4 + v] = sJ * ((mf * gxi[v] + mg * get[v] + mh * gze[v]) + S[d * 4 + v]);
+                }
+            }
+        }
+        if (br2) {
+            __syncthreads();  // all reads of sT done before it is overwritten by the gradient tile
+            double* gU = P.gradU + (size_t)e * 12 * n3 + t;
+#pragma unroll
+            for (int x = 0; x < 12; x++) { sG[x * n3 + tid_] = G[x]; gU[x * n3] = G[x] + S[x]; }
         }
     }
-    __syncthreads();  // all reads of sT done before it is overwritten by the gradient tile
-    double* gU = P.gradU + (size_t)e * 12 * n3 + t;
+    if (!br2) {
+        __syncthreads();  // all reads of sT done before it is overwritten by the gradient tile
+        double* gU = P.gradU + (size_t)e * 12 * n3 + t;
 #pragma unroll
-    for (int x = 0; x < 12; x++) { gU[x * n3] = G[x]; sG[x * n3 + tid_] = G[x]; }
+        for (int x = 0; x < 12; x++) { gU[x * n3] = G[x]; sG[x * n3 + tid_] = G[x]; }
+    }
     __syncthreads();
     // 4. gradients on the faces (ProlongToFaceLifting)
-    extract_faces_tile<n, NT, 12>(sG, P.gm, P.gs, e2s, P.S2V2, sLm, sLp);
+    if (!br2) {
+        extract_faces_tile<n, NT, 12>(sG, P.gm, P.gs, e2s, P.S2V2, sLm, sLp);
+        return;
+    }
+    // BR2 (lifting_br2.t90:126-137, 193-313): trace of the volume part + eta * sum_l L_Minus(l) F_loc(l), F_loc(l) =
+    // sJ(depth l) * Flux * L_HatMinus(l); l = depth from the face (Gauss-Lobatto: l = 0 only)
+    if (GEN) {
+        constexpr int SL = Tile<n>::SLOT;
+        for (int f = t; f < 6 * n2; f += n3) {
+            const int loc = f / n2 + 1;
+            const int side = __ldg(&e2s[0 + 3 * (loc - 1)]) - 1;
+            const int flip = __ldg(&e2s[1 + 3 * (loc - 1)]);
+            const bool xi = (loc == XI_MINUS || loc == XI_PLUS), eta_ = (loc == ETA_MINUS || loc == ETA_PLUS);
+            const bool minus = is_minus(loc);
+            int p, q;
+            face_lane<n>(P.S2V2, f - (loc - 1) * n2, flip, loc, xi, p, q);
+            const int a = s2v2<n>(P.S2V2, 0, p, q, flip, loc);
+            const int b = s2v2<n>(P.S2V2, 1, p, q, flip, loc);
+            double eta = P.etaBR2;
+            if (side < P.nBCSides) {
+                const int bct = __ldg(&P.BCSides[2 * side]);
+                if (bct == 3 || bct == 4) eta = P.etaBR2_wall;
+            }
+            // flux times normal at this face node
+            double Fd[12];
+            if (sMort[loc - 1] >= 0) {
+                const double* gF = P.gm + (size_t)side * 12 * n2 + (p + n * q);  // flip == 0 on a big mortar side
+#pragma unroll
+                for (int x = 0; x < 12; x++) Fd[x] = gF[x * n2];
+            } else {
+                const double* s = sF + (loc - 1) * 7 * n2 + (b * n + a);
+#pragma unroll
+                for (int d = 0; d < 3; d++)
+#pragma unroll
+                    for (int v = 0; v < 4; v++) Fd[d * 4 + v] = s[v * n2] * s[(4 + d) * n2];
+            }
+            double acc[12];
+            // trace of the volume part
+            if (NT == 2) {
+                const int l = minus ? 0 : n - 1;
+                const int id = xi ? Tile<n>::idx(l, a, b) : (eta_ ? Tile<n>::idx(a, l, b) : Tile<n>::idx(a, b, l));
+#pragma unroll
+                for (int x = 0; x < 12; x++) acc[x] = sG[x * SL + id];
+            } else {
+                const double* L = minus ? sLm : sLp;
+#pragma unroll
+                for (int x = 0; x < 12; x++) {
+                    double r = 0.0;
+#pragma unroll
+                    for (int l = 0; l < n; l++) {
+                        const int id = xi ? Tile<n>::idx(l, a, b) : (eta_ ? Tile<n>::idx(a, l, b) : Tile<n>::idx(a, b, l));
+                        r = (l == 0) ? sG[x * SL + id] * L[0] : r + sG[x * SL + id] * L[l];
+                    }
+                    acc[x] = r;
+                }
+            }
+            // penalised surface part
+            const int lmax = (NT == 2) ? 1 : n;
+            for (int l = 0; l < lmax; l++) {
+                const int ln = minus ? l : n - 1 - l;  // node index along the face normal at depth l
+                const int node = xi ? (ln + n * (a + n * b)) : (eta_ ? (a + n * (ln + n * b)) : (a + n * (b + n * ln)));
+                const double sJl = P.sJ[(size_t)e * n3 + node];
+                const double w = eta * sLm[l];
+#pragma unroll
+                for (int x = 0; x < 12; x++) acc[x] += w * ((sJl * Fd[x]) * sLhm[l]);
+            }
+            double* dst = (flip == 0 ? P.gm : P.gs) + (size_t)side * 12 * n2 + (p + n * q);
+#pragma unroll
+            for (int x = 0; x < 12; x++) dst[x * n2] = acc[x];
+        }
+    }
 }
 
 template <int n>
@@ -366,6 +479,7 @@ __global__ void __launch_bounds__(128, 4) k_sideflux(const KParams P, int side0,
     if (gid >= nS * n2) return;
     const int side = side0 + gid / n2;
     const int pq = gid % n2;
+    if (side >= P.nBCSides && side < P.firstInner - 1) return;  // big mortar sides: filled by k_fluxmortar
     const Eos eos = P.eos;
     const double* g = P.geo + (size_t)side * 10 * n2 + pq;
     const double nv[3] = {g[0 * n2], g[1 * n2], g[2 * n2]};

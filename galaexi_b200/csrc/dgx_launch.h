@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "dgx_kernels.cuh"
+#include "dgx_mortar.cuh"
 
 namespace dgx {
 struct KernelTable {
@@ -11,6 +12,10 @@ struct KernelTable {
     void (*sideflux)(const KParams&, int side0, int nS, cudaStream_t);
     void (*volsurf)(const KParams&, int mode, double mRKA, double b_dt, int nBlocks, cudaStream_t);
     void (*timestep)(const KParams&, double CFL, double DFL, double* out, cudaStream_t);
+    // non-conforming interfaces (nBig big mortar sides starting at mp.side0)
+    void (*umortar)(double* am, double* as, int nvar, const MortarParams& mp, int nBig, cudaStream_t);
+    void (*fluxmortar)(double* F, int nvar, int weak, const MortarParams& mp, int nBig, cudaStream_t);
+    void (*mortar_liftflux)(const KParams&, const MortarParams& mp, int nBig, cudaStream_t);
 };
 const KernelTable* kernel_table(int N, int nodeType);  // nullptr if this N was not compiled in
 }  // namespace dgx

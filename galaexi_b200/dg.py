@@ -47,6 +47,10 @@ class DgxConfig(C.Structure):
         + [(k, _ip) for k in ("NbProc", "nMPISides_MINE_Proc", "nMPISides_YOUR_Proc", "offsetMPISides_MINE",
                               "offsetMPISides_YOUR")]
         + [("ncclUniqueId", C.c_char_p), ("device", C.c_int)]
+        + [("lifting", C.c_int), ("etaBR2", C.c_double), ("etaBR2_wall", C.c_double)]
+        + [(k, C.c_int) for k in ("nMortarSides", "firstMortarInnerSide", "lastMortarInnerSide", "firstMortarMPISide",
+                                  "lastMortarMPISide")]
+        + [("MortarType", _ip), ("MortarInfo", _ip)] + [(k, _dp) for k in ("M_0_1", "M_0_2", "M_1_0", "M_2_0")]
     )
 
 
@@ -138,6 +142,10 @@ class DGSolver:
             nMPISides_YOUR_Proc=i32(m.nMPISides_YOUR_Proc if m.nNbProcs else np.zeros(1)),
             offsetMPISides_MINE=i32(m.offsetMPISides_MINE if m.nNbProcs else np.zeros(2)),
             offsetMPISides_YOUR=i32(m.offsetMPISides_YOUR if m.nNbProcs else np.zeros(2)),
+            MortarType=i32(m.MortarType), MortarInfo=i32(m.MortarInfo),
+            # mortar operators: Fortran M(l,p) at [l + n*p] == C array M.T
+            M_0_1=f64(case.mortar["M_0_1"].T), M_0_2=f64(case.mortar["M_0_2"].T),
+            M_1_0=f64(case.mortar["M_1_0"].T), M_2_0=f64(case.mortar["M_2_0"].T),
         )
         self._keep = k
         c = DgxConfig()
@@ -156,8 +164,14 @@ class DGSolver:
                    "SurfElem", "RKA", "RKb", "RKc"):
             setattr(c, nm, k[nm].ctypes.data_as(_dp))
         for nm in ("BCSides", "ElemToSide", "S2V2", "S2V2_inv", "NbProc", "nMPISides_MINE_Proc",
-                   "nMPISides_YOUR_Proc", "offsetMPISides_MINE", "offsetMPISides_YOUR"):
+                   "nMPISides_YOUR_Proc", "offsetMPISides_MINE", "offsetMPISides_YOUR", "MortarType", "MortarInfo"):
             setattr(c, nm, k[nm].ctypes.data_as(_ip))
+        for nm in ("M_0_1", "M_0_2", "M_1_0", "M_2_0"):
+            setattr(c, nm, k[nm].ctypes.data_as(_dp))
+        c.lifting, c.etaBR2, c.etaBR2_wall = case.lifting, case.etaBR2, case.etaBR2_wall
+        c.nMortarSides = m.nMortarSides
+        c.firstMortarInnerSide, c.lastMortarInnerSide = m.firstMortarInnerSide, m.lastMortarInnerSide
+        c.firstMortarMPISide, c.lastMortarMPISide = m.firstMortarMPISide, m.lastMortarMPISide
         c.nRKStages, c.CFLScale, c.DFLScale = td.nRKStages, td.CFLScale, td.DFLScale
         c.myRank, c.nRanks, c.nNbProcs = m.myRank, m.nProcs, m.nNbProcs
         self._id = nccl_id

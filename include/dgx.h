@@ -46,7 +46,7 @@ typedef struct dgx_config {
     int splitDG;        /* SPLIT_DG: -1 off (weak form), 0 SD, 1 MO, 2 DU, 3 KG, 4 PI (src/CMakeLists.txt:73-92) */
     int riemann;        /* RIEMANN: 0 LF, 1 Roe, 2 RoeL2, 3 RoeEntropyFix, 4 HLL, 5 HLLC, 6 HLLE, 7 HLLEM (4-7: non-split
                          * only, src/CMakeLists.txt:97-130); 9 FluxAverage (split only, riemann.f90:1239) */
-    int parabolic;      /* PARABOLIC: 0 Euler, 1 Navier-Stokes with BR1 lifting */
+    int parabolic;      /* PARABOLIC: 0 Euler, 1 Navier-Stokes with BR1 (or BR2, see `lifting`) gradients */
     int viscLaw;        /* PP_VISC: 0 constant, 1 Sutherland */
     /* mesh sizes and side ranges (1-based inclusive, mesh/mesh.f90:259-283) */
     int nElems, nSides, nBCSides;
@@ -79,6 +79,17 @@ typedef struct dgx_config {
     const int *offsetMPISides_YOUR;  /* (0:nNbProcs) */
     const char *ncclUniqueId;        /* 128 bytes from ncclGetUniqueId on rank 0 (broadcast by the host), or NULL */
     int device;                      /* CUDA device ordinal for this rank */
+    /* lifting variant (PP_Lifting, src/CMakeLists.txt:161-183): 0/1 BR1 (the only one GALAEXI builds), 2 BR2 (host FLEXI
+     * code, dg/lifting/lifting_br2.t90:43-313) with the penalties etaBR2 / etaBR2_wall (lifting.f90:86-91) */
+    int lifting;
+    double etaBR2, etaBR2_wall;
+    /* non-conforming interfaces (host FLEXI code src/mortar/; GALAEXI aborts on them, mesh/mesh.f90:140-143):
+     * side ranges mesh.f90:271-283, MortarType(2,nSides), MortarInfo(2,4,nMortarSides) (mesh.f90:318-322,
+     * prepare_mesh.f90:746-775), 1-D operators (0:N,0:N) as stored by mortar.f90:111-256 (transposed). nMortarSides==0:
+     * all unused. */
+    int nMortarSides, firstMortarInnerSide, lastMortarInnerSide, firstMortarMPISide, lastMortarMPISide;
+    const int *MortarType, *MortarInfo;
+    const double *M_0_1, *M_0_2, *M_1_0, *M_2_0;
 } dgx_config;
 
 int dgx_create(dgx_handle **h, const dgx_config *cfg);

@@ -241,3 +241,52 @@ def test_freestream_and_conservation_full_size():
     ref[1:4] = ref[1:4].max()  # the TGV has no z-momentum at t=0: one common momentum scale
     assert np.all(np.abs(d) <= 1e-11 * ref)
     s.FinalizeDG()
+
+
+# ---- non-conforming (mortar) interfaces and BR2 lifting: host-FLEXI features ---------------------
+@pytest.mark.parametrize("mesh,N,node_type,split,riemann,lifting", [
+    ("002", 3, "GAUSS", None, "Roe", "br1"),
+    ("002", 4, "GAUSS-LOBATTO", "PI", "RoeEntropyFix", "br1"),
+    ("004", 3, "GAUSS-LOBATTO", None, "LF", "br1"),
+    ("004", 2, "GAUSS", None, "HLLC", "br2"),
+    ("001", 5, "GAUSS-LOBATTO", "KG", "Roe", "br2"),
+    ("002", 7, "GAUSS-LOBATTO", "PI", "RoeEntropyFix", "br1"),
+])
+def test_mortar_meshes(mesh, N, node_type, split, riemann, lifting):
+    """The reference's CART_HEX_PERIODIC_MORTAR meshes (types 1, 2, 3): U_Mortar / Flux_Mortar / lifting on mortars."""
+    c, U0 = cases.mortar_case(mesh, N=N, node_type=node_type, split=split, riemann=riemann, lifting=lifting)
+    assert c.mesh.nMortarSides > 0
+    _compare_rhs_and_steps(c, U0, nsteps=2)
+
+
+def test_mortar_euler_and_free_stream():
+    from galaexi_b200.host import equation as eq
+    c, U0 = cases.mortar_case("004", N=3, parabolic=False, riemann="Roe")
+    _compare_rhs_and_steps(c, U0, nsteps=2)
+    c, _ = cases.mortar_case("004", N=4, node_type="GAUSS-LOBATTO", split="PI", riemann="RoeEntropyFix")
+    Uu = eq.ini_refstate(c.geo["Elem_xGP"], c.RefStatePrim[0], c.eos)
+    s = _solver(c)
+    s.set_state(Uu)
+    s.DGTimeDerivative_weakForm(0.0)
+    assert np.abs(s.get_ut()).max() <= 1e-10
+    s.FinalizeDG()
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("tgv", dict(E=4, N=5, NGeo=2, deform=0.05, perturb=1e-3)),
+    ("tgv_gauss", dict(E=3, N=3, NGeo=2, deform=0.05, perturb=1e-3, node_type="GAUSS", split=None, riemann="Roe")),
+    ("cavity", {}),
+    ("channel", dict(E=3, N=4)),
+])
+def test_br2_lifting(name, kw):
+    """Lifting_BR2 (lifting_br2.t90): conforming meshes, curved, with wall BCs (etaBR2_wall) and both node types."""
+    if name.startswith("tgv"):
+        c, U0 = cases.tgv_box_case(lifting="br2", **kw)
+    elif name == "cavity":
+        c, U0 = cases.cavity_case(lifting="br2", etaBR2=2.0, etaBR2_wall=3.0)
+        x = c.geo["Elem_xGP"]
+        U0 = U0 * (1.0 + 0.01 * np.sin(5.0 * x[..., 0] + 1.0) * np.cos(3.0 * x[..., 1]) * np.sin(4.0 * x[..., 2] + 0.5))[..., None]
+    else:
+        c, U0 = cases.channel_case(lifting="br2", etaBR2_wall=4.0, **kw)
+    assert c.lifting == 2
+    _compare_rhs_and_steps(c, U0, nsteps=2)

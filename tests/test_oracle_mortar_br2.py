@@ -1,0 +1,161 @@
+"""Oracle checks for the two host-FLEXI features GALAEXI's GPU path lacks: non-conforming (mortar) interfaces and BR2
+lifting.
+
+PARITY UNPINNED by reference artefacts: the reference ships the mortar meshes (tutorials/convtest/
+CART_HEX_PERIODIC_MORTAR_*) but no solution on them, and BR2 is SEND_ERROR in its build (src/CMakeLists.txt:180).
+The restatement is therefore checked through size-independent properties of the scheme: free-stream preservation,
+discrete conservation (the mortar projection conserves the face integral of the flux), exact lifted gradients of
+linear fields across mortar interfaces, BR1 == BR2 volume gradients, and invariance under the rank count."""
+import numpy as np
+import pytest
+
+import cases
+from galaexi_b200.host import basis as bs
+from galaexi_b200.host import equation as eq
+from galaexi_b200.host import mesh as ms
+from galaexi_b200.host import mortar as mo
+from oracle.oracle import Oracle
+
+
+def _integral(c, Ut):
+    w = c.basis.wGP
+    W = w[:, None, None] * w[None, :, None] * w[None, None, :]
+    return np.einsum("ekji,ekjiv->v", W[None] / c.geo["sJ"], Ut)
+
+
+@pytest.mark.parametrize("N", [1, 3, 6])
+@pytest.mark.parametrize("node_type", [bs.NODETYPE_G, bs.NODETYPE_GL])
+def test_mortar_operators(N, node_type):
+    """mortar.f90:88-101 mean-value check, interpolation exactness and projection o interpolation = identity."""
+    m = mo.init_mortar(N, node_type)
+    xi, w, _ = bs.get_nodes_and_weights(N, node_type)
+    for k in range(N + 1):
+        f = xi ** k
+        assert np.allclose(m["M_0_1"].T @ f, (0.5 * (xi - 1.0)) ** k, atol=1e-13)
+        assert np.allclose(m["M_0_2"].T @ f, (0.5 * (xi + 1.0)) ** k, atol=1e-13)
+        # a polynomial of degree <= N restricted to both halves and projected back is reproduced (the operators
+        # lack the interval Jacobian 1/2, which the small-side surface element carries)
+        back = 0.5 * (m["M_1_0"].T @ (m["M_0_1"].T @ f) + m["M_2_0"].T @ (m["M_0_2"].T @ f))
+        assert np.allclose(back, f, atol=1e-12)
+
+
+def test_general_mesh_walk_equals_vectorised_path_on_conforming_meshes():
+    import dataclasses
+    for h, ranks in ((cases.load_mesh("cavity3d_mesh.npz"), (1, 2, 3)), (cases.load_mesh("naca_mesh.npz"), (1, 3)),
+                     (ms.make_box_mesh((4, 4, 4)), (1, 2, 7)),
+                     (ms.make_box_mesh((3, 2, 2), bctype=["periodic", (3, 0), (2, 1), (3, 0), (2, 1), "periodic"]), (1, 2))):
+        for nP in ranks:
+            for r in range(nP):
+                a, b = ms.prepare_mesh(h, nP, r), ms.prepare_mesh(h, nP, r, general=True)
+                for f in dataclasses.fields(a):
+                    x, y = getattr(a, f.name), getattr(b, f.name)
+                    if f.name in ("MortarInfo", "YourMaster"):
+                        continue
+                    if isinstance(x, np.ndarray):
+                        assert np.array_equal(x, y), (f.name, nP, r)
+                    else:
+                        assert x == y, (f.name, nP, r)
+
+
+@pytest.mark.parametrize("mesh", ["001", "002", "004"])
+def test_mortar_side_tables(mesh):
+    h = cases.load_mesh(f"cart_mortar_{mesh}_mesh.npz")
+    m = ms.prepare_mesh(h)
+    assert m.nMortarSides == m.nMortarInnerSides > 0 and m.nMortarMPISides == 0
+    big = np.nonzero(m.MortarType[:, 0] > 0)[0] + 1
+    assert np.array_equal(big, np.arange(m.firstMortarInnerSide, m.lastMortarInnerSide + 1))
+    for sd in big:
+        t, idx = m.MortarType[sd - 1]
+        info = m.MortarInfo[idx - 1]
+        nm = 4 if t == 1 else 2
+        assert np.all(info[:nm, 0] >= m.firstInnerSide) and np.all(info[:nm, 1] == 0) and np.all(info[nm:, 0] == -1)
+        assert m.SideToElem[sd - 1, 0] > 0 and m.SideToElem[sd - 1, 1] == -1      # big side: master element only
+        for s2 in info[:nm, 0]:
+            assert m.SideToElem[s2 - 1, 0] == -1 and m.SideToElem[s2 - 1, 1] > 0  # small side: slave element only
+            assert m.MortarType[s2 - 1, 0] == -1
+    # every rank count keeps the global side census
+    for nP in (2, 3):
+        parts = [ms.prepare_mesh(h, nP, r) for r in range(nP)]
+        assert sum(p.nMortarSides for p in parts) == m.nMortarSides
+        assert sum(p.nMPISides_MINE for p in parts) == sum(p.nMPISides_YOUR for p in parts)
+        assert sum(p.nInnerSides + p.nMPISides_MINE for p in parts) == m.nInnerSides
+
+
+@pytest.mark.parametrize("mesh", ["001", "002", "004"])
+@pytest.mark.parametrize("node_type,split,riemann", [(bs.NODETYPE_G, None, "Roe"), (bs.NODETYPE_GL, "PI", "RoeEntropyFix"),
+                                                     (bs.NODETYPE_GL, None, "LF")])
+@pytest.mark.parametrize("lifting", ["br1", "br2"])
+def test_mortar_free_stream_and_conservation(mesh, node_type, split, riemann, lifting):
+    c, U0 = cases.mortar_case(mesh, N=3, node_type=node_type, split=split, riemann=riemann, lifting=lifting)
+    o = Oracle(c)
+    o.set_state(eq.ini_refstate(c.geo["Elem_xGP"], c.RefStatePrim[0], c.eos))
+    assert np.abs(o.time_derivative()).max() <= 2e-11
+    o.set_state(U0)
+    Ut = o.time_derivative().copy()
+    assert np.all(np.abs(_integral(c, Ut)) <= 1e-13 * _integral(c, np.abs(Ut)))
+    o.close()
+
+
+@pytest.mark.parametrize("mesh", ["002", "004"])
+@pytest.mark.parametrize("node_type", [bs.NODETYPE_G, bs.NODETYPE_GL])
+@pytest.mark.parametrize("lifting", ["br1", "br2"])
+def test_linear_field_gradients_are_exact_across_mortars(mesh, node_type, lifting):
+    c, _ = cases.mortar_case(mesh, N=3, node_type=node_type, lifting=lifting, bc=(2, 1))
+    x = c.geo["Elem_xGP"]
+    prim = np.zeros(x.shape[:-1] + (6,))
+    prim[..., 0] = 1.0 + 0.05 * x[..., 0]
+    prim[..., 1] = 0.3 + 0.2 * x[..., 0] - 0.1 * x[..., 1] + 0.05 * x[..., 2]
+    prim[..., 2] = 0.1 * x[..., 1]
+    prim[..., 3] = -0.3 * x[..., 2] + 0.1 * x[..., 0]
+    prim[..., 4] = prim[..., 0] * c.eos.R * (1.0 + 0.1 * x[..., 0] - 0.05 * x[..., 2])
+    o = Oracle(c)
+    o.set_state(eq.prim_to_cons(prim, c.eos.kappa))
+    o.time_derivative()
+    m = c.mesh
+    inner = np.all(m.ElemToSide[:, :, 0] > m.nBCSides, axis=1)        # no Dirichlet face: the field is continuous there
+    assert np.any(inner & np.any(m.MortarType[m.ElemToSide[:, :, 0] - 1, 0] != 0, axis=1))
+    exact = {1: (0.2, -0.1, 0.05), 2: (0.0, 0.1, 0.0), 3: (0.1, 0.0, -0.3), 4: (0.1, 0.0, -0.05)}
+    for v, g in exact.items():
+        for d, nm in enumerate(("gradUx", "gradUy", "gradUz")):
+            assert np.abs(o.array(nm)[inner][..., v] - g[d]).max() <= 1e-12
+    o.close()
+
+
+@pytest.mark.parametrize("builder", ["tgv", "cavity", "mortar"])
+def test_br2_volume_gradients_equal_br1(builder):
+    """Both schemes lift with the full surface term in the volume (lifting_br2.t90:252-256 vs lifting_br1.t90:118-124);
+    they differ only in the face traces (penalised local lift)."""
+    def make(lifting):
+        if builder == "tgv":
+            return cases.tgv_box_case(E=3, N=4, NGeo=2, deform=0.05, perturb=1e-3, lifting=lifting)
+        if builder == "cavity":
+            c, U = cases.cavity_case(lifting=lifting)
+            xx = c.geo["Elem_xGP"]
+            return c, U * (1.0 + 0.01 * np.sin(5.0 * xx[..., 0] + 1.0) * np.cos(3.0 * xx[..., 1]))[..., None]
+        return cases.mortar_case("004", N=3, lifting=lifting)
+    res = {}
+    for lifting in ("br1", "br2"):
+        c, U0 = make(lifting)
+        o = Oracle(c)
+        o.set_state(U0)
+        o.time_derivative()
+        res[lifting] = [o.array(nm).copy() for nm in ("gradUx", "gradUy", "gradUz", "gradUx_master", "gradUx_slave")]
+        o.close()
+    scale = max(np.abs(a).max() for a in res["br1"][:3])
+    for a, b in zip(res["br1"][:3], res["br2"][:3]):
+        assert np.abs(a - b).max() <= 1e-12 * scale
+    assert np.abs(res["br1"][3] - res["br2"][3]).max() > 1e-6 * scale      # the traces do differ
+
+
+def test_br2_trace_is_local_gradient_plus_eta_times_face_lift():
+    """One-sided check of lifting_br2.t90:193-313 on Gauss-Lobatto nodes: trace = local (D U) gradient + eta * sJ *
+    Flux * L_HatMinus(0), so (trace(eta=3) - trace(eta=1)) = 2 * (trace(eta=2) - trace(eta=1))."""
+    tr = {}
+    for eta in (1.0, 2.0, 3.0):
+        c, U0 = cases.tgv_box_case(E=3, N=3, NGeo=2, deform=0.05, perturb=1e-3, lifting="br2", etaBR2=eta)
+        o = Oracle(c)
+        o.set_state(U0)
+        o.time_derivative()
+        tr[eta] = o.array("gradUy_master").copy()
+        o.close()
+    assert np.allclose(tr[3.0] - tr[1.0], 2.0 * (tr[2.0] - tr[1.0]), rtol=0, atol=1e-12 * np.abs(tr[1.0]).max())

@@ -115,10 +115,23 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """Use every host core this process may run on, also under torchrun (which exports OMP_NUM_THREADS=1): the oracle's
+    OpenMP runtime is told directly."""
+    import ctypes
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except OSError:
+        n = int(os.environ.get("OMP_NUM_THREADS", n))
+    return n
+
+
 def cpu_baseline(sample_elems=12, steps=1, N=N_POLY):
     """The CPU oracle (a port of the reference algorithm, NOT the reference binary) on the host cores, on a bounded
     sample of the same workload: TGV N=7 split-form NS on sample_elems^3 elements, `steps` RK steps."""
     from oracle.oracle import Oracle
+    cores = host_threads()
     c, U0 = build_case(1, 0, elems=(sample_elems,) * 3, N=N)
     o = Oracle(c)
     o.set_state(U0)
@@ -133,7 +146,6 @@ def cpu_baseline(sample_elems=12, steps=1, N=N_POLY):
     wall = time.perf_counter() - t0
     ndof = c.nDOF
     o.close()
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     return dict(value=ndof * NSTAGES * steps / wall, unit="DOF*stage/s", cores=cores, kind="port",
                 sample=f"TGV N={N} GL split-PI NS+BR1, {sample_elems}^3 elements ({ndof} DOF), {steps} RK step(s) of 5 stages, "
                        f"OpenMP over elements; restatement of the reference algorithm (oracle/dg_oracle.c), not the reference binary",
@@ -150,6 +162,7 @@ def run_reference(args):
     sample = 12
     vals = []
     from oracle.oracle import Oracle
+    cores = host_threads()
     c, U0 = build_case(1, 0, elems=(sample,) * 3)
     o = Oracle(c)
     o.set_state(U0)
@@ -163,7 +176,6 @@ def run_reference(args):
             vals.append(time.perf_counter() - s0)
     wall = float(np.sum(vals))
     ndof = c.nDOF
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     value = ndof * NSTAGES * args.steps / wall
     line = dict(metric="DOF-updates/s", value=value, unit="DOF*stage/s", impl="reference", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * wall / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -313,7 +325,7 @@ def main():
     line = None
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # reported at N=1 only
             cpu, _ = cpu_baseline()
         line = dict(metric="DOF-updates/s", value=value, unit="DOF*stage/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",

@@ -105,8 +105,8 @@ def mortar_case(mesh="002", N=3, nProcs=1, myRank=0, bc=None, **kw):
     nt = args.pop("node_type", bs.NODETYPE_G)
     c = cs.build_case(h, N, nt, **args)
     x = c.geo["Elem_xGP"]
-    L = x.reshape(-1, 3).max(axis=0) - x.reshape(-1, 3).min(axis=0)
-    kx = 2.0 * np.pi / np.where(L > 0, L, 1.0) * np.array([1.0, 1.0, 1.0])
+    L = h["NodeCoords"].max(axis=0) - h["NodeCoords"].min(axis=0)   # global extents: the same field on every rank
+    kx = 2.0 * np.pi / np.where(L > 0, L, 1.0)
     prim = np.broadcast_to(c.RefStatePrim[0], x.shape[:-1] + (6,)).copy()
     ph = kx[0] * x[..., 0] + 0.3, kx[1] * x[..., 1] - 0.2, kx[2] * x[..., 2] + 0.1
     prim[..., 0] *= 1.0 + 0.1 * np.sin(ph[0]) * np.cos(ph[1]) * np.cos(ph[2])

@@ -28,6 +28,11 @@ def _build(name, nProcs, myRank):
         return cases.shu_vortex_case(E=4, N=3, nProcs=nProcs, myRank=myRank)
     if name == "naca":
         return cases.naca_case(N=2, nProcs=nProcs, myRank=myRank)
+    if name.startswith("mortar"):
+        # non-conforming interfaces across ranks (MPI mortars, small sides MINE and YOUR); name = mortar<mesh>[_br2]
+        return cases.mortar_case(name[6:9], N=3, nProcs=nProcs, myRank=myRank, lifting="br2" if name.endswith("br2") else "br1")
+    if name == "tgv_br2":
+        return cases.tgv_box_case(E=4, N=3, NGeo=2, deform=0.05, nProcs=nProcs, myRank=myRank, lifting="br2")
     raise ValueError(name)
 
 
@@ -73,7 +78,8 @@ def _worker(rank, world, port, name, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,world", [("tgv", 2), ("tgv", 3), ("cavity", 2), ("shu", 2), ("naca", 3)])
+@pytest.mark.parametrize("name,world", [("tgv", 2), ("tgv", 3), ("cavity", 2), ("shu", 2), ("naca", 3), ("tgv_br2", 2),
+                                        ("mortar001", 2), ("mortar002", 3), ("mortar004_br2", 2), ("mortar004", 3)])
 def test_ranks_reproduce_single_rank(name, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

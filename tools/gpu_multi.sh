@@ -3,7 +3,7 @@
 N=${1:-2}; TAG=${2:-r01}
 OUT=gpurun_out; mkdir -p $OUT
 export NCCL_DEBUG=WARN
-for c in tgv cavity channel shu naca; do
+for c in tgv cavity channel shu naca tgv_br2 mortar001 mortar002 mortar004_br2; do
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/mr_check.py $c > $OUT/mr_${c}_$TAG.log 2>&1
   echo "$c exit $?"; grep MRCHECK $OUT/mr_${c}_$TAG.log || tail -15 $OUT/mr_${c}_$TAG.log
 done

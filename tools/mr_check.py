@@ -42,6 +42,10 @@ def main():
             return cases.shu_vortex_case(E=4, N=3, nProcs=nProcs, myRank=myRank)
         if name == "naca":
             return cases.naca_case(N=3, nProcs=nProcs, myRank=myRank)
+        if name.startswith("mortar"):   # mortar<mesh>[_br2]: non-conforming interfaces across ranks
+            return cases.mortar_case(name[6:9], N=3, nProcs=nProcs, myRank=myRank, lifting="br2" if name.endswith("br2") else "br1")
+        if name == "tgv_br2":
+            return cases.tgv_box_case(E=4, N=4, NGeo=2, deform=0.05, nProcs=nProcs, myRank=myRank, lifting="br2")
         raise SystemExit(f"unknown case {name}")
 
     c, U0 = build(world, rank)

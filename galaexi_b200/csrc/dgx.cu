@@ -10,6 +10,7 @@
 //     on both ranks, which removes the lifting-flux and flux messages (mpi/mpi.f90:277-387, SURVEY 2.3 rows 2,4).
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>

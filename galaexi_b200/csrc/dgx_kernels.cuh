@@ -74,6 +74,31 @@ __device__ __forceinline__ void prefetch_block(const void* base, size_t bytes, i
     for (size_t off = (size_t)tid * 128; off < bytes; off += (size_t)nthr * 128) prefetch_l2(p + off);
 }
 
+// ---- TMA bulk copy (cp.async.bulk, 1-D) with mbarrier completion: one thread moves a contiguous element tile from HBM
+// to shared memory without holding registers; the consumers wait on the mbarrier's phase parity.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(unsigned dst, const void* src, unsigned bytes, unsigned mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned phase) {
+    unsigned ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(mbar), "r"(phase)
+                     : "memory");
+    }
+}
+
 template <int n>
 __device__ __forceinline__ int s2v2(const int* __restrict__ tab, int c, int p, int q, int flip, int loc) {
     return __ldg(&tab[c + 2 * (p + n * (q + n * (flip + 5 * (loc - 1))))]);
@@ -206,14 +231,22 @@ __global__ void __launch_bounds__(n* n* n) k_prolong(const KParams P) {
 
 // ---------------------------------------------------------------------------------------------------------
 // BR1 lifting (strong form, non-conservative volume integral): gradU = sJ * ( M . D U + sum_faces F n Lhat )
+template <int n>
+constexpr bool lifting_uses_tma() { return n % 2 == 0; }
+
 // GEN=0: BR1 on conforming meshes (the GALAEXI configuration, hot path). GEN=1: BR2 and/or elements with a big mortar
 // face, whose projected lifting flux (times normal) k_mortar_liftflux has left in gm[bigSide].
 template <int n, int NT, int GEN = 0>
 __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting(const KParams P, int lookahead) {
     constexpr int n2 = n * n, n3 = n2 * n;
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     __shared__ int sMort[6];  // GEN: 0-based big mortar side of local side loc, or -1
+    __shared__ __align__(8) unsigned long long sBar;  // mbarrier of the metric / Jacobian bulk copy
     const bool br2 = GEN && P.lifting == 2;
+    // even n: the element's metrics (9 n^3) and Jacobian (n^3) are fetched by TMA bulk copies issued at kernel entry into a
+    // staging area behind the operator tables, so this read is in flight from the first cycle of the CTA instead of
+    // starting after the sweeps (16-byte granularity of cp.async.bulk: n^3 * 8 B must be a multiple of 16)
+    constexpr bool TMA = lifting_uses_tma<n>();
     double* sT = smem;                 // [4][n3] lifting variables; later aliased by the gradient tile [12][n3]
     double* sG = smem;                 // alias (used after the sweeps are done)
     double* sF = smem + 12 * n3;       // [6][7][n2] face lifting flux (4) + normal (3), element face order
@@ -223,8 +256,16 @@ __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting
     double* sLhp = sLhm + n;
     double* sLm = sLhp + n;
     double* sLp = sLm + n;
+    double* stM = sLp + n;             // TMA staging: metrics [9][n3], then sJ [n3]
     const int e = P.elemList ? P.elemList[blockIdx.x] : blockIdx.x;
     const int t = threadIdx.x;
+    if (TMA && t == 0) {
+        const unsigned bar = smem_u32(&sBar);
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, (unsigned)(10 * n3 * sizeof(double)));
+        tma_load_1d(smem_u32(stM), P.metrics + (size_t)e * 9 * n3, (unsigned)(9 * n3 * sizeof(double)), bar);
+        tma_load_1d(smem_u32(stM + 9 * n3), P.sJ + (size_t)e * n3, (unsigned)(n3 * sizeof(double)), bar);
+    }
     for (int x = t; x < n * n; x += n3) { sD[x] = P.D_T[x]; sDx[(x / n) + n * (x % n)] = P.D_T[x]; }
     if (t < n) { sLhm[t] = P.L_HatMinus[t]; sLhp[t] = P.L_HatPlus[t]; sLm[t] = P.L_Minus[t]; sLp[t] = P.L_Plus[t]; }
     const Eos eos = P.eos;
@@ -233,7 +274,7 @@ __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting
     const int tid_ = Tile<n>::idx(i, j, k);
     // L2 prefetches (fire and forget, no registers): the metrics / Jacobian this CTA reads two barriers from now, and the
     // volume data of the element that takes this CTA's place once it retires (one resident wave ahead in the grid)
-    if (P.flags & 1) {
+    if (!TMA && (P.flags & 1)) {
         prefetch_block(P.metrics + (size_t)e * 9 * n3, sizeof(double) * 9 * n3, t, n3);
         prefetch_block(P.sJ + (size_t)e * n3, sizeof(double) * n3, t, n3);
     }
@@ -321,7 +362,8 @@ __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting
                 gze[v] += dz * sT[v * n3 + iz];
             }
         }
-        const double* M = P.metrics + (size_t)e * 9 * n3 + t;
+        if (TMA) mbar_wait(smem_u32(&sBar), 0);  // (the barrier after step 2 ordered the init before this wait)
+        const double* M = TMA ? stM + t : P.metrics + (size_t)e * 9 * n3 + t;
         double S[12];
 #pragma unroll
         for (int x = 0; x < 12; x++) S[x] = 0.0;
@@ -340,7 +382,7 @@ __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting
             } else {
                 Lh = minus ? sLhm[l] : sLhp[l];
             }
-            const double sJn = GEN ? P.sJ[(size_t)e * n3 + t] : 1.0;  // BR2: F_loc = sJ * Flux * L_hat (lifting_br2.t90:252,293)
+            const double sJn = GEN ? (TMA ? stM[9 * n3 + t] : P.sJ[(size_t)e * n3 + t]) : 1.0;  // BR2: F_loc = sJ * Flux * L_hat (lifting_br2.t90:252,293)
             if (GEN && sMort[loc - 1] >= 0) {
                 // big mortar face: projected flux*normal in side-local (flip 0) node order
                 const int p = s2v2<n>(P.S2V2inv, 0, a, b, 0, loc), q = s2v2<n>(P.S2V2inv, 1, a, b, 0, loc);
@@ -365,7 +407,7 @@ __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting
                 }
             }
         }
-        const double sJ = P.sJ[(size_t)e * n3 + t];
+        const double sJ = TMA ? stM[9 * n3 + t] : P.sJ[(size_t)e * n3 + t];
 #pragma unroll
         for (int d = 0; d < 3; d++) {
             const double mf = M[(0 + d) * n3], mg = M[(3 + d) * n3], mh = M[(6 + d) * n3];
@@ -468,7 +510,9 @@ __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting
 }
 
 template <int n>
-constexpr size_t lifting_smem_bytes() { return sizeof(double) * (12 * n * n * n + 6 * 7 * n * n + 2 * n * n + 4 * n); }
+constexpr size_t lifting_smem_bytes() {
+    return sizeof(double) * (12 * n * n * n + 6 * 7 * n * n + 2 * n * n + 4 * n + (lifting_uses_tma<n>() ? 10 * n * n * n : 0));
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // Numerical flux on a range of sides [side0, side0+nS): BC flux or Riemann + 1/2(Fv_L+Fv_R).n, times SurfElem

@@ -1,10 +1,12 @@
 #!/usr/bin/env python
 """Hot spots of an ncu --set full capture with --import-source on: stall samples per SASS instruction, grouped into the
-regions between BAR.SYNC instructions (the kernel phases), plus the top instructions. usage: ncu_hot.py report.ncu-rep [topN]"""
+regions between BAR.SYNC instructions (the kernel phases), plus the top instructions.
+usage: ncu_hot.py report.ncu-rep [topN] [kernel-name-substring]"""
 import csv, io, subprocess, sys
 out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+want = sys.argv[3] if len(sys.argv) > 3 else ""
 k = 0
 while k < len(rows):
     if rows[k] and rows[k][0] == "Kernel Name":
@@ -12,6 +14,8 @@ while k < len(rows):
         body = []
         while k < len(rows) and not (rows[k] and rows[k][0] == "Kernel Name"):
             body.append(rows[k]); k += 1
+        if want not in name:
+            continue
         si, ei = hdr.index("# Samples"), hdr.index("Instructions Executed")
         tot = sum(int(r[si] or 0) for r in body)
         print(f"## {name}: {len(body)} SASS instructions, {tot} samples")

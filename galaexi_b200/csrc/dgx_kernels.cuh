@@ -231,8 +231,24 @@ __global__ void __launch_bounds__(n* n* n) k_prolong(const KParams P) {
 
 // ---------------------------------------------------------------------------------------------------------
 // BR1 lifting (strong form, non-conservative volume integral): gradU = sJ * ( M . D U + sum_faces F n Lhat )
+// n == 8 (N=7): the three derivative sweeps of the lifting run on the FP64 tensor-core path (mma.sync m8n8k4, DMMA): the
+// same 36 TFLOP/s as DFMA on a B200 (tools/microbench/fp64_rates.cu) but 8x fewer issue slots and 10x fewer shared-memory
+// loads per flop -- the sweeps of the thread-per-node form were bound by LDS issue (profiles/r02a: mio_throttle).
 template <int n>
-constexpr bool lifting_uses_tma() { return n % 2 == 0; }
+constexpr bool lifting_uses_dmma() { return n == 8; }
+// even n without the DMMA path: metrics / Jacobian staged by TMA (the DMMA path needs the shared memory for its 12 output
+// slots and prefetches them to L2 instead)
+template <int n>
+constexpr bool lifting_uses_tma() { return n % 2 == 0 && !lifting_uses_dmma<n>(); }
+template <int n>
+constexpr int lifting_tile_slots() { return lifting_uses_dmma<n>() ? 16 : 12; }
+
+// Tile layout of the DMMA path (n = 8): conflict-free 64-bit accesses for the point-wise lane mapping and for the B
+// fragments of all three sweep directions (4 consecutive l x 4 consecutive lines per half warp)
+__device__ __forceinline__ int idx_m8(int i, int j, int k) { return ((i ^ (4 * (((j >> 1) ^ k) & 1))) + 8 * (j ^ ((k >> 1) & 1))) + 64 * k; }
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
 // GEN=0: BR1 on conforming meshes (the GALAEXI configuration, hot path). GEN=1: BR2 and/or elements with a big mortar
 // face, whose projected lifting flux (times normal) k_mortar_liftflux has left in gm[bigSide].
@@ -247,9 +263,11 @@ __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting
     // staging area behind the operator tables, so this read is in flight from the first cycle of the CTA instead of
     // starting after the sweeps (16-byte granularity of cp.async.bulk: n^3 * 8 B must be a multiple of 16)
     constexpr bool TMA = lifting_uses_tma<n>();
+    constexpr bool DMMA = lifting_uses_dmma<n>();
     double* sT = smem;                 // [4][n3] lifting variables; later aliased by the gradient tile [12][n3]
     double* sG = smem;                 // alias (used after the sweeps are done)
-    double* sF = smem + 12 * n3;       // [6][7][n2] face lifting flux (4) + normal (3), element face order
+    double* sO = smem + 4 * n3;        // DMMA path: [12][n3] derivatives (dir*4+v) in reference space
+    double* sF = smem + lifting_tile_slots<n>() * n3;  // [6][7][n2] face lifting flux (4) + normal (3), element face order
     double* sD = sF + 6 * 7 * n2;      // D_T [n*n]
     double* sDx = sD + n * n;          // D_T transposed
     double* sLhm = sDx + n * n;
@@ -274,7 +292,7 @@ __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting
     const int tid_ = Tile<n>::idx(i, j, k);
     // L2 prefetches (fire and forget, no registers): the metrics / Jacobian this CTA reads two barriers from now, and the
     // volume data of the element that takes this CTA's place once it retires (one resident wave ahead in the grid)
-    if (!TMA && (P.flags & 1)) {
+    if (!TMA && (DMMA || (P.flags & 1))) {
         prefetch_block(P.metrics + (size_t)e * 9 * n3, sizeof(double) * 9 * n3, t, n3);
         prefetch_block(P.sJ + (size_t)e * n3, sizeof(double) * n3, t, n3);
     }
@@ -291,10 +309,11 @@ __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting
 #pragma unroll
         for (int v = 0; v < 5; v++) Uc[v] = U[v * n3 + t];
         cons_to_prim(Pr, Uc, eos);
-        sT[0 * n3 + tid_] = Pr[VEL1];
-        sT[1 * n3 + tid_] = Pr[VEL2];
-        sT[2 * n3 + tid_] = Pr[VEL3];
-        sT[3 * n3 + tid_] = Pr[TEMP];
+        const int tin = DMMA ? idx_m8(i, j, k) : tid_;
+        sT[0 * n3 + tin] = Pr[VEL1];
+        sT[1 * n3 + tin] = Pr[VEL2];
+        sT[2 * n3 + tin] = Pr[VEL3];
+        sT[3 * n3 + tin] = Pr[TEMP];
     }
     // 2. faces: lifting flux F = 1/2 (U_s - U_m) SurfElem in side orientation -> stored in element face order
     for (int f = t; f < 6 * n2; f += n3) {
@@ -351,15 +370,49 @@ __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting
     double G[12];
     {
         double gxi[4] = {0, 0, 0, 0}, get[4] = {0, 0, 0, 0}, gze[4] = {0, 0, 0, 0};
+        if constexpr (DMMA) {
+            // out(o, line) = sum_l D_T(l,o) u(l, line) as C[8x8] = A[8x8] B[8x8] in two k-steps of m8n8k4:
+            // A[row o][l] = D_T(l,o) (the same fragment for the three directions), B[l][col] = u on 8 lines, one task =
+            // (direction, variable, group of 8 lines); 96 tasks over the 16 warps. Fragments: A: row = lane/4, k = lane%4;
+            // B: k = lane%4, col = lane/4; C: row = lane/4, cols 2 (lane%4) + {0,1}.
+            const int lane = t & 31, r = lane >> 2, c4 = lane & 3;
+            const double a0 = sD[c4 + n * r], a1 = sD[c4 + 4 + n * r];
+#pragma unroll 2
+            for (int task = t >> 5; task < 96; task += n3 / 32) {
+                const int dir = task >> 5, v = (task >> 3) & 3, g = task & 7;
+                int ib0, ib1, ic0, ic1;
+                if (dir == 0) {         // xi: lines (j = col, k = g)
+                    ib0 = idx_m8(c4, r, g); ib1 = idx_m8(c4 + 4, r, g);
+                    ic0 = idx_m8(r, 2 * c4, g); ic1 = idx_m8(r, 2 * c4 + 1, g);
+                } else if (dir == 1) {  // eta: lines (i = col, k = g)
+                    ib0 = idx_m8(r, c4, g); ib1 = idx_m8(r, c4 + 4, g);
+                    ic0 = idx_m8(2 * c4, r, g); ic1 = idx_m8(2 * c4 + 1, r, g);
+                } else {                // zeta: lines (i = col, j = g)
+                    ib0 = idx_m8(r, g, c4); ib1 = idx_m8(r, g, c4 + 4);
+                    ic0 = idx_m8(2 * c4, g, r); ic1 = idx_m8(2 * c4 + 1, g, r);
+                }
+                const double b0 = sT[v * n3 + ib0], b1 = sT[v * n3 + ib1];
+                double c0 = 0.0, c1 = 0.0;
+                dmma_m8n8k4(c0, c1, a0, b0);
+                dmma_m8n8k4(c0, c1, a1, b1);
+                sO[(dir * 4 + v) * n3 + ic0] = c0;
+                sO[(dir * 4 + v) * n3 + ic1] = c1;
+            }
+            __syncthreads();
+            const int tm = idx_m8(i, j, k);
 #pragma unroll
-        for (int l = 0; l < n; l++) {
-            const double dx = sDx[i + n * l], dy = sD[l + n * j], dz = sD[l + n * k];  // sDx: transposed copy, conflict-free over i
-            const int ix = Tile<n>::idx(l, j, k), iy = Tile<n>::idx(i, l, k), iz = Tile<n>::idx(i, j, l);
+            for (int v = 0; v < 4; v++) { gxi[v] = sO[v * n3 + tm]; get[v] = sO[(4 + v) * n3 + tm]; gze[v] = sO[(8 + v) * n3 + tm]; }
+        } else {
 #pragma unroll
-            for (int v = 0; v < 4; v++) {
-                gxi[v] += dx * sT[v * n3 + ix];
-                get[v] += dy * sT[v * n3 + iy];
-                gze[v] += dz * sT[v * n3 + iz];
+            for (int l = 0; l < n; l++) {
+                const double dx = sDx[i + n * l], dy = sD[l + n * j], dz = sD[l + n * k];  // sDx: transposed copy, conflict-free over i
+                const int ix = Tile<n>::idx(l, j, k), iy = Tile<n>::idx(i, l, k), iz = Tile<n>::idx(i, j, l);
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    gxi[v] += dx * sT[v * n3 + ix];
+                    get[v] += dy * sT[v * n3 + iy];
+                    gze[v] += dz * sT[v * n3 + iz];
+                }
             }
         }
         if (TMA) mbar_wait(smem_u32(&sBar), 0);  // (the barrier after step 2 ordered the init before this wait)
@@ -511,7 +564,7 @@ __global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting
 
 template <int n>
 constexpr size_t lifting_smem_bytes() {
-    return sizeof(double) * (12 * n * n * n + 6 * 7 * n * n + 2 * n * n + 4 * n + (lifting_uses_tma<n>() ? 10 * n * n * n : 0));
+    return sizeof(double) * (lifting_tile_slots<n>() * n * n * n + 6 * 7 * n * n + 2 * n * n + 4 * n + (lifting_uses_tma<n>() ? 10 * n * n * n : 0));
 }
 
 // ---------------------------------------------------------------------------------------------------------

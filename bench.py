@@ -192,7 +192,7 @@ def run_reference(args):
 
 def workload_name(ngpus):
     d = box_dims(ngpus)
-    return (f"TGV Navier-Stokes Re1600 Ma0.1, N=7 Gauss-Lobatto, split-form PI + BR1, RoeEntropyFix, CarpenterRK4-5, "
+    return (f"TGV Navier-Stokes Re1600 Ma0.1, N={N_POLY} Gauss-Lobatto, split-form PI + BR1, RoeEntropyFix, CarpenterRK4-5, "
             f"{d[0]}x{d[1]}x{d[2]} elements ({ELEMS_PER_GPU}^3 per GPU), adaptive dt")
 
 
@@ -204,7 +204,10 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--degree", type=int, default=N_POLY,
+                    help="polynomial degree N (default 7 = BASELINE config #2, the headline; 5 = per-GPU load of config #3)")
     args = ap.parse_args()
+    globals()["N_POLY"] = args.degree
     if args.impl == "reference":
         return run_reference(args)
 
@@ -229,7 +232,7 @@ def main():
         nccl_id = ids[0]
 
     t_build = time.perf_counter()
-    c, U0 = build_case(world, rank)
+    c, U0 = build_case(world, rank, N=N_POLY)
     s = dg.DGSolver(c, device=local, nccl_id=nccl_id)
     t_build = time.perf_counter() - t_build
     s.set_state(U0)
@@ -289,9 +292,14 @@ def main():
     n = N_POLY + 1
     vs_ms = prof.get("volsurf_rk", float("nan"))
     ach = b_alg_volsurf(n) * ndof_local / (vs_ms * 1e-3) / 1e9
-    roofline = dict(bound="hbm", kernel="k_volsurf2<8,RK>", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak,
+    # every stage kernel against the HBM roof (algorithmic bytes per DOF from DESIGN.md 4)
+    b_k = {"halo+lifting": 8.0 * (27.0 + 156.0 / n), "sideflux": 8.0 * 147.0 / n, "volsurf_rk": b_alg_volsurf(n)}
+    per_kernel = {k: dict(ms=prof[k], algorithmic_bytes_per_dof=b_k[k], achieved_gbs=b_k[k] * ndof_local / (prof[k] * 1e-3) / 1e9,
+                          frac=b_k[k] * ndof_local / (prof[k] * 1e-3) / 1e9 / hbm_peak) for k in b_k if k in prof}
+    roofline = dict(bound="hbm", kernel=f"k_volsurf2<{n},RK>", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak,
                     traffic=None, peak_source=peak_src, algorithmic_bytes_per_dof=b_alg_volsurf(n), ms_per_launch=vs_ms,
-                    kernel_ms_per_stage=prof,
+                    kernel_ms_per_stage=prof, kernels=per_kernel,
+                    fp64_peak_tflops=dict(dfma=36.0, dmma_m8n8k4=37.1, source="profiles/r02_fp64_rates_b200.txt (tools/microbench/fp64_rates.cu on this pool's B200)"),
                     stage=dict(algorithmic_bytes_per_dof=b_alg_stage(n), achieved=b_alg_stage(n) / pid / 1e9,
                                frac=b_alg_stage(n) / pid / 1e9 / hbm_peak, note="whole RK stage incl. CalcTimeStep: B_alg,NS(N)/PID vs HBM peak"))
     try:
@@ -331,7 +339,7 @@ def main():
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                     data="synthetic", pid_s=pid, pid_floor_s=b_alg_stage(n) / (hbm_peak * 1e9),
                     config=dict(workload=workload_name(world), dof_global=ndof_global, dof_per_gpu=ndof_local, rk_stages=NSTAGES,
-                                l2_policy="inputs larger than L2 (state 671 MB per GPU >> 126 MB L2), no explicit flush",
+                                l2_policy=f"inputs larger than L2 (state {U0.nbytes / 1e6:.0f} MB per GPU >> 126 MB L2), no explicit flush",
                                 timing="CUDA events on the launching stream around K steps, max over ranks",
                                 parallelism=f"dd{world} (SFC element decomposition, NCCL face halos)"),
                     roofline=roofline, cpu_baseline=cpu, clocks=sampler.summary(),

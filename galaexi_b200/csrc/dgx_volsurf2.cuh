@@ -26,6 +26,10 @@ constexpr int vs2_epb() { return (128 + n * n) / (2 * n * n) > 0 ? (128 + n * n)
 template <int n>
 constexpr int vs2_threads() { return vs2_epb<n>() * 2 * n * n; }
 constexpr int VS2_SLOTS = 18;
+#ifndef VS2_CROSS_UNROLL
+#define VS2_CROSS_UNROLL 1
+#endif
+constexpr int VS2_CU = VS2_CROSS_UNROLL;
 template <int n>
 constexpr size_t vs2_smem_bytes() { return sizeof(double) * ((size_t)vs2_epb<n>() * VS2_SLOTS * Tile<n>::SLOT + 2 * n * n); }
 
@@ -134,7 +138,7 @@ __device__ __forceinline__ void vs2_sweep(const double* __restrict__ R, const do
         }
     }
     // pairs with the other half of the line (rolled loop: code size)
-#pragma unroll 1
+#pragma unroll(VS2_CU)
     for (int mf = 0; mf < fcnt; mf++) {
         const int b = f0 + mf;
         const int id = line_idx<n>(d, b, c1, c2);

@@ -252,8 +252,14 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 
 // GEN=0: BR1 on conforming meshes (the GALAEXI configuration, hot path). GEN=1: BR2 and/or elements with a big mortar
 // face, whose projected lifting flux (times normal) k_mortar_liftflux has left in gm[bigSide].
+// resident CTAs per SM the register allocation aims at: about 1024 threads per SM (64 registers per thread)
+template <int n>
+constexpr int lifting_min_blocks() {
+    constexpr int warps = (n * n * n + 31) / 32;
+    return warps >= 32 ? 1 : (32 / warps > 16 ? 16 : 32 / warps);
+}
 template <int n, int NT, int GEN = 0>
-__global__ void __launch_bounds__(n* n* n, (n * n * n >= 512 ? 2 : 1)) k_lifting(const KParams P, int lookahead) {
+__global__ void __launch_bounds__(n* n* n, lifting_min_blocks<n>()) k_lifting(const KParams P, int lookahead) {
     constexpr int n2 = n * n, n3 = n2 * n;
     extern __shared__ __align__(16) double smem[];
     __shared__ int sMort[6];  // GEN: 0-based big mortar side of local side loc, or -1

@@ -30,6 +30,9 @@ constexpr int VS2_SLOTS = 18;
 #define VS2_CROSS_UNROLL 1
 #endif
 constexpr int VS2_CU = VS2_CROSS_UNROLL;
+#ifndef VS2_MIN_BLOCKS
+#define VS2_MIN_BLOCKS(n) ((n) >= 6 ? 3 : 4)
+#endif
 template <int n>
 constexpr size_t vs2_smem_bytes() { return sizeof(double) * ((size_t)vs2_epb<n>() * VS2_SLOTS * Tile<n>::SLOT + 2 * n * n); }
 
@@ -154,7 +157,7 @@ __device__ __forceinline__ void vs2_sweep(const double* __restrict__ R, const do
 }
 
 template <int n, int MODE, int VAR>
-__global__ void __launch_bounds__(vs2_threads<n>(), (n >= 8 ? 3 : 2)) k_volsurf2(const __grid_constant__ KParams P, int nWork, double mRKA, double b_dt, int lookahead) {
+__global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf2(const __grid_constant__ KParams P, int nWork, double mRKA, double b_dt, int lookahead) {
     constexpr int n2 = n * n, n3 = n2 * n, SEG = (n + 1) / 2, SL = Tile<n>::SLOT, T = 2 * n2, EPB = vs2_epb<n>();
     extern __shared__ double smem[];
     const int le = threadIdx.x / T, tid = threadIdx.x - le * T;

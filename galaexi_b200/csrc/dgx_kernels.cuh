@@ -684,8 +684,12 @@ __global__ void __launch_bounds__(128, 4) k_sideflux(const KParams P, int side0,
 // Volume integral (weak or split form, + viscous weak form), surface integral, sign, Jacobian,
 // optional RK 2N update and prolongation of the updated state to the faces.
 //   MODE 0: store Ut only (DGTimeDerivative_weakForm);  MODE 1: RK stage update (+ face extraction)
+// thread-per-node kernel of the weak form / Gauss paths: two resident CTAs at n = 6 (without the bound ptxas takes 158
+// registers and a single 216-thread CTA fits an SM); smaller n already fit 4+ CTAs, larger n would spill
+template <int n>
+constexpr int volsurf_min_blocks() { return n == 6 ? 2 : 1; }
 template <int n, int NT, int MODE>
-__global__ void __launch_bounds__(n* n* n) k_volsurf(const KParams P, double mRKA, double b_dt) {
+__global__ void __launch_bounds__(n* n* n, volsurf_min_blocks<n>()) k_volsurf(const KParams P, double mRKA, double b_dt) {
     constexpr int n2 = n * n, n3 = n2 * n;
     extern __shared__ double smem[];
     double* sA = smem;               // [15][n3] multipurpose: fluxes f,g,h (15) | node record (6) + metrics (9) | U tile (5)

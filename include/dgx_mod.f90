@@ -28,6 +28,13 @@ TYPE, BIND(C), PUBLIC :: dgx_config
   TYPE(C_PTR)    :: NbProc, nMPISides_MINE_Proc, nMPISides_YOUR_Proc, offsetMPISides_MINE, offsetMPISides_YOUR
   TYPE(C_PTR)    :: ncclUniqueId
   INTEGER(C_INT) :: device
+  ! lifting variant (PP_Lifting: 1 BR1, 2 BR2) and BR2 penalties (lifting.f90:86-91)
+  INTEGER(C_INT) :: lifting
+  REAL(C_DOUBLE) :: etaBR2, etaBR2_wall
+  ! non-conforming interfaces (src/mortar, mesh.f90:271-283,318-322); nMortarSides=0: unused
+  INTEGER(C_INT) :: nMortarSides, firstMortarInnerSide, lastMortarInnerSide, firstMortarMPISide, lastMortarMPISide
+  TYPE(C_PTR)    :: MortarType, MortarInfo
+  TYPE(C_PTR)    :: M_0_1, M_0_2, M_1_0, M_2_0
 END TYPE dgx_config
 
 TYPE(C_PTR), PUBLIC, SAVE :: dgx = C_NULL_PTR   !< the library handle (one per rank)

@@ -130,6 +130,9 @@ struct dgx_handle {
     std::vector<int> NbProc, nMine, nYour, offMine, offYour;
     std::vector<HaloMsg> plan;
     ncclComm_t comm = nullptr;
+    // TGV diagnostics (dgx_analyze_tgv)
+    double *tgvV = nullptr, *tgvW = nullptr, *tgvPart = nullptr;
+    int tgvNA1 = 0;
     // non-conforming interfaces: the two ranges of big mortar sides
     MortarParams mp;
     int nMortarInner = 0, nMortarMPI = 0;
@@ -620,6 +623,39 @@ int dgx_calc_timestep(dgx_handle* h, double* dt, int* errType) {
     if (h->comm) flag = (h->hPinned[2] < 0.0) ? 2 : 0;
     if (errType) *errType = flag ? 2 : 0;
     if (dt) *dt = h->hPinned[0] < h->hPinned[1] ? h->hPinned[0] : h->hPinned[1];
+    return 0;
+}
+
+int dgx_analyze_tgv(dgx_handle* h, int NAnalyze, const double* Vdm, const double* wAnalyze, double Vol, double rho0, double* out15) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->cfg.parabolic) return fail(h, "dgx_analyze_tgv needs PARABOLIC (lifted gradients)");
+    if (NAnalyze < 1 || NAnalyze > 32 || !Vdm || !wAnalyze || !out15) return fail(h, "dgx_analyze_tgv: bad arguments");
+    const int NA1 = NAnalyze + 1;
+    if (h->tgvNA1 != NA1) {  // (re)upload the analysis basis
+        if (upload(h, &h->tgvV, Vdm, (size_t)NA1 * h->n) || upload(h, &h->tgvW, wAnalyze, (size_t)NA1)) return 1;
+        if (!h->tgvPart && dalloc(h, &h->tgvPart, (size_t)TGV_NPART * (h->cfg.nElems + 1) + 2 * TGV_NPART)) return 1;
+        h->tgvNA1 = NA1;
+    }
+    double* tot = h->tgvPart + (size_t)TGV_NPART * h->cfg.nElems;
+    int r = h->kt->tgv_analyze(h->P, NA1, h->tgvV, h->tgvW, h->tgvPart, h->s);
+    if (r) return fail(h, "k_tgv_analyze: %s", cudaGetErrorString((cudaError_t)r));
+    if (h->cfg.nElems && check_launch(h, "k_tgv_analyze")) return 1;
+    k_tgv_reduce<<<1, TGV_THREADS, 0, h->s>>>(h->tgvPart, h->cfg.nElems, tot);
+    if (check_launch(h, "k_tgv_reduce")) return 1;
+    if (h->comm) {  // testcase.f90:416-446 MPI_REDUCE (sum x 11, max x 1); every rank gets the result here
+        NK(g_nccl.AllReduce(tot, tot, TGV_NPART - 1, ncclFloat64, 0 /* ncclSum */, h->comm, h->s));
+        NK(g_nccl.AllReduce(tot + TGV_NPART - 1, tot + TGV_NPART - 1, 1, ncclFloat64, 2 /* ncclMax */, h->comm, h->s));
+    }
+    double p[TGV_NPART];
+    CK(cudaMemcpyAsync(p, tot, sizeof p, cudaMemcpyDeviceToHost, h->s));
+    CK(cudaStreamSynchronize(h->s));
+    const double mu0 = h->P.eos.mu0;
+    const double T_mean = p[0] / Vol, Entropy = p[1] / Vol, Ekin = p[2] / Vol, Ekin_comp = p[3] / Vol / rho0;
+    const double Enstr = p[4] / (rho0 * Vol), DR_u = p[5] * mu0 / Vol, DR_S = p[6] * 2. * mu0 / (rho0 * Vol);
+    const double DR_Sd = p[7] * 2. * mu0 / (rho0 * Vol), DR_p = -p[8] / (rho0 * Vol), ED_S = p[9] / Vol, ED_D = p[10] * 4. / 3. / Vol;
+    const double uPrime = sqrt(2. / 3. * Ekin);
+    const double o[15] = {DR_S, DR_Sd + DR_p, Ekin, Ekin_comp, Enstr, DR_u, DR_S, DR_Sd, DR_p, p[11], T_mean, uPrime, Entropy, ED_S, ED_D};
+    memcpy(out15, o, sizeof o);
     return 0;
 }
 

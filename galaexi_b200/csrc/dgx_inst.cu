@@ -104,14 +104,22 @@ struct L {
         if (mode == 0) k_volsurf<n, NT, 0><<<nb, n3, volsurf_smem_bytes<n>(), s>>>(P, mRKA, b_dt);
         else k_volsurf<n, NT, 1><<<nb, n3, volsurf_smem_bytes<n>(), s>>>(P, mRKA, b_dt);
     }
+    static int tgv_analyze(const KParams& P, int NA1, const double* Vdm, const double* wA, double* partials, cudaStream_t s) {
+        if (P.nElems <= 0) return 0;
+        const size_t sm = tgv_smem_bytes<n>(NA1);
+        cudaError_t e = cudaFuncSetAttribute(k_tgv_analyze<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return (int)e;
+        k_tgv_analyze<n><<<P.nElems, TGV_THREADS, sm, s>>>(P, NA1, Vdm, wA, partials);
+        return 0;
+    }
     static void timestep(const KParams& P, double CFL, double DFL, double* out, cudaStream_t s) {
         if (P.nElems > 0) k_timestep<n><<<P.nElems, timestep_threads<n>(), 0, s>>>(P, CFL, DFL, out);
     }
 };
 const KernelTable tabG = {L<1>::setup, L<1>::prolong, L<1>::lifting, L<1>::sideflux, L<1>::volsurf, L<1>::timestep,
-                          L<1>::umortar, L<1>::fluxmortar, L<1>::mortar_liftflux};
+                          L<1>::umortar, L<1>::fluxmortar, L<1>::mortar_liftflux, L<1>::tgv_analyze};
 const KernelTable tabGL = {L<2>::setup, L<2>::prolong, L<2>::lifting, L<2>::sideflux, L<2>::volsurf, L<2>::timestep,
-                           L<2>::umortar, L<2>::fluxmortar, L<2>::mortar_liftflux};
+                           L<2>::umortar, L<2>::fluxmortar, L<2>::mortar_liftflux, L<2>::tgv_analyze};
 }  // namespace
 
 #define DGX_CAT2(a, b) a##b

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include "dgx_kernels.cuh"
 #include "dgx_mortar.cuh"
+#include "dgx_analyze.cuh"
 
 namespace dgx {
 struct KernelTable {
@@ -16,6 +17,8 @@ struct KernelTable {
     void (*umortar)(double* am, double* as, int nvar, const MortarParams& mp, int nBig, cudaStream_t);
     void (*fluxmortar)(double* F, int nvar, int weak, const MortarParams& mp, int nBig, cudaStream_t);
     void (*mortar_liftflux)(const KParams&, const MortarParams& mp, int nBig, cudaStream_t);
+    // TGV diagnostics: per-element partials [nElems][TGV_NPART]; returns a cudaError_t
+    int (*tgv_analyze)(const KParams&, int NA1, const double* Vdm, const double* wA, double* partials, cudaStream_t);
 };
 const KernelTable* kernel_table(int N, int nodeType);  // nullptr if this N was not compiled in
 }  // namespace dgx

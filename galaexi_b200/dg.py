@@ -28,7 +28,7 @@ _ip = C.POINTER(C.c_int)
 
 EXPORTS = ("dgx_create", "dgx_destroy", "dgx_last_error", "dgx_set_state", "dgx_get_state", "dgx_get_ut",
            "dgx_get_gradients", "dgx_time_derivative", "dgx_rk_stage", "dgx_rk_step", "dgx_calc_timestep",
-           "dgx_sync", "dgx_run_steps", "dgx_profile_stage", "dgx_nccl_unique_id", "dgx_launch_count", "dgx_sizeof_config", "dgx_halo_plan")
+           "dgx_analyze_tgv", "dgx_sync", "dgx_run_steps", "dgx_profile_stage", "dgx_nccl_unique_id", "dgx_launch_count", "dgx_sizeof_config", "dgx_halo_plan")
 
 
 class DgxConfig(C.Structure):
@@ -79,6 +79,7 @@ def load_library():
     lib.dgx_rk_stage.argtypes = [h, C.c_int, C.c_double, C.c_double]
     lib.dgx_rk_step.argtypes = [h, C.c_double, C.c_double]
     lib.dgx_calc_timestep.argtypes = [h, _dp, _ip]
+    lib.dgx_analyze_tgv.argtypes = [h, C.c_int, _dp, _dp, C.c_double, C.c_double, _dp]
     lib.dgx_sync.argtypes = [h]
     lib.dgx_run_steps.argtypes = [h, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]
     lib.dgx_profile_stage.argtypes = [h, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), _ip]
@@ -230,6 +231,23 @@ class DGSolver:
         dt, err = C.c_double(), C.c_int()
         self._ck(self.lib.dgx_calc_timestep(self.h, C.byref(dt), C.byref(err)))
         return dt.value, err.value
+
+    def AnalyzeTestcase(self, NAnalyze: int | None = None, Vol: float | None = None, rho0: float = 1.0) -> np.ndarray:
+        """The 15 TGVAnalysis columns (testcase/taylorgreenvortex/testcase.f90:283-515), integrated on the device.
+        Vol: global volume (all ranks); defaults to this rank's volume (single-rank runs)."""
+        from .host import analyze as an
+        key = (NAnalyze,)
+        if getattr(self, "_an_key", None) != key:
+            NA, V, wA = an.init_analyze_basis(self.case.N, self.case.node_type, NAnalyze)
+            # Fortran Vdm(0:NA,0:N) at [I + (NA+1) i] == C array V.T
+            self._an = (NA, np.ascontiguousarray(V.T, dtype=np.float64), np.ascontiguousarray(wA, dtype=np.float64))
+            self._an_vol = an.volume(self.case)
+            self._an_key = key
+        NA, Vt, wA = self._an
+        out = np.zeros(15)
+        self._ck(self.lib.dgx_analyze_tgv(self.h, NA, Vt.ctypes.data_as(_dp), wA.ctypes.data_as(_dp),
+                                          float(self._an_vol if Vol is None else Vol), float(rho0), out.ctypes.data_as(_dp)))
+        return out
 
     def FinalizeDG(self):
         if getattr(self, "h", None):

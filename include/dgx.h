@@ -109,6 +109,17 @@ int dgx_rk_step(dgx_handle *h, double t, double dt);
 /* dt = min(convective, viscous) over all ranks; errType != 0 if the state is not finite */
 int dgx_calc_timestep(dgx_handle *h, double *dt, int *errType);
 
+/* AnalyzeTestcase of testcase/taylorgreenvortex/testcase.f90:283-515, on the device (the reference downloads U and the three
+ * gradient arrays and integrates on the host, :361-364): the nTGVvars = 15 columns of the *_TGVAnalysis.csv file
+ * (Dissipation Rate Incompressible, ... , ED_D; order of testcase.f90:497-498), integrated on the Gauss-Lobatto analysis
+ * nodes of degree NAnalyze from U and the lifted gradients of the most recent dgx_time_derivative / RK stage -- i.e. the
+ * data the reference analyses when called after TimeStep (timedisc_func.f90:351).
+ *   Vdm_GaussN_NAnalyze(0:NAnalyze,0:N), wAnalyze(0:NAnalyze): analyze.f90:236-272 (wGPVolAnalyze is the tensor product of
+ *   wAnalyze); Vol: global volume (analyze.f90:160-189); rho0: testcase reference density. Sums are reduced over all ranks.
+ * Requires PARABOLIC. */
+int dgx_analyze_tgv(dgx_handle *h, int NAnalyze, const double *Vdm_GaussN_NAnalyze, const double *wAnalyze, double Vol,
+                    double rho0, double *out15);
+
 /* measurement helpers (not part of the reference interface) */
 int dgx_sync(dgx_handle *h);
 /* nSteps RK steps with fixed dt, state resident in HBM; returns device-timed milliseconds (CUDA events on

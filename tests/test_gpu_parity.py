@@ -290,3 +290,59 @@ def test_br2_lifting(name, kw):
         c, U0 = cases.channel_case(lifting="br2", etaBR2_wall=4.0, **kw)
     assert c.lifting == 2
     _compare_rhs_and_steps(c, U0, nsteps=2)
+
+
+# ---- TGV diagnostics on the device --------------------------------------------------------------
+def test_tgv_analysis_matches_oracle():
+    """dgx_analyze_tgv vs the numpy restatement of AnalyzeTestcase on the same state and gradients (curved mesh, default
+    NAnalyze = 2 (N+1))."""
+    from galaexi_b200.host import analyze as an
+    from oracle.analyze_tgv import analyze_tgv
+    c, U0 = cases.tgv_box_case(E=3, N=4, NGeo=2, deform=0.05, perturb=1e-3)
+    s, o = _solver(c), _oracle(c)
+    s.set_state(U0)
+    o.set_state(U0)
+    s.DGTimeDerivative_weakForm(0.0)
+    o.time_derivative(0.0)
+    NA, V, wA = an.init_analyze_basis(c.N, c.node_type)
+    ref = analyze_tgv(c, o.array("U"), o.array("gradUx"), o.array("gradUy"), o.array("gradUz"), V, wA, an.volume(c))
+    got = s.AnalyzeTestcase()
+    assert np.all(np.abs(got - ref) <= 1e-11 * np.maximum(np.abs(ref), 1e-3 * np.abs(ref).max())), (got, ref)
+    s.FinalizeDG()
+    o.close()
+
+
+def test_tgv_reference_csv_all_columns():
+    """The reference's own regression file tgv/split, all 15 diagnostics over ALL 555 analyze rows (5540 time steps of the
+    CUDA path with adaptive dt, t = 0 ... 13, through transition), evaluated on the device. Reference criterion: rel 1e-4
+    (analyze.ini); held here: 1e-8 of each column's magnitude over the first 40 rows, the reference's 1e-4 over the whole
+    file (round-off is amplified by the flow's sensitivity at late times)."""
+    import os
+    c, U0 = cases.tgv_split_case()
+    rows = np.load(os.path.join(cases.GOLD, "tgv_split_csv.npz"))["rows"]
+    scale = np.abs(rows[:, 1:]).max(axis=0)
+    s = _solver(c)
+    s.set_state(U0)
+    s.DGTimeDerivative_weakForm(0.0)
+    d = s.AnalyzeTestcase(NAnalyze=10)
+    worst40 = worst = float(np.max(np.abs(d - rows[0][1:]) / scale))
+    t = 0.0
+    for ir, r in enumerate(rows[1:], start=1):
+        if ir == len(rows) - 1:
+            # the last row is written at tEnd = 13 (timedisc_func.f90:246-300: the final step is clipped to the end time)
+            t, nlast = timeloop.advance(s, t, float(r[0]))
+            assert 1 <= nlast <= 10
+        else:
+            for _ in range(10):
+                dt, err = s.CalcTimeStep()
+                assert err == 0
+                s.TimeStepByLSERKW2(t, dt)
+                t += dt
+        assert abs(t - r[0]) <= 1e-6 * r[0]
+        d = s.AnalyzeTestcase(NAnalyze=10)
+        worst = max(worst, float(np.max(np.abs(d - r[1:]) / scale)))
+        if ir < 40:
+            worst40 = worst
+    print(f"TGV CSV: worst column deviation, first 40 rows {worst40:.2e}, all {len(rows)} rows {worst:.2e}")
+    assert worst40 <= 1e-8 and worst <= 1e-4
+    s.FinalizeDG()

@@ -346,3 +346,15 @@ def test_tgv_reference_csv_all_columns():
     print(f"TGV CSV: worst column deviation, first 40 rows {worst40:.2e}, all {len(rows)} rows {worst:.2e}")
     assert worst40 <= 1e-8 and worst <= 1e-4
     s.FinalizeDG()
+
+
+# ---- every compiled polynomial degree, both node types ------------------------------------------------------------------
+@pytest.mark.parametrize("N", [1, 2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("node_type", ["GAUSS", "GAUSS-LOBATTO"])
+def test_all_degrees(N, node_type):
+    """Kernels are instantiated for N = 1..9 (the reference compiles PP_N in, src/CMakeLists.txt:63-72): curved periodic box,
+    Navier-Stokes + BR1; split form PI on Gauss-Lobatto nodes, weak form on Gauss nodes."""
+    split = "PI" if node_type == "GAUSS-LOBATTO" else None
+    c, U0 = cases.tgv_box_case(E=2 if N >= 8 else 3, N=N, NGeo=2, deform=0.05, perturb=1e-3, node_type=node_type, split=split,
+                               riemann="RoeEntropyFix" if split else "Roe")
+    _compare_rhs_and_steps(c, U0, nsteps=1)

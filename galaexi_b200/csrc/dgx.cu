@@ -109,8 +109,9 @@ struct dgx_handle {
     KParams P;
     std::string err;
     long long launches = 0;
-    cudaStream_t s = nullptr, cs = nullptr;
+    cudaStream_t s = nullptr, cs = nullptr, s2 = nullptr;  // compute, communication, halo-dependent compute (multi rank)
     cudaEvent_t evFaces = nullptr, evUhalo = nullptr, evGrad = nullptr, evGhalo = nullptr, evT0 = nullptr, evT1 = nullptr;
+    cudaEvent_t evSide = nullptr, evBnd = nullptr;
     // device memory
     std::vector<void*> allocs;
     double *U = nullptr, *Ut = nullptr, *Ut_tmp = nullptr, *gradU = nullptr, *metrics = nullptr, *sJ = nullptr, *geo = nullptr;
@@ -283,6 +284,42 @@ int rhs(dgx_handle* h, int mode, double mRKA, double b_dt, StageTimes* st = null
         Pb.elemList = h->bndList; Pb.nList = h->nBnd;
     }
     const bool mortar = h->hasMortar();
+    // multi rank, conforming mesh: the halo-dependent launches (elements / sides touching an MPI side) run on a second,
+    // high-priority stream concurrently with the inner-element kernels, so neither waits for the other's tail
+    const bool split2 = multi && !mortar && !getenv("DGX_NO_SPLIT_STREAM");
+    if (split2) {
+        if (c.parabolic) {
+            kt->lifting(Pi, h->nInner, h->s);
+            if (h->nInner > 0 && check_launch(h, "k_lifting")) return 1;
+            CK(cudaStreamWaitEvent(h->s2, h->evFaces, 0));
+            CK(cudaStreamWaitEvent(h->s2, h->evUhalo, 0));
+            if (h->nBnd) { kt->lifting(Pb, h->nBnd, h->s2); if (check_launch(h, "k_lifting(bnd)")) return 1; }
+            CK(cudaEventRecord(h->evGrad, h->s2));
+            CK(cudaStreamWaitEvent(h->cs, h->evGrad, 0));
+            if (exchange(h, P.gm, P.gs, 12)) return 1;
+            CK(cudaEventRecord(h->evGhalo, h->cs));
+            CK(cudaStreamWaitEvent(h->s, h->evGrad, 0));  // inner sides may border halo-dependent elements
+        } else {
+            CK(cudaStreamWaitEvent(h->s2, h->evFaces, 0));
+            CK(cudaStreamWaitEvent(h->s2, h->evUhalo, 0));
+        }
+        mark();
+        kt->sideflux(P, 0, c.lastInnerSide, h->s);
+        if (c.lastInnerSide > 0 && check_launch(h, "k_sideflux")) return 1;
+        CK(cudaEventRecord(h->evSide, h->s));
+        mark();
+        CK(cudaStreamWaitEvent(h->s2, h->evSide, 0));
+        if (c.parabolic) CK(cudaStreamWaitEvent(h->s2, h->evGhalo, 0));
+        const int nMPI = c.lastMPISide_YOUR - c.firstMPISide_MINE + 1;
+        if (nMPI > 0) { kt->sideflux(P, c.firstMPISide_MINE - 1, nMPI, h->s2); if (check_launch(h, "k_sideflux(mpi)")) return 1; }
+        if (h->nBnd) { kt->volsurf(Pb, mode, mRKA, b_dt, h->nBnd, h->s2); if (check_launch(h, "k_volsurf(bnd)")) return 1; }
+        CK(cudaEventRecord(h->evBnd, h->s2));
+        if (h->nInner) { kt->volsurf(Pi, mode, mRKA, b_dt, h->nInner, h->s); if (check_launch(h, "k_volsurf(inner)")) return 1; }
+        CK(cudaStreamWaitEvent(h->s, h->evBnd, 0));
+        mark();
+        if (mode == 1) h->cur ^= 1;
+        return 0;
+    }
     if (c.parabolic) {
         if (mortar && !multi && mortar_liftflux(h, P)) return 1;
         kt->lifting(multi ? Pi : P, multi ? h->nInner : c.nElems, h->s);
@@ -376,13 +413,15 @@ void dgx_destroy(dgx_handle* h) {
     cudaSetDevice(h->cfg.device);
     if (h->s) cudaStreamSynchronize(h->s);
     if (h->cs) cudaStreamSynchronize(h->cs);
+    if (h->s2) cudaStreamSynchronize(h->s2);
     if (h->comm) g_nccl.CommDestroy(h->comm);
     for (void* p : h->allocs) cudaFree(p);
     if (h->hPinned) cudaFreeHost(h->hPinned);
-    cudaEvent_t evs[] = {h->evFaces, h->evUhalo, h->evGrad, h->evGhalo, h->evT0, h->evT1};
+    cudaEvent_t evs[] = {h->evFaces, h->evUhalo, h->evGrad, h->evGhalo, h->evT0, h->evT1, h->evSide, h->evBnd};
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     if (h->s) cudaStreamDestroy(h->s);
     if (h->cs) cudaStreamDestroy(h->cs);
+    if (h->s2) cudaStreamDestroy(h->s2);
     delete h;
 }
 
@@ -415,7 +454,8 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CK(cudaStreamCreateWithPriority(&h->s, cudaStreamNonBlocking, lo));
     CK(cudaStreamCreateWithPriority(&h->cs, cudaStreamNonBlocking, hi));
-    cudaEvent_t* evs[] = {&h->evFaces, &h->evUhalo, &h->evGrad, &h->evGhalo};
+    CK(cudaStreamCreateWithPriority(&h->s2, cudaStreamNonBlocking, hi));
+    cudaEvent_t* evs[] = {&h->evFaces, &h->evUhalo, &h->evGrad, &h->evGhalo, &h->evSide, &h->evBnd};
     for (cudaEvent_t* e : evs) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     CK(cudaEventCreate(&h->evT0));
     CK(cudaEventCreate(&h->evT1));
@@ -544,6 +584,7 @@ int dgx_sync(dgx_handle* h) {
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->s));
     CK(cudaStreamSynchronize(h->cs));
+    CK(cudaStreamSynchronize(h->s2));
     return 0;
 }
 

@@ -272,6 +272,12 @@ int rhs(dgx_handle* h, int mode, double mRKA, double b_dt, StageTimes* st = null
     const bool multi = c.nRanks > 1 && !h->NbProc.empty();
     auto mark = [&](void) { if (st) cudaEventRecord(st->ev[st->nev++], h->s); };
     mark();
+    if (P.FilterMat) {
+        // 1. dg.f90:331: filter U in place (every RHS evaluation, like the reference) and re-extract the face states
+        kt->filter(P, c.nElems, h->s);
+        if (c.nElems > 0 && check_launch(h, "k_filter")) return 1;
+        if (h->hasMortar() && mortar_u(h, P.Um, P.Us, 5)) return 1;
+    }
     if (multi) {
         CK(cudaEventRecord(h->evFaces, h->s));
         CK(cudaStreamWaitEvent(h->cs, h->evFaces, 0));
@@ -512,6 +518,12 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
     P.gm = h->gm; P.gs = h->gs; P.Flux = h->Flux; P.errFlag = h->errFlag;
     P.lifting = c.lifting == 2 ? 2 : 1; P.etaBR2 = c.etaBR2; P.etaBR2_wall = c.etaBR2_wall;
     P.MortarType = nullptr;
+    P.FilterMat = nullptr;
+    if (c.FilterMat) {
+        double* fm;
+        if (upload(h, &fm, c.FilterMat, (size_t)n * n)) return 1;
+        P.FilterMat = fm;
+    }
     h->mp = MortarParams{nullptr, nullptr, nullptr, 0};
     if (c.nMortarSides > 0) {
         h->nMortarInner = c.lastMortarInnerSide - c.firstMortarInnerSide + 1;
@@ -576,6 +588,7 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
     CK(cudaStreamSynchronize(h->s));
     h->cfg.RefStatePrim = nullptr;  // pointers are not retained
     h->cfg.MortarType = h->cfg.MortarInfo = nullptr;
+    h->cfg.FilterMat = nullptr;
     h->cfg.M_0_1 = h->cfg.M_0_2 = h->cfg.M_1_0 = h->cfg.M_2_0 = nullptr;
     return 0;
 }

@@ -61,6 +61,7 @@ struct KParams {
     int lifting;               // 1 BR1, 2 BR2
     double etaBR2, etaBR2_wall;
     const int* MortarType;     // (2,nSides) or nullptr when the mesh has no mortars
+    const double* FilterMat;   // device (0:N,0:N) Fortran layout, or nullptr (FilterType 0)
     int flags;  // tuning switches (DGX_FLAGS): 1 lifting: L2 prefetch of own later-phase data; 2 lifting: L2 prefetch of the element
                 // a resident wave ahead; 4 / 8: the same two for k_volsurf2
 };
@@ -228,6 +229,55 @@ __global__ void __launch_bounds__(n* n* n) k_prolong(const KParams P) {
     __syncthreads();
     extract_faces<n, NT, 5>(tile, P.Um, P.Us, P.E2S + 18 * e, P.S2V2, sLm, sLp);
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Step 1 of the RHS when FilterType > 0 (dg/dg.f90:331, filter/filter.f90:272-306 -> changeBasis.t90:287-360): U <- FilterMat
+// applied along xi, eta, zeta, in place; the face states of the filtered solution are extracted from the tile in the same
+// kernel (they replace the ones the previous stage's epilogue wrote from the unfiltered state).
+template <int n, int NT>
+__global__ void __launch_bounds__(n* n* n) k_filter(const KParams P) {
+    constexpr int n2 = n * n, n3 = n2 * n;
+    extern __shared__ double smem[];
+    double *b0 = smem, *b1 = smem + 5 * n3, *sM = smem + 10 * n3, *sLm = sM + n * n, *sLp = sLm + n;
+    const int e = P.elemList ? P.elemList[blockIdx.x] : blockIdx.x;
+    const int t = threadIdx.x;
+    for (int x = t; x < n * n; x += n3) sM[x] = P.FilterMat[x];
+    if (t < n) { sLm[t] = P.L_Minus[t]; sLp[t] = P.L_Plus[t]; }
+    double* U = P.U + (size_t)e * 5 * n3;
+#pragma unroll
+    for (int v = 0; v < 5; v++) b0[v * n3 + t] = U[v * n3 + t];
+    __syncthreads();
+    const int k = t / n2, j = (t - k * n2) / n, i = t - k * n2 - j * n;
+#pragma unroll
+    for (int v = 0; v < 5; v++) {
+        double a = 0.0;
+#pragma unroll
+        for (int l = 0; l < n; l++) a += sM[i + n * l] * b0[v * n3 + l + n * j + n2 * k];
+        b1[v * n3 + t] = a;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < 5; v++) {
+        double a = 0.0;
+#pragma unroll
+        for (int l = 0; l < n; l++) a += sM[j + n * l] * b1[v * n3 + i + n * l + n2 * k];
+        b0[v * n3 + t] = a;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < 5; v++) {
+        double a = 0.0;
+#pragma unroll
+        for (int l = 0; l < n; l++) a += sM[k + n * l] * b0[v * n3 + i + n * j + n2 * l];
+        b1[v * n3 + t] = a;
+        U[v * n3 + t] = a;
+    }
+    __syncthreads();
+    extract_faces<n, NT, 5>(b1, P.Um, P.Us, P.E2S + 18 * e, P.S2V2, sLm, sLp);
+}
+
+template <int n>
+constexpr size_t filter_smem_bytes() { return sizeof(double) * (10 * n * n * n + n * n + 2 * n); }
 
 // ---------------------------------------------------------------------------------------------------------
 // BR1 lifting (strong form, non-conservative volume integral): gradU = sJ * ( M . D U + sum_faces F n Lhat )

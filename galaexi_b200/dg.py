@@ -50,7 +50,7 @@ class DgxConfig(C.Structure):
         + [("lifting", C.c_int), ("etaBR2", C.c_double), ("etaBR2_wall", C.c_double)]
         + [(k, C.c_int) for k in ("nMortarSides", "firstMortarInnerSide", "lastMortarInnerSide", "firstMortarMPISide",
                                   "lastMortarMPISide")]
-        + [("MortarType", _ip), ("MortarInfo", _ip)] + [(k, _dp) for k in ("M_0_1", "M_0_2", "M_1_0", "M_2_0")]
+        + [("MortarType", _ip), ("MortarInfo", _ip)] + [(k, _dp) for k in ("M_0_1", "M_0_2", "M_1_0", "M_2_0", "FilterMat")]
     )
 
 
@@ -169,6 +169,9 @@ class DGSolver:
             setattr(c, nm, k[nm].ctypes.data_as(_ip))
         for nm in ("M_0_1", "M_0_2", "M_1_0", "M_2_0"):
             setattr(c, nm, k[nm].ctypes.data_as(_dp))
+        if case.FilterMat is not None:
+            k["FilterMat"] = f64(np.asarray(case.FilterMat).T)      # Fortran FilterMat(i,l) at [i + n*l]
+            c.FilterMat = k["FilterMat"].ctypes.data_as(_dp)
         c.lifting, c.etaBR2, c.etaBR2_wall = case.lifting, case.etaBR2, case.etaBR2_wall
         c.nMortarSides = m.nMortarSides
         c.firstMortarInnerSide, c.lastMortarInnerSide = m.firstMortarInnerSide, m.lastMortarInnerSide

@@ -90,6 +90,10 @@ typedef struct dgx_config {
     int nMortarSides, firstMortarInnerSide, lastMortarInnerSide, firstMortarMPISide, lastMortarMPISide;
     const int *MortarType, *MortarInfo;
     const double *M_0_1, *M_0_2, *M_1_0, *M_2_0;
+    /* modal filter of step 1 of the RHS (dg/dg.f90:331, filter/filter.f90:272-306): FilterMat(0:N,0:N) as built by
+     * InitFilter (filter.f90:95-212, FilterType cutoff / modal), or NULL for FilterType 0. Applied in place to U at the
+     * start of every dgx_time_derivative / RK stage, like the reference. */
+    const double *FilterMat;
 } dgx_config;
 
 int dgx_create(dgx_handle **h, const dgx_config *cfg);

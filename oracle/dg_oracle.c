@@ -86,6 +86,8 @@ typedef struct {
     const int *MortarType, *MortarInfo, *FS2M;
     const int *SideToElem; /* (5,nSides) */
     const double *M_0_1, *M_0_2, *M_1_0, *M_2_0;
+    /* modal filter applied to U at the start of the RHS (dg.f90:331): FilterMat(0:N,0:N) or NULL (FilterType 0) */
+    const double *FilterMat;
 } dgo_config;
 
 typedef struct {
@@ -1273,12 +1275,45 @@ static int fill_flux(dgo *s)
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* filter/filter.f90:272-306 Filter -> interpolation/changeBasis.t90:287-360 ChangeBasis3D_GPU with X_Out absent: U is
+ * replaced by FilterMat applied along xi, then eta, then zeta */
+static void filter_u(dgo *s)
+{
+    const dgo_config *c = &s->c;
+    const int n = s->n;
+    if (!c->FilterMat) return;
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < c->nElems; e++) {
+        double b1[NV * 1000], b2[NV * 1000];
+        for (int k = 0; k < n; k++) for (int j = 0; j < n; j++) for (int i = 0; i < n; i++)
+            for (int v = 0; v < NV; v++) {
+                double a = 0.;
+                for (int l = 0; l < n; l++) a = a + c->FilterMat[i + n * l] * s->U[IDX_VOL(s, NV, v, l, j, k, e)];
+                b1[v + NV * (i + n * (j + n * k))] = a;
+            }
+        for (int k = 0; k < n; k++) for (int j = 0; j < n; j++) for (int i = 0; i < n; i++)
+            for (int v = 0; v < NV; v++) {
+                double a = 0.;
+                for (int l = 0; l < n; l++) a = a + c->FilterMat[j + n * l] * b1[v + NV * (i + n * (l + n * k))];
+                b2[v + NV * (i + n * (j + n * k))] = a;
+            }
+        for (int k = 0; k < n; k++) for (int j = 0; j < n; j++) for (int i = 0; i < n; i++)
+            for (int v = 0; v < NV; v++) {
+                double a = 0.;
+                for (int l = 0; l < n; l++) a = a + c->FilterMat[k + n * l] * b2[v + NV * (i + n * (j + n * l))];
+                s->U[IDX_VOL(s, NV, v, i, j, k, e)] = a;
+            }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* dg/dg.f90:255-425 DGTimeDerivative_weakForm (single rank: no halo phases) */
 int dgo_time_derivative(dgo *s, double t)
 {
     (void)t;
     const dgo_config *c = &s->c;
     const double kappa = c->EOS[EOS_KAPPA], R = c->EOS[EOS_R];
+    /* 1. dg.f90:331 */ filter_u(s);
     /* 2. */ prolong_to_face(s, NV, s->U, s->U_master, s->U_slave);
     /* 2b. (host FLEXI) big mortar sides -> small sides */ u_mortar_all(s, NV, s->U_master, s->U_slave);
     /* 3. eos.f90:328 ConsToPrim volume */
@@ -1315,6 +1350,7 @@ int dgo_rhs_phase(dgo *s, int phase)
     int err = 0;
     switch (phase) {
     case 0:
+        filter_u(s);
         prolong_to_face(s, NV, s->U, s->U_master, s->U_slave);
         u_mortar_all(s, NV, s->U_master, s->U_slave);
 #pragma omp parallel for schedule(static)
@@ -1480,6 +1516,7 @@ double *dgo_array(dgo *s, const char *name)
 void dgo_prolong_to_face(dgo *s, int nVar, const double *Uvol, double *Um, double *Us) { prolong_to_face(s, nVar, Uvol, Um, Us); }
 void dgo_surf_int(dgo *s, int nVar, const double *Fm, const double *Fs, double *Ut) { surf_int(s, nVar, Fm, Fs, Ut, 0, 0, 0); }
 void dgo_lifting(dgo *s) { lifting_br1(s); }
+void dgo_filter(dgo *s) { filter_u(s); }
 void dgo_u_mortar(dgo *s, int nVar, double *Um, double *Us) { u_mortar_all(s, nVar, Um, Us); }
 void dgo_flux_mortar(dgo *s, int nVar, double *Fm, const double *Fs, int weak) { flux_mortar_all(s, nVar, Fm, Fs, weak); }
 size_t dgo_sizeof_config(void) { return sizeof(dgo_config); }

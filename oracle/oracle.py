@@ -41,7 +41,7 @@ class _Prec:
                        [(k, C.c_int) for k in ("firstMortarInnerSide", "lastMortarInnerSide", "firstMortarMPISide",
                                                "lastMortarMPISide")] + \
                        [(k, _ip) for k in ("MortarType", "MortarInfo", "FS2M", "SideToElem")] + \
-                       [(k, rp) for k in ("M_0_1", "M_0_2", "M_1_0", "M_2_0")]
+                       [(k, rp) for k in ("M_0_1", "M_0_2", "M_1_0", "M_2_0", "FilterMat")]
         self.Config = Config
         self._lib = None
 
@@ -66,6 +66,7 @@ class _Prec:
             L.dgo_prolong_to_face.argtypes = [C.c_void_p, C.c_int, rp, rp, rp]
             L.dgo_surf_int.argtypes = [C.c_void_p, C.c_int, rp, rp, rp]
             L.dgo_lifting.argtypes = [C.c_void_p]
+            L.dgo_filter.argtypes = [C.c_void_p]
             L.dgo_rhs_phase.argtypes = [C.c_void_p, C.c_int]
             L.dgo_rk_update.argtypes = [C.c_void_p, r, r]
             L.dgo_sizeof_config.restype = C.c_size_t
@@ -153,6 +154,10 @@ class Oracle:
             setattr(c, k, _d(self._keep[k]))
         for k in ("ElemToSide", "S2V2", "S2V2_inv", "BCSides", "MortarType", "MortarInfo", "FS2M", "SideToElem"):
             setattr(c, k, _i(self._keep[k]))
+        FilterMat = getattr(case, "FilterMat", None)
+        if FilterMat is not None:
+            self._keep["FilterMat"] = f64(np.asarray(FilterMat).T)   # Fortran FilterMat(i,l) at [i + n*l]
+            c.FilterMat = _d(self._keep["FilterMat"])
         c.lifting, c.etaBR2 = getattr(case, "lifting", 1), getattr(case, "etaBR2", 2.0)
         c.etaBR2_wall = getattr(case, "etaBR2_wall", c.etaBR2)
         c.firstMortarInnerSide = getattr(m, "firstMortarInnerSide", m.nBCSides + 1)

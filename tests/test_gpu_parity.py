@@ -358,3 +358,19 @@ def test_all_degrees(N, node_type):
     c, U0 = cases.tgv_box_case(E=2 if N >= 8 else 3, N=N, NGeo=2, deform=0.05, perturb=1e-3, node_type=node_type, split=split,
                                riemann="RoeEntropyFix" if split else "Roe")
     _compare_rhs_and_steps(c, U0, nsteps=1)
+
+
+# ---- modal filter at the start of the RHS (dg.f90:331) ---------------------------------------------------------------------
+@pytest.mark.parametrize("kw", [dict(N=5, FilterType="cutoff", NFilter=3), dict(N=7, FilterType="modal"),
+                                dict(N=4, FilterType="cutoff", NFilter=2, node_type="GAUSS", split=None, riemann="Roe"),
+                                dict(N=9, FilterType="cutoff", NFilter=6, E=2)])
+def test_filter(kw):
+    kw = dict(kw)
+    c, U0 = cases.tgv_box_case(E=kw.pop("E", 3), NGeo=2, deform=0.05, perturb=1e-2, **kw)
+    assert c.FilterMat is not None
+    _compare_rhs_and_steps(c, U0, nsteps=2)
+
+
+def test_filter_on_mortar_mesh():
+    c, U0 = cases.mortar_case("002", N=4, FilterType="cutoff", NFilter=2)
+    _compare_rhs_and_steps(c, U0, nsteps=1)

@@ -158,3 +158,41 @@ def test_slip_wall_variants_differ_only_in_viscous_flux():
     a, b = run((9, 0), True), run((91, 0), True)
     assert not np.array_equal(a, b)
     assert cases.rel_l2(a, b) <= 1e-2
+
+
+# ---- modal filter (dg.f90:331, filter/filter.f90) ------------------------------------------------------------------------
+@pytest.mark.parametrize("node_type", ["GAUSS", "GAUSS-LOBATTO"])
+def test_filter_matrix_properties(node_type):
+    from galaexi_b200.host import basis as bs
+    from galaexi_b200.host import filter as fl
+    N, Nc = 6, 3
+    F = fl.filter_matrix(N, node_type, "cutoff", NFilter=Nc)
+    x, w, _ = bs.get_nodes_and_weights(N, node_type)
+    assert np.allclose(F @ F, F, atol=1e-12)                      # a cut-off filter is a projection
+    for k in range(Nc + 1):
+        assert np.allclose(F @ x ** k, x ** k, atol=1e-12)        # modes up to NFilter pass unchanged
+    leg = np.array([bs.legendre_poly_and_deriv(N, float(xi))[0] for xi in x])
+    assert np.allclose(F @ leg, 0.0, atol=1e-12)                  # the highest mode is removed
+    H = fl.filter_matrix(N, node_type, "modal", HestFilterParam=(36.0, 12.0, 1.0))
+    assert np.allclose(H @ np.ones(N + 1), 1.0, atol=1e-13)       # the mean mode is untouched
+    assert np.allclose(fl.filter_matrix(N, node_type, "cutoff", NFilter=N), np.eye(N + 1), atol=1e-12)
+
+
+def test_filter_in_the_rhs_oracle():
+    """FilterType > 0 filters U in place at the start of every RHS (dg.f90:331): polynomials below the cut-off are
+    unchanged, the element means are conserved, filtering twice changes nothing more."""
+    c, U0 = cases.tgv_box_case(E=2, N=5, NGeo=2, deform=0.05, perturb=1e-2, FilterType="cutoff", NFilter=3)
+    o = Oracle(c)
+    o.set_state(U0)
+    o.prec.lib().dgo_filter(o.h)
+    U1 = o.array("U").copy()
+    assert np.abs(U1 - U0).max() > 1e-6
+    o.prec.lib().dgo_filter(o.h)
+    assert np.abs(o.array("U") - U1).max() <= 1e-13 * np.abs(U1).max()
+    w = c.basis.wGP
+    W = (w[:, None, None] * w[None, :, None] * w[None, None, :])[None, ..., None]
+    assert np.allclose(np.sum(W * U1, axis=(1, 2, 3)), np.sum(W * U0, axis=(1, 2, 3)), rtol=1e-12, atol=1e-12)
+    o.set_state(U0)
+    o.time_derivative(0.0)
+    assert np.abs(o.array("U") - U1).max() <= 1e-13 * np.abs(U1).max()   # the RHS call itself filters the state
+    o.close()

@@ -118,6 +118,50 @@ def mortar_case(mesh="002", N=3, nProcs=1, myRank=0, bc=None, **kw):
     return c, U0
 
 
+CONV_ADV = (0.3, 0.3, 0.3)     # AdvVel of regressioncheck/checks/convtest/h_3D/parameter.ini
+
+
+def exact_sine(x, t, kappa=1.4, adv=CONV_ADV):
+    """IniExactFunc = 2 (idealgas/exactfunc.f90:254-268): density sine wave advected with AdvVel -- an exact solution of
+    the Euler equations on the periodic [-1,1]^3 box."""
+    adv = np.asarray(adv)
+    cent = x - adv * t
+    rho = 1.0 * (1.0 + 0.3 * np.sin(2.0 * np.pi * 0.5 * np.sum(cent, axis=-1)))
+    U = np.empty(x.shape[:-1] + (5,))
+    U[..., 0] = rho
+    U[..., 1:4] = rho[..., None] * adv
+    U[..., 4] = 1.0 / (kappa - 1.0) + 0.5 * rho * np.sum(adv * adv)
+    return U
+
+
+def convtest_case(mesh="cart_periodic_004", N=3, nProcs=1, myRank=0, **kw):
+    """tutorials/convtest + regressioncheck/checks/convtest: periodic [-1,1]^3, conforming (cart_periodic_*) or
+    non-conforming (cart_mortar_*) meshes, Euler, exact function 2."""
+    h = load_mesh(f"{mesh}_mesh.npz")
+    eos = eq.Eos(kappa=1.4, R=287.058)
+    args = dict(split=None, riemann="RoeEntropyFix", parabolic=False, eos=eos, refstates=((1.0, 0.3, 0.0, 0.0, 0.71428571),),
+                nProcs=nProcs, myRank=myRank, CFLScale=0.7, useCurveds=False)
+    args.update(kw)
+    nt = args.pop("node_type", bs.NODETYPE_G)
+    c = cs.build_case(h, N, nt, **args)
+    return c, exact_sine(c.geo["Elem_xGP"], 0.0)
+
+
+def l2_error(c, U, t, NAnalyze=None):
+    """CalcErrorNorms (analyze/analyze.f90:383-470): L2 error against the exact function on the analysis nodes."""
+    from galaexi_b200.host import analyze as an
+    NA, V, wA = an.init_analyze_basis(c.N, c.node_type, NAnalyze)
+
+    def up(X):
+        Y = np.einsum("Ii,ekjic->ekjIc", V, X)
+        Y = np.einsum("Jj,ekjIc->ekJIc", V, Y)
+        return np.einsum("Kk,ekJIc->eKJIc", V, Y)
+    Ua, xa, Ja = up(U), up(c.geo["Elem_xGP"]), up((1.0 / c.geo["sJ"])[..., None])[..., 0]
+    w3 = wA[:, None, None] * wA[None, :, None] * wA[None, None, :]
+    d = Ua - exact_sine(xa, t)
+    return np.sqrt(np.sum((w3[None] * Ja)[..., None] * d * d, axis=(0, 1, 2, 3)) / an.volume(c))
+
+
 def channel_case(E=4, N=5, nProcs=1, myRank=0, **kw):
     """BASELINE config #4-like: plane channel, isothermal walls (4) at y+-, periodic x,z, Roe flux, y-stretched."""
     def stretch(d, s):

@@ -374,3 +374,31 @@ def test_filter(kw):
 def test_filter_on_mortar_mesh():
     c, U0 = cases.mortar_case("002", N=4, FilterType="cutoff", NFilter=2)
     _compare_rhs_and_steps(c, U0, nsteps=1)
+
+
+# ---- design-order convergence (the reference's convtest criterion), conforming and mortar meshes --------------------------------
+@pytest.mark.parametrize("node_type,split", [("GAUSS", None), ("GAUSS-LOBATTO", "PI"), ("GAUSS-LOBATTO", None)])
+def test_h_convergence_exact_density_wave(node_type, split):
+    """regressioncheck/checks/convtest/h_3D idea (analyze.ini: orders N+1 within 15 %) with the exact Euler solution
+    IniExactFunc=2: L2 error of the density at t=0.2 on the 2^3 / 4^3 / 8^3 meshes of tutorials/convtest, N=3, conforming
+    (CART_HEX_PERIODIC_*) and non-conforming (CART_HEX_PERIODIC_MORTAR_*, all three mortar types). Gauss nodes: order
+    >= 0.85 (N+1) on both families; Gauss-Lobatto (collocated, under-integrated mass matrix): >= N; and on every node
+    set the mortar meshes must converge as fast as the conforming ones (within 0.25)."""
+    N, tEnd = 3, 0.2
+    res = {}
+    for family in ("cart_periodic", "cart_mortar"):
+        errs = []
+        for lvl in ("002", "004", "008"):
+            c, U0 = cases.convtest_case(f"{family}_{lvl}", N=N, node_type=node_type, split=split,
+                                        riemann="RoeEntropyFix" if split else "Roe")
+            s = _solver(c)
+            s.set_state(U0)
+            t, _ = timeloop.advance(s, 0.0, tEnd)
+            errs.append(cases.l2_error(c, s.get_state(), t)[0])
+            s.FinalizeDG()
+        orders = [float(np.log(errs[i] / errs[i + 1]) / np.log(2.0)) for i in range(2)]
+        print(f"{family} {node_type} split={split}: L2(rho) {[float(e) for e in errs]}, orders {orders}")
+        res[family] = (errs, orders)
+    floor = (N + 1) * 0.85 if node_type == "GAUSS" else float(N)
+    assert res["cart_periodic"][1][-1] >= floor and res["cart_mortar"][1][-1] >= floor, res
+    assert res["cart_mortar"][1][-1] >= res["cart_periodic"][1][-1] - 0.25, res

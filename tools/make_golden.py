@@ -73,8 +73,10 @@ def main():
     mesh_npz("regressioncheck/checks/parabolic/cavity_3D/cavity4x4x4_mesh.h5", "cavity3d_mesh.npz")
     mesh_npz("regressioncheck/checks/naca/3D/NACA0012_652_Ng2_mesh.h5", "naca_mesh.npz")
     mesh_npz("tutorials/convtest/CART_HEX_PERIODIC_002_mesh.h5", "cart_periodic_002_mesh.npz")
+    mesh_npz("tutorials/convtest/CART_HEX_PERIODIC_004_mesh.h5", "cart_periodic_004_mesh.npz")
+    mesh_npz("tutorials/convtest/CART_HEX_PERIODIC_008_mesh.h5", "cart_periodic_008_mesh.npz")
     # non-conforming (mortar) meshes of the convergence-test tutorial: types 1 (1->4), 2 and 3 (1->2), periodic
-    for nm in ("001", "002", "004"):
+    for nm in ("001", "002", "004", "008"):
         mesh_npz(f"tutorials/convtest/CART_HEX_PERIODIC_MORTAR_{nm}_mesh.h5", f"cart_mortar_{nm}_mesh.npz")
     csv = np.loadtxt(os.path.join(REF, "regressioncheck/checks/tgv/split/TGV_Re1600_Split_TGVAnalysis_Reference.csv"),
                      delimiter=",", skiprows=1, converters=lambda s: float(s.replace("E+0", "E+").replace("E-0", "E-")))

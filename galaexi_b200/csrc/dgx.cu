@@ -261,7 +261,7 @@ struct StageTimes {
     int nev = 0;
 };
 
-int rhs(dgx_handle* h, int mode, double mRKA, double b_dt, StageTimes* st = nullptr) {
+int rhs(dgx_handle* h, int mode, double t, double mRKA, double b_dt, StageTimes* st = nullptr) {
     const dgx_config& c = h->cfg;
     const KernelTable* kt = h->kt;
     KParams P = h->P;
@@ -270,6 +270,9 @@ int rhs(dgx_handle* h, int mode, double mRKA, double b_dt, StageTimes* st = null
     P.UmNext = h->Uf[h->cur ^ 1][0];
     P.UsNext = h->Uf[h->cur ^ 1][1];
     const bool multi = c.nRanks > 1 && !h->NbProc.empty();
+    // CalcSource (dg.f90:418): the volume kernels store Ut (MODE 0), k_source_rk adds the source and does the stage update
+    const bool src = P.iniExactFunc == 4;
+    const int vmode = src ? 0 : mode;
     auto mark = [&](void) { if (st) cudaEventRecord(st->ev[st->nev++], h->s); };
     mark();
     if (P.FilterMat) {
@@ -318,10 +321,11 @@ int rhs(dgx_handle* h, int mode, double mRKA, double b_dt, StageTimes* st = null
         if (c.parabolic) CK(cudaStreamWaitEvent(h->s2, h->evGhalo, 0));
         const int nMPI = c.lastMPISide_YOUR - c.firstMPISide_MINE + 1;
         if (nMPI > 0) { kt->sideflux(P, c.firstMPISide_MINE - 1, nMPI, h->s2); if (check_launch(h, "k_sideflux(mpi)")) return 1; }
-        if (h->nBnd) { kt->volsurf(Pb, mode, mRKA, b_dt, h->nBnd, h->s2); if (check_launch(h, "k_volsurf(bnd)")) return 1; }
+        if (h->nBnd) { kt->volsurf(Pb, vmode, mRKA, b_dt, h->nBnd, h->s2); if (check_launch(h, "k_volsurf(bnd)")) return 1; }
         CK(cudaEventRecord(h->evBnd, h->s2));
-        if (h->nInner) { kt->volsurf(Pi, mode, mRKA, b_dt, h->nInner, h->s); if (check_launch(h, "k_volsurf(inner)")) return 1; }
+        if (h->nInner) { kt->volsurf(Pi, vmode, mRKA, b_dt, h->nInner, h->s); if (check_launch(h, "k_volsurf(inner)")) return 1; }
         CK(cudaStreamWaitEvent(h->s, h->evBnd, 0));
+        if (src) { kt->source_rk(P, mode, t, mRKA, b_dt, c.nElems, h->s); if (c.nElems > 0 && check_launch(h, "k_source_rk")) return 1; }
         mark();
         if (mode == 1) h->cur ^= 1;
         return 0;
@@ -350,16 +354,17 @@ int rhs(dgx_handle* h, int mode, double mRKA, double b_dt, StageTimes* st = null
     mark();
     if (!multi) {
         if (mortar && mortar_flux(h, P.Flux, 5, 1)) return 1;
-        kt->volsurf(P, mode, mRKA, b_dt, c.nElems, h->s);
+        kt->volsurf(P, vmode, mRKA, b_dt, c.nElems, h->s);
         if (check_launch(h, "k_volsurf")) return 1;
     } else {
-        if (h->nInner) { kt->volsurf(Pi, mode, mRKA, b_dt, h->nInner, h->s); if (check_launch(h, "k_volsurf(inner)")) return 1; }
+        if (h->nInner) { kt->volsurf(Pi, vmode, mRKA, b_dt, h->nInner, h->s); if (check_launch(h, "k_volsurf(inner)")) return 1; }
         if (c.parabolic) CK(cudaStreamWaitEvent(h->s, h->evGhalo, 0));
         const int nMPI = c.lastMPISide_YOUR - c.firstMPISide_MINE + 1;
         if (nMPI > 0) { kt->sideflux(P, c.firstMPISide_MINE - 1, nMPI, h->s); if (check_launch(h, "k_sideflux(mpi)")) return 1; }
         if (mortar && mortar_flux(h, P.Flux, 5, 1)) return 1;
-        if (h->nBnd) { kt->volsurf(Pb, mode, mRKA, b_dt, h->nBnd, h->s); if (check_launch(h, "k_volsurf(bnd)")) return 1; }
+        if (h->nBnd) { kt->volsurf(Pb, vmode, mRKA, b_dt, h->nBnd, h->s); if (check_launch(h, "k_volsurf(bnd)")) return 1; }
     }
+    if (src) { kt->source_rk(P, mode, t, mRKA, b_dt, c.nElems, h->s); if (c.nElems > 0 && check_launch(h, "k_source_rk")) return 1; }
     if (mode == 1 && mortar && mortar_u(h, P.UmNext, P.UsNext, 5)) return 1;
     mark();
     if (mode == 1) h->cur ^= 1;
@@ -518,6 +523,19 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
     P.gm = h->gm; P.gs = h->gs; P.Flux = h->Flux; P.errFlag = h->errFlag;
     P.lifting = c.lifting == 2 ? 2 : 1; P.etaBR2 = c.etaBR2; P.etaBR2_wall = c.etaBR2_wall;
     P.MortarType = nullptr;
+    P.xGP = nullptr; P.advVel1 = c.AdvVel[0]; P.iniExactFunc = 0;
+    if (c.IniExactFunc == 4) {
+        if (!c.Elem_xGP) return fail(h, "IniExactFunc=4 (CalcSource) needs Elem_xGP");
+        // reference layout (3,n^3,nElems) -> [elem][3][n^3]
+        std::vector<double> xs((size_t)3 * nDOF);
+        for (size_t e = 0; e < (size_t)c.nElems; e++)
+            for (int node = 0; node < n3; node++)
+                for (int d = 0; d < 3; d++) xs[(e * 3 + d) * n3 + node] = c.Elem_xGP[(e * n3 + node) * 3 + d];
+        double* xd;
+        if (upload(h, &xd, xs.data(), xs.size())) return 1;
+        CK(cudaStreamSynchronize(h->s));
+        P.xGP = xd; P.iniExactFunc = 4;
+    }
     P.FilterMat = nullptr;
     if (c.FilterMat) {
         double* fm;
@@ -589,6 +607,7 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
     h->cfg.RefStatePrim = nullptr;  // pointers are not retained
     h->cfg.MortarType = h->cfg.MortarInfo = nullptr;
     h->cfg.FilterMat = nullptr;
+    h->cfg.Elem_xGP = nullptr;
     h->cfg.M_0_1 = h->cfg.M_0_2 = h->cfg.M_1_0 = h->cfg.M_2_0 = nullptr;
     return 0;
 }
@@ -636,18 +655,16 @@ int dgx_get_gradients(dgx_handle* h, double* gx, double* gy, double* gz) {
 }
 
 int dgx_time_derivative(dgx_handle* h, double t) {
-    (void)t;
     CK(cudaSetDevice(h->cfg.device));
-    if (rhs(h, 0, 0.0, 0.0)) return 1;
+    if (rhs(h, 0, t, 0.0, 0.0)) return 1;
     return check_err_flag(h, "dgx_time_derivative");
 }
 
 int dgx_rk_stage(dgx_handle* h, int iStage, double t, double dt) {
-    (void)t;
     CK(cudaSetDevice(h->cfg.device));
     if (iStage < 1 || iStage > h->cfg.nRKStages) return fail(h, "iStage out of range");
     const double mRKA = (iStage == 1) ? 0.0 : -1.0 * h->RKA[iStage - 1];
-    return rhs(h, 1, mRKA, h->RKb[iStage - 1] * dt);
+    return rhs(h, 1, t, mRKA, h->RKb[iStage - 1] * dt);  // t: the stage time (timestep.f90:86-93)
 }
 
 int dgx_rk_step(dgx_handle* h, double t, double dt) {
@@ -734,14 +751,13 @@ int dgx_run_steps(dgx_handle* h, int nSteps, double t, double dt, int adaptive_d
 }
 
 int dgx_profile_stage(dgx_handle* h, double t, double dt, int cap, const char** names, float* ms, int* count) {
-    (void)t;
     if (count) *count = 0;
     CK(cudaSetDevice(h->cfg.device));
     StageTimes st;
     for (int i = 0; i < 8; i++) CK(cudaEventCreate(&st.ev[i]));
     const int stage = h->cfg.nRKStages > 1 ? 2 : 1;
     const double mRKA = (stage == 1) ? 0.0 : -1.0 * h->RKA[stage - 1];
-    if (rhs(h, 1, mRKA, h->RKb[stage - 1] * dt, &st)) return 1;
+    if (rhs(h, 1, t, mRKA, h->RKb[stage - 1] * dt, &st)) return 1;
     CK(cudaStreamSynchronize(h->s));
     static const char* nm[] = {"halo+lifting", "sideflux", "volsurf_rk"};
     int cnt = 0;

@@ -62,6 +62,10 @@ struct KParams {
     double etaBR2, etaBR2_wall;
     const int* MortarType;     // (2,nSides) or nullptr when the mesh has no mortars
     const double* FilterMat;   // device (0:N,0:N) Fortran layout, or nullptr (FilterType 0)
+    // manufactured-solution source (exactfunc.f90:946-1113): coordinates [elem][3][n^3] or nullptr, AdvVel(1), selector
+    const double* xGP;
+    double advVel1;
+    int iniExactFunc;
     int flags;  // tuning switches (DGX_FLAGS): 1 lifting: L2 prefetch of own later-phase data; 2 lifting: L2 prefetch of the element
                 // a resident wave ahead; 4 / 8: the same two for k_volsurf2
 };
@@ -275,6 +279,62 @@ __global__ void __launch_bounds__(n* n* n) k_filter(const KParams P) {
     __syncthreads();
     extract_faces<n, NT, 5>(b1, P.Um, P.Us, P.E2S + 18 * e, P.S2V2, sLm, sLp);
 }
+
+// Source term + (MODE 1) Williamson 2N update + next-stage face states, for runs with CalcSource (dg.f90:418): the volume
+// kernels then run in MODE 0 and leave Ut = -sJ * (DG operator); here Ut += Ut_src (the reference adds Ut_src / sJ before
+// the Jacobian is applied, exactfunc.f90:1109), then vector.f90:163-183 and the face extraction of the fused epilogue.
+template <int n, int NT, int MODE>
+__global__ void __launch_bounds__(n* n* n) k_source_rk(const KParams P, double t, double mRKA, double b_dt) {
+    constexpr int n2 = n * n, n3 = n2 * n;
+    extern __shared__ double smem[];
+    double *tile = smem, *sLm = smem + 5 * n3, *sLp = sLm + n;
+    const int e = P.elemList ? P.elemList[blockIdx.x] : blockIdx.x;
+    const int tt = threadIdx.x;
+    if (tt < n) { sLm[tt] = P.L_Minus[tt]; sLp[tt] = P.L_Plus[tt]; }
+    double src[5] = {0, 0, 0, 0, 0};
+    if (P.iniExactFunc == 4) {
+        const double* X = P.xGP + (size_t)e * 3 * n3 + tt;
+        const double Kappa = P.eos.kappa, PP_Pi = acos(-1.0), Amplitude = 0.1;
+        const double Omega = PP_Pi * 1.0, a = P.advVel1 * 2. * PP_Pi;
+        double tmp[6];
+        tmp[0] = -a + 3. * Omega;
+        tmp[1] = -a + 0.5 * Omega * (1. + Kappa * 5.);
+        tmp[2] = Amplitude * Omega * (Kappa - 1.);
+        tmp[3] = 0.5 * ((9. + Kappa * 15.) * Omega - 8. * a);
+        tmp[4] = Amplitude * (3. * Omega * Kappa - a);
+        tmp[5] = P.parabolic ? 3. * P.eos.mu0 * Kappa * Omega * Omega / P.eos.Pr : 0.;
+#pragma unroll
+        for (int x = 0; x < 6; x++) tmp[x] = tmp[x] * Amplitude;
+        const double arg = Omega * (X[0] + X[n3] + X[2 * n3]) - a * t;
+        const double cosX = cos(arg), sinX = sin(arg), sin2 = 2. * sinX * cosX;
+        src[0] = tmp[0] * cosX;
+        src[1] = src[2] = src[3] = tmp[1] * cosX + tmp[2] * sin2;
+        src[4] = tmp[3] * cosX + tmp[4] * sin2 + tmp[5] * sinX;
+    }
+    double* Utg = P.Ut + (size_t)e * 5 * n3 + tt;
+#pragma unroll
+    for (int v = 0; v < 5; v++) {
+        // Ut holds sJ * (-R); the reference forms (-R + src / sJ) * sJ = sJ * (-R) + src up to one rounding
+        const double ut = Utg[v * n3] + src[v];
+        if (MODE == 0) {
+            Utg[v * n3] = ut;
+        } else {
+            double* ot = P.Ut_tmp + (size_t)e * 5 * n3 + tt;
+            double* ou = P.U + (size_t)e * 5 * n3 + tt;
+            const double r = (mRKA == 0.0) ? ut : ot[v * n3] * mRKA + ut;
+            ot[v * n3] = r;
+            const double un = ou[v * n3] + r * b_dt;
+            ou[v * n3] = un;
+            tile[v * n3 + tt] = un;
+        }
+    }
+    if (MODE == 1) {
+        __syncthreads();
+        extract_faces<n, NT, 5>(tile, P.UmNext, P.UsNext, P.E2S + 18 * e, P.S2V2, sLm, sLp);
+    }
+}
+template <int n>
+constexpr size_t source_smem_bytes() { return sizeof(double) * (5 * n * n * n + 2 * n); }
 
 template <int n>
 constexpr size_t filter_smem_bytes() { return sizeof(double) * (10 * n * n * n + n * n + 2 * n); }

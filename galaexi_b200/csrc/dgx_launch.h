@@ -18,6 +18,7 @@ struct KernelTable {
     void (*fluxmortar)(double* F, int nvar, int weak, const MortarParams& mp, int nBig, cudaStream_t);
     void (*mortar_liftflux)(const KParams&, const MortarParams& mp, int nBig, cudaStream_t);
     void (*filter)(const KParams&, int nBlocks, cudaStream_t);  // FilterType > 0: U <- FilterMat U, faces of the filtered state
+    void (*source_rk)(const KParams&, int mode, double t, double mRKA, double b_dt, int nBlocks, cudaStream_t);  // CalcSource path
     // TGV diagnostics: per-element partials [nElems][TGV_NPART]; returns a cudaError_t
     int (*tgv_analyze)(const KParams&, int NA1, const double* Vdm, const double* wA, double* partials, cudaStream_t);
 };

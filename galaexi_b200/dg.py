@@ -51,6 +51,7 @@ class DgxConfig(C.Structure):
         + [(k, C.c_int) for k in ("nMortarSides", "firstMortarInnerSide", "lastMortarInnerSide", "firstMortarMPISide",
                                   "lastMortarMPISide")]
         + [("MortarType", _ip), ("MortarInfo", _ip)] + [(k, _dp) for k in ("M_0_1", "M_0_2", "M_1_0", "M_2_0", "FilterMat")]
+        + [("IniExactFunc", C.c_int), ("AdvVel", C.c_double * 3), ("Elem_xGP", _dp)]
     )
 
 
@@ -169,6 +170,12 @@ class DGSolver:
             setattr(c, nm, k[nm].ctypes.data_as(_ip))
         for nm in ("M_0_1", "M_0_2", "M_1_0", "M_2_0"):
             setattr(c, nm, k[nm].ctypes.data_as(_dp))
+        if case.IniExactFunc:
+            k["Elem_xGP"] = f64(g["Elem_xGP"])
+            c.Elem_xGP = k["Elem_xGP"].ctypes.data_as(_dp)
+            c.IniExactFunc = int(case.IniExactFunc)
+            for i_, v_ in enumerate(case.AdvVel):
+                c.AdvVel[i_] = v_
         if case.FilterMat is not None:
             k["FilterMat"] = f64(np.asarray(case.FilterMat).T)      # Fortran FilterMat(i,l) at [i + n*l]
             c.FilterMat = k["FilterMat"].ctypes.data_as(_dp)

@@ -165,3 +165,15 @@ def perturb(U: np.ndarray, amp: float = 1e-3, seed: int = 12345) -> np.ndarray:
     """Optional deterministic perturbation to defeat value-dependent shortcuts; keeps rho, p > 0."""
     rng = np.random.default_rng(seed)
     return U * (1.0 + amp * rng.standard_normal(U.shape))
+
+
+def exact_func_4(x: np.ndarray, t: float, adv_vel=(0.3, 0.3, 0.3)) -> np.ndarray:
+    """IniExactFunc = 4 (idealgas/exactfunc.f90:326-333): oblique sine wave, the manufactured solution of the convergence
+    tests; needs the source term of CalcSource (exactfunc.f90:991-1023)."""
+    omega = PI * 1.0
+    a = adv_vel[0] * 2.0 * PI
+    r = 2.0 + 0.1 * np.sin(omega * np.sum(x, axis=-1) - a * t)
+    U = np.empty(x.shape[:-1] + (5,))
+    U[..., 0:4] = r[..., None]
+    U[..., 4] = r * r
+    return U

@@ -94,6 +94,12 @@ typedef struct dgx_config {
      * InitFilter (filter.f90:95-212, FilterType cutoff / modal), or NULL for FilterType 0. Applied in place to U at the
      * start of every dgx_time_derivative / RK stage, like the reference. */
     const double *FilterMat;
+    /* source term of the manufactured solutions (dg/dg.f90:418 CalcSource, idealgas/exactfunc.f90:946-1113): IniExactFunc
+     * (4: oblique sine wave of the convergence tests; 0 or any other value: no source), AdvVel(3), and the node
+     * coordinates Elem_xGP(3,0:N,0:N,0:N,nElems) (only read when a source is active) */
+    int IniExactFunc;
+    double AdvVel[3];
+    const double *Elem_xGP;
 } dgx_config;
 
 int dgx_create(dgx_handle **h, const dgx_config *cfg);

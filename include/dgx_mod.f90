@@ -36,6 +36,9 @@ TYPE, BIND(C), PUBLIC :: dgx_config
   TYPE(C_PTR)    :: MortarType, MortarInfo
   TYPE(C_PTR)    :: M_0_1, M_0_2, M_1_0, M_2_0
   TYPE(C_PTR)    :: FilterMat   ! filter.f90:203, C_NULL_PTR if FilterType=0
+  INTEGER(C_INT) :: IniExactFunc ! source term selection (exactfunc.f90:665-926)
+  REAL(C_DOUBLE) :: AdvVel(3)
+  TYPE(C_PTR)    :: Elem_xGP
 END TYPE dgx_config
 
 TYPE(C_PTR), PUBLIC, SAVE :: dgx = C_NULL_PTR   !< the library handle (one per rank)

@@ -88,6 +88,10 @@ typedef struct {
     const double *M_0_1, *M_0_2, *M_1_0, *M_2_0;
     /* modal filter applied to U at the start of the RHS (dg.f90:331): FilterMat(0:N,0:N) or NULL (FilterType 0) */
     const double *FilterMat;
+    /* source term of the manufactured solution (exactfunc.f90:665-926 CalcSource, GPU kernel :946-1113): IniExactFunc 4 */
+    int iniExactFunc;
+    double AdvVel[3];
+    const double *Elem_xGP; /* (3,n,n,n,nElems) */
 } dgo_config;
 
 typedef struct {
@@ -1275,6 +1279,37 @@ static int fill_flux(dgo *s)
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* idealgas/exactfunc.f90:946-1113 CalcSource_CUDA_Kernel, CASE(4) (3D): Ut += Ut_src / sJ, called between the sign change
+ * and the Jacobian (dg.f90:413-423) */
+static void calc_source(dgo *s, double t)
+{
+    const dgo_config *c = &s->c;
+    if (c->iniExactFunc != 4) return;
+    const double Kappa = c->EOS[EOS_KAPPA], PP_Pi = acos(-1.0);
+    const double Frequency = 1., Amplitude = 0.1;
+    const double Omega = PP_Pi * Frequency, a = c->AdvVel[0] * 2. * PP_Pi;
+    double tmp[6];
+    tmp[0] = -a + 3. * Omega;
+    tmp[1] = -a + 0.5 * Omega * (1. + Kappa * 5.);
+    tmp[2] = Amplitude * Omega * (Kappa - 1.);
+    tmp[3] = 0.5 * ((9. + Kappa * 15.) * Omega - 8. * a);
+    tmp[4] = Amplitude * (3. * Omega * Kappa - a);
+    tmp[5] = c->parabolic ? 3. * c->EOS[EOS_MU0] * Kappa * Omega * Omega / c->EOS[EOS_PR] : 0.;
+    for (int x = 0; x < 6; x++) tmp[x] = tmp[x] * Amplitude;
+#pragma omp parallel for schedule(static)
+    for (size_t d = 0; d < s->nDOF; d++) {
+        const double *X = &c->Elem_xGP[3 * d];
+        const double arg = Omega * (X[0] + X[1] + X[2]) - a * t;
+        const double cosX = cos(arg), sinX = sin(arg), sin2 = 2. * sinX * cosX;
+        double src[NV];
+        src[DENS] = tmp[0] * cosX;
+        src[MOM1] = src[MOM2] = src[MOM3] = tmp[1] * cosX + tmp[2] * sin2;
+        src[ENER] = tmp[3] * cosX + tmp[4] * sin2 + tmp[5] * sinX;
+        for (int v = 0; v < NV; v++) s->Ut[NV * d + v] = s->Ut[NV * d + v] + src[v] / c->sJ[d];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* filter/filter.f90:272-306 Filter -> interpolation/changeBasis.t90:287-360 ChangeBasis3D_GPU with X_Out absent: U is
  * replaced by FilterMat applied along xi, then eta, then zeta */
 static void filter_u(dgo *s)
@@ -1310,7 +1345,6 @@ static void filter_u(dgo *s)
 /* dg/dg.f90:255-425 DGTimeDerivative_weakForm (single rank: no halo phases) */
 int dgo_time_derivative(dgo *s, double t)
 {
-    (void)t;
     const dgo_config *c = &s->c;
     const double kappa = c->EOS[EOS_KAPPA], R = c->EOS[EOS_R];
     /* 1. dg.f90:331 */ filter_u(s);
@@ -1332,10 +1366,12 @@ int dgo_time_derivative(dgo *s, double t)
     /* 11.5 */ surf_int(s, NV, s->Flux_master, s->Flux_slave, s->Ut, 0, 0, 0);
     /* 12. vector.f90:210 VAX_GPU(-1), 14. applyjacobian.t90:196 */
 #pragma omp parallel for schedule(static)
-    for (size_t d = 0; d < s->nDOF; d++) {
+    for (size_t d = 0; d < s->nDOF; d++)
         for (int v = 0; v < NV; v++) s->Ut[NV * d + v] = s->Ut[NV * d + v] * (-1.);
+    /* 13. */ calc_source(s, t);
+#pragma omp parallel for schedule(static)
+    for (size_t d = 0; d < s->nDOF; d++)
         for (int v = 0; v < NV; v++) s->Ut[NV * d + v] = s->Ut[NV * d + v] * c->sJ[d];
-    }
     return err;
 }
 

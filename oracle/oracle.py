@@ -41,7 +41,8 @@ class _Prec:
                        [(k, C.c_int) for k in ("firstMortarInnerSide", "lastMortarInnerSide", "firstMortarMPISide",
                                                "lastMortarMPISide")] + \
                        [(k, _ip) for k in ("MortarType", "MortarInfo", "FS2M", "SideToElem")] + \
-                       [(k, rp) for k in ("M_0_1", "M_0_2", "M_1_0", "M_2_0", "FilterMat")]
+                       [(k, rp) for k in ("M_0_1", "M_0_2", "M_1_0", "M_2_0", "FilterMat")] + \
+                       [("iniExactFunc", C.c_int), ("AdvVel", self.real * 3), ("Elem_xGP", rp)]
         self.Config = Config
         self._lib = None
 
@@ -154,6 +155,12 @@ class Oracle:
             setattr(c, k, _d(self._keep[k]))
         for k in ("ElemToSide", "S2V2", "S2V2_inv", "BCSides", "MortarType", "MortarInfo", "FS2M", "SideToElem"):
             setattr(c, k, _i(self._keep[k]))
+        if getattr(case, "IniExactFunc", 0):
+            self._keep["Elem_xGP"] = f64(g["Elem_xGP"])
+            c.Elem_xGP = _d(self._keep["Elem_xGP"])
+            c.iniExactFunc = int(case.IniExactFunc)
+            for k_, v_ in enumerate(case.AdvVel):
+                c.AdvVel[k_] = v_
         FilterMat = getattr(case, "FilterMat", None)
         if FilterMat is not None:
             self._keep["FilterMat"] = f64(np.asarray(FilterMat).T)   # Fortran FilterMat(i,l) at [i + n*l]

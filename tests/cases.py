@@ -147,8 +147,22 @@ def convtest_case(mesh="cart_periodic_004", N=3, nProcs=1, myRank=0, **kw):
     return c, exact_sine(c.geo["Elem_xGP"], 0.0)
 
 
-def l2_error(c, U, t, NAnalyze=None):
+def manufactured_case(mesh="cart_periodic_004", N=3, nProcs=1, myRank=0, **kw):
+    """regressioncheck/checks/convtest/h_3D: Navier-Stokes, IniExactFunc=4 (oblique sine wave) with the source term of
+    CalcSource, AdvVel=(0.3,0.3,0.3), mu0=1e-3, CFLScale=DFLScale=0.7 (parameter.ini)."""
+    h = kw.pop("hopr", None) or load_mesh(f"{mesh}_mesh.npz")
+    eos = eq.Eos(kappa=1.4, R=287.058, Pr=0.72, mu0=1.0e-3)
+    args = dict(split=None, riemann="RoeEntropyFix", parabolic=True, eos=eos, refstates=((1.0, 0.3, 0.0, 0.0, 0.71428571),),
+                nProcs=nProcs, myRank=myRank, CFLScale=0.7, DFLScale=0.7, useCurveds=False, IniExactFunc=4, AdvVel=CONV_ADV)
+    args.update(kw)
+    nt = args.pop("node_type", bs.NODETYPE_G)
+    c = cs.build_case(h, N, nt, **args)
+    return c, eq.exact_func_4(c.geo["Elem_xGP"], 0.0, CONV_ADV)
+
+
+def l2_error(c, U, t, NAnalyze=None, exact=None):
     """CalcErrorNorms (analyze/analyze.f90:383-470): L2 error against the exact function on the analysis nodes."""
+    exact = exact or exact_sine
     from galaexi_b200.host import analyze as an
     NA, V, wA = an.init_analyze_basis(c.N, c.node_type, NAnalyze)
 
@@ -158,7 +172,7 @@ def l2_error(c, U, t, NAnalyze=None):
         return np.einsum("Kk,ekJIc->eKJIc", V, Y)
     Ua, xa, Ja = up(U), up(c.geo["Elem_xGP"]), up((1.0 / c.geo["sJ"])[..., None])[..., 0]
     w3 = wA[:, None, None] * wA[None, :, None] * wA[None, None, :]
-    d = Ua - exact_sine(xa, t)
+    d = Ua - exact(xa, t)
     return np.sqrt(np.sum((w3[None] * Ja)[..., None] * d * d, axis=(0, 1, 2, 3)) / an.volume(c))
 
 

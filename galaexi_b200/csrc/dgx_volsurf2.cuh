@@ -21,6 +21,20 @@
 
 namespace dgx {
 
+// Tile layout of k_volsurf2: the conflict-free swizzle for n = 8 (Tile<8>), and for the other sizes the plain layout with
+// a padded zeta stride chosen by exhaustive search over the kernel's access patterns (point-wise and the three line
+// directions, both line halves, 2 elements per CTA): n = 6: 1.84 -> 1.39 wavefronts per ideal wavefront, n = 4: 2.71 ->
+// 1.29; n = 5, 7 gain nothing (odd strides) and stay unpadded.
+template <int n>
+struct TileV {
+    static constexpr int PK = (n == 6) ? 41 : ((n == 4) ? 19 : n * n);
+    static constexpr int SLOT = (n == 8) ? Tile<n>::SLOT : PK * n;
+    __device__ __forceinline__ static int idx(int i, int j, int k) {
+        if constexpr (n == 8) return Tile<n>::idx(i, j, k);
+        else return i + n * j + PK * k;
+    }
+};
+
 template <int n>
 constexpr int vs2_epb() { return (128 + n * n) / (2 * n * n) > 0 ? (128 + n * n) / (2 * n * n) : 1; }
 template <int n>
@@ -34,7 +48,7 @@ constexpr int VS2_CU = VS2_CROSS_UNROLL;
 #define VS2_MIN_BLOCKS(n) ((n) >= 6 ? 3 : 4)
 #endif
 template <int n>
-constexpr size_t vs2_smem_bytes() { return sizeof(double) * ((size_t)vs2_epb<n>() * VS2_SLOTS * Tile<n>::SLOT + 2 * n * n); }
+constexpr size_t vs2_smem_bytes() { return sizeof(double) * ((size_t)vs2_epb<n>() * VS2_SLOTS * TileV<n>::SLOT + 2 * n * n); }
 
 // tile index of position l on the line (c1,c2) of direction d (0 xi: (j,k), 1 eta: (i,k), 2 zeta: (i,j)); d is a run-time
 // value on purpose: one copy of the sweep code serves the three directions (the fully unrolled variant was
@@ -44,7 +58,7 @@ __device__ __forceinline__ int line_idx(int d, int l, int c1, int c2) {
     const int i = (d == 0) ? l : c1;
     const int j = (d == 0) ? c1 : ((d == 1) ? l : c2);
     const int k = (d == 2) ? l : c2;
-    return Tile<n>::idx(i, j, k);
+    return TileV<n>::idx(i, j, k);
 }
 
 // Two-point flux of one node pair for split variant VAR (compile-time: no variant branches in the sweeps, and the dead
@@ -109,7 +123,7 @@ __device__ __forceinline__ void vs2_pair_acc(const double* __restrict__ a, const
 template <int n, int VAR>
 __device__ __forceinline__ void vs2_sweep(const double* __restrict__ R, const double* __restrict__ Mx, const double* __restrict__ Dv, int d,
                                           int c1, int c2, int h, double (&acc)[(n + 1) / 2][5]) {
-    constexpr int SEG = (n + 1) / 2, SL = Tile<n>::SLOT;
+    constexpr int SEG = (n + 1) / 2, SL = TileV<n>::SLOT;
     const int a0 = h * SEG, cnt = h ? n - SEG : SEG;
     const int f0 = h ? 0 : SEG, fcnt = n - cnt;
     double own[SEG][9];
@@ -158,7 +172,7 @@ __device__ __forceinline__ void vs2_sweep(const double* __restrict__ R, const do
 
 template <int n, int MODE, int VAR>
 __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf2(const __grid_constant__ KParams P, int nWork, double mRKA, double b_dt, int lookahead) {
-    constexpr int n2 = n * n, n3 = n2 * n, SEG = (n + 1) / 2, SL = Tile<n>::SLOT, T = 2 * n2, EPB = vs2_epb<n>();
+    constexpr int n2 = n * n, n3 = n2 * n, SEG = (n + 1) / 2, SL = TileV<n>::SLOT, T = 2 * n2, EPB = vs2_epb<n>();
     extern __shared__ double smem[];
     const int le = threadIdx.x / T, tid = threadIdx.x - le * T;
     const int we = blockIdx.x * EPB + le;
@@ -207,7 +221,7 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
             for (int m = 0; m < SEG; m++) {
                 if (m < cnt) {
                     const int node = c1 + n * c2 + n2 * (a0 + m);
-                    const unsigned dst = (unsigned)__cvta_generic_to_shared(S + Tile<n>::idx(c1, c2, a0 + m));
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(S + TileV<n>::idx(c1, c2, a0 + m));
 #pragma unroll
                     for (int x = 0; x < 12; x++)
                         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (unsigned)(x * SL * 8)), "l"(gU + x * n3 + node) : "memory");
@@ -228,7 +242,7 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
 #pragma unroll
         for (int m = 0; m < SEG; m++) {
             if (m < cnt) {
-                const int id = Tile<n>::idx(c1, c2, a0 + m);
+                const int id = TileV<n>::idx(c1, c2, a0 + m);
                 double Pr[6];
                 cons_to_prim(Pr, Uc[m], eos);
                 vs2_record<VAR>(Rec[m], Uc[m], Pr);
@@ -262,7 +276,7 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
     if (par && live) {
 #pragma unroll 2
         for (int l = 0; l < n; l++) {
-            const int idz = Tile<n>::idx(c1, c2, l);
+            const int idz = TileV<n>::idx(c1, c2, l);
             double hz[4];
 #pragma unroll
             for (int v = 0; v < 4; v++) hz[v] = S[(8 + v) * SL + idz];
@@ -272,7 +286,7 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
                 if (m < cnt) {
                     const int k = a0 + m;
                     const double dz = Dh[l + n * k];
-                    const int idx_ = Tile<n>::idx(l, c2, k), idy = Tile<n>::idx(c1, l, k);
+                    const int idx_ = TileV<n>::idx(l, c2, k), idy = TileV<n>::idx(c1, l, k);
 #pragma unroll
                     for (int v = 0; v < 4; v++) UtV[m][v] = fma(dy, S[(4 + v) * SL + idy], fma(dz, hz[v], fma(dx, S[v * SL + idx_], UtV[m][v])));
                 }
@@ -285,7 +299,7 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
 #pragma unroll
         for (int m = 0; m < SEG; m++) {
             if (m < cnt) {
-                const int id = Tile<n>::idx(c1, c2, a0 + m);
+                const int id = TileV<n>::idx(c1, c2, a0 + m);
 #pragma unroll
                 for (int v = 0; v < 4; v++) S[v * SL + id] = UtV[m][v];
                 S[10 * SL + id] = 0.0;
@@ -306,7 +320,7 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
                 for (int m = 0; m < SEG; m++) {
                     if (m < cnt) {
                         const double* Mg = gM_e + (c1 + n * c2 + n2 * (a0 + m)) + (size_t)6 * n3;
-                        const unsigned dst = (unsigned)__cvta_generic_to_shared(S + 12 * SL + Tile<n>::idx(c1, c2, a0 + m));
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(S + 12 * SL + TileV<n>::idx(c1, c2, a0 + m));
 #pragma unroll
                         for (int c = 0; c < 3; c++)
                             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (unsigned)(c * SL * 8)), "l"(Mg + c * n3) : "memory");
@@ -347,7 +361,7 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
             const int a = s2v2<n>(P.S2V2, 0, p, qq, flip, loc);
             const int b = s2v2<n>(P.S2V2, 1, p, qq, flip, loc);
             const int l = h ? n - 1 : 0;
-            idf[r] = (r == 0) ? Tile<n>::idx(l, a, b) : ((r == 1) ? Tile<n>::idx(a, l, b) : Tile<n>::idx(a, b, l));
+            idf[r] = (r == 0) ? TileV<n>::idx(l, a, b) : ((r == 1) ? TileV<n>::idx(a, l, b) : TileV<n>::idx(a, b, l));
             wf[r] = ((flip == 0) ? 1.0 : -1.0) * (h ? P.L_HatPlus[n - 1] : P.L_HatMinus[0]);
             const double* F = P.Flux + (size_t)side * 5 * n2 + (p + n * qq);
 #pragma unroll
@@ -380,7 +394,7 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
             if (m < cnt) {
                 const int k = a0 + m;
                 const int node = c1 + n * c2 + n2 * k;
-                const int id = Tile<n>::idx(c1, c2, k);
+                const int id = TileV<n>::idx(c1, c2, k);
                 const double msJ = -sJv[m];
                 double Ut[5];
                 Ut[0] = S[10 * SL + id] * msJ;
@@ -421,9 +435,9 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
                 const int b = s2v2<n>(P.S2V2, 1, p, qq, flip, loc);
                 const int l = is_minus(loc) ? 0 : n - 1;
                 int id;
-                if (loc == XI_MINUS || loc == XI_PLUS) id = Tile<n>::idx(l, a, b);
-                else if (loc == ETA_MINUS || loc == ETA_PLUS) id = Tile<n>::idx(a, l, b);
-                else id = Tile<n>::idx(a, b, l);
+                if (loc == XI_MINUS || loc == XI_PLUS) id = TileV<n>::idx(l, a, b);
+                else if (loc == ETA_MINUS || loc == ETA_PLUS) id = TileV<n>::idx(a, l, b);
+                else id = TileV<n>::idx(a, b, l);
                 double* dst = (flip == 0 ? P.UmNext : P.UsNext) + (size_t)side * 5 * n2 + pq;
 #pragma unroll
                 for (int v = 0; v < 5; v++) dst[v * n2] = S[(4 + v) * SL + id];

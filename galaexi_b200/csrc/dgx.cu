@@ -131,6 +131,7 @@ struct dgx_handle {
     std::vector<int> NbProc, nMine, nYour, offMine, offYour;
     std::vector<HaloMsg> plan;
     ncclComm_t comm = nullptr;
+    double *bvPart = nullptr, *bvW = nullptr;  // dgx_calc_bulk_velocity
     // TGV diagnostics (dgx_analyze_tgv)
     double *tgvV = nullptr, *tgvW = nullptr, *tgvPart = nullptr;
     int tgvNA1 = 0;
@@ -271,7 +272,7 @@ int rhs(dgx_handle* h, int mode, double t, double mRKA, double b_dt, StageTimes*
     P.UsNext = h->Uf[h->cur ^ 1][1];
     const bool multi = c.nRanks > 1 && !h->NbProc.empty();
     // CalcSource (dg.f90:418): the volume kernels store Ut (MODE 0), k_source_rk adds the source and does the stage update
-    const bool src = P.iniExactFunc == 4;
+    const bool src = P.iniExactFunc == 4 || P.tcSource;
     const int vmode = src ? 0 : mode;
     auto mark = [&](void) { if (st) cudaEventRecord(st->ev[st->nev++], h->s); };
     mark();
@@ -524,6 +525,7 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
     P.lifting = c.lifting == 2 ? 2 : 1; P.etaBR2 = c.etaBR2; P.etaBR2_wall = c.etaBR2_wall;
     P.MortarType = nullptr;
     P.xGP = nullptr; P.advVel1 = c.AdvVel[0]; P.iniExactFunc = 0;
+    P.tcSource = 0; P.tcDpdx = 0.0; P.tcBulkVel = 0.0;
     if (c.IniExactFunc == 4) {
         if (!c.Elem_xGP) return fail(h, "IniExactFunc=4 (CalcSource) needs Elem_xGP");
         // reference layout (3,n^3,nElems) -> [elem][3][n^3]
@@ -694,6 +696,33 @@ int dgx_calc_timestep(dgx_handle* h, double* dt, int* errType) {
     if (h->comm) flag = (h->hPinned[2] < 0.0) ? 2 : 0;
     if (errType) *errType = flag ? 2 : 0;
     if (dt) *dt = h->hPinned[0] < h->hPinned[1] ? h->hPinned[0] : h->hPinned[1];
+    return 0;
+}
+
+int dgx_set_channel_forcing(dgx_handle* h, int on, double dpdx, double BulkVel) {
+    h->P.tcSource = on ? 1 : 0;
+    h->P.tcDpdx = dpdx;
+    h->P.tcBulkVel = BulkVel;
+    return 0;
+}
+
+int dgx_calc_bulk_velocity(dgx_handle* h, const double* wGP, double Vol, double* BulkVel) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (!wGP || !BulkVel) return fail(h, "dgx_calc_bulk_velocity: bad arguments");
+    if (!h->bvPart) {
+        if (dalloc(h, &h->bvPart, (size_t)h->cfg.nElems + 2) || dalloc(h, &h->bvW, (size_t)h->n)) return 1;
+    }
+    CK(cudaMemcpyAsync(h->bvW, wGP, h->n * sizeof(double), cudaMemcpyHostToDevice, h->s));
+    h->kt->bulkvel(h->P, h->bvW, h->bvPart, h->s);
+    if (h->cfg.nElems && check_launch(h, "k_bulkvel")) return 1;
+    double* tot = h->bvPart + h->cfg.nElems;
+    k_sum_partials<<<1, 256, 0, h->s>>>(h->bvPart, h->cfg.nElems, tot);
+    if (check_launch(h, "k_sum_partials")) return 1;
+    if (h->comm) NK(g_nccl.AllReduce(tot, tot, 1, ncclFloat64, 0 /* ncclSum */, h->comm, h->s));  // testcase.f90:266-268
+    double b = 0.0;
+    CK(cudaMemcpyAsync(&b, tot, sizeof b, cudaMemcpyDeviceToHost, h->s));
+    CK(cudaStreamSynchronize(h->s));
+    *BulkVel = b / Vol;
     return 0;
 }
 

@@ -66,6 +66,9 @@ struct KParams {
     const double* xGP;
     double advVel1;
     int iniExactFunc;
+    // channel forcing (testcase/channel/testcase.f90:277-296 TestcaseSource)
+    int tcSource;
+    double tcDpdx, tcBulkVel;
     int flags;  // tuning switches (DGX_FLAGS): 1 lifting: L2 prefetch of own later-phase data; 2 lifting: L2 prefetch of the element
                 // a resident wave ahead; 4 / 8: the same two for k_volsurf2
 };
@@ -311,6 +314,7 @@ __global__ void __launch_bounds__(n* n* n) k_source_rk(const KParams P, double t
         src[1] = src[2] = src[3] = tmp[1] * cosX + tmp[2] * sin2;
         src[4] = tmp[3] * cosX + tmp[4] * sin2 + tmp[5] * sinX;
     }
+    if (P.tcSource) { src[1] -= P.tcDpdx; src[4] -= P.tcDpdx * P.tcBulkVel; }
     double* Utg = P.Ut + (size_t)e * 5 * n3 + tt;
 #pragma unroll
     for (int v = 0; v < 5; v++) {
@@ -1058,6 +1062,42 @@ __global__ void __launch_bounds__(timestep_threads<n>()) k_timestep(const KParam
             if (dtv > 0.0 && isfinite(dtv)) atomic_min_pos(&out[1], dtv);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CalcForcing of the channel testcase (testcase/channel/testcase.f90:241-271): per-element sum of u wGPVol / sJ; the
+// partials are reduced in a fixed order by k_sum_partials
+template <int n>
+__global__ void __launch_bounds__(timestep_threads<n>()) k_bulkvel(const KParams P, const double* __restrict__ wGP, double* __restrict__ partials) {
+    constexpr int n2 = n * n, n3 = n2 * n;
+    __shared__ double red[32];
+    const int e = blockIdx.x, t = threadIdx.x;
+    double v = 0.0;
+    if (t < n3) {
+        const int k = t / n2, j = (t - k * n2) / n, i = t - k * n2 - j * n;
+        const double* U = P.U + (size_t)e * 5 * n3 + t;
+        v = U[n3] / U[0] * (wGP[i] * wGP[j] * wGP[k]) / P.sJ[(size_t)e * n3 + t];
+    }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((t & 31) == 0) red[t >> 5] = v;
+    __syncthreads();
+    if (t == 0) {
+        double s = red[0];
+        for (int w = 1; w < timestep_threads<n>() / 32; w++) s += red[w];
+        partials[e] = s;
+    }
+}
+static __global__ void __launch_bounds__(256) k_sum_partials(const double* __restrict__ partials, int count, double* __restrict__ out) {
+    __shared__ double red[256];
+    double v = 0.0;
+    for (int e = threadIdx.x; e < count; e += 256) v += partials[e];
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = red[0];
 }
 
 // ---------------------------------------------------------------------------------------------------------

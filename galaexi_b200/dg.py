@@ -28,7 +28,7 @@ _ip = C.POINTER(C.c_int)
 
 EXPORTS = ("dgx_create", "dgx_destroy", "dgx_last_error", "dgx_set_state", "dgx_get_state", "dgx_get_ut",
            "dgx_get_gradients", "dgx_time_derivative", "dgx_rk_stage", "dgx_rk_step", "dgx_calc_timestep",
-           "dgx_analyze_tgv", "dgx_sync", "dgx_run_steps", "dgx_profile_stage", "dgx_nccl_unique_id", "dgx_launch_count", "dgx_sizeof_config", "dgx_halo_plan")
+           "dgx_analyze_tgv", "dgx_calc_bulk_velocity", "dgx_set_channel_forcing", "dgx_sync", "dgx_run_steps", "dgx_profile_stage", "dgx_nccl_unique_id", "dgx_launch_count", "dgx_sizeof_config", "dgx_halo_plan")
 
 
 class DgxConfig(C.Structure):
@@ -81,6 +81,8 @@ def load_library():
     lib.dgx_rk_step.argtypes = [h, C.c_double, C.c_double]
     lib.dgx_calc_timestep.argtypes = [h, _dp, _ip]
     lib.dgx_analyze_tgv.argtypes = [h, C.c_int, _dp, _dp, C.c_double, C.c_double, _dp]
+    lib.dgx_calc_bulk_velocity.argtypes = [h, _dp, C.c_double, _dp]
+    lib.dgx_set_channel_forcing.argtypes = [h, C.c_int, C.c_double, C.c_double]
     lib.dgx_sync.argtypes = [h]
     lib.dgx_run_steps.argtypes = [h, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]
     lib.dgx_profile_stage.argtypes = [h, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), _ip]
@@ -258,6 +260,19 @@ class DGSolver:
         self._ck(self.lib.dgx_analyze_tgv(self.h, NA, Vt.ctypes.data_as(_dp), wA.ctypes.data_as(_dp),
                                           float(self._an_vol if Vol is None else Vol), float(rho0), out.ctypes.data_as(_dp)))
         return out
+
+    def CalcForcing(self, Vol: float | None = None) -> float:
+        """CalcForcing of the channel testcase (testcase/channel/testcase.f90:241-271): the bulk velocity."""
+        from .host import analyze as an
+        w = np.ascontiguousarray(self.case.basis.wGP, dtype=np.float64)
+        b = C.c_double()
+        self._ck(self.lib.dgx_calc_bulk_velocity(self.h, w.ctypes.data_as(_dp), float(an.volume(self.case) if Vol is None else Vol),
+                                                 C.byref(b)))
+        return b.value
+
+    def set_channel_forcing(self, dpdx: float, BulkVel: float, on: bool = True):
+        """Parameters of TestcaseSource (testcase/channel/testcase.f90:277-296)."""
+        self._ck(self.lib.dgx_set_channel_forcing(self.h, int(on), float(dpdx), float(BulkVel)))
 
     def FinalizeDG(self):
         if getattr(self, "h", None):

@@ -130,6 +130,14 @@ int dgx_calc_timestep(dgx_handle *h, double *dt, int *errType);
 int dgx_analyze_tgv(dgx_handle *h, int NAnalyze, const double *Vdm_GaussN_NAnalyze, const double *wAnalyze, double Vol,
                     double rho0, double *out15);
 
+/* Channel testcase (testcase/channel/testcase.f90; absent from GALAEXI's GPU path, dg.f90:419 is commented out):
+ * dgx_calc_bulk_velocity = CalcForcing (:241-271): BulkVel = 1/Vol sum u wGPVol / sJ over the solution nodes of all ranks,
+ * wGP(0:N) the 1-D weights of the solution nodes, Vol the global volume.
+ * dgx_set_channel_forcing = the parameters of TestcaseSource (:277-296): with on != 0 every following RHS adds
+ * Ut(MOM1) -= dpdx / sJ, Ut(ENER) -= dpdx / sJ * BulkVel before the Jacobian is applied. */
+int dgx_calc_bulk_velocity(dgx_handle *h, const double *wGP, double Vol, double *BulkVel);
+int dgx_set_channel_forcing(dgx_handle *h, int on, double dpdx, double BulkVel);
+
 /* measurement helpers (not part of the reference interface) */
 int dgx_sync(dgx_handle *h);
 /* nSteps RK steps with fixed dt, state resident in HBM; returns device-timed milliseconds (CUDA events on

@@ -92,6 +92,9 @@ typedef struct {
     int iniExactFunc;
     double AdvVel[3];
     const double *Elem_xGP; /* (3,n,n,n,nElems) */
+    /* channel testcase forcing (testcase/channel/testcase.f90:277-296 TestcaseSource): active if tcSource != 0 */
+    int tcSource;
+    double dpdx, BulkVel;
 } dgo_config;
 
 typedef struct {
@@ -1369,6 +1372,13 @@ int dgo_time_derivative(dgo *s, double t)
     for (size_t d = 0; d < s->nDOF; d++)
         for (int v = 0; v < NV; v++) s->Ut[NV * d + v] = s->Ut[NV * d + v] * (-1.);
     /* 13. */ calc_source(s, t);
+    if (c->tcSource) { /* dg.f90:419 TestcaseSource (commented out in GALAEXI; host FLEXI testcase/channel/testcase.f90:277-296) */
+#pragma omp parallel for schedule(static)
+        for (size_t d = 0; d < s->nDOF; d++) {
+            s->Ut[NV * d + MOM1] = s->Ut[NV * d + MOM1] - c->dpdx / c->sJ[d];
+            s->Ut[NV * d + ENER] = s->Ut[NV * d + ENER] - c->dpdx / c->sJ[d] * c->BulkVel;
+        }
+    }
 #pragma omp parallel for schedule(static)
     for (size_t d = 0; d < s->nDOF; d++)
         for (int v = 0; v < NV; v++) s->Ut[NV * d + v] = s->Ut[NV * d + v] * c->sJ[d];
@@ -1553,6 +1563,20 @@ void dgo_prolong_to_face(dgo *s, int nVar, const double *Uvol, double *Um, doubl
 void dgo_surf_int(dgo *s, int nVar, const double *Fm, const double *Fs, double *Ut) { surf_int(s, nVar, Fm, Fs, Ut, 0, 0, 0); }
 void dgo_lifting(dgo *s) { lifting_br1(s); }
 void dgo_filter(dgo *s) { filter_u(s); }
+void dgo_set_forcing(dgo *s, int on, double dpdx, double BulkVel) { s->c.tcSource = on; s->c.dpdx = dpdx; s->c.BulkVel = BulkVel; }
+/* testcase/channel/testcase.f90:241-271 CalcForcing: BulkVel = 1/Vol sum u wGPVol / sJ over the solution nodes */
+double dgo_bulk_velocity(dgo *s, const double *wGP, double Vol)
+{
+    const dgo_config *c = &s->c;
+    const int n = s->n;
+    double b = 0.;
+    for (int e = 0; e < c->nElems; e++)
+        for (int k = 0; k < n; k++) for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) {
+            size_t d = i + n * (j + n * (k + (size_t)n * e));
+            b = b + s->U[NV * d + MOM1] / s->U[NV * d + DENS] * (wGP[i] * wGP[j] * wGP[k]) / c->sJ[d];
+        }
+    return b / Vol;
+}
 void dgo_u_mortar(dgo *s, int nVar, double *Um, double *Us) { u_mortar_all(s, nVar, Um, Us); }
 void dgo_flux_mortar(dgo *s, int nVar, double *Fm, const double *Fs, int weak) { flux_mortar_all(s, nVar, Fm, Fs, weak); }
 size_t dgo_sizeof_config(void) { return sizeof(dgo_config); }

@@ -42,7 +42,8 @@ class _Prec:
                                                "lastMortarMPISide")] + \
                        [(k, _ip) for k in ("MortarType", "MortarInfo", "FS2M", "SideToElem")] + \
                        [(k, rp) for k in ("M_0_1", "M_0_2", "M_1_0", "M_2_0", "FilterMat")] + \
-                       [("iniExactFunc", C.c_int), ("AdvVel", self.real * 3), ("Elem_xGP", rp)]
+                       [("iniExactFunc", C.c_int), ("AdvVel", self.real * 3), ("Elem_xGP", rp)] + \
+                       [("tcSource", C.c_int), ("dpdx", self.real), ("BulkVel", self.real)]
         self.Config = Config
         self._lib = None
 
@@ -68,6 +69,9 @@ class _Prec:
             L.dgo_surf_int.argtypes = [C.c_void_p, C.c_int, rp, rp, rp]
             L.dgo_lifting.argtypes = [C.c_void_p]
             L.dgo_filter.argtypes = [C.c_void_p]
+            L.dgo_set_forcing.argtypes = [C.c_void_p, C.c_int, r, r]
+            L.dgo_bulk_velocity.restype = r
+            L.dgo_bulk_velocity.argtypes = [C.c_void_p, rp, r]
             L.dgo_rhs_phase.argtypes = [C.c_void_p, C.c_int]
             L.dgo_rk_update.argtypes = [C.c_void_p, r, r]
             L.dgo_sizeof_config.restype = C.c_size_t
@@ -219,6 +223,13 @@ class Oracle:
         err = self.prec.lib().dgo_rk_step(self.h, float(t), float(dt), td.nRKStages, _d(A), _d(b), _d(c))
         if err:
             raise RuntimeError("oracle: unsupported boundary condition type")
+
+    def set_forcing(self, dpdx: float, BulkVel: float, on: bool = True):
+        self.prec.lib().dgo_set_forcing(self.h, int(on), float(dpdx), float(BulkVel))
+
+    def bulk_velocity(self, Vol: float) -> float:
+        w = np.ascontiguousarray(self.case.basis.wGP, dtype=self.prec.np)
+        return float(self.prec.lib().dgo_bulk_velocity(self.h, self.prec.d(w), float(Vol)))
 
     def calc_timestep(self):
         tc, tv = self.prec.real(), self.prec.real()

@@ -453,3 +453,36 @@ def test_h_convergence_manufactured_navier_stokes():
     ok = res["cart_periodic"] >= (N + 1) * (1.0 - 0.15)
     assert ok.mean() >= 0.8 or np.all(res["cart_periodic"][-1] >= (N + 1) * 0.85), res["cart_periodic"]
     assert np.all(res["cart_mortar"] >= res["cart_periodic"][:2] - 0.25), res
+
+
+# ---- channel testcase: CalcForcing + TestcaseSource (testcase/channel/testcase.f90) -----------------------------------------------
+def test_channel_forcing():
+    """BASELINE config #4 made physically meaningful: bulk velocity on the device vs the oracle, and the
+    reference's time loop `CalcForcing; TimeStep` (timedisc.f90:185-187) with the pressure-gradient forcing dpdx = -1."""
+    from galaexi_b200.host import analyze as an
+    c, U0 = cases.channel_case(E=4, N=5)
+    o, s = _oracle(c), _solver(c)
+    o.set_state(U0)
+    s.set_state(U0)
+    Vol = an.volume(c)
+    bv_ref = o.bulk_velocity(Vol)
+    bv = s.CalcForcing()
+    assert abs(bv - bv_ref) <= 1e-13 * abs(bv_ref)
+    dpdx = -1.0
+    o.set_forcing(dpdx, bv_ref)
+    s.set_channel_forcing(dpdx, bv)
+    Ut_ref = o.time_derivative(0.0).copy()
+    s.DGTimeDerivative_weakForm(0.0)
+    assert cases.rel_l2(s.get_ut(), Ut_ref) <= TOL_UT
+    t = 0.0
+    for _ in range(3):
+        bv_ref, bv = o.bulk_velocity(Vol), s.CalcForcing()
+        o.set_forcing(dpdx, bv_ref)
+        s.set_channel_forcing(dpdx, bv)
+        dt = o.calc_timestep()[0]
+        o.rk_step(t, dt)
+        s.TimeStepByLSERKW2(t, dt)
+        t += dt
+    assert cases.rel_l2(s.get_state(), o.array("U")) <= TOL_U
+    s.FinalizeDG()
+    o.close()

@@ -219,3 +219,29 @@ def test_manufactured_source_balances_the_operator(parabolic):
         o.close()
     # measured: 1.97, 0.19, 0.012 (max norm, 2^3 elements): one order of magnitude per two degrees
     assert errs[1] < 0.15 * errs[0] and errs[2] < 0.15 * errs[1] and errs[2] < 0.05, errs
+
+
+# ---- channel testcase forcing (testcase/channel/testcase.f90) -----------------------------------------------------------------
+def test_channel_forcing_oracle():
+    """TestcaseSource adds -dpdx to the x-momentum and -dpdx*BulkVel to the energy equation (after the Jacobian); CalcForcing
+    integrates the bulk velocity (here checked against the analytic mean of the parabolic profile of the test state)."""
+    from galaexi_b200.host import analyze as an
+    c, U0 = cases.channel_case(E=3, N=4)
+    o = Oracle(c)
+    o.set_state(U0)
+    Ut0 = o.time_derivative(0.0).copy()
+    Vol = an.volume(c)
+    bv = o.bulk_velocity(Vol)
+    rho_u = U0[..., 1] / U0[..., 0]
+    w = c.basis.wGP
+    W = w[:, None, None] * w[None, :, None] * w[None, None, :]
+    assert abs(bv - np.sum(W[None] / c.geo["sJ"] * rho_u) / Vol) <= 1e-13 * abs(bv)
+    assert abs(bv - 1.0) < 0.05            # mean of 1.5 (1 - y^2) (1 + small perturbation) over y in [-1, 1]
+    dpdx = -1.0
+    o.set_forcing(dpdx, bv)
+    Ut1 = o.time_derivative(0.0).copy()
+    d = Ut1 - Ut0
+    scale = np.abs(Ut0).max()
+    assert np.abs(d[..., 1] - (-dpdx)).max() <= 1e-12 * scale and np.abs(d[..., 4] - (-dpdx * bv)).max() <= 1e-12 * scale
+    assert np.abs(d[..., [0, 2, 3]]).max() == 0.0
+    o.close()

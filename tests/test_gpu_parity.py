@@ -486,3 +486,58 @@ def test_channel_forcing():
     assert cases.rel_l2(s.get_state(), o.array("U")) <= TOL_U
     s.FinalizeDG()
     o.close()
+
+
+# ---- error behaviour (the reference aborts; the library returns an error the Fortran shim maps to Abort) ------------------------
+def test_nan_state_is_reported_by_calc_timestep():
+    """calctimestep.f90:134-146: a non-finite / inadmissible state sets errType and the time loop aborts with
+    'density, convective / viscous timestep is NaN'."""
+    c, U0 = cases.tgv_box_case(E=2, N=3)
+    s = _solver(c)
+    U = U0.copy()
+    U[1, 2, 1, 0, 0] = -1.0          # negative density in one node
+    s.set_state(U)
+    dt, err = s.CalcTimeStep()
+    assert err != 0
+    with pytest.raises(Exception):
+        s.calc_timestep()
+    U = U0.copy()
+    U[0, 0, 0, 0, 4] = np.nan
+    s.set_state(U)
+    assert s.CalcTimeStep()[1] != 0
+    s.set_state(U0)
+    assert s.CalcTimeStep()[1] == 0
+    s.FinalizeDG()
+
+
+def test_unsupported_boundary_type_is_an_error():
+    """getboundaryflux.f90:483-486 'no BC defined in navierstokes/getboundaryflux.f90!' -> CALL Abort."""
+    from galaexi_b200.dg import DGError
+    c, U_uniform, U0 = cases.duct_case((2, 1), (24, 1), (3, 0), N=2)
+    c.BCSides[0, 0] = 77             # a type the equation system does not know
+    s = _solver(c)
+    s.set_state(U0)
+    with pytest.raises(DGError, match="boundary condition"):
+        s.DGTimeDerivative_weakForm(0.0)
+    s.FinalizeDG()
+
+
+def test_handle_reuse_and_two_solvers_on_one_device():
+    """Two handles live side by side (the reference has module globals: one operator per process); results are independent."""
+    c1, U1 = cases.tgv_box_case(E=2, N=3)
+    c2, U2 = cases.tgv_box_case(E=3, N=4, NGeo=2, deform=0.05)
+    a, b = _solver(c1), _solver(c2)
+    a.set_state(U1)
+    b.set_state(U2)
+    a.DGTimeDerivative_weakForm(0.0)
+    b.DGTimeDerivative_weakForm(0.0)
+    ua, ub = a.get_ut(), b.get_ut()
+    a.FinalizeDG()
+    a2 = _solver(c1)
+    a2.set_state(U1)
+    a2.DGTimeDerivative_weakForm(0.0)
+    assert np.array_equal(a2.get_ut(), ua)         # bitwise reproducible
+    b.DGTimeDerivative_weakForm(0.0)
+    assert np.array_equal(b.get_ut(), ub)
+    a2.FinalizeDG()
+    b.FinalizeDG()

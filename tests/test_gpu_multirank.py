@@ -15,7 +15,7 @@ def _ngpus():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("case", ["tgv", "cavity", "channel", "shu", "tgv_br2", "mortar001", "mortar004_br2"])
+@pytest.mark.parametrize("case", ["tgv", "cavity", "channel", "shu", "tgv_br2", "mortar001", "mortar004_br2", "tgv_filter", "manufactured"])
 def test_two_ranks_match_single_rank(case):
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")
@@ -26,4 +26,4 @@ def test_two_ranks_match_single_rank(case):
     lines = [l for l in p.stdout.splitlines() if l.startswith("MRCHECK ")]
     assert p.returncode == 0 and lines, p.stdout[-2000:] + p.stderr[-4000:]
     r = json.loads(lines[-1][8:])
-    assert r["u_rel_l2"] <= 1e-10 and r["dt_rel"] <= 1e-13
+    assert r["u_rel_l2"] <= 1e-10 and r["dt_rel"] <= 1e-13 and r["diag_rel"] <= 1e-9 and r["bulk_rel"] <= 1e-10

@@ -206,8 +206,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--degree", type=int, default=N_POLY,
                     help="polynomial degree N (default 7 = BASELINE config #2, the headline; 5 = per-GPU load of config #3)")
+    ap.add_argument("--elems", type=int, default=ELEMS_PER_GPU, help="elements per direction and GPU (default 32; 64 = config #3 on one GPU)")
     args = ap.parse_args()
     globals()["N_POLY"] = args.degree
+    globals()["ELEMS_PER_GPU"] = args.elems
     if args.impl == "reference":
         return run_reference(args)
 

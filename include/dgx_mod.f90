@@ -80,10 +80,24 @@ INTERFACE
   INTEGER(C_INT) FUNCTION dgx_nccl_unique_id(id) BIND(C,NAME='dgx_nccl_unique_id')
     IMPORT; CHARACTER(KIND=C_CHAR),INTENT(OUT) :: id(128)
   END FUNCTION
+  !> AnalyzeTestcase of the Taylor-Green vortex (testcase/taylorgreenvortex/testcase.f90:283-515) on the device
+  INTEGER(C_INT) FUNCTION dgx_analyze_tgv(h,NAnalyze,Vdm_GaussN_NAnalyze,wAnalyze,Vol,rho0,out15) BIND(C,NAME='dgx_analyze_tgv')
+    IMPORT; TYPE(C_PTR),VALUE :: h; INTEGER(C_INT),VALUE :: NAnalyze
+    REAL(C_DOUBLE),INTENT(IN) :: Vdm_GaussN_NAnalyze(*),wAnalyze(*); REAL(C_DOUBLE),VALUE :: Vol,rho0
+    REAL(C_DOUBLE),INTENT(OUT) :: out15(15)
+  END FUNCTION
+  !> CalcForcing / TestcaseSource of the channel testcase (testcase/channel/testcase.f90:241-296)
+  INTEGER(C_INT) FUNCTION dgx_calc_bulk_velocity(h,wGP,Vol,BulkVel) BIND(C,NAME='dgx_calc_bulk_velocity')
+    IMPORT; TYPE(C_PTR),VALUE :: h; REAL(C_DOUBLE),INTENT(IN) :: wGP(*); REAL(C_DOUBLE),VALUE :: Vol; REAL(C_DOUBLE),INTENT(OUT) :: BulkVel
+  END FUNCTION
+  INTEGER(C_INT) FUNCTION dgx_set_channel_forcing(h,on,dpdx,BulkVel) BIND(C,NAME='dgx_set_channel_forcing')
+    IMPORT; TYPE(C_PTR),VALUE :: h; INTEGER(C_INT),VALUE :: on; REAL(C_DOUBLE),VALUE :: dpdx,BulkVel
+  END FUNCTION
 END INTERFACE
 
 PUBLIC :: dgx_create,dgx_destroy,dgx_last_error,dgx_set_state,dgx_get_state,dgx_get_ut,dgx_get_gradients
 PUBLIC :: dgx_time_derivative,dgx_rk_stage,dgx_rk_step,dgx_calc_timestep,dgx_nccl_unique_id
+PUBLIC :: dgx_analyze_tgv,dgx_calc_bulk_velocity,dgx_set_channel_forcing
 PUBLIC :: DGX_Check
 
 CONTAINS

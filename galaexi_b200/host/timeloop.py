@@ -9,14 +9,35 @@ Works with any operator exposing ``calc_timestep() -> (dt, dt_conv, dt_visc)`` a
 from __future__ import annotations
 
 
-def advance(op, t0: float, tEnd: float, maxIter: int | None = None, fixed_dt: float | None = None):
-    """Advance ``op`` from t0 to tEnd; returns (t, nTimeSteps)."""
+def advance(op, t0: float, tEnd: float, maxIter: int | None = None, fixed_dt: float | None = None,
+            nCalcTimeStepMax: int = 1):
+    """Advance ``op`` from t0 to tEnd; returns (t, nTimeSteps).
+
+    nCalcTimeStepMax (ini key NCalcTimeStepMax, default 1 = every step): the reference re-evaluates dt only every
+    n-th step, n = min(floor(|log10((dt_old/dt - 1)^2 * 100 + eps)|), nCalcTimeStepMax), i.e. less often the slower dt
+    changes (timedisc_func.f90:265-280); the end-time clipping is applied when dt is evaluated, as in the reference."""
+    import math
+    import sys
     t = t0
     it = 0
+    nCalc = 0
+    dt_old = -999.0
+    dt_keep = None
     while True:
         if maxIter is not None and it >= maxIter:
             break
+        if nCalc >= 1 and dt_keep is not None and tEnd - t > dt_keep * 1.01:
+            nCalc -= 1
+            op.rk_step(t, dt_keep)
+            t += dt_keep
+            it += 1
+            continue
         dt_min = fixed_dt if fixed_dt is not None else op.calc_timestep()[0]
+        if nCalcTimeStepMax > 1:
+            arg = abs(dt_old / dt_min - 1.0) ** 2 * 100.0 + sys.float_info.epsilon
+            nCalc = min(int(math.floor(abs(math.log10(arg)))), nCalcTimeStepMax) - 1
+            dt_old = dt_min
+            dt_keep = dt_min
         dt_end = tEnd - t
         dt = min(dt_min, dt_end)
         finalize = dt == dt_end

@@ -245,3 +245,25 @@ def test_channel_forcing_oracle():
     assert np.abs(d[..., 1] - (-dpdx)).max() <= 1e-12 * scale and np.abs(d[..., 4] - (-dpdx * bv)).max() <= 1e-12 * scale
     assert np.abs(d[..., [0, 2, 3]]).max() == 0.0
     o.close()
+
+
+def test_time_loop_dt_reuse_rule():
+    """UpdateTimeStep (timedisc_func.f90:246-300): with NCalcTimeStepMax > 1 dt is re-evaluated less often the slower it
+    changes; the default (1) evaluates it every step. Checked on a stub operator with a slowly drifting dt."""
+    from galaexi_b200.host import timeloop
+
+    class Op:
+        def __init__(self):
+            self.ncalc, self.t = 0, 0.0
+
+        def calc_timestep(self):
+            self.ncalc += 1
+            return (1e-2 * (1.0 + 1e-6 * self.t), None, None)
+
+        def rk_step(self, t, dt):
+            self.t = t + dt
+    a, b = Op(), Op()
+    ta, na = timeloop.advance(a, 0.0, 1.0)
+    tb, nb = timeloop.advance(b, 0.0, 1.0, nCalcTimeStepMax=10)
+    assert ta == tb == 1.0 and a.ncalc == na and abs(na - nb) <= 1
+    assert b.ncalc <= nb // 4            # dt drifts by 1e-8 per step -> the evaluation is skipped most of the time

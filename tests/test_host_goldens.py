@@ -201,3 +201,51 @@ def test_hilbert_curve_is_a_space_filling_curve():
     order = np.argsort(key)
     steps = np.abs(np.diff(ijk[order], axis=0)).sum(axis=1)
     assert np.all(steps == 1)
+
+
+def test_change_basis_unit_golden(goldens):
+    """unitTests/ChangeBasis.f90: ChangeBasis3D / ChangeBasis3D_XYZ / ChangeBasis2D with the test's synthetic Vandermonde
+    matrices (NIn=4 -> NOut=5) against ChangeBasis.bin (50 eps). The same tensor-product routine interpolates the metrics,
+    feeds the analysis quadrature and -- with a square matrix -- is the modal filter of the RHS."""
+    from galaexi_b200.host import metrics as mt
+    nVar, NIn, NOut, nElems = 3, 4, 5, 6
+    V1 = np.zeros((NOut + 1, NIn + 1))
+    V2, V3 = np.zeros_like(V1), np.zeros_like(V1)
+    z = 1
+    for q in range(NIn + 1):
+        for p in range(NOut + 1):
+            z += 1
+            V1[p, q], V2[p, q], V3[p, q] = 1.0 + 1.0 / z, 1.0 - 1.0 / z, 1.0 + 0.1 * z
+    UIn = np.zeros((nElems, NIn + 1, NIn + 1, NIn + 1, nVar))
+    z = 1
+    for e in range(nElems):
+        for k in range(NIn + 1):
+            for j in range(NIn + 1):
+                for i in range(NIn + 1):
+                    for v in range(nVar):
+                        z += 1
+                        UIn[e, k, j, i, v] = 1.0 + 0.1 * z
+    ref = goldens["cb_UOut"]
+    got = mt.change_basis_volume(V1, UIn[:1])[0]
+    assert almost_equal_abs_or_rel(got, ref[2, 0], 0.5 * TOL)
+    xyz = np.einsum("Ii,kjic->kjIc", V1, UIn[0])
+    xyz = np.einsum("Jj,kjIc->kJIc", V2, xyz)
+    xyz = np.einsum("Kk,kJIc->KJIc", V3, xyz)
+    assert almost_equal_abs_or_rel(xyz, ref[3, 0], 0.5 * TOL)
+    got2d = mt.change_basis_surf(V1, UIn[:1, 0])[0]
+    assert almost_equal_abs_or_rel(got2d, goldens["cb_UOut2D"][0, 0], 0.5 * TOL)
+
+
+def test_oracle_filter_is_the_pinned_change_basis():
+    """filter.f90:272-306 applies ChangeBasis3D with FilterMat in place: the oracle's restatement equals the golden-pinned
+    host routine."""
+    import cases
+    from galaexi_b200.host import metrics as mt
+    from oracle.oracle import Oracle
+    c, U0 = cases.tgv_box_case(E=2, N=4, NGeo=2, deform=0.05, perturb=1e-2, FilterType="modal")
+    o = Oracle(c)
+    o.set_state(U0)
+    o.prec.lib().dgo_filter(o.h)
+    ref = mt.change_basis_volume(c.FilterMat, U0)
+    assert np.abs(o.array("U") - ref).max() <= 1e-13 * np.abs(ref).max()
+    o.close()

@@ -60,6 +60,12 @@ def main():
     for nt in ("G", "GL"):
         rr = fort_records(os.path.join(U, f"SurfInt_{nt}3D.bin"))
         g[f"si_{nt}"] = np.frombuffer(rr[0], "<f8").reshape(10, 10, 10)       # [k][j][i]
+    r = fort_records(os.path.join(U, "ChangeBasis.bin"))[0]
+    a = np.frombuffer(r, "<f8")
+    n3d = 3 * 6 * 6 * 6 * 6 * 4
+    g["cb_UOut"] = a[:n3d].reshape(4, 6, 6, 6, 6, 3)          # [slot][elem][k][j][i][var]  (ChangeBasis.f90:27-32)
+    g["cb_UOut2D"] = a[n3d:].reshape(3, 6, 6, 6, 3)           # [slot][elem][j][i][var]
+    assert a.size == n3d + 3 * 6 * 6 * 6 * 3
     rr = fort_records(os.path.join(U, "Vandermonde.bin"))
     g["vdm_raw"] = np.frombuffer(b"".join(rr), "<f8")
     np.savez_compressed(os.path.join(OUT, "unit_goldens.npz"), **g)

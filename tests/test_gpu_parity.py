@@ -541,3 +541,37 @@ def test_handle_reuse_and_two_solvers_on_one_device():
     assert np.array_equal(b.get_ut(), ub)
     a2.FinalizeDG()
     b.FinalizeDG()
+
+
+# ---- regressioncheck/checks/run_basic/freestream_3D: the build-option matrix on the check's own set-up ------------------------------
+_FS_MATRIX = [(N, nt, par, visc, split) for N in (2, 3, 5) for nt in ("GAUSS", "GAUSS-LOBATTO") for par in (False, True)
+              for visc in (0, 1) for split in (None, "PI") if not (split and nt == "GAUSS") and not (visc and not par)]
+
+
+@pytest.mark.parametrize("mesh", ["cartbox", "mortar"])
+def test_run_basic_freestream_matrix(mesh):
+    """run_basic/freestream_3D (builds.ini: N x node type x PARABOLIC x viscosity law x SPLIT_DG; parameter.ini: 2^3 box,
+    six Dirichlet BCs (type 2, RefState 1), RefState (1,1,1,1,1), mu0 = 1.8547e-5, R = 1, CFLscale 0.99, DFLscale 0.4,
+    tend = 1e-6; analyze.ini: L2 error <= 1e-1). Held here: 1e-12. Second variant: a mortar mesh with the same BCs
+    (hopr_mortar.ini of the check describes one; the mesh file itself does not ship)."""
+    from galaexi_b200.host import basis as bs, case as cs, equation as eq, mesh as ms
+    worst = 0.0
+    for N, nt, par, visc, split in _FS_MATRIX:
+        if mesh == "cartbox":
+            h = ms.make_box_mesh((2, 2, 2), x0=(0.0, 0.0, 0.0), x1=(1.0, 1.0, 1.0), bctype=[(2, 1)] * 6)
+            ubc = None
+        else:
+            h = cases.load_mesh("cart_mortar_002_mesh.npz")
+            ubc = {nm: (2, 1) for nm in ("BC_z-", "BC_y-", "BC_x+", "BC_y+", "BC_x-", "BC_z+")}
+        eos = eq.Eos(kappa=1.4, R=1.0, Pr=0.72, mu0=0.000018547 if par else 0.0, visc_law=visc)
+        c = cs.build_case(h, N, nt, split=split, riemann="RoeEntropyFix", parabolic=par, eos=eos, refstates=((1.0, 1.0, 1.0, 1.0, 1.0),),
+                          user_bcs=ubc, CFLScale=0.99, DFLScale=0.4)
+        U0 = eq.ini_refstate(c.geo["Elem_xGP"], c.RefStatePrim[0], eos)
+        s = _solver(c)
+        s.set_state(U0)
+        t, it = timeloop.advance(s, 0.0, 1e-6)
+        err = float(np.sqrt(np.mean((s.get_state() - U0) ** 2)))
+        s.FinalizeDG()
+        worst = max(worst, err)
+        assert err <= 1e-12, (N, nt, par, visc, split, err)
+    print(f"{mesh}: {len(_FS_MATRIX)} builds, worst L2 deviation from the free stream {worst:.2e}")

@@ -575,3 +575,28 @@ def test_run_basic_freestream_matrix(mesh):
         worst = max(worst, err)
         assert err <= 1e-12, (N, nt, par, visc, split, err)
     print(f"{mesh}: {len(_FS_MATRIX)} builds, worst L2 deviation from the free stream {worst:.2e}")
+
+
+def test_p_convergence_manufactured_navier_stokes():
+    """regressioncheck/checks/convtest/p_3D: fixed 2^3 mesh, N = 2, 3, ... (the check goes to 13; kernels exist up to 9),
+    IniExactFunc=4 + CalcSource, mu0=1e-3, CFLscale 0.25, tend shortened to 0.1. reggie's p-convergence criterion
+    (analyze_Convtest_p_rate / _percentage): the order of convergence must INCREASE from one degree to the next in at least
+    75 % of the steps -- i.e. spectral convergence. Asserted per variable on the density / momentum / energy L2 errors."""
+    from galaexi_b200.host import equation as eq
+    tEnd = 0.1
+    Ns = [2, 3, 4, 5, 6, 7, 8, 9]
+    errs = []
+    for N in Ns:
+        c, U0 = cases.manufactured_case("cart_periodic_002", N=N, CFLScale=0.25)
+        s = _solver(c)
+        s.set_state(U0)
+        t, _ = timeloop.advance(s, 0.0, tEnd)
+        errs.append(cases.l2_error(c, s.get_state(), t, exact=lambda x, tt: eq.exact_func_4(x, tt, cases.CONV_ADV)))
+        s.FinalizeDG()
+    errs = np.array(errs)
+    # EOC between successive degrees w.r.t. the number of points per direction (reggie: log(e_i/e_{i+1}) / log((N_{i+1}+1)/(N_i+1)))
+    eoc = np.log(errs[:-1] / errs[1:]) / np.log((np.array(Ns[1:]) + 1.0) / (np.array(Ns[:-1]) + 1.0))[:, None]
+    print("p-convergence: L2(rho) per N", errs[:, 0], "\\nEOC", eoc[:, 0])
+    inc = (eoc[1:] > eoc[:-1]).mean(axis=0)
+    assert np.all(errs[-1] < 1e-7 * errs[0] * 1e3) and np.all(errs[1:] < errs[:-1])
+    assert np.all(inc >= 0.5) and np.all(eoc[-1] > Ns[-2])     # spectral: the rate keeps growing and ends above N

@@ -600,3 +600,15 @@ def test_p_convergence_manufactured_navier_stokes():
     inc = (eoc[1:] > eoc[:-1]).mean(axis=0)
     assert np.all(errs[-1] < 1e-7 * errs[0] * 1e3) and np.all(errs[1:] < errs[:-1])
     assert np.all(inc >= 0.5) and np.all(eoc[-1] > Ns[-2])     # spectral: the rate keeps growing and ends above N
+
+
+# ---- every low-storage Runge-Kutta scheme of the LSERKW2 family (timedisc_vars.f90:137-470) ----------------------------------------
+@pytest.mark.parametrize("scheme", ["standardrk3-3", "carpenterrk4-5", "niegemannrk4-14", "toulorgerk4-8c", "toulorgerk3-7c",
+                                    "toulorgerk4-8f"])
+def test_all_lserkw2_schemes(scheme):
+    """TimeStepByLSERKW2 takes its coefficients from SetTimeDiscCoefs; the CFL/DFL scaling (timedisc_func.f90:480-550) and
+    the stage count differ per scheme. Two time steps vs the oracle, adaptive dt."""
+    c, U0 = cases.tgv_box_case(E=3, N=4, NGeo=2, deform=0.05, perturb=1e-3, timedisc=scheme)
+    assert c.timedisc.nRKStages == {"standardrk3-3": 3, "carpenterrk4-5": 5, "niegemannrk4-14": 14, "toulorgerk4-8c": 8,
+                                    "toulorgerk3-7c": 7, "toulorgerk4-8f": 8}[scheme]
+    _compare_rhs_and_steps(c, U0, nsteps=2)

@@ -523,6 +523,8 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
     P.U = h->U; P.Ut = h->Ut; P.Ut_tmp = h->Ut_tmp; P.gradU = h->gradU;
     P.gm = h->gm; P.gs = h->gs; P.Flux = h->Flux; P.errFlag = h->errFlag;
     P.lifting = c.lifting == 2 ? 2 : 1; P.etaBR2 = c.etaBR2; P.etaBR2_wall = c.etaBR2_wall;
+    P.liftWeak = (c.doWeakLifting && P.lifting != 2) ? 1 : 0;               // BR2 is always strong (lifting_vars.f90:77)
+    P.liftCons = (P.liftWeak || c.doConservativeLifting) ? 1 : 0;          // lifting_br1.t90:95
     P.MortarType = nullptr;
     P.xGP = nullptr; P.advVel1 = c.AdvVel[0]; P.iniExactFunc = 0;
     P.tcSource = 0; P.tcDpdx = 0.0; P.tcBulkVel = 0.0;

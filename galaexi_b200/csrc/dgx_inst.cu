@@ -79,7 +79,7 @@ struct L {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_lifting<n, NT>, n3, lifting_smem_bytes<n>());
             resident = sms * (per > 0 ? per : 1);
         }
-        if (P.lifting == 2 || P.MortarType) k_lifting<n, NT, 1><<<nb, n3, lifting_smem_bytes<n>(), s>>>(P, resident);
+        if (P.lifting == 2 || P.MortarType || P.liftWeak || P.liftCons) k_lifting<n, NT, 1><<<nb, n3, lifting_smem_bytes<n>(), s>>>(P, resident);
         else k_lifting<n, NT><<<nb, n3, lifting_smem_bytes<n>(), s>>>(P, resident);
     }
     static void umortar(double* am, double* as, int nvar, const MortarParams& mp, int nBig, cudaStream_t s) {

@@ -59,6 +59,7 @@ struct KParams {
     int* errFlag;
     // general lifting path (k_lifting<..., GEN=1>): BR2 (host FLEXI, dg/lifting/lifting_br2.t90) and/or big mortar faces
     int lifting;               // 1 BR1, 2 BR2
+    int liftWeak, liftCons;    // non-default lifting forms (lifting.f90:81-85): weak form; conservative volume form
     double etaBR2, etaBR2_wall;
     const int* MortarType;     // (2,nSides) or nullptr when the mesh has no mortars
     const double* FilterMat;   // device (0:N,0:N) Fortran layout, or nullptr (FilterType 0)
@@ -377,6 +378,7 @@ __global__ void __launch_bounds__(n* n* n, lifting_min_blocks<n>()) k_lifting(co
     constexpr int n2 = n * n, n3 = n2 * n;
     extern __shared__ __align__(16) double smem[];
     __shared__ int sMort[6];  // GEN: 0-based big mortar side of local side loc, or -1
+    __shared__ double sSig[6];  // GEN: sign of the face in the surface integral (weak form: -1 on slave faces, surfint.t90:640-644)
     __shared__ __align__(8) unsigned long long sBar;  // mbarrier of the metric / Jacobian bulk copy
     const bool br2 = GEN && P.lifting == 2;
     // even n: the element's metrics (9 n^3) and Jacobian (n^3) are fetched by TMA bulk copies issued at kernel entry into a
@@ -447,7 +449,7 @@ __global__ void __launch_bounds__(n* n* n, lifting_min_blocks<n>()) k_lifting(co
         const int b = s2v2<n>(P.S2V2, 1, p, q, flip, loc);
         if (GEN) {
             const bool big = P.MortarType && __ldg(&P.MortarType[2 * side]) > 0;
-            if (f == (loc - 1) * n2) sMort[loc - 1] = big ? side : -1;
+            if (f == (loc - 1) * n2) { sMort[loc - 1] = big ? side : -1; sSig[loc - 1] = (P.liftWeak && flip != 0) ? -1.0 : 1.0; }
             if (big) continue;  // flux comes projected from the small sides
         }
         const double* g = P.geo + (size_t)side * 10 * n2 + pq;
@@ -471,15 +473,20 @@ __global__ void __launch_bounds__(n* n* n, lifting_min_blocks<n>()) k_lifting(co
             } else {
                 Fl[0] = Pb[VEL1]; Fl[1] = Pb[VEL2]; Fl[2] = Pb[VEL3]; Fl[3] = Pm[TEMP];
             }
-            Fl[0] = (Fl[0] - Pm[VEL1]) * se; Fl[1] = (Fl[1] - Pm[VEL2]) * se;
-            Fl[2] = (Fl[2] - Pm[VEL3]) * se; Fl[3] = (Fl[3] - Pm[TEMP]) * se;
+            if (GEN && P.liftWeak) {  // weak form: the inner state is not subtracted (getboundaryflux.f90:1014)
+                Fl[0] *= se; Fl[1] *= se; Fl[2] *= se; Fl[3] *= se;
+            } else {
+                Fl[0] = (Fl[0] - Pm[VEL1]) * se; Fl[1] = (Fl[1] - Pm[VEL2]) * se;
+                Fl[2] = (Fl[2] - Pm[VEL3]) * se; Fl[3] = (Fl[3] - Pm[TEMP]) * se;
+            }
         } else {
             double Us[5], Ps[6];
 #pragma unroll
             for (int v = 0; v < 5; v++) Us[v] = P.Us[(size_t)side * 5 * n2 + v * n2 + pq];
             cons_to_prim(Ps, Us, eos);
-            Fl[0] = 0.5 * se * (-Pm[VEL1] + Ps[VEL1]); Fl[1] = 0.5 * se * (-Pm[VEL2] + Ps[VEL2]);
-            Fl[2] = 0.5 * se * (-Pm[VEL3] + Ps[VEL3]); Fl[3] = 0.5 * se * (-Pm[TEMP] + Ps[TEMP]);
+            const double sig = (GEN && P.liftWeak) ? 1.0 : -1.0;  // lifting_fillflux.t90:78
+            Fl[0] = 0.5 * se * (sig * Pm[VEL1] + Ps[VEL1]); Fl[1] = 0.5 * se * (sig * Pm[VEL2] + Ps[VEL2]);
+            Fl[2] = 0.5 * se * (sig * Pm[VEL3] + Ps[VEL3]); Fl[3] = 0.5 * se * (sig * Pm[TEMP] + Ps[TEMP]);
         }
         double* d = sF + (loc - 1) * 7 * n2 + (b * n + a);
         d[0 * n2] = Fl[0]; d[1 * n2] = Fl[1]; d[2 * n2] = Fl[2]; d[3 * n2] = Fl[3];
@@ -565,7 +572,8 @@ __global__ void __launch_bounds__(n* n* n, lifting_min_blocks<n>()) k_lifting(co
                 continue;
             }
             const double* s = sF + (loc - 1) * 7 * n2 + (b * n + a);
-            const double nx = s[4 * n2], ny = s[5 * n2], nz = s[6 * n2];
+            double nx = s[4 * n2], ny = s[5 * n2], nz = s[6 * n2];
+            if (GEN) { const double fsig = sSig[loc - 1]; nx *= fsig; ny *= fsig; nz *= fsig; }
 #pragma unroll
             for (int v = 0; v < 4; v++) {
                 const double F = s[v * n2];
@@ -581,18 +589,39 @@ __global__ void __launch_bounds__(n* n* n, lifting_min_blocks<n>()) k_lifting(co
             }
         }
         const double sJ = TMA ? stM[9 * n3 + t] : P.sJ[(size_t)e * n3 + t];
+        double V[12];
+        if (GEN && P.liftCons) {
+            // conservative volume form (lifting_volint.t90:125-200): the metrics sit inside the derivative; DMat = D_Hat_T
+            // for the weak form, D_T otherwise. Metrics of the line nodes come from the TMA staging area or from L2.
+            const double* __restrict__ Dm = P.liftWeak ? P.D_Hat_T : P.D_T;
+            const double* __restrict__ Mb = TMA ? stM : P.metrics + (size_t)e * 9 * n3;
 #pragma unroll
-        for (int d = 0; d < 3; d++) {
-            const double mf = M[(0 + d) * n3], mg = M[(3 + d) * n3], mh = M[(6 + d) * n3];
+            for (int x = 0; x < 12; x++) V[x] = 0.0;
+            for (int l = 0; l < n; l++) {
+                const double dx = Dm[l + n * i], dy = Dm[l + n * j], dz = Dm[l + n * k];
+                const int nxn = l + n * j + n2 * k, nyn = i + n * l + n2 * k, nzn = i + n * j + n2 * l;
+                const int ix = DMMA ? idx_m8(l, j, k) : Tile<n>::idx(l, j, k), iy = DMMA ? idx_m8(i, l, k) : Tile<n>::idx(i, l, k),
+                          iz = DMMA ? idx_m8(i, j, l) : Tile<n>::idx(i, j, l);
 #pragma unroll
-            for (int v = 0; v < 4; v++) {
-                if (br2) {
-                    // volume part times sJ (ApplyJacobianLifting, lifting_br2.t90:118-124); S holds the surface part
-                    G[d * 4 + v] = (mf * gxi[v] + mg * get[v] + mh * gze[v]) * sJ;
-                } else {
-                    G[d * 4 + v] = sJ * ((mf * gxi[v] + mg * get[v] + mh * gze[v]) + S[d * 4 + v]);
+                for (int d = 0; d < 3; d++) {
+                    const double mfx = Mb[(0 + d) * n3 + nxn], mgy = Mb[(3 + d) * n3 + nyn], mhz = Mb[(6 + d) * n3 + nzn];
+#pragma unroll
+                    for (int v = 0; v < 4; v++)
+                        V[d * 4 + v] += dx * (mfx * sT[v * n3 + ix]) + dz * (mhz * sT[v * n3 + iz]) + dy * (mgy * sT[v * n3 + iy]);
                 }
             }
+        } else {
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                const double mf = M[(0 + d) * n3], mg = M[(3 + d) * n3], mh = M[(6 + d) * n3];
+#pragma unroll
+                for (int v = 0; v < 4; v++) V[d * 4 + v] = mf * gxi[v] + mg * get[v] + mh * gze[v];
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < 12; x++) {
+            // BR2: volume part times sJ (ApplyJacobianLifting, lifting_br2.t90:118-124), S holds the surface part
+            G[x] = br2 ? V[x] * sJ : sJ * (V[x] + S[x]);
         }
         if (br2) {
             __syncthreads();  // all reads of sT done before it is overwritten by the gradient tile

@@ -154,8 +154,9 @@ __global__ void __launch_bounds__(n* n) k_mortar_liftflux(const KParams P, const
         cons_to_prim(Pm, Um, eos);
         cons_to_prim(Ps, Us, eos);
         const int iv = (v < 3) ? VEL1 + v : TEMP;
-        const double Fl = 0.5 * g[9 * n2] * (-Pm[iv] + Ps[iv]);
-        sIn[im][t] = Fl * g[d * n2];
+        const double Fl = 0.5 * g[9 * n2] * ((P.liftWeak ? 1.0 : -1.0) * Pm[iv] + Ps[iv]);
+        const double val = Fl * g[d * n2];
+        sIn[im][t] = (P.liftWeak && flip != 0) ? -val : val;  // Flux_MortarLifting(weak=doWeakLifting)
     }
     __syncthreads();
     P.gm[((size_t)sd * 12 + x) * n2 + t] = mortar_project<n>(type, sM1, sM2, sIn, sT2, p, q);

@@ -52,6 +52,7 @@ class DgxConfig(C.Structure):
                                   "lastMortarMPISide")]
         + [("MortarType", _ip), ("MortarInfo", _ip)] + [(k, _dp) for k in ("M_0_1", "M_0_2", "M_1_0", "M_2_0", "FilterMat")]
         + [("IniExactFunc", C.c_int), ("AdvVel", C.c_double * 3), ("Elem_xGP", _dp)]
+        + [("doWeakLifting", C.c_int), ("doConservativeLifting", C.c_int)]
     )
 
 
@@ -172,6 +173,7 @@ class DGSolver:
             setattr(c, nm, k[nm].ctypes.data_as(_ip))
         for nm in ("M_0_1", "M_0_2", "M_1_0", "M_2_0"):
             setattr(c, nm, k[nm].ctypes.data_as(_dp))
+        c.doWeakLifting, c.doConservativeLifting = int(case.doWeakLifting), int(case.doConservativeLifting)
         if case.IniExactFunc:
             k["Elem_xGP"] = f64(g["Elem_xGP"])
             c.Elem_xGP = k["Elem_xGP"].ctypes.data_as(_dp)

@@ -47,6 +47,8 @@ class Case:
     etaBR2_wall: float = -1.0   # -1: use etaBR2 (lifting.f90:89-91)
     mortar: dict = field(repr=False, default=None)   # M_0_1, M_0_2, M_1_0, M_2_0 (mortar/mortar.f90)
     FilterMat: np.ndarray = None                     # (N+1,N+1) or None: FilterType 0 (filter/filter.f90)
+    doWeakLifting: bool = False                      # lifting.f90:81-85, 139-141 (BR2 is always strong)
+    doConservativeLifting: bool = False
     IniExactFunc: int = 0                            # selects the source term of CalcSource (exactfunc.f90:665-926): 4 or 0
     AdvVel: tuple = (0.0, 0.0, 0.0)
 
@@ -66,7 +68,8 @@ def build_case(hopr: dict, N: int, node_type: str = bs.NODETYPE_GL, split: str |
                DFLScale: float = 0.9, useCurveds: bool = True, crossProductMetrics: bool = False,
                lifting: str = "br1", etaBR2: float = 2.0, etaBR2_wall: float = -1.0,
                FilterType: int | str = 0, NFilter: int | None = None, HestFilterParam=(36.0, 12.0, 1.0),
-               IniExactFunc: int = 0, AdvVel=(0.0, 0.0, 0.0)) -> Case:
+               IniExactFunc: int = 0, AdvVel=(0.0, 0.0, 0.0), doWeakLifting: bool = False,
+               doConservativeLifting: bool = False) -> Case:
     eos = eos or eq.Eos()
     node_type = node_type.upper()
     split_id = SPLIT_IDS[split.upper() if isinstance(split, str) else split]
@@ -93,4 +96,5 @@ def build_case(hopr: dict, N: int, node_type: str = bs.NODETYPE_GL, split: str |
     return Case(N, node_type, basis, mesh, geo, maps, eos, refprim, bcs, tdisc, split_id, riem_id, bool(parabolic), hopr,
                 lift_id, float(etaBR2), float(etaBR2_wall), mo.init_mortar(N, node_type),
                 None if str(FilterType).lower() in ("0", "none") else fl.filter_matrix(N, node_type, FilterType, NFilter, HestFilterParam),
+                bool(doWeakLifting), bool(doConservativeLifting) and not bool(doWeakLifting),
                 int(IniExactFunc), tuple(float(v) for v in AdvVel))

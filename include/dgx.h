@@ -100,6 +100,9 @@ typedef struct dgx_config {
     int IniExactFunc;
     double AdvVel[3];
     const double *Elem_xGP;
+    /* non-default lifting forms (ini keys doWeakLifting, doConservativeLifting; lifting.f90:81-85, 139-141): weak form
+     * (ignored by BR2, which is always strong) and conservative volume form (implied by the weak form) */
+    int doWeakLifting, doConservativeLifting;
 } dgx_config;
 
 int dgx_create(dgx_handle **h, const dgx_config *cfg);

@@ -39,6 +39,7 @@ TYPE, BIND(C), PUBLIC :: dgx_config
   INTEGER(C_INT) :: IniExactFunc ! source term selection (exactfunc.f90:665-926)
   REAL(C_DOUBLE) :: AdvVel(3)
   TYPE(C_PTR)    :: Elem_xGP
+  INTEGER(C_INT) :: doWeakLifting, doConservativeLifting   ! lifting.f90:139-141
 END TYPE dgx_config
 
 TYPE(C_PTR), PUBLIC, SAVE :: dgx = C_NULL_PTR   !< the library handle (one per rank)

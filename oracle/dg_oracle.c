@@ -95,6 +95,9 @@ typedef struct {
     /* channel testcase forcing (testcase/channel/testcase.f90:277-296 TestcaseSource): active if tcSource != 0 */
     int tcSource;
     double dpdx, BulkVel;
+    /* non-default lifting forms (lifting.f90:81-85, 139-141): weak form (surface flux 1/2 (U_m + U_s), D_Hat_T, signed
+     * surface integral) and conservative volume form (metrics inside the derivative); BR2 is always strong */
+    int doWeakLifting, doConservativeLifting;
 } dgo_config;
 
 typedef struct {
@@ -877,6 +880,10 @@ static void flux_mortar_all(const dgo *s, int nVar, double *Fm, const double *Fs
     flux_mortar(s, nVar, Fm, Fs, s->c.firstMortarMPISide, s->c.lastMortarMPISide, weak);
 }
 
+/* lifting.f90:139-141: BR2 is always strong; the conservative form is only read for strong lifting */
+static inline int lift_weak(const dgo_config *c) { return c->doWeakLifting && c->lifting != 2; }
+static inline int lift_cons(const dgo_config *c) { return lift_weak(c) || c->doConservativeLifting; }
+
 /* ------------------------------------------------------------------------------------------------ */
 /* lifting: dg/lifting/lifting_br1.t90:47-167 (strong form, non-conservative volume integral) */
 static void lifting_br1_fillflux(dgo *s)
@@ -902,17 +909,18 @@ static void lifting_br1_fillflux(dgo *s)
             } else {
                 Fl[LIFT_DENS] = Pm[DENS]; Fl[LIFT_VEL1] = Pb[VEL1]; Fl[LIFT_VEL2] = Pb[VEL2]; Fl[LIFT_VEL3] = Pb[VEL3]; Fl[LIFT_TEMP] = Pm[TEMP];
             }
-            for (int v = 0; v < NL; v++) Fl[v] = Fl[v] - Pm[PRIM_LIFT[v]];
+            if (!lift_weak(c)) for (int v = 0; v < NL; v++) Fl[v] = Fl[v] - Pm[PRIM_LIFT[v]]; /* getboundaryflux.f90:1014 */
             double se = c->SurfElem[p + n * (q + (size_t)n * sd)];
             for (int v = 0; v < NL; v++) Flux[IDX_FACE(s, NL, v, p, q, sd)] = Fl[v] * se;
         }
-    /* lifting_fillflux.t90:39-93 Lifting_FillFlux: inner + MPI MINE sides, sig=-1 (strong) */
+    /* lifting_fillflux.t90:39-93 Lifting_FillFlux: inner + MPI MINE sides, sig = -1 (strong) or +1 (weak) */
+    const double sig = lift_weak(c) ? 1. : -1.;
 #pragma omp parallel for schedule(static)
     for (int sd = c->firstInnerSide - 1; sd < c->lastMPISide_MINE; sd++)
         for (int q = 0; q < n; q++) for (int p = 0; p < n; p++) {
             double se = c->SurfElem[p + n * (q + (size_t)n * sd)];
             for (int v = 0; v < NL; v++)
-                Flux[IDX_FACE(s, NL, v, p, q, sd)] = 0.5 * se * (-1. * s->UPrim_master[IDX_FACE(s, NP, PRIM_LIFT[v], p, q, sd)]
+                Flux[IDX_FACE(s, NL, v, p, q, sd)] = 0.5 * se * (sig * s->UPrim_master[IDX_FACE(s, NP, PRIM_LIFT[v], p, q, sd)]
                                                                  + s->UPrim_slave[IDX_FACE(s, NP, PRIM_LIFT[v], p, q, sd)]);
         }
 }
@@ -938,14 +946,15 @@ static void lifting_br1_finish(dgo *s)
         }
     /* big mortar sides: project the small-side lifting fluxes (strong form: no sign change), as the host code does
      * with Flux_MortarLifting on FluxX/Y/Z (lifting_br2.t90:102-106) */
-    flux_mortar_all(s, NL, s->gradUx_master, s->gradUx_master, 0);
-    flux_mortar_all(s, NL, s->gradUy_master, s->gradUy_master, 0);
-    flux_mortar_all(s, NL, s->gradUz_master, s->gradUz_master, 0);
+    const int weak = lift_weak(c);
+    flux_mortar_all(s, NL, s->gradUx_master, s->gradUx_master, weak);
+    flux_mortar_all(s, NL, s->gradUy_master, s->gradUy_master, weak);
+    flux_mortar_all(s, NL, s->gradUz_master, s->gradUz_master, weak);
     lifting_volint(s);
-    /* lifting_br1.t90:118-124 SurfIntLifting x3 (single flux, strong, with sJ) */
-    surf_int(s, NL, s->gradUx_master, NULL, s->gradUx, 1, 0, 1);
-    surf_int(s, NL, s->gradUy_master, NULL, s->gradUy, 1, 0, 1);
-    surf_int(s, NL, s->gradUz_master, NULL, s->gradUz, 1, 0, 1);
+    /* lifting_br1.t90:118-124 SurfIntLifting x3 (single flux, strong or weak sign, with sJ) */
+    surf_int(s, NL, s->gradUx_master, NULL, s->gradUx, 1, weak, 1);
+    surf_int(s, NL, s->gradUy_master, NULL, s->gradUy, 1, weak, 1);
+    surf_int(s, NL, s->gradUz_master, NULL, s->gradUz, 1, weak, 1);
     /* lifting_br1.t90:152-156 ProlongToFaceLifting x3 */
     prolong_to_face(s, NL, s->gradUx, s->gradUx_master, s->gradUx_slave);
     prolong_to_face(s, NL, s->gradUy, s->gradUy_master, s->gradUy_slave);
@@ -956,11 +965,36 @@ static void lifting_br1_finish(dgo *s)
     u_mortar_all(s, NL, s->gradUz_master, s->gradUz_slave);
 }
 
+/* lifting_volint.t90:125-200 Lifting_VolInt_Conservative (x3 directions): DMat = D_Hat_T (weak) or D_T (strong) */
+static void lifting_volint_conservative(dgo *s)
+{
+    const dgo_config *c = &s->c;
+    const int n = s->n;
+    const double *DMat = lift_weak(c) ? c->D_Hat_T : c->D_T;
+    double *grad[3] = {s->gradUx, s->gradUy, s->gradUz};
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < c->nElems; e++)
+        for (int dir = 0; dir < 3; dir++)
+            for (int k = 0; k < n; k++) for (int j = 0; j < n; j++) for (int i = 0; i < n; i++)
+                for (int v = 0; v < NL; v++) {
+                    double a = 0.;
+                    for (int l = 0; l < n; l++) {
+                        double f = c->Metrics_fTilde[IDX_VOL(s, 3, dir, l, j, k, e)] * s->UPrim[IDX_VOL(s, NP, PRIM_LIFT[v], l, j, k, e)];
+                        double h = c->Metrics_hTilde[IDX_VOL(s, 3, dir, i, j, l, e)] * s->UPrim[IDX_VOL(s, NP, PRIM_LIFT[v], i, j, l, e)];
+                        double g = c->Metrics_gTilde[IDX_VOL(s, 3, dir, i, l, k, e)] * s->UPrim[IDX_VOL(s, NP, PRIM_LIFT[v], i, l, k, e)];
+                        if (l == 0) a = DMat[0 + n * i] * f + DMat[0 + n * k] * h + DMat[0 + n * j] * g;
+                        else a = a + DMat[l + n * i] * f + DMat[l + n * k] * h + DMat[l + n * j] * g;
+                    }
+                    grad[dir][IDX_VOL(s, NL, v, i, j, k, e)] = a;
+                }
+}
+
 /* lifting_volint.t90:262-328 Lifting_VolInt_Nonconservative_GPU_Kernel */
 static void lifting_volint(dgo *s)
 {
     const dgo_config *c = &s->c;
     const int n = s->n;
+    if (lift_cons(c)) { lifting_volint_conservative(s); return; }
 #pragma omp parallel for schedule(static)
     for (int e = 0; e < c->nElems; e++)
         for (int k = 0; k < n; k++) for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) {

@@ -43,7 +43,8 @@ class _Prec:
                        [(k, _ip) for k in ("MortarType", "MortarInfo", "FS2M", "SideToElem")] + \
                        [(k, rp) for k in ("M_0_1", "M_0_2", "M_1_0", "M_2_0", "FilterMat")] + \
                        [("iniExactFunc", C.c_int), ("AdvVel", self.real * 3), ("Elem_xGP", rp)] + \
-                       [("tcSource", C.c_int), ("dpdx", self.real), ("BulkVel", self.real)]
+                       [("tcSource", C.c_int), ("dpdx", self.real), ("BulkVel", self.real)] + \
+                       [("doWeakLifting", C.c_int), ("doConservativeLifting", C.c_int)]
         self.Config = Config
         self._lib = None
 
@@ -165,6 +166,8 @@ class Oracle:
             c.iniExactFunc = int(case.IniExactFunc)
             for k_, v_ in enumerate(case.AdvVel):
                 c.AdvVel[k_] = v_
+        c.doWeakLifting = int(getattr(case, "doWeakLifting", False))
+        c.doConservativeLifting = int(getattr(case, "doConservativeLifting", False))
         FilterMat = getattr(case, "FilterMat", None)
         if FilterMat is not None:
             self._keep["FilterMat"] = f64(np.asarray(FilterMat).T)   # Fortran FilterMat(i,l) at [i + n*l]

@@ -612,3 +612,30 @@ def test_all_lserkw2_schemes(scheme):
     assert c.timedisc.nRKStages == {"standardrk3-3": 3, "carpenterrk4-5": 5, "niegemannrk4-14": 14, "toulorgerk4-8c": 8,
                                     "toulorgerk3-7c": 7, "toulorgerk4-8f": 8}[scheme]
     _compare_rhs_and_steps(c, U0, nsteps=2)
+
+
+# ---- non-default lifting forms (lifting.f90:81-85) ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,kw", [
+    ("tgv_weak_gl", dict(E=3, N=4, NGeo=2, deform=0.05, perturb=1e-3, doWeakLifting=True)),
+    ("tgv_cons_gl_n7", dict(E=2, N=7, NGeo=2, deform=0.05, perturb=1e-3, doConservativeLifting=True)),
+    ("tgv_weak_gauss", dict(E=3, N=3, NGeo=2, deform=0.05, perturb=1e-3, node_type="GAUSS", split=None, riemann="Roe", doWeakLifting=True)),
+    ("tgv_cons_br2", dict(E=3, N=5, NGeo=2, deform=0.05, perturb=1e-3, doConservativeLifting=True, lifting="br2")),
+    ("cavity_weak", dict(doWeakLifting=True)),
+    ("channel_cons", dict(E=3, N=4, doConservativeLifting=True)),
+    ("mortar_weak", dict(mesh="004", N=3, doWeakLifting=True)),
+    ("mortar_cons_gl", dict(mesh="002", N=4, node_type="GAUSS-LOBATTO", split="PI", riemann="RoeEntropyFix", doConservativeLifting=True)),
+])
+def test_weak_and_conservative_lifting(name, kw):
+    kw = dict(kw)
+    if name.startswith("tgv"):
+        c, U0 = cases.tgv_box_case(**kw)
+    elif name.startswith("cavity"):
+        c, U0 = cases.cavity_case(**kw)
+        x = c.geo["Elem_xGP"]
+        U0 = U0 * (1.0 + 0.01 * np.sin(5.0 * x[..., 0] + 1.0) * np.cos(3.0 * x[..., 1]) * np.sin(4.0 * x[..., 2] + 0.5))[..., None]
+    elif name.startswith("channel"):
+        c, U0 = cases.channel_case(**kw)
+    else:
+        c, U0 = cases.mortar_case(kw.pop("mesh"), **kw)
+    assert c.doWeakLifting or c.doConservativeLifting
+    _compare_rhs_and_steps(c, U0, nsteps=2)

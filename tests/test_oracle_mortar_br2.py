@@ -159,3 +159,57 @@ def test_br2_trace_is_local_gradient_plus_eta_times_face_lift():
         tr[eta] = o.array("gradUy_master").copy()
         o.close()
     assert np.allclose(tr[3.0] - tr[1.0], 2.0 * (tr[2.0] - tr[1.0]), rtol=0, atol=1e-12 * np.abs(tr[1.0]).max())
+
+
+# ---- non-default lifting forms (lifting.f90:81-85): doWeakLifting, doConservativeLifting -------------------------------------------
+@pytest.mark.parametrize("node_type", [bs.NODETYPE_G, bs.NODETYPE_GL])
+def test_lifting_forms_agree_where_they_must(node_type):
+    """On a Cartesian mesh (constant metrics) the conservative and the non-conservative volume forms are identical, and the
+    weak form equals the strong form by the summation-by-parts property of the operators -- for Gauss-Lobatto nodes for all
+    lifted variables; for Gauss nodes for the variables whose face trace commutes with the conversion to primitive
+    variables (velocities at constant density; the temperature does not: prim(trace(U)) != trace(prim(U))). Curved mesh:
+    every form lifts a constant state to zero gradients (metric identities)."""
+    kw = dict(E=2, N=3, node_type=node_type, split=None, riemann="Roe")
+
+    def run(U, **var):
+        c, _ = cases.tgv_box_case(**kw, **var)
+        o = Oracle(c)
+        o.set_state(U)
+        o.time_derivative(0.0)
+        g = [o.array(nm).copy() for nm in ("gradUx", "gradUy", "gradUz")]
+        o.close()
+        return g
+    c, U0 = cases.tgv_box_case(perturb=1e-2, **kw)
+    U0 = U0.copy()
+    U0[..., 1:4] /= U0[..., 0:1]
+    U0[..., 0] = 1.0
+    ref = run(U0)
+    sc = max(np.abs(x).max() for x in ref)
+    cons = run(U0, doConservativeLifting=True)
+    weak = run(U0, doWeakLifting=True)
+    assert max(np.abs(a - b).max() for a, b in zip(ref, cons)) <= 1e-12 * sc
+    vel = slice(1, 4) if node_type == bs.NODETYPE_G else slice(1, 5)
+    assert max(np.abs(a[..., vel] - b[..., vel]).max() for a, b in zip(ref, weak)) <= 1e-12 * sc
+    for var in (dict(doWeakLifting=True), dict(doConservativeLifting=True)):
+        cc, _ = cases.tgv_box_case(E=2, N=3, NGeo=2, deform=0.05, node_type=node_type, split=None, riemann="Roe", **var)
+        o = Oracle(cc)
+        o.set_state(eq.ini_refstate(cc.geo["Elem_xGP"], cc.RefStatePrim[0], cc.eos))
+        o.time_derivative(0.0)
+        assert max(np.abs(o.array(nm)).max() for nm in ("gradUx", "gradUy", "gradUz")) <= 1e-9
+        o.close()
+
+
+def test_weak_lifting_on_mortar_mesh_matches_strong_for_commuting_variables():
+    res = {}
+    for weak in (False, True):
+        c, U0 = cases.mortar_case("002", N=3, doWeakLifting=weak)
+        U0 = U0.copy()
+        U0[..., 1:4] /= U0[..., 0:1]
+        U0[..., 0] = 1.0
+        o = Oracle(c)
+        o.set_state(U0)
+        o.time_derivative(0.0)
+        res[weak] = [o.array(nm)[..., 1:4].copy() for nm in ("gradUx", "gradUy", "gradUz")]
+        o.close()
+    sc = max(np.abs(x).max() for x in res[False])
+    assert max(np.abs(a - b).max() for a, b in zip(res[False], res[True])) <= 1e-11 * sc

@@ -272,7 +272,7 @@ int rhs(dgx_handle* h, int mode, double t, double mRKA, double b_dt, StageTimes*
     P.UsNext = h->Uf[h->cur ^ 1][1];
     const bool multi = c.nRanks > 1 && !h->NbProc.empty();
     // CalcSource (dg.f90:418): the volume kernels store Ut (MODE 0), k_source_rk adds the source and does the stage update
-    const bool src = P.iniExactFunc == 4 || P.tcSource;
+    const bool src = P.iniExactFunc == 4 || P.tcSource || P.spMat;
     const int vmode = src ? 0 : mode;
     auto mark = [&](void) { if (st) cudaEventRecord(st->ev[st->nev++], h->s); };
     mark();
@@ -528,6 +528,17 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
     P.MortarType = nullptr;
     P.xGP = nullptr; P.advVel1 = c.AdvVel[0]; P.iniExactFunc = 0;
     P.tcSource = 0; P.tcDpdx = 0.0; P.tcBulkVel = 0.0;
+    P.spMat = nullptr; P.spBase = nullptr;
+    if (c.SpongeMat) {
+        if (!c.SpBaseFlow) return fail(h, "SpongeMat given without SpBaseFlow");
+        double *sm, *sb;
+        if (upload(h, &sm, c.SpongeMat, nDOF) || dalloc(h, &sb, 5 * nDOF)) return 1;
+        // base flow: reference layout -> tiles, through the staging buffer
+        CK(cudaMemcpyAsync(h->stage, c.SpBaseFlow, 5 * nDOF * sizeof(double), cudaMemcpyHostToDevice, h->s));
+        if (nDOF) { k_aos_to_soa<5><<<blocks_for(5 * nDOF, 256), 256, 0, h->s>>>(h->stage, sb, n3, 5 * nDOF); if (check_launch(h, "k_aos_to_soa(base flow)")) return 1; }
+        CK(cudaStreamSynchronize(h->s));
+        P.spMat = sm; P.spBase = sb;
+    }
     if (c.IniExactFunc == 4) {
         if (!c.Elem_xGP) return fail(h, "IniExactFunc=4 (CalcSource) needs Elem_xGP");
         // reference layout (3,n^3,nElems) -> [elem][3][n^3]
@@ -612,6 +623,7 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
     h->cfg.MortarType = h->cfg.MortarInfo = nullptr;
     h->cfg.FilterMat = nullptr;
     h->cfg.Elem_xGP = nullptr;
+    h->cfg.SpongeMat = h->cfg.SpBaseFlow = nullptr;
     h->cfg.M_0_1 = h->cfg.M_0_2 = h->cfg.M_1_0 = h->cfg.M_2_0 = nullptr;
     return 0;
 }
@@ -699,6 +711,18 @@ int dgx_calc_timestep(dgx_handle* h, double* dt, int* errType) {
     if (errType) *errType = flag ? 2 : 0;
     if (dt) *dt = h->hPinned[0] < h->hPinned[1] ? h->hPinned[0] : h->hPinned[1];
     return 0;
+}
+
+int dgx_temp_filter_time_deriv(dgx_handle* h, double dt, double tempFilterWidth) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->P.spBase) return fail(h, "dgx_temp_filter_time_deriv: no sponge base flow (SpongeMat / SpBaseFlow not set)");
+    const size_t tot = 5 * h->nDOF();
+    if (tot) { k_pruett<<<blocks_for(tot, 256), 256, 0, h->s>>>(h->U, h->P.spBase, dt / tempFilterWidth, tot); if (check_launch(h, "k_pruett")) return 1; }
+    return 0;
+}
+int dgx_get_baseflow(dgx_handle* h, double* SpBaseFlow) {
+    if (!h->P.spBase) return fail(h, "dgx_get_baseflow: no sponge base flow");
+    return get_vol(h, h->P.spBase, SpBaseFlow, 5, 0, 5);
 }
 
 int dgx_set_channel_forcing(dgx_handle* h, int on, double dpdx, double BulkVel) {

@@ -67,6 +67,9 @@ struct KParams {
     const double* xGP;
     double advVel1;
     int iniExactFunc;
+    // sponge (sponge/sponge.f90:529-588): SpongeMat [elem][n^3] (= damping sigma / sJ) and base flow [elem][5][n^3], or nullptr
+    const double* spMat;
+    double* spBase;
     // channel forcing (testcase/channel/testcase.f90:277-296 TestcaseSource)
     int tcSource;
     double tcDpdx, tcBulkVel;
@@ -316,6 +319,12 @@ __global__ void __launch_bounds__(n* n* n) k_source_rk(const KParams P, double t
         src[4] = tmp[3] * cosX + tmp[4] * sin2 + tmp[5] * sinX;
     }
     if (P.tcSource) { src[1] -= P.tcDpdx; src[4] -= P.tcDpdx * P.tcBulkVel; }
+    if (P.spMat) {
+        // Ut = Ut - SpongeMat (U - SpBaseFlow) before the Jacobian (sponge.f90:574-579): times sJ here
+        const double sm = P.spMat[(size_t)e * n3 + tt] * P.sJ[(size_t)e * n3 + tt];
+#pragma unroll
+        for (int v = 0; v < 5; v++) src[v] -= sm * (P.U[(size_t)e * 5 * n3 + v * n3 + tt] - P.spBase[(size_t)e * 5 * n3 + v * n3 + tt]);
+    }
     double* Utg = P.Ut + (size_t)e * 5 * n3 + tt;
 #pragma unroll
     for (int v = 0; v < 5; v++) {
@@ -1115,6 +1124,11 @@ __global__ void __launch_bounds__(timestep_threads<n>()) k_bulkvel(const KParams
         for (int w = 1; w < timestep_threads<n>() / 32; w++) s += red[w];
         partials[e] = s;
     }
+}
+// sponge/pruettdamping.f90:69-92 TempFilterTimeDeriv: SpBaseFlow += (U - SpBaseFlow) dt / tempFilterWidth
+static __global__ void k_pruett(const double* __restrict__ U, double* __restrict__ base, double fac, size_t total) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < total) base[gid] = base[gid] + (U[gid] - base[gid]) * fac;
 }
 static __global__ void __launch_bounds__(256) k_sum_partials(const double* __restrict__ partials, int count, double* __restrict__ out) {
     __shared__ double red[256];

@@ -28,7 +28,7 @@ _ip = C.POINTER(C.c_int)
 
 EXPORTS = ("dgx_create", "dgx_destroy", "dgx_last_error", "dgx_set_state", "dgx_get_state", "dgx_get_ut",
            "dgx_get_gradients", "dgx_time_derivative", "dgx_rk_stage", "dgx_rk_step", "dgx_calc_timestep",
-           "dgx_analyze_tgv", "dgx_calc_bulk_velocity", "dgx_set_channel_forcing", "dgx_sync", "dgx_run_steps", "dgx_profile_stage", "dgx_nccl_unique_id", "dgx_launch_count", "dgx_sizeof_config", "dgx_halo_plan")
+           "dgx_analyze_tgv", "dgx_calc_bulk_velocity", "dgx_set_channel_forcing", "dgx_temp_filter_time_deriv", "dgx_get_baseflow", "dgx_sync", "dgx_run_steps", "dgx_profile_stage", "dgx_nccl_unique_id", "dgx_launch_count", "dgx_sizeof_config", "dgx_halo_plan")
 
 
 class DgxConfig(C.Structure):
@@ -53,6 +53,7 @@ class DgxConfig(C.Structure):
         + [("MortarType", _ip), ("MortarInfo", _ip)] + [(k, _dp) for k in ("M_0_1", "M_0_2", "M_1_0", "M_2_0", "FilterMat")]
         + [("IniExactFunc", C.c_int), ("AdvVel", C.c_double * 3), ("Elem_xGP", _dp)]
         + [("doWeakLifting", C.c_int), ("doConservativeLifting", C.c_int)]
+        + [("SpongeMat", _dp), ("SpBaseFlow", _dp)]
     )
 
 
@@ -82,6 +83,8 @@ def load_library():
     lib.dgx_rk_step.argtypes = [h, C.c_double, C.c_double]
     lib.dgx_calc_timestep.argtypes = [h, _dp, _ip]
     lib.dgx_analyze_tgv.argtypes = [h, C.c_int, _dp, _dp, C.c_double, C.c_double, _dp]
+    lib.dgx_temp_filter_time_deriv.argtypes = [h, C.c_double, C.c_double]
+    lib.dgx_get_baseflow.argtypes = [h, _dp]
     lib.dgx_calc_bulk_velocity.argtypes = [h, _dp, C.c_double, _dp]
     lib.dgx_set_channel_forcing.argtypes = [h, C.c_int, C.c_double, C.c_double]
     lib.dgx_sync.argtypes = [h]
@@ -174,6 +177,9 @@ class DGSolver:
         for nm in ("M_0_1", "M_0_2", "M_1_0", "M_2_0"):
             setattr(c, nm, k[nm].ctypes.data_as(_dp))
         c.doWeakLifting, c.doConservativeLifting = int(case.doWeakLifting), int(case.doConservativeLifting)
+        if case.SpongeMat is not None:
+            k["SpongeMat"], k["SpBaseFlow"] = f64(case.SpongeMat), f64(case.SpBaseFlow)
+            c.SpongeMat, c.SpBaseFlow = k["SpongeMat"].ctypes.data_as(_dp), k["SpBaseFlow"].ctypes.data_as(_dp)
         if case.IniExactFunc:
             k["Elem_xGP"] = f64(g["Elem_xGP"])
             c.Elem_xGP = k["Elem_xGP"].ctypes.data_as(_dp)
@@ -262,6 +268,15 @@ class DGSolver:
         self._ck(self.lib.dgx_analyze_tgv(self.h, NA, Vt.ctypes.data_as(_dp), wA.ctypes.data_as(_dp),
                                           float(self._an_vol if Vol is None else Vol), float(rho0), out.ctypes.data_as(_dp)))
         return out
+
+    def TempFilterTimeDeriv(self, dt: float, tempFilterWidth: float):
+        """Pruett temporal filter of the sponge base flow (sponge/pruettdamping.f90:69-92), once per time step."""
+        self._ck(self.lib.dgx_temp_filter_time_deriv(self.h, float(dt), float(tempFilterWidth)))
+
+    def get_baseflow(self) -> np.ndarray:
+        B = np.empty(self.shape_U)
+        self._ck(self.lib.dgx_get_baseflow(self.h, B.ctypes.data_as(_dp)))
+        return B
 
     def CalcForcing(self, Vol: float | None = None) -> float:
         """CalcForcing of the channel testcase (testcase/channel/testcase.f90:241-271): the bulk velocity."""

@@ -47,6 +47,8 @@ class Case:
     etaBR2_wall: float = -1.0   # -1: use etaBR2 (lifting.f90:89-91)
     mortar: dict = field(repr=False, default=None)   # M_0_1, M_0_2, M_1_0, M_2_0 (mortar/mortar.f90)
     FilterMat: np.ndarray = None                     # (N+1,N+1) or None: FilterType 0 (filter/filter.f90)
+    SpongeMat: np.ndarray = None                     # [e,k,j,i] damping*sigma/sJ (sponge.f90:259-457) or None
+    SpBaseFlow: np.ndarray = None                    # [e,k,j,i,5] initial sponge base flow
     doWeakLifting: bool = False                      # lifting.f90:81-85, 139-141 (BR2 is always strong)
     doConservativeLifting: bool = False
     IniExactFunc: int = 0                            # selects the source term of CalcSource (exactfunc.f90:665-926): 4 or 0
@@ -96,5 +98,5 @@ def build_case(hopr: dict, N: int, node_type: str = bs.NODETYPE_GL, split: str |
     return Case(N, node_type, basis, mesh, geo, maps, eos, refprim, bcs, tdisc, split_id, riem_id, bool(parabolic), hopr,
                 lift_id, float(etaBR2), float(etaBR2_wall), mo.init_mortar(N, node_type),
                 None if str(FilterType).lower() in ("0", "none") else fl.filter_matrix(N, node_type, FilterType, NFilter, HestFilterParam),
-                bool(doWeakLifting), bool(doConservativeLifting) and not bool(doWeakLifting),
+                None, None, bool(doWeakLifting), bool(doConservativeLifting) and not bool(doWeakLifting),
                 int(IniExactFunc), tuple(float(v) for v in AdvVel))

@@ -10,12 +10,13 @@ from __future__ import annotations
 
 
 def advance(op, t0: float, tEnd: float, maxIter: int | None = None, fixed_dt: float | None = None,
-            nCalcTimeStepMax: int = 1):
+            nCalcTimeStepMax: int = 1, after_step=None):
     """Advance ``op`` from t0 to tEnd; returns (t, nTimeSteps).
 
     nCalcTimeStepMax (ini key NCalcTimeStepMax, default 1 = every step): the reference re-evaluates dt only every
     n-th step, n = min(floor(|log10((dt_old/dt - 1)^2 * 100 + eps)|), nCalcTimeStepMax), i.e. less often the slower dt
-    changes (timedisc_func.f90:265-280); the end-time clipping is applied when dt is evaluated, as in the reference."""
+    changes (timedisc_func.f90:265-280); the end-time clipping is applied when dt is evaluated, as in the reference.
+    after_step(t_new, dt): the per-step part of AnalyzeTimeStep (timedisc_func.f90:351-357), e.g. the Pruett filter."""
     import math
     import sys
     t = t0
@@ -31,6 +32,8 @@ def advance(op, t0: float, tEnd: float, maxIter: int | None = None, fixed_dt: fl
             op.rk_step(t, dt_keep)
             t += dt_keep
             it += 1
+            if after_step is not None:
+                after_step(t, dt_keep)
             continue
         dt_min = fixed_dt if fixed_dt is not None else op.calc_timestep()[0]
         if nCalcTimeStepMax > 1:
@@ -47,6 +50,8 @@ def advance(op, t0: float, tEnd: float, maxIter: int | None = None, fixed_dt: fl
         op.rk_step(t, dt)
         t += dt
         it += 1
+        if after_step is not None:
+            after_step(t, dt)
         if finalize:
             t = tEnd
             break

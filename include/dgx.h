@@ -103,6 +103,10 @@ typedef struct dgx_config {
     /* non-default lifting forms (ini keys doWeakLifting, doConservativeLifting; lifting.f90:81-85, 139-141): weak form
      * (ignored by BR2, which is always strong) and conservative volume form (implied by the weak form) */
     int doWeakLifting, doConservativeLifting;
+    /* sponge zone (sponge/sponge.f90; step 13 of the RHS, dg.f90:419): SpongeMat(0:N,0:N,0:N,nElems) = damping sigma / sJ as
+     * CalcSpongeRamp leaves it (:449-454), expanded to all elements (zero outside the SpongeMap), and the initial base flow
+     * SpBaseFlow(PP_nVar,0:N,0:N,0:N,nElems) (InitSponge :203-243). NULL: no sponge. */
+    const double *SpongeMat, *SpBaseFlow;
 } dgx_config;
 
 int dgx_create(dgx_handle **h, const dgx_config *cfg);
@@ -140,6 +144,12 @@ int dgx_analyze_tgv(dgx_handle *h, int NAnalyze, const double *Vdm_GaussN_NAnaly
  * Ut(MOM1) -= dpdx / sJ, Ut(ENER) -= dpdx / sJ * BulkVel before the Jacobian is applied. */
 int dgx_calc_bulk_velocity(dgx_handle *h, const double *wGP, double Vol, double *BulkVel);
 int dgx_set_channel_forcing(dgx_handle *h, int on, double dpdx, double BulkVel);
+
+/* TempFilterTimeDeriv (sponge/pruettdamping.f90:69-92), called once per time step after TimeStep (timedisc_func.f90:357) when
+ * SpongeBaseFlow = pruett: SpBaseFlow += (U - SpBaseFlow) dt / tempFilterWidth. dgx_get_baseflow downloads it (the reference
+ * writes it to the *_BaseFlow_* file). */
+int dgx_temp_filter_time_deriv(dgx_handle *h, double dt, double tempFilterWidth);
+int dgx_get_baseflow(dgx_handle *h, double *SpBaseFlow);
 
 /* measurement helpers (not part of the reference interface) */
 int dgx_sync(dgx_handle *h);

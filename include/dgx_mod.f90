@@ -40,6 +40,7 @@ TYPE, BIND(C), PUBLIC :: dgx_config
   REAL(C_DOUBLE) :: AdvVel(3)
   TYPE(C_PTR)    :: Elem_xGP
   INTEGER(C_INT) :: doWeakLifting, doConservativeLifting   ! lifting.f90:139-141
+  TYPE(C_PTR)    :: SpongeMat, SpBaseFlow                  ! sponge.f90 (SpongeMat expanded to all elements), C_NULL_PTR: no sponge
 END TYPE dgx_config
 
 TYPE(C_PTR), PUBLIC, SAVE :: dgx = C_NULL_PTR   !< the library handle (one per rank)
@@ -91,6 +92,13 @@ INTERFACE
   INTEGER(C_INT) FUNCTION dgx_calc_bulk_velocity(h,wGP,Vol,BulkVel) BIND(C,NAME='dgx_calc_bulk_velocity')
     IMPORT; TYPE(C_PTR),VALUE :: h; REAL(C_DOUBLE),INTENT(IN) :: wGP(*); REAL(C_DOUBLE),VALUE :: Vol; REAL(C_DOUBLE),INTENT(OUT) :: BulkVel
   END FUNCTION
+  !> TempFilterTimeDeriv (sponge/pruettdamping.f90:69-92)
+  INTEGER(C_INT) FUNCTION dgx_temp_filter_time_deriv(h,dt,tempFilterWidth) BIND(C,NAME='dgx_temp_filter_time_deriv')
+    IMPORT; TYPE(C_PTR),VALUE :: h; REAL(C_DOUBLE),VALUE :: dt,tempFilterWidth
+  END FUNCTION
+  INTEGER(C_INT) FUNCTION dgx_get_baseflow(h,SpBaseFlow) BIND(C,NAME='dgx_get_baseflow')
+    IMPORT; TYPE(C_PTR),VALUE :: h; REAL(C_DOUBLE),INTENT(OUT) :: SpBaseFlow(*)
+  END FUNCTION
   INTEGER(C_INT) FUNCTION dgx_set_channel_forcing(h,on,dpdx,BulkVel) BIND(C,NAME='dgx_set_channel_forcing')
     IMPORT; TYPE(C_PTR),VALUE :: h; INTEGER(C_INT),VALUE :: on; REAL(C_DOUBLE),VALUE :: dpdx,BulkVel
   END FUNCTION
@@ -98,7 +106,7 @@ END INTERFACE
 
 PUBLIC :: dgx_create,dgx_destroy,dgx_last_error,dgx_set_state,dgx_get_state,dgx_get_ut,dgx_get_gradients
 PUBLIC :: dgx_time_derivative,dgx_rk_stage,dgx_rk_step,dgx_calc_timestep,dgx_nccl_unique_id
-PUBLIC :: dgx_analyze_tgv,dgx_calc_bulk_velocity,dgx_set_channel_forcing
+PUBLIC :: dgx_analyze_tgv,dgx_calc_bulk_velocity,dgx_set_channel_forcing,dgx_temp_filter_time_deriv,dgx_get_baseflow
 PUBLIC :: DGX_Check
 
 CONTAINS

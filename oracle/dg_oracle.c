@@ -98,6 +98,9 @@ typedef struct {
     /* non-default lifting forms (lifting.f90:81-85, 139-141): weak form (surface flux 1/2 (U_m + U_s), D_Hat_T, signed
      * surface integral) and conservative volume form (metrics inside the derivative); BR2 is always strong */
     int doWeakLifting, doConservativeLifting;
+    /* sponge (sponge/sponge.f90:529-588): SpongeMat(0:N,0:N,0:N,nElems) = damping sigma / sJ, zero outside the sponge zone,
+     * or NULL; the base flow lives in the oracle (array "SpBaseFlow") */
+    const double *SpongeMat;
 } dgo_config;
 
 typedef struct {
@@ -111,6 +114,7 @@ typedef struct {
     double *f, *g, *h;
     double *MetricsAdv, *MetricsVisc;
     double *FluxX, *FluxY, *FluxZ; /* BR2 lifting fluxes (lifting_br2.t90) */
+    double *SpBaseFlow;            /* sponge base flow (PP_nVar,n,n,n,nElems) */
 } dgo;
 
 #define IDX_VOL(s, nv, v, i, j, k, e) ((size_t)(v) + (size_t)(nv) * ((size_t)(i) + (s)->n * ((size_t)(j) + (s)->n * ((size_t)(k) + (size_t)(s)->n * (size_t)(e)))))
@@ -1406,6 +1410,11 @@ int dgo_time_derivative(dgo *s, double t)
     for (size_t d = 0; d < s->nDOF; d++)
         for (int v = 0; v < NV; v++) s->Ut[NV * d + v] = s->Ut[NV * d + v] * (-1.);
     /* 13. */ calc_source(s, t);
+    if (c->SpongeMat) { /* sponge.f90:529-588 Sponge */
+#pragma omp parallel for schedule(static)
+        for (size_t d = 0; d < s->nDOF; d++)
+            for (int v = 0; v < NV; v++) s->Ut[NV * d + v] = s->Ut[NV * d + v] - c->SpongeMat[d] * (s->U[NV * d + v] - s->SpBaseFlow[NV * d + v]);
+    }
     if (c->tcSource) { /* dg.f90:419 TestcaseSource (commented out in GALAEXI; host FLEXI testcase/channel/testcase.f90:277-296) */
 #pragma omp parallel for schedule(static)
         for (size_t d = 0; d < s->nDOF; d++) {
@@ -1564,6 +1573,7 @@ dgo *dgo_create(const dgo_config *cfg)
     AL(gradUx_slave, NL * s->nFace); AL(gradUy_slave, NL * s->nFace); AL(gradUz_slave, NL * s->nFace);
     AL(f, NV * s->nDOF); AL(g, NV * s->nDOF); AL(h, NV * s->nDOF);
     AL(FluxX, NL * s->nFace); AL(FluxY, NL * s->nFace); AL(FluxZ, NL * s->nFace);
+    AL(SpBaseFlow, NV * s->nDOF);
 #undef AL
     /* the reference initialises U_slave/UPrim_slave of BC sides to 0 and never touches them; prim of a zero
      * state would divide by zero, so the slave arrays of sides without a slave element get a benign state. */
@@ -1576,7 +1586,7 @@ void dgo_destroy(dgo *s)
     if (!s) return;
     double *p[] = {s->U, s->Ut, s->UPrim, s->Ut_tmp, s->U_master, s->U_slave, s->UPrim_master, s->UPrim_slave, s->Flux_master,
                    s->Flux_slave, s->gradUx, s->gradUy, s->gradUz, s->gradUx_master, s->gradUy_master, s->gradUz_master,
-                   s->gradUx_slave, s->gradUy_slave, s->gradUz_slave, s->f, s->g, s->h, s->FluxX, s->FluxY, s->FluxZ};
+                   s->gradUx_slave, s->gradUy_slave, s->gradUz_slave, s->f, s->g, s->h, s->FluxX, s->FluxY, s->FluxZ, s->SpBaseFlow};
     for (size_t i = 0; i < sizeof(p) / sizeof(p[0]); i++) free(p[i]);
     free(s);
 }
@@ -1587,7 +1597,7 @@ double *dgo_array(dgo *s, const char *name)
 #define R(x) if (!strcmp(name, #x)) return s->x
     R(U); R(Ut); R(UPrim); R(Ut_tmp); R(U_master); R(U_slave); R(UPrim_master); R(UPrim_slave); R(Flux_master); R(Flux_slave);
     R(gradUx); R(gradUy); R(gradUz); R(gradUx_master); R(gradUy_master); R(gradUz_master);
-    R(gradUx_slave); R(gradUy_slave); R(gradUz_slave);
+    R(gradUx_slave); R(gradUy_slave); R(gradUz_slave); R(SpBaseFlow);
 #undef R
     return NULL;
 }
@@ -1597,6 +1607,14 @@ void dgo_prolong_to_face(dgo *s, int nVar, const double *Uvol, double *Um, doubl
 void dgo_surf_int(dgo *s, int nVar, const double *Fm, const double *Fs, double *Ut) { surf_int(s, nVar, Fm, Fs, Ut, 0, 0, 0); }
 void dgo_lifting(dgo *s) { lifting_br1(s); }
 void dgo_filter(dgo *s) { filter_u(s); }
+/* sponge/pruettdamping.f90:69-92 TempFilterTimeDeriv: the base flow follows the solution with the time scale tempFilterWidth */
+void dgo_temp_filter_time_deriv(dgo *s, double dt, double tempFilterWidth)
+{
+    const double fac = dt / tempFilterWidth;
+    size_t nTot = NV * s->nDOF;
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < nTot; i++) s->SpBaseFlow[i] = s->SpBaseFlow[i] + (s->U[i] - s->SpBaseFlow[i]) * fac;
+}
 void dgo_set_forcing(dgo *s, int on, double dpdx, double BulkVel) { s->c.tcSource = on; s->c.dpdx = dpdx; s->c.BulkVel = BulkVel; }
 /* testcase/channel/testcase.f90:241-271 CalcForcing: BulkVel = 1/Vol sum u wGPVol / sJ over the solution nodes */
 double dgo_bulk_velocity(dgo *s, const double *wGP, double Vol)

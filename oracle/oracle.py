@@ -44,7 +44,8 @@ class _Prec:
                        [(k, rp) for k in ("M_0_1", "M_0_2", "M_1_0", "M_2_0", "FilterMat")] + \
                        [("iniExactFunc", C.c_int), ("AdvVel", self.real * 3), ("Elem_xGP", rp)] + \
                        [("tcSource", C.c_int), ("dpdx", self.real), ("BulkVel", self.real)] + \
-                       [("doWeakLifting", C.c_int), ("doConservativeLifting", C.c_int)]
+                       [("doWeakLifting", C.c_int), ("doConservativeLifting", C.c_int)] + \
+                       [("SpongeMat", rp)]
         self.Config = Config
         self._lib = None
 
@@ -70,6 +71,7 @@ class _Prec:
             L.dgo_surf_int.argtypes = [C.c_void_p, C.c_int, rp, rp, rp]
             L.dgo_lifting.argtypes = [C.c_void_p]
             L.dgo_filter.argtypes = [C.c_void_p]
+            L.dgo_temp_filter_time_deriv.argtypes = [C.c_void_p, r, r]
             L.dgo_set_forcing.argtypes = [C.c_void_p, C.c_int, r, r]
             L.dgo_bulk_velocity.restype = r
             L.dgo_bulk_velocity.argtypes = [C.c_void_p, rp, r]
@@ -166,6 +168,9 @@ class Oracle:
             c.iniExactFunc = int(case.IniExactFunc)
             for k_, v_ in enumerate(case.AdvVel):
                 c.AdvVel[k_] = v_
+        if getattr(case, "SpongeMat", None) is not None:
+            self._keep["SpongeMat"] = f64(case.SpongeMat)
+            c.SpongeMat = _d(self._keep["SpongeMat"])
         c.doWeakLifting = int(getattr(case, "doWeakLifting", False))
         c.doConservativeLifting = int(getattr(case, "doConservativeLifting", False))
         FilterMat = getattr(case, "FilterMat", None)
@@ -182,8 +187,10 @@ class Oracle:
         self.h = L.dgo_create(C.byref(c))
         n, nE, nS = self.n, m.nElems, m.nSides
         self._shapes = {}
-        for nm in ("U", "Ut", "Ut_tmp"):
+        for nm in ("U", "Ut", "Ut_tmp", "SpBaseFlow"):
             self._shapes[nm] = (nE, n, n, n, 5)
+        if getattr(case, "SpBaseFlow", None) is not None:
+            self.array("SpBaseFlow")[...] = case.SpBaseFlow
         self._shapes["UPrim"] = (nE, n, n, n, 6)
         for nm in ("gradUx", "gradUy", "gradUz"):
             self._shapes[nm] = (nE, n, n, n, 5)
@@ -226,6 +233,9 @@ class Oracle:
         err = self.prec.lib().dgo_rk_step(self.h, float(t), float(dt), td.nRKStages, _d(A), _d(b), _d(c))
         if err:
             raise RuntimeError("oracle: unsupported boundary condition type")
+
+    def temp_filter_time_deriv(self, dt: float, tempFilterWidth: float):
+        self.prec.lib().dgo_temp_filter_time_deriv(self.h, float(dt), float(tempFilterWidth))
 
     def set_forcing(self, dpdx: float, BulkVel: float, on: bool = True):
         self.prec.lib().dgo_set_forcing(self.h, int(on), float(dpdx), float(BulkVel))

@@ -176,6 +176,22 @@ def l2_error(c, U, t, NAnalyze=None, exact=None):
     return np.sqrt(np.sum((w3[None] * Ja)[..., None] * d * d, axis=(0, 1, 2, 3)) / an.volume(c))
 
 
+def naca_regression_case(nProcs=1, myRank=0):
+    """regressioncheck/checks/naca/3D/parameter.ini: NACA0012, Re=5000, AoA 8 deg; N=3 Gauss, weak form, BR1, build-default
+    RoeEntropyFix, curved NGeo=2 mesh, BCs 2 (refstate) / 3 (adiabatic wall) / periodic z, sponge ramp from x=2 over a distance
+    of 3 with the Pruett base flow (tempFilterWidth 2). Returns case, initial state, tempFilterWidth."""
+    from galaexi_b200.host import sponge as sp
+    h = load_mesh("naca_mesh.npz")
+    eos = eq.Eos(kappa=1.4, R=2.857142857, Pr=0.72, mu0=0.0002)
+    c = cs.build_case(h, 3, bs.NODETYPE_G, split=None, riemann="RoeEntropyFix", parabolic=True, eos=eos,
+                      refstates=((1.0, 0.990268069, 0.139173101, 0.0, 4.4642857),), nProcs=nProcs, myRank=myRank,
+                      user_bcs={"BC_inflow": (2, 1), "BC_outflow": (2, 1)}, CFLScale=0.9, DFLScale=0.9)
+    U0 = eq.ini_refstate(c.geo["Elem_xGP"], c.RefStatePrim[0], eos)          # IniExactFunc = 1
+    c.SpongeMat = sp.sponge_mat(c, [dict(shape=1, xStart=(2.0, 0.0, 0.0), dir=(1.0, 0.0, 0.0), distance=3.0)], damping=1.0)
+    c.SpBaseFlow = U0.copy()                                                  # Pruett from scratch: the exact function
+    return c, U0, 2.0
+
+
 def channel_case(E=4, N=5, nProcs=1, myRank=0, **kw):
     """BASELINE config #4-like: plane channel, isothermal walls (4) at y+-, periodic x,z, Roe flux, y-stretched."""
     def stretch(d, s):

@@ -639,3 +639,46 @@ def test_weak_and_conservative_lifting(name, kw):
         c, U0 = cases.mortar_case(kw.pop("mesh"), **kw)
     assert c.doWeakLifting or c.doConservativeLifting
     _compare_rhs_and_steps(c, U0, nsteps=2)
+
+
+# ---- sponge zone + Pruett base flow: the reference's NACA regression (config #5) ------------------------------------------------------
+def test_sponge_parity():
+    c, U0, width = cases.naca_regression_case()
+    x = c.geo["Elem_xGP"]
+    U = U0 * (1.0 + 0.02 * np.sin(3.0 * x[..., 0]) * np.cos(2.0 * x[..., 1]))[..., None]
+    o, s = _oracle(c), _solver(c)
+    o.set_state(U)
+    s.set_state(U)
+    Ut_ref = o.time_derivative(0.0).copy()
+    s.DGTimeDerivative_weakForm(0.0)
+    assert cases.rel_l2(s.get_ut(), Ut_ref) <= TOL_UT
+    t = 0.0
+    for _ in range(3):
+        dt = o.calc_timestep()[0]
+        o.rk_step(t, dt)
+        s.TimeStepByLSERKW2(t, dt)
+        o.temp_filter_time_deriv(dt, width)
+        s.TempFilterTimeDeriv(dt, width)
+        t += dt
+    assert cases.rel_l2(s.get_state(), o.array("U")) <= TOL_U
+    assert cases.rel_l2(s.get_baseflow(), o.array("SpBaseFlow")) <= 1e-13
+    s.FinalizeDG()
+    o.close()
+
+
+def test_naca_reference_state():
+    """regressioncheck/checks/naca/3D: the whole run of the reference's check (t = 0 ... 10, about 28 000 adaptive time
+    steps, curved NACA0012 mesh, BCs 2 / 3 / periodic, sponge with the Pruett base flow) through the CUDA path, compared with
+    the reference's own state file NACA0012_Re5000_AoA8_3D_Referenz_0000010.000000000.h5. analyze.ini: h5diff of DG_Solution,
+    absolute tolerance 5e-11."""
+    import os
+    c, U0, width = cases.naca_regression_case()
+    s = _solver(c)
+    s.set_state(U0)
+    t, it = timeloop.advance(s, 0.0, 10.0, after_step=lambda tn, dt: s.TempFilterTimeDeriv(dt, width))
+    ref = np.load(os.path.join(cases.GOLD, "naca3d_state.npz"))["DG_Solution"]
+    err = float(np.abs(s.get_state() - ref).max())
+    print(f"NACA regression: {it} time steps, max abs deviation from the reference state {err:.3e}")
+    assert it > 20000
+    assert err <= 5.0e-11
+    s.FinalizeDG()

@@ -267,3 +267,27 @@ def test_time_loop_dt_reuse_rule():
     tb, nb = timeloop.advance(b, 0.0, 1.0, nCalcTimeStepMax=10)
     assert ta == tb == 1.0 and a.ncalc == na and abs(na - nb) <= 1
     assert b.ncalc <= nb // 4            # dt drifts by 1e-8 per step -> the evaluation is skipped most of the time
+
+
+# ---- sponge zone and Pruett base flow (sponge/sponge.f90, pruettdamping.f90) -------------------------------------------------------
+def test_sponge_source_and_pruett_filter_oracle():
+    c, U0, width = cases.naca_regression_case()
+    x = c.geo["Elem_xGP"]
+    sig = c.SpongeMat * c.geo["sJ"]
+    # ramp from x = 2 to x = 5 (the domain ends at x = 4.98): zero upstream, monotone, close to the full damping at the outflow
+    assert sig.min() == 0.0 and 0.999 < sig.max() <= 1.0 and np.all(sig[x[..., 0] <= 2.0] == 0.0) and np.all(sig[x[..., 0] > 4.5] > 0.9)
+    U = U0 * (1.0 + 0.02 * np.sin(3.0 * x[..., 0]) * np.cos(2.0 * x[..., 1]))[..., None]
+    o = Oracle(c)
+    o.set_state(U)
+    Ut1 = o.time_derivative(0.0).copy()
+    c2, _, _ = cases.naca_regression_case()
+    c2.SpongeMat = None
+    o2 = Oracle(c2)
+    o2.set_state(U)
+    Ut0 = o2.time_derivative(0.0).copy()
+    # after the Jacobian: Ut_sponge - Ut = -damping sigma (U - U_base)
+    assert np.abs((Ut1 - Ut0) + sig[..., None] * (U - U0)).max() <= 1e-12 * np.abs(Ut0).max()
+    o.temp_filter_time_deriv(0.01, width)
+    assert np.allclose(o.array("SpBaseFlow"), U0 + (U - U0) * 0.01 / width, rtol=0, atol=1e-15)
+    o.close()
+    o2.close()

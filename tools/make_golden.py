@@ -89,6 +89,8 @@ def main():
     np.savez_compressed(os.path.join(OUT, "tgv_split_csv.npz"), rows=csv)   # all 555 analyze rows (t = 0 ... 13)
     st = h5lite.read_state(os.path.join(REF, "regressioncheck/checks/parabolic/cavity_3D/reggie_cavity_Re100_State_0000001.000000000.h5"))
     np.savez_compressed(os.path.join(OUT, "cavity3d_state.npz"), DG_Solution=st["DG_Solution"], Time=st["attrs"]["Time"])
+    st = h5lite.read_state(os.path.join(REF, "regressioncheck/checks/naca/3D/NACA0012_Re5000_AoA8_3D_Referenz_0000010.000000000.h5"))
+    np.savez_compressed(os.path.join(OUT, "naca3d_state.npz"), DG_Solution=st["DG_Solution"], Time=st["attrs"]["Time"])
     print("wrote", sorted(os.listdir(OUT)))
 
 

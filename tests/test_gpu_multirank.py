@@ -27,3 +27,18 @@ def test_two_ranks_match_single_rank(case):
     assert p.returncode == 0 and lines, p.stdout[-2000:] + p.stderr[-4000:]
     r = json.loads(lines[-1][8:])
     assert r["u_rel_l2"] <= 1e-10 and r["dt_rel"] <= 1e-13 and r["diag_rel"] <= 1e-9 and r["bulk_rel"] <= 1e-10
+
+
+def test_naca_regression_on_two_ranks():
+    """regressioncheck/checks/naca/3D is run with MPI=6 by the reference: the whole run to t=10 on two ranks (NCCL halos, sponge,
+    Pruett base flow) against the reference's state file, abs 5e-11."""
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    port = 29700 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tools", "mr_check.py"), "naca_regression"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    lines = [l for l in p.stdout.splitlines() if l.startswith("MRCHECK ")]
+    assert p.returncode == 0 and lines, p.stdout[-2000:] + p.stderr[-4000:]
+    r = json.loads(lines[-1][8:])
+    assert r["steps"] > 20000 and r["max_abs_vs_reference_state"] <= 5e-11

@@ -52,6 +52,29 @@ def main():
             return cases.tgv_box_case(E=4, N=4, NGeo=2, deform=0.05, nProcs=nProcs, myRank=myRank, lifting="br2")
         raise SystemExit(f"unknown case {name}")
 
+    if name == "naca_regression":
+        # the reference's naca/3D check is run with MPI=6 (command_line.ini): the whole run to t=10 on `world` ranks against the
+        # reference's state file (h5diff, abs 5e-11)
+        from galaexi_b200.host import timeloop
+        c, U0, width = cases.naca_regression_case(nProcs=world, myRank=rank)
+        s = dg.DGSolver(c, device=local, nccl_id=ids[0])
+        s.set_state(U0)
+        t, it = timeloop.advance(s, 0.0, 10.0, after_step=lambda tn, dt_: s.TempFilterTimeDeriv(dt_, width))
+        U = s.get_state()
+        s.sync()
+        outs = [None] * world
+        dist.gather_object((c.mesh.offsetElem, U), outs if rank == 0 else None, dst=0)
+        ok = True
+        if rank == 0:
+            outs.sort(key=lambda x: x[0])
+            ref = np.load(os.path.join(ROOT, "tests", "golden", "naca3d_state.npz"))["DG_Solution"]
+            err = float(np.abs(np.concatenate([o[1] for o in outs]) - ref).max())
+            print("MRCHECK " + json.dumps(dict(case=name, world=world, steps=it, max_abs_vs_reference_state=err)), flush=True)
+            ok = err <= 5e-11
+        s.FinalizeDG()
+        dist.barrier()
+        dist.destroy_process_group()
+        sys.exit(0 if ok else 3)
     c, U0 = build(world, rank)
     s = dg.DGSolver(c, device=local, nccl_id=ids[0])
     s.set_state(U0)

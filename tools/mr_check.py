@@ -75,6 +75,46 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
         sys.exit(0 if ok else 3)
+    if name in ("cavity_regression", "tgv_csv"):
+        # parabolic/cavity_3D is run with MPI=1,2 and tgv/split with MPI=6 by the reference (command_line.ini)
+        from galaexi_b200.host import analyze as an
+        from galaexi_b200.host import timeloop
+        c, U0 = (cases.cavity_case if name == "cavity_regression" else cases.tgv_split_case)(nProcs=world, myRank=rank)
+        s = dg.DGSolver(c, device=local, nccl_id=ids[0])
+        s.set_state(U0)
+        res = dict(case=name, world=world)
+        if name == "cavity_regression":
+            t, it = timeloop.advance(s, 0.0, 1.0)
+            outs = [None] * world
+            dist.gather_object((c.mesh.offsetElem, s.get_state()), outs if rank == 0 else None, dst=0)
+            if rank == 0:
+                outs.sort(key=lambda x: x[0])
+                ref = np.load(os.path.join(ROOT, "tests", "golden", "cavity3d_state.npz"))["DG_Solution"]
+                res.update(steps=it, max_abs_vs_reference_state=float(np.abs(np.concatenate([o[1] for o in outs]) - ref).max()))
+                ok = res["max_abs_vs_reference_state"] <= 1e-12
+        else:
+            rows = np.load(os.path.join(ROOT, "tests", "golden", "tgv_split_csv.npz"))["rows"][:41]
+            scale = np.abs(rows[:, 1:]).max(axis=0)
+            vol = torch.tensor([an.volume(c)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(vol)
+            s.DGTimeDerivative_weakForm(0.0)
+            worst = float(np.max(np.abs(s.AnalyzeTestcase(NAnalyze=10, Vol=float(vol.item())) - rows[0][1:]) / scale))
+            t = 0.0
+            for r in rows[1:]:
+                for _ in range(10):
+                    dt, err = s.CalcTimeStep()
+                    s.TimeStepByLSERKW2(t, dt)
+                    t += dt
+                worst = max(worst, float(np.max(np.abs(s.AnalyzeTestcase(NAnalyze=10, Vol=float(vol.item())) - r[1:]) / scale)))
+            res.update(rows=len(rows), worst_column_deviation=worst, t=t)
+            ok = worst <= 1e-8
+        s.sync()
+        if rank == 0:
+            print("MRCHECK " + json.dumps(res), flush=True)
+        s.FinalizeDG()
+        dist.barrier()
+        dist.destroy_process_group()
+        sys.exit(0 if (rank != 0 or ok) else 3)
     c, U0 = build(world, rank)
     s = dg.DGSolver(c, device=local, nccl_id=ids[0])
     s.set_state(U0)

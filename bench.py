@@ -31,6 +31,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 N_POLY = 7
+CURVED = False
 ELEMS_PER_GPU = 32          # 32^3 elements per GPU
 NSTAGES = 5
 
@@ -57,7 +58,7 @@ def build_case(ngpus: int, rank: int, elems=None, N=N_POLY):
     import cases
     dims = elems or box_dims(ngpus)
     L = tuple(2 * np.pi * d / min(dims) for d in dims)
-    h = ms.make_box_mesh(dims, x0=(0.0, 0.0, 0.0), x1=L, NGeo=1)
+    h = ms.make_box_mesh(dims, x0=(0.0, 0.0, 0.0), x1=L, NGeo=2, deform=0.1) if CURVED else ms.make_box_mesh(dims, x0=(0.0, 0.0, 0.0), x1=L, NGeo=1)
     eos = eq.Eos(**cases.TGV_EOS)
     c = cs.build_case(h, N, bs.NODETYPE_GL, split="PI", riemann="RoeEntropyFix", parabolic=True, eos=eos,
                       refstates=cases.TGV_REF, nProcs=ngpus, myRank=rank, CFLScale=0.9, DFLScale=0.9)
@@ -193,7 +194,7 @@ def run_reference(args):
 def workload_name(ngpus):
     d = box_dims(ngpus)
     return (f"TGV Navier-Stokes Re1600 Ma0.1, N={N_POLY} Gauss-Lobatto, split-form PI + BR1, RoeEntropyFix, CarpenterRK4-5, "
-            f"{d[0]}x{d[1]}x{d[2]} elements ({ELEMS_PER_GPU}^3 per GPU), adaptive dt")
+            f"{d[0]}x{d[1]}x{d[2]} elements ({ELEMS_PER_GPU}^3 per GPU){', curved NGeo=2 mesh (sine deformation 0.1)' if CURVED else ''}, adaptive dt")
 
 
 def main():
@@ -206,10 +207,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--degree", type=int, default=N_POLY,
                     help="polynomial degree N (default 7 = BASELINE config #2, the headline; 5 = per-GPU load of config #3)")
+    ap.add_argument("--curved", action="store_true", help="NGeo=2 mesh deformed by the reference's meshdeform sine (mesh.f90:224-235) instead of the Cartesian one")
     ap.add_argument("--elems", type=int, default=ELEMS_PER_GPU, help="elements per direction and GPU (default 32; 64 = config #3 on one GPU)")
     args = ap.parse_args()
     globals()["N_POLY"] = args.degree
     globals()["ELEMS_PER_GPU"] = args.elems
+    globals()["CURVED"] = bool(args.curved)
     if args.impl == "reference":
         return run_reference(args)
 

@@ -291,6 +291,32 @@ class DGSolver:
         """Parameters of TestcaseSource (testcase/channel/testcase.f90:277-296)."""
         self._ck(self.lib.dgx_set_channel_forcing(self.h, int(on), float(dpdx), float(BulkVel)))
 
+    def WriteState(self, MeshFileName: str, OutputTime: float, FutureTime: float, ProjectName: str, out_dir: str = ".",
+                   NOut: int | None = None, dt: float | None = None, ini_text: str = "", isErrorFile: bool = False, barrier=None) -> str:
+        """WriteState (io_hdf5/hdf5_output.f90:84-211): D2H of U through dgx_get_state and a state file in the reference
+        layout (readable by posti and by the reference's Restart). All ranks call it; each writes its own element range."""
+        from .host import state_io
+        m = self.case.mesh
+        ed = {"myRank": float(m.myRank)}
+        if dt is not None:
+            ed["dt"] = float(dt)
+        return state_io.write_state(self.get_state(), self.case.N, self.case.node_type, ProjectName, MeshFileName, OutputTime,
+                                    FutureTime, out_dir=out_dir, sJ=self.case.geo["sJ"], NOut=NOut, elem_data=ed, ini_text=ini_text,
+                                    is_error_file=isErrorFile, offsetElem=m.offsetElem, nGlobalElems=m.nGlobalElems,
+                                    rank=m.myRank, barrier=barrier)
+
+    def Restart(self, RestartFile: str, ResetTime: bool = False) -> float:
+        """InitRestart + Restart (restart/restart.f90:60-135, 304-560): this rank's element range of DG_Solution, interpolated
+        when the file's degree / node type differ, H2D through dgx_set_state; returns RestartTime."""
+        from .host import metrics, state_io
+        m = self.case.mesh
+        info = state_io.read_state_attrs(RestartFile)
+        dj = metrics.det_jac_ref(m.NodeCoords, m.NGeo, self.case.node_type) if info["N"] > self.case.N else None
+        U, t = state_io.restart(RestartFile, self.case.N, self.case.node_type, sJ=self.case.geo["sJ"], detJac_Ref=dj, NGeo=m.NGeo,
+                                offsetElem=m.offsetElem, nElems=m.nElems, nGlobalElems=m.nGlobalElems, ResetTime=ResetTime)
+        self.set_state(U)
+        return t
+
     def FinalizeDG(self):
         if getattr(self, "h", None):
             self.lib.dgx_destroy(self.h)

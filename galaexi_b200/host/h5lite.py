@@ -14,6 +14,7 @@ File layouts consumed (mesh_readin.f90:33-50, hdf5_output.f90:84-
 """
 from __future__ import annotations
 
+import mmap
 import struct
 
 import numpy as np
@@ -24,7 +25,10 @@ _SIG = b"\x89HDF\r\n\x1a\n"
 class H5File:
     def __init__(self, path: str):
         with open(path, "rb") as f:
-            self.buf = f.read()
+            try:
+                self.buf = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)   # multi-GB states: pages on demand
+            except (ValueError, OSError):
+                self.buf = f.read()
         self.base = self._find_base()
         b = self.base
         ver = self.buf[b + 8]
@@ -100,7 +104,7 @@ class H5File:
             e = a + 8 + 40 * i
             name_off, hdr = struct.unpack_from("<QQ", self.buf, e)
             s = heap_data + name_off
-            t = self.buf.index(b"\x00", s)
+            t = self.buf.find(b"\x00", s)
             out[self.buf[s:t].decode()] = hdr
 
     # ------------------------------------------------------------------ datatypes
@@ -137,7 +141,17 @@ class H5File:
             self._cache[name] = self._read_header(self.objects[name])
         return self._cache[name]
 
-    def dataset(self, name: str) -> np.ndarray:
+    def dataset_shape(self, name: str) -> tuple[int, ...]:
+        for mtype, p in self._msgs(name):
+            if mtype == 0x01:
+                return self._dspace(p)
+        raise KeyError(name)
+
+    def dataset_rows(self, name: str, start: int, count: int) -> np.ndarray:
+        """Rows [start, start+count) along the slowest dimension (an element range: what one rank reads)."""
+        return self.dataset(name, start, count)
+
+    def dataset(self, name: str, start: int = 0, count: int | None = None) -> np.ndarray:
         dt = shape = None
         data = None
         for mtype, p in self._msgs(name):
@@ -157,11 +171,19 @@ class H5File:
                     data = bytes(p[4:4 + size])
                 else:
                     raise NotImplementedError("chunked layout")
-        n = int(np.prod(shape)) if shape else 1
+        skip = 0
+        if shape and (start or count is not None):
+            count = shape[0] - start if count is None else count
+            if start < 0 or count < 0 or start + count > shape[0]:
+                raise IndexError(f"rows {start}:{start + count} outside {name}{shape}")
+            row = int(np.prod(shape[1:], dtype=np.int64))
+            skip = start * row * dt.itemsize
+            shape = (count,) + tuple(shape[1:])
+        n = int(np.prod(shape, dtype=np.int64)) if shape else 1
         if isinstance(data, tuple):
-            arr = np.frombuffer(self.buf, dtype=dt, count=n, offset=data[0]) if data[1] else np.zeros(n, dt)
+            arr = np.frombuffer(self.buf, dtype=dt, count=n, offset=data[0] + skip) if data[1] else np.zeros(n, dt)
         else:
-            arr = np.frombuffer(data, dtype=dt, count=n)
+            arr = np.frombuffer(data, dtype=dt, count=n, offset=skip)
         return arr.reshape(shape).copy()
 
     def attrs(self, name: str | None = None) -> dict[str, np.ndarray]:

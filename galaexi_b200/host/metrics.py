@@ -123,6 +123,23 @@ def _elem_geometry(ops: _Ops, NodeCoords: np.ndarray, crossProductMetrics: bool)
     return XCL_N, Ja, detJac_N
 
 
+def det_jac_ref(NodeCoords: np.ndarray, NGeo: int, node_type: str, chunk: int = 4096) -> np.ndarray:
+    """detJac_Ref(1,0:3*NGeo,0:3*NGeo,0:3*NGeo,nElems) (metrics.f90:262-283): the Jacobian determinant on the 3*NGeo
+    interpolation points of ``node_type``; [e,k,j,i]. Kept by the reference for the conservative restart projection
+    (restart.f90:500-512); NodeCoords [e,k,j,i,3] on the equidistant NGeo points."""
+    ops = _Ops(NGeo, NGeo, node_type)
+    out = np.empty((NodeCoords.shape[0],) + (3 * NGeo + 1,) * 3)
+    for s0 in range(0, NodeCoords.shape[0], chunk):
+        XCL = change_basis_volume(ops.Vdm_EQNGeo_CLNGeo, NodeCoords[s0:s0 + chunk])
+        d = _deriv(ops.DCL_NGeo, XCL)
+        a = change_basis_volume(ops.Vdm_CLNGeo_NGeoRef, d.reshape(d.shape[:4] + (9,)))
+        a = a.reshape(a.shape[:4] + (3, 3))
+        out[s0:s0 + chunk] = (a[..., 0, 0] * (a[..., 1, 1] * a[..., 2, 2] - a[..., 2, 1] * a[..., 1, 2])
+                              + a[..., 1, 0] * (a[..., 2, 1] * a[..., 0, 2] - a[..., 0, 1] * a[..., 2, 2])
+                              + a[..., 2, 0] * (a[..., 0, 1] * a[..., 1, 2] - a[..., 1, 1] * a[..., 0, 2]))
+    return out
+
+
 def _face_slice(A: np.ndarray, loc: int, N: int) -> np.ndarray:
     """A[e,k,j,i,...] -> face array tmp[e,b,a,...] with (a,b) the two remaining volume indices in order."""
     if loc == mp.XI_MINUS:

@@ -48,11 +48,11 @@ def tgv_box_case(E=4, N=5, NGeo=1, deform=0.0, nProcs=1, myRank=0, perturb=0.0, 
     return c, U0
 
 
-def cavity_case(nProcs=1, myRank=0, riemann="RoeEntropyFix", **kw):
+def cavity_case(nProcs=1, myRank=0, riemann="RoeEntropyFix", N=2, node_type=bs.NODETYPE_G, **kw):
     """regressioncheck/checks/parabolic/cavity_3D: N=2 Gauss, weak form, BR1, walls (4) + Dirichlet lid (2)."""
     h = load_mesh("cavity3d_mesh.npz")
     eos = eq.Eos(kappa=1.4, R=1.0, Pr=0.72, mu0=0.01)
-    c = cs.build_case(h, 2, bs.NODETYPE_G, split=None, riemann=riemann, parabolic=True, eos=eos,
+    c = cs.build_case(h, N, node_type, split=None, riemann=riemann, parabolic=True, eos=eos,
                       refstates=((1.0, 1.0, 0.0, 0.0, 71.4285714286), (1.0, 0.0, 0.0, 0.0, 71.4285714286)),
                       user_bcs={"BC_wall_left": (4, 1), "BC_wall_right": (4, 1), "BC_free": (2, 1)}, CFLScale=0.99,
                       DFLScale=0.4, useCurveds=False, nProcs=nProcs, myRank=myRank, **kw)

@@ -682,3 +682,55 @@ def test_naca_reference_state():
     assert it > 20000
     assert err <= 5.0e-11
     s.FinalizeDG()
+
+
+def test_write_state_and_restart_continue_bit_exact(tmp_path):
+    """WriteState at t1 + Restart into a fresh handle continues bit-identically to the uninterrupted run (the state file
+    holds U in full FP64 and the RK scheme has no memory across steps); restart on another degree / node type
+    (restart.f90:455-523) reproduces the file's polynomial on the new nodes."""
+    from galaexi_b200.host import state_io
+    c, U0 = cases.cavity_case()
+    s = _solver(c)
+    s.set_state(U0)
+    t1, _ = timeloop.advance(s, 0.0, 0.05)
+    path = s.WriteState("cavity4x4x4_mesh.h5", t1, 1.0, "cavity_Re100", out_dir=str(tmp_path), dt=1e-3, ini_text="N=2\n")
+    assert path.endswith("cavity_Re100_State_0000000.050000000.h5")
+    info = state_io.read_state_attrs(path)
+    assert info["complete"] and info["N"] == 2 and info["NodeType"] == "GAUSS" and info["Time"] == t1
+    timeloop.advance(s, t1, 0.1)
+    U_ref = s.get_state()
+    s.FinalizeDG()
+    s2 = _solver(c)
+    assert s2.Restart(path) == t1
+    timeloop.advance(s2, t1, 0.1)
+    assert np.array_equal(s2.get_state(), U_ref)
+    s2.FinalizeDG()
+    # restart N=2 Gauss -> N=4 Gauss-Lobatto and back down (conservative branch): the degree-2 data survives the round trip
+    c4, _ = cases.cavity_case(N=4, node_type="GAUSS-LOBATTO")
+    s4 = _solver(c4)
+    s4.Restart(path)
+    p4 = s4.WriteState("cavity4x4x4_mesh.h5", t1, 1.0, "up", out_dir=str(tmp_path))
+    s4.FinalizeDG()
+    s3 = _solver(c)
+    s3.Restart(p4)
+    U_file = state_io.restart(path, 2, "GAUSS")[0]
+    assert np.abs(s3.get_state() - U_file).max() < 1e-12
+    s3.FinalizeDG()
+
+
+def test_restart_from_reference_state_file_layout(tmp_path):
+    """The reference's own cavity state (fixture arrays) written in its layout, restarted, advanced: the RHS of the restarted
+    handle equals the oracle's on the same state."""
+    import os
+    from galaexi_b200.host import state_io
+    c, _ = cases.cavity_case()
+    ref = np.load(os.path.join(cases.GOLD, "cavity3d_state.npz"))["DG_Solution"]
+    path = state_io.write_state(ref, 2, "GAUSS", "cavity_Re100", "cavity4x4x4_mesh.h5", 1.0, 2.0, out_dir=str(tmp_path))
+    s = _solver(c)
+    assert s.Restart(path) == 1.0 and s.Restart(path, ResetTime=True) == 0.0
+    s.DGTimeDerivative_weakForm(1.0)
+    o = _oracle(c)
+    o.set_state(ref)
+    _check_ut(c, ref, s.get_ut(), o.time_derivative(1.0).copy())
+    o.close()
+    s.FinalizeDG()

@@ -91,7 +91,44 @@ def main():
     np.savez_compressed(os.path.join(OUT, "cavity3d_state.npz"), DG_Solution=st["DG_Solution"], Time=st["attrs"]["Time"])
     st = h5lite.read_state(os.path.join(REF, "regressioncheck/checks/naca/3D/NACA0012_Re5000_AoA8_3D_Referenz_0000010.000000000.h5"))
     np.savez_compressed(os.path.join(OUT, "naca3d_state.npz"), DG_Solution=st["DG_Solution"], Time=st["attrs"]["Time"])
+    state_h5_structs()
     print("wrote", sorted(os.listdir(OUT)))
+
+
+def state_h5_structs():
+    """The HDF5 structures libhdf5 wrote into the reference's cavity state file, as hex strings: superblock, the root
+    attribute messages, the object-header messages of DG_Solution / ElemData, the local heap and the B-tree / symbol node
+    heads. tests/test_state_io.py compares what galaexi_b200/host/h5write.py emits with them."""
+    import json
+    import struct
+    f = h5lite.H5File(os.path.join(REF, "regressioncheck/checks/parabolic/cavity_3D/reggie_cavity_Re100_State_0000001.000000000.h5"))
+    b, buf = f.base, f.buf
+    out = dict(userblock_size=b, file_size=len(buf), superblock=bytes(buf[b:b + 96]).hex())
+    out["root_attr_msgs"] = {}
+    for t, pl in f.root_msgs:
+        if t == 0x0C:
+            nsz = struct.unpack_from("<H", pl, 2)[0]
+            out["root_attr_msgs"][bytes(pl[8:8 + nsz - 1]).decode()] = bytes(pl).hex()
+    out["datasets"] = {}
+    for nm, addr in f.objects.items():
+        a = b + addr
+        nmsgs, size = struct.unpack_from("<H", buf, a + 2)[0], struct.unpack_from("<I", buf, a + 8)[0]
+        pos, msgs = a + 16, []
+        while pos < a + 16 + size:
+            t, sz, fl = struct.unpack_from("<HHB", buf, pos)
+            msgs.append([t, fl, bytes(buf[pos + 8:pos + 8 + sz]).hex()])
+            pos += 8 + sz
+        out["datasets"][nm] = dict(header=bytes(buf[a:a + 16]).hex(), msgs=msgs)
+    heap_a = b + struct.unpack_from("<Q", buf, b + 56 + 32)[0]
+    dsz, free, daddr = struct.unpack_from("<QQQ", buf, heap_a + 8)
+    out["heap_header"] = bytes(buf[heap_a:heap_a + 32]).hex()
+    out["heap_data"] = bytes(buf[b + daddr:b + daddr + dsz]).hex()
+    bt = b + struct.unpack_from("<Q", buf, b + 56 + 24)[0]
+    out["btree_head"] = bytes(buf[bt:bt + 48]).hex()
+    sn = b + struct.unpack_from("<Q", buf, bt + 32)[0]
+    out["snod"] = bytes(buf[sn:sn + 8 + 2 * 40]).hex()
+    with open(os.path.join(OUT, "state_h5_structs.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
 
 
 if __name__ == "__main__":

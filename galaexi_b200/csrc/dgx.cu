@@ -132,6 +132,9 @@ struct dgx_handle {
     std::vector<HaloMsg> plan;
     ncclComm_t comm = nullptr;
     double *bvPart = nullptr, *bvW = nullptr;  // dgx_calc_bulk_velocity
+    double *bfPart = nullptr, *bfW = nullptr;  // dgx_calc_body_forces
+    int* bfBC = nullptr;
+    int bfNBCs = 0;
     // TGV diagnostics (dgx_analyze_tgv)
     double *tgvV = nullptr, *tgvW = nullptr, *tgvPart = nullptr;
     int tgvNA1 = 0;
@@ -749,6 +752,65 @@ int dgx_calc_bulk_velocity(dgx_handle* h, const double* wGP, double Vol, double*
     CK(cudaMemcpyAsync(&b, tot, sizeof b, cudaMemcpyDeviceToHost, h->s));
     CK(cudaStreamSynchronize(h->s));
     *BulkVel = b / Vol;
+    return 0;
+}
+
+namespace {
+// wall diagnostics shared by dgx_calc_body_forces / dgx_calc_wall_velocity: r[x * nBCs + iBC], reduced over all ranks
+int wall_diagnostics(dgx_handle* h, const char* who, const double* wGP, const int* BC, int nBCs, std::vector<double>& r) {
+    CK(cudaSetDevice(h->cfg.device));
+    const int nB = h->cfg.nBCSides;
+    if (!wGP || nBCs < 1 || nBCs > 4096 || (nB > 0 && !BC)) return fail(h, "%s: bad arguments", who);
+    for (int sd = 0; sd < nB; sd++)
+        if (BC[sd] < 1 || BC[sd] > nBCs) return fail(h, "%s: BC(%d) = %d outside 1..nBCs = %d", who, sd + 1, BC[sd], nBCs);
+    if (!h->bfPart || h->bfNBCs < nBCs) {
+        if (dalloc(h, &h->bfPart, (size_t)WALL_NPART * (nB + nBCs)) || dalloc(h, &h->bfW, (size_t)h->n) || dalloc(h, &h->bfBC, (size_t)nB)) return 1;
+        h->bfNBCs = nBCs;
+    }
+    CK(cudaMemcpyAsync(h->bfW, wGP, h->n * sizeof(double), cudaMemcpyHostToDevice, h->s));
+    if (nB) CK(cudaMemcpyAsync(h->bfBC, BC, nB * sizeof(int), cudaMemcpyHostToDevice, h->s));
+    double* tot = h->bfPart + (size_t)WALL_NPART * nB;
+    if (nB) {
+        k_wall_sides<<<nB, BF_THREADS, 0, h->s>>>(h->P, h->n, h->Uf[h->cur][0], h->bfW, h->bfPart);
+        if (check_launch(h, "k_wall_sides")) return 1;
+    }
+    k_wall_reduce<<<nBCs, BF_THREADS, 0, h->s>>>(h->bfPart, h->bfBC, nB, nBCs, tot);
+    if (check_launch(h, "k_wall_reduce")) return 1;
+    if (h->comm) {  // calcbodyforces.f90:95-104, analyze_equation.f90:483-493
+        NK(g_nccl.AllReduce(tot, tot, (size_t)7 * nBCs, ncclFloat64, 0 /* ncclSum */, h->comm, h->s));
+        NK(g_nccl.AllReduce(tot + 7 * nBCs, tot + 7 * nBCs, (size_t)nBCs, ncclFloat64, 2 /* ncclMax */, h->comm, h->s));
+        NK(g_nccl.AllReduce(tot + 8 * nBCs, tot + 8 * nBCs, (size_t)nBCs, ncclFloat64, 3 /* ncclMin */, h->comm, h->s));
+    }
+    r.resize((size_t)WALL_NPART * nBCs);
+    CK(cudaMemcpyAsync(r.data(), tot, r.size() * sizeof(double), cudaMemcpyDeviceToHost, h->s));
+    CK(cudaStreamSynchronize(h->s));
+    return 0;
+}
+}  // namespace
+
+int dgx_calc_body_forces(dgx_handle* h, const double* wGP, const int* BC, int nBCs, double* Fp, double* Fv) {
+    if (!Fp || !Fv) return fail(h, "dgx_calc_body_forces: bad arguments");
+    std::vector<double> r;
+    if (wall_diagnostics(h, "dgx_calc_body_forces", wGP, BC, nBCs, r)) return 1;
+    for (int b = 0; b < nBCs; b++)
+        for (int d = 0; d < 3; d++) {
+            Fp[3 * b + d] = r[(size_t)d * nBCs + b];
+            Fv[3 * b + d] = r[(size_t)(3 + d) * nBCs + b];
+        }
+    return 0;
+}
+
+int dgx_calc_wall_velocity(dgx_handle* h, const double* wGP, const int* BC, int nBCs, const double* Surf, double* maxV, double* minV,
+                           double* meanV) {
+    if (!Surf || !maxV || !minV || !meanV) return fail(h, "dgx_calc_wall_velocity: bad arguments");
+    std::vector<double> r;
+    if (wall_diagnostics(h, "dgx_calc_wall_velocity", wGP, BC, nBCs, r)) return 1;
+    for (int b = 0; b < nBCs; b++) {
+        maxV[b] = r[(size_t)7 * nBCs + b];
+        minV[b] = r[(size_t)8 * nBCs + b];
+        // a boundary condition without wall sides keeps the reference's initial values (-1e14 / 1e14 / 0)
+        meanV[b] = (maxV[b] > -WALL_HUGE && Surf[b] > 0.0) ? r[(size_t)6 * nBCs + b] / Surf[b] : 0.0;
+    }
     return 0;
 }
 

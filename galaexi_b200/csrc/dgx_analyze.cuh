@@ -148,4 +148,93 @@ static __global__ void __launch_bounds__(TGV_THREADS) k_tgv_reduce(const double*
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// CalcBodyForces (equations/navierstokes/calcbodyforces.f90:41-205): pressure force sum p n wGPSurf SurfElem and friction
+// force -sum tau n wGPSurf SurfElem on the wall boundary sides (BC types 3, 4, 9: analyze_equation.f90:113-121), and
+// CalcWallVelocity (analyze_equation.f90:435-499): sum |v| wGPSurf SurfElem, max |v|, min |v| on the same sides -- from the
+// face states and the lifted gradient traces of the last DGTimeDerivative_weakForm. One CTA per boundary side writes the
+// WALL_NPART values of that side (neutral elements for a non-wall side); k_wall_reduce combines them per boundary condition
+// in a fixed order: out[x * nBCs + iBC], x = 0..2 Fp, 3..5 Fv, 6 sum |v| dA, 7 max |v|, 8 min |v|.
+constexpr int BF_THREADS = 128;
+constexpr int WALL_NPART = 9;
+constexpr double WALL_HUGE = 1.e14;  // the reference's initial values of minV / maxV
+__device__ __forceinline__ double wall_combine(int x, double a, double b) { return x < 7 ? a + b : (x == 7 ? fmax(a, b) : fmin(a, b)); }
+static __global__ void __launch_bounds__(BF_THREADS) k_wall_sides(const KParams P, int n, const double* __restrict__ Um, const double* __restrict__ wGP,
+                                                                  double* __restrict__ partials) {
+    __shared__ double red[WALL_NPART * (BF_THREADS / 32)];
+    const int side = blockIdx.x, t = threadIdx.x, n2 = n * n;
+    const int type = P.BCSides[2 * side];
+    double acc[WALL_NPART] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, -WALL_HUGE, WALL_HUGE};
+    if (type == 3 || type == 4 || type == 9) {
+        const Eos eos = P.eos;
+        for (int pq = t; pq < n2; pq += BF_THREADS) {
+            const int q = pq / n, p = pq - q * n;
+            const double* g = P.geo + (size_t)side * 10 * n2 + pq;
+            const double nv[3] = {g[0], g[n2], g[2 * n2]};
+            const double dA = wGP[p] * wGP[q] * g[9 * n2];
+            double U[5], Pr[6];
+#pragma unroll
+            for (int c = 0; c < 5; c++) U[c] = Um[((size_t)side * 5 + c) * n2 + pq];
+            cons_to_prim(Pr, U, eos);
+#pragma unroll
+            for (int d = 0; d < 3; d++) acc[d] += Pr[PRES] * nv[d] * dA;
+            const double locV = sqrt(Pr[VEL1] * Pr[VEL1] + Pr[VEL2] * Pr[VEL2] + Pr[VEL3] * Pr[VEL3]);
+            acc[6] += locV * dA;
+            acc[7] = fmax(acc[7], locV);
+            acc[8] = fmin(acc[8], locV);
+            if (P.parabolic) {
+                const double mu = viscosity(eos, Pr[TEMP]);
+                double G[3][3];  // G[i][d] = d v_i / d x_d
+#pragma unroll
+                for (int d = 0; d < 3; d++)
+#pragma unroll
+                    for (int i = 0; i < 3; i++) G[i][d] = P.gm[((size_t)side * 12 + d * 4 + i) * n2 + pq];
+                const double div = G[0][0] + G[1][1] + G[2][2];
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    double f = 0.0;
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        double tau = mu * (G[i][d] + G[d][i]);
+                        if (i == d) tau -= 2.0 / 3.0 * mu * div;
+                        f += tau * nv[d];
+                    }
+                    acc[3 + i] -= f * dA;  // force acting on the wall
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int x = 0; x < WALL_NPART; x++) {
+        double v = acc[x];
+        for (int o = 16; o > 0; o >>= 1) v = wall_combine(x, v, __shfl_xor_sync(0xffffffffu, v, o));
+        if ((t & 31) == 0) red[x * (BF_THREADS / 32) + (t >> 5)] = v;
+    }
+    __syncthreads();
+    if (t < WALL_NPART) {
+        double v = red[t * (BF_THREADS / 32)];
+        for (int w = 1; w < BF_THREADS / 32; w++) v = wall_combine(t, v, red[t * (BF_THREADS / 32) + w]);
+        partials[(size_t)side * WALL_NPART + t] = v;
+    }
+}
+// one CTA per boundary condition: combine the sides with BC(side) == iBC+1
+static __global__ void __launch_bounds__(BF_THREADS) k_wall_reduce(const double* __restrict__ partials, const int* __restrict__ BC, int nBCSides,
+                                                                   int nBCs, double* __restrict__ out) {
+    __shared__ double red[BF_THREADS];
+    const int iBC = blockIdx.x + 1;
+    for (int x = 0; x < WALL_NPART; x++) {
+        double v = x < 7 ? 0.0 : (x == 7 ? -WALL_HUGE : WALL_HUGE);
+        for (int sd = threadIdx.x; sd < nBCSides; sd += BF_THREADS)
+            if (BC[sd] == iBC) v = wall_combine(x, v, partials[(size_t)sd * WALL_NPART + x]);
+        red[threadIdx.x] = v;
+        __syncthreads();
+        for (int s = BF_THREADS / 2; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) red[threadIdx.x] = wall_combine(x, red[threadIdx.x], red[threadIdx.x + s]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[(size_t)x * nBCs + blockIdx.x] = red[0];
+        __syncthreads();
+    }
+}
+
 }  // namespace dgx

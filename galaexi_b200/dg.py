@@ -28,7 +28,7 @@ _ip = C.POINTER(C.c_int)
 
 EXPORTS = ("dgx_create", "dgx_destroy", "dgx_last_error", "dgx_set_state", "dgx_get_state", "dgx_get_ut",
            "dgx_get_gradients", "dgx_time_derivative", "dgx_rk_stage", "dgx_rk_step", "dgx_calc_timestep",
-           "dgx_analyze_tgv", "dgx_calc_bulk_velocity", "dgx_set_channel_forcing", "dgx_temp_filter_time_deriv", "dgx_get_baseflow", "dgx_sync", "dgx_run_steps", "dgx_profile_stage", "dgx_nccl_unique_id", "dgx_launch_count", "dgx_sizeof_config", "dgx_halo_plan")
+           "dgx_analyze_tgv", "dgx_calc_bulk_velocity", "dgx_calc_body_forces", "dgx_calc_wall_velocity", "dgx_set_channel_forcing", "dgx_temp_filter_time_deriv", "dgx_get_baseflow", "dgx_sync", "dgx_run_steps", "dgx_profile_stage", "dgx_nccl_unique_id", "dgx_launch_count", "dgx_sizeof_config", "dgx_halo_plan")
 
 
 class DgxConfig(C.Structure):
@@ -86,6 +86,8 @@ def load_library():
     lib.dgx_temp_filter_time_deriv.argtypes = [h, C.c_double, C.c_double]
     lib.dgx_get_baseflow.argtypes = [h, _dp]
     lib.dgx_calc_bulk_velocity.argtypes = [h, _dp, C.c_double, _dp]
+    lib.dgx_calc_body_forces.argtypes = [h, _dp, C.POINTER(C.c_int), C.c_int, _dp, _dp]
+    lib.dgx_calc_wall_velocity.argtypes = [h, _dp, C.POINTER(C.c_int), C.c_int, _dp, _dp, _dp, _dp]
     lib.dgx_set_channel_forcing.argtypes = [h, C.c_int, C.c_double, C.c_double]
     lib.dgx_sync.argtypes = [h]
     lib.dgx_run_steps.argtypes = [h, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]
@@ -286,6 +288,32 @@ class DGSolver:
         self._ck(self.lib.dgx_calc_bulk_velocity(self.h, w.ctypes.data_as(_dp), float(an.volume(self.case) if Vol is None else Vol),
                                                  C.byref(b)))
         return b.value
+
+    def CalcBodyForces(self):
+        """CalcBodyForces(BodyForce,Fp,Fv) (equations/navierstokes/calcbodyforces.f90:41-110) from the face data of the last
+        DGTimeDerivative_weakForm: arrays (nBCs,3) == Fortran (3,nBCs), zero for boundary conditions that are not walls."""
+        m = self.case.mesh
+        nBCs = int(m.BoundaryType.shape[0])
+        w = np.ascontiguousarray(self.case.basis.wGP, dtype=np.float64)
+        bc = np.ascontiguousarray(m.BC[:m.nBCSides] if m.nBCSides else np.zeros(1), dtype=np.int32)
+        Fp, Fv = np.zeros((nBCs, 3)), np.zeros((nBCs, 3))
+        self._ck(self.lib.dgx_calc_body_forces(self.h, w.ctypes.data_as(_dp), bc.ctypes.data_as(C.POINTER(C.c_int)), nBCs,
+                                               Fp.ctypes.data_as(_dp), Fv.ctypes.data_as(_dp)))
+        return Fp + Fv, Fp, Fv
+
+    def CalcWallVelocity(self, Surf: np.ndarray | None = None):
+        """CalcWallVelocity(maxV,minV,meanV) (analyze_equation.f90:435-499); Surf(nBCs): global surface per boundary condition
+        (default: integrated from this rank's SurfElem, i.e. single-rank)."""
+        from .host import analyze as an
+        m = self.case.mesh
+        nBCs = int(m.BoundaryType.shape[0])
+        w = np.ascontiguousarray(self.case.basis.wGP, dtype=np.float64)
+        bc = np.ascontiguousarray(m.BC[:m.nBCSides] if m.nBCSides else np.zeros(1), dtype=np.int32)
+        S = np.ascontiguousarray(an.bc_surfaces(self.case) if Surf is None else Surf, dtype=np.float64)
+        out = [np.zeros(nBCs) for _ in range(3)]
+        self._ck(self.lib.dgx_calc_wall_velocity(self.h, w.ctypes.data_as(_dp), bc.ctypes.data_as(C.POINTER(C.c_int)), nBCs,
+                                                 S.ctypes.data_as(_dp), *[o.ctypes.data_as(_dp) for o in out]))
+        return tuple(out)
 
     def set_channel_forcing(self, dpdx: float, BulkVel: float, on: bool = True):
         """Parameters of TestcaseSource (testcase/channel/testcase.f90:277-296)."""

@@ -25,3 +25,23 @@ def volume(case) -> float:
     w = case.basis.wGP
     W = w[:, None, None] * w[None, :, None] * w[None, None, :]
     return float(np.sum(W[None] / case.geo["sJ"]))
+
+
+def bc_surfaces(case) -> np.ndarray:
+    """Surf(nBCs) of this rank's sides (analyze.f90:168-194): sum wGPSurf SurfElem over the sides with AnalyzeSide = iBC;
+    the caller sums over the ranks. Boundary conditions without sides get HUGE (the reference's guard against 0-division)."""
+    m = case.mesh
+    w = case.basis.wGP
+    wS = w[:, None] * w[None, :]
+    nBCs = int(m.BoundaryType.shape[0])
+    S = np.zeros(nBCs)
+    has = np.zeros(nBCs, dtype=bool)
+    az = m.AnalyzeSide if m.AnalyzeSide is not None else np.concatenate([m.BC[:m.nBCSides], np.zeros(m.nSides - m.nBCSides, dtype=np.int64)])
+    for s in range(m.nSides):
+        b = int(az[s])
+        if b == 0:
+            continue
+        has[b - 1] = True
+        S[b - 1] += float(np.sum(wS * case.geo["SurfElem"][s]))
+    S[~has] = np.finfo(np.float64).max
+    return S

@@ -145,6 +145,22 @@ int dgx_analyze_tgv(dgx_handle *h, int NAnalyze, const double *Vdm_GaussN_NAnaly
 int dgx_calc_bulk_velocity(dgx_handle *h, const double *wGP, double Vol, double *BulkVel);
 int dgx_set_channel_forcing(dgx_handle *h, int on, double dpdx, double BulkVel);
 
+/* CalcBodyForces (equations/navierstokes/calcbodyforces.f90:41-110, called from AnalyzeEquation, analyze_equation.f90:190-221),
+ * on the device from the face states and lifted gradient traces of the most recent dgx_time_derivative (the reference calls
+ * DGTimeDerivative_weakForm before analysing, timedisc_func.f90:348): for every boundary condition iBC that is a wall (BC type
+ * 3, 4 or 9, analyze_equation.f90:113-121) Fp(:,iBC) = sum p n wGPSurf SurfElem and Fv(:,iBC) = -sum tau n wGPSurf SurfElem
+ * over its sides, summed over all ranks (every rank gets the result); zero for other boundary conditions.
+ *   wGP(0:N): 1-D weights of the solution nodes; BC(1:nBCSides): the mesh array BC (1-based index of the boundary condition
+ *   of every boundary side, mesh_vars.f90); Fp, Fv: (3,nBCs) column-major. BodyForce = Fp + Fv is left to the caller. */
+int dgx_calc_body_forces(dgx_handle *h, const double *wGP, const int *BC, int nBCs, double *Fp, double *Fv);
+
+/* CalcWallVelocity (equations/navierstokes/analyze_equation.f90:435-499), same data and arguments: per wall boundary condition
+ * the maximum, minimum and surface mean (sum |v| wGPSurf SurfElem / Surf(iBC)) of the velocity magnitude on its sides, reduced
+ * over all ranks. Surf(1:nBCs): the global surface of every boundary condition (analyze.f90:200-230). Boundary conditions
+ * without wall sides return the reference's initial values maxV = -1e14, minV = 1e14, meanV = 0. */
+int dgx_calc_wall_velocity(dgx_handle *h, const double *wGP, const int *BC, int nBCs, const double *Surf, double *maxV,
+                           double *minV, double *meanV);
+
 /* TempFilterTimeDeriv (sponge/pruettdamping.f90:69-92), called once per time step after TimeStep (timedisc_func.f90:357) when
  * SpongeBaseFlow = pruett: SpBaseFlow += (U - SpBaseFlow) dt / tempFilterWidth. dgx_get_baseflow downloads it (the reference
  * writes it to the *_BaseFlow_* file). */

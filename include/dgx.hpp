@@ -14,6 +14,7 @@
 //   TimeDisc: the time loop incl. UpdateTimeStep       timedisc/timedisc.f90:36-203, timedisc_func.f90:246-300   TimeDisc(t0, tEnd)
 //   AnalyzeTestcase (Taylor-Green vortex)              testcase/taylorgreenvortex/testcase.f90:283-515            AnalyzeTestcase(...)
 //   CalcForcing / TestcaseSource (channel)             testcase/channel/testcase.f90:241-296                     CalcForcing, SetChannelForcing
+//   CalcBodyForces(BodyForce,Fp,Fv)                    equations/navierstokes/calcbodyforces.f90:41-110          CalcBodyForces(...)
 //   Abort(__STAMP__, msg)                              globals/globals.f90:175-221 dgx::Abort (exception carrying dgx_last_error)
 #pragma once
 #include <functional>
@@ -89,6 +90,14 @@ class DG {
         double b = 0.0;
         ck(dgx_calc_bulk_velocity(h_, wGP, Vol, &b));
         return b;
+    }
+    // Fp, Fv, BodyForce: (3,nBCs) column-major; BC(1:nBCSides) the mesh array of 1-based boundary-condition indices
+    void CalcBodyForces(const double* wGP, const int* BC, int nBCs, double* BodyForce, double* Fp, double* Fv) {
+        ck(dgx_calc_body_forces(h_, wGP, BC, nBCs, Fp, Fv));
+        for (int i = 0; i < 3 * nBCs; i++) BodyForce[i] = Fv[i] + Fp[i];
+    }
+    void CalcWallVelocity(const double* wGP, const int* BC, int nBCs, const double* Surf, double* maxV, double* minV, double* meanV) {
+        ck(dgx_calc_wall_velocity(h_, wGP, BC, nBCs, Surf, maxV, minV, meanV));
     }
     void SetChannelForcing(double dpdx, double BulkVel, bool on = true) { ck(dgx_set_channel_forcing(h_, on ? 1 : 0, dpdx, BulkVel)); }
 

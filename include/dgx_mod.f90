@@ -92,6 +92,16 @@ INTERFACE
   INTEGER(C_INT) FUNCTION dgx_calc_bulk_velocity(h,wGP,Vol,BulkVel) BIND(C,NAME='dgx_calc_bulk_velocity')
     IMPORT; TYPE(C_PTR),VALUE :: h; REAL(C_DOUBLE),INTENT(IN) :: wGP(*); REAL(C_DOUBLE),VALUE :: Vol; REAL(C_DOUBLE),INTENT(OUT) :: BulkVel
   END FUNCTION
+  !> CalcBodyForces (equations/navierstokes/calcbodyforces.f90:41-110): Fp, Fv(3,nBCs) of the wall boundary conditions
+  INTEGER(C_INT) FUNCTION dgx_calc_body_forces(h,wGP,BC,nBCs,Fp,Fv) BIND(C,NAME='dgx_calc_body_forces')
+    IMPORT; TYPE(C_PTR),VALUE :: h; REAL(C_DOUBLE),INTENT(IN) :: wGP(*); INTEGER(C_INT),INTENT(IN) :: BC(*); INTEGER(C_INT),VALUE :: nBCs
+    REAL(C_DOUBLE),INTENT(OUT) :: Fp(3,*),Fv(3,*)
+  END FUNCTION
+  !> CalcWallVelocity (equations/navierstokes/analyze_equation.f90:435-499)
+  INTEGER(C_INT) FUNCTION dgx_calc_wall_velocity(h,wGP,BC,nBCs,Surf,maxV,minV,meanV) BIND(C,NAME='dgx_calc_wall_velocity')
+    IMPORT; TYPE(C_PTR),VALUE :: h; REAL(C_DOUBLE),INTENT(IN) :: wGP(*),Surf(*); INTEGER(C_INT),INTENT(IN) :: BC(*); INTEGER(C_INT),VALUE :: nBCs
+    REAL(C_DOUBLE),INTENT(OUT) :: maxV(*),minV(*),meanV(*)
+  END FUNCTION
   !> TempFilterTimeDeriv (sponge/pruettdamping.f90:69-92)
   INTEGER(C_INT) FUNCTION dgx_temp_filter_time_deriv(h,dt,tempFilterWidth) BIND(C,NAME='dgx_temp_filter_time_deriv')
     IMPORT; TYPE(C_PTR),VALUE :: h; REAL(C_DOUBLE),VALUE :: dt,tempFilterWidth

@@ -133,6 +133,18 @@ def main():
     dist.all_reduce(vol)
     diag = s.AnalyzeTestcase(Vol=float(vol.item())) if c.parabolic else None
     bulk = s.CalcForcing(Vol=float(vol.item()))
+    # wall diagnostics (sum / max / min over ranks) and the state file written by all ranks, each its own element range
+    surf = torch.tensor(np.where(an.bc_surfaces(c) > 1e300, 0.0, an.bc_surfaces(c)), dtype=torch.float64, device="cuda")
+    dist.all_reduce(surf)
+    surf = np.where(surf.cpu().numpy() > 0.0, surf.cpu().numpy(), np.finfo(np.float64).max)
+    s.DGTimeDerivative_weakForm(t)
+    forces = s.CalcBodyForces()
+    wallv = s.CalcWallVelocity(Surf=surf)
+    import tempfile
+    tmpd = [tempfile.mkdtemp() if rank == 0 else None]
+    dist.broadcast_object_list(tmpd, src=0)
+    t_mr = t
+    state_path = s.WriteState("mesh.h5", t_mr, t_mr + 1.0, "mr", out_dir=tmpd[0], dt=dt, barrier=dist.barrier)
     s.sync()
     outs = [None] * world
     dist.gather_object((c.mesh.offsetElem, Ut, U, dt), outs if rank == 0 else None, dst=0)
@@ -162,8 +174,21 @@ def main():
             s1.TimeStepByLSERKW2(k1 * dt_ref, dt_ref)   # the same two steps as the multi-rank run
         diag1 = s1.AnalyzeTestcase() if c1.parabolic else None
         bulk1 = s1.CalcForcing()
+        s1.DGTimeDerivative_weakForm(t)
+        forces1 = s1.CalcBodyForces()
+        wallv1 = s1.CalcWallVelocity()
+        fscale = max(float(np.abs(forces1[1]).max()), float(np.abs(forces1[2]).max()), 1e-300)
+        wall_err = max(float(np.abs(forces[1] - forces1[1]).max()) / fscale, float(np.abs(forces[2] - forces1[2]).max()) / fscale)
+        for a, b in zip(wallv, wallv1):
+            wall_err = max(wall_err, float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-30))))
+        from galaexi_b200.host import state_io
+        Ufile, tfile = state_io.restart(state_path, c1.N, c1.node_type)
+        info = state_io.read_state_attrs(state_path)
+        state_ok = bool(np.array_equal(Ufile, U_all) and tfile == t_mr and info["complete"] and info["nGlobalElems"] == c1.mesh.nElems)
         diag_err = float(np.max(np.abs(diag - diag1) / np.maximum(np.abs(diag1), 1e-3 * np.abs(diag1).max()))) if diag is not None else 0.0
-        res = dict(diag_rel=diag_err, bulk_rel=abs(bulk - bulk1) / max(abs(bulk1), 1.0),   # relative to the O(1) velocity scale (the TGV mean is zero)case=name, world=world, ut_rel_l2=cases.rel_l2(Ut_all, Ut_ref), u_rel_l2=cases.rel_l2(U_all, U_ref),
+        # bulk_rel is relative to the O(1) velocity scale (the TGV mean velocity is zero)
+        res = dict(wall_rel=wall_err, state_file_ok=state_ok, diag_rel=diag_err, bulk_rel=abs(bulk - bulk1) / max(abs(bulk1), 1.0), case=name, world=world,
+                   ut_rel_l2=cases.rel_l2(Ut_all, Ut_ref), u_rel_l2=cases.rel_l2(U_all, U_ref),
                    dt_rel=abs(outs[0][3] - dt_ref) / dt_ref, ut_vs_1gpu_maxabs=float(np.abs(Ut_all - Ut1).max()),
                    ut_scale=float(np.abs(Ut_ref).max()))
         s1.FinalizeDG()
@@ -173,7 +198,7 @@ def main():
     dist.destroy_process_group()
     if rank == 0:
         ok = (res["u_rel_l2"] <= 1e-10 and res["dt_rel"] <= 1e-13 and res["ut_vs_1gpu_maxabs"] <= 1e-9 * res["ut_scale"]
-              and res["diag_rel"] <= 1e-9 and res["bulk_rel"] <= 1e-10)
+              and res["diag_rel"] <= 1e-9 and res["bulk_rel"] <= 1e-10 and res["wall_rel"] <= 1e-10 and res["state_file_ok"])
         sys.exit(0 if ok else 3)
 
 

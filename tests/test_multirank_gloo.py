@@ -118,3 +118,53 @@ def test_ranks_reproduce_single_rank(name, world):
     assert cases.rel_l2(Ut, Ut_ref) <= 1e-12
     assert cases.rel_l2(U, o1.array("U")) <= 1e-12
     o1.close()
+
+
+def _state_worker(rank, world, port, out_dir, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from galaexi_b200.host import state_io
+        c, U0 = _build("cavity", world, rank)
+        ms = c.mesh
+        path = state_io.write_state(U0, c.N, c.node_type, "mr", "cavity4x4x4_mesh.h5", 0.125, 0.25, out_dir=out_dir,
+                                    elem_data={"myRank": float(rank)}, offsetElem=ms.offsetElem, nGlobalElems=ms.nGlobalElems,
+                                    rank=rank, barrier=dist.barrier)
+        dist.barrier()
+        # every rank restarts its own element range from the collectively written file (restart.f90: ReadArray with offsetElem)
+        U, t = state_io.restart(path, c.N, c.node_type, offsetElem=ms.offsetElem, nElems=ms.nElems, nGlobalElems=ms.nGlobalElems)
+        out = [None] * world
+        dist.gather_object((ms.offsetElem, ms.nElems, bool(np.array_equal(U, U0)), t, path), out if rank == 0 else None, dst=0)
+        if rank == 0:
+            q.put(out)
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_ranks_write_one_state_file_and_restart_from_it(tmp_path):
+    """WriteState on 3 ranks (GatheredWriteArray's role: every rank writes its contiguous element range, rank 0 the skeleton and
+    the closing TIME attribute) gives the file a single rank writes; each rank reads its own range back."""
+    from galaexi_b200.host import h5lite, state_io
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() * 11 + 77) % 300
+    procs = [ctx.Process(target=_state_worker, args=(r, world, port, str(tmp_path), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert all(o[2] for o in out) and all(o[3] == 0.125 for o in out)
+    assert sorted(o[0] for o in out) == [0, 22, 43] and sum(o[1] for o in out) == 64        # mesh_readin.f90:766-778: 22+21+21
+    c1, U1 = _build("cavity", 1, 0)
+    f = h5lite.read_state(out[0][4])
+    assert np.array_equal(f["DG_Solution"], U1)
+    info = state_io.read_state_attrs(out[0][4])
+    assert info["complete"] and info["nGlobalElems"] == 64 and info["Time"] == 0.125
+    ranks = f["ElemData"][:, 0]
+    assert np.array_equal(ranks, np.repeat([0.0, 1.0, 2.0], [22, 21, 21]))

@@ -127,6 +127,8 @@ struct dgx_handle {
     int nInner = 0, nBnd = 0;
     // RK
     std::vector<double> RKA, RKb, RKc;
+    std::vector<double> RKdelta, RKg1, RKg2, RKg3;  // three-register schemes (empty: Williamson 2N)
+    int rk3Stage = 0;                                // stage of the 3-register update rhs() applies (0: none)
     // MPI-like neighbour tables
     std::vector<int> NbProc, nMine, nYour, offMine, offYour;
     std::vector<HaloMsg> plan;
@@ -275,7 +277,12 @@ int rhs(dgx_handle* h, int mode, double t, double mRKA, double b_dt, StageTimes*
     P.UsNext = h->Uf[h->cur ^ 1][1];
     const bool multi = c.nRanks > 1 && !h->NbProc.empty();
     // CalcSource (dg.f90:418): the volume kernels store Ut (MODE 0), k_source_rk adds the source and does the stage update
-    const bool src = P.iniExactFunc == 4 || P.tcSource || P.spMat;
+    if (mode == 1 && h->rk3Stage > 0) {  // timestep.f90:168-186
+        const int i = h->rk3Stage - 1;
+        P.rk3 = i == 0 ? 1 : 2;
+        P.rk3Delta = h->RKdelta[i]; P.rk3G1 = h->RKg1[i]; P.rk3G2 = h->RKg2[i]; P.rk3G3 = h->RKg3[i];
+    }
+    const bool src = P.iniExactFunc == 4 || P.tcSource || P.spMat || P.rk3;
     const int vmode = src ? 0 : mode;
     auto mark = [&](void) { if (st) cudaEventRecord(st->ev[st->nev++], h->s); };
     mark();
@@ -531,6 +538,7 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
     P.MortarType = nullptr;
     P.xGP = nullptr; P.advVel1 = c.AdvVel[0]; P.iniExactFunc = 0;
     P.tcSource = 0; P.tcDpdx = 0.0; P.tcBulkVel = 0.0;
+    P.rk3 = 0; P.rk3Delta = P.rk3G1 = P.rk3G2 = P.rk3G3 = 0.0; P.rk3S2 = nullptr; P.rk3UPrev = nullptr;
     P.spMat = nullptr; P.spBase = nullptr;
     if (c.SpongeMat) {
         if (!c.SpBaseFlow) return fail(h, "SpongeMat given without SpBaseFlow");
@@ -591,6 +599,14 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
     h->RKA.assign(c.RKA, c.RKA + c.nRKStages);
     h->RKb.assign(c.RKb, c.RKb + c.nRKStages);
     h->RKc.assign(c.RKc, c.RKc + c.nRKStages);
+    if (c.RKdelta || c.RKg1 || c.RKg2 || c.RKg3) {  // TimeDiscType LSERKK3 (timedisc_vars.f90:140-141)
+        if (!(c.RKdelta && c.RKg1 && c.RKg2 && c.RKg3)) return fail(h, "three-register Runge-Kutta needs RKdelta, RKg1, RKg2 and RKg3");
+        h->RKdelta.assign(c.RKdelta, c.RKdelta + c.nRKStages);
+        h->RKg1.assign(c.RKg1, c.RKg1 + c.nRKStages);
+        h->RKg2.assign(c.RKg2, c.RKg2 + c.nRKStages);
+        h->RKg3.assign(c.RKg3, c.RKg3 + c.nRKStages);
+        if (dalloc(h, &h->P.rk3S2, 5 * h->nDOF()) || dalloc(h, &h->P.rk3UPrev, 5 * h->nDOF())) return 1;
+    }
     // ---- domain decomposition
     if (c.nRanks > 1) {
         for (int ib = 0; ib < c.nNbProcs; ib++) {
@@ -682,6 +698,12 @@ int dgx_time_derivative(dgx_handle* h, double t) {
 int dgx_rk_stage(dgx_handle* h, int iStage, double t, double dt) {
     CK(cudaSetDevice(h->cfg.device));
     if (iStage < 1 || iStage > h->cfg.nRKStages) return fail(h, "iStage out of range");
+    if (!h->RKg1.empty()) {  // TimeStepByLSERKK3 (timestep.f90:129-200)
+        h->rk3Stage = iStage;
+        const int rc = rhs(h, 1, t, 0.0, h->RKb[iStage - 1] * dt);
+        h->rk3Stage = 0;
+        return rc;
+    }
     const double mRKA = (iStage == 1) ? 0.0 : -1.0 * h->RKA[iStage - 1];
     return rhs(h, 1, t, mRKA, h->RKb[iStage - 1] * dt);  // t: the stage time (timestep.f90:86-93)
 }
@@ -874,7 +896,10 @@ int dgx_profile_stage(dgx_handle* h, double t, double dt, int cap, const char** 
     for (int i = 0; i < 8; i++) CK(cudaEventCreate(&st.ev[i]));
     const int stage = h->cfg.nRKStages > 1 ? 2 : 1;
     const double mRKA = (stage == 1) ? 0.0 : -1.0 * h->RKA[stage - 1];
-    if (rhs(h, 1, t, mRKA, h->RKb[stage - 1] * dt, &st)) return 1;
+    h->rk3Stage = h->RKg1.empty() ? 0 : stage;
+    const int rc = rhs(h, 1, t, mRKA, h->RKb[stage - 1] * dt, &st);
+    h->rk3Stage = 0;
+    if (rc) return 1;
     CK(cudaStreamSynchronize(h->s));
     static const char* nm[] = {"halo+lifting", "sideflux", "volsurf_rk"};
     int cnt = 0;

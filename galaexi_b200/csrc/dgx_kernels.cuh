@@ -73,6 +73,11 @@ struct KParams {
     // channel forcing (testcase/channel/testcase.f90:277-296 TestcaseSource)
     int tcSource;
     double tcDpdx, tcBulkVel;
+    // three-register low-storage Runge-Kutta (timestep.f90:129-200 TimeStepByLSERKK3): 0 off, 1 first stage, 2 later stage;
+    // registers S2 and UPrev [elem][5][n^3]
+    int rk3;
+    double rk3Delta, rk3G1, rk3G2, rk3G3;
+    double *rk3S2, *rk3UPrev;
     int flags;  // tuning switches (DGX_FLAGS): 1 lifting: L2 prefetch of own later-phase data; 2 lifting: L2 prefetch of the element
                 // a resident wave ahead; 4 / 8: the same two for k_volsurf2
 };
@@ -287,7 +292,8 @@ __global__ void __launch_bounds__(n* n* n) k_filter(const KParams P) {
     extract_faces<n, NT, 5>(b1, P.Um, P.Us, P.E2S + 18 * e, P.S2V2, sLm, sLp);
 }
 
-// Source term + (MODE 1) Williamson 2N update + next-stage face states, for runs with CalcSource (dg.f90:418): the volume
+// Source term + (MODE 1) Williamson 2N or Ketcheson 3-register update + next-stage face states, for runs with CalcSource
+// (dg.f90:418) or a 3-register scheme: the volume
 // kernels then run in MODE 0 and leave Ut = -sJ * (DG operator); here Ut += Ut_src (the reference adds Ut_src / sJ before
 // the Jacobian is applied, exactfunc.f90:1109), then vector.f90:163-183 and the face extraction of the fused epilogue.
 template <int n, int NT, int MODE>
@@ -333,11 +339,30 @@ __global__ void __launch_bounds__(n* n* n) k_source_rk(const KParams P, double t
         if (MODE == 0) {
             Utg[v * n3] = ut;
         } else {
-            double* ot = P.Ut_tmp + (size_t)e * 5 * n3 + tt;
             double* ou = P.U + (size_t)e * 5 * n3 + tt;
-            const double r = (mRKA == 0.0) ? ut : ot[v * n3] * mRKA + ut;
-            ot[v * n3] = r;
-            const double un = ou[v * n3] + r * b_dt;
+            double un;
+            if (P.rk3) {
+                // S1 == U, S2, S3 == UPrev (timestep.f90:176-185)
+                double* s2 = P.rk3S2 + (size_t)e * 5 * n3 + tt;
+                double* up = P.rk3UPrev + (size_t)e * 5 * n3 + tt;
+                const double u = ou[v * n3];
+                if (P.rk3 == 1) {
+                    up[v * n3] = u;
+                    s2[v * n3] = u;
+                    un = u;
+                } else {
+                    const double sn = s2[v * n3] + u * P.rk3Delta;
+                    s2[v * n3] = sn;
+                    un = u * P.rk3G1 + sn * P.rk3G2;
+                    un = un + up[v * n3] * P.rk3G3;
+                }
+                un = un + ut * b_dt;
+            } else {
+                double* ot = P.Ut_tmp + (size_t)e * 5 * n3 + tt;
+                const double r = (mRKA == 0.0) ? ut : ot[v * n3] * mRKA + ut;
+                ot[v * n3] = r;
+                un = ou[v * n3] + r * b_dt;
+            }
             ou[v * n3] = un;
             tile[v * n3 + tt] = un;
         }

@@ -54,6 +54,7 @@ class DgxConfig(C.Structure):
         + [("IniExactFunc", C.c_int), ("AdvVel", C.c_double * 3), ("Elem_xGP", _dp)]
         + [("doWeakLifting", C.c_int), ("doConservativeLifting", C.c_int)]
         + [("SpongeMat", _dp), ("SpBaseFlow", _dp)]
+        + [(k, _dp) for k in ("RKdelta", "RKg1", "RKg2", "RKg3")]
     )
 
 
@@ -179,6 +180,11 @@ class DGSolver:
         for nm in ("M_0_1", "M_0_2", "M_1_0", "M_2_0"):
             setattr(c, nm, k[nm].ctypes.data_as(_dp))
         c.doWeakLifting, c.doConservativeLifting = int(case.doWeakLifting), int(case.doConservativeLifting)
+        if getattr(td, "RKg1", None) is not None:   # three-register scheme (TimeStepByLSERKK3)
+            for nm in ("RKdelta", "RKg1", "RKg2", "RKg3"):
+                if getattr(td, nm) is not None:
+                    k[nm] = f64(getattr(td, nm))
+                    setattr(c, nm, k[nm].ctypes.data_as(_dp))
         if case.SpongeMat is not None:
             k["SpongeMat"], k["SpBaseFlow"] = f64(case.SpongeMat), f64(case.SpBaseFlow)
             c.SpongeMat, c.SpBaseFlow = k["SpongeMat"].ctypes.data_as(_dp), k["SpBaseFlow"].ctypes.data_as(_dp)
@@ -245,6 +251,11 @@ class DGSolver:
 
     def TimeStepByLSERKW2(self, t: float, dt: float):
         self._ck(self.lib.dgx_rk_step(self.h, float(t), float(dt)))
+
+    # the reference binds one of the two through the procedure pointer TimeStep (timedisc_func.f90:143-151); the library picks the
+    # update from the tables it was created with, so both names run dgx_rk_step
+    TimeStepByLSERKK3 = TimeStepByLSERKW2
+    TimeStep = TimeStepByLSERKW2
 
     def rk_stage(self, iStage: int, t: float, dt: float):
         self._ck(self.lib.dgx_rk_stage(self.h, int(iStage), float(t), float(dt)))

@@ -107,6 +107,10 @@ typedef struct dgx_config {
      * CalcSpongeRamp leaves it (:449-454), expanded to all elements (zero outside the SpongeMap), and the initial base flow
      * SpBaseFlow(PP_nVar,0:N,0:N,0:N,nElems) (InitSponge :203-243). NULL: no sponge. */
     const double *SpongeMat, *SpBaseFlow;
+    /* three-register low-storage Runge-Kutta, TimeDiscType LSERKK3 (timedisc_vars.f90:140-141, 464-760: ketchesonrk4-20,
+     * ketchesonrk4-18; stage update of TimeStepByLSERKK3, timestep.f90:129-200): RKdelta, RKg1, RKg2, RKg3 (1:nRKStages);
+     * RKb, RKc as above (RKc(1) = 0), RKA unused. All four NULL: Williamson 2N (TimeStepByLSERKW2). */
+    const double *RKdelta, *RKg1, *RKg2, *RKg3;
 } dgx_config;
 
 int dgx_create(dgx_handle **h, const dgx_config *cfg);

@@ -54,6 +54,8 @@ class DG {
 
     void DGTimeDerivative_weakForm(double t) { ck(dgx_time_derivative(h_, t)); }
     void TimeStepByLSERKW2(double t, double dt) { ck(dgx_rk_step(h_, t, dt)); }
+    // timestep.f90:129 -- the same entry point: the library applies the 3-register update when created with RKdelta/RKg1-3
+    void TimeStepByLSERKK3(double t, double dt) { ck(dgx_rk_step(h_, t, dt)); }
     double CalcTimeStep(int& errType) {
         double dt = 0.0;
         ck(dgx_calc_timestep(h_, &dt, &errType));

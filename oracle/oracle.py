@@ -228,11 +228,31 @@ class Oracle:
 
     def rk_step(self, t: float, dt: float):
         td = self.case.timedisc
+        if getattr(td, "kind", "LSERKW2") == "LSERKK3":
+            return self._rk_step_k3(t, dt)
         _d = self.prec.d
         A, b, c = (np.ascontiguousarray(x, dtype=self.prec.np) for x in (td.RKA, td.RKb, td.RKc))
         err = self.prec.lib().dgo_rk_step(self.h, float(t), float(dt), td.nRKStages, _d(A), _d(b), _d(c))
         if err:
             raise RuntimeError("oracle: unsupported boundary condition type")
+
+    def _rk_step_k3(self, t: float, dt: float):
+        """TimeStepByLSERKK3 (timedisc/timestep.f90:129-200): S1 == U, S2, S3 == UPrev; one operation per VAXPBY call."""
+        td = self.case.timedisc
+        U = self.array("U")
+        b_dt = td.RKb * dt
+        S2 = UPrev = None
+        for i in range(td.nRKStages):
+            tStage = t if i == 0 else t + td.RKc[i] * dt
+            Ut = self.time_derivative(tStage)
+            if i == 0:
+                UPrev = U.copy()
+                S2 = U.copy()
+            else:
+                S2 = S2 + U * td.RKdelta[i]
+                U[...] = U * td.RKg1[i] + S2 * td.RKg2[i]
+                U[...] = U + UPrev * td.RKg3[i]
+            U[...] = U + Ut * b_dt[i]
 
     def temp_filter_time_deriv(self, dt: float, tempFilterWidth: float):
         self.prec.lib().dgo_temp_filter_time_deriv(self.h, float(dt), float(tempFilterWidth))

@@ -614,6 +614,40 @@ def test_all_lserkw2_schemes(scheme):
     _compare_rhs_and_steps(c, U0, nsteps=2)
 
 
+# ---- the three-register schemes (TimeDiscType LSERKK3, timestep.f90:129-200) ----------------------------------------------------------
+@pytest.mark.parametrize("scheme,kw", [("ketchesonrk4-20", dict()), ("ketchesonrk4-18", dict()),
+                                       ("ketchesonrk4-18", dict(node_type="GAUSS", split=None)),
+                                       ("ketchesonrk4-20", dict(mesh="mortar"))])
+def test_lserkk3_schemes(scheme, kw):
+    """TimeStepByLSERKK3: registers S2 and UPrev, update coefficients RKdelta / RKg1 / RKg2 / RKg3. Two adaptive time steps (40 / 36
+    right-hand sides) vs the oracle, split-form GL, weak-form Gauss and a mortar mesh; dgx_rk_stage one by one equals dgx_rk_step."""
+    if kw.get("mesh") == "mortar":
+        c, U0 = cases.mortar_case("002", N=3, timedisc=scheme)
+    else:
+        c, U0 = cases.tgv_box_case(E=3, N=4, NGeo=2, deform=0.05, perturb=1e-3, timedisc=scheme, **kw)
+    td = c.timedisc
+    assert td.kind == "LSERKK3" and td.nRKStages == int(scheme[-2:])
+    _compare_rhs_and_steps(c, U0, nsteps=2)
+    s = _solver(c)
+    s.set_state(U0)
+    dt = s.CalcTimeStep()[0]
+    s.TimeStepByLSERKW2(0.0, dt)
+    U1 = s.get_state()
+    s.set_state(U0)
+    for i in range(1, td.nRKStages + 1):
+        s.rk_stage(i, 0.0 if i == 1 else td.RKc[i - 1] * dt, dt)
+    assert np.array_equal(s.get_state(), U1)
+    s.FinalizeDG()
+
+
+def test_lserkk3_needs_all_four_tables():
+    from galaexi_b200 import dg
+    c, _ = cases.tgv_box_case(E=2, N=2, timedisc="ketchesonrk4-18")
+    c.timedisc.RKg3 = None          # RKg1 given, another table missing -> dgx_create refuses
+    with pytest.raises(dg.DGError, match="needs RKdelta, RKg1, RKg2 and RKg3"):
+        dg.DGSolver(c)
+
+
 # ---- non-default lifting forms (lifting.f90:81-85) ----------------------------------------------------------------------------------
 @pytest.mark.parametrize("name,kw", [
     ("tgv_weak_gl", dict(E=3, N=4, NGeo=2, deform=0.05, perturb=1e-3, doWeakLifting=True)),

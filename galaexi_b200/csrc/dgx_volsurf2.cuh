@@ -35,8 +35,11 @@ struct TileV {
     }
 };
 
+#ifndef VS2_EPB6
+#define VS2_EPB6 2   // elements per CTA at n = 6 (tuning knob)
+#endif
 template <int n>
-constexpr int vs2_epb() { return (128 + n * n) / (2 * n * n) > 0 ? (128 + n * n) / (2 * n * n) : 1; }
+constexpr int vs2_epb() { return n == 6 ? VS2_EPB6 : ((128 + n * n) / (2 * n * n) > 0 ? (128 + n * n) / (2 * n * n) : 1); }
 template <int n>
 constexpr int vs2_threads() { return vs2_epb<n>() * 2 * n * n; }
 constexpr int VS2_SLOTS = 18;
@@ -45,7 +48,10 @@ constexpr int VS2_SLOTS = 18;
 #endif
 constexpr int VS2_CU = VS2_CROSS_UNROLL;
 #ifndef VS2_MIN_BLOCKS
-#define VS2_MIN_BLOCKS(n) ((n) >= 6 ? 3 : 4)
+#ifndef VS2_MINB6
+#define VS2_MINB6 3
+#endif
+#define VS2_MIN_BLOCKS(n) ((n) == 6 ? VS2_MINB6 : ((n) >= 6 ? 3 : 4))
 #endif
 template <int n>
 constexpr size_t vs2_smem_bytes() { return sizeof(double) * ((size_t)vs2_epb<n>() * VS2_SLOTS * TileV<n>::SLOT + 2 * n * n); }

@@ -66,10 +66,11 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} not found: build the CUDA extension first "
+    path = os.environ.get("DGX_LIB", LIB_PATH)    # A/B runs of tuning builds; the default is the in-tree library
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: build the CUDA extension first "
                            f"(python -c 'import __graft_entry__ as g; g.build()' or make -C galaexi_b200/csrc)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     h = C.c_void_p
     lib.dgx_create.argtypes = [C.POINTER(h), C.POINTER(DgxConfig)]
     lib.dgx_destroy.argtypes = [h]

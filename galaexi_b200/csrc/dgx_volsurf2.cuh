@@ -51,7 +51,10 @@ constexpr int VS2_CU = VS2_CROSS_UNROLL;
 #ifndef VS2_MINB6
 #define VS2_MINB6 3
 #endif
-#define VS2_MIN_BLOCKS(n) ((n) == 6 ? VS2_MINB6 : ((n) >= 6 ? 3 : 4))
+#ifndef VS2_MINB8
+#define VS2_MINB8 3
+#endif
+#define VS2_MIN_BLOCKS(n) ((n) == 6 ? VS2_MINB6 : ((n) == 8 ? VS2_MINB8 : ((n) >= 6 ? 3 : 4)))
 #endif
 template <int n>
 constexpr size_t vs2_smem_bytes() { return sizeof(double) * ((size_t)vs2_epb<n>() * VS2_SLOTS * TileV<n>::SLOT + 2 * n * n); }

@@ -40,8 +40,15 @@ struct TileV {
 #endif
 template <int n>
 constexpr int vs2_epb() { return n == 6 ? VS2_EPB6 : ((128 + n * n) / (2 * n * n) > 0 ? (128 + n * n) / (2 * n * n) : 1); }
+#ifndef VS2_PARTS8
+#define VS2_PARTS8 2   // threads per line at n = 8 (2: half line per thread, 4: quarter line per thread)
+#endif
 template <int n>
-constexpr int vs2_threads() { return vs2_epb<n>() * 2 * n * n; }
+constexpr int vs2_parts() { return n == 8 ? VS2_PARTS8 : 2; }
+template <int n>
+constexpr int vs2_seg() { return (n + vs2_parts<n>() - 1) / vs2_parts<n>(); }
+template <int n>
+constexpr int vs2_threads() { return vs2_epb<n>() * vs2_parts<n>() * n * n; }
 constexpr int VS2_SLOTS = 18;
 #ifndef VS2_CROSS_UNROLL
 #define VS2_CROSS_UNROLL 1
@@ -131,9 +138,9 @@ __device__ __forceinline__ void vs2_pair_acc(const double* __restrict__ a, const
 // One flux-differencing sweep of direction d for the half line (c1,c2,h): acc[m][v] = sum_l DVolSurf(l,a_m) F#(a_m,l)
 template <int n, int VAR>
 __device__ __forceinline__ void vs2_sweep(const double* __restrict__ R, const double* __restrict__ Mx, const double* __restrict__ Dv, int d,
-                                          int c1, int c2, int h, double (&acc)[(n + 1) / 2][5]) {
-    constexpr int SEG = (n + 1) / 2, SL = TileV<n>::SLOT;
-    const int a0 = h * SEG, cnt = h ? n - SEG : SEG;
+                                          int c1, int c2, int h, double (&acc)[vs2_seg<n>()][5]) {
+    constexpr int SEG = vs2_seg<n>(), SL = TileV<n>::SLOT;
+    const int a0 = h * SEG, cnt = (vs2_parts<n>() == 2) ? (h ? n - SEG : SEG) : ((n - a0 < SEG) ? n - a0 : SEG);
     const int f0 = h ? 0 : SEG, fcnt = n - cnt;
     double own[SEG][9];
 #pragma unroll
@@ -163,10 +170,10 @@ __device__ __forceinline__ void vs2_sweep(const double* __restrict__ R, const do
             }
         }
     }
-    // pairs with the other half of the line (rolled loop: code size)
+    // pairs with the rest of the line (rolled loop: code size)
 #pragma unroll(VS2_CU)
     for (int mf = 0; mf < fcnt; mf++) {
-        const int b = f0 + mf;
+        const int b = (vs2_parts<n>() == 2) ? f0 + mf : ((mf < a0) ? mf : mf + cnt);
         const int id = line_idx<n>(d, b, c1, c2);
         double ot[9];
 #pragma unroll
@@ -181,7 +188,7 @@ __device__ __forceinline__ void vs2_sweep(const double* __restrict__ R, const do
 
 template <int n, int MODE, int VAR>
 __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf2(const __grid_constant__ KParams P, int nWork, double mRKA, double b_dt, int lookahead) {
-    constexpr int n2 = n * n, n3 = n2 * n, SEG = (n + 1) / 2, SL = TileV<n>::SLOT, T = 2 * n2, EPB = vs2_epb<n>();
+    constexpr int n2 = n * n, n3 = n2 * n, SEG = vs2_seg<n>(), SL = TileV<n>::SLOT, T = vs2_parts<n>() * n2, EPB = vs2_epb<n>();
     extern __shared__ double smem[];
     const int le = threadIdx.x / T, tid = threadIdx.x - le * T;
     const int we = blockIdx.x * EPB + le;
@@ -193,7 +200,8 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
     for (int x = threadIdx.x; x < n2; x += EPB * T) { sDh[x] = P.D_Hat_T[x]; sDhx[(x / n) + n * (x % n)] = P.D_Hat_T[x]; }
     const int h = tid / n2, q = tid - h * n2;
     const int c1 = q % n, c2 = q / n;          // point-wise phases: (i,j) = (c1,c2), k in the own half of the zeta column
-    const int a0 = h * SEG, cnt = h ? n - SEG : SEG;
+    const int a0 = h * SEG, cnt = (vs2_parts<n>() == 2) ? (h ? n - SEG : SEG) : ((n - a0 < SEG) ? n - a0 : SEG);
+    const bool facer = (vs2_parts<n>() == 2) || h < 2;                  // P4: the threads of the first two parts take the - / + face of each axis
     const Eos eos = P.eos;
     const bool par = P.parabolic != 0;
     const double* __restrict__ Dh = P.D_Hat_T;  // uniform index only (constant bank)
@@ -362,6 +370,7 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
     if (live) {
 #pragma unroll
         for (int r = 0; r < 3; r++) {
+            if (!facer) break;
             const int loc = (r == 0) ? (h ? XI_PLUS : XI_MINUS) : ((r == 1) ? (h ? ETA_PLUS : ETA_MINUS) : (h ? ZETA_PLUS : ZETA_MINUS));
             const int side = __ldg(&e2s[0 + 3 * (loc - 1)]) - 1;
             const int flip = __ldg(&e2s[1 + 3 * (loc - 1)]);
@@ -389,7 +398,7 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
 #pragma unroll
     for (int r = 0; r < 3; r++) {
         __syncthreads();
-        if (live) {
+        if (live && facer) {
             S[10 * SL + idf[r]] += Ff[r][0] * wf[r];
 #pragma unroll
             for (int v = 0; v < 4; v++) S[v * SL + idf[r]] += Ff[r][1 + v] * wf[r];

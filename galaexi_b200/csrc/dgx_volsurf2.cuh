@@ -66,6 +66,59 @@ constexpr int VS2_CU = VS2_CROSS_UNROLL;
 template <int n>
 constexpr size_t vs2_smem_bytes() { return sizeof(double) * ((size_t)vs2_epb<n>() * VS2_SLOTS * TileV<n>::SLOT + 2 * n * n); }
 
+// Paired operand layout (n = 8, knob VS2_PAIRED8): the node record is kept as three double2 ([0,1] [2,3] [4,5]) and a metric
+// triple as double2 + double, so that a partner node costs 5 shared-memory load instructions (4 LDS.128 + 1 LDS.64) instead
+// of 9 LDS.64. Tile<8> puts (i xor k) into the low three bits of the node index: the eight lanes of a quarter warp hit eight
+// different 16-byte bank groups in the point-wise phases and in all three sweep directions.
+#ifndef VS2_PAIRED8
+#define VS2_PAIRED8 0
+#endif
+template <int n>
+constexpr bool vs2_paired() { return n == 8 && VS2_PAIRED8 != 0; }
+template <int n>
+__device__ __forceinline__ void vs2_rec_load(const double* __restrict__ R, int id, double* __restrict__ o) {
+    constexpr int SL = TileV<n>::SLOT;
+    if constexpr (vs2_paired<n>()) {
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+            const double2 x = reinterpret_cast<const double2*>(R + 2 * p * SL)[id];
+            o[2 * p] = x.x; o[2 * p + 1] = x.y;
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < 6; v++) o[v] = R[v * SL + id];
+    }
+}
+template <int n>
+__device__ __forceinline__ void vs2_rec_store(double* __restrict__ R, int id, const double* __restrict__ r) {
+    constexpr int SL = TileV<n>::SLOT;
+    if constexpr (vs2_paired<n>()) {
+#pragma unroll
+        for (int p = 0; p < 3; p++) reinterpret_cast<double2*>(R + 2 * p * SL)[id] = make_double2(r[2 * p], r[2 * p + 1]);
+    } else {
+#pragma unroll
+        for (int v = 0; v < 6; v++) R[v * SL + id] = r[v];
+    }
+}
+// address of component c of the metric triple stored at Mx for node id
+template <int n>
+__device__ __forceinline__ double* vs2_met_ptr(double* Mx, int id, int c) {
+    constexpr int SL = TileV<n>::SLOT;
+    if constexpr (vs2_paired<n>()) return c < 2 ? Mx + 2 * id + c : Mx + 2 * SL + id;
+    else return Mx + c * SL + id;
+}
+template <int n>
+__device__ __forceinline__ void vs2_met_load(const double* __restrict__ Mx, int id, double* __restrict__ o) {
+    constexpr int SL = TileV<n>::SLOT;
+    if constexpr (vs2_paired<n>()) {
+        const double2 x = reinterpret_cast<const double2*>(Mx)[id];
+        o[0] = x.x; o[1] = x.y; o[2] = Mx[2 * SL + id];
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; c++) o[c] = Mx[c * SL + id];
+    }
+}
+
 // tile index of position l on the line (c1,c2) of direction d (0 xi: (j,k), 1 eta: (i,k), 2 zeta: (i,j)); d is a run-time
 // value on purpose: one copy of the sweep code serves the three directions (the fully unrolled variant was
 // instruction-cache bound, profiles/r01e_volsurf2_full.md)
@@ -146,10 +199,8 @@ __device__ __forceinline__ void vs2_sweep(const double* __restrict__ R, const do
 #pragma unroll
     for (int m = 0; m < SEG; m++) {
         const int id = line_idx<n>(d, m < cnt ? a0 + m : a0, c1, c2);
-#pragma unroll
-        for (int v = 0; v < 6; v++) own[m][v] = R[v * SL + id];
-#pragma unroll
-        for (int c = 0; c < 3; c++) own[m][6 + c] = Mx[c * SL + id];
+        vs2_rec_load<n>(R, id, own[m]);
+        vs2_met_load<n>(Mx, id, own[m] + 6);
 #pragma unroll
         for (int v = 0; v < 5; v++) acc[m][v] = 0.0;
     }
@@ -176,10 +227,8 @@ __device__ __forceinline__ void vs2_sweep(const double* __restrict__ R, const do
         const int b = (vs2_parts<n>() == 2) ? f0 + mf : ((mf < a0) ? mf : mf + cnt);
         const int id = line_idx<n>(d, b, c1, c2);
         double ot[9];
-#pragma unroll
-        for (int v = 0; v < 6; v++) ot[v] = R[v * SL + id];
-#pragma unroll
-        for (int c = 0; c < 3; c++) ot[6 + c] = Mx[c * SL + id];
+        vs2_rec_load<n>(R, id, ot);
+        vs2_met_load<n>(Mx, id, ot + 6);
 #pragma unroll
         for (int m = 0; m < SEG; m++)
             if (m < cnt) vs2_pair_acc<VAR>(own[m], ot, Dv[b + n * (a0 + m)], acc[m]);
@@ -264,7 +313,7 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
                 cons_to_prim(Pr, Uc[m], eos);
                 vs2_record<VAR>(Rec[m], Uc[m], Pr);
 #pragma unroll
-                for (int c = 0; c < 6; c++) S[(12 + c) * SL + id] = M[m][c];  // M_xi -> slots 12..14, M_eta -> 15..17
+                for (int c = 0; c < 6; c++) *vs2_met_ptr<n>(S + (c < 3 ? 12 : 15) * SL, id, c % 3) = M[m][c];  // M_xi -> slots 12..14, M_eta -> 15..17
                 if (par) {
                     double gr[12];
 #pragma unroll
@@ -320,8 +369,7 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
 #pragma unroll
                 for (int v = 0; v < 4; v++) S[v * SL + id] = UtV[m][v];
                 S[10 * SL + id] = 0.0;
-#pragma unroll
-                for (int v = 0; v < 6; v++) S[(4 + v) * SL + id] = Rec[m][v];
+                vs2_rec_store<n>(S + 4 * SL, id, Rec[m]);
             }
         }
     }
@@ -337,10 +385,12 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
                 for (int m = 0; m < SEG; m++) {
                     if (m < cnt) {
                         const double* Mg = gM_e + (c1 + n * c2 + n2 * (a0 + m)) + (size_t)6 * n3;
-                        const unsigned dst = (unsigned)__cvta_generic_to_shared(S + 12 * SL + TileV<n>::idx(c1, c2, a0 + m));
+                        const int idm = TileV<n>::idx(c1, c2, a0 + m);
 #pragma unroll
-                        for (int c = 0; c < 3; c++)
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (unsigned)(c * SL * 8)), "l"(Mg + c * n3) : "memory");
+                        for (int c = 0; c < 3; c++) {
+                            const unsigned dst = (unsigned)__cvta_generic_to_shared(vs2_met_ptr<n>(S + 12 * SL, idm, c));
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(Mg + c * n3) : "memory");
+                        }
                     }
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");

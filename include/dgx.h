@@ -149,7 +149,7 @@ int dgx_analyze_tgv(dgx_handle *h, int NAnalyze, const double *Vdm_GaussN_NAnaly
 int dgx_calc_bulk_velocity(dgx_handle *h, const double *wGP, double Vol, double *BulkVel);
 int dgx_set_channel_forcing(dgx_handle *h, int on, double dpdx, double BulkVel);
 
-/* CalcBodyForces (equations/navierstokes/calcbodyforces.f90:41-110, called from AnalyzeEquation, analyze_equation.f90:190-221),
+/* CalcBodyForces (equations/navierstokes/calcbodyforces.f90:41-110, called from AnalyzeEquation, analyze_equation.f90:205),
  * on the device from the face states and lifted gradient traces of the most recent dgx_time_derivative (the reference calls
  * DGTimeDerivative_weakForm before analysing, timedisc_func.f90:348): for every boundary condition iBC that is a wall (BC type
  * 3, 4 or 9, analyze_equation.f90:113-121) Fp(:,iBC) = sum p n wGPSurf SurfElem and Fv(:,iBC) = -sum tau n wGPSurf SurfElem

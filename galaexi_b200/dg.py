@@ -162,7 +162,7 @@ class DGSolver:
         self._keep = k
         c = DgxConfig()
         c.N = case.N
-        c.nodeType = 2 if case.node_type == "GAUSS-LOBATTO" else 1
+        c.nodeType = getattr(case, "op_node_type", 2 if case.node_type == "GAUSS-LOBATTO" else 1)
         c.splitDG, c.riemann, c.parabolic, c.viscLaw = case.split, case.riemann, int(case.parabolic), case.eos.visc_law
         c.nElems, c.nSides, c.nBCSides = m.nElems, m.nSides, m.nBCSides
         c.firstInnerSide, c.lastInnerSide = m.firstInnerSide, m.lastInnerSide

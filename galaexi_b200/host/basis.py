@@ -286,14 +286,35 @@ class DGBasis:
     L_HatPlus: np.ndarray
 
 
-def init_dg_basis(N: int, node_type: str) -> DGBasis:
+def polynomial_mass_matrix(N: int, x: np.ndarray, w: np.ndarray, exact_mm: bool = False) -> tuple[np.ndarray, np.ndarray]:
+    """PolynomialMassMatrix (basis.f90:762-807): diag(wGP) and its inverse; with EXACT_MM on Gauss-Lobatto nodes the exact mass
+    matrix and its inverse as rank-one updates with the Legendre polynomial of degree N (Teukolsky, JCP 2015)."""
+    M = np.diag(np.asarray(w, dtype=np.float64))
+    Minv = np.diag(1.0 / np.asarray(w, dtype=np.float64))
+    if exact_mm:
+        hN = 2.0 / (2.0 * N + 1.0)
+        gammaN = 2.0 / N
+        norm = legendre_poly_and_deriv(N, 1.0)[0]
+        alpha = (hN - gammaN) / (gammaN ** 2 * norm ** 2)
+        beta = -(hN - gammaN) / (gammaN * hN * norm ** 2)
+        pN = np.array([legendre_poly_and_deriv(N, float(xi))[0] for xi in x])
+        for i in range(N + 1):
+            for j in range(N + 1):
+                M[i, j] = M[i, j] + alpha * w[i] * w[j] * pN[i] * pN[j]
+                Minv[i, j] = Minv[i, j] + beta * pN[i] * pN[j]
+    return M, Minv
+
+
+def init_dg_basis(N: int, node_type: str, exact_mm: bool = False) -> DGBasis:
+    """exact_mm: the build option FLEXI_EXACT_MASSMATRIX (-DEXACT_MM, src/CMakeLists.txt:150-156), Gauss-Lobatto nodes only."""
+    if exact_mm and node_type.strip().upper() != NODETYPE_GL:
+        raise ValueError("FLEXI_EXACT_MASSMATRIX only works on FLEXI_NODETYPE==GAUSS-LOBATTO points.")
     x, w, wb = get_nodes_and_weights(N, node_type)
     L_plus = lagrange_interpolation_polys(1.0, x, wb)
     L_minus = lagrange_interpolation_polys(-1.0, x, wb)
     D = polynomial_derivative_matrix(x)
     D_T = D.T.copy()
-    M = np.diag(w)
-    Minv = np.diag(1.0 / w)
+    M, Minv = polynomial_mass_matrix(N, x, w, exact_mm)
     # D_Hat = -MATMUL(Minv, MATMUL(TRANSPOSE(D), M))  (dg.f90:222)
     D_Hat = -(Minv @ (D.T @ M))
     D_Hat_T = D_Hat.T.copy()

@@ -53,6 +53,15 @@ class Case:
     doConservativeLifting: bool = False
     IniExactFunc: int = 0                            # selects the source term of CalcSource (exactfunc.f90:665-926): 4 or 0
     AdvVel: tuple = (0.0, 0.0, 0.0)
+    exact_mm: bool = False                           # FLEXI_EXACT_MASSMATRIX (GL nodes, exact mass matrix): see op_node_type
+
+    @property
+    def op_node_type(self) -> int:
+        """PP_NodeType as the operator applications see it (dgx_config.nodeType): 1 = interpolating prolongation and full
+        L_Hat surface integral, 2 = Gauss-Lobatto collocation short cuts. The reference compiles the first form for
+        `PP_NodeType==1 || (PP_NodeType==2 && defined(EXACT_MM))` (surfint.t90:74-104, lifting_br1.t90:238-270); on GL nodes
+        L_Minus / L_Plus are unit vectors, so the interpolating prolongation returns the boundary node values exactly."""
+        return 2 if (self.node_type == bs.NODETYPE_GL and not self.exact_mm) else 1
 
     @property
     def n(self):
@@ -71,7 +80,7 @@ def build_case(hopr: dict, N: int, node_type: str = bs.NODETYPE_GL, split: str |
                lifting: str = "br1", etaBR2: float = 2.0, etaBR2_wall: float = -1.0,
                FilterType: int | str = 0, NFilter: int | None = None, HestFilterParam=(36.0, 12.0, 1.0),
                IniExactFunc: int = 0, AdvVel=(0.0, 0.0, 0.0), doWeakLifting: bool = False,
-               doConservativeLifting: bool = False) -> Case:
+               doConservativeLifting: bool = False, exact_mm: bool = False) -> Case:
     eos = eos or eq.Eos()
     node_type = node_type.upper()
     split_id = SPLIT_IDS[split.upper() if isinstance(split, str) else split]
@@ -85,13 +94,15 @@ def build_case(hopr: dict, N: int, node_type: str = bs.NODETYPE_GL, split: str |
     if split_id < 0 and riem_id == 9:
         # riemann.f90:1236-1252: Riemann_FluxAverage only exists inside #ifdef SPLIT_DG
         raise ValueError("The flux-average Riemann solver is only available with SplitDG")
-    basis = bs.init_dg_basis(N, node_type)
+    if exact_mm and split_id >= 0:
+        raise ValueError("EXACT_MM with SplitDG is not built (the split-form kernels use the collocation surface integral)")
+    basis = bs.init_dg_basis(N, node_type, exact_mm)
     mesh = ms.prepare_mesh(hopr, nProcs=nProcs, myRank=myRank, useCurveds=useCurveds, user_bcs=user_bcs)
     geo = mt.calc_metrics(mesh, N, node_type, crossProductMetrics=crossProductMetrics, hopr=hopr)
     maps = mp.build_mappings(N)
     refprim = eq.init_bc_refstates(eq.refstate_prim(refstates, eos), mesh.BoundaryType)
     bcs = eq.bc_sides(mesh)
-    tdisc = td.set_timedisc(timedisc, N, node_type, CFLScale, DFLScale)
+    tdisc = td.set_timedisc(timedisc, N, node_type, CFLScale, DFLScale, exact_mm=exact_mm)
     lift_id = {"br1": 1, "br2": 2}[lifting.lower()]
     if etaBR2_wall == -1.0:
         etaBR2_wall = etaBR2   # lifting.f90:158-159
@@ -99,4 +110,4 @@ def build_case(hopr: dict, N: int, node_type: str = bs.NODETYPE_GL, split: str |
                 lift_id, float(etaBR2), float(etaBR2_wall), mo.init_mortar(N, node_type),
                 None if str(FilterType).lower() in ("0", "none") else fl.filter_matrix(N, node_type, FilterType, NFilter, HestFilterParam),
                 None, None, bool(doWeakLifting), bool(doConservativeLifting) and not bool(doWeakLifting),
-                int(IniExactFunc), tuple(float(v) for v in AdvVel))
+                int(IniExactFunc), tuple(float(v) for v in AdvVel), bool(exact_mm))

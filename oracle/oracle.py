@@ -151,7 +151,7 @@ class Oracle:
         c.nBCSides, c.firstInnerSide, c.lastInnerSide = m.nBCSides, m.firstInnerSide, m.lastInnerSide
         c.firstMPISide_MINE, c.lastMPISide_MINE = m.firstMPISide_MINE, m.lastMPISide_MINE
         c.firstMPISide_YOUR, c.lastMPISide_YOUR = m.firstMPISide_YOUR, m.lastMPISide_YOUR
-        c.nodeType = 2 if case.node_type == "GAUSS-LOBATTO" else 1
+        c.nodeType = getattr(case, "op_node_type", 2 if case.node_type == "GAUSS-LOBATTO" else 1)
         c.splitDG, c.riemann, c.parabolic = case.split, case.riemann, int(case.parabolic)
         c.viscLaw, c.nRefState = case.eos.visc_law, case.RefStatePrim.shape[0]
         for k, v in enumerate(case.eos.eos_vars()):

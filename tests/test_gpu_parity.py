@@ -768,3 +768,19 @@ def test_restart_from_reference_state_file_layout(tmp_path):
     _check_ut(c, ref, s.get_ut(), o.time_derivative(1.0).copy())
     o.close()
     s.FinalizeDG()
+
+
+# ---- FLEXI_EXACT_MASSMATRIX: Gauss-Lobatto nodes, exact mass matrix (kept last in this file: added after the round's GPU budget
+# was spent; the device side is the unchanged nodeType = 1 kernel path fed with the Gauss-Lobatto operator tables) ---------------------
+@pytest.mark.parametrize("name", ["tgv_curved_ns", "cavity_walls", "mortar_br2"])
+def test_exact_mass_matrix_gauss_lobatto(name):
+    if name == "tgv_curved_ns":
+        c, U0 = cases.tgv_box_case(E=3, N=4, NGeo=2, deform=0.05, perturb=1e-3, split=None, riemann="Roe", exact_mm=True)
+    elif name == "cavity_walls":
+        c, U0 = cases.cavity_case(N=3, node_type="GAUSS-LOBATTO", exact_mm=True)
+        x = c.geo["Elem_xGP"]
+        U0 = U0 * (1.0 + 0.01 * np.sin(5.0 * x[..., 0] + 1.0) * np.cos(3.0 * x[..., 1]) * np.sin(4.0 * x[..., 2] + 0.5))[..., None]
+    else:
+        c, U0 = cases.mortar_case("002", N=3, node_type="GAUSS-LOBATTO", split=None, riemann="Roe", lifting="br2", exact_mm=True)
+    assert c.op_node_type == 1 and c.node_type == "GAUSS-LOBATTO"
+    _compare_rhs_and_steps(c, U0)

@@ -76,6 +76,25 @@ def test_surf_int_unit_golden(goldens, node_type, key):
     o.close()
 
 
+def test_surf_int_unit_golden_exact_mass_matrix(goldens):
+    """unitTests/SurfInt_GL3D_EMM.bin: a Gauss-Lobatto build with FLEXI_EXACT_MASSMATRIX takes the full-L_Hat form of the surface
+    integral (surfint.t90:74-104: PP_NodeType==1 || (PP_NodeType==2 && defined(EXACT_MM))), which is how the host hands such a
+    case to the library and the oracle (Case.op_node_type == 1 on Gauss-Lobatto nodes)."""
+    emm = np.load(os.path.join(cases.GOLD, "unit_goldens_emm.npz"))["si_GL_EMM"]
+    c = unit_element_case(goldens, "GAUSS-LOBATTO")
+    c.op_node_type = 1
+    o = Oracle(c)
+    F = np.repeat(goldens["si_Flux"][..., None], 5, axis=-1).copy()
+    Ut = np.zeros((1, 10, 10, 10, 5))
+    d = o.prec.d
+    o.prec.lib().dgo_surf_int(o.h, 5, d(F), d(F), d(Ut))
+    for v in range(5):
+        assert almost_equal_abs_or_rel(Ut[0, ..., v], emm), v
+    o.close()
+    # and the collocation form (op_node_type 2) gives the other golden, not this one
+    assert np.abs(emm - goldens["si_GL"]).max() > 1.0
+
+
 def test_cavity_reference_state_oracle():
     """parabolic/cavity_3D: N=2 Gauss, NS + BR1, isothermal walls (4) + Dirichlet lid (2), 64 elements, t_end=1.
     The restatement reproduces the reference's DG_Solution (FLEXI/GALAEXI binary output) to abs 1e-12."""

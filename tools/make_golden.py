@@ -92,7 +92,15 @@ def main():
     st = h5lite.read_state(os.path.join(REF, "regressioncheck/checks/naca/3D/NACA0012_Re5000_AoA8_3D_Referenz_0000010.000000000.h5"))
     np.savez_compressed(os.path.join(OUT, "naca3d_state.npz"), DG_Solution=st["DG_Solution"], Time=st["attrs"]["Time"])
     state_h5_structs()
+    unit_goldens_emm()
     print("wrote", sorted(os.listdir(OUT)))
+
+
+def unit_goldens_emm():
+    """unitTests/SurfInt_GL3D_EMM.bin: the SurfInt unit test of a Gauss-Lobatto build with FLEXI_EXACT_MASSMATRIX (first record:
+    Ut of the DG element; the second record is the FV variant)."""
+    rr = fort_records(os.path.join(REF, "unitTests", "SurfInt_GL3D_EMM.bin"))
+    np.savez_compressed(os.path.join(OUT, "unit_goldens_emm.npz"), si_GL_EMM=np.frombuffer(rr[0], "<f8").reshape(10, 10, 10))
 
 
 def state_h5_structs():

@@ -301,6 +301,12 @@ class DGSolver:
                                                  C.byref(b)))
         return b.value
 
+    def CalcErrorNorms(self, Time: float, exact, NAnalyze: int | None = None, Vol: float | None = None, reduce=None):
+        """CalcErrorNorms(Time,L_2_Error,L_Inf_Error) (analyze.f90:383-470) on the downloaded state; ``exact(x, t)`` plays
+        ExactFunc(AnalyzeExactFunc, ...). Host arithmetic like the reference (it analyses the host copy U = d_U)."""
+        from .host import analyze as an
+        return an.calc_error_norms(self.case, self.get_state(), Time, exact, NAnalyze, Vol, reduce)
+
     def CalcBodyForces(self):
         """CalcBodyForces(BodyForce,Fp,Fv) (equations/navierstokes/calcbodyforces.f90:41-110) from the face data of the last
         DGTimeDerivative_weakForm: arrays (nBCs,3) == Fortran (3,nBCs), zero for boundary conditions that are not walls."""

@@ -45,3 +45,26 @@ def bc_surfaces(case) -> np.ndarray:
         S[b - 1] += float(np.sum(wS * case.geo["SurfElem"][s]))
     S[~has] = np.finfo(np.float64).max
     return S
+
+
+def calc_error_norms(case, U: np.ndarray, t: float, exact, NAnalyze: int | None = None, Vol: float | None = None,
+                     reduce=None) -> tuple[np.ndarray, np.ndarray]:
+    """CalcErrorNorms(Time,L_2_Error,L_Inf_Error) (analyze.f90:383-470): the solution U [e,k,j,i,var], the node coordinates and
+    the Jacobian 1/sJ are interpolated to the NAnalyze Gauss-Lobatto points, ``exact(x, t)`` (ExactFunc with AnalyzeExactFunc) is
+    evaluated there; L2 = sqrt(sum (U - U_exact)^2 wGPVolAnalyze J / Vol), Linf = max |U - U_exact|, per variable.
+    ``reduce(sum_array, max_array)`` combines the partial results of several ranks (MPI_REDUCE SUM / MAX, :456-464)."""
+    NA, V, wA = init_analyze_basis(case.N, case.node_type, NAnalyze)
+
+    def up(X):
+        Y = np.einsum("Ii,ekjic->ekjIc", V, X)
+        Y = np.einsum("Jj,ekjIc->ekJIc", V, Y)
+        return np.einsum("Kk,ekJIc->eKJIc", V, Y)
+    Ua, xa, Ja = up(U), up(case.geo["Elem_xGP"]), up((1.0 / case.geo["sJ"])[..., None])[..., 0]
+    w3 = wA[:, None, None] * wA[None, :, None] * wA[None, None, :]
+    d = Ua - exact(xa, t)
+    l2 = np.sum((w3[None] * Ja)[..., None] * d * d, axis=(0, 1, 2, 3))
+    linf = np.abs(d).max(axis=(0, 1, 2, 3)) if d.size else np.full(U.shape[-1], -1.0e10)
+    vol = volume(case) if Vol is None else Vol
+    if reduce is not None:
+        l2, linf = reduce(l2, linf)
+    return np.sqrt(l2 / vol), linf

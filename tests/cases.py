@@ -162,18 +162,8 @@ def manufactured_case(mesh="cart_periodic_004", N=3, nProcs=1, myRank=0, **kw):
 
 def l2_error(c, U, t, NAnalyze=None, exact=None):
     """CalcErrorNorms (analyze/analyze.f90:383-470): L2 error against the exact function on the analysis nodes."""
-    exact = exact or exact_sine
     from galaexi_b200.host import analyze as an
-    NA, V, wA = an.init_analyze_basis(c.N, c.node_type, NAnalyze)
-
-    def up(X):
-        Y = np.einsum("Ii,ekjic->ekjIc", V, X)
-        Y = np.einsum("Jj,ekjIc->ekJIc", V, Y)
-        return np.einsum("Kk,ekJIc->eKJIc", V, Y)
-    Ua, xa, Ja = up(U), up(c.geo["Elem_xGP"]), up((1.0 / c.geo["sJ"])[..., None])[..., 0]
-    w3 = wA[:, None, None] * wA[None, :, None] * wA[None, None, :]
-    d = Ua - exact(xa, t)
-    return np.sqrt(np.sum((w3[None] * Ja)[..., None] * d * d, axis=(0, 1, 2, 3)) / an.volume(c))
+    return an.calc_error_norms(c, U, t, exact or exact_sine, NAnalyze)[0]
 
 
 def naca_regression_case(nProcs=1, myRank=0):

@@ -249,3 +249,31 @@ def test_oracle_filter_is_the_pinned_change_basis():
     ref = mt.change_basis_volume(c.FilterMat, U0)
     assert np.abs(o.array("U") - ref).max() <= 1e-13 * np.abs(ref).max()
     o.close()
+
+
+def test_calc_error_norms_reference_norm_of_resting_cavity():
+    """CalcErrorNorms (analyze.f90:383-470): exact for polynomial data, zero for the exact function itself, and the L2 / Linf
+    pair of a known perturbation; Vol and the analysis quadrature integrate the deformed box exactly."""
+    import cases
+    from galaexi_b200.host import analyze as an
+    c, _ = cases.tgv_box_case(E=2, N=4, NGeo=2, deform=0.05, split=None, riemann="Roe")
+    assert abs(an.volume(c) - (2.0 * np.pi) ** 3) < 1e-10 * (2.0 * np.pi) ** 3
+    f = lambda x, t: np.stack([1.0 + 0.1 * x[..., 0] * t, x[..., 1] ** 2, x[..., 2], 0.0 * x[..., 0], 2.0 + x[..., 0] * x[..., 1]], axis=-1)
+    U = f(c.geo["Elem_xGP"], 0.7)
+    L2, Linf = an.calc_error_norms(c, U, 0.7, f)
+    assert np.all(L2 < 1e-11) and np.all(Linf < 1e-11)
+    # constant offset d in one variable: L2 = |d| (sqrt(d^2 Vol / Vol)), Linf = |d|
+    U2 = U.copy(); U2[..., 2] += 0.25
+    L2, Linf = an.calc_error_norms(c, U2, 0.7, f)
+    assert abs(L2[2] - 0.25) < 1e-10 and abs(Linf[2] - 0.25) < 1e-12 and L2[0] < 1e-11
+    # two "ranks": partial sums reduced like MPI_REDUCE(SUM) / (MAX) give the single-rank numbers
+    import copy
+    halves = []
+    for sl in (slice(0, 4), slice(4, 8)):
+        ch = copy.copy(c)
+        ch.geo = {k: (v[sl] if k in ("Elem_xGP", "sJ") else v) for k, v in c.geo.items()}
+        halves.append((ch, U2[sl]))
+    parts = [an.calc_error_norms(ch, Uh, 0.7, f, Vol=1.0) for ch, Uh in halves]
+    l2sum = sum(p[0] ** 2 for p in parts)
+    assert np.allclose(np.sqrt(l2sum / an.volume(c)), L2, rtol=1e-12, atol=1e-14)
+    assert np.allclose(np.maximum(parts[0][1], parts[1][1]), Linf, rtol=0, atol=1e-15)

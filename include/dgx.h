@@ -80,7 +80,7 @@ typedef struct dgx_config {
     const char *ncclUniqueId;        /* 128 bytes from ncclGetUniqueId on rank 0 (broadcast by the host), or NULL */
     int device;                      /* CUDA device ordinal for this rank */
     /* lifting variant (PP_Lifting, src/CMakeLists.txt:161-183): 0/1 BR1 (the only one GALAEXI builds), 2 BR2 (host FLEXI
-     * code, dg/lifting/lifting_br2.t90:43-313) with the penalties etaBR2 / etaBR2_wall (lifting.f90:86-91) */
+     * code, dg/lifting/lifting_br2.t90:43-311) with the penalties etaBR2 / etaBR2_wall (lifting.f90:86-91) */
     int lifting;
     double etaBR2, etaBR2_wall;
     /* non-conforming interfaces (host FLEXI code src/mortar/; GALAEXI aborts on them, mesh/mesh.f90:140-143):
@@ -107,7 +107,7 @@ typedef struct dgx_config {
      * CalcSpongeRamp leaves it (:449-454), expanded to all elements (zero outside the SpongeMap), and the initial base flow
      * SpBaseFlow(PP_nVar,0:N,0:N,0:N,nElems) (InitSponge :203-243). NULL: no sponge. */
     const double *SpongeMat, *SpBaseFlow;
-    /* three-register low-storage Runge-Kutta, TimeDiscType LSERKK3 (timedisc_vars.f90:140-141, 464-760: ketchesonrk4-20,
+    /* three-register low-storage Runge-Kutta, TimeDiscType LSERKK3 (timedisc_vars.f90:140-141, 464-773: ketchesonrk4-20,
      * ketchesonrk4-18; stage update of TimeStepByLSERKK3, timestep.f90:129-200): RKdelta, RKg1, RKg2, RKg3 (1:nRKStages);
      * RKb, RKc as above (RKc(1) = 0), RKA unused. All four NULL: Williamson 2N (TimeStepByLSERKW2). */
     const double *RKdelta, *RKg1, *RKg2, *RKg3;

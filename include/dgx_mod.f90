@@ -41,7 +41,7 @@ TYPE, BIND(C), PUBLIC :: dgx_config
   TYPE(C_PTR)    :: Elem_xGP
   INTEGER(C_INT) :: doWeakLifting, doConservativeLifting   ! lifting.f90:139-141
   TYPE(C_PTR)    :: SpongeMat, SpBaseFlow                  ! sponge.f90 (SpongeMat expanded to all elements), C_NULL_PTR: no sponge
-  TYPE(C_PTR)    :: RKdelta, RKg1, RKg2, RKg3              ! TimeDiscType LSERKK3 (timedisc_vars.f90:464-760), C_NULL_PTR: LSERKW2
+  TYPE(C_PTR)    :: RKdelta, RKg1, RKg2, RKg3              ! TimeDiscType LSERKK3 (timedisc_vars.f90:464-773), C_NULL_PTR: LSERKW2
 END TYPE dgx_config
 
 TYPE(C_PTR), PUBLIC, SAVE :: dgx = C_NULL_PTR   !< the library handle (one per rank)

@@ -1036,7 +1036,7 @@ static inline void s2v3(const dgo *s, int l, int p, int q, int flip, int loc, in
     }
 }
 
-/* lifting_br2.t90:193-313 Lifting_SurfInt_BR2 for one gradient direction: slave sides, then master sides */
+/* lifting_br2.t90:193-311 Lifting_SurfInt_BR2 for one gradient direction: slave sides, then master sides */
 static void lifting_surfint_br2(dgo *s, const double *Flux, double *gradU, double *gm, double *gs)
 {
     const dgo_config *c = &s->c;

@@ -148,7 +148,7 @@ def test_br2_volume_gradients_equal_br1(builder):
 
 
 def test_br2_trace_is_local_gradient_plus_eta_times_face_lift():
-    """One-sided check of lifting_br2.t90:193-313 on Gauss-Lobatto nodes: trace = local (D U) gradient + eta * sJ *
+    """One-sided check of lifting_br2.t90:193-311 on Gauss-Lobatto nodes: trace = local (D U) gradient + eta * sJ *
     Flux * L_HatMinus(0), so (trace(eta=3) - trace(eta=1)) = 2 * (trace(eta=2) - trace(eta=1))."""
     tr = {}
     for eta in (1.0, 2.0, 3.0):

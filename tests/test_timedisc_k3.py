@@ -1,4 +1,4 @@
-"""Three-register low-storage Runge-Kutta (TimeDiscType LSERKK3: timedisc_vars.f90:464-760, timestep.f90:129-200).
+"""Three-register low-storage Runge-Kutta (TimeDiscType LSERKK3: timedisc_vars.f90:464-773, timestep.f90:129-200).
 
 No reference golden exists for these schemes beyond the free-stream criterion of regressioncheck/checks/timedisc/freestream_3D
 (analyze_L2 = 1e-1), so the transcribed tables are pinned by their design properties: temporal order of accuracy on a

@@ -318,3 +318,28 @@ def test_writer_many_datasets_and_types(tmp_path):
     assert np.array_equal(f.dataset("ints"), np.arange(12).reshape(3, 4)) and f.dataset("ints").dtype == np.int32
     assert list(f.dataset("names")) == [b"BC_wall ", b"BC_inlet"]
     assert int(f.attrs()["nElems"][0]) == 7 and f.attrs("d03")["unit"][0] == b"m"
+
+
+REF = "/root/reference/regressioncheck/checks"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+@pytest.mark.parametrize("rel,N,nt,nE,t", [("parabolic/cavity_3D/reggie_cavity_Re100_State_0000001.000000000.h5", 2, "GAUSS", 64, 1.0),
+                                            ("naca/3D/NACA0012_Re5000_AoA8_3D_Referenz_0000010.000000000.h5", 3, "GAUSS", 652, 10.0),
+                                            ("h5diff/cavity/cavity_reference_State_0000000.000200000.h5", 3, "GAUSS", 36, 2e-4)])
+def test_restart_reads_files_written_by_libhdf5(rel, N, nt, nE, t):
+    """InitRestart + Restart on the reference's own state files (written by libhdf5 through FLEXI): attributes, element ranges of
+    two 'ranks', and interpolation to another degree all work on the library's container layout (object-header continuation
+    blocks, 4 096-byte userblock)."""
+    path = os.path.join(REF, rel)
+    info = state_io.read_state_attrs(path)
+    assert (info["N"], info["NodeType"], info["nGlobalElems"], info["Time"], info["complete"]) == (N, nt, nE, t, True)
+    U, tr = state_io.restart(path, N, nt, nGlobalElems=nE)
+    assert tr == t and U.shape == (nE, N + 1, N + 1, N + 1, 5) and np.all(U[..., 0] > 0)
+    h = nE // 2
+    Ua, _ = state_io.restart(path, N, nt, offsetElem=0, nElems=h)
+    Ub, _ = state_io.restart(path, N, nt, offsetElem=h, nElems=nE - h)
+    assert np.array_equal(np.concatenate([Ua, Ub]), U)
+    Uup, _ = state_io.restart(path, N + 2, "GAUSS-LOBATTO")
+    back = metrics.change_basis_volume(bs.get_vandermonde(N + 2, "GAUSS-LOBATTO", N, nt, modal=True), Uup)
+    assert np.abs(back - U).max() <= 1e-11 * np.abs(U).max()

@@ -5,6 +5,8 @@ Criterion of the reference's unit tests: ALMOSTEQUALABSORREL(x, ref, 100*PP_Real
 PP_RealTolerance = EPSILON(1.0D0) (src/flexi.h:66-68): |x-ref| <= tol  or  |x-ref| <= tol*max(|x|,|ref|).
 Integer tables are compared bit-exactly.
 """
+import os
+
 import numpy as np
 import pytest
 

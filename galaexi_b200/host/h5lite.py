@@ -223,6 +223,10 @@ def read_hopr_mesh(path: str) -> dict:
         BCType=f.dataset("BCType").astype(np.int32),
         isMortarMesh=int(a["isMortarMesh"].ravel()[0]) if "isMortarMesh" in a else 0,
     )
+    if out["isMortarMesh"] and "TreeCoords" in f.objects:
+        # octree data of non-conforming meshes (mesh_readin.f90:515-560): kept so that the mesh can be written again
+        out.update(NgeoTree=int(a["NgeoTree"].ravel()[0]), nTrees=int(a["nTrees"].ravel()[0]), xiMinMax=f.dataset("xiMinMax"),
+                   ElemToTree=f.dataset("ElemToTree"), TreeCoords=f.dataset("TreeCoords"))
     return out
 
 

@@ -250,3 +250,59 @@ class _Reserved:
     def __init__(self, shape, dtype):
         self.shape, self.dtype = shape, dtype
         self.nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+
+
+def write_hopr_mesh(path: str, hopr: dict):
+    """A mesh in the HOPR file layout the reference reads (mesh/mesh_readin.f90:33-50, 100-160, 280-320, 470-560, 845-855):
+    attributes Version, Ngeo, nElems, nSides, nNodes, nUniqueSides, nUniqueNodes, nBCs; data sets BCNames, BCType, ElemInfo,
+    SideInfo, NodeCoords, GlobalNodeIDs, ElemBarycenters, ElemWeight, ElemCounter and, for structured meshes, Elem_IJK /
+    nElems_IJK. ``hopr`` is the dict of read_hopr_mesh / make_box_mesh (arrays in file order). The reference itself reads only
+    Ngeo, BCNames, BCType, ElemInfo, SideInfo, NodeCoords (and the optional tree / IJK data); the rest is written for the posti
+    tools and HOPR's own consistency."""
+    ei = np.asarray(hopr["ElemInfo"], dtype=np.int32)
+    si = np.asarray(hopr["SideInfo"], dtype=np.int32)
+    nc = np.asarray(hopr["NodeCoords"], dtype=np.float64)
+    NGeo = int(hopr["NGeo"])
+    nE, nn = ei.shape[0], (NGeo + 1) ** 3
+    if nc.shape != (nE * nn, 3):
+        raise ValueError("NodeCoords does not hold (NGeo+1)^3 nodes per element")
+    w = H5Writer()
+    gid = hopr.get("GlobalNodeIDs")
+    if gid is None:
+        # unique nodes: coordinates equal up to a tolerance relative to the mesh extent, numbered in order of first appearance
+        ext = float(np.max(nc.max(axis=0) - nc.min(axis=0))) or 1.0
+        key = np.round((nc - nc.min(axis=0)) / (ext * 1e-9)).astype(np.int64)
+        _, first, inv = np.unique(key, axis=0, return_index=True, return_inverse=True)
+        order = np.argsort(np.argsort(first))
+        gid = (order[inv.ravel()] + 1).astype(np.int32)
+    gid = np.asarray(gid, dtype=np.int32)
+    ind = si[:, 1]
+    for k, v in (("Version", 1.0), ("Ngeo", NGeo), ("nElems", nE), ("nSides", si.shape[0]), ("nNodes", nc.shape[0]),
+                 ("nUniqueSides", int(np.count_nonzero(ind > 0)) if np.any(ind < 0) else len(np.unique(np.abs(ind)))),
+                 ("nUniqueNodes", int(gid.max()) if gid.size else 0), ("nBCs", len(hopr["BCNames"]))):
+        w.set_attr(k, v)
+    if int(hopr.get("isMortarMesh", 0)):
+        if hopr.get("TreeCoords") is None:
+            raise ValueError("a non-conforming (mortar) mesh needs its octree data: NgeoTree, nTrees, xiMinMax, ElemToTree, TreeCoords")
+        w.set_attr("isMortarMesh", 1)
+        w.set_attr("NgeoTree", int(hopr["NgeoTree"]))
+        w.set_attr("nTrees", int(hopr["nTrees"]))
+        w.create_dataset("xiMinMax", np.asarray(hopr["xiMinMax"], dtype=np.float64))
+        w.create_dataset("ElemToTree", np.asarray(hopr["ElemToTree"], dtype=np.int32))
+        w.create_dataset("TreeCoords", np.asarray(hopr["TreeCoords"], dtype=np.float64))
+    w.create_dataset("BCNames", np.array([fortran_str(str(s)) for s in hopr["BCNames"]], dtype="S255"))
+    w.create_dataset("BCType", np.asarray(hopr["BCType"], dtype=np.int32))
+    w.create_dataset("ElemInfo", ei)
+    w.create_dataset("SideInfo", si)
+    w.create_dataset("NodeCoords", nc)
+    w.create_dataset("GlobalNodeIDs", gid)
+    corners = nc.reshape(nE, NGeo + 1, NGeo + 1, NGeo + 1, 3)[:, ::NGeo, ::NGeo, ::NGeo].reshape(nE, 8, 3)
+    w.create_dataset("ElemBarycenters", corners.mean(axis=1))     # HOPR: mean of the eight corner nodes
+    w.create_dataset("ElemWeight", np.ones(nE))
+    types = np.array([104, 204, 105, 115, 205, 106, 116, 206, 108, 118, 208], dtype=np.int32)
+    cnt = np.array([int(np.count_nonzero(ei[:, 0] == t)) for t in types], dtype=np.int32)
+    w.create_dataset("ElemCounter", np.stack([types, cnt], axis=1))
+    if hopr.get("Elem_IJK") is not None and hopr.get("nElems_IJK") is not None:
+        w.create_dataset("Elem_IJK", np.asarray(hopr["Elem_IJK"], dtype=np.int32))
+        w.create_dataset("nElems_IJK", np.asarray(hopr["nElems_IJK"], dtype=np.int32))
+    w.write(path)

@@ -343,3 +343,57 @@ def test_restart_reads_files_written_by_libhdf5(rel, N, nt, nE, t):
     Uup, _ = state_io.restart(path, N + 2, "GAUSS-LOBATTO")
     back = metrics.change_basis_volume(bs.get_vandermonde(N + 2, "GAUSS-LOBATTO", N, nt, modal=True), Uup)
     assert np.abs(back - U).max() <= 1e-11 * np.abs(U).max()
+
+
+def test_hopr_mesh_writer_round_trip_of_generated_meshes(tmp_path):
+    """write_hopr_mesh: a generated (curved, periodic / wall) box in the HOPR layout reads back to the same arrays and builds the
+    same case tables; unique node / side counts as HOPR counts them."""
+    from galaexi_b200.host import mesh as ms
+    h = ms.make_box_mesh((3, 2, 2), NGeo=2, deform=0.05, bctype=["periodic", (4, 1), "periodic", (4, 1), "periodic", "periodic"])
+    p = str(tmp_path / "box_mesh.h5")
+    h5write.write_hopr_mesh(p, h)
+    g = h5lite.read_hopr_mesh(p)
+    for k in ("ElemInfo", "SideInfo", "NodeCoords", "BCType"):
+        assert np.array_equal(g[k], h[k]), k
+    assert g["NGeo"] == 2 and g["BCNames"] == [str(s) for s in h["BCNames"]]
+    f = h5lite.H5File(p)
+    a = f.attrs()
+    assert int(a["nElems"][0]) == 12 and int(a["nSides"][0]) == 72 and int(a["nNodes"][0]) == 12 * 27
+    assert int(a["nUniqueNodes"][0]) == 7 * 5 * 5                      # physical nodes (periodic copies are distinct in HOPR)
+    assert int(a["nUniqueSides"][0]) == 36 + 3 * 2                     # 72 element sides, 60 of them paired (periodic in x and z), 12 walls
+    assert np.array_equal(f.dataset("Elem_IJK"), h["Elem_IJK"]) and list(f.dataset("nElems_IJK")) == [3, 2, 2]
+    m1 = ms.prepare_mesh(h)
+    m2 = ms.prepare_mesh(g)
+    assert np.array_equal(m1.ElemToSide, m2.ElemToSide) and np.array_equal(m1.SideToElem, m2.SideToElem) and np.array_equal(m1.BC, m2.BC)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present")
+@pytest.mark.parametrize("rel", ["regressioncheck/checks/tgv/split/CART_HEX_PERIODIC_008_mesh.h5",
+                                 "regressioncheck/checks/naca/3D/NACA0012_652_Ng2_mesh.h5",
+                                 "tutorials/convtest/CART_HEX_PERIODIC_MORTAR_002_mesh.h5",
+                                 "regressioncheck/checks/parabolic/cavity_3D/cavity4x4x4_mesh.h5"])
+def test_hopr_mesh_writer_reproduces_reference_mesh_files(tmp_path, rel):
+    """Reading a HOPR-written mesh and writing it again gives the same data sets (all of them: also the ones only HOPR / posti
+    use -- GlobalNodeIDs handed through, ElemBarycenters, ElemWeight, ElemCounter recomputed) and the same attributes
+    (nUniqueSides, nUniqueNodes ... recomputed)."""
+    src = os.path.join("/root/reference", rel)
+    f = h5lite.H5File(src)
+    m = h5lite.read_hopr_mesh(src)
+    for k in ("Elem_IJK", "nElems_IJK", "GlobalNodeIDs"):
+        if k in f.keys():
+            m[k] = f.dataset(k)
+    p = str(tmp_path / "m.h5")
+    h5write.write_hopr_mesh(p, m)
+    g = h5lite.H5File(p)
+    assert set(f.keys()) == set(g.keys())                              # incl. the octree data of the mortar mesh
+    for k in g.keys():
+        a, b = f.dataset(k), g.dataset(k)
+        assert a.shape == b.shape and a.dtype == b.dtype, k
+        if a.dtype.kind == "f":
+            assert np.allclose(a, b, rtol=0, atol=1e-13), k
+        else:
+            assert np.array_equal(a, b), k
+    fa, ga = f.attrs(), g.attrs()
+    assert set(fa) == set(ga)
+    for k in fa:
+        assert np.array_equal(fa[k], ga[k]) and fa[k].dtype == ga[k].dtype, k

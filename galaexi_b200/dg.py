@@ -351,6 +351,14 @@ class DGSolver:
                                     is_error_file=isErrorFile, offsetElem=m.offsetElem, nGlobalElems=m.nGlobalElems,
                                     rank=m.myRank, barrier=barrier)
 
+    def WriteBaseFlow(self, MeshFileName: str, OutputTime: float, FutureTime: float, ProjectName: str, out_dir: str = ".", barrier=None) -> str:
+        """WriteBaseflow (io_hdf5/hdf5_output.f90:527-603) of the sponge base flow held on the device (dgx_get_baseflow)."""
+        from .host import state_io
+        m = self.case.mesh
+        return state_io.write_baseflow(self.get_baseflow(), self.case.N, self.case.node_type, ProjectName, MeshFileName, OutputTime,
+                                       FutureTime, out_dir=out_dir, offsetElem=m.offsetElem, nGlobalElems=m.nGlobalElems, rank=m.myRank,
+                                       barrier=barrier)
+
     def Restart(self, RestartFile: str, ResetTime: bool = False) -> float:
         """InitRestart + Restart (restart/restart.f90:60-135, 304-560): this rank's element range of DG_Solution, interpolated
         when the file's degree / node type differ, H2D through dgx_set_state; returns RestartTime."""

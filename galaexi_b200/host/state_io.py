@@ -123,6 +123,46 @@ def write_state(U: np.ndarray, N: int, node_type: str, project: str, mesh_file: 
     return path
 
 
+def write_baseflow(SpBaseFlow: np.ndarray, N: int, node_type: str, project: str, mesh_file: str, t: float, t_next: float, *,
+                   out_dir: str = ".", offsetElem: int = 0, nGlobalElems: int | None = None, rank: int = 0, barrier=None,
+                   now: datetime.datetime | None = None) -> str:
+    """WriteBaseflow(MeshFileName,OutputTime,FutureTime) (hdf5_output.f90:527-603): the sponge base flow [e,k,j,i,var] as
+    Project_BaseFlow_<time>.h5 -- a file of File_Type 'BaseFlow' with the data set DG_Solution on the computation's degree, no
+    userblock, no ElemData. InitSponge reads it back on a restart (sponge.f90:174-190)."""
+    nE = SpBaseFlow.shape[0]
+    nG = nE if nGlobalElems is None else nGlobalElems
+    path = os.path.join(out_dir, state_file_name(project, t, "BaseFlow"))
+    w = _skeleton(project, "BaseFlow", mesh_file, N, N, node_type, t, t_next, nG, SpBaseFlow.shape[-1], STR_VAR_NAMES[:SpBaseFlow.shape[-1]],
+                  [], b"")
+    off, data_start = w.layout(reserve=_DATA_RESERVE)
+    if rank == 0:
+        w.write(path, data_start=data_start)
+    if barrier is not None:
+        barrier()
+    with open(path, "r+b") as f:
+        f.seek(off["DG_Solution"] + offsetElem * (N + 1) ** 3 * SpBaseFlow.shape[-1] * 8)
+        np.ascontiguousarray(SpBaseFlow, dtype="<f8").tofile(f)
+    if barrier is not None:
+        barrier()
+    if rank == 0:
+        mark_write_successful(w, path, data_start, now)
+    return path
+
+
+def read_baseflow(path: str, N: int, node_type: str, *, offsetElem: int = 0, nElems: int | None = None,
+                  nGlobalElems: int | None = None, nVar: int = 5) -> np.ndarray:
+    """ReadBaseFlow(FileName) (sponge.f90:468-518): DG_Solution of a BaseFlow / State / TimeAvg file, interpolated (plain change of
+    basis, no Jacobian) when its degree or node type differ."""
+    info = read_state_attrs(path)
+    if nGlobalElems is not None and info["nGlobalElems"] != nGlobalElems:
+        raise RuntimeError(f"Baseflow file does not match solution. Elements,nVar {info['nGlobalElems']} {info['nVar']}")
+    nE = info["nGlobalElems"] - offsetElem if nElems is None else nElems
+    U = h5lite.H5File(path).dataset_rows("DG_Solution", offsetElem, nE)[..., :nVar]
+    if info["N"] == N and info["NodeType"] == node_type:
+        return np.ascontiguousarray(U)
+    return change_basis_volume(bs.get_vandermonde(info["N"], info["NodeType"], N, node_type, modal=True), U)
+
+
 def mark_write_successful(w: h5write.H5Writer, path: str, data_start: int, now: datetime.datetime | None = None):
     """MarkWriteSuccessfull: DATE_AND_TIME values as the TIME attribute, written when all data is in the file."""
     d = now or datetime.datetime.now().astimezone()

@@ -397,3 +397,21 @@ def test_hopr_mesh_writer_reproduces_reference_mesh_files(tmp_path, rel):
     assert set(fa) == set(ga)
     for k in fa:
         assert np.array_equal(fa[k], ga[k]) and fa[k].dtype == ga[k].dtype, k
+
+
+def test_baseflow_file_round_trip_and_interpolation(tmp_path):
+    """WriteBaseflow / ReadBaseFlow (hdf5_output.f90:527-603, sponge.f90:468-518)."""
+    NC, X = _cart_coords(3, 3, bs.NODETYPE_G)
+    B = _poly_state(X, 3)
+    p = state_io.write_baseflow(B, 3, bs.NODETYPE_G, "naca", "m.h5", 2.0, 2.5, out_dir=str(tmp_path))
+    assert os.path.basename(p) == "naca_BaseFlow_0000002.000000000.h5"
+    f = h5lite.H5File(p)
+    a = f.attrs()
+    assert a["File_Type"][0] == b"BaseFlow" and a["NextFile"][0].decode().strip() == "naca_BaseFlow_0000002.500000000.h5"
+    assert f.base == 0 and f.keys() == ["DG_Solution"] and "TIME" in a
+    assert np.array_equal(state_io.read_baseflow(p, 3, bs.NODETYPE_G, nGlobalElems=3), B)
+    assert np.array_equal(state_io.read_baseflow(p, 3, bs.NODETYPE_G, offsetElem=1, nElems=2), B[1:])
+    _, X5 = _cart_coords(3, 5, bs.NODETYPE_GL)
+    assert np.abs(state_io.read_baseflow(p, 5, bs.NODETYPE_GL) - _poly_state(X5, 3)).max() < 1e-13
+    with pytest.raises(RuntimeError, match="Baseflow file does not match solution"):
+        state_io.read_baseflow(p, 3, bs.NODETYPE_G, nGlobalElems=4)

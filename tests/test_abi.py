@@ -77,3 +77,54 @@ def test_product_package_never_imports_the_oracle():
         for fn in fns:
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
                 assert not pat.search(open(os.path.join(dp, fn)).read()), (dp, fn)
+
+
+def _c_config_fields():
+    """Field names of struct dgx_config in declaration order (include/dgx.h), comments stripped."""
+    import re
+    src = open(os.path.join(ROOT, "include", "dgx.h")).read()
+    body = src[src.index("typedef struct dgx_config"):src.index("} dgx_config;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    body = body[body.index("{") + 1:]
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        decl = re.sub(r"^(const\s+)?(int|double|char)\s+", "", decl)
+        for part in decl.split(","):
+            nm = re.sub(r"\[.*?\]", "", part).replace("*", "").strip()
+            if nm:
+                names.append(nm)
+    return names
+
+
+def _f_config_fields():
+    import re
+    src = open(os.path.join(ROOT, "include", "dgx_mod.f90")).read()
+    body = src[src.index("TYPE, BIND(C), PUBLIC :: dgx_config"):src.index("END TYPE dgx_config")]
+    names = []
+    for line in body.splitlines()[1:]:
+        line = line.split("!")[0]
+        if "::" not in line:
+            continue
+        for part in line.split("::", 1)[1].split(","):
+            nm = re.sub(r"\(.*?\)", "", part).strip()
+            if nm:
+                names.append(nm)
+    return names
+
+
+def test_fortran_module_mirrors_the_c_header():
+    """include/dgx_mod.f90 (the ISO_C_BINDING interface a maintainer USEs) declares dgx_config with the fields of include/dgx.h in
+    the same order, and an INTERFACE for every function the Fortran shim calls."""
+    import re
+    c, f = _c_config_fields(), _f_config_fields()
+    assert len(c) > 60
+    assert [x.lower() for x in c] == [x.lower() for x in f]
+    from galaexi_b200 import dg
+    assert [x.lower() for x in c] == [n.lower() for n, _ in dg.DgxConfig._fields_]
+    fsrc = open(os.path.join(ROOT, "include", "dgx_mod.f90")).read()
+    bound = set(re.findall(r"BIND\(C,\s*NAME='(dgx_\w+)'\)", fsrc))
+    helpers = {"dgx_halo_plan", "dgx_sizeof_config", "dgx_sync", "dgx_run_steps", "dgx_profile_stage", "dgx_launch_count"}   # test / measurement only
+    assert set(dg.EXPORTS) - helpers <= bound, sorted(set(dg.EXPORTS) - helpers - bound)

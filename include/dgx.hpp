@@ -56,6 +56,11 @@ class DG {
     void TimeStepByLSERKW2(double t, double dt) { ck(dgx_rk_step(h_, t, dt)); }
     // timestep.f90:129 -- the same entry point: the library applies the 3-register update when created with RKdelta/RKg1-3
     void TimeStepByLSERKK3(double t, double dt) { ck(dgx_rk_step(h_, t, dt)); }
+    // one iteration of the stage loop (timestep.f90:86-105 / :160-190) for hosts that keep per-stage hooks
+    void RKStage(int iStage, double tStage, double dt) { ck(dgx_rk_stage(h_, iStage, tStage, dt)); }
+    // sponge/pruettdamping.f90:69-92 and the base flow the reference writes with WriteBaseflow
+    void TempFilterTimeDeriv(double dt, double tempFilterWidth) { ck(dgx_temp_filter_time_deriv(h_, dt, tempFilterWidth)); }
+    void GetBaseFlow(double* SpBaseFlow) { ck(dgx_get_baseflow(h_, SpBaseFlow)); }
     double CalcTimeStep(int& errType) {
         double dt = 0.0;
         ck(dgx_calc_timestep(h_, &dt, &errType));

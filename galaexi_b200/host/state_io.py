@@ -104,6 +104,7 @@ def write_state(U: np.ndarray, N: int, node_type: str, project: str, mesh_file: 
                   names, make_userblock(ini_text) if ini_text else b"")
     off, data_start = w.layout(reserve=_DATA_RESERVE)
     if rank == 0:
+        os.makedirs(out_dir, exist_ok=True)
         w.write(path, data_start=data_start)
     if barrier is not None:
         barrier()
@@ -136,6 +137,7 @@ def write_baseflow(SpBaseFlow: np.ndarray, N: int, node_type: str, project: str,
                   [], b"")
     off, data_start = w.layout(reserve=_DATA_RESERVE)
     if rank == 0:
+        os.makedirs(out_dir, exist_ok=True)
         w.write(path, data_start=data_start)
     if barrier is not None:
         barrier()

@@ -68,3 +68,9 @@ def calc_error_norms(case, U: np.ndarray, t: float, exact, NAnalyze: int | None 
     if reduce is not None:
         l2, linf = reduce(l2, linf)
     return np.sqrt(l2 / vol), linf
+
+
+# nTGVvars = 15 columns of the *_TGVAnalysis file in the order of testcase/taylorgreenvortex/testcase.f90:497-498 (what
+# dgx_analyze_tgv / DGSolver.AnalyzeTestcase return)
+TGV_COLUMNS = ("Dissipation Rate Incompressible", "Dissipation Rate Compressible", "Ekin incomp", "Ekin comp", "Enstrophy comp",
+               "DR_u", "DR_S", "DR_Sd", "DR_p", "Maximum Vorticity", "Mean Temperature", "uprime", "Mean Entropy", "ED_S", "ED_D")

@@ -36,3 +36,10 @@ def test_reference_csv_files_are_reproduced_byte_for_byte(tmp_path, rel):
     assert open(fn).read().splitlines() == lines
     with pytest.raises(RuntimeError, match="cannot open"):
         output.output_to_file(str(tmp_path / "missing"), [0.0], [[1.0]])
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+def test_tgv_column_names_are_the_reference_header():
+    from galaexi_b200.host import analyze as an
+    hdr = open(os.path.join(REF, "regressioncheck/checks/tgv/split/TGV_Re1600_Split_TGVAnalysis_Reference.csv")).readline().strip().split(",")
+    assert hdr == ["Time"] + list(an.TGV_COLUMNS)

@@ -48,9 +48,15 @@ def b_alg_stage(n: int) -> float:
 
 
 def b_alg_volsurf(n: int) -> float:
-    """Algorithmic bytes per DOF of the dominant kernel k_volsurf: reads U 5, gradU 12, metrics 9,
-    sJ 1, Ut_tmp 5, face fluxes 30/n; writes Ut_tmp 5, U 5, next-stage face states 30/n."""
-    return 8.0 * (42.0 + 60.0 / n)
+    """Algorithmic bytes per DOF of the dominant kernel k_volsurf2: reads U 5, the viscous volume integral
+    k_lifting left in Ut 4, metrics 9, sJ 1, Ut_tmp 5, face fluxes 30/n; writes Ut_tmp 5, U 5, next-stage face states 30/n."""
+    return 8.0 * (34.0 + 60.0 / n)
+
+
+def b_alg_lifting(n: int) -> float:
+    """k_lifting: reads U 5, metrics 9, sJ 1, face states 10 + geometry 4 per element face node (6/n per DOF); writes the viscous
+    volume integral 4 and the gradient traces 12 per element face node."""
+    return 8.0 * (19.0 + 156.0 / n)
 
 
 def build_case(ngpus: int, rank: int, elems=None, N=N_POLY):
@@ -298,7 +304,7 @@ def main():
     vs_ms = prof.get("volsurf_rk", float("nan"))
     ach = b_alg_volsurf(n) * ndof_local / (vs_ms * 1e-3) / 1e9
     # every stage kernel against the HBM roof (algorithmic bytes per DOF from DESIGN.md 4)
-    b_k = {"halo+lifting": 8.0 * (27.0 + 156.0 / n), "sideflux": 8.0 * 147.0 / n, "volsurf_rk": b_alg_volsurf(n)}
+    b_k = {"halo+lifting": b_alg_lifting(n), "sideflux": 8.0 * 147.0 / n, "volsurf_rk": b_alg_volsurf(n)}
     per_kernel = {k: dict(ms=prof[k], algorithmic_bytes_per_dof=b_k[k], achieved_gbs=b_k[k] * ndof_local / (prof[k] * 1e-3) / 1e9,
                           frac=b_k[k] * ndof_local / (prof[k] * 1e-3) / 1e9 / hbm_peak) for k in b_k if k in prof}
     roofline = dict(bound="hbm", kernel=f"k_volsurf2<{n},RK>", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak,

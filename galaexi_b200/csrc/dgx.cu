@@ -122,6 +122,12 @@ struct dgx_handle {
     double *hPinned = nullptr;  // [4] pinned host scalars
     int *errFlag = nullptr;
     int cur = 0;
+    // volume gradients: only analysis reads them (the viscous volume integral is formed inside k_lifting). keepGrad: the last
+    // stage of every dgx_rk_step stores them, like the reference, whose d_gradUx/y/z then hold the last stage's gradients
+    // (testcase.f90:361-364 reads them at analyze steps without a new RHS evaluation); gradValid: the last RHS stored them
+    int keepGrad = 1;
+    bool gradValid = false;
+    bool bcChecked = false;
     // element / side lists for overlap
     int *innerList = nullptr, *bndList = nullptr;
     int nInner = 0, nBnd = 0;
@@ -267,10 +273,12 @@ struct StageTimes {
     int nev = 0;
 };
 
-int rhs(dgx_handle* h, int mode, double t, double mRKA, double b_dt, StageTimes* st = nullptr) {
+int rhs(dgx_handle* h, int mode, double t, double mRKA, double b_dt, StageTimes* st = nullptr, int storeGrad = 0) {
     const dgx_config& c = h->cfg;
     const KernelTable* kt = h->kt;
     KParams P = h->P;
+    P.storeGrad = (mode == 0 || storeGrad) ? 1 : 0;
+    h->gradValid = c.parabolic && P.storeGrad;
     P.Um = h->Uf[h->cur][0];
     P.Us = h->Uf[h->cur][1];
     P.UmNext = h->Uf[h->cur ^ 1][0];
@@ -468,6 +476,15 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
     if (c.nMortarSides < 0) return fail(h, "nMortarSides < 0");
     if (c.nMortarSides > 0 && (!c.MortarType || !c.MortarInfo || !c.M_0_1 || !c.M_0_2 || !c.M_1_0 || !c.M_2_0))
         return fail(h, "mortar mesh (nMortarSides=%d) needs MortarType, MortarInfo and the operators M_0_1, M_0_2, M_1_0, M_2_0", c.nMortarSides);
+    // boundary conditions: types of the equation system (getboundaryflux.f90:262-838) and reference states that exist
+    for (int sd = 0; sd < c.nBCSides; sd++) {
+        const int bct = c.BCSides[2 * sd], bcs = c.BCSides[2 * sd + 1];
+        const bool known = bct == 2 || bct == 3 || bct == 4 || bct == 9 || bct == 91 || bct == 23 || bct == 24 || bct == 25 || bct == 27;
+        if (!known) return fail(h, "boundary side %d: boundary condition type %d not supported (supported: 2,3,4,9,91,23,24,25,27)", sd + 1, bct);
+        if (bcs > c.nRefState) return fail(h, "boundary side %d: BC state %d exceeds nRefState = %d", sd + 1, bcs, c.nRefState);
+        const bool needsRef = bct == 2 || bct == 4 || bct == 23 || bct == 24 || bct == 25 || bct == 27;
+        if (needsRef && c.nRefState < 1) return fail(h, "boundary side %d: boundary condition type %d needs a reference state, nRefState = 0", sd + 1, bct);
+    }
     CK(cudaSetDevice(c.device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, c.device));
@@ -663,6 +680,7 @@ int dgx_set_state(dgx_handle* h, const double* U) {
         k_aos_to_soa<5><<<blocks_for(tot, 256), 256, 0, h->s>>>(h->stage, h->U, h->n3, tot);
         if (check_launch(h, "k_aos_to_soa")) return 1;
         CK(cudaMemsetAsync(h->Ut_tmp, 0, tot * sizeof(double), h->s));
+        h->gradValid = false;
         if (prolong_current(h)) return 1;
     }
     CK(cudaStreamSynchronize(h->s));
@@ -684,6 +702,7 @@ int dgx_get_state(dgx_handle* h, double* U) { return get_vol(h, h->U, U, 5, 0, 5
 int dgx_get_ut(dgx_handle* h, double* Ut) { return get_vol(h, h->Ut, Ut, 5, 0, 5); }
 int dgx_get_gradients(dgx_handle* h, double* gx, double* gy, double* gz) {
     if (!h->cfg.parabolic) return fail(h, "gradients are only available for PARABOLIC runs");
+    if (!h->gradValid) return fail(h, "dgx_get_gradients: the last RHS evaluation did not store the volume gradients (call dgx_time_derivative, or dgx_set_keep_gradients(h, 1) before the step)");
     if (get_vol(h, h->gradU, gx, 12, 0, 4)) return 1;
     if (get_vol(h, h->gradU, gy, 12, 4, 4)) return 1;
     return get_vol(h, h->gradU, gz, 12, 8, 4);
@@ -698,19 +717,29 @@ int dgx_time_derivative(dgx_handle* h, double t) {
 int dgx_rk_stage(dgx_handle* h, int iStage, double t, double dt) {
     CK(cudaSetDevice(h->cfg.device));
     if (iStage < 1 || iStage > h->cfg.nRKStages) return fail(h, "iStage out of range");
+    const int store = (iStage == h->cfg.nRKStages && h->keepGrad) ? 1 : 0;
     if (!h->RKg1.empty()) {  // TimeStepByLSERKK3 (timestep.f90:129-200)
         h->rk3Stage = iStage;
-        const int rc = rhs(h, 1, t, 0.0, h->RKb[iStage - 1] * dt);
+        const int rc = rhs(h, 1, t, 0.0, h->RKb[iStage - 1] * dt, nullptr, store);
         h->rk3Stage = 0;
         return rc;
     }
     const double mRKA = (iStage == 1) ? 0.0 : -1.0 * h->RKA[iStage - 1];
-    return rhs(h, 1, t, mRKA, h->RKb[iStage - 1] * dt);  // t: the stage time (timestep.f90:86-93)
+    return rhs(h, 1, t, mRKA, h->RKb[iStage - 1] * dt, nullptr, store);  // t: the stage time (timestep.f90:86-93)
 }
 
 int dgx_rk_step(dgx_handle* h, double t, double dt) {
     for (int st = 1; st <= h->cfg.nRKStages; st++)
         if (dgx_rk_stage(h, st, st == 1 ? t : t + h->RKc[st - 1] * dt, dt)) return 1;
+    // an unsupported boundary condition type raises errFlag bit 1 in the first RHS (the reference Aborts in GetBoundaryFlux):
+    // checked once, after the first step, so that the step loop stays free of host syncs
+    if (!h->bcChecked) { h->bcChecked = true; return check_err_flag(h, "dgx_rk_step"); }
+    return 0;
+}
+
+int dgx_set_keep_gradients(dgx_handle* h, int on) {
+    if (!h) return 1;
+    h->keepGrad = on ? 1 : 0;
     return 0;
 }
 
@@ -719,7 +748,8 @@ int dgx_calc_timestep(dgx_handle* h, double* dt, int* errType) {
     const double big = 1.7976931348623157e308;
     h->hPinned[0] = big; h->hPinned[1] = big; h->hPinned[2] = 0.0;
     CK(cudaMemcpyAsync(h->dtOut, h->hPinned, 3 * sizeof(double), cudaMemcpyHostToDevice, h->s));
-    CK(cudaMemsetAsync(h->errFlag, 0, sizeof(int), h->s));
+    k_clear_flag_bits<<<1, 1, 0, h->s>>>(h->errFlag, 2);  // bit 2 (dt) only: bit 1 (boundary condition) stays raised
+    if (check_launch(h, "k_clear_flag_bits")) return 1;
     h->kt->timestep(h->P, h->cfg.CFLScale, h->cfg.DFLScale, h->dtOut, h->s);
     if (h->cfg.nElems && check_launch(h, "k_timestep")) return 1;
     int flag = 0;
@@ -840,6 +870,7 @@ int dgx_analyze_tgv(dgx_handle* h, int NAnalyze, const double* Vdm, const double
     CK(cudaSetDevice(h->cfg.device));
     if (!h->cfg.parabolic) return fail(h, "dgx_analyze_tgv needs PARABOLIC (lifted gradients)");
     if (NAnalyze < 1 || NAnalyze > 32 || !Vdm || !wAnalyze || !out15) return fail(h, "dgx_analyze_tgv: bad arguments");
+    if (!h->gradValid) return fail(h, "dgx_analyze_tgv: the last RHS evaluation did not store the volume gradients (call dgx_time_derivative, or dgx_set_keep_gradients(h, 1) before the step)");
     const int NA1 = NAnalyze + 1;
     if (h->tgvNA1 != NA1) {  // (re)upload the analysis basis
         if (upload(h, &h->tgvV, Vdm, (size_t)NA1 * h->n) || upload(h, &h->tgvW, wAnalyze, (size_t)NA1)) return 1;
@@ -874,11 +905,18 @@ int dgx_run_steps(dgx_handle* h, int nSteps, double t, double dt, int adaptive_d
     const long long l0 = h->launches;
     CK(cudaStreamSynchronize(h->s));
     CK(cudaEventRecord(h->evT0, h->s));
+    const int keep = h->keepGrad;
     for (int it = 0; it < nSteps; it++) {
-        if (adaptive_dt) { int et = 0; if (dgx_calc_timestep(h, &dt, &et)) return 1; if (et) return fail(h, "timestep is NaN / state not admissible at t=%g", t); }
-        if (dgx_rk_step(h, t, dt)) return 1;
+        h->keepGrad = (it == nSteps - 1) ? keep : 0;  // nothing can read the gradients between the steps of this call
+        if (adaptive_dt) {
+            int et = 0;
+            if (dgx_calc_timestep(h, &dt, &et)) { h->keepGrad = keep; return 1; }
+            if (et) { h->keepGrad = keep; return fail(h, "timestep is NaN / state not admissible at t=%g", t); }
+        }
+        if (dgx_rk_step(h, t, dt)) { h->keepGrad = keep; return 1; }
         t += dt;
     }
+    h->keepGrad = keep;
     CK(cudaEventRecord(h->evT1, h->s));
     CK(cudaEventSynchronize(h->evT1));
     CK(cudaStreamSynchronize(h->cs));

@@ -78,6 +78,8 @@ struct KParams {
     int rk3;
     double rk3Delta, rk3G1, rk3G2, rk3G3;
     double *rk3S2, *rk3UPrev;
+    int storeGrad;  // k_lifting also writes the volume gradients (only analysis / dgx_get_gradients read them; the viscous volume
+                    // integral is formed inside k_lifting and travels as 4 doubles per node in Ut)
     int flags;  // tuning switches (DGX_FLAGS): 1 lifting: L2 prefetch of own later-phase data; 2 lifting: L2 prefetch of the element
                 // a resident wave ahead; 4 / 8: the same two for k_volsurf2
 };
@@ -430,7 +432,9 @@ __global__ void __launch_bounds__(n* n* n, lifting_min_blocks<n>()) k_lifting(co
     double* sLhp = sLhm + n;
     double* sLm = sLhp + n;
     double* sLp = sLm + n;
-    double* stM = sLp + n;             // TMA staging: metrics [9][n3], then sJ [n3]
+    double* sDh = sLp + n;             // D_Hat_T [l + n o] (viscous volume integral)
+    double* sDhx = sDh + n * n;        // its transpose [o + n l] (lane-varying o)
+    double* stM = sDhx + n * n;        // TMA staging: metrics [9][n3], then sJ [n3]
     const int e = P.elemList ? P.elemList[blockIdx.x] : blockIdx.x;
     const int t = threadIdx.x;
     if (TMA && t == 0) {
@@ -440,7 +444,10 @@ __global__ void __launch_bounds__(n* n* n, lifting_min_blocks<n>()) k_lifting(co
         tma_load_1d(smem_u32(stM), P.metrics + (size_t)e * 9 * n3, (unsigned)(9 * n3 * sizeof(double)), bar);
         tma_load_1d(smem_u32(stM + 9 * n3), P.sJ + (size_t)e * n3, (unsigned)(n3 * sizeof(double)), bar);
     }
-    for (int x = t; x < n * n; x += n3) { sD[x] = P.D_T[x]; sDx[(x / n) + n * (x % n)] = P.D_T[x]; }
+    for (int x = t; x < n * n; x += n3) {
+        sD[x] = P.D_T[x]; sDx[(x / n) + n * (x % n)] = P.D_T[x];
+        sDh[x] = P.D_Hat_T[x]; sDhx[(x / n) + n * (x % n)] = P.D_Hat_T[x];
+    }
     if (t < n) { sLhm[t] = P.L_HatMinus[t]; sLhp[t] = P.L_HatPlus[t]; sLm[t] = P.L_Minus[t]; sLp[t] = P.L_Plus[t]; }
     const Eos eos = P.eos;
     const int* e2s = P.E2S + 18 * e;
@@ -528,7 +535,7 @@ __global__ void __launch_bounds__(n* n* n, lifting_min_blocks<n>()) k_lifting(co
     }
     __syncthreads();
     // 3. node: volume derivative + surface lifting, Jacobian
-    double G[12];
+    double G[12], fv[12];
     {
         double gxi[4] = {0, 0, 0, 0}, get[4] = {0, 0, 0, 0}, gze[4] = {0, 0, 0, 0};
         if constexpr (DMMA) {
@@ -657,28 +664,51 @@ __global__ void __launch_bounds__(n* n* n, lifting_min_blocks<n>()) k_lifting(co
             // BR2: volume part times sJ (ApplyJacobianLifting, lifting_br2.t90:118-124), S holds the surface part
             G[x] = br2 ? V[x] * sJ : sJ * (V[x] + S[x]);
         }
+        // 3b. transformed viscous fluxes of the node (VolInt_weakForm_Visc, dg/volint.f90:60-119 -> flux.f90:351-384, 619-697)
+        // from the volume gradients, while the metrics are at hand; they are swept with D_Hat_T in step 5
+        {
+            const int tin = DMMA ? idx_m8(i, j, k) : tid_;
+            double Pn[6];
+            Pn[VEL1] = sT[0 * n3 + tin]; Pn[VEL2] = sT[1 * n3 + tin]; Pn[VEL3] = sT[2 * n3 + tin]; Pn[TEMP] = sT[3 * n3 + tin];
+            double gr[12];
+#pragma unroll
+            for (int x = 0; x < 12; x++) gr[x] = br2 ? G[x] + S[x] : G[x];
+            const double mu = viscosity(eos, Pn[TEMP]);
+            Tau ta;
+            stress(ta, Pn, gr, mu, conductivity(eos, mu));
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                const double Md[3] = {M[(3 * d + 0) * n3], M[(3 * d + 1) * n3], M[(3 * d + 2) * n3]};
+                visc_flux_dir(ta, Md, fv + 4 * d);
+            }
+        }
         if (br2) {
             __syncthreads();  // all reads of sT done before it is overwritten by the gradient tile
-            double* gU = P.gradU + (size_t)e * 12 * n3 + t;
 #pragma unroll
-            for (int x = 0; x < 12; x++) { sG[x * n3 + tid_] = G[x]; gU[x * n3] = G[x] + S[x]; }
+            for (int x = 0; x < 12; x++) sG[x * n3 + tid_] = G[x];
+            if (P.storeGrad) {
+                double* gU = P.gradU + (size_t)e * 12 * n3 + t;
+#pragma unroll
+                for (int x = 0; x < 12; x++) gU[x * n3] = G[x] + S[x];
+            }
         }
     }
     if (!br2) {
         __syncthreads();  // all reads of sT done before it is overwritten by the gradient tile
-        double* gU = P.gradU + (size_t)e * 12 * n3 + t;
 #pragma unroll
-        for (int x = 0; x < 12; x++) { gU[x * n3] = G[x]; sG[x * n3 + tid_] = G[x]; }
+        for (int x = 0; x < 12; x++) sG[x * n3 + tid_] = G[x];
+        if (P.storeGrad) {
+            double* gU = P.gradU + (size_t)e * 12 * n3 + t;
+#pragma unroll
+            for (int x = 0; x < 12; x++) gU[x * n3] = G[x];
+        }
     }
     __syncthreads();
     // 4. gradients on the faces (ProlongToFaceLifting)
-    if (!br2) {
-        extract_faces_tile<n, NT, 12>(sG, P.gm, P.gs, e2s, P.S2V2, sLm, sLp);
-        return;
-    }
+    if (!br2) extract_faces_tile<n, NT, 12>(sG, P.gm, P.gs, e2s, P.S2V2, sLm, sLp);
     // BR2 (lifting_br2.t90:126-137, 193-313): trace of the volume part + eta * sum_l L_Minus(l) F_loc(l), F_loc(l) =
     // sJ(depth l) * Flux * L_HatMinus(l); l = depth from the face (Gauss-Lobatto: l = 0 only)
-    if (GEN) {
+    if (GEN && br2) {
         constexpr int SL = Tile<n>::SLOT;
         for (int f = t; f < 6 * n2; f += n3) {
             const int loc = f / n2 + 1;
@@ -743,11 +773,69 @@ __global__ void __launch_bounds__(n* n* n, lifting_min_blocks<n>()) k_lifting(co
             for (int x = 0; x < 12; x++) dst[x * n2] = acc[x];
         }
     }
+    // 5. viscous volume integral (applydmatrix.t90:19-75 with D_Hat_T): Ut_visc(v) = sum_l D_Hat_T(l,i) f_v(l,j,k) +
+    // D_Hat_T(l,k) h_v(i,j,l) + D_Hat_T(l,j) g_v(i,l,k) for the four momentum / energy rows (the density row of the viscous
+    // flux is zero). The result goes to Ut(1..4) of the element; the volume kernel takes it as its initial accumulator
+    // (volint.f90:238-243: the viscous integral overwrites Ut, the advective one adds), so the 12 gradient components per
+    // node never make the round trip through HBM.
+    __syncthreads();  // face extraction done with the gradient tile
+    double* UtV = P.Ut + (size_t)e * 5 * n3 + n3;
+    if constexpr (DMMA) {
+        const int tm = idx_m8(i, j, k);
+#pragma unroll
+        for (int x = 0; x < 12; x++) smem[x * n3 + tm] = fv[x];
+        __syncthreads();
+        // FP64 tensor-core form (fragments as in step 3). zeta first, as C[i][o=k] = sum_l h(i,g,l) D_Hat_T(l,o) on the planes
+        // j = g (A = flux tile, B = operator), parked in slots 12..15; then on the planes k = g the xi product
+        // C[o=i][j] += sum_l D_Hat_T(l,o) f(l,j,g) (A = operator) and the eta product C[i][o=j] += sum_l g(i,l,g) D_Hat_T(l,o)
+        // (A = flux tile) accumulate on top of it in the same fragment, which is stored straight to global memory.
+        const int lane = t & 31, r = lane >> 2, c4 = lane & 3;
+        const double a0 = sDh[c4 + n * r], a1 = sDh[c4 + 4 + n * r];
+#pragma unroll 2
+        for (int task = t >> 5; task < 32; task += n3 / 32) {
+            const int v = task >> 3, g = task & 7;
+            const double h0 = smem[(8 + v) * n3 + idx_m8(r, g, c4)], h1 = smem[(8 + v) * n3 + idx_m8(r, g, c4 + 4)];
+            double c0 = 0.0, c1 = 0.0;
+            dmma_m8n8k4(c0, c1, h0, a0);
+            dmma_m8n8k4(c0, c1, h1, a1);
+            smem[(12 + v) * n3 + idx_m8(r, g, 2 * c4)] = c0;
+            smem[(12 + v) * n3 + idx_m8(r, g, 2 * c4 + 1)] = c1;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int task = t >> 5; task < 32; task += n3 / 32) {
+            const int v = task >> 3, g = task & 7;
+            double c0 = smem[(12 + v) * n3 + idx_m8(r, 2 * c4, g)], c1 = smem[(12 + v) * n3 + idx_m8(r, 2 * c4 + 1, g)];
+            const double f0 = smem[v * n3 + idx_m8(c4, r, g)], f1 = smem[v * n3 + idx_m8(c4 + 4, r, g)];
+            const double g0 = smem[(4 + v) * n3 + idx_m8(r, c4, g)], g1 = smem[(4 + v) * n3 + idx_m8(r, c4 + 4, g)];
+            dmma_m8n8k4(c0, c1, a0, f0);
+            dmma_m8n8k4(c0, c1, a1, f1);
+            dmma_m8n8k4(c0, c1, g0, a0);
+            dmma_m8n8k4(c0, c1, g1, a1);
+            double* o = UtV + v * n3 + (r + n * (2 * c4) + n2 * g);
+            o[0] = c0;
+            o[n] = c1;
+        }
+    } else {
+#pragma unroll
+        for (int x = 0; x < 12; x++) smem[x * n3 + tid_] = fv[x];
+        __syncthreads();
+        double a[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int l = 0; l < n; l++) {
+            const double dx = sDhx[i + n * l], dy = sDh[l + n * j], dz = sDh[l + n * k];
+            const int ix = Tile<n>::idx(l, j, k), iy = Tile<n>::idx(i, l, k), iz = Tile<n>::idx(i, j, l);
+#pragma unroll
+            for (int v = 0; v < 4; v++) a[v] += dx * smem[v * n3 + ix] + dz * smem[(8 + v) * n3 + iz] + dy * smem[(4 + v) * n3 + iy];
+        }
+#pragma unroll
+        for (int v = 0; v < 4; v++) UtV[v * n3 + t] = a[v];
+    }
 }
 
 template <int n>
 constexpr size_t lifting_smem_bytes() {
-    return sizeof(double) * (lifting_tile_slots<n>() * n * n * n + 6 * 7 * n * n + 2 * n * n + 4 * n + (lifting_uses_tma<n>() ? 10 * n * n * n : 0));
+    return sizeof(double) * (lifting_tile_slots<n>() * n * n * n + 6 * 7 * n * n + 4 * n * n + 4 * n + (lifting_uses_tma<n>() ? 10 * n * n * n : 0));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -915,60 +1003,42 @@ __global__ void __launch_bounds__(n* n* n, volsurf_min_blocks<n>()) k_volsurf(co
     cons_to_prim(Pr, Uc, eos);
     double Ut[5] = {0, 0, 0, 0, 0};
 
-    // ---- weak-form part: Euler(+viscous) fluxes (non-split) or viscous fluxes only (split + parabolic)
-    if (!split || P.parabolic) {
+    // ---- viscous volume integral: formed by k_lifting (its step 5), taken over as the initial value (volint.f90:238-243)
+    if (P.parabolic) {
+        const double* uv = P.Ut + (size_t)e * 5 * n3 + n3 + t;
+#pragma unroll
+        for (int v = 0; v < 4; v++) Ut[1 + v] = uv[v * n3];
+    }
+    // ---- weak-form part: Euler fluxes (non-split)
+    if (!split) {
         double f[5], g[5], h[5];
-        if (!split) {
-            const double Ep = (Uc[ENER] + Pr[PRES]) / Uc[DENS];
-            double* Fs[3] = {f, g, h};
+        const double Ep = (Uc[ENER] + Pr[PRES]) / Uc[DENS];
+        double* Fs[3] = {f, g, h};
 #pragma unroll
-            for (int d = 0; d < 3; d++) {
-                const double* Md = M + 3 * d;
-                const double Mmom = Md[0] * Uc[MOM1] + Md[1] * Uc[MOM2] + Md[2] * Uc[MOM3];
-                Fs[d][DENS] = Mmom;
-                Fs[d][MOM1] = Mmom * Pr[VEL1] + Md[0] * Pr[PRES];
-                Fs[d][MOM2] = Mmom * Pr[VEL2] + Md[1] * Pr[PRES];
-                Fs[d][MOM3] = Mmom * Pr[VEL3] + Md[2] * Pr[PRES];
-                Fs[d][ENER] = Mmom * Ep;
-            }
-        } else {
-#pragma unroll
-            for (int v = 0; v < 5; v++) f[v] = g[v] = h[v] = 0.0;
-        }
-        if (P.parabolic) {
-            double gr[12];
-            const double* gU = P.gradU + (size_t)e * 12 * n3 + t;
-#pragma unroll
-            for (int x = 0; x < 12; x++) gr[x] = gU[x * n3];
-            const double mu = viscosity(eos, Pr[TEMP]);
-            Tau ta;
-            stress(ta, Pr, gr, mu, conductivity(eos, mu));
-            double v4[4];
-            visc_flux_dir(ta, M + 0, v4);
-#pragma unroll
-            for (int v = 0; v < 4; v++) f[1 + v] += v4[v];
-            visc_flux_dir(ta, M + 3, v4);
-#pragma unroll
-            for (int v = 0; v < 4; v++) g[1 + v] += v4[v];
-            visc_flux_dir(ta, M + 6, v4);
-#pragma unroll
-            for (int v = 0; v < 4; v++) h[1 + v] += v4[v];
+        for (int d = 0; d < 3; d++) {
+            const double* Md = M + 3 * d;
+            const double Mmom = Md[0] * Uc[MOM1] + Md[1] * Uc[MOM2] + Md[2] * Uc[MOM3];
+            Fs[d][DENS] = Mmom;
+            Fs[d][MOM1] = Mmom * Pr[VEL1] + Md[0] * Pr[PRES];
+            Fs[d][MOM2] = Mmom * Pr[VEL2] + Md[1] * Pr[PRES];
+            Fs[d][MOM3] = Mmom * Pr[VEL3] + Md[2] * Pr[PRES];
+            Fs[d][ENER] = Mmom * Ep;
         }
 #pragma unroll
         for (int v = 0; v < 5; v++) { sA[v * n3 + t] = f[v]; sA[(5 + v) * n3 + t] = g[v]; sA[(10 + v) * n3 + t] = h[v]; }
         __syncthreads();
-        // D_Hat sweep (applydmatrix.t90:60-67); the DENS row is skipped when only viscous fluxes are present
-        const int v0 = split ? 1 : 0;
+        // D_Hat sweep (applydmatrix.t90:60-67)
+        double A[5] = {0, 0, 0, 0, 0};
 #pragma unroll
         for (int l = 0; l < n; l++) {
             const double dx = sDh[l + n * i], dy = sDh[l + n * j], dz = sDh[l + n * k];
 #pragma unroll
-            for (int v = 0; v < 5; v++) {
-                if (v < v0) continue;
-                Ut[v] += dx * sA[v * n3 + l + n * (j + n * k)] + dz * sA[(10 + v) * n3 + i + n * (j + n * l)] +
-                         dy * sA[(5 + v) * n3 + i + n * (l + n * k)];
-            }
+            for (int v = 0; v < 5; v++)
+                A[v] += dx * sA[v * n3 + l + n * (j + n * k)] + dz * sA[(10 + v) * n3 + i + n * (j + n * l)] +
+                        dy * sA[(5 + v) * n3 + i + n * (l + n * k)];
         }
+#pragma unroll
+        for (int v = 0; v < 5; v++) Ut[v] += A[v];
         __syncthreads();
     }
 
@@ -1150,6 +1220,7 @@ __global__ void __launch_bounds__(timestep_threads<n>()) k_bulkvel(const KParams
         partials[e] = s;
     }
 }
+static __global__ void k_clear_flag_bits(int* flag, int bits) { *flag &= ~bits; }
 // sponge/pruettdamping.f90:69-92 TempFilterTimeDeriv: SpBaseFlow += (U - SpBaseFlow) dt / tempFilterWidth
 static __global__ void k_pruett(const double* __restrict__ U, double* __restrict__ base, double fac, size_t total) {
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

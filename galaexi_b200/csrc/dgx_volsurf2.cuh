@@ -10,8 +10,10 @@
 //     Shared-memory loads per node drop from 24*9 to about 2*9 per direction.
 //   * In the point-wise phases the same thread owns the nodes (i,j,k in its half of the zeta column), so global
 //     accesses stay coalesced and the zeta sweep accumulates directly into the registers of the epilogue.
-//   * 15 tile slots of shared memory per element (12 viscous fluxes + M_xi, later Ut partials + node record + one
-//     metric triple) -> 3 CTAs per SM at N=7, which overlaps the load / sweep / store phases of different elements.
+//   * The viscous volume integral (volint.f90:60-119) is NOT evaluated here: k_lifting, which has the element's gradients in
+//     registers, forms it and hands over 4 doubles per node in Ut(1..4); this kernel starts its accumulators from them.
+//   * 17 tile slots of shared memory per element (5 Ut partials, 6 node record, 2 metric triples) -> 3 CTAs per SM at N=7,
+//     which overlaps the load / sweep / store phases of different elements.
 //   * Shared-memory tile layout for n=8: (i xor k) + 8 j + 72 k, conflict-free for 64-bit accesses of all three
 //     line directions with the lane mappings used below.
 //   * Gauss-Lobatto only (split DG requires it, splitflux.f90:116-119): surface integral and next-stage face
@@ -49,7 +51,10 @@ template <int n>
 constexpr int vs2_seg() { return (n + vs2_parts<n>() - 1) / vs2_parts<n>(); }
 template <int n>
 constexpr int vs2_threads() { return vs2_epb<n>() * vs2_parts<n>() * n * n; }
-constexpr int VS2_SLOTS = 18;
+// shared-memory slots of one element: Ut partials (momentum, energy), density partial, node record (6), metric triple of the
+// xi (later zeta) sweep, metric triple of the eta sweep
+constexpr int S_UT = 0, S_RHO = 4, S_REC = 5, S_MX = 11, S_ME = 14;
+constexpr int VS2_SLOTS = 17;
 #ifndef VS2_CROSS_UNROLL
 #define VS2_CROSS_UNROLL 1
 #endif
@@ -64,7 +69,7 @@ constexpr int VS2_CU = VS2_CROSS_UNROLL;
 #define VS2_MIN_BLOCKS(n) ((n) == 6 ? VS2_MINB6 : ((n) == 8 ? VS2_MINB8 : ((n) >= 6 ? 3 : 4)))
 #endif
 template <int n>
-constexpr size_t vs2_smem_bytes() { return sizeof(double) * ((size_t)vs2_epb<n>() * VS2_SLOTS * TileV<n>::SLOT + 2 * n * n); }
+constexpr size_t vs2_smem_bytes() { return sizeof(double) * ((size_t)vs2_epb<n>() * VS2_SLOTS * TileV<n>::SLOT); }
 
 // Paired operand layout (n = 8, knob VS2_PAIRED8): the node record is kept as three double2 ([0,1] [2,3] [4,5]) and a metric
 // triple as double2 + double, so that a partner node costs 5 shared-memory load instructions (4 LDS.128 + 1 LDS.64) instead
@@ -244,16 +249,12 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
     const bool live = we < nWork;
     const int e = live ? (P.elemList ? P.elemList[we] : we) : 0;
     double* S = smem + (size_t)le * VS2_SLOTS * SL;
-    double* sDh = smem + (size_t)EPB * VS2_SLOTS * SL;  // D_Hat_T [l + n a] and its transpose [a + n l] (lane-varying index)
-    double* sDhx = sDh + n2;
-    for (int x = threadIdx.x; x < n2; x += EPB * T) { sDh[x] = P.D_Hat_T[x]; sDhx[(x / n) + n * (x % n)] = P.D_Hat_T[x]; }
     const int h = tid / n2, q = tid - h * n2;
     const int c1 = q % n, c2 = q / n;          // point-wise phases: (i,j) = (c1,c2), k in the own half of the zeta column
     const int a0 = h * SEG, cnt = (vs2_parts<n>() == 2) ? (h ? n - SEG : SEG) : ((n - a0 < SEG) ? n - a0 : SEG);
     const bool facer = (vs2_parts<n>() == 2) || h < 2;                  // P4: the threads of the first two parts take the - / + face of each axis
     const Eos eos = P.eos;
     const bool par = P.parabolic != 0;
-    const double* __restrict__ Dh = P.D_Hat_T;  // uniform index only (constant bank)
     const double* __restrict__ Dv = P.DVolSurf;
     const double* __restrict__ gU_e = P.U + (size_t)e * 5 * n3;
     const double* __restrict__ gM_e = P.metrics + (size_t)e * 9 * n3;
@@ -274,107 +275,57 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
         const int en = P.elemList ? P.elemList[we + lookahead * EPB] : we + lookahead * EPB;
         prefetch_block(P.U + (size_t)en * 5 * n3, sizeof(double) * 5 * n3, tid, T);
         prefetch_block(P.metrics + (size_t)en * 9 * n3, sizeof(double) * 6 * n3, tid, T);
-        if (par) prefetch_block(P.gradU + (size_t)en * 12 * n3, sizeof(double) * 12 * n3, tid, T);
+        if (par) prefetch_block(P.Ut + (size_t)en * 5 * n3 + n3, sizeof(double) * 4 * n3, tid, T);
     }
-    // ---- P0: point-wise. All global reads of the phase are issued before the first use (one DRAM round trip per CTA
-    // instead of one per node): lifted gradients by 8-byte cp.async straight into slots 0..11 at the thread's own nodes
-    // (no registers held), state and metrics into registers. The viscous fluxes then overwrite the gradients in place.
-    double Rec[SEG][6];
+    // ---- P0: point-wise. The viscous volume integral of the element (4 doubles per node, formed by k_lifting's step 5)
+    // is the initial value of the Ut partials (volint.f90:238-243): 8-byte cp.async straight into slots S_UT.. at the
+    // thread's own nodes (no registers held); state and metrics into registers; node record and the xi / eta metric triples
+    // into their slots.
     if (live) {
         if (par) {
-            const double* gU = P.gradU + (size_t)e * 12 * n3;
+            const double* gV = P.Ut + (size_t)e * 5 * n3 + n3;
 #pragma unroll
             for (int m = 0; m < SEG; m++) {
                 if (m < cnt) {
                     const int node = c1 + n * c2 + n2 * (a0 + m);
-                    const unsigned dst = (unsigned)__cvta_generic_to_shared(S + TileV<n>::idx(c1, c2, a0 + m));
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(S + S_UT * SL + TileV<n>::idx(c1, c2, a0 + m));
 #pragma unroll
-                    for (int x = 0; x < 12; x++)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (unsigned)(x * SL * 8)), "l"(gU + x * n3 + node) : "memory");
+                    for (int v = 0; v < 4; v++)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (unsigned)(v * SL * 8)), "l"(gV + v * n3 + node) : "memory");
                 }
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        double Uc[SEG][5], M[SEG][9];
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        double Uc[SEG][5], M[SEG][6];
 #pragma unroll
         for (int m = 0; m < SEG; m++) {
             const int node = c1 + n * c2 + n2 * (m < cnt ? a0 + m : a0);
 #pragma unroll
             for (int v = 0; v < 5; v++) Uc[m][v] = gU_e[v * n3 + node];
 #pragma unroll
-            for (int x = 0; x < 9; x++) M[m][x] = gM_e[x * n3 + node];
+            for (int x = 0; x < 6; x++) M[m][x] = gM_e[x * n3 + node];
         }
-        if (par) asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
         for (int m = 0; m < SEG; m++) {
             if (m < cnt) {
                 const int id = TileV<n>::idx(c1, c2, a0 + m);
-                double Pr[6];
+                double Pr[6], Rec[6];
                 cons_to_prim(Pr, Uc[m], eos);
-                vs2_record<VAR>(Rec[m], Uc[m], Pr);
+                vs2_record<VAR>(Rec, Uc[m], Pr);
+                vs2_rec_store<n>(S + S_REC * SL, id, Rec);
 #pragma unroll
-                for (int c = 0; c < 6; c++) *vs2_met_ptr<n>(S + (c < 3 ? 12 : 15) * SL, id, c % 3) = M[m][c];  // M_xi -> slots 12..14, M_eta -> 15..17
-                if (par) {
-                    double gr[12];
+                for (int c = 0; c < 6; c++) *vs2_met_ptr<n>(S + (c < 3 ? S_MX : S_ME) * SL, id, c % 3) = M[m][c];
+                S[S_RHO * SL + id] = 0.0;
+                if (!par) {
 #pragma unroll
-                    for (int x = 0; x < 12; x++) gr[x] = S[x * SL + id];
-                    const double mu = viscosity(eos, Pr[TEMP]);
-                    Tau ta;
-                    stress(ta, Pr, gr, mu, conductivity(eos, mu));
-                    double v4[4];
-#pragma unroll
-                    for (int d = 0; d < 3; d++) {
-                        visc_flux_dir(ta, M[m] + 3 * d, v4);
-#pragma unroll
-                        for (int v = 0; v < 4; v++) S[(4 * d + v) * SL + id] = v4[v];
-                    }
+                    for (int v = 0; v < 4; v++) S[(S_UT + v) * SL + id] = 0.0;
                 }
             }
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    __syncthreads();
-    // ---- P1: D_Hat sweep of the viscous fluxes (applydmatrix.t90:60-67), zeta column register-blocked
-    double UtV[SEG][4];
-#pragma unroll
-    for (int m = 0; m < SEG; m++)
-#pragma unroll
-        for (int v = 0; v < 4; v++) UtV[m][v] = 0.0;
-    if (par && live) {
-#pragma unroll 2
-        for (int l = 0; l < n; l++) {
-            const int idz = TileV<n>::idx(c1, c2, l);
-            double hz[4];
-#pragma unroll
-            for (int v = 0; v < 4; v++) hz[v] = S[(8 + v) * SL + idz];
-            const double dx = sDhx[c1 + n * l], dy = sDh[l + n * c2];
-#pragma unroll
-            for (int m = 0; m < SEG; m++) {
-                if (m < cnt) {
-                    const int k = a0 + m;
-                    const double dz = Dh[l + n * k];
-                    const int idx_ = TileV<n>::idx(l, c2, k), idy = TileV<n>::idx(c1, l, k);
-#pragma unroll
-                    for (int v = 0; v < 4; v++) UtV[m][v] = fma(dy, S[(4 + v) * SL + idy], fma(dz, hz[v], fma(dx, S[v * SL + idx_], UtV[m][v])));
-                }
-            }
-        }
-    }
-    __syncthreads();  // viscous fluxes consumed: slots 0..11 are free
-    // ---- P2: Ut partials -> slots 0..3 (momentum, energy) and 10 (density); node record -> slots 4..9
-    if (live) {
-#pragma unroll
-        for (int m = 0; m < SEG; m++) {
-            if (m < cnt) {
-                const int id = TileV<n>::idx(c1, c2, a0 + m);
-#pragma unroll
-                for (int v = 0; v < 4; v++) S[v * SL + id] = UtV[m][v];
-                S[10 * SL + id] = 0.0;
-                vs2_rec_store<n>(S + 4 * SL, id, Rec[m]);
-            }
-        }
-    }
-    // ---- P3: the three flux-differencing sweeps (volint.f90:306-347). Metric triples: xi in slots 12..14 and eta in
-    // 15..17 (from P0); zeta is copied by cp.async into 12..14 while the eta sweep runs.
+    // ---- P3: the three flux-differencing sweeps (volint.f90:306-347). Metric triples: xi in slots S_MX.. and eta in
+    // S_ME.. (from P0); zeta is copied by cp.async into S_MX.. while the eta sweep runs.
 #pragma unroll 1
     for (int d = 0; d < 3; d++) {
         if (d == 2) asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -388,7 +339,7 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
                         const int idm = TileV<n>::idx(c1, c2, a0 + m);
 #pragma unroll
                         for (int c = 0; c < 3; c++) {
-                            const unsigned dst = (unsigned)__cvta_generic_to_shared(vs2_met_ptr<n>(S + 12 * SL, idm, c));
+                            const unsigned dst = (unsigned)__cvta_generic_to_shared(vs2_met_ptr<n>(S + S_MX * SL, idm, c));
                             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(Mg + c * n3) : "memory");
                         }
                     }
@@ -398,14 +349,14 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
             // lane -> line mapping: xi lines take (j,k) = (q/n, q%n), eta (i,k) and zeta (i,j) = (q%n, q/n): conflict-free
             const int l1 = (d == 0) ? c2 : c1, l2 = (d == 0) ? c1 : c2;
             double acc[SEG][5];
-            vs2_sweep<n, VAR>(S + 4 * SL, S + (d == 1 ? 15 : 12) * SL, Dv, d, l1, l2, h, acc);
+            vs2_sweep<n, VAR>(S + S_REC * SL, S + (d == 1 ? S_ME : S_MX) * SL, Dv, d, l1, l2, h, acc);
 #pragma unroll
             for (int m = 0; m < SEG; m++) {
                 if (m < cnt) {
                     const int id = line_idx<n>(d, a0 + m, l1, l2);
-                    S[10 * SL + id] += acc[m][0];
+                    S[S_RHO * SL + id] += acc[m][0];
 #pragma unroll
-                    for (int v = 0; v < 4; v++) S[v * SL + id] += acc[m][1 + v];
+                    for (int v = 0; v < 4; v++) S[(S_UT + v) * SL + id] += acc[m][1 + v];
                 }
             }
         }
@@ -449,9 +400,9 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
     for (int r = 0; r < 3; r++) {
         __syncthreads();
         if (live && facer) {
-            S[10 * SL + idf[r]] += Ff[r][0] * wf[r];
+            S[S_RHO * SL + idf[r]] += Ff[r][0] * wf[r];
 #pragma unroll
-            for (int v = 0; v < 4; v++) S[v * SL + idf[r]] += Ff[r][1 + v] * wf[r];
+            for (int v = 0; v < 4; v++) S[(S_UT + v) * SL + idf[r]] += Ff[r][1 + v] * wf[r];
         }
     }
     __syncthreads();  // Ut complete in slots 10, 0..3; node record consumed: slots 4..8 take the updated state
@@ -465,9 +416,9 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
                 const int id = TileV<n>::idx(c1, c2, k);
                 const double msJ = -sJv[m];
                 double Ut[5];
-                Ut[0] = S[10 * SL + id] * msJ;
+                Ut[0] = S[S_RHO * SL + id] * msJ;
 #pragma unroll
-                for (int v = 0; v < 4; v++) Ut[1 + v] = S[v * SL + id] * msJ;
+                for (int v = 0; v < 4; v++) Ut[1 + v] = S[(S_UT + v) * SL + id] * msJ;
                 if (MODE == 0) {
                     double* o = P.Ut + (size_t)e * 5 * n3 + node;
 #pragma unroll
@@ -481,7 +432,7 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
                         ot[v * n3] = r;
                         const double un = Uo[m][v] + r * b_dt;
                         ou[v * n3] = un;
-                        S[(4 + v) * SL + id] = un;
+                        S[(S_REC + v) * SL + id] = un;
                     }
                 }
             }
@@ -508,7 +459,7 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
                 else id = TileV<n>::idx(a, b, l);
                 double* dst = (flip == 0 ? P.UmNext : P.UsNext) + (size_t)side * 5 * n2 + pq;
 #pragma unroll
-                for (int v = 0; v < 5; v++) dst[v * n2] = S[(4 + v) * SL + id];
+                for (int v = 0; v < 5; v++) dst[v * n2] = S[(S_REC + v) * SL + id];
             }
         }
     }

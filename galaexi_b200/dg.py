@@ -27,7 +27,7 @@ _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 
 EXPORTS = ("dgx_create", "dgx_destroy", "dgx_last_error", "dgx_set_state", "dgx_get_state", "dgx_get_ut",
-           "dgx_get_gradients", "dgx_time_derivative", "dgx_rk_stage", "dgx_rk_step", "dgx_calc_timestep",
+           "dgx_get_gradients", "dgx_set_keep_gradients", "dgx_time_derivative", "dgx_rk_stage", "dgx_rk_step", "dgx_calc_timestep",
            "dgx_analyze_tgv", "dgx_calc_bulk_velocity", "dgx_calc_body_forces", "dgx_calc_wall_velocity", "dgx_set_channel_forcing", "dgx_temp_filter_time_deriv", "dgx_get_baseflow", "dgx_sync", "dgx_run_steps", "dgx_profile_stage", "dgx_nccl_unique_id", "dgx_launch_count", "dgx_sizeof_config", "dgx_halo_plan")
 
 
@@ -80,6 +80,7 @@ def load_library():
     for nm in ("dgx_set_state", "dgx_get_state", "dgx_get_ut"):
         getattr(lib, nm).argtypes = [h, _dp]
     lib.dgx_get_gradients.argtypes = [h, _dp, _dp, _dp]
+    lib.dgx_set_keep_gradients.argtypes = [h, C.c_int]
     lib.dgx_time_derivative.argtypes = [h, C.c_double]
     lib.dgx_rk_stage.argtypes = [h, C.c_int, C.c_double, C.c_double]
     lib.dgx_rk_step.argtypes = [h, C.c_double, C.c_double]
@@ -245,6 +246,11 @@ class DGSolver:
         g = [np.empty(self.shape_grad) for _ in range(3)]
         self._ck(self.lib.dgx_get_gradients(self.h, *[x.ctypes.data_as(_dp) for x in g]))
         return g
+
+    def set_keep_gradients(self, on: bool):
+        """on (default): the last stage of every RK step stores the volume gradients, as the reference's d_gradUx/y/z hold them
+        at analyze steps (testcase.f90:361-364); off: RK stages never write them (steps no analysis follows)."""
+        self._ck(self.lib.dgx_set_keep_gradients(self.h, int(bool(on))))
 
     # ---- the reference's procedures ------------------------------------------------------------------------
     def DGTimeDerivative_weakForm(self, t: float = 0.0):

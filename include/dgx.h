@@ -123,6 +123,12 @@ int dgx_set_state(dgx_handle *h, const double *U);
 int dgx_get_state(dgx_handle *h, double *U);
 int dgx_get_ut(dgx_handle *h, double *Ut);
 int dgx_get_gradients(dgx_handle *h, double *gradUx, double *gradUy, double *gradUz);
+/* The volume gradients d_gradUx/y/z are read by analysis only (testcase.f90:361-364); the viscous volume integral is formed
+ * inside the lifting kernel and the 12 gradient components per node are not written in every stage. on != 0 (default): the
+ * LAST stage of every dgx_rk_step stores them, so that after a step they hold what the reference's device arrays hold (the
+ * gradients of the last stage's RHS); on == 0: RK stages never store them (steps that no analysis follows).
+ * dgx_time_derivative always stores them. dgx_get_gradients / dgx_analyze_tgv fail if the last RHS did not store. */
+int dgx_set_keep_gradients(dgx_handle *h, int on);
 
 int dgx_time_derivative(dgx_handle *h, double t);
 int dgx_rk_stage(dgx_handle *h, int iStage /* 1-based */, double t, double dt);

@@ -51,6 +51,7 @@ class DG {
     void GetState(double* U) { ck(dgx_get_state(h_, U)); }
     void GetUt(double* Ut) { ck(dgx_get_ut(h_, Ut)); }
     void GetGradients(double* gx, double* gy, double* gz) { ck(dgx_get_gradients(h_, gx, gy, gz)); }
+    void SetKeepGradients(bool on) { ck(dgx_set_keep_gradients(h_, on ? 1 : 0)); }
 
     void DGTimeDerivative_weakForm(double t) { ck(dgx_time_derivative(h_, t)); }
     void TimeStepByLSERKW2(double t, double dt) { ck(dgx_rk_step(h_, t, dt)); }

@@ -68,6 +68,9 @@ INTERFACE
   INTEGER(C_INT) FUNCTION dgx_get_gradients(h,gx,gy,gz) BIND(C,NAME='dgx_get_gradients')
     IMPORT; TYPE(C_PTR),VALUE :: h; REAL(C_DOUBLE),INTENT(OUT) :: gx(*),gy(*),gz(*)
   END FUNCTION
+  INTEGER(C_INT) FUNCTION dgx_set_keep_gradients(h,on) BIND(C,NAME='dgx_set_keep_gradients')
+    IMPORT; TYPE(C_PTR),VALUE :: h; INTEGER(C_INT),VALUE :: on
+  END FUNCTION
   INTEGER(C_INT) FUNCTION dgx_time_derivative(h,t) BIND(C,NAME='dgx_time_derivative')
     IMPORT; TYPE(C_PTR),VALUE :: h; REAL(C_DOUBLE),VALUE :: t
   END FUNCTION
@@ -116,7 +119,7 @@ INTERFACE
 END INTERFACE
 
 PUBLIC :: dgx_create,dgx_destroy,dgx_last_error,dgx_set_state,dgx_get_state,dgx_get_ut,dgx_get_gradients
-PUBLIC :: dgx_time_derivative,dgx_rk_stage,dgx_rk_step,dgx_calc_timestep,dgx_nccl_unique_id
+PUBLIC :: dgx_set_keep_gradients,dgx_time_derivative,dgx_rk_stage,dgx_rk_step,dgx_calc_timestep,dgx_nccl_unique_id
 PUBLIC :: dgx_analyze_tgv,dgx_calc_bulk_velocity,dgx_set_channel_forcing,dgx_temp_filter_time_deriv,dgx_get_baseflow
 PUBLIC :: DGX_Check
 

@@ -515,11 +515,8 @@ def test_unsupported_boundary_type_is_an_error():
     from galaexi_b200.dg import DGError
     c, U_uniform, U0 = cases.duct_case((2, 1), (24, 1), (3, 0), N=2)
     c.BCSides[0, 0] = 77             # a type the equation system does not know
-    s = _solver(c)
-    s.set_state(U0)
-    with pytest.raises(DGError, match="boundary condition"):
-        s.DGTimeDerivative_weakForm(0.0)
-    s.FinalizeDG()
+    with pytest.raises(DGError, match="boundary condition"):   # rejected when the operator is created (InitBC)
+        _solver(c)
 
 
 def test_handle_reuse_and_two_solvers_on_one_device():

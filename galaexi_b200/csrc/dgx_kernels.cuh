@@ -543,11 +543,14 @@ __global__ void __launch_bounds__(n* n* n, lifting_min_blocks<n>()) k_lifting(co
             // A[row o][l] = D_T(l,o) (the same fragment for the three directions), B[l][col] = u on 8 lines, one task =
             // (direction, variable, group of 8 lines); 96 tasks over the 16 warps. Fragments: A: row = lane/4, k = lane%4;
             // B: k = lane%4, col = lane/4; C: row = lane/4, cols 2 (lane%4) + {0,1}.
+            // 96 tasks over the 16 warps: task = warp + 16 it, so that the direction is a compile-time value of the unrolled
+            // loop and the line group g = warp & 7 is fixed per warp (all tile indices are loop invariants)
             const int lane = t & 31, r = lane >> 2, c4 = lane & 3;
+            const int g = (t >> 5) & 7, vh = t >> 8;
             const double a0 = sD[c4 + n * r], a1 = sD[c4 + 4 + n * r];
-#pragma unroll 2
-            for (int task = t >> 5; task < 96; task += n3 / 32) {
-                const int dir = task >> 5, v = (task >> 3) & 3, g = task & 7;
+#pragma unroll
+            for (int it = 0; it < 6; it++) {
+                const int dir = it >> 1, v = vh + 2 * (it & 1);
                 int ib0, ib1, ic0, ic1;
                 if (dir == 0) {         // xi: lines (j = col, k = g)
                     ib0 = idx_m8(c4, r, g); ib1 = idx_m8(c4 + 4, r, g);
@@ -790,31 +793,39 @@ __global__ void __launch_bounds__(n* n* n, lifting_min_blocks<n>()) k_lifting(co
         // C[o=i][j] += sum_l D_Hat_T(l,o) f(l,j,g) (A = operator) and the eta product C[i][o=j] += sum_l g(i,l,g) D_Hat_T(l,o)
         // (A = flux tile) accumulate on top of it in the same fragment, which is stored straight to global memory.
         const int lane = t & 31, r = lane >> 2, c4 = lane & 3;
+        const int g = (t >> 5) & 7, vh = t >> 8;  // 32 tasks per phase over the 16 warps: v = vh + 2 it, plane g = warp & 7
         const double a0 = sDh[c4 + n * r], a1 = sDh[c4 + 4 + n * r];
-#pragma unroll 2
-        for (int task = t >> 5; task < 32; task += n3 / 32) {
-            const int v = task >> 3, g = task & 7;
-            const double h0 = smem[(8 + v) * n3 + idx_m8(r, g, c4)], h1 = smem[(8 + v) * n3 + idx_m8(r, g, c4 + 4)];
-            double c0 = 0.0, c1 = 0.0;
-            dmma_m8n8k4(c0, c1, h0, a0);
-            dmma_m8n8k4(c0, c1, h1, a1);
-            smem[(12 + v) * n3 + idx_m8(r, g, 2 * c4)] = c0;
-            smem[(12 + v) * n3 + idx_m8(r, g, 2 * c4 + 1)] = c1;
+        {
+            const int ih0 = idx_m8(r, g, c4), ih1 = idx_m8(r, g, c4 + 4), io0 = idx_m8(r, g, 2 * c4), io1 = idx_m8(r, g, 2 * c4 + 1);
+#pragma unroll
+            for (int it = 0; it < 2; it++) {
+                const int v = vh + 2 * it;
+                const double h0 = smem[(8 + v) * n3 + ih0], h1 = smem[(8 + v) * n3 + ih1];
+                double c0 = 0.0, c1 = 0.0;
+                dmma_m8n8k4(c0, c1, h0, a0);
+                dmma_m8n8k4(c0, c1, h1, a1);
+                smem[(12 + v) * n3 + io0] = c0;
+                smem[(12 + v) * n3 + io1] = c1;
+            }
         }
         __syncthreads();
-#pragma unroll 2
-        for (int task = t >> 5; task < 32; task += n3 / 32) {
-            const int v = task >> 3, g = task & 7;
-            double c0 = smem[(12 + v) * n3 + idx_m8(r, 2 * c4, g)], c1 = smem[(12 + v) * n3 + idx_m8(r, 2 * c4 + 1, g)];
-            const double f0 = smem[v * n3 + idx_m8(c4, r, g)], f1 = smem[v * n3 + idx_m8(c4 + 4, r, g)];
-            const double g0 = smem[(4 + v) * n3 + idx_m8(r, c4, g)], g1 = smem[(4 + v) * n3 + idx_m8(r, c4 + 4, g)];
-            dmma_m8n8k4(c0, c1, a0, f0);
-            dmma_m8n8k4(c0, c1, a1, f1);
-            dmma_m8n8k4(c0, c1, g0, a0);
-            dmma_m8n8k4(c0, c1, g1, a1);
-            double* o = UtV + v * n3 + (r + n * (2 * c4) + n2 * g);
-            o[0] = c0;
-            o[n] = c1;
+        {
+            const int ic0 = idx_m8(r, 2 * c4, g), ic1 = idx_m8(r, 2 * c4 + 1, g);
+            const int if0 = idx_m8(c4, r, g), if1 = idx_m8(c4 + 4, r, g), ig0 = idx_m8(r, c4, g), ig1 = idx_m8(r, c4 + 4, g);
+#pragma unroll
+            for (int it = 0; it < 2; it++) {
+                const int v = vh + 2 * it;
+                double c0 = smem[(12 + v) * n3 + ic0], c1 = smem[(12 + v) * n3 + ic1];
+                const double f0 = smem[v * n3 + if0], f1 = smem[v * n3 + if1];
+                const double g0 = smem[(4 + v) * n3 + ig0], g1 = smem[(4 + v) * n3 + ig1];
+                dmma_m8n8k4(c0, c1, a0, f0);
+                dmma_m8n8k4(c0, c1, a1, f1);
+                dmma_m8n8k4(c0, c1, g0, a0);
+                dmma_m8n8k4(c0, c1, g1, a1);
+                double* o = UtV + v * n3 + (r + n * (2 * c4) + n2 * g);
+                o[0] = c0;
+                o[n] = c1;
+            }
         }
     } else {
 #pragma unroll

@@ -60,7 +60,7 @@ def b_alg_lifting(n: int) -> float:
 
 
 def build_case(ngpus: int, rank: int, elems=None, N=N_POLY):
-    from galaexi_b200.host import basis as bs, case as cs, equation as eq, mesh as ms
+    from galaexi_b200.host_standin import basis as bs, case as cs, equation as eq, mesh as ms
     import cases
     dims = elems or box_dims(ngpus)
     L = tuple(2 * np.pi * d / min(dims) for d in dims)

@@ -1,7 +1,7 @@
 """Host-side mirror of the reference's DG module interface over the C ABI (include/dgx.h).
 
 The reference toolchain (nvfortran) is absent here, so this Python driver plays the role of the
-Fortran host: it feeds the arrays built by ``galaexi_b200.host`` (the stand-in for InitMesh /
+Fortran host: it feeds the arrays built by ``galaexi_b200.host_standin`` (the stand-in for InitMesh /
 InitInterpolation / InitEquation) through ``dgx_create`` and calls the same procedures, with the same
 names and argument meaning, that ``src/timedisc`` calls in the reference:
 
@@ -275,7 +275,7 @@ class DGSolver:
     def AnalyzeTestcase(self, NAnalyze: int | None = None, Vol: float | None = None, rho0: float = 1.0) -> np.ndarray:
         """The 15 TGVAnalysis columns (testcase/taylorgreenvortex/testcase.f90:283-515), integrated on the device.
         Vol: global volume (all ranks); defaults to this rank's volume (single-rank runs)."""
-        from .host import analyze as an
+        from .host_standin import analyze as an
         key = (NAnalyze,)
         if getattr(self, "_an_key", None) != key:
             NA, V, wA = an.init_analyze_basis(self.case.N, self.case.node_type, NAnalyze)
@@ -300,7 +300,7 @@ class DGSolver:
 
     def CalcForcing(self, Vol: float | None = None) -> float:
         """CalcForcing of the channel testcase (testcase/channel/testcase.f90:241-271): the bulk velocity."""
-        from .host import analyze as an
+        from .host_standin import analyze as an
         w = np.ascontiguousarray(self.case.basis.wGP, dtype=np.float64)
         b = C.c_double()
         self._ck(self.lib.dgx_calc_bulk_velocity(self.h, w.ctypes.data_as(_dp), float(an.volume(self.case) if Vol is None else Vol),
@@ -310,7 +310,7 @@ class DGSolver:
     def CalcErrorNorms(self, Time: float, exact, NAnalyze: int | None = None, Vol: float | None = None, reduce=None):
         """CalcErrorNorms(Time,L_2_Error,L_Inf_Error) (analyze.f90:383-470) on the downloaded state; ``exact(x, t)`` plays
         ExactFunc(AnalyzeExactFunc, ...). Host arithmetic like the reference (it analyses the host copy U = d_U)."""
-        from .host import analyze as an
+        from .host_standin import analyze as an
         return an.calc_error_norms(self.case, self.get_state(), Time, exact, NAnalyze, Vol, reduce)
 
     def CalcBodyForces(self):
@@ -328,7 +328,7 @@ class DGSolver:
     def CalcWallVelocity(self, Surf: np.ndarray | None = None):
         """CalcWallVelocity(maxV,minV,meanV) (analyze_equation.f90:435-499); Surf(nBCs): global surface per boundary condition
         (default: integrated from this rank's SurfElem, i.e. single-rank)."""
-        from .host import analyze as an
+        from .host_standin import analyze as an
         m = self.case.mesh
         nBCs = int(m.BoundaryType.shape[0])
         w = np.ascontiguousarray(self.case.basis.wGP, dtype=np.float64)
@@ -347,7 +347,7 @@ class DGSolver:
                    NOut: int | None = None, dt: float | None = None, ini_text: str = "", isErrorFile: bool = False, barrier=None) -> str:
         """WriteState (io_hdf5/hdf5_output.f90:84-211): D2H of U through dgx_get_state and a state file in the reference
         layout (readable by posti and by the reference's Restart). All ranks call it; each writes its own element range."""
-        from .host import state_io
+        from .host_standin import state_io
         m = self.case.mesh
         ed = {"myRank": float(m.myRank)}
         if dt is not None:
@@ -359,7 +359,7 @@ class DGSolver:
 
     def WriteBaseFlow(self, MeshFileName: str, OutputTime: float, FutureTime: float, ProjectName: str, out_dir: str = ".", barrier=None) -> str:
         """WriteBaseflow (io_hdf5/hdf5_output.f90:527-603) of the sponge base flow held on the device (dgx_get_baseflow)."""
-        from .host import state_io
+        from .host_standin import state_io
         m = self.case.mesh
         return state_io.write_baseflow(self.get_baseflow(), self.case.N, self.case.node_type, ProjectName, MeshFileName, OutputTime,
                                        FutureTime, out_dir=out_dir, offsetElem=m.offsetElem, nGlobalElems=m.nGlobalElems, rank=m.myRank,
@@ -368,7 +368,7 @@ class DGSolver:
     def Restart(self, RestartFile: str, ResetTime: bool = False) -> float:
         """InitRestart + Restart (restart/restart.f90:60-135, 304-560): this rank's element range of DG_Solution, interpolated
         when the file's degree / node type differ, H2D through dgx_set_state; returns RestartTime."""
-        from .host import metrics, state_io
+        from .host_standin import metrics, state_io
         m = self.case.mesh
         info = state_io.read_state_attrs(RestartFile)
         dj = metrics.det_jac_ref(m.NodeCoords, m.NGeo, self.case.node_type) if info["N"] > self.case.N else None

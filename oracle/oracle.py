@@ -109,7 +109,7 @@ def _i(a):
 
 
 class Oracle:
-    """One single-rank DG operator instance built from a galaexi_b200.host.case.Case."""
+    """One single-rank DG operator instance built from a galaexi_b200.host_standin.case.Case."""
 
     def __init__(self, case, precision: str = "double"):
         self.prec = _PREC[precision]
@@ -128,7 +128,7 @@ class Oracle:
         SideToElem = -np.ones((nS_, 5)) if SideToElem is None else SideToElem
         mortar = getattr(case, "mortar", None)
         if mortar is None:
-            from galaexi_b200.host import mortar as _mo
+            from galaexi_b200.host_standin import mortar as _mo
             mortar = _mo.init_mortar(case.N, case.node_type)
         # keep references: the C side stores raw pointers
         f64 = lambda a: np.ascontiguousarray(a, dtype=self.prec.np)

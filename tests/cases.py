@@ -3,10 +3,10 @@ import os
 
 import numpy as np
 
-from galaexi_b200.host import basis as bs
-from galaexi_b200.host import case as cs
-from galaexi_b200.host import equation as eq
-from galaexi_b200.host import mesh as ms
+from galaexi_b200.host_standin import basis as bs
+from galaexi_b200.host_standin import case as cs
+from galaexi_b200.host_standin import equation as eq
+from galaexi_b200.host_standin import mesh as ms
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -162,7 +162,7 @@ def manufactured_case(mesh="cart_periodic_004", N=3, nProcs=1, myRank=0, **kw):
 
 def l2_error(c, U, t, NAnalyze=None, exact=None):
     """CalcErrorNorms (analyze/analyze.f90:383-470): L2 error against the exact function on the analysis nodes."""
-    from galaexi_b200.host import analyze as an
+    from galaexi_b200.host_standin import analyze as an
     return an.calc_error_norms(c, U, t, exact or exact_sine, NAnalyze)[0]
 
 
@@ -170,7 +170,7 @@ def naca_regression_case(nProcs=1, myRank=0):
     """regressioncheck/checks/naca/3D/parameter.ini: NACA0012, Re=5000, AoA 8 deg; N=3 Gauss, weak form, BR1, build-default
     RoeEntropyFix, curved NGeo=2 mesh, BCs 2 (refstate) / 3 (adiabatic wall) / periodic z, sponge ramp from x=2 over a distance
     of 3 with the Pruett base flow (tempFilterWidth 2). Returns case, initial state, tempFilterWidth."""
-    from galaexi_b200.host import sponge as sp
+    from galaexi_b200.host_standin import sponge as sp
     h = load_mesh("naca_mesh.npz")
     eos = eq.Eos(kappa=1.4, R=2.857142857, Pr=0.72, mu0=0.0002)
     c = cs.build_case(h, 3, bs.NODETYPE_G, split=None, riemann="RoeEntropyFix", parabolic=True, eos=eos,

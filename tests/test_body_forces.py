@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import cases
-from galaexi_b200.host import equation as eq
+from galaexi_b200.host_standin import equation as eq
 from oracle.analyze_body_forces import calc_body_forces, calc_wall_velocity
 
 
@@ -74,7 +74,7 @@ def _gpu_forces(c, U, t=0.0):
 
 
 def _oracle_wall_velocity(c, U):
-    from galaexi_b200.host import analyze as an
+    from galaexi_b200.host_standin import analyze as an
     from oracle.oracle import Oracle
     o = Oracle(c, "double")
     o.set_state(U)
@@ -87,7 +87,7 @@ def _oracle_wall_velocity(c, U):
 def test_wall_velocity_oracle_uniform_flow():
     """Uniform |v| = 3 along slip walls of the duct: max = min = mean = 3 on the wall BCs, the reference's initial values
     (-1e14, 1e14, 0) elsewhere; Surf of a BC without sides is HUGE."""
-    from galaexi_b200.host import analyze as an
+    from galaexi_b200.host_standin import analyze as an
     c, U, _ = cases.duct_case((2, 1), (24, 1), (9, 0), parabolic=False)
     v0 = np.sqrt(np.sum((U[..., 1:4] / U[..., :1]) ** 2, axis=-1)).max()
     mx, mn, me = _oracle_wall_velocity(c, U)

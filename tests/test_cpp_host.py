@@ -75,7 +75,7 @@ def test_cpp_host_compiles_and_links():
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["tgv_curved", "mortar_br2"])
 def test_cpp_host_runs_the_reference_call_sequence(name, tmp_path):
-    from galaexi_b200.host import timeloop
+    from galaexi_b200.host_standin import timeloop
     from oracle.oracle import Oracle
     if name == "tgv_curved":
         c, U0 = cases.tgv_box_case(E=3, N=4, NGeo=2, deform=0.05, perturb=1e-3)

@@ -9,10 +9,10 @@ import numpy as np
 import pytest
 
 import cases
-from galaexi_b200.host import basis as bs
-from galaexi_b200.host import equation as eq
-from galaexi_b200.host import timedisc as td
-from galaexi_b200.host import timeloop
+from galaexi_b200.host_standin import basis as bs
+from galaexi_b200.host_standin import equation as eq
+from galaexi_b200.host_standin import timedisc as td
+from galaexi_b200.host_standin import timeloop
 
 
 @pytest.mark.parametrize("N", [1, 2, 3, 5, 7, 9])

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import cases
-from galaexi_b200.host import timeloop
+from galaexi_b200.host_standin import timeloop
 
 pytestmark = pytest.mark.gpu
 
@@ -121,7 +121,7 @@ def test_weak_form_navier_stokes(node_type):
 @pytest.mark.parametrize("riemann", ["HLL", "HLLE", "HLLEM", "HLLC"])
 def test_hll_family_supersonic(riemann):
     """Mach 2.5 stream: exercises the one-sided (Ssl >= 0) branches of the HLL-type solvers."""
-    from galaexi_b200.host import basis as bs, case as cs, equation as eq, mesh as ms
+    from galaexi_b200.host_standin import basis as bs, case as cs, equation as eq, mesh as ms
     h = ms.make_box_mesh((3, 2, 2), NGeo=2, deform=0.03)
     c = cs.build_case(h, 3, bs.NODETYPE_G, split=None, riemann=riemann, parabolic=False, eos=eq.Eos(kappa=1.4, R=1.0),
                       refstates=((1.0, 3.0, 0.0, 0.0, 1.0),))
@@ -144,7 +144,7 @@ def test_inflow_outflow_slip_bcs(inflow, outflow, wall, form):
 
 
 def test_sutherland_viscosity():
-    from galaexi_b200.host import equation as eq
+    from galaexi_b200.host_standin import equation as eq
     eos = eq.Eos(kappa=1.4, R=71.42857, Pr=0.72, mu0=6.25e-4, visc_law=1, Ts=0.4, Tref=1.0, ExpoSuth=1.5)
     c, U0 = cases.tgv_box_case(E=3, N=3, eos=eos, perturb=1e-3)
     _compare_rhs_and_steps(c, U0)
@@ -216,7 +216,7 @@ def test_freestream_and_conservation_full_size():
     size; here: constant state -> Ut == 0 (to round-off) and sum_w J Ut == 0 for the periodic TGV (conservation)."""
     c, U0 = cases.tgv_box_case(E=32, N=7)
     s = _solver(c)
-    from galaexi_b200.host import equation as eq
+    from galaexi_b200.host_standin import equation as eq
     const = eq.ini_refstate(c.geo["Elem_xGP"], c.RefStatePrim[0], c.eos)
     s.set_state(const)
     s.DGTimeDerivative_weakForm(0.0)
@@ -260,7 +260,7 @@ def test_mortar_meshes(mesh, N, node_type, split, riemann, lifting):
 
 
 def test_mortar_euler_and_free_stream():
-    from galaexi_b200.host import equation as eq
+    from galaexi_b200.host_standin import equation as eq
     c, U0 = cases.mortar_case("004", N=3, parabolic=False, riemann="Roe")
     _compare_rhs_and_steps(c, U0, nsteps=2)
     c, _ = cases.mortar_case("004", N=4, node_type="GAUSS-LOBATTO", split="PI", riemann="RoeEntropyFix")
@@ -296,7 +296,7 @@ def test_br2_lifting(name, kw):
 def test_tgv_analysis_matches_oracle():
     """dgx_analyze_tgv vs the numpy restatement of AnalyzeTestcase on the same state and gradients (curved mesh, default
     NAnalyze = 2 (N+1))."""
-    from galaexi_b200.host import analyze as an
+    from galaexi_b200.host_standin import analyze as an
     from oracle.analyze_tgv import analyze_tgv
     c, U0 = cases.tgv_box_case(E=3, N=4, NGeo=2, deform=0.05, perturb=1e-3)
     s, o = _solver(c), _oracle(c)
@@ -431,8 +431,8 @@ def test_h_convergence_manufactured_navier_stokes():
     shorter end time: conforming family (the 16^3 mesh is generated, same box): either that 80 % rule or all five variables
     above 0.85 (N+1) on the finest pair (measured: 3.2-3.7 on the coarse pairs, 4.2-4.7 on 8 -> 16); mortar family (2/4/8
     levels ship): every order within 0.25 of the conforming one on the same level pair (measured: equal or higher)."""
-    from galaexi_b200.host import equation as eq
-    from galaexi_b200.host import mesh as ms
+    from galaexi_b200.host_standin import equation as eq
+    from galaexi_b200.host_standin import mesh as ms
     N, tEnd = 3, 0.2
     res = {}
     for family, levels in (("cart_periodic", ("002", "004", "008", "016")), ("cart_mortar", ("002", "004", "008"))):
@@ -459,7 +459,7 @@ def test_h_convergence_manufactured_navier_stokes():
 def test_channel_forcing():
     """BASELINE config #4 made physically meaningful: bulk velocity on the device vs the oracle, and the
     reference's time loop `CalcForcing; TimeStep` (timedisc.f90:185-187) with the pressure-gradient forcing dpdx = -1."""
-    from galaexi_b200.host import analyze as an
+    from galaexi_b200.host_standin import analyze as an
     c, U0 = cases.channel_case(E=4, N=5)
     o, s = _oracle(c), _solver(c)
     o.set_state(U0)
@@ -551,7 +551,7 @@ def test_run_basic_freestream_matrix(mesh):
     six Dirichlet BCs (type 2, RefState 1), RefState (1,1,1,1,1), mu0 = 1.8547e-5, R = 1, CFLscale 0.99, DFLscale 0.4,
     tend = 1e-6; analyze.ini: L2 error <= 1e-1). Held here: 1e-12. Second variant: a mortar mesh with the same BCs
     (hopr_mortar.ini of the check describes one; the mesh file itself does not ship)."""
-    from galaexi_b200.host import basis as bs, case as cs, equation as eq, mesh as ms
+    from galaexi_b200.host_standin import basis as bs, case as cs, equation as eq, mesh as ms
     worst = 0.0
     for N, nt, par, visc, split in _FS_MATRIX:
         if mesh == "cartbox":
@@ -579,7 +579,7 @@ def test_p_convergence_manufactured_navier_stokes():
     IniExactFunc=4 + CalcSource, mu0=1e-3, CFLscale 0.25, tend shortened to 0.1. reggie's p-convergence criterion
     (analyze_Convtest_p_rate / _percentage): the order of convergence must INCREASE from one degree to the next in at least
     75 % of the steps -- i.e. spectral convergence. Asserted per variable on the density / momentum / energy L2 errors."""
-    from galaexi_b200.host import equation as eq
+    from galaexi_b200.host_standin import equation as eq
     tEnd = 0.1
     Ns = [2, 3, 4, 5, 6, 7, 8, 9]
     errs = []
@@ -719,7 +719,7 @@ def test_write_state_and_restart_continue_bit_exact(tmp_path):
     """WriteState at t1 + Restart into a fresh handle continues bit-identically to the uninterrupted run (the state file
     holds U in full FP64 and the RK scheme has no memory across steps); restart on another degree / node type
     (restart.f90:455-523) reproduces the file's polynomial on the new nodes."""
-    from galaexi_b200.host import state_io
+    from galaexi_b200.host_standin import state_io
     c, U0 = cases.cavity_case()
     s = _solver(c)
     s.set_state(U0)
@@ -753,7 +753,7 @@ def test_restart_from_reference_state_file_layout(tmp_path):
     """The reference's own cavity state (fixture arrays) written in its layout, restarted, advanced: the RHS of the restarted
     handle equals the oracle's on the same state."""
     import os
-    from galaexi_b200.host import state_io
+    from galaexi_b200.host_standin import state_io
     c, _ = cases.cavity_case()
     ref = np.load(os.path.join(cases.GOLD, "cavity3d_state.npz"))["DG_Solution"]
     path = state_io.write_state(ref, 2, "GAUSS", "cavity_Re100", "cavity4x4x4_mesh.h5", 1.0, 2.0, out_dir=str(tmp_path))

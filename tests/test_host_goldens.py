@@ -1,4 +1,4 @@
-"""Host init mirror (galaexi_b200.host) against the reference's own unit-test golden files (unitTests/*.bin,
+"""Host init mirror (galaexi_b200.host_standin) against the reference's own unit-test golden files (unitTests/*.bin,
 converted by tools/make_golden.py into tests/golden/unit_goldens.npz). CPU only.
 
 Criterion of the reference's unit tests: ALMOSTEQUALABSORREL(x, ref, 100*PP_RealTolerance) with
@@ -10,9 +10,9 @@ import os
 import numpy as np
 import pytest
 
-from galaexi_b200.host import basis as bs
-from galaexi_b200.host import mappings as mp
-from galaexi_b200.host import mesh as ms
+from galaexi_b200.host_standin import basis as bs
+from galaexi_b200.host_standin import mappings as mp
+from galaexi_b200.host_standin import mesh as ms
 
 TOL = 100.0 * np.finfo(np.float64).eps
 TYPES = ("GAUSS", "GAUSS-LOBATTO", "CHEBYSHEV-GAUSS-LOBATTO", "VISU")
@@ -209,7 +209,7 @@ def test_change_basis_unit_golden(goldens):
     """unitTests/ChangeBasis.f90: ChangeBasis3D / ChangeBasis3D_XYZ / ChangeBasis2D with the test's synthetic Vandermonde
     matrices (NIn=4 -> NOut=5) against ChangeBasis.bin (50 eps). The same tensor-product routine interpolates the metrics,
     feeds the analysis quadrature and -- with a square matrix -- is the modal filter of the RHS."""
-    from galaexi_b200.host import metrics as mt
+    from galaexi_b200.host_standin import metrics as mt
     nVar, NIn, NOut, nElems = 3, 4, 5, 6
     V1 = np.zeros((NOut + 1, NIn + 1))
     V2, V3 = np.zeros_like(V1), np.zeros_like(V1)
@@ -242,7 +242,7 @@ def test_oracle_filter_is_the_pinned_change_basis():
     """filter.f90:272-306 applies ChangeBasis3D with FilterMat in place: the oracle's restatement equals the golden-pinned
     host routine."""
     import cases
-    from galaexi_b200.host import metrics as mt
+    from galaexi_b200.host_standin import metrics as mt
     from oracle.oracle import Oracle
     c, U0 = cases.tgv_box_case(E=2, N=4, NGeo=2, deform=0.05, perturb=1e-2, FilterType="modal")
     o = Oracle(c)
@@ -257,7 +257,7 @@ def test_calc_error_norms_reference_norm_of_resting_cavity():
     """CalcErrorNorms (analyze.f90:383-470): exact for polynomial data, zero for the exact function itself, and the L2 / Linf
     pair of a known perturbation; Vol and the analysis quadrature integrate the deformed box exactly."""
     import cases
-    from galaexi_b200.host import analyze as an
+    from galaexi_b200.host_standin import analyze as an
     c, _ = cases.tgv_box_case(E=2, N=4, NGeo=2, deform=0.05, split=None, riemann="Roe")
     assert abs(an.volume(c) - (2.0 * np.pi) ** 3) < 1e-10 * (2.0 * np.pi) ** 3
     f = lambda x, t: np.stack([1.0 + 0.1 * x[..., 0] * t, x[..., 1] ** 2, x[..., 2], 0.0 * x[..., 0], 2.0 + x[..., 0] * x[..., 1]], axis=-1)
@@ -287,7 +287,7 @@ def test_h5lite_reads_every_hdf5_file_of_the_reference():
     opens and every data set in it can be read; the one exception is h5diff/cavity/..._0000000.200000000.h5, whose HDF5
     signature sits at byte 4104 -- not a valid userblock size, libhdf5 rejects it too (its analyze.ini has the file commented out)."""
     import subprocess
-    from galaexi_b200.host import h5lite
+    from galaexi_b200.host_standin import h5lite
     files = subprocess.check_output(["find", "/root/reference", "-name", "*.h5"], text=True).split()
     assert len(files) > 100
     nds, failed = 0, []

@@ -1,4 +1,4 @@
-"""N>1 on CPU (gloo, world_size 2 and 3): the SFC partition + side numbering + halo tables of galaexi_b200.host,
+"""N>1 on CPU (gloo, world_size 2 and 3): the SFC partition + side numbering + halo tables of galaexi_b200.host_standin,
 the reference's four-phase halo flow restated around the oracle, and the C library's two-phase halo message plan.
 
 Criterion: the reference's own MPI=1 vs MPI=2 invariance (regressioncheck parabolic/cavity_3D runs both against one
@@ -126,7 +126,7 @@ def _state_worker(rank, world, port, out_dir, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from galaexi_b200.host import state_io
+        from galaexi_b200.host_standin import state_io
         c, U0 = _build("cavity", world, rank)
         ms = c.mesh
         path = state_io.write_state(U0, c.N, c.node_type, "mr", "cavity4x4x4_mesh.h5", 0.125, 0.25, out_dir=out_dir,
@@ -147,7 +147,7 @@ def _state_worker(rank, world, port, out_dir, q):
 def test_ranks_write_one_state_file_and_restart_from_it(tmp_path):
     """WriteState on 3 ranks (GatheredWriteArray's role: every rank writes its contiguous element range, rank 0 the skeleton and
     the closing TIME attribute) gives the file a single rank writes; each rank reads its own range back."""
-    from galaexi_b200.host import h5lite, state_io
+    from galaexi_b200.host_standin import h5lite, state_io
     world = 3
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

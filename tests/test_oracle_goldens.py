@@ -13,11 +13,11 @@ import numpy as np
 import pytest
 
 import cases
-from galaexi_b200.host import basis as bs
-from galaexi_b200.host import equation as eq
-from galaexi_b200.host import mappings as mp
-from galaexi_b200.host import timedisc as td
-from galaexi_b200.host import timeloop
+from galaexi_b200.host_standin import basis as bs
+from galaexi_b200.host_standin import equation as eq
+from galaexi_b200.host_standin import mappings as mp
+from galaexi_b200.host_standin import timedisc as td
+from galaexi_b200.host_standin import timeloop
 from oracle.oracle import Oracle
 from test_host_goldens import almost_equal_abs_or_rel
 
@@ -197,7 +197,7 @@ def test_tgv_analysis_oracle_reproduces_reference_csv_columns():
     parameter.ini) at t=0 and after 10 and 20 time steps. Reference criterion for this file: rel 1e-4 (analyze.ini); the
     restatement holds 1e-9 relative to the column's magnitude over the file (columns that are round-off zeros at t=0 -- DR_p,
     ED_D -- are compared absolutely)."""
-    from galaexi_b200.host import analyze as an
+    from galaexi_b200.host_standin import analyze as an
     from oracle.analyze_tgv import analyze_tgv
     c, U0 = cases.tgv_split_case()
     rows = np.load(os.path.join(cases.GOLD, "tgv_split_csv.npz"))["rows"]

@@ -10,10 +10,10 @@ import numpy as np
 import pytest
 
 import cases
-from galaexi_b200.host import basis as bs
-from galaexi_b200.host import equation as eq
-from galaexi_b200.host import mesh as ms
-from galaexi_b200.host import mortar as mo
+from galaexi_b200.host_standin import basis as bs
+from galaexi_b200.host_standin import equation as eq
+from galaexi_b200.host_standin import mesh as ms
+from galaexi_b200.host_standin import mortar as mo
 from oracle.oracle import Oracle
 
 

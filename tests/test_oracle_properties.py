@@ -7,10 +7,10 @@ import numpy as np
 import pytest
 
 import cases
-from galaexi_b200.host import basis as bs
-from galaexi_b200.host import case as cs
-from galaexi_b200.host import equation as eq
-from galaexi_b200.host import mesh as ms
+from galaexi_b200.host_standin import basis as bs
+from galaexi_b200.host_standin import case as cs
+from galaexi_b200.host_standin import equation as eq
+from galaexi_b200.host_standin import mesh as ms
 from oracle.oracle import Oracle
 
 SPLITS = ["SD", "MO", "DU", "KG", "PI"]
@@ -163,8 +163,8 @@ def test_slip_wall_variants_differ_only_in_viscous_flux():
 # ---- modal filter (dg.f90:331, filter/filter.f90) ------------------------------------------------------------------------
 @pytest.mark.parametrize("node_type", ["GAUSS", "GAUSS-LOBATTO"])
 def test_filter_matrix_properties(node_type):
-    from galaexi_b200.host import basis as bs
-    from galaexi_b200.host import filter as fl
+    from galaexi_b200.host_standin import basis as bs
+    from galaexi_b200.host_standin import filter as fl
     N, Nc = 6, 3
     F = fl.filter_matrix(N, node_type, "cutoff", NFilter=Nc)
     x, w, _ = bs.get_nodes_and_weights(N, node_type)
@@ -225,7 +225,7 @@ def test_manufactured_source_balances_the_operator(parabolic):
 def test_channel_forcing_oracle():
     """TestcaseSource adds -dpdx to the x-momentum and -dpdx*BulkVel to the energy equation (after the Jacobian); CalcForcing
     integrates the bulk velocity (here checked against the analytic mean of the parabolic profile of the test state)."""
-    from galaexi_b200.host import analyze as an
+    from galaexi_b200.host_standin import analyze as an
     c, U0 = cases.channel_case(E=3, N=4)
     o = Oracle(c)
     o.set_state(U0)
@@ -250,7 +250,7 @@ def test_channel_forcing_oracle():
 def test_time_loop_dt_reuse_rule():
     """UpdateTimeStep (timedisc_func.f90:246-300): with NCalcTimeStepMax > 1 dt is re-evaluated less often the slower it
     changes; the default (1) evaluates it every step. Checked on a stub operator with a slowly drifting dt."""
-    from galaexi_b200.host import timeloop
+    from galaexi_b200.host_standin import timeloop
 
     class Op:
         def __init__(self):

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from galaexi_b200.host import output
+from galaexi_b200.host_standin import output
 
 REF = "/root/reference"
 
@@ -40,6 +40,6 @@ def test_reference_csv_files_are_reproduced_byte_for_byte(tmp_path, rel):
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
 def test_tgv_column_names_are_the_reference_header():
-    from galaexi_b200.host import analyze as an
+    from galaexi_b200.host_standin import analyze as an
     hdr = open(os.path.join(REF, "regressioncheck/checks/tgv/split/TGV_Re1600_Split_TGVAnalysis_Reference.csv")).readline().strip().split(",")
     assert hdr == ["Time"] + list(an.TGV_COLUMNS)

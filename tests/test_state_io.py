@@ -1,4 +1,4 @@
-"""State files in the reference layout + restart: galaexi_b200/host/h5write.py, state_io.py.
+"""State files in the reference layout + restart: galaexi_b200/host_standin/h5write.py, state_io.py.
 
 No HDF5 library exists here, so the writer is pinned against what libhdf5 itself wrote: tests/golden/state_h5_structs.json
 holds the raw superblock / attribute messages / dataset header messages / heap / B-tree bytes of the reference's shipped
@@ -13,8 +13,8 @@ import struct
 import numpy as np
 import pytest
 
-from galaexi_b200.host import basis as bs
-from galaexi_b200.host import h5lite, h5write, metrics, state_io
+from galaexi_b200.host_standin import basis as bs
+from galaexi_b200.host_standin import h5lite, h5write, metrics, state_io
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -348,7 +348,7 @@ def test_restart_reads_files_written_by_libhdf5(rel, N, nt, nE, t):
 def test_hopr_mesh_writer_round_trip_of_generated_meshes(tmp_path):
     """write_hopr_mesh: a generated (curved, periodic / wall) box in the HOPR layout reads back to the same arrays and builds the
     same case tables; unique node / side counts as HOPR counts them."""
-    from galaexi_b200.host import mesh as ms
+    from galaexi_b200.host_standin import mesh as ms
     h = ms.make_box_mesh((3, 2, 2), NGeo=2, deform=0.05, bctype=["periodic", (4, 1), "periodic", (4, 1), "periodic", "periodic"])
     p = str(tmp_path / "box_mesh.h5")
     h5write.write_hopr_mesh(p, h)

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import cases
-from galaexi_b200.host import timedisc as td
+from galaexi_b200.host_standin import timedisc as td
 
 
 def _step_k3(f, u, t, dt, T):
@@ -57,7 +57,7 @@ def test_unknown_scheme_is_rejected():
 def test_oracle_k3_free_stream_and_agreement_with_carpenter(name):
     """Oracle DG run: the free stream is preserved to round-off (timedisc/freestream_3D), and at a small fixed dt the solution
     equals the Carpenter RK4-5 one up to the (tiny) time-integration errors of both."""
-    from galaexi_b200.host import equation as eq
+    from galaexi_b200.host_standin import equation as eq
     from oracle.oracle import Oracle
     c, U0 = cases.tgv_box_case(E=2, N=3, NGeo=2, deform=0.05, perturb=1e-3, timedisc=name)
     o = Oracle(c)

@@ -2,7 +2,7 @@
 import numpy as np
 
 import cases
-from galaexi_b200.host import timeloop
+from galaexi_b200.host_standin import timeloop
 
 
 class _Stub:

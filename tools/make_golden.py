@@ -17,7 +17,7 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
-from galaexi_b200.host import h5lite  # noqa: E402
+from galaexi_b200.host_standin import h5lite  # noqa: E402
 
 REF = "/root/reference"
 OUT = os.path.join(os.path.dirname(__file__), "..", "tests", "golden")
@@ -106,7 +106,7 @@ def unit_goldens_emm():
 def state_h5_structs():
     """The HDF5 structures libhdf5 wrote into the reference's cavity state file, as hex strings: superblock, the root
     attribute messages, the object-header messages of DG_Solution / ElemData, the local heap and the B-tree / symbol node
-    heads. tests/test_state_io.py compares what galaexi_b200/host/h5write.py emits with them."""
+    heads. tests/test_state_io.py compares what galaexi_b200/host_standin/h5write.py emits with them."""
     import json
     import struct
     f = h5lite.H5File(os.path.join(REF, "regressioncheck/checks/parabolic/cavity_3D/reggie_cavity_Re100_State_0000001.000000000.h5"))

@@ -2,21 +2,28 @@
 """Headline benchmark: PID / DOF-updates per second of the DG RHS + LSERK stage (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--config 2|3|4|5] [--scaling weak|strong] [--degree N] [--elems E] [--curved]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...       (one rank per GPU, N>1)
 
-Workload (config.workload): BASELINE config #2 -- Taylor-Green vortex, Navier-Stokes, N=7 Gauss-Lobatto,
-split form (Pirozzoli) + BR1 lifting, RoeEntropyFix, CarpenterRK4-5, 32^3 elements PER GPU (weak scaling:
-the global box grows with the GPU count and is cut along the Hilbert curve like the reference does).
-A "step" is one full RK time step (5 stages) including CalcTimeStep and its min-reduction, exactly the
-window the reference's PID covers (src/output/output.f90:430).
+Default line (config.workload): BASELINE config #2 -- Taylor-Green vortex, Navier-Stokes, N=7 Gauss-Lobatto, split form
+(Pirozzoli) + BR1 lifting, RoeEntropyFix, CarpenterRK4-5, 32^3 elements PER GPU (weak scaling: the global box grows with the
+GPU count and is cut along the Hilbert curve like the reference does). A "step" is one full RK time step (5 stages)
+including CalcTimeStep and its min-reduction, exactly the window the reference's PID covers (src/output/output.f90:430).
 
-One JSON line on rank 0; see the task contract for the keys. `value` = DOF-updates/s (DOF x RK stages / s,
-whole job) with the state resident in HBM; `e2e` = the same metric through the C ABI with HOST buffers
-(dgx_set_state + dgx_rk_step + dgx_get_state every step, H2D/D2H inside the timed region).
+--config selects the other BASELINE configurations (3: TGV N=5 on the 64^3 box, weak = 32^3 per GPU / strong = 64^3 in total;
+4: turbulent channel N=5 with isothermal walls and the pressure-gradient forcing; 5: NACA0012 N=4 on the tutorial's curved
+mesh). The default invocation also measures config #3 (weak) with a few steps and attaches it as `extras.config3_weak`.
+
+One JSON line on rank 0; see the task contract for the keys. `value` = DOF-updates/s (DOF x RK stages / s, whole job) with the
+state resident in HBM; `e2e` = the same metric through the C ABI with HOST buffers (dgx_set_state + dgx_calc_timestep +
+dgx_rk_step + dgx_get_state every step, H2D/D2H inside the timed region). With N>1 the line carries `parity`: a small N-rank
+run (TGV 8^3 N=7 and a channel with walls) checked against the single-rank CPU oracle outside the timed region.
 """
 from __future__ import annotations
 
 import argparse
+import csv
+import io
 import json
 import os
 import subprocess
@@ -26,30 +33,77 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
-N_POLY = 7
-CURVED = False
-ELEMS_PER_GPU = 32          # 32^3 elements per GPU
 NSTAGES = 5
+FP64_PEAK_TFLOPS = 36.0   # measured DFMA rate of this pool's B200s (profiles/r02_fp64_rates_b200.txt, tools/microbench/fp64_rates.cu)
 
 
-def box_dims(ngpus: int):
-    """Global element counts for weak scaling: 32^3 per GPU."""
-    e = ELEMS_PER_GPU
-    return {1: (e, e, e), 2: (2 * e, e, e), 4: (2 * e, 2 * e, e), 8: (2 * e, 2 * e, 2 * e)}[ngpus]
+# ---------------------------------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------------------------------
+def workload_dims(cfg: int, scaling: str, world: int, elems):
+    from galaexi_b200.host_standin import workloads as wl
+    e = elems if elems is not None else 32
+    if cfg == 5:
+        return None, e
+    if scaling == "strong" and cfg in (3, 4):
+        return (2 * e, 2 * e, 2 * e), e
+    return wl.box_dims(world, e), e
 
 
+def workload_desc(cfg: int, scaling: str, world: int, degree=None, elems=None, curved=False, dims=None) -> str:
+    """config.workload (both arms print the same string; no mesh is built here)."""
+    from galaexi_b200.host_standin import workloads as wl
+    d, e = workload_dims(cfg, scaling, world, elems)
+    d = dims or d
+    if cfg != 5:
+        size = f"{d[0]}x{d[1]}x{d[2]} elements" + (" (fixed total)" if (scaling == "strong" and cfg in (3, 4)) else f" ({e}^3 per GPU)")
+        if dims is not None:
+            size = f"{d[0]}x{d[1]}x{d[2]} elements"
+    if cfg in (2, 3):
+        N = degree if degree is not None else (7 if cfg == 2 else 5)
+        return (f"TGV Navier-Stokes Re1600 Ma0.1, N={N} Gauss-Lobatto, split-form PI + BR1, RoeEntropyFix, CarpenterRK4-5, {size}"
+                + (", curved NGeo=2 mesh (sine deformation 0.1)" if curved else "") + f", adaptive dt, CFLscale=DFLscale={wl.TGV_CFL}")
+    if cfg == 4:
+        N = degree if degree is not None else 5
+        return (f"plane turbulent channel Re_tau=180, N={N} Gauss-Lobatto, split-form PI + BR1, RoeEntropyFix, isothermal walls (BC 4) at "
+                f"y=+-1, dp/dx forcing with CalcForcing every step, {size}, y-stretched, adaptive dt, CFLscale=DFLscale=0.5")
+    N = degree if degree is not None else 4
+    return (f"NACA0012 Re5000 AoA8, N={N} Gauss, weak form + BR1, RoeEntropyFix, tutorial mesh NACA0012_652_Ng2 (652 curved elements, "
+            f"BC 2 / adiabatic wall 3 / periodic z), fixed total, adaptive dt, CFLscale=DFLscale=0.9")
+
+
+def make_workload(cfg: int, scaling: str, world: int, rank: int, degree=None, elems=None, curved=False, dims=None):
+    """This rank's slice of BASELINE config `cfg` on `world` ranks."""
+    from galaexi_b200.host_standin import workloads as wl
+    d, _ = workload_dims(cfg, scaling, world, elems)
+    d = dims or d
+    desc = workload_desc(cfg, scaling, world, degree, elems, curved, dims)
+    if cfg in (2, 3):
+        N = degree if degree is not None else (7 if cfg == 2 else 5)
+        c, U0 = wl.tgv(d, N, nProcs=world, myRank=rank, curved=curved)
+    elif cfg == 4:
+        N = degree if degree is not None else 5
+        c, U0 = wl.channel(d, N, nProcs=world, myRank=rank)
+    elif cfg == 5:
+        N = degree if degree is not None else 4
+        c, U0 = wl.naca(N, nProcs=world, myRank=rank)
+    else:
+        raise SystemExit(f"unknown --config {cfg}")
+    return dict(c=c, U0=U0, N=N, forcing=cfg == 4, desc=desc, dims=d, cfg=cfg)
+
+
+# algorithmic bytes per DOF (DESIGN.md 4), n = N+1, Navier-Stokes
 def b_alg_stage(n: int) -> float:
-    """Algorithmic bytes per DOF per NS RK stage (SURVEY.md 8d / BASELINE.md 3)."""
+    """SURVEY.md 8d / BASELINE.md 3: whole NS RK stage as the reference's data flow needs it (volume gradients materialised)."""
     return 8.0 * (75.0 + 360.0 / n)
 
 
 def b_alg_volsurf(n: int) -> float:
-    """Algorithmic bytes per DOF of the dominant kernel k_volsurf2: reads U 5, the viscous volume integral
-    k_lifting left in Ut 4, metrics 9, sJ 1, Ut_tmp 5, face fluxes 30/n; writes Ut_tmp 5, U 5, next-stage face states 30/n."""
+    """k_volsurf2: reads U 5, the viscous volume integral k_lifting left in Ut 4, metrics 9, sJ 1, Ut_tmp 5, face fluxes 30/n;
+    writes Ut_tmp 5, U 5, next-stage face states 30/n."""
     return 8.0 * (34.0 + 60.0 / n)
 
 
@@ -59,19 +113,30 @@ def b_alg_lifting(n: int) -> float:
     return 8.0 * (19.0 + 156.0 / n)
 
 
-def build_case(ngpus: int, rank: int, elems=None, N=N_POLY):
-    from galaexi_b200.host_standin import basis as bs, case as cs, equation as eq, mesh as ms
-    import cases
-    dims = elems or box_dims(ngpus)
-    L = tuple(2 * np.pi * d / min(dims) for d in dims)
-    h = ms.make_box_mesh(dims, x0=(0.0, 0.0, 0.0), x1=L, NGeo=2, deform=0.1) if CURVED else ms.make_box_mesh(dims, x0=(0.0, 0.0, 0.0), x1=L, NGeo=1)
-    eos = eq.Eos(**cases.TGV_EOS)
-    c = cs.build_case(h, N, bs.NODETYPE_GL, split="PI", riemann="RoeEntropyFix", parabolic=True, eos=eos,
-                      refstates=cases.TGV_REF, nProcs=ngpus, myRank=rank, CFLScale=0.9, DFLScale=0.9)
-    U0 = eq.ini_tgv(c.geo["Elem_xGP"], eos)
-    return c, U0
+def b_alg_sideflux(n: int) -> float:
+    """k_sideflux per volume DOF (3/n sides per DOF): face states 10, gradient traces 24, geometry 10 in, flux 5 out."""
+    return 8.0 * 147.0 / n
 
 
+def b_alg_stage_fused(n: int) -> float:
+    """What the three fused kernels of this library have to move per DOF and stage (sum of the per-kernel figures)."""
+    return b_alg_lifting(n) + b_alg_sideflux(n) + b_alg_volsurf(n)
+
+
+KERNEL_BYTES = {"halo+lifting": b_alg_lifting, "sideflux": b_alg_sideflux, "volsurf_rk": b_alg_volsurf}
+KERNEL_OF = {"halo+lifting": "k_lifting", "sideflux": "k_sideflux", "volsurf_rk": "k_volsurf"}
+
+
+def load_counts():
+    """Executed FP64 flops and DRAM bytes per DOF of each kernel from committed ncu captures (profiles/kernel_counts.json, written
+    by tools/ncu_counts.py); the live ncu pass of this run (below) replaces them when it succeeds."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "kernel_counts.json")))
+    except Exception:
+        return {}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -87,7 +152,7 @@ class ClockSampler(threading.Thread):
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
                     break
@@ -134,12 +199,16 @@ def host_threads():
     return n
 
 
-def cpu_baseline(sample_elems=12, steps=1, N=N_POLY):
-    """The CPU oracle (a port of the reference algorithm, NOT the reference binary) on the host cores, on a bounded
-    sample of the same workload: TGV N=7 split-form NS on sample_elems^3 elements, `steps` RK steps."""
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arms (the oracle is the checker / the reported baseline, never the product path)
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_baseline(cfg=2, degree=None, sample_elems=16, steps=1):
+    """The CPU oracle (a port of the reference algorithm, NOT the reference binary) on the host cores, on a bounded sample of
+    the same workload: sample_elems^3 elements, `steps` RK steps (the per-DOF cost does not depend on the mesh size)."""
     from oracle.oracle import Oracle
     cores = host_threads()
-    c, U0 = build_case(1, 0, elems=(sample_elems,) * 3, N=N)
+    wl = make_workload(cfg, "weak", 1, 0, degree=degree, dims=(sample_elems,) * 3 if cfg != 5 else None)
+    c, U0 = wl["c"], wl["U0"]
     o = Oracle(c)
     o.set_state(U0)
     dt = o.calc_timestep()[0]
@@ -154,26 +223,29 @@ def cpu_baseline(sample_elems=12, steps=1, N=N_POLY):
     ndof = c.nDOF
     o.close()
     return dict(value=ndof * NSTAGES * steps / wall, unit="DOF*stage/s", cores=cores, kind="port",
-                sample=f"TGV N={N} GL split-PI NS+BR1, {sample_elems}^3 elements ({ndof} DOF), {steps} RK step(s) of 5 stages, "
-                       f"OpenMP over elements; restatement of the reference algorithm (oracle/dg_oracle.c), not the reference binary",
-                pid_s=wall * cores / (ndof * NSTAGES * steps), wall_s=wall), c
+                sample=f"{wl['desc']} -- {ndof} DOF, {steps} RK step(s) of 5 stages, OpenMP over elements; restatement of the reference "
+                       f"algorithm (oracle/dg_oracle.c), not the reference binary",
+                pid_s=wall * cores / (ndof * NSTAGES * steps), wall_s=wall)
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path cannot be built here (CUDA Fortran + HDF5 + MPI), so the arm times
-    the oracle port with all host threads on a bounded sample per step."""
+    """--impl reference: the reference's CPU path cannot be built here (CUDA Fortran + HDF5 + MPI), so the arm times the oracle
+    port with all host threads. Each bench step is one RK step (CalcTimeStep + 5 stages) of ONE GPU's share of the workload --
+    at the default that is the whole 32^3-element box of the N=1 product arm (same mesh, same state). The per-DOF cost of the
+    CPU path does not depend on how many such boxes the job has, so the value is the CPU's DOF-updates/s for the workload at
+    every N."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     t0 = time.perf_counter()
-    sample = 12
-    vals = []
     from oracle.oracle import Oracle
     cores = host_threads()
-    c, U0 = build_case(1, 0, elems=(sample,) * 3)
+    wl = make_workload(args.config, "weak" if args.config != 5 else "strong", 1, 0, degree=args.degree, elems=args.elems, curved=args.curved)
+    c, U0 = wl["c"], wl["U0"]
     o = Oracle(c)
     o.set_state(U0)
     t = 0.0
+    vals = []
     for it in range(args.warmup + args.steps):
         s0 = time.perf_counter()
         dt = o.calc_timestep()[0]
@@ -184,23 +256,323 @@ def run_reference(args):
     wall = float(np.sum(vals))
     ndof = c.nDOF
     value = ndof * NSTAGES * args.steps / wall
+    sample = (f"one GPU's share of the workload ({wl['desc']}): {ndof} DOF, one RK step (CalcTimeStep + 5 stages) per bench step, "
+              f"OpenMP over elements on {cores} host threads")
     line = dict(metric="DOF-updates/s", value=value, unit="DOF*stage/s", impl="reference", n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=1e3 * wall / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                warmup=args.warmup, ms_per_step=1e3 * wall / args.steps, higher_is_better=True, scaling=args.scaling, vs_baseline=None,
                 dtype="f64", data="synthetic",
-                config=dict(workload=workload_name(args.gpus), sample=f"{sample}^3 elements per step"),
+                config=dict(workload=workload_desc(args.config, args.scaling, args.gpus, args.degree, args.elems, args.curved), rk_stages=NSTAGES),
                 pid_s=wall * cores / (ndof * NSTAGES * args.steps),
-                cpu_baseline=dict(value=value, unit="DOF*stage/s", cores=cores, kind="port",
-                                  sample=f"TGV N=7 GL split-PI NS+BR1 on {sample}^3 elements ({ndof} DOF), one RK step (5 stages) per bench step"),
+                cpu_baseline=dict(value=value, unit="DOF*stage/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=value, unit="DOF*stage/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 note="reference binary not buildable offline (nvfortran/HDF5/MPI absent); this arm is the C restatement "
                      "(oracle/dg_oracle.c) on all host threads", wall_total_s=time.perf_counter() - t0)
     print(json.dumps(line), flush=True)
 
 
-def workload_name(ngpus):
-    d = box_dims(ngpus)
-    return (f"TGV Navier-Stokes Re1600 Ma0.1, N={N_POLY} Gauss-Lobatto, split-form PI + BR1, RoeEntropyFix, CarpenterRK4-5, "
-            f"{d[0]}x{d[1]}x{d[2]} elements ({ELEMS_PER_GPU}^3 per GPU){', curved NGeo=2 mesh (sine deformation 0.1)' if CURVED else ''}, adaptive dt")
+# ---------------------------------------------------------------------------------------------------------------------
+# product arm
+# ---------------------------------------------------------------------------------------------------------------------
+class Comm:
+    """torch.distributed plumbing of one bench process."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+
+    def init(self):
+        torch = self.torch
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+
+    def new_nccl_id(self):
+        """A fresh NCCL id for one DGSolver (the library owns its communicator)."""
+        from galaexi_b200 import dg
+        if self.world == 1:
+            return None
+        ids = [dg.nccl_unique_id() if self.rank == 0 else None]
+        self.dist.broadcast_object_list(ids, src=0)
+        return ids[0]
+
+    def barrier(self, s=None):
+        if s is not None:
+            s.sync()
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max(self, x):
+        if self.world == 1:
+            return x
+        tt = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(tt, op=self.dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def sum(self, x):
+        if self.world == 1:
+            return x
+        tt = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(tt)
+        return float(tt.item())
+
+
+def measure(comm: Comm, wl: dict, steps: int, warmup: int, sample_clocks: bool = True, pacing: str = "graph"):
+    """W warm-up + K timed RK steps with the state resident in HBM (adaptive dt every step; CalcForcing every step for the
+    channel), then the per-kernel stage profile. Returns the solver (kept for the e2e leg) and the numbers."""
+    from galaexi_b200 import dg
+    from galaexi_b200.host_standin import analyze as an
+    c, U0 = wl["c"], wl["U0"]
+    t_build = time.perf_counter()
+    s = dg.DGSolver(c, device=comm.local, nccl_id=comm.new_nccl_id())
+    t_build = time.perf_counter() - t_build
+    s.set_state(U0)
+    ndof_local = c.nDOF
+    ndof_global = int(round(comm.sum(float(ndof_local))))
+    forcing = bool(wl["forcing"])
+    if forcing:
+        from galaexi_b200.host_standin import workloads as wls
+        vol = comm.sum(an.volume(c))
+        bv = s.CalcForcing(Vol=vol)                       # also leaves the quadrature of the per-step CalcForcing in the library
+        s.set_channel_forcing(wls.CHANNEL_DPDX, bv)
+    dt0, err = s.CalcTimeStep()
+    if err:
+        raise SystemExit("initial state not admissible")
+    kw = dict(adaptive=True, forcing=forcing, device_paced=pacing != "host", graph=pacing == "graph")
+    s.run_steps(warmup, 0.0, dt0, **kw)
+    comm.barrier(s)
+    sampler = ClockSampler(comm.local)
+    if comm.rank == 0 and sample_clocks:
+        sampler.start()
+        time.sleep(0.3)
+    comm.barrier(s)
+    l0 = s.launch_count()
+    ms, _ = s.run_steps(steps, 0.0, dt0, **kw)   # fails when the state leaves the admissible set
+    comm.barrier(s)
+    if comm.rank == 0 and sample_clocks:
+        time.sleep(0.15)
+        sampler.stop()
+    ms = comm.max(ms)
+    launches = s.launch_count() - l0
+    sec = ms * 1e-3
+    value = ndof_global * NSTAGES * steps / sec
+    pid = sec * comm.world / (ndof_global * steps * NSTAGES)
+    prof = {}
+    for _ in range(5):
+        for k, v in s.profile_stage(0.0, dt0).items():
+            prof.setdefault(k, []).append(v)
+    prof = {k: comm.max(float(np.mean(v))) for k, v in prof.items()}
+    return s, dict(value=value, ms_per_step=ms / steps, pid_s=pid, launches=int(launches), kernel_ms_per_stage=prof, dt0=dt0,
+                   ndof_local=ndof_local, ndof_global=ndof_global, setup_s=t_build,
+                   pacing=pacing + (" (graph active)" if pacing == "graph" and s.step_graph_active() else (" (graph capture failed: stream launches)" if pacing == "graph" else "")), clocks=sampler.summary() if sample_clocks else None)
+
+
+def peaks():
+    p = {}
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(p.get("hbm_gbs", 6650.0))
+    src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in p else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    return hbm, src
+
+
+def roofline_of(wl, m, counts_live=None):
+    """Per kernel: achieved algorithmic GB/s vs the measured HBM peak, executed FP64 TFLOP/s vs the measured DFMA peak, the
+    governing (slower) roof and the fraction of it. Top level = the kernel with the longest launch."""
+    n = wl["N"] + 1
+    hbm_peak, peak_src = peaks()
+    prof, ndof = m["kernel_ms_per_stage"], m["ndof_local"]
+    counts = load_counts().get(f"cfg{wl['cfg']}_N{wl['N']}", {})
+    if counts_live:
+        counts = counts_live
+    kernels = {}
+    for k, ms in prof.items():
+        if k not in KERNEL_BYTES or not ms > 0.0:
+            continue
+        b = KERNEL_BYTES[k](n)
+        gbs = b * ndof / (ms * 1e-3) / 1e9
+        ent = dict(ms=ms, algorithmic_bytes_per_dof=b, achieved_gbs=gbs, hbm_frac=gbs / hbm_peak)
+        kc = counts.get(KERNEL_OF[k])
+        if kc:
+            tf = kc["flops_per_dof"] * ndof / (ms * 1e-3) / 1e12
+            t_hbm, t_f64 = b / (hbm_peak * 1e9), kc["flops_per_dof"] / (FP64_PEAK_TFLOPS * 1e12)
+            ent.update(flops_per_dof=kc["flops_per_dof"], achieved_tflops=tf, fp64_frac=tf / FP64_PEAK_TFLOPS,
+                       bound="hbm" if t_hbm >= t_f64 else "fp64", dram_bytes_per_dof=kc.get("dram_bytes_per_dof"))
+            ent["frac"] = ent["hbm_frac"] if ent["bound"] == "hbm" else ent["fp64_frac"]
+        else:
+            ent.update(fp64_frac=None, bound="hbm", frac=ent["hbm_frac"])
+        kernels[k] = ent
+    top = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
+    r = dict(bound="hbm", kernel=None, achieved=None, peak=hbm_peak, unit="GB/s", frac=None, traffic=None, peak_source=peak_src)
+    if top:
+        e = kernels[top]
+        traffic = e.get("dram_bytes_per_dof")
+        hb = e["bound"] == "hbm"
+        r.update(bound=e["bound"], kernel=f"{KERNEL_OF[top]}<{n}> ({top})", achieved=e["achieved_gbs"] if hb else e["achieved_tflops"],
+                 peak=hbm_peak if hb else FP64_PEAK_TFLOPS, unit="GB/s" if hb else "TFLOP/s", frac=e["frac"],
+                 traffic=None if traffic is None else traffic * ndof, algorithmic_bytes_per_dof=e["algorithmic_bytes_per_dof"],
+                 ms_per_launch=e["ms"])
+    r.update(kernel_ms_per_stage=prof, kernels=kernels, counts_source=counts.get("source"),
+             fp64_peak_tflops=dict(dfma=FP64_PEAK_TFLOPS, dmma_m8n8k4=37.1,
+                                   source="profiles/r02_fp64_rates_b200.txt (tools/microbench/fp64_rates.cu on this pool's B200)"),
+             stage=dict(algorithmic_bytes_per_dof=b_alg_stage_fused(n), achieved=b_alg_stage_fused(n) / m["pid_s"] / 1e9,
+                        frac=b_alg_stage_fused(n) / m["pid_s"] / 1e9 / hbm_peak, reference_dataflow_bytes_per_dof=b_alg_stage(n),
+                        note="whole RK stage incl. CalcTimeStep: bytes the three fused kernels must move / PID vs HBM peak"))
+    return r
+
+
+NCU_METRICS = ("gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,"
+               "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,"
+               "sm__ops_path_tensor_src_fp64.sum")
+
+
+def parse_ncu_counts(text: str, ndof: int):
+    """ncu --csv (one row per launch and metric) -> {kernel: flops_per_dof, dram_bytes_per_dof}, from the LAST launch of each
+    kernel family (a mid-step RK stage, not the first-touch one)."""
+    rows = list(csv.reader(io.StringIO(text)))
+    hdr = None
+    per = {}
+    for r in rows:
+        if "Kernel Name" in r and "Metric Name" in r:
+            hdr = r
+            continue
+        if hdr is None or len(r) != len(hdr):
+            continue
+        d = dict(zip(hdr, r))
+        nm = d["Kernel Name"]
+        key = "k_lifting" if "k_lifting" in nm else ("k_sideflux" if "k_sideflux" in nm else ("k_volsurf" if "k_volsurf" in nm else None))
+        if key is None:
+            continue
+        try:
+            val = float(d["Metric Value"].replace(",", ""))
+        except ValueError:
+            continue
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}.get(d.get("Metric Unit", ""), 1.0)
+        per.setdefault(key, {}).setdefault(int(d["ID"]), {})[d["Metric Name"]] = val * scale
+    out = {}
+    for key, launches in per.items():
+        last = launches[max(launches)]
+        flops = (2.0 * last.get("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", 0.0)
+                 + last.get("smsp__sass_thread_inst_executed_op_dmul_pred_on.sum", 0.0)
+                 + last.get("smsp__sass_thread_inst_executed_op_dadd_pred_on.sum", 0.0) + last.get("sm__ops_path_tensor_src_fp64.sum", 0.0))
+        out[key] = dict(flops_per_dof=flops / ndof,
+                        dram_bytes_per_dof=(last.get("dram__bytes_read.sum", 0.0) + last.get("dram__bytes_write.sum", 0.0)) / ndof)
+    return out
+
+
+def live_ncu_counts(args, ndof):
+    """DRAM bytes and executed FP64 flops of this run's own kernels: one RK step of the same workload under `ncu --metrics ...`
+    in a child process (counters only -- no time is taken from it)."""
+    cmd = ["ncu", "--metrics", NCU_METRICS, "--clock-control", "none", "--csv", "-k", "regex:k_lifting|k_sideflux|k_volsurf",
+           sys.executable, os.path.abspath(__file__), "--ncu-child", "--config", str(args.config), "--scaling", args.scaling]
+    for k in ("degree", "elems"):
+        if getattr(args, k) is not None:
+            cmd += [f"--{k}", str(getattr(args, k))]
+    if args.curved:
+        cmd.append("--curved")
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=args.ncu_timeout)
+        c = parse_ncu_counts(p.stdout, ndof)
+        if not c:
+            return None, f"ncu pass gave no counters (rc {p.returncode}): {(p.stderr or p.stdout)[-300:]}"
+        c["source"] = ("live: ncu --metrics dram__bytes_{read,write}.sum, smsp__sass_thread_inst_executed_op_d{fma,mul,add}_pred_on.sum, "
+                       "sm__ops_path_tensor_src_fp64.sum on one RK step of this workload in a child process of this run")
+        return c, None
+    except Exception as ex:  # ncu missing, no permission for the counters, timeout ...
+        return None, f"ncu pass failed: {ex}"
+
+
+def ncu_child(args):
+    """The process profiled by live_ncu_counts: one RK step (5 stages) of the workload."""
+    import torch
+    torch.cuda.set_device(0)
+    from galaexi_b200 import dg
+    wl = make_workload(args.config, args.scaling, 1, 0, degree=args.degree, elems=args.elems, curved=args.curved)
+    s = dg.DGSolver(wl["c"], device=0)
+    s.set_state(wl["U0"])
+    dt0, _ = s.CalcTimeStep()
+    s.TimeStepByLSERKW2(0.0, dt0)
+    s.sync()
+    s.FinalizeDG()
+
+
+def multirank_parity(comm: Comm):
+    """N ranks vs the single-rank CPU oracle, outside every timed region (the reference's MPI=1 vs MPI=2 criterion,
+    regressioncheck/checks/parabolic/cavity_3D/command_line.ini): RHS and two RK steps of (a) TGV 8^3 N=7 split form and
+    (b) a 4^3 channel with isothermal walls, N=5, gathered on rank 0 and compared by oracle/parity.py."""
+    from galaexi_b200 import dg
+    from galaexi_b200.host_standin import workloads as wl
+    out = {}
+    for label, build in (("tgv_8x8x8_N7", lambda P, r: wl.tgv((8, 8, 8), 7, nProcs=P, myRank=r)),
+                         ("channel_4x4x4_N5_walls", lambda P, r: wl.channel((4, 4, 4), 5, nProcs=P, myRank=r))):
+        c, U0 = build(comm.world, comm.rank)
+        s = dg.DGSolver(c, device=comm.local, nccl_id=comm.new_nccl_id())
+        s.set_state(U0)
+        s.DGTimeDerivative_weakForm(0.0)
+        Ut = s.get_ut()
+        dt, err = s.CalcTimeStep()
+        t = 0.0
+        for _ in range(2):
+            s.TimeStepByLSERKW2(t, dt)
+            t += dt
+        U = s.get_state()
+        s.sync()
+        s.FinalizeDG()
+        parts = [None] * comm.world
+        comm.dist.gather_object((c.mesh.offsetElem, Ut, U, dt, err), parts if comm.rank == 0 else None, dst=0)
+        if comm.rank == 0:
+            from oracle import parity
+            host_threads()
+            parts.sort(key=lambda x: x[0])
+            c1, U01 = build(1, 0)
+            r = parity.compare(c1, U01, np.concatenate([p[1] for p in parts]), parts[0][3], np.concatenate([p[2] for p in parts]),
+                               nsteps=2, label=label)
+            r["dt_equal_on_all_ranks"] = bool(all(p[3] == parts[0][3] and p[4] == 0 for p in parts))
+            r["ok"] = bool(r["ok"] and r["dt_equal_on_all_ranks"])
+            out[label] = r
+        comm.dist.barrier()
+    if comm.rank != 0:
+        return None
+    worst = lambda k: max(v[k] for v in out.values())
+    return dict(ok=bool(all(v["ok"] for v in out.values())), ranks=comm.world, ut_rel_l2=worst("ut_rel_l2"), u_rel_l2=worst("u_rel_l2"),
+                dt_rel=worst("dt_rel"), cases=out,
+                criterion="Ut rel-L2 <= 1e-12 vs the FP64 oracle (or within 2x the FP64 oracle's own round-off of the 80-bit oracle), "
+                          "U after 2 RK steps rel-L2 and Linf <= 1e-10, dt rel <= 1e-13, identical dt on all ranks")
+
+
+def e2e_leg(comm: Comm, s, wl, m, steps):
+    """End to end through the C ABI with host buffers: H2D state + CalcTimeStep + RK step + D2H state, every step."""
+    torch = comm.torch
+    U0 = wl["U0"]
+    pinned_in = torch.from_numpy(U0).pin_memory()
+    pinned_out = torch.empty_like(pinned_in).pin_memory()
+    uin, uout = pinned_in.numpy(), pinned_out.numpy()
+    steps = max(1, steps)
+    s.set_state(uin)
+    s.TimeStepByLSERKW2(0.0, m["dt0"])
+    s.get_state(uout)
+    comm.barrier(s)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        s.set_state(uin)
+        dt_e, _ = s.CalcTimeStep()
+        s.TimeStepByLSERKW2(0.0, dt_e)
+        s.get_state(uout)
+    comm.barrier(s)
+    sec = comm.max(time.perf_counter() - t0)
+    nbytes = int(U0.nbytes)
+    return dict(value=m["ndof_global"] * NSTAGES * steps / sec, unit="DOF*stage/s", h2d_bytes_per_step=nbytes, d2h_bytes_per_step=nbytes + 8,
+                steps=steps, ms_per_step=1e3 * sec / steps,
+                call="dgx_set_state(U_host) + dgx_calc_timestep + dgx_rk_step + dgx_get_state(U_host) per step, pinned host buffers")
 
 
 def main():
@@ -209,160 +581,97 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--config", type=int, default=2, choices=(2, 3, 4, 5), help="BASELINE.json configuration (default 2, the headline)")
+    ap.add_argument("--scaling", default="weak", choices=("weak", "strong"),
+                    help="weak: --elems^3 elements per GPU; strong: fixed total (config 3/4: (2 elems)^3, config 5: the 652-element mesh)")
+    ap.add_argument("--degree", type=int, default=None, help="polynomial degree N (default: the configuration's)")
+    ap.add_argument("--elems", type=int, default=None, help="elements per direction and GPU (default 32)")
+    ap.add_argument("--curved", action="store_true", help="TGV on the NGeo=2 mesh deformed by the reference's meshdeform sine (mesh.f90:224-235)")
+    ap.add_argument("--pacing", default="graph", choices=("host", "device", "graph"),
+                    help="dgx_run_steps: host = dt through the host every step (dgx_calc_timestep + dgx_rk_step); device = dt stays on the "
+                         "device, CalcTimeStep fused into stage 1; graph (default) = device + CUDA-graph replay of step pairs; bit-identical results")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--degree", type=int, default=N_POLY,
-                    help="polynomial degree N (default 7 = BASELINE config #2, the headline; 5 = per-GPU load of config #3)")
-    ap.add_argument("--curved", action="store_true", help="NGeo=2 mesh deformed by the reference's meshdeform sine (mesh.f90:224-235) instead of the Cartesian one")
-    ap.add_argument("--elems", type=int, default=ELEMS_PER_GPU, help="elements per direction and GPU (default 32; 64 = config #3 on one GPU)")
+    ap.add_argument("--no-extras", action="store_true", help="skip extras.config3_weak")
+    ap.add_argument("--no-parity", action="store_true", help="skip the N>1 parity leg")
+    ap.add_argument("--no-ncu", action="store_true", help="skip the live ncu counter pass (N=1)")
+    ap.add_argument("--ncu-timeout", type=int, default=240)
+    ap.add_argument("--ncu-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
-    globals()["N_POLY"] = args.degree
-    globals()["ELEMS_PER_GPU"] = args.elems
-    globals()["CURVED"] = bool(args.curved)
+    if args.config == 5:
+        args.scaling = "strong"
     if args.impl == "reference":
         return run_reference(args)
-
     import torch
-    import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200 (no CPU fallback for the product path)")
-    torch.cuda.set_device(local)
-    from galaexi_b200 import dg
-    nccl_id = None
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        ids = [dg.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        nccl_id = ids[0]
+    if args.ncu_child:
+        return ncu_child(args)
+    comm = Comm()
+    if comm.world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    comm.init()
+    world, rank = comm.world, comm.rank
 
-    t_build = time.perf_counter()
-    c, U0 = build_case(world, rank, N=N_POLY)
-    s = dg.DGSolver(c, device=local, nccl_id=nccl_id)
-    t_build = time.perf_counter() - t_build
-    s.set_state(U0)
-    ndof_local = c.nDOF
-    ndof_global = ndof_local
-    if world > 1:
-        tt = torch.tensor([ndof_local], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt)
-        ndof_global = int(tt.item())
+    wl = make_workload(args.config, args.scaling, world, rank, degree=args.degree, elems=args.elems, curved=args.curved)
+    s, m = measure(comm, wl, args.steps, args.warmup, pacing=args.pacing)
+    e2e = e2e_leg(comm, s, wl, m, args.e2e_steps)
+    s.FinalizeDG()
+    del s
 
-    def barrier():
-        s.sync()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+    extras = {}
+    default_run = args.config == 2 and args.degree is None and args.elems is None and not args.curved
+    if default_run and not args.no_extras:
+        # BASELINE config #3, the configuration the 8-GPU target is quoted on (64^3 TGV, N=5): 32^3 elements per GPU
+        wl3 = make_workload(3, "weak", world, rank)
+        s3, m3 = measure(comm, wl3, 5, 3, sample_clocks=False, pacing=args.pacing)
+        s3.FinalizeDG()
+        del s3
+        if rank == 0:
+            r3 = roofline_of(wl3, m3)
+            extras["config3_weak"] = dict(workload=wl3["desc"], value=m3["value"], unit="DOF*stage/s", pid_s=m3["pid_s"],
+                                          ms_per_step=m3["ms_per_step"], steps=5, warmup=3, dof_global=m3["ndof_global"],
+                                          gpu_launches=m3["launches"], stage_frac=r3["stage"]["frac"],
+                                          kernels={k: dict(ms=v["ms"], hbm_frac=v["hbm_frac"], fp64_frac=v.get("fp64_frac"), bound=v["bound"])
+                                                   for k, v in r3["kernels"].items()})
+        del wl3
 
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        tt = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item())
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = multirank_parity(comm)
 
-    # ---- device-resident run: W warm-up + K timed steps (adaptive dt every step, as in the reference's PID window)
-    dt0, err = s.CalcTimeStep()
-    ms_w, _ = s.run_steps(args.warmup, 0.0, dt0, adaptive=True)
-    barrier()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    barrier()
-    l0 = s.launch_count()
-    ms, launches = s.run_steps(args.steps, 0.0, dt0, adaptive=True)
-    barrier()
-    if rank == 0:
-        sampler.stop()
-    ms = max_over_ranks(ms)
-    launches = s.launch_count() - l0
-    sec = ms * 1e-3
-    value = ndof_global * NSTAGES * args.steps / sec
-    pid = sec * world / (ndof_global * args.steps * NSTAGES)
-
-    # ---- per-kernel timing (CUDA events on the launching stream) for the roofline of the dominant kernel
-    prof = {}
-    for _ in range(5):
-        for k, v in s.profile_stage(0.0, dt0).items():
-            prof.setdefault(k, []).append(v)
-    prof = {k: float(np.mean(v)) for k, v in prof.items()}
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-    n = N_POLY + 1
-    vs_ms = prof.get("volsurf_rk", float("nan"))
-    ach = b_alg_volsurf(n) * ndof_local / (vs_ms * 1e-3) / 1e9
-    # every stage kernel against the HBM roof (algorithmic bytes per DOF from DESIGN.md 4)
-    b_k = {"halo+lifting": b_alg_lifting(n), "sideflux": 8.0 * 147.0 / n, "volsurf_rk": b_alg_volsurf(n)}
-    per_kernel = {k: dict(ms=prof[k], algorithmic_bytes_per_dof=b_k[k], achieved_gbs=b_k[k] * ndof_local / (prof[k] * 1e-3) / 1e9,
-                          frac=b_k[k] * ndof_local / (prof[k] * 1e-3) / 1e9 / hbm_peak) for k in b_k if k in prof}
-    roofline = dict(bound="hbm", kernel=f"k_volsurf2<{n},RK>", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak,
-                    traffic=None, peak_source=peak_src, algorithmic_bytes_per_dof=b_alg_volsurf(n), ms_per_launch=vs_ms,
-                    kernel_ms_per_stage=prof, kernels=per_kernel,
-                    fp64_peak_tflops=dict(dfma=36.0, dmma_m8n8k4=37.1, source="profiles/r02_fp64_rates_b200.txt (tools/microbench/fp64_rates.cu on this pool's B200)"),
-                    stage=dict(algorithmic_bytes_per_dof=b_alg_stage(n), achieved=b_alg_stage(n) / pid / 1e9,
-                               frac=b_alg_stage(n) / pid / 1e9 / hbm_peak, note="whole RK stage incl. CalcTimeStep: B_alg,NS(N)/PID vs HBM peak"))
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if N_POLY == 7 and world == 1:   # the ncu capture is of the headline workload on one GPU
-            roofline["traffic"] = tr.get("k_volsurf_bytes_per_launch")
-            roofline["traffic_source"] = tr.get("source")
-    except Exception:
-        pass
-
-    # ---- end to end through the C ABI with host buffers: H2D state + RK step + D2H state, every step
-    pinned_in = torch.from_numpy(U0).pin_memory()
-    pinned_out = torch.empty_like(pinned_in).pin_memory()
-    uin = pinned_in.numpy()
-    uout = pinned_out.numpy()
-    e2e_steps = max(1, args.e2e_steps)
-    s.set_state(uin)
-    s.TimeStepByLSERKW2(0.0, dt0)
-    s.get_state(uout)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        s.set_state(uin)
-        dt_e, _ = s.CalcTimeStep()
-        s.TimeStepByLSERKW2(0.0, dt_e)
-        s.get_state(uout)
-    barrier()
-    e2e_sec = max_over_ranks(time.perf_counter() - t0)
-    e2e_val = ndof_global * NSTAGES * e2e_steps / e2e_sec
-    nbytes = int(U0.nbytes)
-
-    line = None
-    if rank == 0:
+        counts_live, ncu_note = None, None
+        if world == 1 and not args.no_ncu:
+            counts_live, ncu_note = live_ncu_counts(args, m["ndof_local"])
+        roof = roofline_of(wl, m, counts_live)
+        if ncu_note:
+            roof["ncu_note"] = ncu_note
         cpu = None
         if not args.no_cpu_baseline and world == 1:   # reported at N=1 only
-            cpu, _ = cpu_baseline()
-        line = dict(metric="DOF-updates/s", value=value, unit="DOF*stage/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
-                    data="synthetic", pid_s=pid, pid_floor_s=b_alg_stage(n) / (hbm_peak * 1e9),
-                    config=dict(workload=workload_name(world), dof_global=ndof_global, dof_per_gpu=ndof_local, rk_stages=NSTAGES,
-                                l2_policy=f"inputs larger than L2 (state {U0.nbytes / 1e6:.0f} MB per GPU >> 126 MB L2), no explicit flush",
+            cpu = cpu_baseline(args.config, args.degree)
+        n = wl["N"] + 1
+        hbm_peak, _ = peaks()
+        big = wl["U0"].nbytes > 2 * 126e6
+        line = dict(metric="DOF-updates/s", value=m["value"], unit="DOF*stage/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=m["ms_per_step"], higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f64",
+                    data="synthetic", pid_s=m["pid_s"], pid_floor_s=b_alg_stage_fused(n) / (hbm_peak * 1e9),
+                    config=dict(workload=wl["desc"], rk_stages=NSTAGES, dof_global=m["ndof_global"], dof_per_gpu=m["ndof_local"],
+                                l2_policy=(f"inputs larger than L2 (state {wl['U0'].nbytes / 1e6:.0f} MB per GPU vs 126 MB L2), no explicit flush" if big
+                                           else f"state {wl['U0'].nbytes / 1e6:.0f} MB per GPU fits L2: launch-bound configuration, no explicit flush"),
                                 timing="CUDA events on the launching stream around K steps, max over ranks",
-                                parallelism=f"dd{world} (SFC element decomposition, NCCL face halos)"),
-                    roofline=roofline, cpu_baseline=cpu, clocks=sampler.summary(),
-                    e2e=dict(value=e2e_val, unit="DOF*stage/s", h2d_bytes_per_step=nbytes, d2h_bytes_per_step=nbytes + 8,
-                             steps=e2e_steps, ms_per_step=1e3 * e2e_sec / e2e_steps,
-                             call="dgx_set_state(U_host) + dgx_calc_timestep + dgx_rk_step + dgx_get_state(U_host) per step, pinned host buffers"),
-                    gpu_launches=int(launches), setup_s=t_build)
+                                parallelism=f"dd{world} (SFC element decomposition, NCCL face halos)",
+                                step_pacing=m["pacing"],
+                                state_check="density > 0, pressure > 0 and a finite time step are checked on the device every step; the run fails otherwise"),
+                    roofline=roof, cpu_baseline=cpu, clocks=m["clocks"], e2e=e2e, gpu_launches=m["launches"], setup_s=m["setup_s"])
+        if extras:
+            line["extras"] = extras
+        if parity is not None:
+            line["parity"] = parity
         print(json.dumps(line), flush=True)
-    s.FinalizeDG()
     if world > 1:
-        dist.destroy_process_group()
+        comm.dist.barrier()
+        comm.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

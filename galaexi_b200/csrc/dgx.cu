@@ -111,7 +111,19 @@ struct dgx_handle {
     long long launches = 0;
     cudaStream_t s = nullptr, cs = nullptr, s2 = nullptr;  // compute, communication, halo-dependent compute (multi rank)
     cudaEvent_t evFaces = nullptr, evUhalo = nullptr, evGrad = nullptr, evGhalo = nullptr, evT0 = nullptr, evT1 = nullptr;
-    cudaEvent_t evSide = nullptr, evBnd = nullptr;
+    cudaEvent_t evSide = nullptr, evBnd = nullptr, evDtPre = nullptr, evDt = nullptr, evNext = nullptr;
+    // U-face halo of the NEXT stage: posted right behind the halo-dependent volume kernel of an RK stage so that it travels
+    // while the inner elements are still being updated (dg.f90:335-350 starts it at the top of the next RHS instead)
+    bool uHaloPosted = false, uHaloJoined = false;
+    // device-paced stepping (dgx_run_steps flag 4): dt / bulk velocity stay on the device, one RK step pair is replayed as a CUDA graph
+    double* dtHist = nullptr;
+    int dtHistCap = 0, dtHistCount = 0;
+    double bvVol = 0.0;  // Vol of the last dgx_calc_bulk_velocity (CalcForcing inside dgx_run_steps)
+    cudaGraphExec_t graph = nullptr;
+    int graphCur = -1, graphKey = -1;
+    long long graphLaunches = 0;
+    int graphFailed = 0;
+    bool warm = false, capturing = false;  // warm: an RK stage has run outside any capture (first-use initialisation done)
     // device memory
     std::vector<void*> allocs;
     double *U = nullptr, *Ut = nullptr, *Ut_tmp = nullptr, *gradU = nullptr, *metrics = nullptr, *sJ = nullptr, *geo = nullptr;
@@ -272,17 +284,39 @@ struct StageTimes {
     cudaEvent_t ev[8];
     int nev = 0;
 };
+// per-stage options of rhs(): storeGrad: k_lifting also stores the volume gradients; devDt: the stage kernels read dt from
+// dtOut[3] (b_dt carries RKb); fuseDt: this stage (the first of a step) evaluates CalcTimeStep on the way and finishes it in
+// dtOut[3]; postHalo: the next stage's U-face halo may be posted behind this stage's halo-dependent volume kernel
+struct StageOpt {
+    int storeGrad = 0;
+    bool devDt = false, fuseDt = false, postHalo = true;
+};
 
-int rhs(dgx_handle* h, int mode, double t, double mRKA, double b_dt, StageTimes* st = nullptr, int storeGrad = 0) {
+// CalcTimeStep tail in device-paced stepping, on stream st: flag -> acc[2], min over the ranks, dt -> acc[3]
+int dt_finish_on(dgx_handle* h, cudaStream_t st) {
+    if (h->comm) {
+        k_dt_pre<<<1, 1, 0, st>>>(h->dtOut, h->errFlag);
+        if (check_launch(h, "k_dt_pre")) return 1;
+        NK(g_nccl.AllReduce(h->dtOut, h->dtOut, 3, ncclFloat64, ncclMin, h->comm, st));  // calctimestep.f90:181
+    }
+    k_dt_finish<<<1, 1, 0, st>>>(h->dtOut, h->errFlag, h->dtHist, h->dtHistCap);
+    return check_launch(h, "k_dt_finish");
+}
+
+int rhs(dgx_handle* h, int mode, double t, double mRKA, double b_dt, StageTimes* st = nullptr, const StageOpt& o = StageOpt()) {
     const dgx_config& c = h->cfg;
     const KernelTable* kt = h->kt;
     KParams P = h->P;
-    P.storeGrad = (mode == 0 || storeGrad) ? 1 : 0;
+    P.storeGrad = (mode == 0 || o.storeGrad) ? 1 : 0;
     h->gradValid = c.parabolic && P.storeGrad;
     P.Um = h->Uf[h->cur][0];
     P.Us = h->Uf[h->cur][1];
     P.UmNext = h->Uf[h->cur ^ 1][0];
     P.UsNext = h->Uf[h->cur ^ 1][1];
+    P.dtDev = o.devDt ? h->dtOut : nullptr;
+    P.dtAcc = h->dtOut; P.dtCFL = c.CFLScale; P.dtDFL = c.DFLScale;
+    P.dtFuse = (o.fuseDt && c.parabolic) ? 1 : 0;
+    if (!o.devDt) P.bulkDev = nullptr;
     const bool multi = c.nRanks > 1 && !h->NbProc.empty();
     // CalcSource (dg.f90:418): the volume kernels store Ut (MODE 0), k_source_rk adds the source and does the stage update
     if (mode == 1 && h->rk3Stage > 0) {  // timestep.f90:168-186
@@ -294,17 +328,29 @@ int rhs(dgx_handle* h, int mode, double t, double mRKA, double b_dt, StageTimes*
     const int vmode = src ? 0 : mode;
     auto mark = [&](void) { if (st) cudaEventRecord(st->ev[st->nev++], h->s); };
     mark();
+    if (o.fuseDt && !c.parabolic) {  // Euler: no lifting kernel to ride on
+        kt->timestep(P, c.CFLScale, c.DFLScale, h->dtOut, h->s);
+        if (c.nElems && check_launch(h, "k_timestep")) return 1;
+        if (dt_finish_on(h, h->s)) return 1;
+    }
     if (P.FilterMat) {
         // 1. dg.f90:331: filter U in place (every RHS evaluation, like the reference) and re-extract the face states
         kt->filter(P, c.nElems, h->s);
         if (c.nElems > 0 && check_launch(h, "k_filter")) return 1;
         if (h->hasMortar() && mortar_u(h, P.Um, P.Us, 5)) return 1;
     }
+    bool waitU = false;  // the halo-dependent launches of this stage have to wait for evUhalo
     if (multi) {
         CK(cudaEventRecord(h->evFaces, h->s));
-        CK(cudaStreamWaitEvent(h->cs, h->evFaces, 0));
-        if (exchange(h, P.Um, P.Us, 5)) return 1;
-        CK(cudaEventRecord(h->evUhalo, h->cs));
+        if (!h->uHaloPosted) {
+            CK(cudaStreamWaitEvent(h->cs, h->evFaces, 0));
+            if (exchange(h, P.Um, P.Us, 5)) return 1;
+            CK(cudaEventRecord(h->evUhalo, h->cs));
+            waitU = true;
+        } else {
+            waitU = !h->uHaloJoined;  // posted behind the previous stage's volume kernel; joined: already ordered before stream s
+        }
+        h->uHaloPosted = h->uHaloJoined = false;
     }
     KParams Pi = P, Pb = P;
     if (multi) {
@@ -315,21 +361,25 @@ int rhs(dgx_handle* h, int mode, double t, double mRKA, double b_dt, StageTimes*
     // multi rank, conforming mesh: the halo-dependent launches (elements / sides touching an MPI side) run on a second,
     // high-priority stream concurrently with the inner-element kernels, so neither waits for the other's tail
     const bool split2 = multi && !mortar && !getenv("DGX_NO_SPLIT_STREAM");
+    static const bool earlyHalo = !getenv("DGX_NO_EARLY_HALO");
     if (split2) {
+        CK(cudaStreamWaitEvent(h->s2, h->evFaces, 0));
+        if (waitU) CK(cudaStreamWaitEvent(h->s2, h->evUhalo, 0));
         if (c.parabolic) {
             kt->lifting(Pi, h->nInner, h->s);
             if (h->nInner > 0 && check_launch(h, "k_lifting")) return 1;
-            CK(cudaStreamWaitEvent(h->s2, h->evFaces, 0));
-            CK(cudaStreamWaitEvent(h->s2, h->evUhalo, 0));
             if (h->nBnd) { kt->lifting(Pb, h->nBnd, h->s2); if (check_launch(h, "k_lifting(bnd)")) return 1; }
             CK(cudaEventRecord(h->evGrad, h->s2));
             CK(cudaStreamWaitEvent(h->cs, h->evGrad, 0));
             if (exchange(h, P.gm, P.gs, 12)) return 1;
             CK(cudaEventRecord(h->evGhalo, h->cs));
             CK(cudaStreamWaitEvent(h->s, h->evGrad, 0));  // inner sides may border halo-dependent elements
-        } else {
-            CK(cudaStreamWaitEvent(h->s2, h->evFaces, 0));
-            CK(cudaStreamWaitEvent(h->s2, h->evUhalo, 0));
+            if (P.dtFuse) {  // both lifting launches are complete on s: finish CalcTimeStep on the communication stream
+                CK(cudaEventRecord(h->evDtPre, h->s));
+                CK(cudaStreamWaitEvent(h->cs, h->evDtPre, 0));
+                if (dt_finish_on(h, h->cs)) return 1;
+                CK(cudaEventRecord(h->evDt, h->cs));
+            }
         }
         mark();
         kt->sideflux(P, 0, c.lastInnerSide, h->s);
@@ -340,13 +390,30 @@ int rhs(dgx_handle* h, int mode, double t, double mRKA, double b_dt, StageTimes*
         if (c.parabolic) CK(cudaStreamWaitEvent(h->s2, h->evGhalo, 0));
         const int nMPI = c.lastMPISide_YOUR - c.firstMPISide_MINE + 1;
         if (nMPI > 0) { kt->sideflux(P, c.firstMPISide_MINE - 1, nMPI, h->s2); if (check_launch(h, "k_sideflux(mpi)")) return 1; }
+        if (P.dtFuse) { CK(cudaStreamWaitEvent(h->s2, h->evDt, 0)); CK(cudaStreamWaitEvent(h->s, h->evDt, 0)); }
         if (h->nBnd) { kt->volsurf(Pb, vmode, mRKA, b_dt, h->nBnd, h->s2); if (check_launch(h, "k_volsurf(bnd)")) return 1; }
         CK(cudaEventRecord(h->evBnd, h->s2));
+        const bool post = mode == 1 && earlyHalo && o.postHalo && !P.FilterMat;
+        if (post && !src) {
+            // every MPI side belongs to a halo-dependent element: their next-stage face states are complete here
+            CK(cudaStreamWaitEvent(h->cs, h->evBnd, 0));
+            if (exchange(h, P.UmNext, P.UsNext, 5)) return 1;
+            CK(cudaEventRecord(h->evUhalo, h->cs));
+            h->uHaloPosted = true;
+        }
         if (h->nInner) { kt->volsurf(Pi, vmode, mRKA, b_dt, h->nInner, h->s); if (check_launch(h, "k_volsurf(inner)")) return 1; }
         CK(cudaStreamWaitEvent(h->s, h->evBnd, 0));
         if (src) { kt->source_rk(P, mode, t, mRKA, b_dt, c.nElems, h->s); if (c.nElems > 0 && check_launch(h, "k_source_rk")) return 1; }
+        if (post && src) {
+            CK(cudaEventRecord(h->evNext, h->s));
+            CK(cudaStreamWaitEvent(h->cs, h->evNext, 0));
+            if (exchange(h, P.UmNext, P.UsNext, 5)) return 1;
+            CK(cudaEventRecord(h->evUhalo, h->cs));
+            h->uHaloPosted = true;
+        }
         mark();
         if (mode == 1) h->cur ^= 1;
+        if (!h->capturing) h->warm = true;
         return 0;
     }
     if (c.parabolic) {
@@ -354,7 +421,7 @@ int rhs(dgx_handle* h, int mode, double t, double mRKA, double b_dt, StageTimes*
         kt->lifting(multi ? Pi : P, multi ? h->nInner : c.nElems, h->s);
         if ((multi ? h->nInner : c.nElems) > 0 && check_launch(h, "k_lifting")) return 1;
         if (multi) {
-            CK(cudaStreamWaitEvent(h->s, h->evUhalo, 0));
+            if (waitU) CK(cudaStreamWaitEvent(h->s, h->evUhalo, 0));
             if (mortar && mortar_liftflux(h, P)) return 1;
             if (h->nBnd) { kt->lifting(Pb, h->nBnd, h->s); if (check_launch(h, "k_lifting(bnd)")) return 1; }
             if (mortar && mortar_u(h, P.gm, P.gs, 12)) return 1;
@@ -363,8 +430,9 @@ int rhs(dgx_handle* h, int mode, double t, double mRKA, double b_dt, StageTimes*
             if (exchange(h, P.gm, P.gs, 12)) return 1;
             CK(cudaEventRecord(h->evGhalo, h->cs));
         } else if (mortar && mortar_u(h, P.gm, P.gs, 12)) return 1;
+        if (P.dtFuse && dt_finish_on(h, h->s)) return 1;
     } else if (multi) {
-        CK(cudaStreamWaitEvent(h->s, h->evUhalo, 0));
+        if (waitU) CK(cudaStreamWaitEvent(h->s, h->evUhalo, 0));
     }
     mark();
     // BC + inner sides
@@ -387,6 +455,7 @@ int rhs(dgx_handle* h, int mode, double t, double mRKA, double b_dt, StageTimes*
     if (mode == 1 && mortar && mortar_u(h, P.UmNext, P.UsNext, 5)) return 1;
     mark();
     if (mode == 1) h->cur ^= 1;
+    if (!h->capturing) h->warm = true;
     return 0;
 }
 
@@ -399,11 +468,12 @@ int prolong_current(dgx_handle* h) {
     return h->hasMortar() ? mortar_u(h, P.Um, P.Us, 5) : 0;
 }
 
-int check_err_flag(dgx_handle* h, const char* where) {
+int check_err_flag(dgx_handle* h, const char* where, bool checkDt = false) {
     int flag = 0;
     CK(cudaMemcpyAsync(&flag, h->errFlag, sizeof(int), cudaMemcpyDeviceToHost, h->s));
     CK(cudaStreamSynchronize(h->s));
     if (flag & 1) return fail(h, "%s: unsupported boundary condition type (supported: 2,3,4,9,91,23,24,25,27)", where);
+    if ((flag & 2) && checkDt) return fail(h, "%s: timestep is NaN / state not admissible (density, convective / viscous timestep)", where);
     return 0;
 }
 
@@ -447,7 +517,8 @@ void dgx_destroy(dgx_handle* h) {
     if (h->comm) g_nccl.CommDestroy(h->comm);
     for (void* p : h->allocs) cudaFree(p);
     if (h->hPinned) cudaFreeHost(h->hPinned);
-    cudaEvent_t evs[] = {h->evFaces, h->evUhalo, h->evGrad, h->evGhalo, h->evT0, h->evT1, h->evSide, h->evBnd};
+    if (h->graph) cudaGraphExecDestroy(h->graph);
+    cudaEvent_t evs[] = {h->evFaces, h->evUhalo, h->evGrad, h->evGhalo, h->evT0, h->evT1, h->evSide, h->evBnd, h->evDtPre, h->evDt, h->evNext};
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     if (h->s) cudaStreamDestroy(h->s);
     if (h->cs) cudaStreamDestroy(h->cs);
@@ -494,7 +565,7 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
     CK(cudaStreamCreateWithPriority(&h->s, cudaStreamNonBlocking, lo));
     CK(cudaStreamCreateWithPriority(&h->cs, cudaStreamNonBlocking, hi));
     CK(cudaStreamCreateWithPriority(&h->s2, cudaStreamNonBlocking, hi));
-    cudaEvent_t* evs[] = {&h->evFaces, &h->evUhalo, &h->evGrad, &h->evGhalo, &h->evSide, &h->evBnd};
+    cudaEvent_t* evs[] = {&h->evFaces, &h->evUhalo, &h->evGrad, &h->evGhalo, &h->evSide, &h->evBnd, &h->evDtPre, &h->evDt, &h->evNext};
     for (cudaEvent_t* e : evs) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     CK(cudaEventCreate(&h->evT0));
     CK(cudaEventCreate(&h->evT1));
@@ -510,7 +581,7 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
     if (dalloc(h, &h->gm, c.parabolic ? 12 * nFace : 1) || dalloc(h, &h->gs, c.parabolic ? 12 * nFace : 1)) return 1;
     if (dalloc(h, &h->Flux, 5 * nFace)) return 1;
     if (dalloc(h, &h->stage, 5 * nDOF > 12 * nFace ? 5 * nDOF : 12 * nFace)) return 1;
-    if (dalloc(h, &h->dtOut, 4) || dalloc(h, &h->errFlag, 1)) return 1;
+    if (dalloc(h, &h->dtOut, 8) || dalloc(h, &h->errFlag, 1)) return 1;
     CK(cudaMallocHost((void**)&h->hPinned, 8 * sizeof(double)));
     // ---- geometry: upload in reference layout, repack on the device
     {
@@ -681,6 +752,8 @@ int dgx_set_state(dgx_handle* h, const double* U) {
         if (check_launch(h, "k_aos_to_soa")) return 1;
         CK(cudaMemsetAsync(h->Ut_tmp, 0, tot * sizeof(double), h->s));
         h->gradValid = false;
+        if (h->uHaloPosted) CK(cudaStreamWaitEvent(h->s, h->evUhalo, 0));  // a halo of the replaced state may still be travelling
+        h->uHaloPosted = h->uHaloJoined = false;
         if (prolong_current(h)) return 1;
     }
     CK(cudaStreamSynchronize(h->s));
@@ -708,6 +781,28 @@ int dgx_get_gradients(dgx_handle* h, double* gx, double* gy, double* gz) {
     return get_vol(h, h->gradU, gz, 12, 8, 4);
 }
 
+// Face arrays of the last RHS evaluation in the reference's layout (nVar,0:N,0:N,nSides), for parity checks of the
+// orientation / sign conventions on the kernels themselves (unitTests/ProlongToFace.f90:70-114, SurfInt.f90:79-132):
+// which = 0 U_master, 1 U_slave (5 variables), 2 Flux_master (5), 3..5 gradUx/y/z_master, 6..8 gradUx/y/z_slave (the 4 lifted
+// variables u, v, w, T). A debugging path: device -> host copy, transposed on the host.
+int dgx_get_face_array(dgx_handle* h, int which, double* out) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (which < 0 || which > 8 || !out) return fail(h, "dgx_get_face_array: bad arguments");
+    if (which >= 3 && !h->cfg.parabolic) return fail(h, "dgx_get_face_array: gradient traces exist only for PARABOLIC runs");
+    const int n2 = h->n2, nvarDev = which < 3 ? 5 : 12, nvar = which < 3 ? 5 : 4, v0 = which < 3 ? 0 : 4 * ((which - 3) % 3);
+    const double* src = which == 0 ? h->Uf[h->cur][0] : which == 1 ? h->Uf[h->cur][1] : which == 2 ? h->Flux : (which < 6 ? h->gm : h->gs);
+    const size_t nS = (size_t)h->cfg.nSides;
+    std::vector<double> tmp(nS * nvarDev * n2);
+    CK(cudaStreamSynchronize(h->s));
+    CK(cudaStreamSynchronize(h->cs));
+    CK(cudaStreamSynchronize(h->s2));
+    if (!tmp.empty()) CK(cudaMemcpy(tmp.data(), src, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t sd = 0; sd < nS; sd++)
+        for (int pq = 0; pq < n2; pq++)
+            for (int v = 0; v < nvar; v++) out[(sd * n2 + pq) * nvar + v] = tmp[(sd * nvarDev + v0 + v) * n2 + pq];
+    return 0;
+}
+
 int dgx_time_derivative(dgx_handle* h, double t) {
     CK(cudaSetDevice(h->cfg.device));
     if (rhs(h, 0, t, 0.0, 0.0)) return 1;
@@ -717,7 +812,8 @@ int dgx_time_derivative(dgx_handle* h, double t) {
 int dgx_rk_stage(dgx_handle* h, int iStage, double t, double dt) {
     CK(cudaSetDevice(h->cfg.device));
     if (iStage < 1 || iStage > h->cfg.nRKStages) return fail(h, "iStage out of range");
-    const int store = (iStage == h->cfg.nRKStages && h->keepGrad) ? 1 : 0;
+    StageOpt store;
+    store.storeGrad = (iStage == h->cfg.nRKStages && h->keepGrad) ? 1 : 0;
     if (!h->RKg1.empty()) {  // TimeStepByLSERKK3 (timestep.f90:129-200)
         h->rk3Stage = iStage;
         const int rc = rhs(h, 1, t, 0.0, h->RKb[iStage - 1] * dt, nullptr, store);
@@ -787,6 +883,20 @@ int dgx_set_channel_forcing(dgx_handle* h, int on, double dpdx, double BulkVel) 
     return 0;
 }
 
+namespace {
+// CalcForcing on the device (testcase.f90:241-271): sum over this rank's nodes, sum over the ranks, / Vol -> tot[1]
+int bulk_velocity_dev(dgx_handle* h) {
+    h->kt->bulkvel(h->P, h->bvW, h->bvPart, h->s);
+    if (h->cfg.nElems && check_launch(h, "k_bulkvel")) return 1;
+    double* tot = h->bvPart + h->cfg.nElems;
+    k_sum_partials<<<1, 256, 0, h->s>>>(h->bvPart, h->cfg.nElems, tot);
+    if (check_launch(h, "k_sum_partials")) return 1;
+    if (h->comm) NK(g_nccl.AllReduce(tot, tot, 1, ncclFloat64, 0 /* ncclSum */, h->comm, h->s));  // testcase.f90:266-268
+    k_bulk_finish<<<1, 1, 0, h->s>>>(tot, h->bvVol);
+    return check_launch(h, "k_bulk_finish");
+}
+}  // namespace
+
 int dgx_calc_bulk_velocity(dgx_handle* h, const double* wGP, double Vol, double* BulkVel) {
     CK(cudaSetDevice(h->cfg.device));
     if (!wGP || !BulkVel) return fail(h, "dgx_calc_bulk_velocity: bad arguments");
@@ -794,14 +904,10 @@ int dgx_calc_bulk_velocity(dgx_handle* h, const double* wGP, double Vol, double*
         if (dalloc(h, &h->bvPart, (size_t)h->cfg.nElems + 2) || dalloc(h, &h->bvW, (size_t)h->n)) return 1;
     }
     CK(cudaMemcpyAsync(h->bvW, wGP, h->n * sizeof(double), cudaMemcpyHostToDevice, h->s));
-    h->kt->bulkvel(h->P, h->bvW, h->bvPart, h->s);
-    if (h->cfg.nElems && check_launch(h, "k_bulkvel")) return 1;
-    double* tot = h->bvPart + h->cfg.nElems;
-    k_sum_partials<<<1, 256, 0, h->s>>>(h->bvPart, h->cfg.nElems, tot);
-    if (check_launch(h, "k_sum_partials")) return 1;
-    if (h->comm) NK(g_nccl.AllReduce(tot, tot, 1, ncclFloat64, 0 /* ncclSum */, h->comm, h->s));  // testcase.f90:266-268
+    h->bvVol = Vol;  // dgx_run_steps with CalcForcing every step reuses this quadrature
+    if (bulk_velocity_dev(h)) return 1;
     double b = 0.0;
-    CK(cudaMemcpyAsync(&b, tot, sizeof b, cudaMemcpyDeviceToHost, h->s));
+    CK(cudaMemcpyAsync(&b, h->bvPart + h->cfg.nElems, sizeof b, cudaMemcpyDeviceToHost, h->s));
     CK(cudaStreamSynchronize(h->s));
     *BulkVel = b / Vol;
     return 0;
@@ -900,32 +1006,164 @@ int dgx_analyze_tgv(dgx_handle* h, int NAnalyze, const double* Vdm, const double
     return 0;
 }
 
-int dgx_run_steps(dgx_handle* h, int nSteps, double t, double dt, int adaptive_dt, float* ms, long long* launches) {
-    CK(cudaSetDevice(h->cfg.device));
+namespace {
+// one RK step of device-paced stepping: CalcForcing (optional), then the stages; stage 1 evaluates CalcTimeStep on the way
+int dev_step(dgx_handle* h, bool forcing, bool storeLast, bool postLast) {
+    if (forcing && bulk_velocity_dev(h)) return 1;
+    const int nst = h->cfg.nRKStages;
+    for (int st = 1; st <= nst; st++) {
+        StageOpt o;
+        o.devDt = true;
+        o.fuseDt = st == 1;
+        o.storeGrad = (st == nst && storeLast) ? 1 : 0;
+        o.postHalo = st < nst || postLast;
+        const double mRKA = (st == 1) ? 0.0 : -1.0 * h->RKA[st - 1];
+        if (rhs(h, 1, 0.0, mRKA, h->RKb[st - 1], nullptr, o)) return 1;
+    }
+    return 0;
+}
+
+// A pair of RK steps captured once as a CUDA graph and replayed (the face double buffer is back in place after 2 nRKStages
+// flips): one launch per 2 x (3 nRKStages + 1) kernels. Multi rank: the capture starts from "U-face halo complete and ordered
+// before stream s" and ends in the same state (the halo the last stage posted is joined into s), which dgx_run_steps
+// establishes before the first replay. Nothing is executed here.
+int build_step_graph(dgx_handle* h, bool forcing, int key) {
+    if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
     const long long l0 = h->launches;
+    const int cur0 = h->cur;
+    const bool posted0 = h->uHaloPosted, joined0 = h->uHaloJoined;
+    const bool multi = h->cfg.nRanks > 1 && !h->NbProc.empty();
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(h->s, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return 1; }
+    h->capturing = true;
+    if (multi) h->uHaloPosted = h->uHaloJoined = true;
+    int rc = dev_step(h, forcing, false, true);
+    if (!rc) rc = dev_step(h, forcing, false, true);
+    if (!rc && multi && h->uHaloPosted && cudaStreamWaitEvent(h->s, h->evUhalo, 0) != cudaSuccess) rc = 1;  // join the communication stream
+    cudaError_t e = cudaStreamEndCapture(h->s, &g);
+    h->capturing = false;
+    h->cur = cur0;
+    h->uHaloPosted = posted0; h->uHaloJoined = joined0;
+    h->graphLaunches = h->launches - l0;
+    h->launches = l0;  // nothing ran
+    if (rc || e != cudaSuccess || !g) {
+        cudaGetLastError();
+        if (g) cudaGraphDestroy(g);
+        return 1;
+    }
+    e = cudaGraphInstantiate(&h->graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { cudaGetLastError(); h->graph = nullptr; return 1; }
+    h->graphCur = cur0;
+    h->graphKey = key;
+    return 0;
+}
+}  // namespace
+
+int dgx_run_steps(dgx_handle* h, int nSteps, double t, double dt, int flags, float* ms, long long* launches) {
+    CK(cudaSetDevice(h->cfg.device));
+    const bool adaptive = flags & 1, forcing = flags & 2, dev = flags & 4;
+    static const bool noGraph = getenv("DGX_NO_GRAPH") != nullptr;
+    const bool graph = (flags & 8) && !noGraph && !h->graphFailed;
+    if (forcing && (!h->bvPart || !(h->bvVol > 0.0))) return fail(h, "dgx_run_steps: CalcForcing every step needs a previous dgx_calc_bulk_velocity (weights, volume)");
+    if (dev && (!adaptive || h->P.iniExactFunc == 4 || !h->RKg1.empty()))
+        return fail(h, "dgx_run_steps: device-paced stepping needs adaptive dt, a time-independent source and a 2-register Runge-Kutta scheme");
+    const long long l0 = h->launches;
+    const int keep = h->keepGrad;
+    const bool multi = h->cfg.nRanks > 1 && !h->NbProc.empty();
+    if (dev && h->dtHistCap < nSteps) {
+        if (dalloc(h, &h->dtHist, (size_t)nSteps + 64)) return 1;
+        h->dtHistCap = nSteps + 64;
+        if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }  // the history buffer is a kernel argument
+    }
     CK(cudaStreamSynchronize(h->s));
     CK(cudaEventRecord(h->evT0, h->s));
-    const int keep = h->keepGrad;
-    for (int it = 0; it < nSteps; it++) {
-        h->keepGrad = (it == nSteps - 1) ? keep : 0;  // nothing can read the gradients between the steps of this call
-        if (adaptive_dt) {
-            int et = 0;
-            if (dgx_calc_timestep(h, &dt, &et)) { h->keepGrad = keep; return 1; }
-            if (et) { h->keepGrad = keep; return fail(h, "timestep is NaN / state not admissible at t=%g", t); }
+    if (dev) {
+        // arm the accumulators: minima, flag, dt, step counter
+        h->hPinned[0] = DT_HUGE; h->hPinned[1] = DT_HUGE; h->hPinned[2] = 0.0; h->hPinned[3] = 0.0; h->hPinned[4] = 0.0;
+        CK(cudaMemcpyAsync(h->dtOut, h->hPinned, 5 * sizeof(double), cudaMemcpyHostToDevice, h->s));
+        k_clear_flag_bits<<<1, 1, 0, h->s>>>(h->errFlag, 2);
+        if (check_launch(h, "k_clear_flag_bits")) return 1;
+        if (forcing) h->P.bulkDev = h->bvPart + h->cfg.nElems + 1;
+        const int key = (forcing ? 1 : 0) | (h->P.tcSource ? 2 : 0) | (h->P.spMat ? 4 : 0) | (h->P.FilterMat ? 8 : 0);
+        int it = 0;
+        if (graph) {
+            if (!h->warm && nSteps > 0) {  // first-use initialisation (occupancy queries, communicator channels) outside any capture
+                if (dev_step(h, forcing, nSteps == 1 && keep, true)) return 1;
+                it = 1;
+            }
+            const int nPairs = (nSteps - it - 1) / 2;
+            if (nPairs > 0) {
+                if ((!h->graph || h->graphCur != h->cur || h->graphKey != key) && build_step_graph(h, forcing, key)) h->graphFailed = 1;
+                if (h->graph && h->graphCur == h->cur && h->graphKey == key) {
+                    if (multi) {
+                        // the graph's first stage expects its U-face halo complete and ordered before stream s
+                        if (!h->uHaloPosted) {
+                            CK(cudaEventRecord(h->evFaces, h->s));
+                            CK(cudaStreamWaitEvent(h->cs, h->evFaces, 0));
+                            if (exchange(h, h->Uf[h->cur][0], h->Uf[h->cur][1], 5)) return 1;
+                            CK(cudaEventRecord(h->evUhalo, h->cs));
+                        }
+                        if (!h->uHaloJoined) CK(cudaStreamWaitEvent(h->s, h->evUhalo, 0));
+                    }
+                    for (int p = 0; p < nPairs; p++) {
+                        CK(cudaGraphLaunch(h->graph, h->s));
+                        h->launches += h->graphLaunches;
+                    }
+                    if (multi) h->uHaloPosted = h->uHaloJoined = true;  // the state every replay ends in
+                    it += 2 * nPairs;
+                }
+            }
         }
-        if (dgx_rk_step(h, t, dt)) { h->keepGrad = keep; return 1; }
-        t += dt;
+        for (; it < nSteps; it++)
+            if (dev_step(h, forcing, it == nSteps - 1 && keep, true)) return 1;
+        h->dtHistCount = nSteps;
+        // capture for the next call, outside its timed region
+        if (graph && h->warm && (!h->graph || h->graphCur != h->cur || h->graphKey != key) && build_step_graph(h, forcing, key)) h->graphFailed = 1;
+        h->P.bulkDev = nullptr;
+    } else {
+        for (int it = 0; it < nSteps; it++) {
+            h->keepGrad = (it == nSteps - 1) ? keep : 0;  // nothing can read the gradients between the steps of this call
+            if (forcing) {
+                double b = 0.0;
+                if (bulk_velocity_dev(h)) { h->keepGrad = keep; return 1; }
+                CK(cudaMemcpyAsync(&b, h->bvPart + h->cfg.nElems + 1, sizeof b, cudaMemcpyDeviceToHost, h->s));
+                CK(cudaStreamSynchronize(h->s));
+                h->P.tcBulkVel = b;
+            }
+            if (adaptive) {
+                int et = 0;
+                if (dgx_calc_timestep(h, &dt, &et)) { h->keepGrad = keep; return 1; }
+                if (et) { h->keepGrad = keep; return fail(h, "timestep is NaN / state not admissible at t=%g", t); }
+            }
+            if (dgx_rk_step(h, t, dt)) { h->keepGrad = keep; return 1; }
+            t += dt;
+        }
+        h->keepGrad = keep;
     }
-    h->keepGrad = keep;
     CK(cudaEventRecord(h->evT1, h->s));
     CK(cudaEventSynchronize(h->evT1));
     CK(cudaStreamSynchronize(h->cs));
+    CK(cudaStreamSynchronize(h->s2));
     float m = 0.f;
     CK(cudaEventElapsedTime(&m, h->evT0, h->evT1));
     if (ms) *ms = m;
     if (launches) *launches = h->launches - l0;
-    return check_err_flag(h, "dgx_run_steps");
+    return check_err_flag(h, "dgx_run_steps", dev);
 }
+
+int dgx_get_dt_history(dgx_handle* h, int cap, double* dts, int* count) {
+    CK(cudaSetDevice(h->cfg.device));
+    const int n = h->dtHistCount < cap ? h->dtHistCount : cap;
+    if (count) *count = h->dtHistCount;
+    if (n > 0 && dts) {
+        CK(cudaMemcpyAsync(dts, h->dtHist, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->s));
+        CK(cudaStreamSynchronize(h->s));
+    }
+    return 0;
+}
+
+int dgx_step_graph_active(const dgx_handle* h) { return h && h->graph ? 1 : 0; }
 
 int dgx_profile_stage(dgx_handle* h, double t, double dt, int cap, const char** names, float* ms, int* count) {
     if (count) *count = 0;

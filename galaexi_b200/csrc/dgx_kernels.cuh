@@ -80,6 +80,14 @@ struct KParams {
     double *rk3S2, *rk3UPrev;
     int storeGrad;  // k_lifting also writes the volume gradients (only analysis / dgx_get_gradients read them; the viscous volume
                     // integral is formed inside k_lifting and travels as 4 doubles per node in Ut)
+    // device-paced time stepping (dgx_run_steps flag 4): dtDev[3] holds the step's dt and the stage kernels form b_dt = RKb * dt
+    // themselves; dtFuse: this k_lifting launch (stage 1 of a step) also evaluates CalcTimeStep of the state it reads and leaves
+    // the minima in dtDev[0..1] (calctimestep.f90:98-186); bulkDev: CalcForcing's bulk velocity kept on the device
+    const double* dtDev;
+    double* dtAcc;
+    int dtFuse;
+    double dtCFL, dtDFL;
+    const double* bulkDev;
     int flags;  // tuning switches (DGX_FLAGS): 1 lifting: L2 prefetch of own later-phase data; 2 lifting: L2 prefetch of the element
                 // a resident wave ahead; 4 / 8: the same two for k_volsurf2
 };
@@ -299,7 +307,8 @@ __global__ void __launch_bounds__(n* n* n) k_filter(const KParams P) {
 // kernels then run in MODE 0 and leave Ut = -sJ * (DG operator); here Ut += Ut_src (the reference adds Ut_src / sJ before
 // the Jacobian is applied, exactfunc.f90:1109), then vector.f90:163-183 and the face extraction of the fused epilogue.
 template <int n, int NT, int MODE>
-__global__ void __launch_bounds__(n* n* n) k_source_rk(const KParams P, double t, double mRKA, double b_dt) {
+__global__ void __launch_bounds__(n* n* n) k_source_rk(const KParams P, double t, double mRKA, double b_dt_in) {
+    const double b_dt = P.dtDev ? b_dt_in * __ldg(P.dtDev + 3) : b_dt_in;  // device-paced stepping: b_dt_in carries RKb, dt lives on the device
     constexpr int n2 = n * n, n3 = n2 * n;
     extern __shared__ double smem[];
     double *tile = smem, *sLm = smem + 5 * n3, *sLp = sLm + n;
@@ -326,7 +335,7 @@ __global__ void __launch_bounds__(n* n* n) k_source_rk(const KParams P, double t
         src[1] = src[2] = src[3] = tmp[1] * cosX + tmp[2] * sin2;
         src[4] = tmp[3] * cosX + tmp[4] * sin2 + tmp[5] * sinX;
     }
-    if (P.tcSource) { src[1] -= P.tcDpdx; src[4] -= P.tcDpdx * P.tcBulkVel; }
+    if (P.tcSource) { src[1] -= P.tcDpdx; src[4] -= P.tcDpdx * (P.bulkDev ? __ldg(P.bulkDev) : P.tcBulkVel); }
     if (P.spMat) {
         // Ut = Ut - SpongeMat (U - SpBaseFlow) before the Jacobian (sponge.f90:574-579): times sJ here
         const double sm = P.spMat[(size_t)e * n3 + tt] * P.sJ[(size_t)e * n3 + tt];
@@ -380,6 +389,85 @@ constexpr size_t source_smem_bytes() { return sizeof(double) * (5 * n * n * n + 
 template <int n>
 constexpr size_t filter_smem_bytes() { return sizeof(double) * (10 * n * n * n + n * n + 2 * n); }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// CalcTimeStep at one node (equations/navierstokes/calctimestep.f90:192-296): the three convective and the three viscous
+// eigenvalue bounds lam[0..5]; returns true when the state is not admissible. M: the nine metric terms of the node.
+__device__ __forceinline__ bool timestep_node(const Eos& eos, bool parabolic, const double (&Uc)[5], const double (&M)[9], double sJ, double (&lam)[6]) {
+    double Pr[6];
+    cons_to_prim(Pr, Uc, eos);
+    const double c = sqrt(eos.kappa * Pr[PRES] / Uc[DENS]);
+    const bool bad = !(Uc[DENS] > 0.0) || !(Pr[PRES] > 0.0) || !isfinite(Uc[ENER]);
+    const double kmax = fmax(4.0 / 3.0, eos.kappa / eos.Pr);
+    const double mu = parabolic ? viscosity(eos, Pr[TEMP]) : 0.0;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const double m0 = M[3 * d], m1 = M[3 * d + 1], m2 = M[3 * d + 2];
+        const double nrm2 = m0 * m0 + m1 * m1 + m2 * m2;
+        lam[d] = fabs(m0 * (Pr[VEL1] * sJ) + m1 * (Pr[VEL2] * sJ) + m2 * (Pr[VEL3] * sJ)) + c * (sJ * sqrt(nrm2));
+        lam[3 + d] = mu / Uc[DENS] * (kmax * (nrm2 * sJ * sJ));
+    }
+    return bad;
+}
+// positive doubles order like their bit patterns
+__device__ __forceinline__ void atomic_min_pos(double* addr, double v) {
+    atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+// Element maxima of lam[0..5] over the NTHR threads of the block (max is exact in any order), then the element's time step
+// bounds into the global minima out[0] (convective) / out[1] (viscous); errFlag bit 2 for inadmissible states
+// (calctimestep.f90:134-186). Every thread of the block must call it; the last warp may be partial.
+template <int NTHR>
+__device__ __forceinline__ void timestep_block_min(const double (&lam)[6], bool bad, double (*red)[32], const KParams& P, double CFL, double DFL,
+                                                   double* out) {
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int nAct = (NTHR - 32 * w) < 32 ? (NTHR - 32 * w) : 32;
+    const unsigned mask = nAct == 32 ? 0xffffffffu : ((1u << nAct) - 1u);
+#pragma unroll
+    for (int x = 0; x < 6; x++) {
+        double v = lam[x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double u = __shfl_down_sync(mask, v, o);
+            if (lane + o < nAct) v = fmax(v, u);
+        }
+        if (lane == 0) red[x][w] = v;
+    }
+    const int anyBad = __syncthreads_or(bad ? 1 : 0);
+    if (t == 0) {
+        constexpr int nw = (NTHR + 31) / 32;
+        double mx[6];
+#pragma unroll
+        for (int x = 0; x < 6; x++) {
+            double v = red[x][0];
+            for (int ww = 1; ww < nw; ww++) v = fmax(v, red[x][ww]);
+            mx[x] = v;
+        }
+        const double lc = mx[0] + mx[1] + mx[2];
+        const double dtc = CFL * 2.0 / lc;
+        if (anyBad || !(dtc > 0.0) || !isfinite(dtc)) atomicOr(P.errFlag, 2);
+        else atomic_min_pos(&out[0], dtc);
+        if (P.parabolic) {
+            const double lv = mx[3] + mx[4] + mx[5];
+            const double dtv = DFL * 4.0 / lv;
+            if (dtv > 0.0 && isfinite(dtv)) atomic_min_pos(&out[1], dtv);
+        }
+    }
+}
+// End of CalcTimeStep in device-paced stepping: dt = min(convective, viscous) into acc[3] and the history, accumulators
+// re-armed for the next step; acc[2] < 0: another rank found an inadmissible state (after the min-reduction over the ranks)
+constexpr double DT_HUGE = 1.7976931348623157e308;
+static __global__ void k_dt_pre(double* acc, const int* errFlag) { acc[2] = (*errFlag & 2) ? -1.0 : 0.0; }
+static __global__ void k_dt_finish(double* acc, int* errFlag, double* hist, int cap) {
+    if (acc[2] < 0.0) atomicOr(errFlag, 2);
+    const double dt = acc[0] < acc[1] ? acc[0] : acc[1];
+    acc[3] = dt;
+    const int slot = (int)acc[4];  // steps finished since dgx_run_steps armed the accumulators
+    if (hist && slot < cap) hist[slot] = dt;
+    acc[4] = (double)(slot + 1);
+    acc[0] = DT_HUGE; acc[1] = DT_HUGE; acc[2] = 0.0;
+}
+static __global__ void k_bulk_finish(double* tot, double Vol) { tot[1] = tot[0] / Vol; }
+
 // ---------------------------------------------------------------------------------------------------------
 // BR1 lifting (strong form, non-conservative volume integral): gradU = sJ * ( M . D U + sum_faces F n Lhat )
 // n == 8 (N=7): the three derivative sweeps of the lifting run on the FP64 tensor-core path (mma.sync m8n8k4, DMMA): the
@@ -416,6 +504,7 @@ __global__ void __launch_bounds__(n* n* n, lifting_min_blocks<n>()) k_lifting(co
     __shared__ int sMort[6];  // GEN: 0-based big mortar side of local side loc, or -1
     __shared__ double sSig[6];  // GEN: sign of the face in the surface integral (weak form: -1 on slave faces, surfint.t90:640-644)
     __shared__ __align__(8) unsigned long long sBar;  // mbarrier of the metric / Jacobian bulk copy
+    __shared__ double sRed[6][32];  // dtFuse: element maxima of the time step eigenvalue bounds
     const bool br2 = GEN && P.lifting == 2;
     // even n: the element's metrics (9 n^3) and Jacobian (n^3) are fetched by TMA bulk copies issued at kernel entry into a
     // staging area behind the operator tables, so this read is in flight from the first cycle of the CTA instead of
@@ -477,6 +566,20 @@ __global__ void __launch_bounds__(n* n* n, lifting_min_blocks<n>()) k_lifting(co
         sT[1 * n3 + tin] = Pr[VEL2];
         sT[2 * n3 + tin] = Pr[VEL3];
         sT[3 * n3 + tin] = Pr[TEMP];
+        if (P.dtFuse) {
+            // CalcTimeStep of the state this stage reads (= the state at the start of the time step, calctimestep.f90:98-186)
+            // while it is in registers: the node's metrics and Jacobian are fetched here already (the same DRAM round trip as
+            // the state; step 3 then finds them in L1 / L2 or in the TMA staging area), which saves k_timestep's separate pass
+            // over U, metrics and sJ (device-paced stepping, dgx_run_steps)
+            if (TMA) { __syncthreads(); mbar_wait(smem_u32(&sBar), 0); }
+            double M9[9], lam[6];
+            const double* M = TMA ? stM + t : P.metrics + (size_t)e * 9 * n3 + t;
+#pragma unroll
+            for (int x = 0; x < 9; x++) M9[x] = M[x * n3];
+            const double sJ = TMA ? stM[9 * n3 + t] : P.sJ[(size_t)e * n3 + t];
+            const bool bad = timestep_node(eos, true, Uc, M9, sJ, lam);
+            timestep_block_min<n3>(lam, bad, sRed, P, P.dtCFL, P.dtDFL, P.dtAcc);
+        }
     }
     // 2. faces: lifting flux F = 1/2 (U_s - U_m) SurfElem in side orientation -> stored in element face order
     for (int f = t; f < 6 * n2; f += n3) {
@@ -965,7 +1068,8 @@ __global__ void __launch_bounds__(128, 4) k_sideflux(const KParams P, int side0,
 template <int n>
 constexpr int volsurf_min_blocks() { return n == 6 ? 2 : 1; }
 template <int n, int NT, int MODE>
-__global__ void __launch_bounds__(n* n* n, volsurf_min_blocks<n>()) k_volsurf(const KParams P, double mRKA, double b_dt) {
+__global__ void __launch_bounds__(n* n* n, volsurf_min_blocks<n>()) k_volsurf(const KParams P, double mRKA, double b_dt_in) {
+    const double b_dt = P.dtDev ? b_dt_in * __ldg(P.dtDev + 3) : b_dt_in;  // device-paced stepping: b_dt_in carries RKb, dt lives on the device
     constexpr int n2 = n * n, n3 = n2 * n;
     extern __shared__ double smem[];
     double* sA = smem;               // [15][n3] multipurpose: fluxes f,g,h (15) | node record (6) + metrics (9) | U tile (5)
@@ -1141,11 +1245,6 @@ template <int n>
 constexpr size_t volsurf_smem_bytes() { return sizeof(double) * (15 * n * n * n + 30 * n * n + 2 * n * n + 4 * n); }
 
 // ---------------------------------------------------------------------------------------------------------
-// positive doubles order like their bit patterns
-__device__ __forceinline__ void atomic_min_pos(double* addr, double v) {
-    atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
-}
-
 // per element max eigenvalues -> global min of CFL*2/lam_c and DFL*4/lam_v  (calctimestep.f90:98-296)
 template <int n>
 constexpr int timestep_threads() { return ((n * n * n + 31) / 32) * 32; }
@@ -1155,57 +1254,20 @@ __global__ void __launch_bounds__(timestep_threads<n>()) k_timestep(const KParam
     constexpr int n3 = n * n * n;
     __shared__ double red[6][32];
     const int e = blockIdx.x, t = threadIdx.x;
-    const bool active = t < n3;  // block is padded to full warps so the shuffles below are well defined
-    const Eos eos = P.eos;
+    const bool active = t < n3;  // block is padded to full warps
     double lam[6] = {0, 0, 0, 0, 0, 0};
     bool bad = false;
     if (active) {
-        double Uc[5], Pr[6], M[9];
+        double Uc[5], M[9];
         const double* U = P.U + (size_t)e * 5 * n3 + t;
 #pragma unroll
         for (int v = 0; v < 5; v++) Uc[v] = U[v * n3];
         const double* Mg = P.metrics + (size_t)e * 9 * n3 + t;
 #pragma unroll
         for (int x = 0; x < 9; x++) M[x] = Mg[x * n3];
-        const double sJ = P.sJ[(size_t)e * n3 + t];
-        cons_to_prim(Pr, Uc, eos);
-        const double c = sqrt(eos.kappa * Pr[PRES] / Uc[DENS]);
-        bad = !(Uc[DENS] > 0.0) || !(Pr[PRES] > 0.0) || !isfinite(Uc[ENER]);
-        const double kmax = fmax(4.0 / 3.0, eos.kappa / eos.Pr);
-        const double mu = P.parabolic ? viscosity(eos, Pr[TEMP]) : 0.0;
-#pragma unroll
-        for (int d = 0; d < 3; d++) {
-            const double* Md = M + 3 * d;
-            const double nrm2 = Md[0] * Md[0] + Md[1] * Md[1] + Md[2] * Md[2];
-            lam[d] = fabs(Md[0] * (Pr[VEL1] * sJ) + Md[1] * (Pr[VEL2] * sJ) + Md[2] * (Pr[VEL3] * sJ)) + c * (sJ * sqrt(nrm2));
-            lam[3 + d] = mu / Uc[DENS] * (kmax * (nrm2 * sJ * sJ));
-        }
+        bad = timestep_node(P.eos, P.parabolic != 0, Uc, M, P.sJ[(size_t)e * n3 + t], lam);
     }
-#pragma unroll
-    for (int x = 0; x < 6; x++) {
-        double v = lam[x];
-        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-        if ((t & 31) == 0) red[x][t >> 5] = v;
-    }
-    const int anyBad = __syncthreads_or(bad ? 1 : 0);
-    if (t == 0) {
-        constexpr int nw = timestep_threads<n>() / 32;
-        double mx[6];
-        for (int x = 0; x < 6; x++) {
-            double v = red[x][0];
-            for (int w = 1; w < nw; w++) v = fmax(v, red[x][w]);
-            mx[x] = v;
-        }
-        const double lc = mx[0] + mx[1] + mx[2];
-        const double dtc = CFL * 2.0 / lc;
-        if (anyBad || !(dtc > 0.0) || !isfinite(dtc)) atomicOr(P.errFlag, 2);
-        else atomic_min_pos(&out[0], dtc);
-        if (P.parabolic) {
-            const double lv = mx[3] + mx[4] + mx[5];
-            const double dtv = DFL * 4.0 / lv;
-            if (dtv > 0.0 && isfinite(dtv)) atomic_min_pos(&out[1], dtv);
-        }
-    }
+    timestep_block_min<timestep_threads<n>()>(lam, bad, red, P, CFL, DFL, out);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -241,7 +241,8 @@ __device__ __forceinline__ void vs2_sweep(const double* __restrict__ R, const do
 }
 
 template <int n, int MODE, int VAR>
-__global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf2(const __grid_constant__ KParams P, int nWork, double mRKA, double b_dt, int lookahead) {
+__global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf2(const __grid_constant__ KParams P, int nWork, double mRKA, double b_dt_in, int lookahead) {
+    const double b_dt = P.dtDev ? b_dt_in * __ldg(P.dtDev + 3) : b_dt_in;  // device-paced stepping: b_dt_in carries RKb, dt lives on the device
     constexpr int n2 = n * n, n3 = n2 * n, SEG = vs2_seg<n>(), SL = TileV<n>::SLOT, T = vs2_parts<n>() * n2, EPB = vs2_epb<n>();
     extern __shared__ double smem[];
     const int le = threadIdx.x / T, tid = threadIdx.x - le * T;

@@ -27,8 +27,8 @@ _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 
 EXPORTS = ("dgx_create", "dgx_destroy", "dgx_last_error", "dgx_set_state", "dgx_get_state", "dgx_get_ut",
-           "dgx_get_gradients", "dgx_set_keep_gradients", "dgx_time_derivative", "dgx_rk_stage", "dgx_rk_step", "dgx_calc_timestep",
-           "dgx_analyze_tgv", "dgx_calc_bulk_velocity", "dgx_calc_body_forces", "dgx_calc_wall_velocity", "dgx_set_channel_forcing", "dgx_temp_filter_time_deriv", "dgx_get_baseflow", "dgx_sync", "dgx_run_steps", "dgx_profile_stage", "dgx_nccl_unique_id", "dgx_launch_count", "dgx_sizeof_config", "dgx_halo_plan")
+           "dgx_get_gradients", "dgx_get_face_array", "dgx_set_keep_gradients", "dgx_time_derivative", "dgx_rk_stage", "dgx_rk_step", "dgx_calc_timestep",
+           "dgx_analyze_tgv", "dgx_calc_bulk_velocity", "dgx_calc_body_forces", "dgx_calc_wall_velocity", "dgx_set_channel_forcing", "dgx_temp_filter_time_deriv", "dgx_get_baseflow", "dgx_sync", "dgx_run_steps", "dgx_get_dt_history", "dgx_step_graph_active", "dgx_profile_stage", "dgx_nccl_unique_id", "dgx_launch_count", "dgx_sizeof_config", "dgx_halo_plan")
 
 
 class DgxConfig(C.Structure):
@@ -80,6 +80,7 @@ def load_library():
     for nm in ("dgx_set_state", "dgx_get_state", "dgx_get_ut"):
         getattr(lib, nm).argtypes = [h, _dp]
     lib.dgx_get_gradients.argtypes = [h, _dp, _dp, _dp]
+    lib.dgx_get_face_array.argtypes = [h, C.c_int, _dp]
     lib.dgx_set_keep_gradients.argtypes = [h, C.c_int]
     lib.dgx_time_derivative.argtypes = [h, C.c_double]
     lib.dgx_rk_stage.argtypes = [h, C.c_int, C.c_double, C.c_double]
@@ -94,6 +95,8 @@ def load_library():
     lib.dgx_set_channel_forcing.argtypes = [h, C.c_int, C.c_double, C.c_double]
     lib.dgx_sync.argtypes = [h]
     lib.dgx_run_steps.argtypes = [h, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]
+    lib.dgx_get_dt_history.argtypes = [h, C.c_int, _dp, _ip]
+    lib.dgx_step_graph_active.argtypes = [h]
     lib.dgx_profile_stage.argtypes = [h, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), _ip]
     lib.dgx_nccl_unique_id.argtypes = [C.c_char_p]
     lib.dgx_launch_count.argtypes = [h]
@@ -247,6 +250,17 @@ class DGSolver:
         self._ck(self.lib.dgx_get_gradients(self.h, *[x.ctypes.data_as(_dp) for x in g]))
         return g
 
+    FACE_ARRAYS = ("U_master", "U_slave", "Flux_master", "gradUx_master", "gradUy_master", "gradUz_master", "gradUx_slave",
+                   "gradUy_slave", "gradUz_slave")
+
+    def get_face_array(self, name: str) -> np.ndarray:
+        """A face array of the last RHS evaluation in the reference layout: numpy [side, q, p, var] == Fortran (var,p,q,side)."""
+        which = self.FACE_ARRAYS.index(name)
+        n = self.case.N + 1
+        out = np.empty((self.case.mesh.nSides, n, n, 5 if which < 3 else 4))
+        self._ck(self.lib.dgx_get_face_array(self.h, which, out.ctypes.data_as(_dp)))
+        return out
+
     def set_keep_gradients(self, on: bool):
         """on (default): the last stage of every RK step stores the volume gradients, as the reference's d_gradUx/y/z hold them
         at analyze steps (testcase.f90:361-364); off: RK stages never write them (steps no analysis follows)."""
@@ -396,10 +410,25 @@ class DGSolver:
     def sync(self):
         self._ck(self.lib.dgx_sync(self.h))
 
-    def run_steps(self, nSteps: int, t: float, dt: float, adaptive: bool = False):
+    def run_steps(self, nSteps: int, t: float, dt: float, adaptive: bool = False, forcing: bool = False, device_paced: bool = False,
+                  graph: bool = False):
+        """The time loop between two analyze points on the device (dgx_run_steps): returns (device ms, kernels launched).
+        device_paced: dt never leaves the device (no host synchronisation inside the call); graph: replay step pairs as a
+        CUDA graph. The step sizes of a device-paced call are read with dt_history()."""
         ms, ln = C.c_float(), C.c_longlong()
-        self._ck(self.lib.dgx_run_steps(self.h, nSteps, float(t), float(dt), int(adaptive), C.byref(ms), C.byref(ln)))
+        flags = int(bool(adaptive)) | 2 * int(bool(forcing)) | 4 * int(bool(device_paced)) | 8 * int(bool(graph))
+        self._ck(self.lib.dgx_run_steps(self.h, nSteps, float(t), float(dt), flags, C.byref(ms), C.byref(ln)))
         return ms.value, ln.value
+
+    def dt_history(self) -> np.ndarray:
+        cnt = C.c_int()
+        self._ck(self.lib.dgx_get_dt_history(self.h, 0, None, C.byref(cnt)))
+        out = np.zeros(max(cnt.value, 1))
+        self._ck(self.lib.dgx_get_dt_history(self.h, cnt.value, out.ctypes.data_as(_dp), C.byref(cnt)))
+        return out[:cnt.value]
+
+    def step_graph_active(self) -> bool:
+        return bool(self.lib.dgx_step_graph_active(self.h))
 
     def profile_stage(self, t: float, dt: float):
         names = (C.c_char_p * 8)()

@@ -177,11 +177,28 @@ int dgx_calc_wall_velocity(dgx_handle *h, const double *wGP, const int *BC, int 
 int dgx_temp_filter_time_deriv(dgx_handle *h, double dt, double tempFilterWidth);
 int dgx_get_baseflow(dgx_handle *h, double *SpBaseFlow);
 
-/* measurement helpers (not part of the reference interface) */
+/* Face arrays of the last RHS evaluation in the reference's layout (nVar,0:N,0:N,nSides): which = 0 U_master, 1 U_slave,
+ * 2 Flux_master (5 variables; dg_vars.f90:62-75), 3..5 gradUx/y/z_master, 6..8 gradUx/y/z_slave (the 4 lifted variables u, v, w,
+ * T; lifting_vars.f90:43-60). For parity checks of orientation and sign conventions; not on the hot path. */
+int dgx_get_face_array(dgx_handle *h, int which, double *out);
 int dgx_sync(dgx_handle *h);
-/* nSteps RK steps with fixed dt, state resident in HBM; returns device-timed milliseconds (CUDA events on
- * the launching stream) and the number of kernels launched */
-int dgx_run_steps(dgx_handle *h, int nSteps, double t, double dt, int adaptive_dt, float *ms, long long *launches);
+/* nSteps RK time steps with the state resident in HBM: the body of the reference's time loop between two analyze points
+ * (timedisc/timedisc.f90:176-200: CalcForcing, CalcTimeStep, TimeStep). flags:
+ *   1  adaptive dt: CalcTimeStep before every step (otherwise the fixed dt given);
+ *   2  CalcForcing before every step (channel testcase, testcase.f90:241-271) with the weights / volume of the last
+ *      dgx_calc_bulk_velocity call; the bulk velocity feeds TestcaseSource;
+ *   4  device-paced: dt (and the bulk velocity) never leave the device -- stage 1 of every step evaluates CalcTimeStep inside
+ *      its lifting kernel, the min over the ranks is an NCCL all-reduce on the communication stream and the stage kernels form
+ *      b_dt = RKb * dt themselves; no host synchronisation inside the call. Needs flag 1, a time-independent source and a
+ *      2-register scheme. An inadmissible state (calctimestep.f90:134-146) is reported when the call returns. The step sizes
+ *      are read back with dgx_get_dt_history (t advances by their sum, added in step order like the reference's t = t + dt);
+ *   8  with 4: pairs of steps are replayed as one CUDA graph (dgx_step_graph_active tells whether capture succeeded).
+ * Results are bit-identical for every combination of 4 and 8. ms: device time of the call (CUDA events on the launching
+ * stream); launches: kernels launched (graph replays count the kernels they contain). */
+int dgx_run_steps(dgx_handle *h, int nSteps, double t, double dt, int flags, float *ms, long long *launches);
+/* the dt of every step of the last device-paced dgx_run_steps: min(cap, count) values into dts, *count = number of steps */
+int dgx_get_dt_history(dgx_handle *h, int cap, double *dts, int *count);
+int dgx_step_graph_active(const dgx_handle *h);
 /* per-kernel CUDA-event timing of one RK stage: names[i] -> ms[i], *count entries (<= cap) */
 int dgx_profile_stage(dgx_handle *h, double t, double dt, int cap, const char **names, float *ms, int *count);
 int dgx_nccl_unique_id(char *out128);

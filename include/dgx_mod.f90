@@ -116,8 +116,27 @@ INTERFACE
   INTEGER(C_INT) FUNCTION dgx_set_channel_forcing(h,on,dpdx,BulkVel) BIND(C,NAME='dgx_set_channel_forcing')
     IMPORT; TYPE(C_PTR),VALUE :: h; INTEGER(C_INT),VALUE :: on; REAL(C_DOUBLE),VALUE :: dpdx,BulkVel
   END FUNCTION
+  !> the time loop between two analyze points on the device (timedisc.f90:176-200); flags: 1 adaptive dt, 2 CalcForcing per step,
+  !> 4 device-paced (no host synchronisation), 8 CUDA-graph replay
+  INTEGER(C_INT) FUNCTION dgx_run_steps(h,nSteps,t,dt,flags,ms,launches) BIND(C,NAME='dgx_run_steps')
+    IMPORT; TYPE(C_PTR),VALUE :: h; INTEGER(C_INT),VALUE :: nSteps,flags; REAL(C_DOUBLE),VALUE :: t,dt
+    REAL(C_FLOAT),INTENT(OUT) :: ms; INTEGER(C_LONG_LONG),INTENT(OUT) :: launches
+  END FUNCTION
+  INTEGER(C_INT) FUNCTION dgx_get_dt_history(h,cap,dts,count) BIND(C,NAME='dgx_get_dt_history')
+    IMPORT; TYPE(C_PTR),VALUE :: h; INTEGER(C_INT),VALUE :: cap; REAL(C_DOUBLE),INTENT(OUT) :: dts(*); INTEGER(C_INT),INTENT(OUT) :: count
+  END FUNCTION
+  INTEGER(C_INT) FUNCTION dgx_step_graph_active(h) BIND(C,NAME='dgx_step_graph_active')
+    IMPORT; TYPE(C_PTR),VALUE :: h
+  END FUNCTION
+  INTEGER(C_INT) FUNCTION dgx_get_face_array(h,which,arr) BIND(C,NAME='dgx_get_face_array')
+    IMPORT; TYPE(C_PTR),VALUE :: h; INTEGER(C_INT),VALUE :: which; REAL(C_DOUBLE),INTENT(OUT) :: arr(*)
+  END FUNCTION
+  INTEGER(C_INT) FUNCTION dgx_sync(h) BIND(C,NAME='dgx_sync')
+    IMPORT; TYPE(C_PTR),VALUE :: h
+  END FUNCTION
 END INTERFACE
 
+PUBLIC :: dgx_run_steps,dgx_get_dt_history,dgx_step_graph_active,dgx_sync,dgx_get_face_array
 PUBLIC :: dgx_create,dgx_destroy,dgx_last_error,dgx_set_state,dgx_get_state,dgx_get_ut,dgx_get_gradients
 PUBLIC :: dgx_set_keep_gradients,dgx_time_derivative,dgx_rk_stage,dgx_rk_step,dgx_calc_timestep,dgx_nccl_unique_id
 PUBLIC :: dgx_analyze_tgv,dgx_calc_bulk_velocity,dgx_set_channel_forcing,dgx_temp_filter_time_deriv,dgx_get_baseflow

@@ -1,0 +1,72 @@
+"""Parity criteria shared by tests/, tools/mr_check.py and the out-of-band parity legs of bench.py.
+
+TEST INFRASTRUCTURE ONLY (uses the CPU oracle as the checker); the product package never imports this module.
+
+Criteria (BASELINE.json north_star): residual Ut per stage rel-L2 <= 1e-12 against the FP64 oracle; where FP64 round-off itself
+moves the oracle's result by more than that (cancellation-dominated residuals such as the low-Mach TGV start field) the
+comparison is made against the same oracle source evaluated in 80-bit extended precision and the CUDA result must be as close
+to that value as twice the FP64 oracle's own round-off. Conserved variables after the steps: rel-L2 and Linf <= 1e-10; dt rel
+<= 1e-13.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+TOL_UT = 1e-12
+TOL_U = 1e-10
+TOL_DT = 1e-13
+
+# every Ut comparison of this process, in order: dict(case, err_fp64, used_extended, floor, err_exact, ok)
+UT_LOG: list[dict] = []
+
+
+def rel_l2(a, b) -> float:
+    return float(np.sqrt(np.sum((a - b) ** 2)) / max(np.sqrt(np.sum(b ** 2)), 1e-300))
+
+
+def ut_error(c, U0, Ut, Ut_ref, t: float = 0.0, label: str = "", prepare=None) -> dict:
+    """Residual parity of Ut (device) against Ut_ref (FP64 oracle) for the single-rank case c at state U0.
+    prepare(oracle): optional set-up applied to the extended-precision oracle (forcing, sponge ...)."""
+    from .oracle import Oracle
+    err = rel_l2(Ut, Ut_ref)
+    rec = dict(case=label, err_fp64=err, used_extended=False, floor=None, err_exact=None, ok=err <= TOL_UT)
+    if err > TOL_UT:
+        x = Oracle(c, "extended")
+        x.set_state(U0)
+        if prepare is not None:
+            prepare(x)
+        exact = np.asarray(x.time_derivative(t), dtype=np.float64)
+        x.close()
+        floor = rel_l2(Ut_ref, exact)
+        err_exact = rel_l2(Ut, exact)
+        rec.update(used_extended=True, floor=floor, err_exact=err_exact, ok=err_exact <= max(TOL_UT, 2.0 * floor))
+    UT_LOG.append(rec)
+    return rec
+
+
+def oracle_rhs_and_steps(c, U0, nsteps: int = 2, t0: float = 0.0):
+    """Ut(t0), dt and the state after nsteps RK steps (fixed dt = the first CalcTimeStep) from the FP64 oracle."""
+    from .oracle import Oracle
+    o = Oracle(c)
+    o.set_state(U0)
+    Ut_ref = o.time_derivative(t0).copy()
+    dt = o.calc_timestep()[0]
+    t = t0
+    for _ in range(nsteps):
+        o.rk_step(t, dt)
+        t += dt
+    U_ref = o.array("U").copy()
+    o.close()
+    return Ut_ref, dt, U_ref
+
+
+def compare(c, U0, Ut, dt, U, nsteps: int = 2, label: str = "") -> dict:
+    """The full single-case verdict used by the multi-rank legs: c is the SINGLE-rank case, Ut / U the gathered device results."""
+    Ut_ref, dt_ref, U_ref = oracle_rhs_and_steps(c, U0, nsteps)
+    r = ut_error(c, U0, Ut, Ut_ref, label=label)
+    u_l2 = rel_l2(U, U_ref)
+    u_inf = float(np.abs(U - U_ref).max() / max(np.abs(U_ref).max(), 1e-300))
+    dt_rel = abs(dt - dt_ref) / dt_ref
+    ok = bool(r["ok"] and u_l2 <= TOL_U and u_inf <= TOL_U and dt_rel <= TOL_DT)
+    return dict(case=label, ut_rel_l2=r["err_fp64"], ut_used_extended_floor=r["used_extended"], ut_fp64_roundoff_floor=r["floor"],
+                ut_rel_l2_vs_extended=r["err_exact"], u_rel_l2=u_l2, u_rel_linf=u_inf, dt_rel=dt_rel, ok=ok)

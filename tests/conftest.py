@@ -16,3 +16,25 @@ def pytest_configure(config):
 def goldens():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "unit_goldens.npz"))
+
+
+def pytest_terminal_summary(terminalreporter):
+    """Which residual comparisons met 1e-12 against the FP64 oracle directly and which needed the extended-precision criterion."""
+    try:
+        from oracle import parity
+    except Exception:
+        return
+    if not parity.UT_LOG:
+        return
+    import json
+    ext = [r for r in parity.UT_LOG if r["used_extended"]]
+    terminalreporter.write_line(f"Ut parity: {len(parity.UT_LOG)} comparisons, {len(ext)} used the extended-precision criterion, "
+                                f"worst direct rel-L2 {max(r['err_fp64'] for r in parity.UT_LOG if not r['used_extended'] or True):.3e}")
+    for r in ext:
+        terminalreporter.write_line(f"  extended: {r['case']}: vs FP64 oracle {r['err_fp64']:.3e}, FP64 round-off floor {r['floor']:.3e}, vs exact {r['err_exact']:.3e}")
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "ut_parity_log.json"), "w") as f:
+            json.dump(parity.UT_LOG, f, indent=1)
+    except OSError:
+        pass

@@ -26,6 +26,7 @@ def test_two_ranks_match_single_rank(case):
     lines = [l for l in p.stdout.splitlines() if l.startswith("MRCHECK ")]
     assert p.returncode == 0 and lines, p.stdout[-2000:] + p.stderr[-4000:]
     r = json.loads(lines[-1][8:])
+    assert r["ut_ok"] and r["paced_bitwise"], r
     assert r["u_rel_l2"] <= 1e-10 and r["dt_rel"] <= 1e-13 and r["diag_rel"] <= 1e-9 and r["bulk_rel"] <= 1e-10
 
 

@@ -25,23 +25,24 @@ def _oracle(c, precision="double"):
     return Oracle(c, precision)
 
 
-def _check_ut(c, U0, Ut, Ut_ref):
-    """Residual parity. Criterion: rel-L2 <= 1e-12 against the FP64 oracle. Where FP64 round-off itself moves the
-    result by more than that (cancellation-dominated residuals, e.g. the low-Mach TGV initial field: the FP64 oracle
-    is 9e-12 away from the exact value of its own formulas), the comparison is made against the exact value (the
-    same oracle source evaluated in 80-bit extended precision) and the CUDA result must be at least as close to it
-    as twice the FP64 oracle's own round-off."""
-    err = cases.rel_l2(Ut, Ut_ref)
-    if err <= TOL_UT:
-        return err
-    x = _oracle(c, "extended")
-    x.set_state(U0)
-    exact = np.asarray(x.time_derivative(0.0), dtype=np.float64)
-    x.close()
-    floor = cases.rel_l2(Ut_ref, exact)
-    err_exact = cases.rel_l2(Ut, exact)
-    assert err_exact <= max(TOL_UT, 2.0 * floor), f"Ut rel L2 vs exact {err_exact}, FP64 oracle round-off {floor}, vs FP64 oracle {err}"
-    return err_exact
+# Cases whose FP64 residual is cancellation-dominated (rel-L2 against the FP64 oracle above 1e-12 although the CUDA result is
+# as close to the exact value as the oracle itself): the only ones allowed to take the extended-precision criterion of
+# oracle/parity.py. Every comparison is logged (gpurun_out/ut_parity_log.json, terminal summary); a case that needs the
+# fallback without being listed here fails.
+UT_EXTENDED_ALLOWED = ("test_tgv_split_reference_mesh", "test_restart_from_reference_state_file_layout")
+
+
+def _check_ut(c, U0, Ut, Ut_ref, t=0.0, prepare=None):
+    """Residual parity (criterion and fallback: oracle/parity.py)."""
+    import os
+    from oracle import parity
+    label = os.environ.get("PYTEST_CURRENT_TEST", "?").split("::")[-1].split(" ")[0]
+    r = parity.ut_error(c, U0, Ut, Ut_ref, t=t, label=label, prepare=prepare)
+    assert r["ok"], f"Ut rel L2 vs FP64 oracle {r['err_fp64']}, vs exact {r['err_exact']}, FP64 oracle round-off {r['floor']}"
+    if r["used_extended"]:
+        assert any(label.startswith(a) for a in UT_EXTENDED_ALLOWED), \
+            f"{label}: Ut rel-L2 {r['err_fp64']} > 1e-12 against the FP64 oracle (extended-precision floor {r['floor']}) in a case not listed in UT_EXTENDED_ALLOWED"
+    return r["err_exact"] if r["used_extended"] else r["err_fp64"]
 
 
 def _compare_rhs_and_steps(c, U0, nsteps=2, fixed_dt=None):

@@ -24,11 +24,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--tag", default="")
     ap.add_argument("--curved", action="store_true")
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--mode", default="host", choices=("host", "device", "graph"), help="time-step pacing of dgx_run_steps")
     args = ap.parse_args()
     import bench
-    bench.N_POLY, bench.ELEMS_PER_GPU, bench.CURVED = args.degree, args.elems, args.curved
     from galaexi_b200 import dg
-    c, U0 = bench.build_case(1, 0, N=args.degree)
+    wl = bench.make_workload(args.config, "weak", 1, 0, degree=args.degree, elems=args.elems, curved=args.curved)
+    c, U0 = wl["c"], wl["U0"]
+    kw = dict(adaptive=True, device_paced=args.mode != "host", graph=args.mode == "graph")
     libs = args.libs or [dg.LIB_PATH]
     ref = None
     n = args.degree + 1
@@ -38,11 +41,11 @@ def main():
         s = dg.DGSolver(c, device=0)
         s.set_state(U0)
         dt0, _ = s.CalcTimeStep()
-        s.run_steps(args.warmup, 0.0, dt0, adaptive=True)
+        s.run_steps(args.warmup, 0.0, dt0, **kw)
         s.sync()
         best = None
         for _ in range(3):
-            ms, launches = s.run_steps(args.steps, 0.0, dt0, adaptive=True)
+            ms, launches = s.run_steps(args.steps, 0.0, dt0, **kw)
             best = ms if best is None else min(best, ms)
         prof = {}
         for _ in range(5):
@@ -56,7 +59,7 @@ def main():
         else:
             dev = float(np.max(np.abs(U - ref)) / np.max(np.abs(ref)))
         s.FinalizeDG()
-        line = dict(lib=os.path.basename(path), degree=args.degree, elems=args.elems, ms_per_step=round(best / args.steps, 4),
+        line = dict(lib=os.path.basename(path), mode=args.mode, degree=args.degree, elems=args.elems, ms_per_step=round(best / args.steps, 4),
                     gdof_per_s=round(c.nDOF * 5 * args.steps / (best * 1e-3) / 1e9, 4), kernels_ms=prof, launches=int(launches),
                     finite=bool(np.isfinite(U).all()), rel_dev_vs_first=dev)
         print(json.dumps(line), flush=True)

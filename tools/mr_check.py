@@ -146,6 +146,32 @@ def main():
     t_mr = t
     state_path = s.WriteState("mesh.h5", t_mr, t_mr + 1.0, "mr", out_dir=tmpd[0], dt=dt, barrier=dist.barrier)
     s.sync()
+    # time stepping paced by the device (dt never on the host, NCCL min-reduction on the communication stream, CUDA-graph replay)
+    # against the host-paced call sequence on the same ranks: bit-identical state and dt history
+    paced = 1
+    if getattr(c.timedisc, "kind", "LSERKW2") != "LSERKK3" and not c.IniExactFunc:
+        finals = []
+        for mode in ("host", "device", "graph"):
+            s.set_state(U0)
+            if mode == "host":
+                tt, dts = 0.0, []
+                for _ in range(5):
+                    d_, e_ = s.CalcTimeStep()
+                    s.TimeStepByLSERKW2(tt, d_)
+                    tt += d_
+                    dts.append(d_)
+                dts = np.array(dts)
+            else:
+                s.run_steps(2, 0.0, dt, adaptive=True, device_paced=True, graph=mode == "graph")
+                d1 = s.dt_history().copy()
+                s.run_steps(3, 0.0, dt, adaptive=True, device_paced=True, graph=mode == "graph")
+                dts = np.concatenate([d1, s.dt_history()])
+            finals.append((dts, s.get_state()))
+        paced = int(all(np.array_equal(f[0], finals[0][0]) and np.array_equal(f[1], finals[0][1]) for f in finals[1:]))
+    pt = torch.tensor([paced], dtype=torch.int32, device="cuda")
+    dist.all_reduce(pt, op=dist.ReduceOp.MIN)
+    paced_ok = bool(pt.item())
+    s.sync()
     outs = [None] * world
     dist.gather_object((c.mesh.offsetElem, Ut, U, dt), outs if rank == 0 else None, dst=0)
     res = None
@@ -187,17 +213,20 @@ def main():
         state_ok = bool(np.array_equal(Ufile, U_all) and tfile == t_mr and info["complete"] and info["nGlobalElems"] == c1.mesh.nElems)
         diag_err = float(np.max(np.abs(diag - diag1) / np.maximum(np.abs(diag1), 1e-3 * np.abs(diag1).max()))) if diag is not None else 0.0
         # bulk_rel is relative to the O(1) velocity scale (the TGV mean velocity is zero)
+        from oracle import parity
+        ut = parity.ut_error(c1, U01, Ut_all, Ut_ref, label=f"{name}@{world}")   # the single-rank criterion, incl. its extended-precision floor
         res = dict(wall_rel=wall_err, state_file_ok=state_ok, diag_rel=diag_err, bulk_rel=abs(bulk - bulk1) / max(abs(bulk1), 1.0), case=name, world=world,
-                   ut_rel_l2=cases.rel_l2(Ut_all, Ut_ref), u_rel_l2=cases.rel_l2(U_all, U_ref),
+                   ut_rel_l2=ut["err_fp64"], ut_ok=bool(ut["ok"]), ut_used_extended_floor=ut["used_extended"], ut_fp64_roundoff_floor=ut["floor"],
+                   ut_rel_l2_vs_extended=ut["err_exact"], u_rel_l2=cases.rel_l2(U_all, U_ref),
                    dt_rel=abs(outs[0][3] - dt_ref) / dt_ref, ut_vs_1gpu_maxabs=float(np.abs(Ut_all - Ut1).max()),
-                   ut_scale=float(np.abs(Ut_ref).max()))
+                   ut_scale=float(np.abs(Ut_ref).max()), paced_bitwise=paced_ok)
         s1.FinalizeDG()
         print("MRCHECK " + json.dumps(res), flush=True)
     s.FinalizeDG()
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
-        ok = (res["u_rel_l2"] <= 1e-10 and res["dt_rel"] <= 1e-13 and res["ut_vs_1gpu_maxabs"] <= 1e-9 * res["ut_scale"]
+        ok = (res["ut_ok"] and res["paced_bitwise"] and res["u_rel_l2"] <= 1e-10 and res["dt_rel"] <= 1e-13 and res["ut_vs_1gpu_maxabs"] <= 1e-9 * res["ut_scale"]
               and res["diag_rel"] <= 1e-9 and res["bulk_rel"] <= 1e-10 and res["wall_rel"] <= 1e-10 and res["state_file_ok"])
         sys.exit(0 if ok else 3)
 

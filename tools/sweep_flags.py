@@ -24,7 +24,8 @@ def main():
     ap.add_argument("sweep", nargs="*")
     a = ap.parse_args()
     from galaexi_b200 import dg
-    c, U0 = bench.build_case(1, 0, elems=(a.elems,) * 3, N=a.N)
+    wl = bench.make_workload(2, 'weak', 1, 0, degree=a.N, elems=a.elems)
+    c, U0 = wl['c'], wl['U0']
     keys = [s.split("=")[0] for s in a.sweep]
     vals = [s.split("=")[1].split(",") for s in a.sweep]
     rows = []

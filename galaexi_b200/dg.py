@@ -224,6 +224,12 @@ class DGSolver:
         self.shape_U = (m.nElems, n, n, n, 5)
         self.shape_grad = (m.nElems, n, n, n, 4)
 
+    def _need_global(self, who: str, what: str, value):
+        """The device sums are reduced over all ranks: the normalising volume / surface has to be the global one as well."""
+        if value is None and self.case.mesh.nProcs > 1:
+            raise DGError(f"{who}: with {self.case.mesh.nProcs} ranks the global {what} has to be given ({what}=...); "
+                          f"this rank's local {what} would scale the rank-reduced sums wrongly")
+
     # ---- error mapping: non-zero return -> Abort ---------------------------------------------------------
     def _ck(self, rc):
         if rc:
@@ -290,6 +296,7 @@ class DGSolver:
         """The 15 TGVAnalysis columns (testcase/taylorgreenvortex/testcase.f90:283-515), integrated on the device.
         Vol: global volume (all ranks); defaults to this rank's volume (single-rank runs)."""
         from .host_standin import analyze as an
+        self._need_global("AnalyzeTestcase", "Vol", Vol)
         key = (NAnalyze,)
         if getattr(self, "_an_key", None) != key:
             NA, V, wA = an.init_analyze_basis(self.case.N, self.case.node_type, NAnalyze)
@@ -315,6 +322,7 @@ class DGSolver:
     def CalcForcing(self, Vol: float | None = None) -> float:
         """CalcForcing of the channel testcase (testcase/channel/testcase.f90:241-271): the bulk velocity."""
         from .host_standin import analyze as an
+        self._need_global("CalcForcing", "Vol", Vol)
         w = np.ascontiguousarray(self.case.basis.wGP, dtype=np.float64)
         b = C.c_double()
         self._ck(self.lib.dgx_calc_bulk_velocity(self.h, w.ctypes.data_as(_dp), float(an.volume(self.case) if Vol is None else Vol),
@@ -343,6 +351,7 @@ class DGSolver:
         """CalcWallVelocity(maxV,minV,meanV) (analyze_equation.f90:435-499); Surf(nBCs): global surface per boundary condition
         (default: integrated from this rank's SurfElem, i.e. single-rank)."""
         from .host_standin import analyze as an
+        self._need_global("CalcWallVelocity", "Surf", Surf)
         m = self.case.mesh
         nBCs = int(m.BoundaryType.shape[0])
         w = np.ascontiguousarray(self.case.basis.wGP, dtype=np.float64)

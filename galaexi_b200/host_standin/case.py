@@ -54,6 +54,13 @@ class Case:
     IniExactFunc: int = 0                            # selects the source term of CalcSource (exactfunc.f90:665-926): 4 or 0
     AdvVel: tuple = (0.0, 0.0, 0.0)
     exact_mm: bool = False                           # FLEXI_EXACT_MASSMATRIX (GL nodes, exact mass matrix): see op_node_type
+    # overintegration of JU_t (dg/overintegration.f90:92-165): 0 none, 1 cut-off filter, 2 conservative cut-off
+    OverintegrationType: int = 0
+    NUnder: int = -1
+    OverintegrationMat: np.ndarray = None            # (N+1,N+1), type 1
+    Vdm_N_NUnder: np.ndarray = None                  # (NUnder+1,N+1), type 2
+    Vdm_NUnder_N: np.ndarray = None                  # (N+1,NUnder+1), type 2
+    sJNUnder: np.ndarray = None                      # [e,kU,jU,iU], type 2
 
     @property
     def op_node_type(self) -> int:
@@ -80,7 +87,8 @@ def build_case(hopr: dict, N: int, node_type: str = bs.NODETYPE_GL, split: str |
                lifting: str = "br1", etaBR2: float = 2.0, etaBR2_wall: float = -1.0,
                FilterType: int | str = 0, NFilter: int | None = None, HestFilterParam=(36.0, 12.0, 1.0),
                IniExactFunc: int = 0, AdvVel=(0.0, 0.0, 0.0), doWeakLifting: bool = False,
-               doConservativeLifting: bool = False, exact_mm: bool = False) -> Case:
+               doConservativeLifting: bool = False, exact_mm: bool = False,
+               OverintegrationType: int | str = 0, NUnder: int | None = None) -> Case:
     eos = eos or eq.Eos()
     node_type = node_type.upper()
     split_id = SPLIT_IDS[split.upper() if isinstance(split, str) else split]
@@ -102,7 +110,31 @@ def build_case(hopr: dict, N: int, node_type: str = bs.NODETYPE_GL, split: str |
     maps = mp.build_mappings(N)
     refprim = eq.init_bc_refstates(eq.refstate_prim(refstates, eos), mesh.BoundaryType)
     bcs = eq.bc_sides(mesh)
-    tdisc = td.set_timedisc(timedisc, N, node_type, CFLScale, DFLScale, exact_mm=exact_mm)
+    # overintegration.f90:92-165 InitOverintegration
+    ot = {"none": 0, "cutoff": 1, "conscutoff": 2}.get(str(OverintegrationType).lower(), OverintegrationType)
+    ot = int(ot)
+    if ot not in (0, 1, 2):
+        raise ValueError("Unknown OverintegrationType!")
+    nunder, omat, vdn, vup, sjn = N, None, None, None, None
+    if ot > 0:
+        if NUnder is None:
+            raise ValueError("NUnder needed for OverintegrationType cutoff / conscutoff")
+        nunder = int(NUnder)
+    if ot == 1:
+        omat = fl.filter_matrix(N, node_type, "cutoff", nunder)     # Vdm_Leg * diag(1 up to NUnder) * sVdm_Leg (:120-131)
+    if ot == 2:
+        if nunder < N:
+            vdn = bs.get_vandermonde(N, node_type, nunder, node_type, modal=True)
+            vup = bs.get_vandermonde(nunder, node_type, N, node_type, modal=True)
+            djr = mt.det_jac_ref(mesh.NodeCoords, mesh.NGeo, node_type)          # on NGeoRef = 3 NGeo
+            v3 = bs.get_vandermonde(3 * mesh.NGeo, node_type, nunder, node_type, modal=True)
+            sjn = 1.0 / mt.change_basis_volume(v3, djr[..., None])[..., 0]
+        else:
+            ot, nunder = 0, N      # "Overintegration is disabled for NUnder >= N" (:158-160)
+    # timedisc_func.f90:171-173: NEff = MIN(PP_N,NFilter,NUnder), FilterType > 2 has no time step effect
+    ftype = {"none": 0, "cutoff": 1, "modal": 2, "laf": 3}.get(str(FilterType).lower(), FilterType)
+    neff = min(N, nunder, int(NFilter) if (NFilter is not None and int(ftype) in (1, 2)) else N)
+    tdisc = td.set_timedisc(timedisc, N, node_type, CFLScale, DFLScale, overintegration=ot > 0, exact_mm=exact_mm, NEff=neff)
     lift_id = {"br1": 1, "br2": 2}[lifting.lower()]
     if etaBR2_wall == -1.0:
         etaBR2_wall = etaBR2   # lifting.f90:158-159
@@ -110,4 +142,4 @@ def build_case(hopr: dict, N: int, node_type: str = bs.NODETYPE_GL, split: str |
                 lift_id, float(etaBR2), float(etaBR2_wall), mo.init_mortar(N, node_type),
                 None if str(FilterType).lower() in ("0", "none") else fl.filter_matrix(N, node_type, FilterType, NFilter, HestFilterParam),
                 None, None, bool(doWeakLifting), bool(doConservativeLifting) and not bool(doWeakLifting),
-                int(IniExactFunc), tuple(float(v) for v in AdvVel), bool(exact_mm))
+                int(IniExactFunc), tuple(float(v) for v in AdvVel), bool(exact_mm), ot, nunder, omat, vdn, vup, sjn)

@@ -43,6 +43,24 @@ class H5File:
         self.objects = self._read_group(self.root_msgs)
         self._cache: dict[str, list] = {}
 
+    def close(self):
+        """Release the mapping (idempotent)."""
+        buf, self.buf = getattr(self, "buf", None), b""
+        if isinstance(buf, mmap.mmap):
+            buf.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     # ------------------------------------------------------------------ low level
     def _find_base(self) -> int:
         off = 0

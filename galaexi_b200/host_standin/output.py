@@ -28,13 +28,45 @@ def format_e23(x: float) -> str:
     return ("-" + body) if neg else ("0" + body)
 
 
-def init_output_to_file(path: str, var_names, last_line_time: float | None = None) -> str:
-    """InitOutputToFile: create ``path``.csv with the header unless it exists already (a restart appends)."""
+def init_output_to_file(path: str, var_names, RestartTime: float = 0.0):
+    """InitOutputToFile (output/output.f90:637-760): create ``path``.csv with the header, or -- when the file exists and the run
+    is a restart (RestartTime >= 0) -- resume it: the records from the first one with Time >= RestartTime on are cut off, so
+    that the restarted run does not leave duplicate or overlapping time rows. Like the reference, the search starts behind
+    the first record (its header loop reads two lines); a file without a record at or after RestartTime is appended to; a file
+    too short to hold a record is rewritten. Returns (file name, lastLine): lastLine = the values of the record the file was
+    cut at (the reference's optional argument), or None."""
     fn = path if path.endswith(".csv") else path + ".csv"
-    if not os.path.exists(fn):
+    exists = os.path.exists(fn) and RestartTime >= 0.0      # RestartTime = 0: a fresh run keeps the header only
+    last = None
+    if exists:
+        with open(fn, "r") as f:
+            lines = f.readlines()
+        if len(lines) < 2:
+            exists = False                      # "file is broken, rewrite"
+        else:
+            keep, t, found = 2, 0.0, True       # header + first record are behind the read position
+            while t < RestartTime:
+                if keep >= len(lines):
+                    found = False               # end of file: "failed. Appending data to end of file."
+                    break
+                try:
+                    t = float(lines[keep].split(",")[0])
+                except ValueError:
+                    found = False
+                    break
+                keep += 1
+            if found:
+                cut = keep - 1                  # BACKSPACE + ENDFILE: the record just read goes, with everything behind it
+                try:
+                    last = [float(v) for v in lines[cut].split(",")]
+                except ValueError:
+                    last = None
+                with open(fn, "w") as f:
+                    f.writelines(lines[:cut])
+    if not exists:
         with open(fn, "w") as f:
             f.write("Time," + ",".join(var_names) + "\n")
-    return fn
+    return fn, last
 
 
 def output_to_file(path: str, times, rows):

@@ -159,7 +159,8 @@ def read_baseflow(path: str, N: int, node_type: str, *, offsetElem: int = 0, nEl
     if nGlobalElems is not None and info["nGlobalElems"] != nGlobalElems:
         raise RuntimeError(f"Baseflow file does not match solution. Elements,nVar {info['nGlobalElems']} {info['nVar']}")
     nE = info["nGlobalElems"] - offsetElem if nElems is None else nElems
-    U = h5lite.H5File(path).dataset_rows("DG_Solution", offsetElem, nE)[..., :nVar]
+    with h5lite.H5File(path) as f:
+        U = np.array(f.dataset_rows("DG_Solution", offsetElem, nE)[..., :nVar])
     if info["N"] == N and info["NodeType"] == node_type:
         return np.ascontiguousarray(U)
     return change_basis_volume(bs.get_vandermonde(info["N"], info["NodeType"], N, node_type, modal=True), U)
@@ -175,10 +176,12 @@ def mark_write_successful(w: h5write.H5Writer, path: str, data_start: int, now: 
 
 def read_state_attrs(path: str) -> dict:
     """What InitRestart reads: N_Restart, NodeType_Restart, RestartTime, nVar_Restart, nElems_Restart."""
-    f = h5lite.H5File(path)
-    a = f.attrs()
-    shape = f.dataset_shape("DG_Solution")
-    return dict(N=int(a["N"][0]), NodeType=a["NodeType"][0].decode().strip(), Time=float(a["Time"][0]),
+    with h5lite.H5File(path) as f:
+        a = {k: np.array(v) for k, v in f.attrs().items()}
+        shape = f.dataset_shape("DG_Solution")
+    # N_Restart is the degree of the DATA (hdf5_input.f90:386 GetDataProps: N_HDF5 = Dims(2)-1); the root attribute 'N' is always
+    # the computation degree PP_N, also when the state was written on NOut /= N
+    return dict(N=int(shape[1]) - 1, NComputation=int(a["N"][0]), NodeType=a["NodeType"][0].decode().strip(), Time=float(a["Time"][0]),
                 MeshFile=a["MeshFile"][0].decode().strip(), Project_Name=a["Project_Name"][0].decode().strip(),
                 NextFile=a["NextFile"][0].decode().strip() if "NextFile" in a else "",
                 complete="TIME" in a, nVar=shape[-1], nGlobalElems=shape[0], shape=shape)
@@ -197,7 +200,8 @@ def restart(path: str, N: int, node_type: str, *, sJ: np.ndarray | None = None, 
     if info["nVar"] < nVar:
         raise RuntimeError("Provided file for restart has not all conservative/primitive variables available!")
     nE = shape[0] - offsetElem if nElems is None else nElems
-    U_local = h5lite.H5File(path).dataset_rows("DG_Solution", offsetElem, nE)[..., :nVar]
+    with h5lite.H5File(path) as f:
+        U_local = np.array(f.dataset_rows("DG_Solution", offsetElem, nE)[..., :nVar])
     t = 0.0 if ResetTime else info["Time"]
     interpolate = NR != N or ntR != node_type
     if not interpolate:

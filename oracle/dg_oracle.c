@@ -101,6 +101,12 @@ typedef struct {
     /* sponge (sponge/sponge.f90:529-588): SpongeMat(0:N,0:N,0:N,nElems) = damping sigma / sJ, zero outside the sponge zone,
      * or NULL; the base flow lives in the oracle (array "SpBaseFlow") */
     const double *SpongeMat;
+    /* overintegration of JU_t, step 14 of the RHS (dg/overintegration.f90:179-340; host FLEXI: GALAEXI stops in InitOverintegration,
+     * :108-114): 0 none; 1 cut-off: Filter(Ut, OverintegrationMat) then ApplyJacobian; 2 conservative cut-off (FilterConservative):
+     * JU_t projected to NUnder with Vdm_N_NUnder(0:NUnder,0:N), times sJNUnder(0:NUnder,0:NUnder,0:NUnder,nElems), interpolated
+     * back with Vdm_NUnder_N(0:N,0:NUnder); matrices in Fortran layout */
+    int OverintegrationType, NUnder;
+    const double *OverintegrationMat, *Vdm_N_NUnder, *Vdm_NUnder_N, *sJNUnder;
 } dgo_config;
 
 typedef struct {
@@ -1353,32 +1359,89 @@ static void calc_source(dgo *s, double t)
 /* ------------------------------------------------------------------------------------------------ */
 /* filter/filter.f90:272-306 Filter -> interpolation/changeBasis.t90:287-360 ChangeBasis3D_GPU with X_Out absent: U is
  * replaced by FilterMat applied along xi, then eta, then zeta */
-static void filter_u(dgo *s)
+static void filter_array(dgo *s, double *A, const double *Mat)
 {
     const dgo_config *c = &s->c;
     const int n = s->n;
-    if (!c->FilterMat) return;
 #pragma omp parallel for schedule(static)
     for (int e = 0; e < c->nElems; e++) {
-        double b1[NV * 1000], b2[NV * 1000];
+        double b1[NV * 4096], b2[NV * 4096]; /* n <= 16 */
         for (int k = 0; k < n; k++) for (int j = 0; j < n; j++) for (int i = 0; i < n; i++)
             for (int v = 0; v < NV; v++) {
                 double a = 0.;
-                for (int l = 0; l < n; l++) a = a + c->FilterMat[i + n * l] * s->U[IDX_VOL(s, NV, v, l, j, k, e)];
+                for (int l = 0; l < n; l++) a = a + Mat[i + n * l] * A[IDX_VOL(s, NV, v, l, j, k, e)];
                 b1[v + NV * (i + n * (j + n * k))] = a;
             }
         for (int k = 0; k < n; k++) for (int j = 0; j < n; j++) for (int i = 0; i < n; i++)
             for (int v = 0; v < NV; v++) {
                 double a = 0.;
-                for (int l = 0; l < n; l++) a = a + c->FilterMat[j + n * l] * b1[v + NV * (i + n * (l + n * k))];
+                for (int l = 0; l < n; l++) a = a + Mat[j + n * l] * b1[v + NV * (i + n * (l + n * k))];
                 b2[v + NV * (i + n * (j + n * k))] = a;
             }
         for (int k = 0; k < n; k++) for (int j = 0; j < n; j++) for (int i = 0; i < n; i++)
             for (int v = 0; v < NV; v++) {
                 double a = 0.;
-                for (int l = 0; l < n; l++) a = a + c->FilterMat[k + n * l] * b2[v + NV * (i + n * (j + n * l))];
-                s->U[IDX_VOL(s, NV, v, i, j, k, e)] = a;
+                for (int l = 0; l < n; l++) a = a + Mat[k + n * l] * b2[v + NV * (i + n * (j + n * l))];
+                A[IDX_VOL(s, NV, v, i, j, k, e)] = a;
             }
+    }
+}
+static void filter_u(dgo *s)
+{
+    if (s->c.FilterMat) filter_array(s, s->U, s->c.FilterMat);
+}
+
+/* dg/overintegration.f90:212-339 FilterConservative (3-D branch): JU_t on N -> NUnder (xi, eta, zeta in this order, each sum
+ * started with l = 0), times sJNUnder, back to N (xi, eta, zeta); the zeta passes accumulate into a zeroed array like the
+ * reference (VNullify + "U = U + ..."). Input JU_t, output U_t on N. */
+static void filter_conservative(dgo *s, double *A)
+{
+    const dgo_config *c = &s->c;
+    const int n = s->n, nu = c->NUnder + 1;
+    const double *VD = c->Vdm_N_NUnder;  /* (0:NUnder,0:N): VD[iU + nu*i] */
+    const double *VU = c->Vdm_NUnder_N;  /* (0:N,0:NUnder): VU[i + n*iU] */
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < c->nElems; e++) {
+        double *B1 = (double *)malloc(sizeof(double) * NV * (size_t)nu * n * n);    /* (nVar,0:NUnder,0:N,0:N) */
+        double *B2 = (double *)malloc(sizeof(double) * NV * (size_t)nu * nu * n);   /* (nVar,0:NUnder,0:NUnder,0:N) */
+        double *UL = (double *)calloc((size_t)NV * nu * nu * nu, sizeof(double));   /* U_loc (nVar,0:NUnder,0:NUnder,0:NUnder) */
+        double *B3 = (double *)malloc(sizeof(double) * NV * (size_t)n * nu * nu);   /* (nVar,0:N,0:NUnder,0:NUnder) */
+        double *B4 = (double *)malloc(sizeof(double) * NV * (size_t)n * n * nu);    /* (nVar,0:N,0:N,0:NUnder) */
+        for (int k = 0; k < n; k++) for (int j = 0; j < n; j++)
+            for (int iU = 0; iU < nu; iU++) for (int v = 0; v < NV; v++) {
+                double a = VD[iU + nu * 0] * A[IDX_VOL(s, NV, v, 0, j, k, e)];
+                for (int i = 1; i < n; i++) a = a + VD[iU + nu * i] * A[IDX_VOL(s, NV, v, i, j, k, e)];
+                B1[v + NV * (iU + nu * (j + n * k))] = a;
+            }
+        for (int k = 0; k < n; k++)
+            for (int jU = 0; jU < nu; jU++) for (int iU = 0; iU < nu; iU++) for (int v = 0; v < NV; v++) {
+                double a = VD[jU + nu * 0] * B1[v + NV * (iU + nu * (0 + n * k))];
+                for (int j = 1; j < n; j++) a = a + VD[jU + nu * j] * B1[v + NV * (iU + nu * (j + n * k))];
+                B2[v + NV * (iU + nu * (jU + nu * k))] = a;
+            }
+        for (int k = 0; k < n; k++)
+            for (int kU = 0; kU < nu; kU++) for (int jU = 0; jU < nu; jU++) for (int iU = 0; iU < nu; iU++) for (int v = 0; v < NV; v++)
+                UL[v + NV * (iU + nu * (jU + nu * kU))] = UL[v + NV * (iU + nu * (jU + nu * kU))] + VD[kU + nu * k] * B2[v + NV * (iU + nu * (jU + nu * k))];
+        for (int kU = 0; kU < nu; kU++) for (int jU = 0; jU < nu; jU++) for (int iU = 0; iU < nu; iU++) for (int v = 0; v < NV; v++)
+            UL[v + NV * (iU + nu * (jU + nu * kU))] = UL[v + NV * (iU + nu * (jU + nu * kU))] * c->sJNUnder[iU + nu * (jU + nu * (kU + (size_t)nu * e))];
+        for (int kU = 0; kU < nu; kU++) for (int jU = 0; jU < nu; jU++)
+            for (int i = 0; i < n; i++) for (int v = 0; v < NV; v++) {
+                double a = VU[i + n * 0] * UL[v + NV * (0 + nu * (jU + nu * kU))];
+                for (int iU = 1; iU < nu; iU++) a = a + VU[i + n * iU] * UL[v + NV * (iU + nu * (jU + nu * kU))];
+                B3[v + NV * (i + n * (jU + nu * kU))] = a;
+            }
+        for (int kU = 0; kU < nu; kU++)
+            for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) for (int v = 0; v < NV; v++) {
+                double a = VU[j + n * 0] * B3[v + NV * (i + n * (0 + nu * kU))];
+                for (int jU = 1; jU < nu; jU++) a = a + VU[j + n * jU] * B3[v + NV * (i + n * (jU + nu * kU))];
+                B4[v + NV * (i + n * (j + n * kU))] = a;
+            }
+        for (int k = 0; k < n; k++) for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) for (int v = 0; v < NV; v++) {
+            double a = 0.;
+            for (int kU = 0; kU < nu; kU++) a = a + VU[k + n * kU] * B4[v + NV * (i + n * (j + n * kU))];
+            A[IDX_VOL(s, NV, v, i, j, k, e)] = a;
+        }
+        free(B1); free(B2); free(UL); free(B3); free(B4);
     }
 }
 
@@ -1421,6 +1484,13 @@ int dgo_time_derivative(dgo *s, double t)
             s->Ut[NV * d + MOM1] = s->Ut[NV * d + MOM1] - c->dpdx / c->sJ[d];
             s->Ut[NV * d + ENER] = s->Ut[NV * d + ENER] - c->dpdx / c->sJ[d] * c->BulkVel;
         }
+    }
+    /* 14. overintegration.f90:179-201 Overintegration(Ut): cut-off filter on JU_t, or the conservative variant which applies
+     * the Jacobian (of NUnder) itself; otherwise applyjacobian.t90:196 */
+    if (c->OverintegrationType == 1) filter_array(s, s->Ut, c->OverintegrationMat);
+    if (c->OverintegrationType == 2) {
+        filter_conservative(s, s->Ut);
+        return err;
     }
 #pragma omp parallel for schedule(static)
     for (size_t d = 0; d < s->nDOF; d++)

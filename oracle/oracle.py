@@ -45,7 +45,9 @@ class _Prec:
                        [("iniExactFunc", C.c_int), ("AdvVel", self.real * 3), ("Elem_xGP", rp)] + \
                        [("tcSource", C.c_int), ("dpdx", self.real), ("BulkVel", self.real)] + \
                        [("doWeakLifting", C.c_int), ("doConservativeLifting", C.c_int)] + \
-                       [("SpongeMat", rp)]
+                       [("SpongeMat", rp)] + \
+                       [("OverintegrationType", C.c_int), ("NUnder", C.c_int)] + \
+                       [(k, rp) for k in ("OverintegrationMat", "Vdm_N_NUnder", "Vdm_NUnder_N", "sJNUnder")]
         self.Config = Config
         self._lib = None
 
@@ -171,6 +173,18 @@ class Oracle:
         if getattr(case, "SpongeMat", None) is not None:
             self._keep["SpongeMat"] = f64(case.SpongeMat)
             c.SpongeMat = _d(self._keep["SpongeMat"])
+        ot = int(getattr(case, "OverintegrationType", 0))
+        if ot:   # dg/overintegration.f90: Fortran M(a,b) at [a + na*b] == C array M.T
+            c.OverintegrationType, c.NUnder = ot, int(case.NUnder)
+            if ot == 1:
+                self._keep["OverintegrationMat"] = f64(np.asarray(case.OverintegrationMat).T)
+                c.OverintegrationMat = _d(self._keep["OverintegrationMat"])
+            else:
+                self._keep["Vdm_N_NUnder"] = f64(np.asarray(case.Vdm_N_NUnder).T)
+                self._keep["Vdm_NUnder_N"] = f64(np.asarray(case.Vdm_NUnder_N).T)
+                self._keep["sJNUnder"] = f64(case.sJNUnder)
+                for k in ("Vdm_N_NUnder", "Vdm_NUnder_N", "sJNUnder"):
+                    setattr(c, k, _d(self._keep[k]))
         c.doWeakLifting = int(getattr(case, "doWeakLifting", False))
         c.doConservativeLifting = int(getattr(case, "doConservativeLifting", False))
         FilterMat = getattr(case, "FilterMat", None)

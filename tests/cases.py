@@ -239,3 +239,16 @@ def duct_case(inflow, outflow, wall, N=3, parabolic=True, node_type=bs.NODETYPE_
 
 def rel_l2(a, b):
     return float(np.sqrt(np.sum((a - b) ** 2)) / max(np.sqrt(np.sum(b ** 2)), 1e-300))
+
+
+def tgv_oint_case(nProcs=1, myRank=0, N=11, NUnder=7, OverintegrationType="cutoff", node_type=bs.NODETYPE_G, **kw):
+    """regressioncheck/checks/tgv/oInt: N=11, weak form (FLEXI_SPLIT_DG=ON is excluded), RoeEntropyFix, BR1, 4^3 periodic elements,
+    OverintegrationType=1 (cut-off filter on JU_t) with NUnder=7, CFLscale = DFLscale = 0.9."""
+    h = load_mesh("tgv_oint_mesh.npz")
+    eos = eq.Eos(**TGV_EOS)
+    args = dict(split=None, riemann="RoeEntropyFix", parabolic=True, eos=eos, refstates=TGV_REF, CFLScale=0.9, DFLScale=0.9,
+                useCurveds=False, nProcs=nProcs, myRank=myRank, OverintegrationType=OverintegrationType, NUnder=NUnder)
+    args.update(kw)
+    c = cs.build_case(h, N, node_type, **args)
+    U0 = eq.ini_tgv(c.geo["Elem_xGP"], eos, mach=0.1, ini_const_dens=True)
+    return c, U0

@@ -221,3 +221,53 @@ def test_tgv_analysis_oracle_reproduces_reference_csv_columns():
         if it in (9, 19):
             check(rows[1 if it == 9 else 2])
     o.close()
+
+
+def test_tgv_oint_csv_pins_the_overintegration_step():
+    """tgv/oInt: N=11 Gauss, weak form, RoeEntropyFix, BR1, OverintegrationType=1 (modal cut-off filter on JU_t before the Jacobian,
+    dg/overintegration.f90:120-131,179-201) with NUnder=7, whose CFL scaling uses NEff = MIN(N,NFilter,NUnder)
+    (timedisc_func.f90:171-173). GALAEXI's GPU build stops in InitOverintegration (:108-114); its reference CSV (written by the
+    host code) still pins the restatement: time stamps of rows 2-4 (30 adaptive steps) within 1e-7 relative, kinetic energy
+    1e-10, every column within 1e-6 of its magnitude over the file (reference criterion: 1e-4 relative, analyze.ini)."""
+    from galaexi_b200.host_standin import analyze as an
+    from oracle.analyze_tgv import analyze_tgv
+    c, U0 = cases.tgv_oint_case()
+    assert c.OverintegrationType == 1 and c.NUnder == 7 and c.N == 11
+    rows = np.load(os.path.join(cases.GOLD, "tgv_oint_csv.npz"))["rows"]
+    scale = np.abs(rows[:, 1:]).max(axis=0)
+    NA, V, wA = an.init_analyze_basis(c.N, c.node_type, 10)
+    Vol = an.volume(c)
+    o = Oracle(c)
+    o.set_state(U0)
+    o.time_derivative(0.0)
+
+    def check(r, t):
+        d = analyze_tgv(c, o.array("U"), o.array("gradUx"), o.array("gradUy"), o.array("gradUz"), V, wA, Vol)
+        assert abs(t - r[0]) <= 1e-7 * max(r[0], 1e-300) or r[0] == 0.0, (t, r[0])
+        assert abs(d[2] - r[3]) <= 1e-10 * r[3]
+        assert np.all(np.abs(d - r[1:]) <= 1e-6 * scale), (d, r[1:])
+
+    check(rows[0], 0.0)
+    t = 0.0
+    for it in range(1, 31):
+        dt = o.calc_timestep()[0]
+        o.rk_step(t, dt)
+        t += dt
+        if it % 10 == 0:
+            check(rows[it // 10], t)
+    # the step is what the golden pins: without it, at the same NEff time step, the unfiltered N=11 scheme does not even stay
+    # finite, let alone reproduce the second row
+    c2, _ = cases.tgv_oint_case()
+    c2.OverintegrationType = 0
+    o2 = Oracle(c2)
+    o2.set_state(U0)
+    t = 0.0
+    for it in range(10):
+        dt = o2.calc_timestep()[0]
+        o2.rk_step(t, dt)
+        t += dt
+    o2.time_derivative(t)
+    d2 = analyze_tgv(c2, o2.array("U"), o2.array("gradUx"), o2.array("gradUy"), o2.array("gradUz"), V, wA, Vol)
+    assert (not np.all(np.isfinite(d2))) or np.max(np.abs(d2 - rows[1][1:]) / scale) > 1e-5   # (measured: unstable, NaN)
+    o.close()
+    o2.close()

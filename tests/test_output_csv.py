@@ -30,10 +30,26 @@ def test_reference_csv_files_are_reproduced_byte_for_byte(tmp_path, rel):
     names = lines[0].split(",")[1:]
     conv = lambda s: float(s.replace("E+0", "E+").replace("E-0", "E-"))
     data = np.array([[conv(x) for x in ln.split(",")] for ln in lines[1:]])
-    fn = output.init_output_to_file(str(tmp_path / "out"), names)
+    fn, last = output.init_output_to_file(str(tmp_path / "out"), names)
+    assert last is None
     output.output_to_file(fn, data[:, 0], data[:, 1:])
-    output.init_output_to_file(str(tmp_path / "out"), names)                      # existing file: header is not written again
     assert open(fn).read().splitlines() == lines
+    # a restart at the time of record k resumes the file: that record and everything behind it is cut off and re-written by
+    # the restarted run (output.f90:690-729: search, BACKSPACE, ENDFILE); no duplicate time rows
+    k = len(data) // 2
+    fn2, last = output.init_output_to_file(str(tmp_path / "out"), names, RestartTime=float(data[k, 0]))
+    assert fn2 == fn and np.allclose(last, data[k]) and open(fn).read().splitlines() == lines[:1 + k]
+    output.output_to_file(fn, data[k:, 0], data[k:, 1:])
+    assert open(fn).read().splitlines() == lines
+    # a restart time behind the last record: nothing to cut, records are appended
+    output.init_output_to_file(str(tmp_path / "out"), names, RestartTime=float(data[-1, 0]) + 1.0)
+    assert open(fn).read().splitlines() == lines
+    # a fresh run (RestartTime = 0) keeps only the header of an existing file; RestartTime < 0 writes a new file
+    output.init_output_to_file(str(tmp_path / "out"), names)
+    assert open(fn).read().splitlines() == lines[:1]
+    output.output_to_file(fn, data[:3, 0], data[:3, 1:])
+    output.init_output_to_file(str(tmp_path / "out"), names, RestartTime=-1.0)
+    assert open(fn).read().splitlines() == lines[:1]
     with pytest.raises(RuntimeError, match="cannot open"):
         output.output_to_file(str(tmp_path / "missing"), [0.0], [[1.0]])
 

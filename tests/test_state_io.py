@@ -281,9 +281,15 @@ def test_write_state_nout_projection(tmp_path):
     sJ = np.full(U.shape[:-1], 8.0)
     p = state_io.write_state(U, 4, bs.NODETYPE_G, "no", "m.h5", 0.0, 1.0, out_dir=str(tmp_path), sJ=sJ, NOut=2)
     info = state_io.read_state_attrs(p)
-    assert info["shape"] == (2, 3, 3, 3, 5) and info["N"] == 4      # attribute N is the computation degree, the data is on NOut
+    # attribute N is the computation degree, the data is on NOut: N_Restart comes from the data extent (hdf5_input.f90:386)
+    assert info["shape"] == (2, 3, 3, 3, 5) and info["NComputation"] == 4 and info["N"] == 2
     _, X2 = _cart_coords(2, 2, bs.NODETYPE_G)
     assert np.abs(h5lite.read_state(p)["DG_Solution"] - _poly_state(X2, 2)).max() < 1e-13
+    # ... so a restart from this file works on NOut directly and is interpolated to the computation degree (degree-2 data: exact)
+    U2, t2 = state_io.restart(p, 2, bs.NODETYPE_G)
+    assert t2 == 0.0 and np.abs(U2 - _poly_state(X2, 2)).max() < 1e-13
+    U4, _ = state_io.restart(p, 4, bs.NODETYPE_G)
+    assert U4.shape == U.shape and np.abs(U4 - U).max() < 1e-12
     with pytest.raises(ValueError):
         state_io.write_state(U, 4, bs.NODETYPE_G, "no", "m.h5", 0.0, 1.0, out_dir=str(tmp_path), NOut=2)
 

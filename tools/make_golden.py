@@ -87,6 +87,11 @@ def main():
     csv = np.loadtxt(os.path.join(REF, "regressioncheck/checks/tgv/split/TGV_Re1600_Split_TGVAnalysis_Reference.csv"),
                      delimiter=",", skiprows=1, converters=lambda s: float(s.replace("E+0", "E+").replace("E-0", "E-")))
     np.savez_compressed(os.path.join(OUT, "tgv_split_csv.npz"), rows=csv)   # all 555 analyze rows (t = 0 ... 13)
+    # tgv/oInt: N=11, OverintegrationType=1 (cut-off filter on JU_t), NUnder=7, 4^3 elements: pins the overintegration step
+    mesh_npz("regressioncheck/checks/tgv/oInt/CART_HEX_PERIODIC_004_mesh.h5", "tgv_oint_mesh.npz")
+    csv = np.loadtxt(os.path.join(REF, "regressioncheck/checks/tgv/oInt/TGV_Re1600_OInt_TGVAnalysis_Reference.csv"),
+                     delimiter=",", skiprows=1, converters=lambda s: float(s.replace("E+0", "E+").replace("E-0", "E-")))
+    np.savez_compressed(os.path.join(OUT, "tgv_oint_csv.npz"), rows=csv)    # all 437 analyze rows (t = 0 ... 13)
     st = h5lite.read_state(os.path.join(REF, "regressioncheck/checks/parabolic/cavity_3D/reggie_cavity_Re100_State_0000001.000000000.h5"))
     np.savez_compressed(os.path.join(OUT, "cavity3d_state.npz"), DG_Solution=st["DG_Solution"], Time=st["attrs"]["Time"])
     st = h5lite.read_state(os.path.join(REF, "regressioncheck/checks/naca/3D/NACA0012_Re5000_AoA8_3D_Referenz_0000010.000000000.h5"))

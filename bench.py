@@ -499,6 +499,7 @@ def ncu_child(args):
     wl = make_workload(args.config, args.scaling, 1, 0, degree=args.degree, elems=args.elems, curved=args.curved)
     s = dg.DGSolver(wl["c"], device=0)
     s.set_state(wl["U0"])
+    s.set_keep_gradients(False)      # like the steps of the timed region: no analysis follows, the volume gradients are not stored
     dt0, _ = s.CalcTimeStep()
     s.TimeStepByLSERKW2(0.0, dt0)
     s.sync()
@@ -675,4 +676,13 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except SystemExit:
+        raise
+    except BaseException:      # a failing rank must not leave the other ranks (and the launcher) waiting in a collective
+        import traceback
+        traceback.print_exc()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(1)

@@ -123,6 +123,9 @@ struct dgx_handle {
     int graphCur = -1, graphKey = -1;
     long long graphLaunches = 0;
     int graphFailed = 0;
+    // events used while capturing: an event recorded inside a stream capture cannot be waited on by eager work afterwards, so the
+    // capture runs on its own set (same order as the eager ones in swap_event_sets)
+    cudaEvent_t evCap[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool warm = false, capturing = false;  // warm: an RK stage has run outside any capture (first-use initialisation done)
     // device memory
     std::vector<void*> allocs;
@@ -315,7 +318,9 @@ int rhs(dgx_handle* h, int mode, double t, double mRKA, double b_dt, StageTimes*
     P.UsNext = h->Uf[h->cur ^ 1][1];
     P.dtDev = o.devDt ? h->dtOut : nullptr;
     P.dtAcc = h->dtOut; P.dtCFL = c.CFLScale; P.dtDFL = c.DFLScale;
-    P.dtFuse = (o.fuseDt && c.parabolic) ? 1 : 0;
+    // CalcTimeStep rides on stage 1's lifting kernel unless there is none (Euler) or the RHS filters U first (dg.f90:331: the
+    // time step belongs to the unfiltered state the step starts from)
+    P.dtFuse = (o.fuseDt && c.parabolic && !h->P.FilterMat) ? 1 : 0;
     if (!o.devDt) P.bulkDev = nullptr;
     const bool multi = c.nRanks > 1 && !h->NbProc.empty();
     // CalcSource (dg.f90:418): the volume kernels store Ut (MODE 0), k_source_rk adds the source and does the stage update
@@ -324,11 +329,25 @@ int rhs(dgx_handle* h, int mode, double t, double mRKA, double b_dt, StageTimes*
         P.rk3 = i == 0 ? 1 : 2;
         P.rk3Delta = h->RKdelta[i]; P.rk3G1 = h->RKg1[i]; P.rk3G2 = h->RKg2[i]; P.rk3G3 = h->RKg3[i];
     }
-    const bool src = P.iniExactFunc == 4 || P.tcSource || P.spMat || P.rk3;
+    // overintegration (step 14): the volume kernels leave Ut without the Jacobian, k_overint adds the sources of step 13 in
+    // reference space, filters and applies the Jacobian; k_source_rk (sources switched off) then does the stage update
+    const bool oint = P.overint != 0;
+    P.noJac = oint ? 1 : 0;
+    // the channel forcing alone does not need the extra pass: the volume kernels add it in their epilogue
+    if (P.tcSource && !(P.iniExactFunc == 4 || P.spMat || P.rk3 || oint)) P.tcSource = 2;
+    const bool src = P.iniExactFunc == 4 || P.tcSource == 1 || P.spMat || P.rk3 || oint;
     const int vmode = src ? 0 : mode;
+    KParams Ps = P;   // parameters of k_source_rk
+    if (oint) { Ps.iniExactFunc = 0; Ps.tcSource = 0; Ps.spMat = nullptr; }
+    auto source_stage = [&](void) -> int {
+        if (oint) { kt->overint(P, t, c.nElems, h->s); if (c.nElems > 0 && check_launch(h, "k_overint")) return 1; }
+        if (mode == 0 && oint) return 0;  // Ut is complete (k_overint has added the sources)
+        kt->source_rk(Ps, mode, t, mRKA, b_dt, c.nElems, h->s);
+        return (c.nElems > 0 && check_launch(h, "k_source_rk")) ? 1 : 0;
+    };
     auto mark = [&](void) { if (st) cudaEventRecord(st->ev[st->nev++], h->s); };
     mark();
-    if (o.fuseDt && !c.parabolic) {  // Euler: no lifting kernel to ride on
+    if (o.fuseDt && !P.dtFuse) {
         kt->timestep(P, c.CFLScale, c.DFLScale, h->dtOut, h->s);
         if (c.nElems && check_launch(h, "k_timestep")) return 1;
         if (dt_finish_on(h, h->s)) return 1;
@@ -403,7 +422,7 @@ int rhs(dgx_handle* h, int mode, double t, double mRKA, double b_dt, StageTimes*
         }
         if (h->nInner) { kt->volsurf(Pi, vmode, mRKA, b_dt, h->nInner, h->s); if (check_launch(h, "k_volsurf(inner)")) return 1; }
         CK(cudaStreamWaitEvent(h->s, h->evBnd, 0));
-        if (src) { kt->source_rk(P, mode, t, mRKA, b_dt, c.nElems, h->s); if (c.nElems > 0 && check_launch(h, "k_source_rk")) return 1; }
+        if (src && source_stage()) return 1;
         if (post && src) {
             CK(cudaEventRecord(h->evNext, h->s));
             CK(cudaStreamWaitEvent(h->cs, h->evNext, 0));
@@ -451,7 +470,7 @@ int rhs(dgx_handle* h, int mode, double t, double mRKA, double b_dt, StageTimes*
         if (mortar && mortar_flux(h, P.Flux, 5, 1)) return 1;
         if (h->nBnd) { kt->volsurf(Pb, vmode, mRKA, b_dt, h->nBnd, h->s); if (check_launch(h, "k_volsurf(bnd)")) return 1; }
     }
-    if (src) { kt->source_rk(P, mode, t, mRKA, b_dt, c.nElems, h->s); if (c.nElems > 0 && check_launch(h, "k_source_rk")) return 1; }
+    if (src && source_stage()) return 1;
     if (mode == 1 && mortar && mortar_u(h, P.UmNext, P.UsNext, 5)) return 1;
     mark();
     if (mode == 1) h->cur ^= 1;
@@ -518,6 +537,7 @@ void dgx_destroy(dgx_handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     if (h->hPinned) cudaFreeHost(h->hPinned);
     if (h->graph) cudaGraphExecDestroy(h->graph);
+    for (cudaEvent_t e : h->evCap) if (e) cudaEventDestroy(e);
     cudaEvent_t evs[] = {h->evFaces, h->evUhalo, h->evGrad, h->evGhalo, h->evT0, h->evT1, h->evSide, h->evBnd, h->evDtPre, h->evDt, h->evNext};
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     if (h->s) cudaStreamDestroy(h->s);
@@ -567,6 +587,7 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
     CK(cudaStreamCreateWithPriority(&h->s2, cudaStreamNonBlocking, hi));
     cudaEvent_t* evs[] = {&h->evFaces, &h->evUhalo, &h->evGrad, &h->evGhalo, &h->evSide, &h->evBnd, &h->evDtPre, &h->evDt, &h->evNext};
     for (cudaEvent_t* e : evs) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (cudaEvent_t& e : h->evCap) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CK(cudaEventCreate(&h->evT0));
     CK(cudaEventCreate(&h->evT1));
     { int r = h->kt->setup(); if (r) return fail(h, "cudaFuncSetAttribute failed: %s", cudaGetErrorString((cudaError_t)r)); }
@@ -656,6 +677,22 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
         if (upload(h, &fm, c.FilterMat, (size_t)n * n)) return 1;
         P.FilterMat = fm;
     }
+    P.overint = 0; P.nUnder = c.N; P.noJac = 0;
+    P.oiMat = P.oiDown = P.oiUp = P.sJNUnder = nullptr;
+    if (c.OverintegrationType < 0 || c.OverintegrationType > 2) return fail(h, "Unknown OverintegrationType!");
+    if (c.OverintegrationType == 1) {
+        if (!c.OverintegrationMat) return fail(h, "OverintegrationType 1 (cut-off) needs OverintegrationMat");
+        double* om;
+        if (upload(h, &om, c.OverintegrationMat, (size_t)n * n)) return 1;
+        P.oiMat = om; P.overint = 1; P.nUnder = c.NUnder;
+    } else if (c.OverintegrationType == 2) {
+        if (c.NUnder < 0 || c.NUnder >= c.N) return fail(h, "conservative cut-off overintegration needs 0 <= NUnder < N (overintegration.f90:139-160)");
+        if (!c.Vdm_N_NUnder || !c.Vdm_NUnder_N || !c.sJNUnder) return fail(h, "OverintegrationType 2 needs Vdm_N_NUnder, Vdm_NUnder_N and sJNUnder");
+        const size_t nu = (size_t)c.NUnder + 1;
+        double *vd, *vu, *sj;
+        if (upload(h, &vd, c.Vdm_N_NUnder, nu * n) || upload(h, &vu, c.Vdm_NUnder_N, nu * n) || upload(h, &sj, c.sJNUnder, nu * nu * nu * c.nElems)) return 1;
+        P.oiDown = vd; P.oiUp = vu; P.sJNUnder = sj; P.overint = 2; P.nUnder = c.NUnder;
+    }
     h->mp = MortarParams{nullptr, nullptr, nullptr, 0};
     if (c.nMortarSides > 0) {
         h->nMortarInner = c.lastMortarInnerSide - c.firstMortarInnerSide + 1;
@@ -732,6 +769,7 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
     h->cfg.Elem_xGP = nullptr;
     h->cfg.SpongeMat = h->cfg.SpBaseFlow = nullptr;
     h->cfg.M_0_1 = h->cfg.M_0_2 = h->cfg.M_1_0 = h->cfg.M_2_0 = nullptr;
+    h->cfg.OverintegrationMat = h->cfg.Vdm_N_NUnder = h->cfg.Vdm_NUnder_N = h->cfg.sJNUnder = nullptr;
     return 0;
 }
 
@@ -877,6 +915,10 @@ int dgx_get_baseflow(dgx_handle* h, double* SpBaseFlow) {
 }
 
 int dgx_set_channel_forcing(dgx_handle* h, int on, double dpdx, double BulkVel) {
+    if (h->graph && ((on ? 1 : 0) != h->P.tcSource || dpdx != h->P.tcDpdx || BulkVel != h->P.tcBulkVel)) {
+        cudaGraphExecDestroy(h->graph);   // the captured kernels carry the old forcing as launch parameters
+        h->graph = nullptr;
+    }
     h->P.tcSource = on ? 1 : 0;
     h->P.tcDpdx = dpdx;
     h->P.tcBulkVel = BulkVel;
@@ -1027,8 +1069,15 @@ int dev_step(dgx_handle* h, bool forcing, bool storeLast, bool postLast) {
 // flips): one launch per 2 x (3 nRKStages + 1) kernels. Multi rank: the capture starts from "U-face halo complete and ordered
 // before stream s" and ends in the same state (the halo the last stage posted is joined into s), which dgx_run_steps
 // establishes before the first replay. Nothing is executed here.
+void swap_event_sets(dgx_handle* h) {
+    cudaEvent_t* evs[9] = {&h->evFaces, &h->evUhalo, &h->evGrad, &h->evGhalo, &h->evSide, &h->evBnd, &h->evDtPre, &h->evDt, &h->evNext};
+    for (int i = 0; i < 9; i++) { cudaEvent_t t = *evs[i]; *evs[i] = h->evCap[i]; h->evCap[i] = t; }
+}
+
 int build_step_graph(dgx_handle* h, bool forcing, int key) {
     if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+    swap_event_sets(h);   // the eager events keep their last recorded state
+    struct Restore { dgx_handle* h; ~Restore() { swap_event_sets(h); } } restore{h};
     const long long l0 = h->launches;
     const int cur0 = h->cur;
     const bool posted0 = h->uHaloPosted, joined0 = h->uHaloJoined;

@@ -63,6 +63,8 @@ struct L {
         if (e != cudaSuccess) return (int)e;
         e = cudaFuncSetAttribute(k_filter<n, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)filter_smem_bytes<n>());
         if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(k_overint<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)overint_smem_bytes<n>());
+        if (e != cudaSuccess) return (int)e;
         if (NT == 2) e = setup_vs2<0>();
         return (int)e;
     }
@@ -116,6 +118,9 @@ struct L {
         if (mode == 0) k_source_rk<n, NT, 0><<<nb, n3, source_smem_bytes<n>(), s>>>(P, t, mRKA, b_dt);
         else k_source_rk<n, NT, 1><<<nb, n3, source_smem_bytes<n>(), s>>>(P, t, mRKA, b_dt);
     }
+    static void overint(const KParams& P, double t, int nb, cudaStream_t s) {
+        if (nb > 0) k_overint<n><<<nb, n3, overint_smem_bytes<n>(), s>>>(P, t);
+    }
     static void bulkvel(const KParams& P, const double* wGP, double* partials, cudaStream_t s) {
         if (P.nElems > 0) k_bulkvel<n><<<P.nElems, timestep_threads<n>(), 0, s>>>(P, wGP, partials);
     }
@@ -132,9 +137,9 @@ struct L {
     }
 };
 const KernelTable tabG = {L<1>::setup, L<1>::prolong, L<1>::lifting, L<1>::sideflux, L<1>::volsurf, L<1>::timestep,
-                          L<1>::umortar, L<1>::fluxmortar, L<1>::mortar_liftflux, L<1>::filter, L<1>::source_rk, L<1>::bulkvel, L<1>::tgv_analyze};
+                          L<1>::umortar, L<1>::fluxmortar, L<1>::mortar_liftflux, L<1>::filter, L<1>::source_rk, L<1>::overint, L<1>::bulkvel, L<1>::tgv_analyze};
 const KernelTable tabGL = {L<2>::setup, L<2>::prolong, L<2>::lifting, L<2>::sideflux, L<2>::volsurf, L<2>::timestep,
-                           L<2>::umortar, L<2>::fluxmortar, L<2>::mortar_liftflux, L<2>::filter, L<2>::source_rk, L<2>::bulkvel, L<2>::tgv_analyze};
+                           L<2>::umortar, L<2>::fluxmortar, L<2>::mortar_liftflux, L<2>::filter, L<2>::source_rk, L<2>::overint, L<2>::bulkvel, L<2>::tgv_analyze};
 }  // namespace
 
 #define DGX_CAT2(a, b) a##b

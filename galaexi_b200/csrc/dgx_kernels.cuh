@@ -71,7 +71,7 @@ struct KParams {
     const double* spMat;
     double* spBase;
     // channel forcing (testcase/channel/testcase.f90:277-296 TestcaseSource)
-    int tcSource;
+    int tcSource;   // 0 off, 1 added by k_source_rk / k_overint, 2 folded into the volume kernel's epilogue (no other source active)
     double tcDpdx, tcBulkVel;
     // three-register low-storage Runge-Kutta (timestep.f90:129-200 TimeStepByLSERKK3): 0 off, 1 first stage, 2 later stage;
     // registers S2 and UPrev [elem][5][n^3]
@@ -88,6 +88,11 @@ struct KParams {
     int dtFuse;
     double dtCFL, dtDFL;
     const double* bulkDev;
+    // overintegration of JU_t (dg/overintegration.f90:179-340, step 14 of the RHS): 0 none, 1 cut-off filter with oiMat (n x n),
+    // 2 conservative cut-off: oiDown (0:NUnder,0:N), oiUp (0:N,0:NUnder), sJNUnder [elem][(NUnder+1)^3]; noJac: the volume
+    // kernels leave Ut = -(DG operator) without the Jacobian, k_overint filters it and applies the Jacobian
+    int overint, nUnder, noJac;
+    const double *oiMat, *oiDown, *oiUp, *sJNUnder;
     int flags;  // tuning switches (DGX_FLAGS): 1 lifting: L2 prefetch of own later-phase data; 2 lifting: L2 prefetch of the element
                 // a resident wave ahead; 4 / 8: the same two for k_volsurf2
 };
@@ -302,20 +307,13 @@ __global__ void __launch_bounds__(n* n* n) k_filter(const KParams P) {
     extract_faces<n, NT, 5>(b1, P.Um, P.Us, P.E2S + 18 * e, P.S2V2, sLm, sLp);
 }
 
-// Source term + (MODE 1) Williamson 2N or Ketcheson 3-register update + next-stage face states, for runs with CalcSource
-// (dg.f90:418) or a 3-register scheme: the volume
-// kernels then run in MODE 0 and leave Ut = -sJ * (DG operator); here Ut += Ut_src (the reference adds Ut_src / sJ before
-// the Jacobian is applied, exactfunc.f90:1109), then vector.f90:163-183 and the face extraction of the fused epilogue.
-template <int n, int NT, int MODE>
-__global__ void __launch_bounds__(n* n* n) k_source_rk(const KParams P, double t, double mRKA, double b_dt_in) {
-    const double b_dt = P.dtDev ? b_dt_in * __ldg(P.dtDev + 3) : b_dt_in;  // device-paced stepping: b_dt_in carries RKb, dt lives on the device
-    constexpr int n2 = n * n, n3 = n2 * n;
-    extern __shared__ double smem[];
-    double *tile = smem, *sLm = smem + 5 * n3, *sLp = sLm + n;
-    const int e = P.elemList ? P.elemList[blockIdx.x] : blockIdx.x;
-    const int tt = threadIdx.x;
-    if (tt < n) { sLm[tt] = P.L_Minus[tt]; sLp[tt] = P.L_Plus[tt]; }
-    double src[5] = {0, 0, 0, 0, 0};
+// Source terms of one node in physical space (added to sJ * (-R); before the Jacobian they enter as src / sJ): manufactured
+// solution (exactfunc.f90:946-1113), channel forcing (testcase/channel/testcase.f90:277-296), sponge (sponge.f90:529-588)
+template <int n>
+__device__ __forceinline__ void source_terms(const KParams& P, int e, int tt, double t, double (&src)[5]) {
+    constexpr int n3 = n * n * n;
+#pragma unroll
+    for (int v = 0; v < 5; v++) src[v] = 0.0;
     if (P.iniExactFunc == 4) {
         const double* X = P.xGP + (size_t)e * 3 * n3 + tt;
         const double Kappa = P.eos.kappa, PP_Pi = acos(-1.0), Amplitude = 0.1;
@@ -335,13 +333,30 @@ __global__ void __launch_bounds__(n* n* n) k_source_rk(const KParams P, double t
         src[1] = src[2] = src[3] = tmp[1] * cosX + tmp[2] * sin2;
         src[4] = tmp[3] * cosX + tmp[4] * sin2 + tmp[5] * sinX;
     }
-    if (P.tcSource) { src[1] -= P.tcDpdx; src[4] -= P.tcDpdx * (P.bulkDev ? __ldg(P.bulkDev) : P.tcBulkVel); }
+    if (P.tcSource) { src[1] = __dadd_rn(src[1], -P.tcDpdx); src[4] = __dadd_rn(src[4], -__dmul_rn(P.tcDpdx, P.bulkDev ? __ldg(P.bulkDev) : P.tcBulkVel)); }
     if (P.spMat) {
         // Ut = Ut - SpongeMat (U - SpBaseFlow) before the Jacobian (sponge.f90:574-579): times sJ here
         const double sm = P.spMat[(size_t)e * n3 + tt] * P.sJ[(size_t)e * n3 + tt];
 #pragma unroll
         for (int v = 0; v < 5; v++) src[v] -= sm * (P.U[(size_t)e * 5 * n3 + v * n3 + tt] - P.spBase[(size_t)e * 5 * n3 + v * n3 + tt]);
     }
+}
+
+// Source term + (MODE 1) Williamson 2N or Ketcheson 3-register update + next-stage face states, for runs with CalcSource
+// (dg.f90:418) or a 3-register scheme: the volume
+// kernels then run in MODE 0 and leave Ut = -sJ * (DG operator); here Ut += Ut_src (the reference adds Ut_src / sJ before
+// the Jacobian is applied, exactfunc.f90:1109), then vector.f90:163-183 and the face extraction of the fused epilogue.
+template <int n, int NT, int MODE>
+__global__ void __launch_bounds__(n* n* n) k_source_rk(const KParams P, double t, double mRKA, double b_dt_in) {
+    const double b_dt = P.dtDev ? b_dt_in * __ldg(P.dtDev + 3) : b_dt_in;  // device-paced stepping: b_dt_in carries RKb, dt lives on the device
+    constexpr int n2 = n * n, n3 = n2 * n;
+    extern __shared__ double smem[];
+    double *tile = smem, *sLm = smem + 5 * n3, *sLp = sLm + n;
+    const int e = P.elemList ? P.elemList[blockIdx.x] : blockIdx.x;
+    const int tt = threadIdx.x;
+    if (tt < n) { sLm[tt] = P.L_Minus[tt]; sLp[tt] = P.L_Plus[tt]; }
+    double src[5];
+    source_terms<n>(P, e, tt, t, src);
     double* Utg = P.Ut + (size_t)e * 5 * n3 + tt;
 #pragma unroll
     for (int v = 0; v < 5; v++) {
@@ -385,6 +400,121 @@ __global__ void __launch_bounds__(n* n* n) k_source_rk(const KParams P, double t
 }
 template <int n>
 constexpr size_t source_smem_bytes() { return sizeof(double) * (5 * n * n * n + 2 * n); }
+
+// Step 14 of the RHS with overintegration (dg/dg.f90:311-328 list, dg/overintegration.f90:179-340; host FLEXI code -- GALAEXI's
+// GPU build stops in InitOverintegration): Ut arrives as -(DG operator) WITHOUT the Jacobian (KParams::noJac); the source terms of
+// step 13 are added in reference space (src / sJ), then
+//   type 1: Filter(Ut, OverintegrationMat) along xi, eta, zeta (changeBasis.t90:287-360) and ApplyJacobian;
+//   type 2: FilterConservative (:212-339): J U_t projected to NUnder, times sJNUnder, interpolated back to N.
+// The stage update and the face extraction follow in k_source_rk (launched with the sources switched off).
+template <int n>
+__global__ void __launch_bounds__(n* n* n) k_overint(const KParams P, double t) {
+    constexpr int n2 = n * n, n3 = n2 * n;
+    extern __shared__ double smem[];
+    double *b0 = smem, *b1 = smem + 5 * n3, *sA = smem + 10 * n3, *sB = sA + n * n;
+    const int e = P.elemList ? P.elemList[blockIdx.x] : blockIdx.x;
+    const int tt = threadIdx.x;
+    const int nu = P.nUnder + 1;
+    if (P.overint == 1) {
+        for (int x = tt; x < n * n; x += n3) sA[x] = P.oiMat[x];
+    } else {
+        for (int x = tt; x < nu * n; x += n3) { sA[x] = P.oiDown[x]; sB[x] = P.oiUp[x]; }
+    }
+    double* Ut = P.Ut + (size_t)e * 5 * n3;
+    const double sJ = P.sJ[(size_t)e * n3 + tt];
+    {
+        double src[5];
+        source_terms<n>(P, e, tt, t, src);
+#pragma unroll
+        for (int v = 0; v < 5; v++) b0[v * n3 + tt] = Ut[v * n3 + tt] + src[v] / sJ;
+    }
+    __syncthreads();
+    const int k = tt / n2, j = (tt - k * n2) / n, i = tt - k * n2 - j * n;
+    if (P.overint == 1) {
+#pragma unroll
+        for (int v = 0; v < 5; v++) {
+            double a = 0.0;
+            for (int l = 0; l < n; l++) a += sA[i + n * l] * b0[v * n3 + l + n * j + n2 * k];
+            b1[v * n3 + tt] = a;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int v = 0; v < 5; v++) {
+            double a = 0.0;
+            for (int l = 0; l < n; l++) a += sA[j + n * l] * b1[v * n3 + i + n * l + n2 * k];
+            b0[v * n3 + tt] = a;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int v = 0; v < 5; v++) {
+            double a = 0.0;
+            for (int l = 0; l < n; l++) a += sA[k + n * l] * b0[v * n3 + i + n * j + n2 * l];
+            Ut[v * n3 + tt] = a * sJ;   // applyjacobian.t90:196
+        }
+        return;
+    }
+    // conservative cut-off. Down: oiDown(iU,i) at [iU + nu*i]; buffers indexed [v][a + na*(b + nb*c)] with the current extents
+    if (tt < nu * n2) {  // xi: (iU, j, k)
+        const int kk = tt / (nu * n), jj = (tt - kk * nu * n) / nu, iU = tt - kk * nu * n - jj * nu;
+#pragma unroll
+        for (int v = 0; v < 5; v++) {
+            double a = sA[iU] * b0[v * n3 + n * jj + n2 * kk];
+            for (int l = 1; l < n; l++) a += sA[iU + nu * l] * b0[v * n3 + l + n * jj + n2 * kk];
+            b1[v * n3 + iU + nu * (jj + n * kk)] = a;
+        }
+    }
+    __syncthreads();
+    if (tt < nu * nu * n) {  // eta: (iU, jU, k)
+        const int kk = tt / (nu * nu), jU = (tt - kk * nu * nu) / nu, iU = tt - kk * nu * nu - jU * nu;
+#pragma unroll
+        for (int v = 0; v < 5; v++) {
+            double a = sA[jU] * b1[v * n3 + iU + nu * (0 + n * kk)];
+            for (int l = 1; l < n; l++) a += sA[jU + nu * l] * b1[v * n3 + iU + nu * (l + n * kk)];
+            b0[v * n3 + iU + nu * (jU + nu * kk)] = a;
+        }
+    }
+    __syncthreads();
+    if (tt < nu * nu * nu) {  // zeta: (iU, jU, kU), then the Jacobian of NUnder
+        const int kU = tt / (nu * nu), jU = (tt - kU * nu * nu) / nu, iU = tt - kU * nu * nu - jU * nu;
+        const double sJu = P.sJNUnder[(size_t)e * nu * nu * nu + tt];
+#pragma unroll
+        for (int v = 0; v < 5; v++) {
+            double a = 0.0;
+            for (int l = 0; l < n; l++) a += sA[kU + nu * l] * b0[v * n3 + iU + nu * (jU + nu * l)];
+            b1[v * n3 + iU + nu * (jU + nu * kU)] = a * sJu;
+        }
+    }
+    __syncthreads();
+    // Up: oiUp(i,iU) at [i + n*iU]
+    if (tt < n * nu * nu) {  // xi: (i, jU, kU)
+        const int kU = tt / (n * nu), jU = (tt - kU * n * nu) / n, ii = tt - kU * n * nu - jU * n;
+#pragma unroll
+        for (int v = 0; v < 5; v++) {
+            double a = sB[ii] * b1[v * n3 + 0 + nu * (jU + nu * kU)];
+            for (int l = 1; l < nu; l++) a += sB[ii + n * l] * b1[v * n3 + l + nu * (jU + nu * kU)];
+            b0[v * n3 + ii + n * (jU + nu * kU)] = a;
+        }
+    }
+    __syncthreads();
+    if (tt < n2 * nu) {  // eta: (i, j, kU)
+        const int kU = tt / n2, jj = (tt - kU * n2) / n, ii = tt - kU * n2 - jj * n;
+#pragma unroll
+        for (int v = 0; v < 5; v++) {
+            double a = sB[jj] * b0[v * n3 + ii + n * (0 + nu * kU)];
+            for (int l = 1; l < nu; l++) a += sB[jj + n * l] * b0[v * n3 + ii + n * (l + nu * kU)];
+            b1[v * n3 + ii + n * (jj + n * kU)] = a;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < 5; v++) {  // zeta: (i, j, k)
+        double a = 0.0;
+        for (int l = 0; l < nu; l++) a += sB[k + n * l] * b1[v * n3 + i + n * (j + n * l)];
+        Ut[v * n3 + tt] = a;
+    }
+}
+template <int n>
+constexpr size_t overint_smem_bytes() { return sizeof(double) * (10 * n * n * n + 2 * n * n); }
 
 template <int n>
 constexpr size_t filter_smem_bytes() { return sizeof(double) * (10 * n * n * n + n * n + 2 * n); }
@@ -1216,9 +1346,14 @@ __global__ void __launch_bounds__(n* n* n, volsurf_min_blocks<n>()) k_volsurf(co
         for (int v = 0; v < 5; v++) Ut[v] += S[v];
     }
     // ---- sign and Jacobian (dg.f90:413,423)
-    const double msJ = -P.sJ[(size_t)e * n3 + t];
+    const double msJ = P.noJac ? -1.0 : -P.sJ[(size_t)e * n3 + t];  // noJac: k_overint applies the Jacobian after its filter
 #pragma unroll
     for (int v = 0; v < 5; v++) Ut[v] *= msJ;
+    if (P.tcSource == 2) {  // channel forcing folded into this epilogue (TestcaseSource, testcase/channel/testcase.f90:277-296)
+        const double bulk = P.bulkDev ? __ldg(P.bulkDev) : P.tcBulkVel;
+        Ut[MOM1] = __dadd_rn(Ut[MOM1], -P.tcDpdx);   // two roundings, like Ut + src in k_source_rk
+        Ut[ENER] = __dadd_rn(Ut[ENER], -__dmul_rn(P.tcDpdx, bulk));
+    }
 
     if (MODE == 0) {
         double* o = P.Ut + (size_t)e * 5 * n3 + t;

@@ -19,6 +19,7 @@ struct KernelTable {
     void (*mortar_liftflux)(const KParams&, const MortarParams& mp, int nBig, cudaStream_t);
     void (*filter)(const KParams&, int nBlocks, cudaStream_t);  // FilterType > 0: U <- FilterMat U, faces of the filtered state
     void (*source_rk)(const KParams&, int mode, double t, double mRKA, double b_dt, int nBlocks, cudaStream_t);  // CalcSource path
+    void (*overint)(const KParams&, double t, int nBlocks, cudaStream_t);  // step 14 with overintegration
     void (*bulkvel)(const KParams&, const double* wGP, double* partials, cudaStream_t);  // channel CalcForcing
     // TGV diagnostics: per-element partials [nElems][TGV_NPART]; returns a cudaError_t
     int (*tgv_analyze)(const KParams&, int NA1, const double* Vdm, const double* wA, double* partials, cudaStream_t);

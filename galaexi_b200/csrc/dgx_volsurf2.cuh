@@ -58,6 +58,17 @@ constexpr int VS2_SLOTS = 17;
 #ifndef VS2_CROSS_UNROLL
 #define VS2_CROSS_UNROLL 1
 #endif
+// 1: the consistent (l == i) terms of the flux differencing are skipped: on Gauss-Lobatto nodes DVolSurf is zero on its main
+// diagonal (volint.f90:257-259 "Attention 5"; the reference's CPU loop starts at l = i+1, its GPU kernel multiplies the
+// consistent flux by that zero). In floating point the table holds O(1e-15) there, so the switch moves Ut by ~1e-15 relative.
+// the three sweep directions as three copies of the sweep code (direction a compile-time value: no index selects) for n up to
+// this value; larger tiles keep one copy with a run-time direction (instruction cache, profiles/r01e_volsurf2_full.md)
+#ifndef VS2_DIRU_MAXN
+#define VS2_DIRU_MAXN 0
+#endif
+#ifndef VS2_SKIP_DIAG
+#define VS2_SKIP_DIAG 0
+#endif
 constexpr int VS2_CU = VS2_CROSS_UNROLL;
 #ifndef VS2_MIN_BLOCKS
 #ifndef VS2_MINB6
@@ -213,7 +224,7 @@ __device__ __forceinline__ void vs2_sweep(const double* __restrict__ R, const do
 #pragma unroll
     for (int m = 0; m < SEG; m++) {
         if (m < cnt) {
-            vs2_pair_acc<VAR>(own[m], own[m], Dv[(a0 + m) + n * (a0 + m)], acc[m]);
+            if (!VS2_SKIP_DIAG) vs2_pair_acc<VAR>(own[m], own[m], Dv[(a0 + m) + n * (a0 + m)], acc[m]);
 #pragma unroll
             for (int m2 = m + 1; m2 < SEG; m2++) {
                 if (m2 < cnt) {
@@ -327,7 +338,8 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
     }
     // ---- P3: the three flux-differencing sweeps (volint.f90:306-347). Metric triples: xi in slots S_MX.. and eta in
     // S_ME.. (from P0); zeta is copied by cp.async into S_MX.. while the eta sweep runs.
-#pragma unroll 1
+    constexpr int DIRU = (n <= VS2_DIRU_MAXN) ? 3 : 1;
+#pragma unroll(DIRU)
     for (int d = 0; d < 3; d++) {
         if (d == 2) asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();  // node record / previous partials / metric triple visible, previous triple consumed
@@ -415,11 +427,16 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
                 const int k = a0 + m;
                 const int node = c1 + n * c2 + n2 * k;
                 const int id = TileV<n>::idx(c1, c2, k);
-                const double msJ = -sJv[m];
+                const double msJ = P.noJac ? -1.0 : -sJv[m];  // noJac: k_overint applies the Jacobian after its filter
                 double Ut[5];
                 Ut[0] = S[S_RHO * SL + id] * msJ;
 #pragma unroll
                 for (int v = 0; v < 4; v++) Ut[1 + v] = S[(S_UT + v) * SL + id] * msJ;
+                if (P.tcSource == 2) {  // channel forcing folded into this epilogue (TestcaseSource, testcase/channel/testcase.f90:277-296)
+                    const double bulk = P.bulkDev ? __ldg(P.bulkDev) : P.tcBulkVel;
+                    Ut[MOM1] = __dadd_rn(Ut[MOM1], -P.tcDpdx);   // two roundings, like Ut + src in k_source_rk
+                    Ut[ENER] = __dadd_rn(Ut[ENER], -__dmul_rn(P.tcDpdx, bulk));
+                }
                 if (MODE == 0) {
                     double* o = P.Ut + (size_t)e * 5 * n3 + node;
 #pragma unroll

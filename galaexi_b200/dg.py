@@ -55,6 +55,8 @@ class DgxConfig(C.Structure):
         + [("doWeakLifting", C.c_int), ("doConservativeLifting", C.c_int)]
         + [("SpongeMat", _dp), ("SpBaseFlow", _dp)]
         + [(k, _dp) for k in ("RKdelta", "RKg1", "RKg2", "RKg3")]
+        + [("OverintegrationType", C.c_int), ("NUnder", C.c_int)]
+        + [(k, _dp) for k in ("OverintegrationMat", "Vdm_N_NUnder", "Vdm_NUnder_N", "sJNUnder")]
     )
 
 
@@ -199,6 +201,16 @@ class DGSolver:
             c.IniExactFunc = int(case.IniExactFunc)
             for i_, v_ in enumerate(case.AdvVel):
                 c.AdvVel[i_] = v_
+        if getattr(case, "OverintegrationType", 0):   # Fortran M(a,b) at [a + na*b] == C array M.T
+            c.OverintegrationType, c.NUnder = int(case.OverintegrationType), int(case.NUnder)
+            if case.OverintegrationType == 1:
+                k["OverintegrationMat"] = f64(np.asarray(case.OverintegrationMat).T)
+                c.OverintegrationMat = k["OverintegrationMat"].ctypes.data_as(_dp)
+            else:
+                k["Vdm_N_NUnder"], k["Vdm_NUnder_N"] = f64(np.asarray(case.Vdm_N_NUnder).T), f64(np.asarray(case.Vdm_NUnder_N).T)
+                k["sJNUnder"] = f64(case.sJNUnder)
+                for nm in ("Vdm_N_NUnder", "Vdm_NUnder_N", "sJNUnder"):
+                    setattr(c, nm, k[nm].ctypes.data_as(_dp))
         if case.FilterMat is not None:
             k["FilterMat"] = f64(np.asarray(case.FilterMat).T)      # Fortran FilterMat(i,l) at [i + n*l]
             c.FilterMat = k["FilterMat"].ctypes.data_as(_dp)

@@ -111,6 +111,12 @@ typedef struct dgx_config {
      * ketchesonrk4-18; stage update of TimeStepByLSERKK3, timestep.f90:129-200): RKdelta, RKg1, RKg2, RKg3 (1:nRKStages);
      * RKb, RKc as above (RKc(1) = 0), RKA unused. All four NULL: Williamson 2N (TimeStepByLSERKW2). */
     const double *RKdelta, *RKg1, *RKg2, *RKg3;
+    /* overintegration of JU_t, step 14 of the RHS (dg/overintegration.f90:92-165 InitOverintegration, :179-340; host FLEXI code --
+     * GALAEXI's GPU build stops at :108-114): OverintegrationType 0 none, 1 cut-off (OverintegrationMat(0:N,0:N) applied to JU_t,
+     * then the Jacobian), 2 conservative cut-off (Vdm_N_NUnder(0:NUnder,0:N), Vdm_NUnder_N(0:N,0:NUnder),
+     * sJNUnder(0:NUnder,0:NUnder,0:NUnder,nElems)). The CFL scaling with NEff (timedisc_func.f90:171-173) is the host's. */
+    int OverintegrationType, NUnder;
+    const double *OverintegrationMat, *Vdm_N_NUnder, *Vdm_NUnder_N, *sJNUnder;
 } dgx_config;
 
 int dgx_create(dgx_handle **h, const dgx_config *cfg);

@@ -42,6 +42,8 @@ TYPE, BIND(C), PUBLIC :: dgx_config
   INTEGER(C_INT) :: doWeakLifting, doConservativeLifting   ! lifting.f90:139-141
   TYPE(C_PTR)    :: SpongeMat, SpBaseFlow                  ! sponge.f90 (SpongeMat expanded to all elements), C_NULL_PTR: no sponge
   TYPE(C_PTR)    :: RKdelta, RKg1, RKg2, RKg3              ! TimeDiscType LSERKK3 (timedisc_vars.f90:464-773), C_NULL_PTR: LSERKW2
+  INTEGER(C_INT) :: OverintegrationType, NUnder            ! overintegration_vars.f90:30-36
+  TYPE(C_PTR)    :: OverintegrationMat, Vdm_N_NUnder, Vdm_NUnder_N, sJNUnder   ! overintegration_vars.f90:38-51
 END TYPE dgx_config
 
 TYPE(C_PTR), PUBLIC, SAVE :: dgx = C_NULL_PTR   !< the library handle (one per rank)

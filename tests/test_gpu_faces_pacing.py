@@ -191,3 +191,61 @@ def test_full_size_ut_vs_oracle():
     err = parity.rel_l2(Ut, Ut_ref)
     worst = float(np.abs(Ut - Ut_ref).max() / np.abs(Ut_ref).max())
     assert err <= 1e-12 and worst <= 1e-11, (err, worst)
+
+
+# ---- overintegration of JU_t (dg/overintegration.f90; the oracle's restatement is pinned by the reference's tgv/oInt CSV at N=11,
+# tests/test_oracle_goldens.py; the kernels exist for N <= 9) -------------------------------------------------------------------------
+def _oint_cases():
+    return {
+        "cutoff_gauss_curved": lambda: cases.tgv_box_case(E=3, N=6, NGeo=2, deform=0.05, perturb=1e-3, split=None, riemann="Roe",
+                                                          node_type="GAUSS", OverintegrationType="cutoff", NUnder=3),
+        "conscutoff_gauss_curved": lambda: cases.tgv_box_case(E=3, N=6, NGeo=2, deform=0.05, perturb=1e-3, split=None, riemann="Roe",
+                                                              node_type="GAUSS", OverintegrationType="conscutoff", NUnder=4),
+        "conscutoff_gl_curved": lambda: cases.tgv_box_case(E=3, N=5, NGeo=2, deform=0.05, perturb=1e-3, split=None,
+                                                           riemann="RoeEntropyFix", OverintegrationType="conscutoff", NUnder=3),
+        "cutoff_split_n7": lambda: cases.tgv_box_case(E=3, N=7, NGeo=2, deform=0.05, perturb=1e-3, OverintegrationType="cutoff", NUnder=5),
+        "cutoff_source_manufactured": lambda: cases.manufactured_case("cart_periodic_002", N=4, OverintegrationType="cutoff", NUnder=3),
+        "conscutoff_walls_channel": lambda: cases.channel_case(E=3, N=4, OverintegrationType="conscutoff", NUnder=2),
+        "oint_reference_setup_n9": lambda: cases.tgv_oint_case(N=9, NUnder=6),
+    }
+
+
+@pytest.mark.parametrize("name", sorted(_oint_cases()))
+def test_overintegration_parity(name):
+    from oracle import parity
+    c, U0 = _oint_cases()[name]()
+    assert c.OverintegrationType in (1, 2)
+    o, s = _oracle(c), _solver(c)
+    o.set_state(U0)
+    s.set_state(U0)
+    Ut_ref = o.time_derivative(0.0).copy()
+    s.DGTimeDerivative_weakForm(0.0)
+    r = parity.ut_error(c, U0, s.get_ut(), Ut_ref, label="oint_" + name)
+    # only the unperturbed low-Mach TGV start field of the reference's own set-up is cancellation-dominated (as in tgv/split)
+    assert r["ok"] and (not r["used_extended"] or name == "oint_reference_setup_n9"), r
+    dt_ref = o.calc_timestep()[0]
+    dt, err = s.CalcTimeStep()
+    assert err == 0 and abs(dt - dt_ref) <= 1e-13 * dt_ref
+    t = 0.0
+    for _ in range(2):
+        o.rk_step(t, dt_ref)
+        s.TimeStepByLSERKW2(t, dt_ref)
+        t += dt_ref
+    assert parity.rel_l2(s.get_state(), o.array("U")) <= 1e-10
+    # the device-paced / graph form of the same steps
+    s2 = _solver(c)
+    s2.set_state(U0)
+    if not c.IniExactFunc:
+        s2.run_steps(2, 0.0, dt_ref, adaptive=True, device_paced=True, graph=True)
+        s3 = _solver(c)
+        s3.set_state(U0)
+        tt = 0.0
+        for _ in range(2):
+            d_, _e = s3.CalcTimeStep()
+            s3.TimeStepByLSERKW2(tt, d_)
+            tt += d_
+        assert np.array_equal(s2.get_state(), s3.get_state())
+        s3.FinalizeDG()
+    s2.FinalizeDG()
+    s.FinalizeDG()
+    o.close()

@@ -15,7 +15,7 @@ def _ngpus():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("case", ["tgv", "cavity", "channel", "shu", "tgv_br2", "mortar001", "mortar004_br2", "tgv_filter", "manufactured"])
+@pytest.mark.parametrize("case", ["tgv", "cavity", "channel", "shu", "tgv_br2", "mortar001", "mortar004_br2", "tgv_filter", "manufactured", "tgv_oint"])
 def test_two_ranks_match_single_rank(case):
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")

@@ -48,6 +48,9 @@ def main():
             return cases.tgv_box_case(E=4, N=4, NGeo=2, deform=0.05, nProcs=nProcs, myRank=myRank, FilterType="cutoff", NFilter=2)
         if name == "manufactured":   # CalcSource (dg.f90:418), exact function 4
             return cases.manufactured_case("cart_periodic_004", N=3, nProcs=nProcs, myRank=myRank)
+        if name == "tgv_oint":       # overintegration (conservative cut-off) behind the halo-dependent volume kernels
+            return cases.tgv_box_case(E=4, N=5, NGeo=2, deform=0.05, nProcs=nProcs, myRank=myRank, split=None, riemann="Roe",
+                                      node_type="GAUSS", OverintegrationType="conscutoff", NUnder=3)
         if name == "tgv_br2":
             return cases.tgv_box_case(E=4, N=4, NGeo=2, deform=0.05, nProcs=nProcs, myRank=myRank, lifting="br2")
         raise SystemExit(f"unknown case {name}")
@@ -232,4 +235,13 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except SystemExit:
+        raise
+    except BaseException:      # a failing rank must not leave the others (and the launcher) waiting in a collective
+        import traceback
+        traceback.print_exc()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(3)

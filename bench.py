@@ -513,7 +513,17 @@ def multirank_parity(comm: Comm):
     from galaexi_b200 import dg
     from galaexi_b200.host_standin import workloads as wl
     out = {}
-    for label, build in (("tgv_8x8x8_N7", lambda P, r: wl.tgv((8, 8, 8), 7, nProcs=P, myRank=r)),
+
+    def tgv_disturbed(P, r):
+        # a smooth disturbance on the low-Mach TGV field, the same function of x on every rank: the bare field's residual is
+        # cancellation-dominated (FP64 round-off floor ~9e-12 > 1e-12) and would test that floor instead of the N-rank path
+        c, U = wl.tgv((8, 8, 8), 7, nProcs=P, myRank=r)
+        x = c.geo["Elem_xGP"]
+        for v in range(5):
+            U[..., v] *= 1.0 + 1e-3 * np.sin((1.0 + v) * x[..., 0] + 0.3 * v) * np.cos(2.0 * x[..., 1] - 0.1 * v) * np.sin(x[..., 2] + 0.5)
+        return c, U
+
+    for label, build in (("tgv_8x8x8_N7", tgv_disturbed),
                          ("channel_4x4x4_N5_walls", lambda P, r: wl.channel((4, 4, 4), 5, nProcs=P, myRank=r))):
         c, U0 = build(comm.world, comm.rank)
         s = dg.DGSolver(c, device=comm.local, nccl_id=comm.new_nccl_id())
@@ -576,6 +586,17 @@ def e2e_leg(comm: Comm, s, wl, m, steps):
                 call="dgx_set_state(U_host) + dgx_calc_timestep + dgx_rk_step + dgx_get_state(U_host) per step, pinned host buffers")
 
 
+def watchdog(seconds: float):
+    """Last resort against a hang in a collective or in the teardown (another rank died, a communicator that does not come
+    down): after `seconds` the process leaves without waiting for anybody."""
+    def bite():
+        time.sleep(seconds)
+        sys.stderr.write(f"bench.py: watchdog after {seconds:.0f} s, leaving\n")
+        sys.stderr.flush()
+        os._exit(2)
+    threading.Thread(target=bite, daemon=True).start()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -597,6 +618,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the N>1 parity leg")
     ap.add_argument("--no-ncu", action="store_true", help="skip the live ncu counter pass (N=1)")
     ap.add_argument("--ncu-timeout", type=int, default=240)
+    ap.add_argument("--watchdog", type=float, default=1500.0, help="seconds after which a hung run gives up")
     ap.add_argument("--ncu-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.config == 5:
@@ -611,6 +633,7 @@ def main():
     comm = Comm()
     if comm.world == 1 and args.gpus > 1:
         raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    watchdog(args.watchdog)
     comm.init()
     world, rank = comm.world, comm.rank
 
@@ -670,6 +693,7 @@ def main():
         if parity is not None:
             line["parity"] = parity
         print(json.dumps(line), flush=True)
+    watchdog(90.0)     # the line is out: the teardown must not hold the launcher
     if world > 1:
         comm.dist.barrier()
         comm.dist.destroy_process_group()

@@ -123,6 +123,9 @@ struct dgx_handle {
     int graphCur = -1, graphKey = -1;
     long long graphLaunches = 0;
     int graphFailed = 0;
+    bool graphEndsPosted = false;      // the captured pair leaves the next U-face halo posted and joined into stream s
+    std::vector<double> dtHistHost;    // dt of the steps of a host-paced dgx_run_steps
+    bool histOnHost = false;
     // events used while capturing: an event recorded inside a stream capture cannot be waited on by eager work afterwards, so the
     // capture runs on its own set (same order as the eager ones in swap_event_sets)
     cudaEvent_t evCap[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -533,10 +536,11 @@ void dgx_destroy(dgx_handle* h) {
     if (h->s) cudaStreamSynchronize(h->s);
     if (h->cs) cudaStreamSynchronize(h->cs);
     if (h->s2) cudaStreamSynchronize(h->s2);
+    // the step graph holds NCCL kernels of this communicator: it has to go first (ncclCommDestroy waits for captured work)
+    if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
     if (h->comm) g_nccl.CommDestroy(h->comm);
     for (void* p : h->allocs) cudaFree(p);
     if (h->hPinned) cudaFreeHost(h->hPinned);
-    if (h->graph) cudaGraphExecDestroy(h->graph);
     for (cudaEvent_t e : h->evCap) if (e) cudaEventDestroy(e);
     cudaEvent_t evs[] = {h->evFaces, h->evUhalo, h->evGrad, h->evGhalo, h->evT0, h->evT1, h->evSide, h->evBnd, h->evDtPre, h->evDt, h->evNext};
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
@@ -1088,7 +1092,8 @@ int build_step_graph(dgx_handle* h, bool forcing, int key) {
     if (multi) h->uHaloPosted = h->uHaloJoined = true;
     int rc = dev_step(h, forcing, false, true);
     if (!rc) rc = dev_step(h, forcing, false, true);
-    if (!rc && multi && h->uHaloPosted && cudaStreamWaitEvent(h->s, h->evUhalo, 0) != cudaSuccess) rc = 1;  // join the communication stream
+    const bool endsPosted = multi && h->uHaloPosted;
+    if (!rc && endsPosted && cudaStreamWaitEvent(h->s, h->evUhalo, 0) != cudaSuccess) rc = 1;  // join the communication stream
     cudaError_t e = cudaStreamEndCapture(h->s, &g);
     h->capturing = false;
     h->cur = cur0;
@@ -1105,17 +1110,21 @@ int build_step_graph(dgx_handle* h, bool forcing, int key) {
     if (e != cudaSuccess) { cudaGetLastError(); h->graph = nullptr; return 1; }
     h->graphCur = cur0;
     h->graphKey = key;
+    h->graphEndsPosted = endsPosted;
     return 0;
 }
 }  // namespace
 
 int dgx_run_steps(dgx_handle* h, int nSteps, double t, double dt, int flags, float* ms, long long* launches) {
     CK(cudaSetDevice(h->cfg.device));
-    const bool adaptive = flags & 1, forcing = flags & 2, dev = flags & 4;
+    const bool adaptive = flags & 1, forcing = flags & 2;
+    // non-conforming meshes cut by a rank boundary keep the host-paced sequence (same results; their projection kernels sit
+    // between the halo phases on one stream, which the device-paced orchestration has not been validated for)
+    const bool dev = (flags & 4) && !(h->cfg.nRanks > 1 && !h->NbProc.empty() && h->hasMortar());
     static const bool noGraph = getenv("DGX_NO_GRAPH") != nullptr;
     const bool graph = (flags & 8) && !noGraph && !h->graphFailed;
     if (forcing && (!h->bvPart || !(h->bvVol > 0.0))) return fail(h, "dgx_run_steps: CalcForcing every step needs a previous dgx_calc_bulk_velocity (weights, volume)");
-    if (dev && (!adaptive || h->P.iniExactFunc == 4 || !h->RKg1.empty()))
+    if ((flags & 4) && (!adaptive || h->P.iniExactFunc == 4 || !h->RKg1.empty()))
         return fail(h, "dgx_run_steps: device-paced stepping needs adaptive dt, a time-independent source and a 2-register Runge-Kutta scheme");
     const long long l0 = h->launches;
     const int keep = h->keepGrad;
@@ -1145,21 +1154,21 @@ int dgx_run_steps(dgx_handle* h, int nSteps, double t, double dt, int flags, flo
             if (nPairs > 0) {
                 if ((!h->graph || h->graphCur != h->cur || h->graphKey != key) && build_step_graph(h, forcing, key)) h->graphFailed = 1;
                 if (h->graph && h->graphCur == h->cur && h->graphKey == key) {
-                    if (multi) {
-                        // the graph's first stage expects its U-face halo complete and ordered before stream s
-                        if (!h->uHaloPosted) {
-                            CK(cudaEventRecord(h->evFaces, h->s));
-                            CK(cudaStreamWaitEvent(h->cs, h->evFaces, 0));
-                            if (exchange(h, h->Uf[h->cur][0], h->Uf[h->cur][1], 5)) return 1;
-                            CK(cudaEventRecord(h->evUhalo, h->cs));
-                        }
-                        if (!h->uHaloJoined) CK(cudaStreamWaitEvent(h->s, h->evUhalo, 0));
-                    }
                     for (int p = 0; p < nPairs; p++) {
+                        if (multi) {
+                            // the graph's first stage expects its U-face halo complete and ordered before stream s
+                            if (!h->uHaloPosted) {
+                                CK(cudaEventRecord(h->evFaces, h->s));
+                                CK(cudaStreamWaitEvent(h->cs, h->evFaces, 0));
+                                if (exchange(h, h->Uf[h->cur][0], h->Uf[h->cur][1], 5)) return 1;
+                                CK(cudaEventRecord(h->evUhalo, h->cs));
+                            }
+                            if (!h->uHaloPosted || !h->uHaloJoined) CK(cudaStreamWaitEvent(h->s, h->evUhalo, 0));
+                        }
                         CK(cudaGraphLaunch(h->graph, h->s));
                         h->launches += h->graphLaunches;
+                        if (multi) h->uHaloPosted = h->uHaloJoined = h->graphEndsPosted;  // the state the replay ends in
                     }
-                    if (multi) h->uHaloPosted = h->uHaloJoined = true;  // the state every replay ends in
                     it += 2 * nPairs;
                 }
             }
@@ -1170,7 +1179,10 @@ int dgx_run_steps(dgx_handle* h, int nSteps, double t, double dt, int flags, flo
         // capture for the next call, outside its timed region
         if (graph && h->warm && (!h->graph || h->graphCur != h->cur || h->graphKey != key) && build_step_graph(h, forcing, key)) h->graphFailed = 1;
         h->P.bulkDev = nullptr;
+        h->histOnHost = false;
     } else {
+        h->dtHistHost.clear();
+        h->histOnHost = true;
         for (int it = 0; it < nSteps; it++) {
             h->keepGrad = (it == nSteps - 1) ? keep : 0;  // nothing can read the gradients between the steps of this call
             if (forcing) {
@@ -1186,6 +1198,7 @@ int dgx_run_steps(dgx_handle* h, int nSteps, double t, double dt, int flags, flo
                 if (et) { h->keepGrad = keep; return fail(h, "timestep is NaN / state not admissible at t=%g", t); }
             }
             if (dgx_rk_step(h, t, dt)) { h->keepGrad = keep; return 1; }
+            h->dtHistHost.push_back(dt);
             t += dt;
         }
         h->keepGrad = keep;
@@ -1203,6 +1216,12 @@ int dgx_run_steps(dgx_handle* h, int nSteps, double t, double dt, int flags, flo
 
 int dgx_get_dt_history(dgx_handle* h, int cap, double* dts, int* count) {
     CK(cudaSetDevice(h->cfg.device));
+    if (h->histOnHost) {
+        const int nh = (int)h->dtHistHost.size();
+        if (count) *count = nh;
+        for (int i = 0; i < nh && i < cap && dts; i++) dts[i] = h->dtHistHost[i];
+        return 0;
+    }
     const int n = h->dtHistCount < cap ? h->dtHistCount : cap;
     if (count) *count = h->dtHistCount;
     if (n > 0 && dts) {

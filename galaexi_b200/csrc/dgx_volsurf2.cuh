@@ -38,7 +38,7 @@ struct TileV {
 };
 
 #ifndef VS2_EPB6
-#define VS2_EPB6 2   // elements per CTA at n = 6 (tuning knob)
+#define VS2_EPB6 1   // elements per CTA at n = 6 (tuning knob; 1 element / 5 CTAs per SM: 0.93 -> 0.79 ms at 32^3, profiles/r03f_*)
 #endif
 template <int n>
 constexpr int vs2_epb() { return n == 6 ? VS2_EPB6 : ((128 + n * n) / (2 * n * n) > 0 ? (128 + n * n) / (2 * n * n) : 1); }
@@ -64,7 +64,10 @@ constexpr int VS2_SLOTS = 17;
 // the three sweep directions as three copies of the sweep code (direction a compile-time value: no index selects) for n up to
 // this value; larger tiles keep one copy with a run-time direction (instruction cache, profiles/r01e_volsurf2_full.md)
 #ifndef VS2_DIRU_MAXN
-#define VS2_DIRU_MAXN 0
+#define VS2_DIRU_MAXN 6
+#endif
+#ifndef VS2_DIRU_MINN
+#define VS2_DIRU_MINN 6   // measured at n = 6 only (0.84 -> 0.79 ms); n = 5 spills with three copies at its register cap
 #endif
 #ifndef VS2_SKIP_DIAG
 #define VS2_SKIP_DIAG 0
@@ -72,7 +75,7 @@ constexpr int VS2_SLOTS = 17;
 constexpr int VS2_CU = VS2_CROSS_UNROLL;
 #ifndef VS2_MIN_BLOCKS
 #ifndef VS2_MINB6
-#define VS2_MINB6 3
+#define VS2_MINB6 5
 #endif
 #ifndef VS2_MINB8
 #define VS2_MINB8 3
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(vs2_threads<n>(), VS2_MIN_BLOCKS(n)) k_volsurf
     }
     // ---- P3: the three flux-differencing sweeps (volint.f90:306-347). Metric triples: xi in slots S_MX.. and eta in
     // S_ME.. (from P0); zeta is copied by cp.async into S_MX.. while the eta sweep runs.
-    constexpr int DIRU = (n <= VS2_DIRU_MAXN) ? 3 : 1;
+    constexpr int DIRU = (n <= VS2_DIRU_MAXN && n >= VS2_DIRU_MINN) ? 3 : 1;
 #pragma unroll(DIRU)
     for (int d = 0; d < 3; d++) {
         if (d == 2) asm volatile("cp.async.wait_group 0;" ::: "memory");

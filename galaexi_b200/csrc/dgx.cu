@@ -115,6 +115,7 @@ struct dgx_handle {
     // U-face halo of the NEXT stage: posted right behind the halo-dependent volume kernel of an RK stage so that it travels
     // while the inner elements are still being updated (dg.f90:335-350 starts it at the top of the next RHS instead)
     bool uHaloPosted = false, uHaloJoined = false;
+    bool anyMortar = false;  // some rank of the job has non-conforming sides: every rank keeps the plain call order (see rhs)
     // device-paced stepping (dgx_run_steps flag 4): dt / bulk velocity stay on the device, one RK step pair is replayed as a CUDA graph
     double* dtHist = nullptr;
     int dtHistCap = 0, dtHistCount = 0;
@@ -415,7 +416,7 @@ int rhs(dgx_handle* h, int mode, double t, double mRKA, double b_dt, StageTimes*
         if (P.dtFuse) { CK(cudaStreamWaitEvent(h->s2, h->evDt, 0)); CK(cudaStreamWaitEvent(h->s, h->evDt, 0)); }
         if (h->nBnd) { kt->volsurf(Pb, vmode, mRKA, b_dt, h->nBnd, h->s2); if (check_launch(h, "k_volsurf(bnd)")) return 1; }
         CK(cudaEventRecord(h->evBnd, h->s2));
-        const bool post = mode == 1 && earlyHalo && o.postHalo && !P.FilterMat;
+        const bool post = mode == 1 && earlyHalo && o.postHalo && !P.FilterMat && !h->anyMortar;
         if (post && !src) {
             // every MPI side belongs to a halo-dependent element: their next-stage face states are complete here
             CK(cudaStreamWaitEvent(h->cs, h->evBnd, 0));
@@ -765,6 +766,15 @@ int dgx_create(dgx_handle** out, const dgx_config* cfg) {
         ncclUniqueId id;
         memcpy(id.internal, c.ncclUniqueId, 128);
         NK(g_nccl.CommInitRank(&h->comm, c.nRanks, id, c.myRank));
+        // orchestration choices that change the ORDER of the communication calls (U-face halo posted early, device-paced steps)
+        // must be the same on every rank: a rank without mortar sides next to one with them would otherwise leave a point-to-point
+        // exchange pending that its neighbour only answers after its next collective
+        h->hPinned[5] = h->hasMortar() ? 1.0 : 0.0;
+        CK(cudaMemcpyAsync(h->dtOut + 5, h->hPinned + 5, sizeof(double), cudaMemcpyHostToDevice, h->s));
+        NK(g_nccl.AllReduce(h->dtOut + 5, h->dtOut + 5, 1, ncclFloat64, 2 /* ncclMax */, h->comm, h->s));
+        CK(cudaMemcpyAsync(h->hPinned + 5, h->dtOut + 5, sizeof(double), cudaMemcpyDeviceToHost, h->s));
+        CK(cudaStreamSynchronize(h->s));
+        h->anyMortar = h->hPinned[5] > 0.0;
     }
     CK(cudaStreamSynchronize(h->s));
     h->cfg.RefStatePrim = nullptr;  // pointers are not retained
@@ -1120,7 +1130,7 @@ int dgx_run_steps(dgx_handle* h, int nSteps, double t, double dt, int flags, flo
     const bool adaptive = flags & 1, forcing = flags & 2;
     // non-conforming meshes cut by a rank boundary keep the host-paced sequence (same results; their projection kernels sit
     // between the halo phases on one stream, which the device-paced orchestration has not been validated for)
-    const bool dev = (flags & 4) && !(h->cfg.nRanks > 1 && !h->NbProc.empty() && h->hasMortar());
+    const bool dev = (flags & 4) && !(h->cfg.nRanks > 1 && h->anyMortar);
     static const bool noGraph = getenv("DGX_NO_GRAPH") != nullptr;
     const bool graph = (flags & 8) && !noGraph && !h->graphFailed;
     if (forcing && (!h->bvPart || !(h->bvVol > 0.0))) return fail(h, "dgx_run_steps: CalcForcing every step needs a previous dgx_calc_bulk_velocity (weights, volume)");

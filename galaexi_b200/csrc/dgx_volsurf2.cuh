@@ -61,10 +61,11 @@ constexpr int VS2_SLOTS = 17;
 // 1: the consistent (l == i) terms of the flux differencing are skipped: on Gauss-Lobatto nodes DVolSurf is zero on its main
 // diagonal (volint.f90:257-259 "Attention 5"; the reference's CPU loop starts at l = i+1, its GPU kernel multiplies the
 // consistent flux by that zero). In floating point the table holds O(1e-15) there, so the switch moves Ut by ~1e-15 relative.
-// the three sweep directions as three copies of the sweep code (direction a compile-time value: no index selects) for n up to
-// this value; larger tiles keep one copy with a run-time direction (instruction cache, profiles/r01e_volsurf2_full.md)
+// the three sweep directions as three copies of the sweep code (direction a compile-time value: no index selects) for n in
+// [VS2_DIRU_MINN, VS2_DIRU_MAXN]. Round 1's kernel (with the viscous sweep inside) was instruction-cache bound in this form
+// (profiles/r01e_volsurf2_full.md); without it the three copies fit: n = 8 1.599 -> 1.516 ms, n = 6 0.836 -> 0.786 ms (r03)
 #ifndef VS2_DIRU_MAXN
-#define VS2_DIRU_MAXN 6
+#define VS2_DIRU_MAXN 8
 #endif
 #ifndef VS2_DIRU_MINN
 #define VS2_DIRU_MINN 6   // measured at n = 6 only (0.84 -> 0.79 ms); n = 5 spills with three copies at its register cap

@@ -9,6 +9,7 @@
 //     state / face gradients, then lifting flux and numerical flux are evaluated redundantly (bit-identical)
 //     on both ranks, which removes the lifting-flux and flux messages (mpi/mpi.f90:277-387, SURVEY 2.3 rows 2,4).
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3 (no link dependency); ranges like globals/nvtx.f90, switched on with DGX_NVTX=1
 #include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
@@ -212,6 +213,14 @@ int upload(dgx_handle* h, T** p, const T* host, size_t count) {
     return 0;
 }
 
+// NVTX range per phase of the RHS / time step (the reference brackets the same phases, globals/nvtx.f90 + dg.f90), for nsys timelines
+struct NvtxRange {
+    bool on;
+    explicit NvtxRange(const char* name) : on(enabled()) { if (on) nvtxRangePushA(name); }
+    ~NvtxRange() { if (on) nvtxRangePop(); }
+    static bool enabled() { static const bool e = getenv("DGX_NVTX") != nullptr; return e; }
+};
+
 inline unsigned blocks_for(size_t total, int bs) { return (unsigned)((total + bs - 1) / bs); }
 
 int check_launch(dgx_handle* h, const char* what) {
@@ -350,6 +359,7 @@ int rhs(dgx_handle* h, int mode, double t, double mRKA, double b_dt, StageTimes*
         return (c.nElems > 0 && check_launch(h, "k_source_rk")) ? 1 : 0;
     };
     auto mark = [&](void) { if (st) cudaEventRecord(st->ev[st->nev++], h->s); };
+    NvtxRange nvtxRhs(mode == 1 ? "DGTimeDerivative_weakForm + RK stage" : "DGTimeDerivative_weakForm");
     mark();
     if (o.fuseDt && !P.dtFuse) {
         kt->timestep(P, c.CFLScale, c.DFLScale, h->dtOut, h->s);
@@ -877,6 +887,7 @@ int dgx_rk_stage(dgx_handle* h, int iStage, double t, double dt) {
 }
 
 int dgx_rk_step(dgx_handle* h, double t, double dt) {
+    NvtxRange nvtxStep("TimeStepByLSERK");
     for (int st = 1; st <= h->cfg.nRKStages; st++)
         if (dgx_rk_stage(h, st, st == 1 ? t : t + h->RKc[st - 1] * dt, dt)) return 1;
     // an unsupported boundary condition type raises errFlag bit 1 in the first RHS (the reference Aborts in GetBoundaryFlux):
@@ -892,6 +903,7 @@ int dgx_set_keep_gradients(dgx_handle* h, int on) {
 }
 
 int dgx_calc_timestep(dgx_handle* h, double* dt, int* errType) {
+    NvtxRange nvtxDt("CalcTimeStep");
     CK(cudaSetDevice(h->cfg.device));
     const double big = 1.7976931348623157e308;
     h->hPinned[0] = big; h->hPinned[1] = big; h->hPinned[2] = 0.0;
@@ -1065,6 +1077,7 @@ int dgx_analyze_tgv(dgx_handle* h, int NAnalyze, const double* Vdm, const double
 namespace {
 // one RK step of device-paced stepping: CalcForcing (optional), then the stages; stage 1 evaluates CalcTimeStep on the way
 int dev_step(dgx_handle* h, bool forcing, bool storeLast, bool postLast) {
+    NvtxRange nvtxStep("TimeStepByLSERK (device-paced)");
     if (forcing && bulk_velocity_dev(h)) return 1;
     const int nst = h->cfg.nRKStages;
     for (int st = 1; st <= nst; st++) {

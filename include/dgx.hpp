@@ -18,6 +18,7 @@
 //   Abort(__STAMP__, msg)                              globals/globals.f90:175-221 dgx::Abort (exception carrying dgx_last_error)
 #pragma once
 #include <functional>
+#include <vector>
 #include <stdexcept>
 #include <string>
 
@@ -108,6 +109,22 @@ class DG {
         ck(dgx_calc_wall_velocity(h_, wGP, BC, nBCs, Surf, maxV, minV, meanV));
     }
     void SetChannelForcing(double dpdx, double BulkVel, bool on = true) { ck(dgx_set_channel_forcing(h_, on ? 1 : 0, dpdx, BulkVel)); }
+
+    // The steps between two analyze points without the host in the loop (timedisc.f90:176-200 on the device): adaptive dt kept in
+    // device memory, CalcTimeStep inside stage 1's lifting kernel, optional CUDA-graph replay; returns the dt of every step
+    // (t advances by their sum, added in step order). Bit-identical to CalcTimeStep + TimeStepByLSERKW2 per step.
+    std::vector<double> RunSteps(int nSteps, double t, bool graph = true, bool calcForcingEveryStep = false) {
+        float ms = 0.f;
+        long long launches = 0;
+        ck(dgx_run_steps(h_, nSteps, t, 0.0, 1 | (calcForcingEveryStep ? 2 : 0) | 4 | (graph ? 8 : 0), &ms, &launches));
+        std::vector<double> dts((size_t)(nSteps > 0 ? nSteps : 0));
+        int count = 0;
+        ck(dgx_get_dt_history(h_, nSteps, dts.data(), &count));
+        dts.resize((size_t)(count < nSteps ? count : nSteps));
+        return dts;
+    }
+    // face arrays of the last RHS in the reference layout (parity checks): which = 0 U_master ... 8 gradUz_slave (dgx.h)
+    void GetFaceArray(int which, double* out) { ck(dgx_get_face_array(h_, which, out)); }
 
     long long LaunchCount() const { return dgx_launch_count(h_); }
     dgx_handle* handle() { return h_; }

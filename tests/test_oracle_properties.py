@@ -291,3 +291,62 @@ def test_sponge_source_and_pruett_filter_oracle():
     assert np.allclose(o.array("SpBaseFlow"), U0 + (U - U0) * 0.01 / width, rtol=0, atol=1e-15)
     o.close()
     o2.close()
+
+
+# ---- overintegration of JU_t (dg/overintegration.f90:179-340): properties of the restated step -------------------------------------
+@pytest.mark.parametrize("otype,nunder", [("cutoff", 2), ("conscutoff", 2), ("conscutoff", 3)])
+def test_overintegration_conserves_and_preserves_the_free_stream(otype, nunder):
+    """On a curved periodic mesh: (a) the free stream stays a steady state; (b) the volume integral of U_t (quadrature of
+    J U_t) vanishes: the cut-off filter keeps the constant mode of J U_t, the conservative variant divides by the projected
+    Jacobian and is conservative in the projected sense -- both leave the mean of every conserved variable untouched up to
+    round-off; (c) the filtered U_t has no modal content above NUnder in J U_t (cut-off) / in U_t (conservative)."""
+    import numpy as np
+    from galaexi_b200.host_standin import basis as bs
+    c, U0 = cases.tgv_box_case(E=2, N=4, NGeo=2, deform=0.05, perturb=1e-2, split=None, riemann="Roe", node_type="GAUSS",
+                               OverintegrationType=otype, NUnder=nunder)
+    o = Oracle(c)
+    ref = np.broadcast_to(np.array([1.1, 0.3, -0.2, 0.1, 3.0]), U0.shape).copy()
+    o.set_state(ref)
+    assert np.abs(o.time_derivative(0.0)).max() <= 1e-11
+    o.set_state(U0)
+    Ut = o.time_derivative(0.0).copy()
+    w = c.basis.wGP
+    W = w[:, None, None] * w[None, :, None] * w[None, None, :]
+    J = 1.0 / c.geo["sJ"]
+    scale = np.einsum("ekji,ekjiv->v", W[None] * J, np.abs(Ut))
+    if otype == "cutoff":
+        total = np.einsum("ekji,ekjiv->v", W[None] * J, Ut)
+        assert np.all(np.abs(total) <= 1e-12 * scale), (total, scale)
+    x, _, _ = bs.get_nodes_and_weights(c.N, c.node_type)
+    _, sV = bs.build_legendre_vdm(x)                       # nodal -> modal (Legendre)
+    A = Ut * J[..., None] if otype == "cutoff" else Ut     # the quantity whose high modes the step removes
+    for axis in (1, 2, 3):
+        modal = np.moveaxis(np.tensordot(sV, np.moveaxis(A, axis, 0), axes=(1, 0)), 0, axis)
+        hi = np.take(modal, range(nunder + 1, c.N + 1), axis=axis)
+        assert np.abs(hi).max() <= 1e-10 * np.abs(modal).max(), (otype, axis, np.abs(hi).max())
+    o.close()
+
+
+def test_overintegration_with_nunder_equal_n_is_the_plain_operator():
+    """overintegration.f90:120-131 with NUnder = N: the filter matrix is the identity (up to the round-off of Vdm_Leg sVdm_Leg);
+    the conservative variant is switched off for NUnder >= N (:158-160)."""
+    import numpy as np
+    kw = dict(E=2, N=3, NGeo=2, deform=0.05, perturb=1e-2, split=None, riemann="Roe", node_type="GAUSS")
+    c0, U0 = cases.tgv_box_case(**kw)
+    c1, _ = cases.tgv_box_case(OverintegrationType="cutoff", NUnder=3, **kw)
+    c2, _ = cases.tgv_box_case(OverintegrationType="conscutoff", NUnder=3, **kw)
+    assert c2.OverintegrationType == 0 and c1.OverintegrationType == 1
+    assert np.abs(c1.OverintegrationMat - np.eye(4)).max() <= 1e-13
+    outs = []
+    for c in (c0, c1):
+        o = Oracle(c)
+        o.set_state(U0)
+        outs.append(o.time_derivative(0.0).copy())
+        o.close()
+    assert cases.rel_l2(outs[1], outs[0]) <= 1e-12
+    # the CFL number follows NEff = MIN(N, NFilter, NUnder) and switches to the Gauss table (timedisc_func.f90:171-173, timedisc_vars.f90:196-203)
+    cg, _ = cases.tgv_box_case(E=2, N=5, OverintegrationType="cutoff", NUnder=3)          # Gauss-Lobatto nodes
+    cn, _ = cases.tgv_box_case(E=2, N=5)
+    from galaexi_b200.host_standin import timedisc as td
+    assert abs(cg.timedisc.CFLScale - 0.9 * 1.5401 / 7.0) <= 1e-15 and abs(cn.timedisc.CFLScale - 0.9 * 2.2027 / 11.0) <= 1e-15
+    assert cg.timedisc.DFLScale == cn.timedisc.DFLScale

@@ -75,6 +75,21 @@ def workload_desc(cfg: int, scaling: str, world: int, degree=None, elems=None, c
             f"BC 2 / adiabatic wall 3 / periodic z), fixed total, adaptive dt, CFLscale=DFLscale=0.9")
 
 
+def workload_dofs(cfg: int, scaling: str, world: int, degree=None, elems=None) -> int:
+    """Global number of DOF of the configuration on `world` GPUs (both arms print it in `config`)."""
+    d, _ = workload_dims(cfg, scaling, world, elems)
+    N = degree if degree is not None else {2: 7, 3: 5, 4: 5, 5: 4}[cfg]
+    return (652 if cfg == 5 else d[0] * d[1] * d[2]) * (N + 1) ** 3
+
+
+def l2_policy(state_bytes_per_gpu: float) -> str:
+    """Timing rule: inputs larger than L2, or say that they are not (a property of the workload; both arms print it in `config`)."""
+    mb = state_bytes_per_gpu / 1e6
+    if state_bytes_per_gpu > 2 * 126e6:
+        return f"inputs larger than L2 (state {mb:.0f} MB per GPU vs 126 MB L2), no explicit flush"
+    return f"state {mb:.1f} MB per GPU fits L2: launch-bound configuration, no explicit flush"
+
+
 def make_workload(cfg: int, scaling: str, world: int, rank: int, degree=None, elems=None, curved=False, dims=None):
     """This rank's slice of BASELINE config `cfg` on `world` ranks."""
     from galaexi_b200.host_standin import workloads as wl
@@ -261,7 +276,9 @@ def run_reference(args):
     line = dict(metric="DOF-updates/s", value=value, unit="DOF*stage/s", impl="reference", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * wall / args.steps, higher_is_better=True, scaling=args.scaling, vs_baseline=None,
                 dtype="f64", data="synthetic",
-                config=dict(workload=workload_desc(args.config, args.scaling, args.gpus, args.degree, args.elems, args.curved), rk_stages=NSTAGES),
+                config=dict(workload=workload_desc(args.config, args.scaling, args.gpus, args.degree, args.elems, args.curved), rk_stages=NSTAGES,
+                            dof_global=workload_dofs(args.config, args.scaling, args.gpus, args.degree, args.elems),
+                            l2_policy=l2_policy(40.0 * workload_dofs(args.config, args.scaling, args.gpus, args.degree, args.elems) / args.gpus)),
                 pid_s=wall * cores / (ndof * NSTAGES * args.steps),
                 cpu_baseline=dict(value=value, unit="DOF*stage/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=value, unit="DOF*stage/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
@@ -684,17 +701,16 @@ def main():
             cpu = cpu_baseline(args.config, args.degree)
         n = wl["N"] + 1
         hbm_peak, _ = peaks()
-        big = wl["U0"].nbytes > 2 * 126e6
         line = dict(metric="DOF-updates/s", value=m["value"], unit="DOF*stage/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=m["ms_per_step"], higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f64",
                     data="synthetic", pid_s=m["pid_s"], pid_floor_s=b_alg_stage_fused(n) / (hbm_peak * 1e9),
-                    config=dict(workload=wl["desc"], rk_stages=NSTAGES, dof_global=m["ndof_global"], dof_per_gpu=m["ndof_local"],
-                                l2_policy=(f"inputs larger than L2 (state {wl['U0'].nbytes / 1e6:.0f} MB per GPU vs 126 MB L2), no explicit flush" if big
-                                           else f"state {wl['U0'].nbytes / 1e6:.0f} MB per GPU fits L2: launch-bound configuration, no explicit flush"),
-                                timing="CUDA events on the launching stream around K steps, max over ranks",
-                                parallelism=f"dd{world} (SFC element decomposition, NCCL face halos)",
-                                step_pacing=m["pacing"],
-                                state_check="density > 0, pressure > 0 and a finite time step are checked on the device every step; the run fails otherwise"),
+                    config=dict(workload=wl["desc"], rk_stages=NSTAGES, dof_global=m["ndof_global"],
+                                l2_policy=l2_policy(40.0 * m["ndof_global"] / world)),
+                    measurement=dict(
+                        dof_per_gpu=m["ndof_local"],
+                        timing="CUDA events on the launching stream around K steps, max over ranks",
+                        parallelism=f"dd{world} (SFC element decomposition, NCCL face halos)", step_pacing=m["pacing"],
+                        state_check="density > 0, pressure > 0 and a finite time step are checked on the device every step; the run fails otherwise"),
                     roofline=roof, cpu_baseline=cpu, clocks=m["clocks"], e2e=e2e, gpu_launches=m["launches"], setup_s=m["setup_s"])
         if extras:
             line["extras"] = extras

@@ -25,6 +25,7 @@ def test_reference_arm_prints_the_contract_line():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["sample"]
     assert "workload" in line["config"] and "model" not in line["config"]
+    assert line["config"]["dof_global"] == 32 ** 3 * 512 and line["config"]["rk_stages"] == 5     # the same keys and values the product arm prints
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="needs a machine without a GPU")

@@ -18,6 +18,8 @@ def test_both_arms_print_the_same_workload_string():
     # weak: the box grows with the GPU count; strong: it does not
     assert "64x64x64" in bench.workload_desc(3, "weak", 8) and "64x64x64" in bench.workload_desc(3, "strong", 1)
     assert "32x32x32" in bench.workload_desc(2, "weak", 1) and "64x32x32" in bench.workload_desc(2, "weak", 2)
+    assert bench.workload_dofs(2, "weak", 1) == 32 ** 3 * 512 and bench.workload_dofs(3, "weak", 8) == 64 ** 3 * 216 == bench.workload_dofs(3, "strong", 2)
+    assert bench.workload_dofs(5, "strong", 4) == 652 * 125
     assert "CFLscale=DFLscale=0.8" in bench.workload_desc(2, "weak", 1)      # tgv/split/parameter.ini:62-63 (0.9 is unstable at N=7 GL)
 
 

@@ -17,7 +17,7 @@ import json
 for nm in ("bench_$TAG", "bench_c3_$TAG", "bench_c4_$TAG", "bench_c5_$TAG", "bench_curved_$TAG"):
     try:
         d=json.loads(open("$OUT/%s.json" % nm).read().strip().splitlines()[-1])
-        print(nm, "value %.4e ms/step %.4f pid %.4e" % (d["value"], d["ms_per_step"], d["pid_s"]), d["config"]["step_pacing"], "e2e %.3e" % d["e2e"]["value"], "launches", d["gpu_launches"], d["clocks"])
+        print(nm, "value %.4e ms/step %.4f pid %.4e" % (d["value"], d["ms_per_step"], d["pid_s"]), d["measurement"]["step_pacing"], "e2e %.3e" % d["e2e"]["value"], "launches", d["gpu_launches"], d["clocks"])
         for k,v in d["roofline"]["kernels"].items(): print("    ", k, {a:(round(b,4) if isinstance(b,float) else b) for a,b in v.items() if a in ("ms","hbm_frac","fp64_frac","bound","dram_bytes_per_dof","algorithmic_bytes_per_dof")})
         print("    roof", d["roofline"]["kernel"], d["roofline"]["frac"], "stage", round(d["roofline"]["stage"]["frac"],4), d["roofline"].get("ncu_note"), "cpu", (d["cpu_baseline"] or {}).get("value"))
         if d.get("extras"): print("    extras", json.dumps(d["extras"])[:400])

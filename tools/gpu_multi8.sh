@@ -11,7 +11,7 @@ run() { # name, args, timeout
 import json
 try:
     d=json.loads([l for l in open("$OUT/bench_n${NG}_$1_$TAG.json").read().strip().splitlines() if l.startswith("{")][-1])
-    print("$1: value %.4e ms/step %.4f pid %.4e" % (d["value"], d["ms_per_step"], d["pid_s"]), d["config"]["step_pacing"], {k: round(v,4) for k,v in d["roofline"]["kernel_ms_per_stage"].items()}, "e2e %.3e" % d["e2e"]["value"], "launches", d["gpu_launches"])
+    print("$1: value %.4e ms/step %.4f pid %.4e" % (d["value"], d["ms_per_step"], d["pid_s"]), d["measurement"]["step_pacing"], {k: round(v,4) for k,v in d["roofline"]["kernel_ms_per_stage"].items()}, "e2e %.3e" % d["e2e"]["value"], "launches", d["gpu_launches"])
     p=d.get("parity")
     if p: print("   parity ok", p["ok"], "ut", p["ut_rel_l2"], "u", p["u_rel_l2"], "dt", p["dt_rel"], {k:(v["ut_rel_l2"], v["ok"]) for k,v in p["cases"].items()})
     x=(d.get("extras") or {}).get("config3_weak")

@@ -9,7 +9,7 @@ run() { # name, args
 import json
 try:
     d=json.loads([l for l in open("$OUT/bench_n${NG}_$1_$TAG.json").read().strip().splitlines() if l.startswith("{")][-1])
-    print("$1: value %.4e ms/step %.4f pid %.4e" % (d["value"], d["ms_per_step"], d["pid_s"]), d["config"]["step_pacing"], {k: round(v,4) for k,v in d["roofline"]["kernel_ms_per_stage"].items()}, "launches", d["gpu_launches"])
+    print("$1: value %.4e ms/step %.4f pid %.4e" % (d["value"], d["ms_per_step"], d["pid_s"]), d["measurement"]["step_pacing"], {k: round(v,4) for k,v in d["roofline"]["kernel_ms_per_stage"].items()}, "launches", d["gpu_launches"])
 except Exception as ex:
     print("$1 parse failed", ex); print(open("$OUT/bench_n${NG}_$1_$TAG.err").read()[-500:])
 PY

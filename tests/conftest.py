@@ -29,10 +29,13 @@ def pytest_terminal_summary(terminalreporter):
     import json
     ext = [r for r in parity.UT_LOG if r["used_extended"]]
     terminalreporter.write_line(f"Ut parity: {len(parity.UT_LOG)} comparisons, {len(ext)} used the extended-precision criterion, "
-                                f"worst direct rel-L2 {max(r['err_fp64'] for r in parity.UT_LOG if not r['used_extended'] or True):.3e}")
+                                f"worst rel-L2 among those that met 1e-12 directly {max([r['err_fp64'] for r in parity.UT_LOG if not r['used_extended']] or [0.0]):.3e}")
     for r in ext:
         terminalreporter.write_line(f"  extended: {r['case']}: vs FP64 oracle {r['err_fp64']:.3e}, FP64 round-off floor {r['floor']:.3e}, vs exact {r['err_exact']:.3e}")
     try:
+        import torch
+        if not torch.cuda.is_available():      # the log is evidence of the GPU suite; CPU runs only exercise the checker itself
+            return
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "ut_parity_log.json"), "w") as f:
             json.dump(parity.UT_LOG, f, indent=1)

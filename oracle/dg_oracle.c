@@ -1534,10 +1534,14 @@ int dgo_rhs_phase(dgo *s, int phase)
         flux_mortar_all(s, NV, s->Flux_master, s->Flux_slave, 1);
         surf_int(s, NV, s->Flux_master, s->Flux_slave, s->Ut, 0, 0, 0);
 #pragma omp parallel for schedule(static)
-        for (size_t d = 0; d < s->nDOF; d++) {
+        for (size_t d = 0; d < s->nDOF; d++)
             for (int v = 0; v < NV; v++) s->Ut[NV * d + v] = s->Ut[NV * d + v] * (-1.);
+        /* 14. overintegration (element-local: no halo involved), then / or the Jacobian */
+        if (c->OverintegrationType == 1) filter_array(s, s->Ut, c->OverintegrationMat);
+        if (c->OverintegrationType == 2) { filter_conservative(s, s->Ut); break; }
+#pragma omp parallel for schedule(static)
+        for (size_t d = 0; d < s->nDOF; d++)
             for (int v = 0; v < NV; v++) s->Ut[NV * d + v] = s->Ut[NV * d + v] * c->sJ[d];
-        }
         break;
     default: err = 4;
     }
